@@ -1,0 +1,160 @@
+/*
+ * spmv_b200.h -- thin C-ABI over the hand-written sm_100a SpMV kernels.
+ *
+ * This is the layer the reference's CUDA driver binds instead of launching its own
+ * __global__ kernels.  Each entry point cites the reference interface it replaces
+ * (paths relative to the reference repository):
+ *
+ *   reference main_cuda.cu:135-145   cudaMalloc + cudaMemcpy of row_ptr/col_idx/values
+ *                                    -> spmv_b200_csr_upload / spmv_b200_csr_wrap_device
+ *   reference main_cuda.cu:166,238,317  spmv_csr_{naive,warp,warp_shared_memory}_kernel<<<>>>
+ *       (cuda_libs/csr_matrix_cuda.cuh:26-49)      -> spmv_b200_csr_spmv
+ *   reference main_cuda.cu:183,255,336  cudaMemcpy(y, D2H) after every product
+ *                                    -> spmv_b200_csr_spmv_host (H2D x, product, D2H y)
+ *   reference main_cuda.cu:369-402   per-block cudaMalloc/cudaMemcpy of ELLPACKBlock.JA/AS
+ *                                    -> spmv_b200_hll_upload (one column-major arena)
+ *   reference main_cuda.cu:454,568,637  spmv_hll_{warp_shared_v1,naive,warp}_kernel<<<>>>
+ *       (cuda_libs/hll_matrix.cuh:40-51)           -> spmv_b200_hll_spmv
+ *   reference main_cuda.cu:471,585,653  cudaMemcpy(y, D2H)   -> spmv_b200_hll_spmv_host
+ *
+ * Conventions: plain C types only; every function returns 0 (SPMV_B200_OK) or a negative
+ * status and never calls exit() (the reference aborts through checkCudaErrors,
+ * cuda_libs/helper_cuda.h:582-595); spmv_b200_last_error() returns a per-thread message.
+ * "d_" pointers are device pointers on the CURRENT CUDA device, "stream" is a cudaStream_t
+ * passed as void* (NULL = default stream).  All arithmetic is fp64, indices are int32 as in
+ * the reference (libs/csr_matrix.h:8-16); nnz and slot counts are 64-bit where they may
+ * exceed 2^31 in bytes.  There is no CPU fallback: without a CUDA device every compute entry
+ * point fails with SPMV_B200_ERR_NO_DEVICE.
+ */
+#ifndef SPMV_B200_H
+#define SPMV_B200_H
+
+#include "hll_matrix.h" /* ELLPACKBlock / HLLMatrix / HACK_SIZE (drop-in host structs) */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPMV_B200_OK 0
+#define SPMV_B200_ERR_INVALID (-1)
+#define SPMV_B200_ERR_CUDA (-2)
+#define SPMV_B200_ERR_NO_DEVICE (-3)
+#define SPMV_B200_ERR_NOMEM (-4)
+
+/* CSR kernel selection for spmv_b200_csr_spmv */
+#define SPMV_B200_ALGO_AUTO 0     /* adaptive row-binned tile kernel (+ long-row split)      */
+#define SPMV_B200_ALGO_VECTOR 1   /* plain vector-per-row kernel with shuffle reduction      */
+#define SPMV_B200_ALGO_TILE 2     /* force the tile kernel                                   */
+
+/* synthetic CSR generators (BASELINE.json configs 2, 3, 5) */
+#define SPMV_B200_SYNTH_LAP2D 1   /* p0 = n   : 5-point Laplacian on an n x n grid           */
+#define SPMV_B200_SYNTH_LAP3D 2   /* p0 = n   : 7-point Laplacian on an n^3 grid             */
+#define SPMV_B200_SYNTH_UNIFORM 3 /* p0 = M, p1 = N, p2 = nnz per row (stratified columns)   */
+
+typedef struct spmv_b200_csr spmv_b200_csr; /* opaque: resident CSR matrix + kernel plan    */
+typedef struct spmv_b200_hll spmv_b200_hll; /* opaque: resident column-major HLL image      */
+
+typedef struct {
+    int M, N;
+    long long nnz;
+    int num_tiles;       /* row-binned tiles of the adaptive kernel                          */
+    int num_long_rows;   /* rows split over several CTAs (deterministic two-phase combine)   */
+    int num_fragments;   /* fragments of those rows                                          */
+    int threads_per_row; /* width of the in-tile shuffle reduction (1 = one thread per row)  */
+    int tile_items;      /* D: rows+nnz per tile                                             */
+    int long_threshold;  /* L: rows longer than this are "long"                              */
+    long long algorithmic_bytes; /* nnz*12 + 4*(M+1) + 8*M + 8*N     */
+} spmv_b200_csr_info_t;
+
+typedef struct {
+    int M, N;
+    int num_hacks;          /* = ceil(M/32), reference src/hll_matrix.c:49                   */
+    int max_maxnz;
+    long long slots;        /* sum_b 32*MAXNZ_b (device image: rows padded to 32)            */
+    long long nnz_reference_slots; /* sum_b rows_b*MAXNZ_b (reference host layout)           */
+    long long algorithmic_bytes;   /* slots*12 + 8*(num_hacks+1) + 8*M + 8*N                 */
+} spmv_b200_hll_info_t;
+
+/* ---- library / device ---------------------------------------------------------------- */
+const char *spmv_b200_last_error(void);
+int spmv_b200_version(void);
+int spmv_b200_device_count(int *count);
+/* name[len], sm count, L2 bytes, total global memory of the current device */
+int spmv_b200_device_info(char *name, int len, int *sm_count, long long *l2_bytes, long long *mem_bytes);
+
+/* ---- CSR ----------------------------------------------------------------------------- */
+/* host arrays (reference CSRMatrix fields, libs/csr_matrix.h:8-16) -> resident device copy */
+int spmv_b200_csr_upload(int M, int N, long long nnz, const int *row_ptr, const int *col_idx,
+                         const double *values, spmv_b200_csr **out);
+/* arrays already on the device (not copied, not owned), e.g. the reference driver's own
+ * cudaMalloc'ed d_row_ptr / d_col_idx / d_values (main_cuda.cu:135-145) */
+int spmv_b200_csr_wrap_device(int M, int N, long long nnz, const int *d_row_ptr,
+                              const int *d_col_idx, const double *d_values, void *stream,
+                              spmv_b200_csr **out);
+/* tuning knobs for the plan (0 keeps the default); rebuilds the plan */
+int spmv_b200_csr_replan(spmv_b200_csr *A, int tile_items, int long_threshold, int threads_per_row,
+                         void *stream);
+int spmv_b200_csr_info(const spmv_b200_csr *A, spmv_b200_csr_info_t *info);
+int spmv_b200_csr_device_arrays(const spmv_b200_csr *A, const int **d_row_ptr, const int **d_col_idx,
+                                const double **d_values);
+int spmv_b200_csr_download(const spmv_b200_csr *A, int *row_ptr, int *col_idx, double *values);
+/* y = A x  (accumulate != 0: y += A x, the reference's serial semantics, src/csr_matrix.c:136) */
+int spmv_b200_csr_spmv(const spmv_b200_csr *A, const double *d_x, double *d_y, int accumulate,
+                       int algo, void *stream);
+/* host x[N] -> device, product, device -> host y[M]; synchronous */
+int spmv_b200_csr_spmv_host(spmv_b200_csr *A, const double *x, double *y, int accumulate, int algo);
+/* product restricted to rows [row_begin,row_end) (the reference's per-thread row ranges,
+ * src/csr_matrix.c:294-313); other rows of y are left untouched. Vector kernel. */
+int spmv_b200_csr_spmv_rows(const spmv_b200_csr *A, int row_begin, int row_end, const double *d_x,
+                            double *d_y, void *stream);
+void spmv_b200_csr_free(spmv_b200_csr *A);
+
+/* plan-free launch on raw device arrays: drop-in for
+ * spmv_csr_warp_kernel<<<grid,block>>>(M,row_ptr,col_idx,values,x,y) (main_cuda.cu:238).
+ * threads_per_row in {0 (auto from nnz/M),1,2,4,8,16,32}. */
+int spmv_b200_csr_spmv_raw(int M, long long nnz, const int *d_row_ptr, const int *d_col_idx,
+                           const double *d_values, const double *d_x, double *d_y,
+                           int threads_per_row, void *stream);
+
+/* ---- HLL ----------------------------------------------------------------------------- */
+/* host HLLMatrix exactly as convert_to_hll builds it (row-major blocks, last block short,
+ * NULL arrays for empty blocks; src/hll_matrix.c:37-257) -> column-major device image */
+int spmv_b200_hll_upload(const HLLMatrix *hll, int M, int N, spmv_b200_hll **out);
+/* device-side conversion of a resident CSR matrix whose rows are column-sorted; identical to
+ * convert_to_hll + upload for duplicate-free rows */
+int spmv_b200_hll_from_csr(const spmv_b200_csr *A, void *stream, spmv_b200_hll **out);
+int spmv_b200_hll_info(const spmv_b200_hll *H, spmv_b200_hll_info_t *info);
+/* device image -> freshly malloc'ed host HLLMatrix in the reference layout (free it with
+ * free_hll_matrix); round trip of spmv_b200_hll_upload */
+int spmv_b200_hll_download(const spmv_b200_hll *H, HLLMatrix *out);
+int spmv_b200_hll_spmv(const spmv_b200_hll *H, const double *d_x, double *d_y, void *stream);
+int spmv_b200_hll_spmv_host(spmv_b200_hll *H, const double *x, double *y);
+/* product restricted to hacks [hack_begin,hack_end) (reference per-thread block ranges,
+ * src/hll_matrix.c:376-408) */
+int spmv_b200_hll_spmv_hacks(const spmv_b200_hll *H, int hack_begin, int hack_end, const double *d_x,
+                             double *d_y, void *stream);
+void spmv_b200_hll_free(spmv_b200_hll *H);
+
+/* ---- synthetic matrices generated on the device (rows [row_begin,row_end) of the global
+ * matrix, global column ids, local row_ptr starting at 0); see SURVEY.md section 8(d) ---- */
+int spmv_b200_synth_csr(int kind, long long p0, long long p1, int p2, unsigned long long seed,
+                        long long row_begin, long long row_end, void *stream, spmv_b200_csr **out);
+/* number of nonzeros in rows [0,row) of a synthetic matrix (closed form; no device needed) */
+long long spmv_b200_synth_row_offset(int kind, long long p0, long long p1, int p2, long long row);
+/* x_i = (hash(seed,i) in (0,1]) */
+int spmv_b200_synth_vector(double *d_x, long long n, unsigned long long seed, void *stream);
+
+/* ---- dense vector helpers for the iterated product (power method, BASELINE config 5) ---- */
+int spmv_b200_vec_fill(double *d_v, long long n, double value, void *stream);
+/* *d_out = sum v_i^2, deterministic two-stage tree (independent of n's partition into CTAs
+ * only through a fixed CTA count); d_ws must hold spmv_b200_vec_ws_doubles() doubles */
+int spmv_b200_vec_ws_doubles(void);
+int spmv_b200_vec_sumsq(const double *d_v, long long n, double *d_ws, double *d_out, void *stream);
+/* d_dst[i] = d_src[i] / sqrt(*d_sumsq)   (no host round trip) */
+int spmv_b200_vec_scale_by_inv_norm(double *d_dst, const double *d_src, long long n,
+                                    const double *d_sumsq, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPMV_B200_H */

@@ -1,0 +1,101 @@
+// common.cuh -- shared device helpers and host-side error plumbing for the sm_100a SpMV kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "spmv_b200.h"
+
+namespace spmv {
+
+// ---- per-thread error message (spmv_b200_last_error) -----------------------------------------
+void set_error(const char *fmt, ...);
+int fail(int code, const char *fmt, ...);
+
+#define SPMV_TRY_CUDA(expr)                                                                      \
+    do {                                                                                         \
+        cudaError_t err__ = (expr);                                                              \
+        if (err__ != cudaSuccess) {                                                              \
+            const int code__ = (err__ == cudaErrorNoDevice || err__ == cudaErrorInsufficientDriver) \
+                                   ? SPMV_B200_ERR_NO_DEVICE                                     \
+                                   : (err__ == cudaErrorMemoryAllocation ? SPMV_B200_ERR_NOMEM   \
+                                                                         : SPMV_B200_ERR_CUDA);  \
+            return spmv::fail(code__, "%s: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+        }                                                                                        \
+    } while (0)
+
+#define SPMV_TRY(expr)                   \
+    do {                                 \
+        int rc__ = (expr);               \
+        if (rc__ != SPMV_B200_OK) return rc__; \
+    } while (0)
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline unsigned int blocks_for(long long items, int per_block) {
+    long long b = (items + per_block - 1) / per_block;
+    return static_cast<unsigned int>(b > 0 ? b : 1);
+}
+
+// ---- streaming loads ---------------------------------------------------------------------------
+// The matrix stream (values / column indices / HLL slots) is read exactly once per product: keep
+// it out of L1 (no_allocate) and mark it evict-first in L2 so that x -- the only operand with
+// reuse -- stays resident in the 126 MB L2.  sm_100 adds 256-bit global loads (LDG.E.256); the
+// L2 eviction qualifier is only accepted on that form.
+__device__ __forceinline__ void ldg_stream_f64x4(const double *p, double (&v)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
+                 : "l"(p));
+}
+
+__device__ __forceinline__ int4 ldg_stream_s32x4(const int *p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void ldg_stream_s32x8(const int *p, int (&c)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7])
+                 : "l"(p));
+}
+
+__device__ __forceinline__ double ldg_stream_f64(const double *p) {
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ int ldg_stream_s32(const int *p) {
+    int r;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
+// x is gathered through the read-only path (LDG.CONSTANT), allocating in L1: neighbouring rows of
+// banded matrices hit the same lines.
+__device__ __forceinline__ double ldg_x(const double *x, int col) { return __ldg(x + col); }
+
+// ---- counter-based hash shared by the device generators and their numpy twins -----------------
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+__host__ __device__ __forceinline__ unsigned long long hash3(unsigned long long seed, unsigned long long a,
+                                                             unsigned long long b) {
+    return mix64(seed + a * 0x9E3779B97F4A7C15ULL + b * 0xD1B54A32D192ED03ULL);
+}
+
+// uniform in (0, 1]: 53 random bits
+__host__ __device__ __forceinline__ double unit_interval(unsigned long long h) {
+    return (double)((h >> 11) + 1ULL) * (1.0 / 9007199254740992.0);
+}
+
+}  // namespace spmv

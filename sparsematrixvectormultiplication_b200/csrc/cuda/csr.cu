@@ -1,0 +1,630 @@
+// csr.cu -- CSR y = A*x for sm_100a (B200): kernels, plan builder and the C-ABI entry points.
+//
+// Replaces the reference's spmv_csr_{naive,warp,warp_shared_memory}_kernel
+// (reference cuda_src/csr_matrix_cuda.cu:122-241, launched from main_cuda.cu:166,238,317).
+//
+// Design: SpMV is an HBM-bound gather (0.15 flop/B), so no tensor cores.
+//   * csr_tile_kernel   -- adaptive row-binned "stream" kernel.  Rows are binned at plan time into
+//       tiles of ~D merge items (rows + nonzeros).  A CTA streams its tile's values/columns with
+//       coalesced 256-bit / 128-bit no-allocate, evict-first loads, gathers x through the
+//       read-only path, parks the products in shared memory, then reduces them per row: one thread
+//       per row for short rows (sequential, left-to-right, no FMA contraction => bit-identical to
+//       the reference's serial loop), or 2..32 lanes per row with a shuffle reduction when a tile
+//       holds few, longer rows.
+//   * csr_long_* kernels -- rows longer than L are split into fixed 8192-nonzero fragments, one
+//       CTA each, combined in a fixed order by a second tiny kernel (deterministic, no atomics).
+//   * csr_vector_kernel -- the plain vector-per-row kernel with shuffle reduction; needs no plan,
+//       works on raw device arrays (drop-in for the reference's warp kernel launch).
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+namespace spmv {
+
+constexpr int kTileThreads = 256;
+constexpr int kDefaultTileItems = 3072;     // D: rows + nonzeros per tile
+constexpr int kDefaultLongThreshold = 1024; // L: longer rows leave the tile kernel
+constexpr int kFragNnz = 8192;              // nonzeros per long-row fragment (one CTA)
+constexpr int kFragThreads = 256;
+constexpr int kSmemSlack = 8;
+
+// ================================================================================================
+// kernels
+// ================================================================================================
+
+// Products of one aligned group of four nonzeros.
+__device__ __forceinline__ void group_products(const int *__restrict__ col_idx, const double *__restrict__ values,
+                                               const double *__restrict__ x, int idx, int nnz_total,
+                                               double (&p)[4]) {
+    if (idx + 4 <= nnz_total) {
+        const int4 c = ldg_stream_s32x4(col_idx + idx);
+        double v[4];
+        ldg_stream_f64x4(values + idx, v);
+        p[0] = __dmul_rn(v[0], ldg_x(x, c.x));
+        p[1] = __dmul_rn(v[1], ldg_x(x, c.y));
+        p[2] = __dmul_rn(v[2], ldg_x(x, c.z));
+        p[3] = __dmul_rn(v[3], ldg_x(x, c.w));
+    } else {  // ragged end of the arrays: never read past nnz_total
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = idx + e;
+            p[e] = k < nnz_total ? __dmul_rn(ldg_stream_f64(values + k), ldg_x(x, ldg_stream_s32(col_idx + k))) : 0.0;
+        }
+    }
+}
+
+// tiles[t] = {first row of tile t, row_ptr[first row]}, tiles[num_tiles] = {M, nnz}.
+// forced_tpr: 0 = pick the reduction width per tile from its row count, else 1,2,4,...,32.
+__global__ void __launch_bounds__(kTileThreads, 4)
+csr_tile_kernel(const int2 *__restrict__ tiles, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                const double *__restrict__ values, const double *__restrict__ x, double *__restrict__ y,
+                int nnz_total, int long_threshold, int forced_tpr, int accumulate) {
+    extern __shared__ __align__(32) double prod[];
+    const int tid = threadIdx.x;
+    const int2 head = tiles[blockIdx.x];
+    const int2 tail = tiles[blockIdx.x + 1];
+    const int r0 = head.x, rows = tail.x - head.x;
+    const int n0 = head.y, n1 = tail.y;
+    if (rows == 1 && n1 - n0 > long_threshold) return;  // long row: csr_long_* kernels own it
+
+    // reduction width for this tile (power of two)
+    int tpr = forced_tpr;
+    if (tpr == 0) {
+        tpr = 1;
+        while (tpr < 32 && rows * tpr * 2 <= kTileThreads) tpr *= 2;
+    }
+    const int tpr_log = 31 - __clz(tpr);
+    const int rows_per_pass = kTileThreads >> tpr_log;
+    const int sub = tid & (tpr - 1);
+
+    // row bounds of this thread's first row: issued now, consumed after the barrier
+    int my_row = tid >> tpr_log;
+    int seg_lo = 0, seg_hi = 0;
+    if (my_row < rows) {
+        seg_lo = __ldg(row_ptr + r0 + my_row);
+        seg_hi = __ldg(row_ptr + r0 + my_row + 1);
+    }
+
+    // ---- phase A: stream the tile, park the products ------------------------------------------
+    const int a0 = n0 & ~3;  // 16 B (columns) / 32 B (values) aligned start
+    const int ngroups = (n1 - a0 + 3) >> 2;
+    int g = tid;
+    for (; g + kTileThreads < ngroups; g += 2 * kTileThreads) {  // two groups in flight per thread
+        double p0[4], p1[4];
+        group_products(col_idx, values, x, a0 + 4 * g, nnz_total, p0);
+        group_products(col_idx, values, x, a0 + 4 * (g + kTileThreads), nnz_total, p1);
+        double2 *d0 = reinterpret_cast<double2 *>(prod + 4 * g);
+        double2 *d1 = reinterpret_cast<double2 *>(prod + 4 * (g + kTileThreads));
+        d0[0] = make_double2(p0[0], p0[1]);
+        d0[1] = make_double2(p0[2], p0[3]);
+        d1[0] = make_double2(p1[0], p1[1]);
+        d1[1] = make_double2(p1[2], p1[3]);
+    }
+    if (g < ngroups) {
+        double p0[4];
+        group_products(col_idx, values, x, a0 + 4 * g, nnz_total, p0);
+        double2 *d0 = reinterpret_cast<double2 *>(prod + 4 * g);
+        d0[0] = make_double2(p0[0], p0[1]);
+        d0[1] = make_double2(p0[2], p0[3]);
+    }
+    __syncthreads();
+
+    // ---- phase B: per-row reduction out of shared memory ---------------------------------------
+    if (tpr == 1) {
+        for (; my_row < rows; my_row += kTileThreads) {
+            double acc = accumulate ? y[r0 + my_row] : 0.0;
+            for (int k = seg_lo - a0; k < seg_hi - a0; ++k) acc = __dadd_rn(acc, prod[k]);  // left to right
+            y[r0 + my_row] = acc;
+            const int next = my_row + kTileThreads;
+            if (next < rows) {
+                seg_lo = __ldg(row_ptr + r0 + next);
+                seg_hi = __ldg(row_ptr + r0 + next + 1);
+            }
+        }
+    } else {
+        // all 32 lanes of a warp take part in every shuffle: iterate on a warp-uniform bound
+        for (int base = 0; base < rows; base += rows_per_pass) {
+            const int row = base + (tid >> tpr_log);
+            double acc = 0.0;
+            if (row < rows) {
+                if (base != 0) {
+                    seg_lo = __ldg(row_ptr + r0 + row);
+                    seg_hi = __ldg(row_ptr + r0 + row + 1);
+                }
+                for (int k = seg_lo - a0 + sub; k < seg_hi - a0; k += tpr) acc = __dadd_rn(acc, prod[k]);
+            }
+            for (int off = tpr >> 1; off > 0; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+            if (row < rows && sub == 0) y[r0 + row] = accumulate ? __dadd_rn(y[r0 + row], acc) : acc;
+        }
+    }
+}
+
+// One CTA per fragment of a long row; partial[f] = sum over the fragment (fixed tree).
+__global__ void __launch_bounds__(kFragThreads)
+csr_long_fragment_kernel(const int *__restrict__ long_rows, const int *__restrict__ frag_first, int num_long,
+                         const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                         const double *__restrict__ values, const double *__restrict__ x,
+                         double *__restrict__ partial) {
+    __shared__ double warp_sum[kFragThreads / 32];
+    const int f = blockIdx.x;
+    int lo = 0, hi = num_long;  // last long row whose first fragment is <= f
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(frag_first + mid) <= f) lo = mid; else hi = mid;
+    }
+    const int row = __ldg(long_rows + lo);
+    const long long begin = (long long)__ldg(row_ptr + row) + (long long)(f - __ldg(frag_first + lo)) * kFragNnz;
+    const long long row_end = __ldg(row_ptr + row + 1);
+    const long long end = begin + kFragNnz < row_end ? begin + kFragNnz : row_end;
+    double acc = 0.0;
+    for (long long k = begin + threadIdx.x; k < end; k += kFragThreads)
+        acc = fma(ldg_stream_f64(values + k), ldg_x(x, ldg_stream_s32(col_idx + k)), acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double total = 0.0;
+#pragma unroll
+        for (int w = 0; w < kFragThreads / 32; ++w) total += warp_sum[w];
+        partial[f] = total;
+    }
+}
+
+__global__ void csr_long_combine_kernel(const int *__restrict__ long_rows, const int *__restrict__ frag_first,
+                                        int num_long, const double *__restrict__ partial, double *__restrict__ y,
+                                        int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_long) return;
+    const int row = long_rows[i];
+    double acc = accumulate ? y[row] : 0.0;
+    for (int f = frag_first[i]; f < frag_first[i + 1]; ++f) acc += partial[f];  // fixed order
+    y[row] = acc;
+}
+
+// Plain vector-per-row kernel: VEC lanes per row, lane-strided loop, xor-shuffle reduction.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+csr_vector_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                  const double *__restrict__ values, const double *__restrict__ x, double *__restrict__ y,
+                  int accumulate) {
+    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long row = row_begin + gt / VEC;
+    const int lane = threadIdx.x & (VEC - 1);
+    const bool live = row < row_end;
+    int lo = 0, hi = 0;
+    if (live) {
+        lo = __ldg(row_ptr + row);
+        hi = __ldg(row_ptr + row + 1);
+    }
+    double acc = 0.0;
+    for (int k = lo + lane; k < hi; k += VEC)
+        acc = fma(ldg_stream_f64(values + k), ldg_x(x, ldg_stream_s32(col_idx + k)), acc);
+#pragma unroll
+    for (int off = VEC >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (live && lane == 0) y[row] = accumulate ? y[row] + acc : acc;
+}
+
+// ---- plan construction kernels ------------------------------------------------------------------
+// boundary[r] = 1 when row r opens a tile: first row, a new window of D merge items
+// (row_ptr[r] + r counts the rows and nonzeros that precede row r), or a neighbour of / a long row.
+__global__ void plan_flag_kernel(int M, const int *__restrict__ row_ptr, int tile_items, int long_threshold,
+                                 unsigned char *__restrict__ boundary, unsigned char *__restrict__ is_long) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= M) return;
+    const int a = row_ptr[r], b = row_ptr[r + 1];
+    const bool long_here = b - a > long_threshold;
+    bool open = r == 0 || long_here;
+    if (r > 0) {
+        const int before = row_ptr[r - 1];
+        open = open || (a - before > long_threshold);
+        open = open || ((long long)a + r) / tile_items != ((long long)before + r - 1) / tile_items;
+    }
+    boundary[r] = open ? 1 : 0;
+    is_long[r] = long_here ? 1 : 0;
+}
+
+__global__ void plan_tiles_kernel(int num_tiles, int M, const int *__restrict__ tile_rows,
+                                  const int *__restrict__ row_ptr, int2 *__restrict__ tiles) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > num_tiles) return;
+    const int row = t < num_tiles ? tile_rows[t] : M;
+    tiles[t] = make_int2(row, row_ptr[row]);
+}
+
+__global__ void plan_fragcount_kernel(int num_long, const int *__restrict__ long_rows,
+                                      const int *__restrict__ row_ptr, int *__restrict__ counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > num_long) return;
+    int c = 0;
+    if (i < num_long) {
+        const int row = long_rows[i];
+        c = (row_ptr[row + 1] - row_ptr[row] + kFragNnz - 1) / kFragNnz;
+    }
+    counts[i] = c;  // counts[num_long] = 0 so that the exclusive scan ends with the total
+}
+
+}  // namespace spmv
+
+// ================================================================================================
+// handle
+// ================================================================================================
+struct spmv_b200_csr {
+    int M = 0, N = 0;
+    long long nnz = 0;
+    int *row_ptr = nullptr;
+    int *col_idx = nullptr;
+    double *values = nullptr;
+    bool owns = false;
+    // plan
+    int tile_items = spmv::kDefaultTileItems;
+    int long_threshold = spmv::kDefaultLongThreshold;
+    int forced_tpr = 0;
+    int num_tiles = 0;
+    int2 *tiles = nullptr;
+    int num_long = 0;
+    int *long_rows = nullptr;
+    int *frag_first = nullptr;
+    int num_frag = 0;
+    double *frag_partial = nullptr;
+    // staging vectors of the *_host entry points
+    double *stage_x = nullptr;
+    double *stage_y = nullptr;
+};
+
+namespace spmv {
+
+static void free_plan(spmv_b200_csr *A) {
+    cudaFree(A->tiles);
+    cudaFree(A->long_rows);
+    cudaFree(A->frag_first);
+    cudaFree(A->frag_partial);
+    A->tiles = nullptr;
+    A->long_rows = nullptr;
+    A->frag_first = nullptr;
+    A->frag_partial = nullptr;
+    A->num_tiles = A->num_long = A->num_frag = 0;
+}
+
+static size_t tile_smem_bytes(const spmv_b200_csr *A) {
+    return (size_t)(A->tile_items + A->long_threshold + kSmemSlack) * sizeof(double);
+}
+
+static int build_plan(spmv_b200_csr *A, cudaStream_t stream) {
+    free_plan(A);
+    const int M = A->M;
+    if (M == 0) return SPMV_B200_OK;
+    if (tile_smem_bytes(A) > 200 * 1024) return fail(SPMV_B200_ERR_INVALID, "tile_items + long_threshold too large for shared memory");
+    SPMV_TRY_CUDA(cudaFuncSetAttribute(csr_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tile_smem_bytes(A)));
+    unsigned char *boundary = nullptr, *is_long = nullptr;
+    int *tile_rows = nullptr, *counts = nullptr, *d_selected = nullptr;
+    void *temp = nullptr;
+    int rc = SPMV_B200_OK;
+    auto cleanup = [&]() {
+        cudaFree(boundary);
+        cudaFree(is_long);
+        cudaFree(tile_rows);
+        cudaFree(counts);
+        cudaFree(d_selected);
+        cudaFree(temp);
+    };
+#define PLAN_TRY(expr)                                                                                  \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            rc = fail(e__ == cudaErrorMemoryAllocation ? SPMV_B200_ERR_NOMEM : SPMV_B200_ERR_CUDA,      \
+                      "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);            \
+            cleanup();                                                                                  \
+            free_plan(A);                                                                               \
+            return rc;                                                                                  \
+        }                                                                                               \
+    } while (0)
+
+    // upper bounds that do not need a counting pass
+    const long long max_long = A->nnz / ((long long)A->long_threshold + 1) + 1;
+    const long long max_tiles = (A->nnz + M) / A->tile_items + 2 + 2 * max_long;
+    PLAN_TRY(cudaMalloc(&boundary, (size_t)M));
+    PLAN_TRY(cudaMalloc(&is_long, (size_t)M));
+    PLAN_TRY(cudaMalloc(&tile_rows, (size_t)std::min<long long>(max_tiles, M) * sizeof(int)));
+    PLAN_TRY(cudaMalloc(&A->long_rows, (size_t)std::min<long long>(max_long, M) * sizeof(int)));
+    PLAN_TRY(cudaMalloc(&d_selected, 2 * sizeof(int)));
+    plan_flag_kernel<<<blocks_for(M, 256), 256, 0, stream>>>(M, A->row_ptr, A->tile_items, A->long_threshold,
+                                                             boundary, is_long);
+    PLAN_TRY(cudaGetLastError());
+
+    thrust::counting_iterator<int> row_ids(0);
+    size_t temp_a = 0, temp_b = 0;
+    PLAN_TRY(cub::DeviceSelect::Flagged(nullptr, temp_a, row_ids, boundary, tile_rows, d_selected, M, stream));
+    PLAN_TRY(cub::DeviceSelect::Flagged(nullptr, temp_b, row_ids, is_long, A->long_rows, d_selected + 1, M, stream));
+    size_t temp_bytes = std::max(temp_a, temp_b);
+    PLAN_TRY(cudaMalloc(&temp, temp_bytes ? temp_bytes : 1));
+    PLAN_TRY(cub::DeviceSelect::Flagged(temp, temp_bytes, row_ids, boundary, tile_rows, d_selected, M, stream));
+    PLAN_TRY(cub::DeviceSelect::Flagged(temp, temp_bytes, row_ids, is_long, A->long_rows, d_selected + 1, M, stream));
+    int selected[2] = {0, 0};
+    PLAN_TRY(cudaMemcpyAsync(selected, d_selected, sizeof selected, cudaMemcpyDeviceToHost, stream));
+    PLAN_TRY(cudaStreamSynchronize(stream));
+    A->num_tiles = selected[0];
+    A->num_long = selected[1];
+
+    PLAN_TRY(cudaMalloc(&A->tiles, (size_t)(A->num_tiles + 1) * sizeof(int2)));
+    plan_tiles_kernel<<<blocks_for(A->num_tiles + 1, 256), 256, 0, stream>>>(A->num_tiles, M, tile_rows, A->row_ptr,
+                                                                            A->tiles);
+    PLAN_TRY(cudaGetLastError());
+
+    if (A->num_long > 0) {
+        PLAN_TRY(cudaMalloc(&counts, (size_t)(A->num_long + 1) * sizeof(int)));
+        PLAN_TRY(cudaMalloc(&A->frag_first, (size_t)(A->num_long + 1) * sizeof(int)));
+        plan_fragcount_kernel<<<blocks_for(A->num_long + 1, 256), 256, 0, stream>>>(A->num_long, A->long_rows,
+                                                                                   A->row_ptr, counts);
+        PLAN_TRY(cudaGetLastError());
+        size_t temp_c = 0;
+        PLAN_TRY(cub::DeviceScan::ExclusiveSum(nullptr, temp_c, counts, A->frag_first, A->num_long + 1, stream));
+        if (temp_c > temp_bytes) {
+            cudaFree(temp);
+            temp = nullptr;
+            PLAN_TRY(cudaMalloc(&temp, temp_c));
+            temp_bytes = temp_c;
+        }
+        PLAN_TRY(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, A->frag_first, A->num_long + 1, stream));
+        PLAN_TRY(cudaMemcpyAsync(&A->num_frag, A->frag_first + A->num_long, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        PLAN_TRY(cudaStreamSynchronize(stream));
+        PLAN_TRY(cudaMalloc(&A->frag_partial, (size_t)std::max(A->num_frag, 1) * sizeof(double)));
+    } else {
+        cudaFree(A->long_rows);
+        A->long_rows = nullptr;
+    }
+    PLAN_TRY(cudaStreamSynchronize(stream));
+#undef PLAN_TRY
+    cleanup();
+    return SPMV_B200_OK;
+}
+
+static int pick_vector_width(long long nnz, int M) {
+    const double avg = M > 0 ? (double)nnz / M : 0.0;
+    if (avg <= 2.0) return 1;
+    if (avg <= 4.0) return 2;
+    if (avg <= 8.0) return 4;
+    if (avg <= 16.0) return 8;
+    if (avg <= 32.0) return 16;
+    return 32;
+}
+
+static int launch_vector(int row_begin, int row_end, const int *row_ptr, const int *col_idx, const double *values,
+                         const double *x, double *y, int vec, int accumulate, cudaStream_t stream) {
+    const long long rows = (long long)row_end - row_begin;
+    if (rows <= 0) return SPMV_B200_OK;
+    const unsigned int grid = blocks_for(rows * vec, 256);
+#define VEC_CASE(V)                                                                                              \
+    case V:                                                                                                      \
+        csr_vector_kernel<V><<<grid, 256, 0, stream>>>(row_begin, row_end, row_ptr, col_idx, values, x, y, accumulate); \
+        break;
+    switch (vec) {
+        VEC_CASE(1) VEC_CASE(2) VEC_CASE(4) VEC_CASE(8) VEC_CASE(16) VEC_CASE(32)
+        default:
+            return fail(SPMV_B200_ERR_INVALID, "threads_per_row must be 0,1,2,4,8,16 or 32 (got %d)", vec);
+    }
+#undef VEC_CASE
+    SPMV_TRY_CUDA(cudaGetLastError());
+    return SPMV_B200_OK;
+}
+
+static int launch_tiles(const spmv_b200_csr *A, const double *x, double *y, int accumulate, cudaStream_t stream) {
+    if (A->num_tiles == 0) return SPMV_B200_OK;
+    csr_tile_kernel<<<A->num_tiles, kTileThreads, tile_smem_bytes(A), stream>>>(
+        A->tiles, A->row_ptr, A->col_idx, A->values, x, y, (int)A->nnz, A->long_threshold, A->forced_tpr, accumulate);
+    SPMV_TRY_CUDA(cudaGetLastError());
+    if (A->num_long > 0) {
+        csr_long_fragment_kernel<<<A->num_frag, kFragThreads, 0, stream>>>(A->long_rows, A->frag_first, A->num_long,
+                                                                          A->row_ptr, A->col_idx, A->values, x,
+                                                                          A->frag_partial);
+        SPMV_TRY_CUDA(cudaGetLastError());
+        csr_long_combine_kernel<<<blocks_for(A->num_long, 128), 128, 0, stream>>>(A->long_rows, A->frag_first,
+                                                                                 A->num_long, A->frag_partial, y,
+                                                                                 accumulate);
+        SPMV_TRY_CUDA(cudaGetLastError());
+    }
+    return SPMV_B200_OK;
+}
+
+static int check_device() {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(SPMV_B200_ERR_NO_DEVICE, "no usable CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return SPMV_B200_OK;
+}
+
+}  // namespace spmv
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+using namespace spmv;
+
+extern "C" {
+
+int spmv_b200_csr_upload(int M, int N, long long nnz, const int *row_ptr, const int *col_idx, const double *values,
+                         spmv_b200_csr **out) {
+    if (!out) return fail(SPMV_B200_ERR_INVALID, "csr_upload: out is NULL");
+    *out = nullptr;
+    if (M < 0 || N < 0 || nnz < 0 || nnz > 0x7fffffffLL || !row_ptr || (nnz > 0 && (!col_idx || !values)))
+        return fail(SPMV_B200_ERR_INVALID, "csr_upload: bad arguments (M=%d N=%d nnz=%lld)", M, N, nnz);
+    SPMV_TRY(check_device());
+    spmv_b200_csr *A = new (std::nothrow) spmv_b200_csr();
+    if (!A) return fail(SPMV_B200_ERR_NOMEM, "csr_upload: out of host memory");
+    A->M = M;
+    A->N = N;
+    A->nnz = nnz;
+    A->owns = true;
+    int rc = SPMV_B200_OK;
+    auto bail = [&](cudaError_t e, const char *what) {
+        rc = fail(e == cudaErrorMemoryAllocation ? SPMV_B200_ERR_NOMEM : SPMV_B200_ERR_CUDA, "csr_upload: %s: %s", what,
+                  cudaGetErrorString(e));
+        spmv_b200_csr_free(A);
+        return rc;
+    };
+    cudaError_t e;
+    // pad the element arrays to a multiple of 4 so that aligned vector loads near the end stay in bounds
+    const size_t padded = ((size_t)nnz + 3) & ~(size_t)3;
+    if ((e = cudaMalloc(&A->row_ptr, ((size_t)M + 1) * sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc row_ptr");
+    if ((e = cudaMalloc(&A->col_idx, std::max<size_t>(padded, 4) * sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc col_idx");
+    if ((e = cudaMalloc(&A->values, std::max<size_t>(padded, 4) * sizeof(double))) != cudaSuccess) return bail(e, "cudaMalloc values");
+    if ((e = cudaMemcpy(A->row_ptr, row_ptr, ((size_t)M + 1) * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "H2D row_ptr");
+    if (nnz > 0) {
+        if ((e = cudaMemcpy(A->col_idx, col_idx, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "H2D col_idx");
+        if ((e = cudaMemcpy(A->values, values, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "H2D values");
+    }
+    rc = build_plan(A, nullptr);
+    if (rc != SPMV_B200_OK) {
+        spmv_b200_csr_free(A);
+        return rc;
+    }
+    *out = A;
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_csr_wrap_device(int M, int N, long long nnz, const int *d_row_ptr, const int *d_col_idx,
+                              const double *d_values, void *stream, spmv_b200_csr **out) {
+    if (!out) return fail(SPMV_B200_ERR_INVALID, "csr_wrap_device: out is NULL");
+    *out = nullptr;
+    if (M < 0 || N < 0 || nnz < 0 || nnz > 0x7fffffffLL || !d_row_ptr || (nnz > 0 && (!d_col_idx || !d_values)))
+        return fail(SPMV_B200_ERR_INVALID, "csr_wrap_device: bad arguments (M=%d N=%d nnz=%lld)", M, N, nnz);
+    if ((reinterpret_cast<uintptr_t>(d_col_idx) & 15) || (reinterpret_cast<uintptr_t>(d_values) & 31))
+        return fail(SPMV_B200_ERR_INVALID, "csr_wrap_device: col_idx must be 16-byte and values 32-byte aligned "
+                                           "(cudaMalloc'ed arrays are)");
+    SPMV_TRY(check_device());
+    spmv_b200_csr *A = new (std::nothrow) spmv_b200_csr();
+    if (!A) return fail(SPMV_B200_ERR_NOMEM, "csr_wrap_device: out of host memory");
+    A->M = M;
+    A->N = N;
+    A->nnz = nnz;
+    A->row_ptr = const_cast<int *>(d_row_ptr);
+    A->col_idx = const_cast<int *>(d_col_idx);
+    A->values = const_cast<double *>(d_values);
+    A->owns = false;
+    int rc = build_plan(A, as_stream(stream));
+    if (rc != SPMV_B200_OK) {
+        spmv_b200_csr_free(A);
+        return rc;
+    }
+    *out = A;
+    return SPMV_B200_OK;
+}
+
+// used by synth.cu: adopt freshly generated device arrays
+int spmv_b200_csr_adopt_device_(int M, int N, long long nnz, int *d_row_ptr, int *d_col_idx, double *d_values,
+                                void *stream, spmv_b200_csr **out) {
+    int rc = spmv_b200_csr_wrap_device(M, N, nnz, d_row_ptr, d_col_idx, d_values, stream, out);
+    if (rc == SPMV_B200_OK) (*out)->owns = true;
+    return rc;
+}
+
+int spmv_b200_csr_replan(spmv_b200_csr *A, int tile_items, int long_threshold, int threads_per_row, void *stream) {
+    if (!A) return fail(SPMV_B200_ERR_INVALID, "csr_replan: NULL matrix");
+    if (threads_per_row < 0 || threads_per_row > 32 || (threads_per_row & (threads_per_row - 1)))
+        return fail(SPMV_B200_ERR_INVALID, "csr_replan: threads_per_row must be 0 or a power of two <= 32");
+    if (tile_items < 0 || long_threshold < 0) return fail(SPMV_B200_ERR_INVALID, "csr_replan: negative parameter");
+    if (tile_items > 0) A->tile_items = std::max(tile_items, 64);
+    if (long_threshold > 0) A->long_threshold = long_threshold;
+    A->forced_tpr = threads_per_row;
+    return build_plan(A, as_stream(stream));
+}
+
+int spmv_b200_csr_info(const spmv_b200_csr *A, spmv_b200_csr_info_t *info) {
+    if (!A || !info) return fail(SPMV_B200_ERR_INVALID, "csr_info: NULL argument");
+    info->M = A->M;
+    info->N = A->N;
+    info->nnz = A->nnz;
+    info->num_tiles = A->num_tiles;
+    info->num_long_rows = A->num_long;
+    info->num_fragments = A->num_frag;
+    info->threads_per_row = A->forced_tpr;
+    info->tile_items = A->tile_items;
+    info->long_threshold = A->long_threshold;
+    info->algorithmic_bytes = A->nnz * 12 + 4LL * ((long long)A->M + 1) + 8LL * A->M + 8LL * A->N;
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_csr_device_arrays(const spmv_b200_csr *A, const int **d_row_ptr, const int **d_col_idx,
+                                const double **d_values) {
+    if (!A) return fail(SPMV_B200_ERR_INVALID, "csr_device_arrays: NULL matrix");
+    if (d_row_ptr) *d_row_ptr = A->row_ptr;
+    if (d_col_idx) *d_col_idx = A->col_idx;
+    if (d_values) *d_values = A->values;
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_csr_download(const spmv_b200_csr *A, int *row_ptr, int *col_idx, double *values) {
+    if (!A) return fail(SPMV_B200_ERR_INVALID, "csr_download: NULL matrix");
+    if (row_ptr) SPMV_TRY_CUDA(cudaMemcpy(row_ptr, A->row_ptr, ((size_t)A->M + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+    if (col_idx && A->nnz) SPMV_TRY_CUDA(cudaMemcpy(col_idx, A->col_idx, (size_t)A->nnz * sizeof(int), cudaMemcpyDeviceToHost));
+    if (values && A->nnz) SPMV_TRY_CUDA(cudaMemcpy(values, A->values, (size_t)A->nnz * sizeof(double), cudaMemcpyDeviceToHost));
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_csr_spmv(const spmv_b200_csr *A, const double *d_x, double *d_y, int accumulate, int algo, void *stream) {
+    if (!A || !d_y || (A->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "csr_spmv: NULL argument");
+    if (A->M == 0) return SPMV_B200_OK;
+    switch (algo) {
+        case SPMV_B200_ALGO_AUTO:
+        case SPMV_B200_ALGO_TILE:
+            return launch_tiles(A, d_x, d_y, accumulate, as_stream(stream));
+        case SPMV_B200_ALGO_VECTOR:
+            return launch_vector(0, A->M, A->row_ptr, A->col_idx, A->values, d_x, d_y, pick_vector_width(A->nnz, A->M),
+                                 accumulate, as_stream(stream));
+        default:
+            return fail(SPMV_B200_ERR_INVALID, "csr_spmv: unknown algo %d", algo);
+    }
+}
+
+int spmv_b200_csr_spmv_rows(const spmv_b200_csr *A, int row_begin, int row_end, const double *d_x, double *d_y,
+                            void *stream) {
+    if (!A || !d_y || !d_x) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_rows: NULL argument");
+    if (row_begin < 0 || row_end > A->M || row_begin > row_end)
+        return fail(SPMV_B200_ERR_INVALID, "csr_spmv_rows: range [%d,%d) outside [0,%d)", row_begin, row_end, A->M);
+    return launch_vector(row_begin, row_end, A->row_ptr, A->col_idx, A->values, d_x, d_y,
+                         pick_vector_width(A->nnz, A->M), 0, as_stream(stream));
+}
+
+int spmv_b200_csr_spmv_raw(int M, long long nnz, const int *d_row_ptr, const int *d_col_idx, const double *d_values,
+                           const double *d_x, double *d_y, int threads_per_row, void *stream) {
+    if (M < 0 || nnz < 0 || !d_row_ptr || !d_y) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_raw: bad arguments");
+    const int vec = threads_per_row > 0 ? threads_per_row : pick_vector_width(nnz, M);
+    return launch_vector(0, M, d_row_ptr, d_col_idx, d_values, d_x, d_y, vec, 0, as_stream(stream));
+}
+
+int spmv_b200_csr_spmv_host(spmv_b200_csr *A, const double *x, double *y, int accumulate, int algo) {
+    if (!A || !y || (A->N > 0 && !x)) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_host: NULL argument");
+    if (!A->stage_x) SPMV_TRY_CUDA(cudaMalloc(&A->stage_x, std::max<size_t>(A->N, 1) * sizeof(double)));
+    if (!A->stage_y) SPMV_TRY_CUDA(cudaMalloc(&A->stage_y, std::max<size_t>(A->M, 1) * sizeof(double)));
+    if (A->N) SPMV_TRY_CUDA(cudaMemcpyAsync(A->stage_x, x, (size_t)A->N * sizeof(double), cudaMemcpyHostToDevice, nullptr));
+    if (accumulate && A->M)
+        SPMV_TRY_CUDA(cudaMemcpyAsync(A->stage_y, y, (size_t)A->M * sizeof(double), cudaMemcpyHostToDevice, nullptr));
+    SPMV_TRY(spmv_b200_csr_spmv(A, A->stage_x, A->stage_y, accumulate, algo, nullptr));
+    if (A->M) SPMV_TRY_CUDA(cudaMemcpyAsync(y, A->stage_y, (size_t)A->M * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+    SPMV_TRY_CUDA(cudaStreamSynchronize(nullptr));
+    return SPMV_B200_OK;
+}
+
+void spmv_b200_csr_free(spmv_b200_csr *A) {
+    if (!A) return;
+    free_plan(A);
+    if (A->owns) {
+        cudaFree(A->row_ptr);
+        cudaFree(A->col_idx);
+        cudaFree(A->values);
+    }
+    cudaFree(A->stage_x);
+    cudaFree(A->stage_y);
+    delete A;
+}
+
+}  // extern "C"

@@ -1,0 +1,416 @@
+// hll.cu -- HLL (hacked ELLPACK, hack size 32) y = A*x for sm_100a: device image, slice kernel,
+// conversions and the C-ABI entry points.
+//
+// Replaces the reference's spmv_hll_{naive,warp,warp_shared_v1}_kernel
+// (reference cuda_src/hll_matrix.cu:346-479) and its array-of-structs device layout with one
+// cudaMalloc pair per block (main_cuda.cu:369-402).
+//
+// Device image: one flat arena, hack b occupies slots
+// [hack_off[b], hack_off[b+1]) = 32*MAXNZ_b, COLUMN-MAJOR and hack-aligned:
+//       slot(b, r, j) = hack_off[b] + j*32 + r          r in [0,32), j in [0,MAXNZ_b)
+// Every hack holds 32 rows (the reference's short last block is padded with JA=0 / AS=0 rows), so
+// every slice starts on a 128 B (JA) / 256 B (AS) boundary.  The host HLLMatrix stays in the
+// reference's row-major layout; spmv_b200_hll_download converts back bit-exactly.
+//
+// Slice kernel: one warp per hack.  Lane = (jj, q) with jj = lane/8, q = lane%8 owns rows
+// 4q..4q+3 of column j = 4*i + jj: one 128-bit load brings the 4 column indices, one 256-bit load
+// the 4 values, so a warp consumes 4 whole columns (512 B + 1 KB, fully coalesced) per step.  The
+// four partial sums per row are combined with two xor-shuffles.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace spmv {
+
+constexpr int kHack = HACK_SIZE;
+constexpr int kHllThreads = 256;
+constexpr int kHllWarps = kHllThreads / 32;
+
+__device__ __forceinline__ void hll_step(const int *__restrict__ JA, const double *__restrict__ AS,
+                                         const double *__restrict__ x, long long slot, double (&acc)[4]) {
+    const int4 c = ldg_stream_s32x4(JA + slot);
+    double v[4];
+    ldg_stream_f64x4(AS + slot, v);
+    acc[0] = fma(v[0], ldg_x(x, c.x), acc[0]);
+    acc[1] = fma(v[1], ldg_x(x, c.y), acc[1]);
+    acc[2] = fma(v[2], ldg_x(x, c.z), acc[2]);
+    acc[3] = fma(v[3], ldg_x(x, c.w), acc[3]);
+}
+
+__global__ void __launch_bounds__(kHllThreads)
+hll_slice_kernel(int hack_begin, int hack_end, const long long *__restrict__ hack_off, const int *__restrict__ JA,
+                 const double *__restrict__ AS, const double *__restrict__ x, double *__restrict__ y, int M) {
+    const int hack = hack_begin + blockIdx.x * kHllWarps + (threadIdx.x >> 5);
+    if (hack >= hack_end) return;  // warp-uniform
+    const int lane = threadIdx.x & 31;
+    const int jj = lane >> 3, q = lane & 7;
+    const long long off = __ldg(hack_off + hack);
+    const int width = (int)((__ldg(hack_off + hack + 1) - off) >> 5);
+    const long long base = off + 4 * q;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    int j = jj;
+    for (; j + 4 < width; j += 8) {  // two column groups in flight
+        double a2[4] = {0.0, 0.0, 0.0, 0.0};
+        hll_step(JA, AS, x, base + (long long)j * kHack, acc);
+        hll_step(JA, AS, x, base + (long long)(j + 4) * kHack, a2);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] += a2[e];
+    }
+    if (j < width) hll_step(JA, AS, x, base + (long long)j * kHack, acc);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+        acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+    }
+    if (jj == 0) {
+        const int row = hack * kHack + 4 * q;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (row + e < M) y[row + e] = acc[e];
+    }
+}
+
+// ---- CSR -> HLL on the device ----------------------------------------------------------------------
+__global__ void hll_width_kernel(int M, int num_hacks, const int *__restrict__ row_ptr, long long *__restrict__ slots,
+                                 int *__restrict__ widths) {
+    const int hack = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (hack > num_hacks) return;
+    const int lane = threadIdx.x & 31;
+    int len = 0;
+    if (hack < num_hacks) {
+        const long long r = (long long)hack * kHack + lane;
+        if (r < M) len = row_ptr[r + 1] - row_ptr[r];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, off));
+    if (lane == 0) {
+        slots[hack] = (long long)len * kHack;  // slots[num_hacks] = 0: the scan ends with the total
+        if (hack < num_hacks) widths[hack] = len;
+    }
+}
+
+__global__ void hll_fill_kernel(int M, int num_hacks, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                                const double *__restrict__ values, const long long *__restrict__ hack_off,
+                                int *__restrict__ JA, double *__restrict__ AS) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= (long long)num_hacks * kHack) return;
+    const int hack = (int)(r / kHack), lr = (int)(r % kHack);
+    const long long off = hack_off[hack];
+    const int width = (int)((hack_off[hack + 1] - off) >> 5);
+    int begin = 0, len = 0;
+    if (r < M) {
+        begin = row_ptr[r];
+        len = row_ptr[r + 1] - begin;
+    }
+    int pad_col = 0;  // reference: padding repeats the last real column, 0 for an empty row
+    for (int j = 0; j < width; ++j) {
+        const long long slot = off + (long long)j * kHack + lr;
+        if (j < len) {
+            pad_col = col_idx[begin + j];
+            JA[slot] = pad_col;
+            AS[slot] = values[begin + j];
+        } else {
+            JA[slot] = pad_col;
+            AS[slot] = 0.0;
+        }
+    }
+}
+
+__global__ void max_int_kernel(const int *__restrict__ v, int n, int *__restrict__ out) {
+    int m = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, v[i]);
+    atomicMax(out, m);  // integer max: order independent
+}
+
+}  // namespace spmv
+
+struct spmv_b200_hll {
+    int M = 0, N = 0, num_hacks = 0, max_width = 0;
+    long long slots = 0, ref_slots = 0;
+    long long *hack_off = nullptr;  // device [num_hacks+1]
+    int *JA = nullptr;              // device [slots]
+    double *AS = nullptr;           // device [slots]
+    std::vector<long long> host_off;
+    double *stage_x = nullptr;
+    double *stage_y = nullptr;
+};
+
+// csr.cu
+extern "C" int spmv_b200_csr_device_arrays(const spmv_b200_csr *A, const int **d_row_ptr, const int **d_col_idx,
+                                           const double **d_values);
+extern "C" int spmv_b200_csr_info(const spmv_b200_csr *A, spmv_b200_csr_info_t *info);
+
+using namespace spmv;
+
+static int hll_launch(const spmv_b200_hll *H, int hack_begin, int hack_end, const double *d_x, double *d_y,
+                      cudaStream_t stream) {
+    if (hack_end <= hack_begin) return SPMV_B200_OK;
+    hll_slice_kernel<<<blocks_for(hack_end - hack_begin, kHllWarps), kHllThreads, 0, stream>>>(
+        hack_begin, hack_end, H->hack_off, H->JA, H->AS, d_x, d_y, H->M);
+    SPMV_TRY_CUDA(cudaGetLastError());
+    return SPMV_B200_OK;
+}
+
+static int hll_alloc_arena(spmv_b200_hll *H) {
+    const size_t n = (size_t)std::max<long long>(H->slots, 32);
+    SPMV_TRY_CUDA(cudaMalloc(&H->JA, n * sizeof(int)));
+    SPMV_TRY_CUDA(cudaMalloc(&H->AS, n * sizeof(double)));
+    return SPMV_B200_OK;
+}
+
+extern "C" {
+
+int spmv_b200_hll_upload(const HLLMatrix *hll, int M, int N, spmv_b200_hll **out) {
+    if (!out) return fail(SPMV_B200_ERR_INVALID, "hll_upload: out is NULL");
+    *out = nullptr;
+    if (!hll || hll->num_blocks < 0 || (hll->num_blocks > 0 && !hll->blocks) || M < 0 || N < 0)
+        return fail(SPMV_B200_ERR_INVALID, "hll_upload: bad arguments");
+    const int nb = hll->num_blocks;
+    if (nb != (M + kHack - 1) / kHack) return fail(SPMV_B200_ERR_INVALID, "hll_upload: %d blocks do not cover %d rows", nb, M);
+    std::vector<long long> off((size_t)nb + 1, 0);
+    long long ref_slots = 0;
+    int max_w = 0;
+    for (int b = 0; b < nb; ++b) {
+        const ELLPACKBlock &blk = hll->blocks[b];
+        const int expect = (b == nb - 1) ? M - b * kHack : kHack;
+        if (blk.M != expect || blk.MAXNZ < 0 || (blk.MAXNZ > 0 && (!blk.JA || !blk.AS)))
+            return fail(SPMV_B200_ERR_INVALID, "hll_upload: block %d is malformed (M=%d, expected %d, MAXNZ=%d)", b, blk.M,
+                        expect, blk.MAXNZ);
+        off[b + 1] = off[b] + (long long)blk.MAXNZ * kHack;
+        ref_slots += (long long)blk.MAXNZ * blk.M;
+        max_w = std::max(max_w, blk.MAXNZ);
+    }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return fail(SPMV_B200_ERR_NO_DEVICE, "hll_upload: no usable CUDA device; this library has no CPU fallback");
+    spmv_b200_hll *H = new (std::nothrow) spmv_b200_hll();
+    if (!H) return fail(SPMV_B200_ERR_NOMEM, "hll_upload: out of host memory");
+    H->M = M;
+    H->N = N;
+    H->num_hacks = nb;
+    H->max_width = max_w;
+    H->slots = off[nb];
+    H->ref_slots = ref_slots;
+    H->host_off = off;
+    // row-major host blocks -> column-major, 32-row padded staging image
+    const size_t n = (size_t)std::max<long long>(H->slots, 1);
+    int *ja = static_cast<int *>(std::calloc(n, sizeof(int)));
+    double *as = static_cast<double *>(std::calloc(n, sizeof(double)));
+    int rc = (ja && as) ? SPMV_B200_OK : fail(SPMV_B200_ERR_NOMEM, "hll_upload: out of host memory");
+    if (rc == SPMV_B200_OK) {
+#pragma omp parallel for schedule(dynamic, 256)
+        for (int b = 0; b < nb; ++b) {
+            const ELLPACKBlock &blk = hll->blocks[b];
+            const int w = blk.MAXNZ;
+            for (int r = 0; r < blk.M; ++r)
+                for (int j = 0; j < w; ++j) {
+                    ja[off[b] + (long long)j * kHack + r] = blk.JA[(size_t)r * w + j];
+                    as[off[b] + (long long)j * kHack + r] = blk.AS[(size_t)r * w + j];
+                }
+        }
+        auto dev = [&]() -> int {
+            SPMV_TRY_CUDA(cudaMalloc(&H->hack_off, ((size_t)nb + 1) * sizeof(long long)));
+            SPMV_TRY(hll_alloc_arena(H));
+            SPMV_TRY_CUDA(cudaMemcpy(H->hack_off, off.data(), ((size_t)nb + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+            if (H->slots) {
+                SPMV_TRY_CUDA(cudaMemcpy(H->JA, ja, (size_t)H->slots * sizeof(int), cudaMemcpyHostToDevice));
+                SPMV_TRY_CUDA(cudaMemcpy(H->AS, as, (size_t)H->slots * sizeof(double), cudaMemcpyHostToDevice));
+            }
+            return SPMV_B200_OK;
+        };
+        rc = dev();
+    }
+    std::free(ja);
+    std::free(as);
+    if (rc != SPMV_B200_OK) {
+        spmv_b200_hll_free(H);
+        return rc;
+    }
+    *out = H;
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_hll_from_csr(const spmv_b200_csr *A, void *stream_, spmv_b200_hll **out) {
+    if (!out) return fail(SPMV_B200_ERR_INVALID, "hll_from_csr: out is NULL");
+    *out = nullptr;
+    if (!A) return fail(SPMV_B200_ERR_INVALID, "hll_from_csr: NULL matrix");
+    cudaStream_t stream = as_stream(stream_);
+    spmv_b200_csr_info_t ci;
+    const int *row_ptr, *col_idx;
+    const double *values;
+    SPMV_TRY(spmv_b200_csr_info(A, &ci));
+    SPMV_TRY(spmv_b200_csr_device_arrays(A, &row_ptr, &col_idx, &values));
+    spmv_b200_hll *H = new (std::nothrow) spmv_b200_hll();
+    if (!H) return fail(SPMV_B200_ERR_NOMEM, "hll_from_csr: out of host memory");
+    H->M = ci.M;
+    H->N = ci.N;
+    const int nb = H->num_hacks = (ci.M + kHack - 1) / kHack;
+    long long *slots = nullptr;
+    int *widths = nullptr, *d_max = nullptr;
+    void *temp = nullptr;
+    auto body = [&]() -> int {
+        SPMV_TRY_CUDA(cudaMalloc(&H->hack_off, ((size_t)nb + 1) * sizeof(long long)));
+        SPMV_TRY_CUDA(cudaMalloc(&slots, ((size_t)nb + 1) * sizeof(long long)));
+        SPMV_TRY_CUDA(cudaMalloc(&widths, (size_t)std::max(nb, 1) * sizeof(int)));
+        SPMV_TRY_CUDA(cudaMalloc(&d_max, sizeof(int)));
+        SPMV_TRY_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), stream));
+        hll_width_kernel<<<blocks_for(nb + 1, 8), 256, 0, stream>>>(ci.M, nb, row_ptr, slots, widths);
+        SPMV_TRY_CUDA(cudaGetLastError());
+        size_t temp_bytes = 0;
+        SPMV_TRY_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, slots, H->hack_off, nb + 1, stream));
+        SPMV_TRY_CUDA(cudaMalloc(&temp, temp_bytes ? temp_bytes : 1));
+        SPMV_TRY_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, slots, H->hack_off, nb + 1, stream));
+        if (nb > 0) {
+            max_int_kernel<<<std::min(blocks_for(nb, 256), 1024u), 256, 0, stream>>>(widths, nb, d_max);
+            SPMV_TRY_CUDA(cudaGetLastError());
+        }
+        H->host_off.resize((size_t)nb + 1);
+        SPMV_TRY_CUDA(cudaMemcpyAsync(H->host_off.data(), H->hack_off, ((size_t)nb + 1) * sizeof(long long),
+                                      cudaMemcpyDeviceToHost, stream));
+        SPMV_TRY_CUDA(cudaMemcpyAsync(&H->max_width, d_max, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        SPMV_TRY_CUDA(cudaStreamSynchronize(stream));
+        H->slots = H->host_off[nb];
+        // reference layout keeps the last block short: its padded rows do not exist there
+        const int last_rows = nb > 0 ? ci.M - (nb - 1) * kHack : 0;
+        H->ref_slots = H->slots;
+        if (nb > 0) H->ref_slots -= ((H->host_off[nb] - H->host_off[nb - 1]) / kHack) * (kHack - last_rows);
+        SPMV_TRY(hll_alloc_arena(H));
+        if (nb > 0) {
+            hll_fill_kernel<<<blocks_for((long long)nb * kHack, 256), 256, 0, stream>>>(ci.M, nb, row_ptr, col_idx, values,
+                                                                                       H->hack_off, H->JA, H->AS);
+            SPMV_TRY_CUDA(cudaGetLastError());
+        }
+        SPMV_TRY_CUDA(cudaStreamSynchronize(stream));
+        return SPMV_B200_OK;
+    };
+    int rc = body();
+    cudaFree(slots);
+    cudaFree(widths);
+    cudaFree(d_max);
+    cudaFree(temp);
+    if (rc != SPMV_B200_OK) {
+        spmv_b200_hll_free(H);
+        return rc;
+    }
+    *out = H;
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_hll_info(const spmv_b200_hll *H, spmv_b200_hll_info_t *info) {
+    if (!H || !info) return fail(SPMV_B200_ERR_INVALID, "hll_info: NULL argument");
+    info->M = H->M;
+    info->N = H->N;
+    info->num_hacks = H->num_hacks;
+    info->max_maxnz = H->max_width;
+    info->slots = H->slots;
+    info->nnz_reference_slots = H->ref_slots;
+    info->algorithmic_bytes = H->slots * 12 + 8LL * ((long long)H->num_hacks + 1) + 8LL * H->M + 8LL * H->N;
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_hll_download(const spmv_b200_hll *H, HLLMatrix *out) {
+    if (!H || !out) return fail(SPMV_B200_ERR_INVALID, "hll_download: NULL argument");
+    const int nb = H->num_hacks;
+    out->num_blocks = nb;
+    out->blocks = static_cast<ELLPACKBlock *>(std::calloc((size_t)std::max(nb, 1), sizeof(ELLPACKBlock)));
+    const size_t n = (size_t)std::max<long long>(H->slots, 1);
+    int *ja = static_cast<int *>(std::malloc(n * sizeof(int)));
+    double *as = static_cast<double *>(std::malloc(n * sizeof(double)));
+    if (!out->blocks || !ja || !as) {
+        std::free(ja);
+        std::free(as);
+        std::free(out->blocks);
+        out->blocks = nullptr;
+        out->num_blocks = 0;
+        return fail(SPMV_B200_ERR_NOMEM, "hll_download: out of host memory");
+    }
+    if (H->slots) {
+        cudaError_t e1 = cudaMemcpy(ja, H->JA, (size_t)H->slots * sizeof(int), cudaMemcpyDeviceToHost);
+        cudaError_t e2 = cudaMemcpy(as, H->AS, (size_t)H->slots * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+            std::free(ja);
+            std::free(as);
+            std::free(out->blocks);
+            out->blocks = nullptr;
+            out->num_blocks = 0;
+            return fail(SPMV_B200_ERR_CUDA, "hll_download: D2H copy failed");
+        }
+    }
+    bool oom = false;
+    for (int b = 0; b < nb; ++b) {
+        ELLPACKBlock &blk = out->blocks[b];
+        const int w = (int)((H->host_off[b + 1] - H->host_off[b]) / kHack);
+        blk.M = (b == nb - 1) ? H->M - b * kHack : kHack;
+        blk.N = H->N;
+        blk.MAXNZ = w;
+        blk.JA = nullptr;
+        blk.AS = nullptr;
+        if (w == 0) continue;
+        blk.JA = static_cast<int *>(std::malloc((size_t)w * blk.M * sizeof(int)));
+        blk.AS = static_cast<double *>(std::malloc((size_t)w * blk.M * sizeof(double)));
+        if (!blk.JA || !blk.AS) {
+            oom = true;
+            break;
+        }
+        for (int r = 0; r < blk.M; ++r)
+            for (int j = 0; j < w; ++j) {
+                blk.JA[(size_t)r * w + j] = ja[H->host_off[b] + (long long)j * kHack + r];
+                blk.AS[(size_t)r * w + j] = as[H->host_off[b] + (long long)j * kHack + r];
+            }
+    }
+    std::free(ja);
+    std::free(as);
+    if (oom) {
+        for (int b = 0; b < nb; ++b) {
+            std::free(out->blocks[b].JA);
+            std::free(out->blocks[b].AS);
+        }
+        std::free(out->blocks);
+        out->blocks = nullptr;
+        out->num_blocks = 0;
+        return fail(SPMV_B200_ERR_NOMEM, "hll_download: out of host memory");
+    }
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_hll_spmv(const spmv_b200_hll *H, const double *d_x, double *d_y, void *stream) {
+    if (!H || !d_y || (H->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "hll_spmv: NULL argument");
+    return hll_launch(H, 0, H->num_hacks, d_x, d_y, as_stream(stream));
+}
+
+int spmv_b200_hll_spmv_hacks(const spmv_b200_hll *H, int hack_begin, int hack_end, const double *d_x, double *d_y,
+                             void *stream) {
+    if (!H || !d_y || !d_x) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_hacks: NULL argument");
+    if (hack_begin < 0 || hack_end > H->num_hacks || hack_begin > hack_end)
+        return fail(SPMV_B200_ERR_INVALID, "hll_spmv_hacks: range [%d,%d) outside [0,%d)", hack_begin, hack_end, H->num_hacks);
+    return hll_launch(H, hack_begin, hack_end, d_x, d_y, as_stream(stream));
+}
+
+int spmv_b200_hll_spmv_host(spmv_b200_hll *H, const double *x, double *y) {
+    if (!H || !y || (H->N > 0 && !x)) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_host: NULL argument");
+    if (!H->stage_x) SPMV_TRY_CUDA(cudaMalloc(&H->stage_x, std::max<size_t>(H->N, 1) * sizeof(double)));
+    if (!H->stage_y) SPMV_TRY_CUDA(cudaMalloc(&H->stage_y, std::max<size_t>(H->M, 1) * sizeof(double)));
+    if (H->N) SPMV_TRY_CUDA(cudaMemcpyAsync(H->stage_x, x, (size_t)H->N * sizeof(double), cudaMemcpyHostToDevice, nullptr));
+    SPMV_TRY(hll_launch(H, 0, H->num_hacks, H->stage_x, H->stage_y, nullptr));
+    if (H->M) SPMV_TRY_CUDA(cudaMemcpyAsync(y, H->stage_y, (size_t)H->M * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+    SPMV_TRY_CUDA(cudaStreamSynchronize(nullptr));
+    return SPMV_B200_OK;
+}
+
+void spmv_b200_hll_free(spmv_b200_hll *H) {
+    if (!H) return;
+    cudaFree(H->hack_off);
+    cudaFree(H->JA);
+    cudaFree(H->AS);
+    cudaFree(H->stage_x);
+    cudaFree(H->stage_y);
+    delete H;
+}
+
+}  // extern "C"

@@ -1,0 +1,307 @@
+// synth.cu -- device-side generators for the BASELINE.json synthetic matrices (SURVEY.md section
+// 8(d): C2 2-D 5-point Laplacian, C3 uniform 32 nnz/row with stratified columns, C5 3-D 7-point
+// Laplacian), the dense-vector helpers of the iterated product, and the library bookkeeping
+// (last error, device queries).  The reference has no generator for these shapes (its
+// src/matrix_generator.py writes 10x10 files); the numpy twins in
+// sparsematrixvectormultiplication_b200/synth.py produce bit-identical arrays on the CPU so the
+// oracle can check the GPU results.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+
+// csr.cu
+extern "C" int spmv_b200_csr_adopt_device_(int M, int N, long long nnz, int *d_row_ptr, int *d_col_idx,
+                                           double *d_values, void *stream, spmv_b200_csr **out);
+
+namespace spmv {
+
+// ---- error plumbing -----------------------------------------------------------------------------
+static thread_local char g_error[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+}
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+// ---- closed-form row offsets -------------------------------------------------------------------
+// Number of nonzeros in rows [0, r) of the n x n 5-point Laplacian (row r = i*n + j).
+__host__ __device__ inline long long lap2d_offset(long long n, long long r) {
+    const long long top = r < n ? r : n;                              // rows with i == 0
+    const long long bottom = r > (n - 1) * n ? r - (n - 1) * n : 0;   // rows with i == n-1
+    const long long left = (r + n - 1) / n;                           // rows with j == 0
+    const long long right = r / n;                                    // rows with j == n-1
+    return 5 * r - top - bottom - left - right;
+}
+
+// Rows [0, r) of the n^3 7-point Laplacian (row r = (i*n + j)*n + k).
+__host__ __device__ inline long long lap3d_offset(long long n, long long r) {
+    const long long n2 = n * n;
+    const long long i = r / n2, j = (r / n) % n, k = r % n;
+    const long long i_lo = r < n2 ? r : n2;
+    const long long i_hi = r > (n - 1) * n2 ? r - (n - 1) * n2 : 0;
+    const long long j_lo = i * n + (j > 0 ? n : k);
+    const long long j_hi = i * n + (j == n - 1 ? k : 0);
+    const long long k_lo = (r + n - 1) / n;
+    const long long k_hi = r / n;
+    return 7 * r - i_lo - i_hi - j_lo - j_hi - k_lo - k_hi;
+}
+
+__host__ __device__ inline long long synth_offset(int kind, long long p0, int p2, long long r) {
+    switch (kind) {
+        case SPMV_B200_SYNTH_LAP2D: return lap2d_offset(p0, r);
+        case SPMV_B200_SYNTH_LAP3D: return lap3d_offset(p0, r);
+        default: return (long long)p2 * r;
+    }
+}
+
+// ---- fill kernels ------------------------------------------------------------------------------
+__global__ void lap2d_fill_kernel(long long n, long long row_begin, long long rows, int *__restrict__ row_ptr,
+                                  int *__restrict__ col_idx, double *__restrict__ values) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > rows) return;
+    const long long r = row_begin + t;
+    const long long base = lap2d_offset(n, row_begin);
+    long long o = lap2d_offset(n, r) - base;
+    row_ptr[t] = (int)o;
+    if (t == rows) return;
+    const long long i = r / n, j = r % n;
+    if (i > 0) { col_idx[o] = (int)(r - n); values[o++] = -1.0; }
+    if (j > 0) { col_idx[o] = (int)(r - 1); values[o++] = -1.0; }
+    col_idx[o] = (int)r; values[o++] = 4.0;
+    if (j < n - 1) { col_idx[o] = (int)(r + 1); values[o++] = -1.0; }
+    if (i < n - 1) { col_idx[o] = (int)(r + n); values[o++] = -1.0; }
+}
+
+__global__ void lap3d_fill_kernel(long long n, long long row_begin, long long rows, int *__restrict__ row_ptr,
+                                  int *__restrict__ col_idx, double *__restrict__ values) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > rows) return;
+    const long long r = row_begin + t;
+    const long long base = lap3d_offset(n, row_begin);
+    long long o = lap3d_offset(n, r) - base;
+    row_ptr[t] = (int)o;
+    if (t == rows) return;
+    const long long n2 = n * n;
+    const long long i = r / n2, j = (r / n) % n, k = r % n;
+    if (i > 0) { col_idx[o] = (int)(r - n2); values[o++] = -1.0; }
+    if (j > 0) { col_idx[o] = (int)(r - n); values[o++] = -1.0; }
+    if (k > 0) { col_idx[o] = (int)(r - 1); values[o++] = -1.0; }
+    col_idx[o] = (int)r; values[o++] = 6.0;
+    if (k < n - 1) { col_idx[o] = (int)(r + 1); values[o++] = -1.0; }
+    if (j < n - 1) { col_idx[o] = (int)(r + n); values[o++] = -1.0; }
+    if (i < n - 1) { col_idx[o] = (int)(r + n2); values[o++] = -1.0; }
+}
+
+// Exactly k nonzeros per row; column of entry e lies in stratum e: e*stride + hash % stride, so a
+// row is sorted and duplicate free by construction.  One thread per entry (coalesced stores).
+__global__ void uniform_fill_kernel(long long row_begin, long long rows, long long ncols, int k,
+                                    unsigned long long seed, int *__restrict__ row_ptr, int *__restrict__ col_idx,
+                                    double *__restrict__ values) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t <= rows) row_ptr[t] = (int)(t * k);
+    if (t >= rows * k) return;
+    const unsigned long long r = (unsigned long long)(row_begin + t / k), e = (unsigned long long)(t % k);
+    const unsigned long long stride = (unsigned long long)(ncols / k);
+    col_idx[t] = (int)(e * stride + hash3(seed, r, e) % stride);
+    values[t] = unit_interval(hash3(seed + 0x5851F42D4C957F2DULL, r, e));
+}
+
+__global__ void vector_hash_kernel(double *__restrict__ x, long long n, unsigned long long seed) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = unit_interval(hash3(seed, (unsigned long long)i, 0x7Eull));
+}
+
+__global__ void vector_fill_kernel(double *__restrict__ v, long long n, double value) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = value;
+}
+
+// ---- deterministic sum of squares ----------------------------------------------------------------
+constexpr int kSumsqCtas = 1184;  // 148 SMs x 8
+constexpr int kSumsqThreads = 256;
+
+__device__ __forceinline__ double block_sum(double v, double *scratch) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double total = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) total += scratch[w];
+    return total;  // valid in thread 0
+}
+
+__global__ void __launch_bounds__(kSumsqThreads) sumsq_stage1_kernel(const double *__restrict__ v, long long n,
+                                                                     double *__restrict__ ws) {
+    __shared__ double scratch[kSumsqThreads / 32];
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * kSumsqThreads + threadIdx.x; i < n; i += (long long)kSumsqCtas * kSumsqThreads) {
+        const double a = v[i];
+        acc = fma(a, a, acc);
+    }
+    const double total = block_sum(acc, scratch);
+    if (threadIdx.x == 0) ws[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kSumsqThreads) sumsq_stage2_kernel(const double *__restrict__ ws, double *__restrict__ out) {
+    __shared__ double scratch[kSumsqThreads / 32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < kSumsqCtas; i += kSumsqThreads) acc += ws[i];
+    const double total = block_sum(acc, scratch);
+    if (threadIdx.x == 0) *out = total;
+}
+
+__global__ void scale_by_inv_norm_kernel(double *__restrict__ dst, const double *__restrict__ src, long long n,
+                                         const double *__restrict__ sumsq) {
+    const double norm = sqrt(*sumsq);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i] / norm;
+}
+
+}  // namespace spmv
+
+using namespace spmv;
+
+extern "C" {
+
+const char *spmv_b200_last_error(void) { return g_error; }
+
+int spmv_b200_version(void) { return 100; }
+
+int spmv_b200_device_count(int *count) {
+    if (!count) return fail(SPMV_B200_ERR_INVALID, "device_count: NULL argument");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(SPMV_B200_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_device_info(char *name, int len, int *sm_count, long long *l2_bytes, long long *mem_bytes) {
+    int dev = 0;
+    SPMV_TRY_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    SPMV_TRY_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (name && len > 0) {
+        strncpy(name, prop.name, (size_t)len - 1);
+        name[len - 1] = '\0';
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (l2_bytes) *l2_bytes = prop.l2CacheSize;
+    if (mem_bytes) *mem_bytes = (long long)prop.totalGlobalMem;
+    return SPMV_B200_OK;
+}
+
+long long spmv_b200_synth_row_offset(int kind, long long p0, long long p1, int p2, long long row) {
+    (void)p1;
+    return synth_offset(kind, p0, p2, row);
+}
+
+int spmv_b200_synth_csr(int kind, long long p0, long long p1, int p2, unsigned long long seed, long long row_begin,
+                        long long row_end, void *stream_, spmv_b200_csr **out) {
+    if (!out) return fail(SPMV_B200_ERR_INVALID, "synth_csr: out is NULL");
+    *out = nullptr;
+    long long M_global, N_global;
+    switch (kind) {
+        case SPMV_B200_SYNTH_LAP2D: M_global = N_global = p0 * p0; break;
+        case SPMV_B200_SYNTH_LAP3D: M_global = N_global = p0 * p0 * p0; break;
+        case SPMV_B200_SYNTH_UNIFORM:
+            M_global = p0;
+            N_global = p1;
+            if (p2 <= 0 || p1 < p2) return fail(SPMV_B200_ERR_INVALID, "synth_csr: uniform needs 0 < nnz_per_row <= N");
+            break;
+        default: return fail(SPMV_B200_ERR_INVALID, "synth_csr: unknown kind %d", kind);
+    }
+    if (p0 <= 0 || M_global > 0x7fffffffLL || N_global > 0x7fffffffLL)
+        return fail(SPMV_B200_ERR_INVALID, "synth_csr: dimensions out of int32 range");
+    if (row_begin < 0 || row_end > M_global || row_begin > row_end)
+        return fail(SPMV_B200_ERR_INVALID, "synth_csr: row range [%lld,%lld) outside [0,%lld)", row_begin, row_end, M_global);
+    const long long rows = row_end - row_begin;
+    const long long nnz = synth_offset(kind, p0, p2, row_end) - synth_offset(kind, p0, p2, row_begin);
+    if (nnz > 0x7fffffffLL) return fail(SPMV_B200_ERR_INVALID, "synth_csr: %lld nonzeros exceed int32 indexing", nnz);
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return fail(SPMV_B200_ERR_NO_DEVICE, "synth_csr: no usable CUDA device; this library has no CPU fallback");
+    cudaStream_t stream = as_stream(stream_);
+    int *row_ptr = nullptr, *col_idx = nullptr;
+    double *values = nullptr;
+    const size_t padded = std::max<size_t>(((size_t)nnz + 3) & ~(size_t)3, 4);
+    auto body = [&]() -> int {
+        SPMV_TRY_CUDA(cudaMalloc(&row_ptr, ((size_t)rows + 1) * sizeof(int)));
+        SPMV_TRY_CUDA(cudaMalloc(&col_idx, padded * sizeof(int)));
+        SPMV_TRY_CUDA(cudaMalloc(&values, padded * sizeof(double)));
+        SPMV_TRY_CUDA(cudaMemsetAsync(col_idx + (padded - 4), 0, 4 * sizeof(int), stream));
+        SPMV_TRY_CUDA(cudaMemsetAsync(values + (padded - 4), 0, 4 * sizeof(double), stream));
+        if (kind == SPMV_B200_SYNTH_LAP2D)
+            lap2d_fill_kernel<<<blocks_for(rows + 1, 256), 256, 0, stream>>>(p0, row_begin, rows, row_ptr, col_idx, values);
+        else if (kind == SPMV_B200_SYNTH_LAP3D)
+            lap3d_fill_kernel<<<blocks_for(rows + 1, 256), 256, 0, stream>>>(p0, row_begin, rows, row_ptr, col_idx, values);
+        else
+            uniform_fill_kernel<<<blocks_for(std::max(rows * p2, rows + 1), 256), 256, 0, stream>>>(
+                row_begin, rows, p1, p2, seed, row_ptr, col_idx, values);
+        SPMV_TRY_CUDA(cudaGetLastError());
+        SPMV_TRY_CUDA(cudaStreamSynchronize(stream));
+        return SPMV_B200_OK;
+    };
+    int rc = body();
+    if (rc == SPMV_B200_OK)
+        rc = spmv_b200_csr_adopt_device_((int)rows, (int)N_global, nnz, row_ptr, col_idx, values, stream_, out);
+    if (rc != SPMV_B200_OK) {
+        cudaFree(row_ptr);
+        cudaFree(col_idx);
+        cudaFree(values);
+    }
+    return rc;
+}
+
+int spmv_b200_synth_vector(double *d_x, long long n, unsigned long long seed, void *stream) {
+    if (n < 0 || (n > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "synth_vector: bad arguments");
+    if (n == 0) return SPMV_B200_OK;
+    vector_hash_kernel<<<blocks_for(n, 256), 256, 0, as_stream(stream)>>>(d_x, n, seed);
+    SPMV_TRY_CUDA(cudaGetLastError());
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_vec_fill(double *d_v, long long n, double value, void *stream) {
+    if (n < 0 || (n > 0 && !d_v)) return fail(SPMV_B200_ERR_INVALID, "vec_fill: bad arguments");
+    if (n == 0) return SPMV_B200_OK;
+    vector_fill_kernel<<<blocks_for(n, 256), 256, 0, as_stream(stream)>>>(d_v, n, value);
+    SPMV_TRY_CUDA(cudaGetLastError());
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_vec_ws_doubles(void) { return kSumsqCtas; }
+
+int spmv_b200_vec_sumsq(const double *d_v, long long n, double *d_ws, double *d_out, void *stream) {
+    if (n < 0 || (n > 0 && !d_v) || !d_ws || !d_out) return fail(SPMV_B200_ERR_INVALID, "vec_sumsq: bad arguments");
+    sumsq_stage1_kernel<<<kSumsqCtas, kSumsqThreads, 0, as_stream(stream)>>>(d_v, n, d_ws);
+    SPMV_TRY_CUDA(cudaGetLastError());
+    sumsq_stage2_kernel<<<1, kSumsqThreads, 0, as_stream(stream)>>>(d_ws, d_out);
+    SPMV_TRY_CUDA(cudaGetLastError());
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_vec_scale_by_inv_norm(double *d_dst, const double *d_src, long long n, const double *d_sumsq,
+                                    void *stream) {
+    if (n < 0 || (n > 0 && (!d_dst || !d_src)) || !d_sumsq)
+        return fail(SPMV_B200_ERR_INVALID, "vec_scale_by_inv_norm: bad arguments");
+    if (n == 0) return SPMV_B200_OK;
+    scale_by_inv_norm_kernel<<<blocks_for(n, 256), 256, 0, as_stream(stream)>>>(d_dst, d_src, n, d_sumsq);
+    SPMV_TRY_CUDA(cudaGetLastError());
+    return SPMV_B200_OK;
+}
+
+}  // extern "C"

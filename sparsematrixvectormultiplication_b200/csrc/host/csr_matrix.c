@@ -1,0 +1,240 @@
+/*
+ * csr_matrix.c -- drop-in for reference src/csr_matrix.c.
+ *
+ *   convert_in_csr               host, bit-exact with reference :63-126 (duplicates included)
+ *   prepare_thread_distribution  host, same ranges as reference :167-266
+ *   csr_matrix_vector_mult, spvm_csr_parallel[_simd]
+ *                                same signatures as reference :130-139 / :269-313 but the product
+ *                                runs on the GPU through the C-ABI of spmv_b200.h.  No CPU fallback.
+ */
+#include "csr_matrix.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "spmv_b200.h"
+#include "utility.h"
+
+void init_csr_matrix(CSRMatrix *mat) {
+    mat->M = mat->N = mat->nz = 0;
+    mat->row_ptr = NULL;
+    mat->col_idx = NULL;
+    mat->values = NULL;
+}
+
+void free_csr_matrix(CSRMatrix *mat) {
+    FREE_CHECK(mat->row_ptr);
+    FREE_CHECK(mat->col_idx);
+    FREE_CHECK(mat->values);
+    init_csr_matrix(mat);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Row ordering.
+ *
+ * The reference sorts every row with an unstable Lomuto quicksort (src/utility.c:38-91).  When a
+ * row has no repeated column the sorted row is unique, so any algorithm gives the same bytes;
+ * only rows with duplicate (row, col) entries depend on the reference's exact swap sequence.
+ * Strategy per row:
+ *   1. already strictly increasing            -> nothing to do (the common case for files written
+ *                                                row by row; the reference spends O(len^2) here)
+ *   2. short rows                             -> run the reference-equivalent quicksort directly
+ *   3. long rows: merge-sort a copy (O(n log n)); if the result has no equal neighbours it is THE
+ *      answer; otherwise fall back to the reference-equivalent quicksort on the original data.
+ * ---------------------------------------------------------------------------------------- */
+#define SHORT_ROW 48
+
+static int strictly_increasing(const int *c, int n) {
+    for (int k = 1; k < n; ++k)
+        if (c[k - 1] >= c[k]) return 0;
+    return 1;
+}
+
+static void merge_sort_pairs(int *c, double *v, int *tc, double *tv, int n) {
+    for (int width = 1; width < n; width *= 2) {
+        for (int lo = 0; lo < n; lo += 2 * width) {
+            const int mid = lo + width < n ? lo + width : n;
+            const int hi = lo + 2 * width < n ? lo + 2 * width : n;
+            int a = lo, b = mid, o = lo;
+            while (a < mid && b < hi) {
+                if (c[b] < c[a]) { tc[o] = c[b]; tv[o++] = v[b++]; }
+                else { tc[o] = c[a]; tv[o++] = v[a++]; }
+            }
+            while (a < mid) { tc[o] = c[a]; tv[o++] = v[a++]; }
+            while (b < hi) { tc[o] = c[b]; tv[o++] = v[b++]; }
+        }
+        memcpy(c, tc, (size_t)n * sizeof(int));
+        memcpy(v, tv, (size_t)n * sizeof(double));
+    }
+}
+
+static void order_row(int *c, double *v, int n) {
+    if (n < 2 || strictly_increasing(c, n)) return;
+    if (n > SHORT_ROW) {
+        int *sc = malloc((size_t)n * 2 * sizeof(int));
+        double *sv = malloc((size_t)n * 2 * sizeof(double));
+        if (sc && sv) {
+            memcpy(sc, c, (size_t)n * sizeof(int));
+            memcpy(sv, v, (size_t)n * sizeof(double));
+            merge_sort_pairs(sc, sv, sc + n, sv + n, n);
+            if (strictly_increasing(sc, n)) { /* no duplicates: unique answer */
+                memcpy(c, sc, (size_t)n * sizeof(int));
+                memcpy(v, sv, (size_t)n * sizeof(double));
+                free(sc);
+                free(sv);
+                return;
+            }
+        }
+        free(sc);
+        free(sv);
+    }
+    sort_row(c, v, 0, (size_t)n - 1);
+}
+
+int convert_in_csr(const PreMatrix *pre, CSRMatrix *csr, const char *matrix_name) {
+    (void)matrix_name;
+    init_csr_matrix(csr);
+    csr->M = pre->M;
+    csr->N = pre->N;
+    csr->nz = pre->nz;
+    memcpy(csr->type, pre->type, sizeof(MM_typecode));
+    const int M = pre->M, nz = pre->nz;
+    csr->row_ptr = calloc((size_t)M + 1, sizeof(int));
+    csr->col_idx = malloc((size_t)(nz > 0 ? nz : 1) * sizeof(int));
+    csr->values = malloc((size_t)(nz > 0 ? nz : 1) * sizeof(double));
+    int *cursor = malloc((size_t)(M > 0 ? M : 1) * sizeof(int));
+    if (!csr->row_ptr || !csr->col_idx || !csr->values || !cursor) {
+        printf("convert_in_csr: out of memory\n");
+        free(cursor);
+        free_csr_matrix(csr);
+        return -1;
+    }
+    int *rp = csr->row_ptr;
+    for (int k = 0; k < nz; ++k) rp[pre->I[k] + 1]++;
+    for (int r = 0; r < M; ++r) rp[r + 1] += rp[r];
+    memcpy(cursor, rp, (size_t)M * sizeof(int));
+    for (int k = 0; k < nz; ++k) { /* entries of a row keep their file order */
+        const int slot = cursor[pre->I[k]]++;
+        csr->col_idx[slot] = pre->J[k];
+        csr->values[slot] = pre->val[k];
+    }
+    free(cursor);
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int r = 0; r < M; ++r) order_row(csr->col_idx + rp[r], csr->values + rp[r], rp[r + 1] - rp[r]);
+    return 0;
+}
+
+void print_csr_matrix(const CSRMatrix *mat) {
+    char *kind = mm_typecode_to_str((char *)mat->type);
+    printf("CSR %d x %d, %d nonzeros, type: %s\n", mat->M, mat->N, mat->nz, kind ? kind : "?");
+    free(kind);
+    if (mat->M > 30 || mat->N > 30) return;
+    printf("row_ptr:"); for (int i = 0; i <= mat->M; ++i) printf(" %d", mat->row_ptr[i]); printf("\n");
+    printf("col_idx:"); for (int i = 0; i < mat->nz; ++i) printf(" %d", mat->col_idx[i]); printf("\n");
+    printf("values :"); for (int i = 0; i < mat->nz; ++i) printf(" %f", mat->values[i]); printf("\n");
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Contiguous row ranges balanced by nnz -- the reference's greedy rule (:196-238): a range is
+ * closed as soon as the nonzeros gathered since the previous cut reach ceil(total/T), the last
+ * range takes what is left, and ranges that collected no nonzero are dropped.  The same rule
+ * partitions the rows over GPUs (sparsematrixvectormultiplication_b200/partition.py).
+ * ---------------------------------------------------------------------------------------- */
+int prepare_thread_distribution(const int num_row, const int *row_ptr, int num_threads,
+                                const long long total_nnz, int **thread_row_start, int **thread_row_end) {
+    if (num_row <= 0 || num_threads <= 0) return 0;
+    if (num_threads > num_row) num_threads = num_row;
+    int *start = malloc((size_t)num_threads * sizeof(int));
+    int *end = malloc((size_t)num_threads * sizeof(int));
+    if (!start || !end) {
+        free(start);
+        free(end);
+        *thread_row_start = *thread_row_end = NULL;
+        return 0;
+    }
+    const long long target = (total_nnz + num_threads - 1) / num_threads;
+    int used = 0, part = 0, first = 0;
+    long long gathered = 0;
+    for (int r = 0; r < num_row; ++r) {
+        gathered += row_ptr[r + 1] - row_ptr[r];
+        const int last_part = part == num_threads - 1;
+        const int close = (!last_part && gathered >= target) || r == num_row - 1;
+        if (!close) continue;
+        if (gathered > 0) { /* empty ranges are compacted away */
+            start[used] = first;
+            end[used] = r + 1;
+            ++used;
+        }
+        first = r + 1;
+        gathered = 0;
+        ++part;
+    }
+    *thread_row_start = start;
+    *thread_row_end = end;
+    return used;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * GPU-backed product entry points.
+ * ---------------------------------------------------------------------------------------- */
+static void poison(double *y, int lo, int hi, const char *who) {
+    fprintf(stderr, "%s: GPU product failed: %s\n", who, spmv_b200_last_error());
+    for (int i = lo; i < hi; ++i) y[i] = NAN;
+}
+
+/* x has one entry per column; the signatures do not carry N, so take the largest referenced
+ * column (the kernels never read past it). */
+static int columns_referenced(const int *col_idx, long long nnz) {
+    int top = -1;
+#pragma omp parallel for reduction(max : top)
+    for (long long k = 0; k < nnz; ++k)
+        if (col_idx[k] > top) top = col_idx[k];
+    return top + 1;
+}
+
+void csr_matrix_vector_mult(int num_row, const int *row_ptr, const int *col_idx, const double *values,
+                            const double *x, double *y) {
+    if (num_row <= 0) return;
+    const long long nnz = row_ptr[num_row];
+    spmv_b200_csr *A = NULL;
+    int rc = spmv_b200_csr_upload(num_row, columns_referenced(col_idx, nnz), nnz, row_ptr, col_idx, values, &A);
+    if (rc == SPMV_B200_OK) rc = spmv_b200_csr_spmv_host(A, x, y, /*accumulate=*/1, SPMV_B200_ALGO_AUTO);
+    spmv_b200_csr_free(A);
+    if (rc != SPMV_B200_OK) poison(y, 0, num_row, "csr_matrix_vector_mult");
+}
+
+static void ranged_product(const char *who, const int *row_ptr, const int *col_idx, const double *values,
+                           const double *x, double *y, int num_threads, const int *lo, const int *hi) {
+    if (num_threads <= 0) return;
+    int M = 0;
+    for (int t = 0; t < num_threads; ++t)
+        if (hi[t] > M) M = hi[t];
+    if (M <= 0) return;
+    const long long nnz = row_ptr[M];
+    const int N = columns_referenced(col_idx, nnz);
+    spmv_b200_csr *A = NULL;
+    int rc = spmv_b200_csr_upload(M, N, nnz, row_ptr, col_idx, values, &A);
+    double *full = rc == SPMV_B200_OK ? malloc((size_t)M * sizeof(double)) : NULL;
+    if (rc == SPMV_B200_OK && !full) rc = SPMV_B200_ERR_NOMEM;
+    if (rc == SPMV_B200_OK) rc = spmv_b200_csr_spmv_host(A, x, full, 0, SPMV_B200_ALGO_AUTO);
+    spmv_b200_csr_free(A);
+    for (int t = 0; t < num_threads; ++t) { /* only rows inside a range are written */
+        if (rc == SPMV_B200_OK) memcpy(y + lo[t], full + lo[t], (size_t)(hi[t] - lo[t]) * sizeof(double));
+        else poison(y, lo[t], hi[t], who);
+    }
+    free(full);
+}
+
+void spvm_csr_parallel(const int *row_ptr, const int *col_idx, const double *values, const double *x, double *y,
+                       int num_threads, const int *thread_row_start, const int *thread_row_end) {
+    ranged_product("spvm_csr_parallel", row_ptr, col_idx, values, x, y, num_threads, thread_row_start,
+                   thread_row_end);
+}
+
+void spvm_csr_parallel_simd(const int *row_ptr, const int *col_idx, const double *values, const double *x,
+                            double *y, int num_threads, const int *thread_row_start, const int *thread_row_end) {
+    ranged_product("spvm_csr_parallel_simd", row_ptr, col_idx, values, x, y, num_threads, thread_row_start,
+                   thread_row_end);
+}

@@ -1,0 +1,260 @@
+"""Resident matrices on the B200: thin handle classes over the C-ABI of include/spmv_b200.h.
+
+PyTorch is plumbing only: it owns the dense vectors (x, y), the CUDA streams and -- in
+distributed.py -- the process group.  The matrix arenas, plans and every kernel live in
+libspmv_b200.so.  Nothing here falls back to PyTorch or the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+ALGO_AUTO, ALGO_VECTOR, ALGO_TILE = 0, 1, 2
+SYNTH_LAP2D, SYNTH_LAP3D, SYNTH_UNIFORM = 1, 2, 3
+
+
+def _ptr(t):
+    """Device (torch tensor) or host (numpy array) pointer as void*."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return C.c_void_p(t.ctypes.data)
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def _check_vec(t, n, what):
+    import torch
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+            and t.numel() >= n):
+        raise ValueError(f"{what} must be a contiguous float64 CUDA tensor with at least {n} elements")
+
+
+def device_count() -> int:
+    n = C.c_int()
+    N.lib().spmv_b200_device_count(C.byref(n))
+    return n.value
+
+
+def device_info():
+    name = C.create_string_buffer(256)
+    sm, l2, mem = C.c_int(), C.c_longlong(), C.c_longlong()
+    N.check(N.lib().spmv_b200_device_info(name, 256, C.byref(sm), C.byref(l2), C.byref(mem)))
+    return {"name": name.value.decode(), "sm_count": sm.value, "l2_bytes": l2.value, "mem_bytes": mem.value}
+
+
+class DeviceCSR:
+    """A CSR matrix resident in HBM plus its row-binning plan (spmv_b200_csr)."""
+
+    def __init__(self, handle, keepalive=None):
+        self._h = handle
+        self._keep = keepalive
+
+    # -- construction ------------------------------------------------------------------------------
+    @classmethod
+    def upload(cls, M, N_, row_ptr, col_idx, values):
+        """Host CSR arrays (reference CSRMatrix fields) -> device.  reference main_cuda.cu:135-145."""
+        row_ptr = np.ascontiguousarray(row_ptr, np.int32)
+        col_idx = np.ascontiguousarray(col_idx, np.int32)
+        values = np.ascontiguousarray(values, np.float64)
+        h = C.c_void_p()
+        N.check(N.lib().spmv_b200_csr_upload(int(M), int(N_), int(row_ptr[-1]) if len(row_ptr) else 0,
+                                             _ptr(row_ptr), _ptr(col_idx), _ptr(values), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_host(cls, csr):
+        """From a host.CSRMatrix produced by convert_in_csr."""
+        return cls.upload(csr.M, csr.N, csr.row_ptr, csr.col_idx, csr.values)
+
+    @classmethod
+    def wrap(cls, M, N_, row_ptr, col_idx, values, stream=None):
+        """CUDA tensors (int32, int32, float64) used in place; they must outlive this object."""
+        h = C.c_void_p()
+        N.check(N.lib().spmv_b200_csr_wrap_device(int(M), int(N_), int(values.numel()), _ptr(row_ptr), _ptr(col_idx),
+                                                  _ptr(values), _stream(stream), C.byref(h)))
+        return cls(h, keepalive=(row_ptr, col_idx, values))
+
+    @classmethod
+    def synth(cls, kind, p0, p1=0, p2=0, seed=0x5EED, row_begin=0, row_end=None, stream=None):
+        """Rows [row_begin,row_end) of a synthetic matrix, generated on the device."""
+        if row_end is None:
+            row_end = {SYNTH_LAP2D: p0 * p0, SYNTH_LAP3D: p0 ** 3, SYNTH_UNIFORM: p0}[kind]
+        h = C.c_void_p()
+        N.check(N.lib().spmv_b200_synth_csr(kind, int(p0), int(p1), int(p2), int(seed), int(row_begin), int(row_end),
+                                            _stream(stream), C.byref(h)))
+        return cls(h)
+
+    # -- introspection -----------------------------------------------------------------------------
+    def info(self) -> N.CsrInfo:
+        i = N.CsrInfo()
+        N.check(N.lib().spmv_b200_csr_info(self._h, C.byref(i)))
+        return i
+
+    @property
+    def shape(self):
+        i = self.info()
+        return i.M, i.N
+
+    @property
+    def nnz(self):
+        return self.info().nnz
+
+    def replan(self, tile_items=0, long_threshold=0, threads_per_row=0, stream=None):
+        N.check(N.lib().spmv_b200_csr_replan(self._h, tile_items, long_threshold, threads_per_row, _stream(stream)))
+        return self
+
+    def download(self):
+        i = self.info()
+        row_ptr = np.zeros(i.M + 1, np.int32)
+        col_idx = np.zeros(i.nnz, np.int32)
+        values = np.zeros(i.nnz, np.float64)
+        N.check(N.lib().spmv_b200_csr_download(self._h, _ptr(row_ptr), _ptr(col_idx), _ptr(values)))
+        return row_ptr, col_idx, values
+
+    # -- products ----------------------------------------------------------------------------------
+    def spmv(self, x, y, accumulate=False, algo=ALGO_AUTO, stream=None):
+        """y = A x (or y += A x) on CUDA tensors, asynchronous on ``stream``."""
+        i = self.info()
+        _check_vec(x, i.N, "x")
+        _check_vec(y, i.M, "y")
+        N.check(N.lib().spmv_b200_csr_spmv(self._h, _ptr(x), _ptr(y), int(bool(accumulate)), algo, _stream(stream)))
+        return y
+
+    def spmv_rows(self, row_begin, row_end, x, y, stream=None):
+        N.check(N.lib().spmv_b200_csr_spmv_rows(self._h, int(row_begin), int(row_end), _ptr(x), _ptr(y), _stream(stream)))
+        return y
+
+    def spmv_host(self, x, y=None, accumulate=False, algo=ALGO_AUTO):
+        """Host numpy x -> H2D, product, D2H -> host numpy y (synchronous): the end-to-end call."""
+        i = self.info()
+        x = np.ascontiguousarray(x, np.float64)
+        if y is None:
+            y = np.zeros(i.M, np.float64)
+        N.check(N.lib().spmv_b200_csr_spmv_host(self._h, _ptr(x), _ptr(y), int(bool(accumulate)), algo))
+        return y
+
+    def spmv_host_ptr(self, x_ptr: int, y_ptr: int, accumulate=False, algo=ALGO_AUTO):
+        """Same, on raw host addresses (e.g. pinned torch tensors' data_ptr())."""
+        N.check(N.lib().spmv_b200_csr_spmv_host(self._h, C.c_void_p(x_ptr), C.c_void_p(y_ptr), int(bool(accumulate)), algo))
+
+    def to_hll(self, stream=None) -> "DeviceHLL":
+        h = C.c_void_p()
+        N.check(N.lib().spmv_b200_hll_from_csr(self._h, _stream(stream), C.byref(h)))
+        return DeviceHLL(h)
+
+    def close(self):
+        if self._h:
+            N.lib().spmv_b200_csr_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def csr_spmv_raw(M, row_ptr, col_idx, values, x, y, threads_per_row=0, stream=None):
+    """Plan-free vector-per-row product on raw CUDA tensors (drop-in for the reference's
+    spmv_csr_warp_kernel launch, main_cuda.cu:238)."""
+    N.check(N.lib().spmv_b200_csr_spmv_raw(int(M), int(values.numel()), _ptr(row_ptr), _ptr(col_idx), _ptr(values),
+                                           _ptr(x), _ptr(y), threads_per_row, _stream(stream)))
+    return y
+
+
+class DeviceHLL:
+    """Column-major, hack-aligned HLL image resident in HBM (spmv_b200_hll)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def from_host(cls, hll, M=None, N_=None):
+        """From a host.HLLMatrix produced by convert_to_hll (reference row-major layout)."""
+        h = C.c_void_p()
+        N.check(N.lib().spmv_b200_hll_upload(C.byref(hll.c), int(hll.rows_total if M is None else M),
+                                             int(hll.cols if N_ is None else N_), C.byref(h)))
+        return cls(h)
+
+    def info(self) -> N.HllInfo:
+        i = N.HllInfo()
+        N.check(N.lib().spmv_b200_hll_info(self._h, C.byref(i)))
+        return i
+
+    def download(self):
+        """-> host.HLLMatrix in the reference layout (round trip of from_host)."""
+        from .host import HLLMatrix
+        out = HLLMatrix()
+        N.check(N.lib().spmv_b200_hll_download(self._h, C.byref(out.c)))
+        out._owned = True
+        i = self.info()
+        out.rows_total, out.cols = i.M, i.N
+        return out
+
+    def spmv(self, x, y, stream=None):
+        i = self.info()
+        _check_vec(x, i.N, "x")
+        _check_vec(y, i.M, "y")
+        N.check(N.lib().spmv_b200_hll_spmv(self._h, _ptr(x), _ptr(y), _stream(stream)))
+        return y
+
+    def spmv_hacks(self, hack_begin, hack_end, x, y, stream=None):
+        N.check(N.lib().spmv_b200_hll_spmv_hacks(self._h, int(hack_begin), int(hack_end), _ptr(x), _ptr(y), _stream(stream)))
+        return y
+
+    def spmv_host(self, x, y=None):
+        i = self.info()
+        x = np.ascontiguousarray(x, np.float64)
+        if y is None:
+            y = np.zeros(i.M, np.float64)
+        N.check(N.lib().spmv_b200_hll_spmv_host(self._h, _ptr(x), _ptr(y)))
+        return y
+
+    def spmv_host_ptr(self, x_ptr: int, y_ptr: int):
+        N.check(N.lib().spmv_b200_hll_spmv_host(self._h, C.c_void_p(x_ptr), C.c_void_p(y_ptr)))
+
+    def close(self):
+        if self._h:
+            N.lib().spmv_b200_hll_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- dense-vector helpers of the iterated product -------------------------------------------------
+def synth_vector(x, seed, stream=None):
+    N.check(N.lib().spmv_b200_synth_vector(_ptr(x), x.numel(), int(seed), _stream(stream)))
+    return x
+
+
+def vec_fill(v, value, stream=None):
+    N.check(N.lib().spmv_b200_vec_fill(_ptr(v), v.numel(), float(value), _stream(stream)))
+    return v
+
+
+def vec_ws_doubles() -> int:
+    return N.lib().spmv_b200_vec_ws_doubles()
+
+
+def vec_sumsq(v, ws, out, n=None, stream=None):
+    N.check(N.lib().spmv_b200_vec_sumsq(_ptr(v), int(v.numel() if n is None else n), _ptr(ws), _ptr(out), _stream(stream)))
+    return out
+
+
+def vec_scale_by_inv_norm(dst, src, sumsq, n=None, stream=None):
+    N.check(N.lib().spmv_b200_vec_scale_by_inv_norm(_ptr(dst), _ptr(src), int(src.numel() if n is None else n),
+                                                    _ptr(sumsq), _stream(stream)))
+    return dst
