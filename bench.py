@@ -1,0 +1,526 @@
+#!/usr/bin/env python
+"""bench.py -- SpMV GFLOPS and HBM GB/s for CSR and HLL on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--quick]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+N = 1  workload "lap2d_4096_csr" (BASELINE.json configs[1]): fp64 CSR product of the 2-D 5-point
+       Laplacian on a 4096 x 4096 grid (16.8 M rows, 83.9 M nnz, 1.34 GB streamed per product).
+       A step is ONE product y = A x with the matrix resident in HBM.  The other single-GPU configs
+       (HLL of the same matrix, uniform 8M x 8M x 32 CSR/HLL, R-MAT, the 512^3 power iteration on one
+       GPU) are measured too and reported under "others" -- they are not the headline.
+N > 1  workload "lap3d_512_power" (configs[4]): power iteration on the 512^3 7-point Laplacian,
+       rows partitioned by nnz over the N ranks, x refreshed every iteration ("halo" = only the
+       referenced column range, "allgather" = the whole vector; both reported).  A step is one
+       iteration (product + norm + scale + exchange); value = 2 * nnz_global / t, strong scaling.
+
+--impl reference times the reference's own CPU implementation (oracle/_ref, built from the unmodified
+reference sources; the oracle port if that .so is absent) on the host cores, same workload and metric.
+
+One JSON line on stdout (rank 0).  Everything else goes to stderr.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+HBM_NOMINAL_GBS = 8000.0   # BASELINE.json quotes fractions of 8 TB/s
+FALLBACK_PEAK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
+# ncu --set full capture (profiles/); None until a capture exists for that kernel.
+NCU_TRAFFIC_BYTES = {"lap2d_4096_csr": None}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return FALLBACK_PEAK_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks: NVML sampled in a thread while the GPU is busy
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+
+    def __init__(self, index=0, period=0.004):
+        self.samples = []   # (t, sm_mhz, reasons_bitmask, power_w)
+        self.windows = []
+        self.period = period
+        self._stop = threading.Event()
+        self._thread = None
+        self.max_sm = None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    index = int(vis.split(",")[index])
+                except (ValueError, IndexError):
+                    pass
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            log(f"[clocks] NVML unavailable: {e}")
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                try:
+                    power = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                except Exception:
+                    power = None
+                self.samples.append((time.perf_counter(), sm, reasons, power))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self.ok:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=1.0)
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": [], "samples": 0, "source": "unavailable"}
+        inside = [s for s in self.samples if any(a <= s[0] <= b for a, b in self.windows)]
+        src = "nvml, sampled during the timed regions"
+        if len(inside) < 3:  # a very short timed region: use every sample taken while the bench kept the GPU busy
+            inside, src = self.samples, "nvml, sampled during the whole GPU-busy phase (timed region too short)"
+        mask = 0
+        for s in inside:
+            mask |= s[2]
+        reasons = sorted({name for bit, name in self.REASONS.items() if mask & bit})
+        powers = [s[3] for s in inside if s[3] is not None]
+        return {"sm_mhz": statistics.median(s[1] for s in inside), "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "samples": len(inside), "power_w_max": max(powers) if powers else None, "source": src}
+
+
+# ---------------------------------------------------------------------------------------------------
+# timing helpers
+# ---------------------------------------------------------------------------------------------------
+def time_device(fn, steps, warmup, sampler=None, world=1):
+    """W untimed + exactly K timed calls; CUDA events on the current (launching) stream, barrier and
+    synchronize on both sides, MAX over ranks.  Returns (ms_per_step, per_step_ms_list)."""
+    import torch
+    import torch.distributed as dist
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    t0 = time.perf_counter()
+    marks[0].record()
+    for i in range(steps):
+        fn()
+        marks[i + 1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    if sampler:
+        sampler.window(t0, t1)
+    total = marks[0].elapsed_time(marks[steps])
+    per = [marks[i].elapsed_time(marks[i + 1]) for i in range(steps)]
+    if world > 1:
+        t = torch.tensor([total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total = float(t.item())
+    return total / steps, per
+
+
+def spmv_stats(nnz, bytes_alg, ms, peak):
+    s = ms * 1e-3
+    gbs = bytes_alg / s / 1e9
+    return {"gflops": 2.0 * nnz / s / 1e9, "ms": ms, "gbs": gbs, "frac_of_measured_peak": gbs / peak,
+            "frac_of_8tbs": gbs / HBM_NOMINAL_GBS, "algorithmic_bytes": int(bytes_alg)}
+
+
+def ramp_vector(n, device):
+    import torch
+    return 1.0 + (torch.arange(n, device=device, dtype=torch.int64) % 7).to(torch.float64) / 8.0
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU baseline (the reference's own CPU path on the host cores)
+# ---------------------------------------------------------------------------------------------------
+def cpu_baseline_lap2d(n, rp, ci, va, budget_s=20.0):
+    """oracle/_ref (kind 'reference') or the oracle port, OpenMP over all host cores + the serial loop,
+    on the full workload matrix; a bounded number of products."""
+    from oracle import oracle as O
+    chk = O.best_available()
+    cores = os.cpu_count() or 1
+    N = n * n
+    x = 1.0 + (np.arange(N) % 7) / 8.0
+    nnz = int(rp[-1])
+    t0 = time.perf_counter()
+    chk.spmv_csr_serial(rp, ci, va, x)
+    serial_s = time.perf_counter() - t0
+    starts, ends = chk.partition_rows(rp, cores)
+    y = np.zeros(N)
+    chk.spmv_csr_parallel(rp, ci, va, x, starts, ends, y=y)  # warm-up
+    times = []
+    t_begin = time.perf_counter()
+    while len(times) < 95 and (time.perf_counter() - t_begin) < budget_s:
+        t0 = time.perf_counter()
+        chk.spmv_csr_parallel(rp, ci, va, x, starts, ends, y=y)
+        times.append(time.perf_counter() - t0)
+    mean_s = sum(times) / len(times)
+    return {"value": 2.0 * nnz / mean_s / 1e9, "unit": "GFLOP/s", "cores": len(starts), "kind": chk.kind,
+            "sample": f"full lap2d_4096 matrix ({nnz} nnz), {len(times)} timed OpenMP CSR products (spvm_csr_parallel) "
+                      f"after 1 warm-up, mean; host has {cores} logical cores",
+            "serial_gflops": 2.0 * nnz / serial_s / 1e9, "best_gflops": 2.0 * nnz / min(times) / 1e9}
+
+
+# ---------------------------------------------------------------------------------------------------
+# arms
+# ---------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's CPU implementation of the path on the host cores, on our arm's config/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from sparsematrixvectormultiplication_b200 import synth
+    from oracle import oracle as O
+    chk = O.best_available()
+    cores = os.cpu_count() or 1
+    if args.gpus == 1:
+        n = 4096
+        workload = "lap2d_4096_csr"
+        log("[reference] generating lap2d 4096^2 on the host (numpy twin) ...")
+        rp, ci, va = synth.lap2d_csr(n)
+        x = 1.0 + (np.arange(n * n) % 7) / 8.0
+        nnz = int(rp[-1])
+        starts, ends = chk.partition_rows(rp, cores)
+        y = np.zeros(n * n)
+
+        def step():
+            chk.spmv_csr_parallel(rp, ci, va, x, starts, ends, y=y)
+        sample = f"full lap2d_4096 matrix, one OpenMP CSR product (spvm_csr_parallel) per step on {len(starts)} threads"
+        config = {"workload": workload, "rows": n * n, "nnz": nnz, "format": "csr", "l2": "inputs_exceed_l2"}
+        scaling = "weak"
+    else:
+        # power iteration on a bounded 3-D Laplacian sample (the 512^3 matrix needs 11.8 GB and ~2 s per
+        # serial product): 256^3, same stencil, same per-iteration algorithm, OpenMP product.
+        n = 256
+        workload = "lap3d_512_power"
+        log("[reference] generating lap3d 256^3 sample on the host ...")
+        rp, ci, va = synth.lap3d_csr(n)
+        nnz = int(rp[-1])
+        starts, ends = chk.partition_rows(rp, cores)
+        state = {"x": np.ones(n ** 3)}
+        y = np.zeros(n ** 3)
+
+        def step():
+            chk.spmv_csr_parallel(rp, ci, va, state["x"], starts, ends, y=y)
+            lam = float(np.sqrt(np.dot(y, y)))
+            state["x"] = y / lam
+        sample = (f"bounded sample: 256^3 7-point Laplacian ({nnz} nnz, 1/8 of the 512^3 workload), one power iteration "
+                  f"(OpenMP CSR product + norm + scale) per step on {len(starts)} threads; GFLOPS = 2 nnz / t is size independent")
+        config = {"workload": workload, "rows": 512 ** 3, "nnz": 937951232, "format": "csr", "exchange": "none (single host)",
+                  "sample_rows": n ** 3, "l2": "inputs_exceed_l2"}
+        scaling = "strong"
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = 2.0 * nnz / dt / 1e9
+    line = {"impl": "reference", "metric": "spmv_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": value, "unit": "GFLOP/s", "cores": len(starts), "kind": chk.kind, "sample": sample},
+            "e2e": {"value": value, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def bench_single_gpu(args):
+    import torch
+    from sparsematrixvectormultiplication_b200 import device, synth
+    torch.cuda.set_device(0)
+    peak, peak_src = measured_peak()
+    sampler = ClockSampler(0)
+    sampler.start()
+    n = 4096
+    workload = "lap2d_4096_csr"
+    log(f"[bench] {device.device_info()}")
+    A = device.DeviceCSR.synth(synth.SYNTH_LAP2D, n)
+    info = A.info()
+    M, nnz, bytes_alg = info.M, info.nnz, info.algorithmic_bytes
+    x = ramp_vector(M, "cuda")
+    y = torch.empty(M, dtype=torch.float64, device="cuda")
+    launches_per_step = 1 + (2 if info.num_long_rows else 0)
+
+    ms, per = time_device(lambda: A.spmv(x, y), args.steps, args.warmup, sampler)
+    head = spmv_stats(nnz, bytes_alg, ms, peak)
+    log(f"[bench] {workload}: {head['gflops']:.1f} GFLOP/s, {head['gbs']:.0f} GB/s, {ms*1e3:.1f} us/product "
+        f"(min {min(per)*1e3:.1f}, median {statistics.median(per)*1e3:.1f})")
+
+    # ---- end to end through the C-ABI host call: pinned host x -> H2D, product, D2H -> pinned host y ----
+    xh = torch.empty(M, dtype=torch.float64).pin_memory()
+    xh.copy_(x.cpu())
+    yh = torch.empty(M, dtype=torch.float64).pin_memory()
+    e2e_steps = max(3, min(args.steps, 30))
+    for _ in range(2):
+        A.spmv_host_ptr(xh.data_ptr(), yh.data_ptr())
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        A.spmv_host_ptr(xh.data_ptr(), yh.data_ptr())
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    sampler.window(t0, time.perf_counter())
+    torch.cuda.synchronize()
+    assert torch.equal(yh.cuda(), y), "end-to-end result differs from the resident product"
+    e2e = {"value": 2.0 * nnz / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * info.N, "d2h_bytes_per_step": 8 * M,
+           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "api": "spmv_b200_csr_spmv_host (pinned host x -> device, product, device -> pinned host y, synchronous)"}
+    log(f"[bench] e2e: {e2e['value']:.1f} GFLOP/s ({e2e_s*1e3:.2f} ms/step)")
+
+    others = {}
+    if not args.quick:
+        others = measure_others(args, A, x, y, peak, sampler)
+
+    # ---- CPU baseline on the host cores (bounded) ----
+    cpu = None
+    if not args.no_cpu:
+        try:
+            rp, ci, va = A.download()
+            cpu = cpu_baseline_lap2d(n, rp, ci, va, budget_s=args.cpu_budget)
+            log(f"[bench] cpu_baseline: {cpu['value']:.2f} GFLOP/s on {cpu['cores']} threads ({cpu['kind']}), serial {cpu['serial_gflops']:.2f}")
+            del rp, ci, va
+        except Exception as e:  # pragma: no cover
+            log(f"[bench] cpu baseline failed: {e!r}")
+    sampler.stop()
+
+    line = {"metric": "spmv_gflops", "value": head["gflops"], "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "rows": M, "cols": info.N, "nnz": nnz, "format": "csr", "x": "1+(i mod 7)/8",
+                       "kernel": "csr_tile_kernel (adaptive row-binned stream kernel)", "tiles": info.num_tiles,
+                       "l2": "inputs_exceed_l2 (1.34 GB streamed per product vs 126 MB L2)",
+                       "step": "one product y = A x, matrix resident in HBM"},
+            "roofline": {"bound": "hbm", "achieved": head["gbs"], "peak": peak, "unit": "GB/s", "frac": head["gbs"] / peak,
+                         "traffic": NCU_TRAFFIC_BYTES.get(workload), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(bytes_alg), "frac_of_8tbs": head["frac_of_8tbs"],
+                         "kernel_ms_min": min(per), "kernel_ms_median": statistics.median(per)},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "clocks": sampler.summary(), "others": others}
+    print(json.dumps(line), flush=True)
+
+
+def measure_others(args, A2d, x2d, y2d, peak, sampler):
+    """The remaining single-GPU configs of BASELINE.json -- reported, not the headline."""
+    import torch
+    from sparsematrixvectormultiplication_b200 import device, synth
+    out = {}
+    steps, warm = max(5, min(args.steps, 100)), max(3, min(args.warmup, 10))
+
+    def run(name, fn, nnz, bytes_alg, extra=None):
+        try:
+            ms, per = time_device(fn, steps, warm, sampler)
+            out[name] = spmv_stats(nnz, bytes_alg, ms, peak)
+            out[name]["ms_min"] = min(per)
+            if extra:
+                out[name].update(extra)
+            log(f"[bench] {name}: {out[name]['gflops']:.1f} GFLOP/s, {out[name]['gbs']:.0f} GB/s ({ms*1e3:.1f} us)")
+        except Exception as e:  # pragma: no cover
+            out[name] = {"error": repr(e)}
+            log(f"[bench] {name} failed: {e!r}")
+
+    i2 = A2d.info()
+    run("lap2d_4096_csr_vector_kernel", lambda: A2d.spmv(x2d, y2d, algo=device.ALGO_VECTOR), i2.nnz, i2.algorithmic_bytes)
+    try:
+        H = A2d.to_hll()
+        hi = H.info()
+        run("lap2d_4096_hll", lambda: H.spmv(x2d, y2d), i2.nnz, hi.algorithmic_bytes, {"slots": hi.slots})
+        H.close()
+    except Exception as e:  # pragma: no cover
+        out["lap2d_4096_hll"] = {"error": repr(e)}
+
+    # config 3: uniform 8M x 8M, 32 nnz/row, CSR vs HLL hack 32
+    try:
+        M = 1 << 23
+        A = device.DeviceCSR.synth(synth.SYNTH_UNIFORM, M, M, 32)
+        x = torch.empty(M, dtype=torch.float64, device="cuda")
+        device.synth_vector(x, 4242)
+        y = torch.empty(M, dtype=torch.float64, device="cuda")
+        ia = A.info()
+        run("uniform_8m_32_csr", lambda: A.spmv(x, y), ia.nnz, ia.algorithmic_bytes)
+        run("uniform_8m_32_csr_vector_kernel", lambda: A.spmv(x, y, algo=device.ALGO_VECTOR), ia.nnz, ia.algorithmic_bytes)
+        H = A.to_hll()
+        hi = H.info()
+        run("uniform_8m_32_hll", lambda: H.spmv(x, y), ia.nnz, hi.algorithmic_bytes, {"slots": hi.slots})
+        H.close()
+        A.close()
+        del x, y
+    except Exception as e:  # pragma: no cover
+        out["uniform_8m_32"] = {"error": repr(e)}
+        log(f"[bench] uniform failed: {e!r}")
+
+    # config 4: R-MAT scale 24, 16 edges/row, skewed rows
+    try:
+        torch.cuda.empty_cache()
+        rp, ci, va = synth.rmat_csr_device(24, 16)
+        Mr = (1 << 24)
+        A = device.DeviceCSR.wrap(Mr, Mr, rp, ci, va)
+        ia = A.info()
+        max_row = int((rp[1:] - rp[:-1]).max().item())
+        x = torch.empty(Mr, dtype=torch.float64, device="cuda")
+        device.synth_vector(x, 777)
+        y = torch.empty(Mr, dtype=torch.float64, device="cuda")
+        extra = {"max_row_nnz": max_row, "long_rows": ia.num_long_rows, "fragments": ia.num_fragments, "tiles": ia.num_tiles}
+        run("rmat_24_16_csr", lambda: A.spmv(x, y), ia.nnz, ia.algorithmic_bytes, extra)
+        run("rmat_24_16_csr_vector_kernel", lambda: A.spmv(x, y, algo=device.ALGO_VECTOR), ia.nnz, ia.algorithmic_bytes)
+        A.close()
+        del rp, ci, va, x, y
+        torch.cuda.empty_cache()
+    except Exception as e:  # pragma: no cover
+        out["rmat_24_16_csr"] = {"error": repr(e)}
+        log(f"[bench] rmat failed: {e!r}")
+
+    # config 5 on ONE GPU: T1 of the multi-GPU scaling series
+    try:
+        from sparsematrixvectormultiplication_b200.distributed import PowerIteration
+        P = PowerIteration(synth.SYNTH_LAP3D, 512)
+        ms, per = time_device(P.step, steps, warm, sampler)
+        out["lap3d_512_power_1gpu"] = {"gflops": 2.0 * P.nnz_global / (ms * 1e-3) / 1e9, "ms_per_iteration": ms,
+                                       "nnz": P.nnz_global, "launches_per_step": P.launches_per_step}
+        A3 = P.A
+        i3 = A3.info()
+        run("lap3d_512_csr_product_only", lambda: A3.spmv(P.x, P.y), i3.nnz, i3.algorithmic_bytes)
+        log(f"[bench] lap3d_512_power_1gpu: {out['lap3d_512_power_1gpu']['gflops']:.1f} GFLOP/s ({ms:.3f} ms/iteration)")
+        del P
+        torch.cuda.empty_cache()
+    except Exception as e:  # pragma: no cover
+        out["lap3d_512_power_1gpu"] = {"error": repr(e)}
+        log(f"[bench] lap3d failed: {e!r}")
+    return out
+
+
+def bench_multi_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from sparsematrixvectormultiplication_b200 import device, synth
+    from sparsematrixvectormultiplication_b200.distributed import PowerIteration
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peak, peak_src = measured_peak()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n = args.lap3d_n
+    results = {}
+    for mode in ("halo", "allgather"):
+        P = PowerIteration(synth.SYNTH_LAP3D, n, exchange=mode)
+        P.reset(1.0)
+        steps = args.steps if mode == "halo" else max(3, min(args.steps, 20))
+        ms, per = time_device(P.step, steps, args.warmup, sampler if mode == "halo" else None, world)
+        lam = P.eigenvalue_estimate()
+        recv = P.plan.halo_doubles_received() if mode == "halo" else P.plan.allgather_doubles_received()
+        results[mode] = {"ms_per_step": ms, "gflops": 2.0 * P.nnz_global / (ms * 1e-3) / 1e9, "steps": steps,
+                         "lambda": lam, "rows_local": P.rows, "nnz_local": P.nnz_local, "recv_bytes_per_step": 8 * recv,
+                         "launches_per_step": P.launches_per_step, "nnz_global": P.nnz_global,
+                         "bytes_local": P.algorithmic_bytes_local}
+        if rank == 0:
+            log(f"[bench] {world} GPUs {mode}: {results[mode]['gflops']:.1f} GFLOP/s, {ms:.3f} ms/iteration, lambda={lam:.12g}")
+        # kernel-only product time on this rank (roofline of the dominant kernel)
+        if mode == "halo":
+            kms, kper = time_device(lambda: P.A.spmv(P.x, P.y), max(5, min(args.steps, 50)), 3, None, world)
+            results["product_only_ms"] = kms
+        del P
+        torch.cuda.empty_cache()
+    if sampler:
+        sampler.stop()
+    if rank == 0:
+        h = results["halo"]
+        gbs = h["bytes_local"] / (results["product_only_ms"] * 1e-3) / 1e9
+        line = {"metric": "spmv_gflops", "value": h["gflops"], "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": h["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"lap3d_{n}_power", "rows": n ** 3, "nnz": h["nnz_global"], "format": "csr",
+                           "partition": "contiguous rows balanced by nnz (reference greedy rule)", "exchange": "halo",
+                           "step": "one power iteration: y=Ax, 1-double all-reduce of |y|^2, x=y/|y|, refresh of x",
+                           "l2": "inputs_exceed_l2"},
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                             "peak_source": peak_src, "note": "rank 0's local CSR product alone (max over ranks), algorithmic bytes of its row slice",
+                             "algorithmic_bytes_per_launch": int(h["bytes_local"])},
+                "cpu_baseline": None,
+                "e2e": {"value": h["gflops"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                        "note": "iterated product: x and y never leave the devices between iterations; see the N=1 line for the host-buffer path"},
+                "gpu_launches": h["launches_per_step"] * args.steps, "clocks": sampler.summary() if sampler else None,
+                "exchange_modes": {k: v for k, v in results.items() if isinstance(v, dict)}}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--quick", action="store_true", help="headline only: skip the other single-GPU configs")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--lap3d-n", type=int, default=512)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 or args.gpus > 1:
+        if world == 1:
+            log("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+            sys.exit(2)
+        return bench_multi_gpu(args)
+    return bench_single_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,153 @@
+"""Row-partitioned iterated product (power method, BASELINE.json config 5) over torch.distributed.
+
+One process per GPU.  The matrix is split into contiguous row ranges balanced by nnz with the
+reference's greedy rule (partition.py <- reference src/csr_matrix.c:167-266); every rank keeps its
+rows (global column ids) and a full-length replica of x.  One iteration is
+
+    y_loc = A_loc x ;  s = sum_ranks |y_loc|^2 (1-double all-reduce) ;  x[rows_loc] = y_loc / sqrt(s)
+    refresh of the replicas of x   <- the only data-path exchange
+
+Two refresh strategies, same numerical result (the exchange only copies doubles):
+  * "allgather": every rank receives every other rank's slice (the literal "NCCL allgather of x");
+    slices differ by a few rows, so it is issued as one broadcast per owner;
+  * "halo": a rank receives only the part of x its rows actually reference -- the contiguous column
+    range [min col, max col] of its local matrix -- from the ranks that own it (for the 7-point
+    Laplacian: one n^2 plane from each neighbour instead of the whole vector).
+
+The exchange plan is pure host logic and backend agnostic (NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class ExchangePlan:
+    """Who owns which rows and who needs which columns."""
+    parts: List[Tuple[int, int]]                 # owned row range of every rank
+    needs: List[Tuple[int, int]]                 # referenced column range [lo, hi) of every rank
+    rank: int
+    sends: List[Tuple[int, int, int]] = field(default_factory=list)   # (peer, lo, hi) of MY rows to ship
+    recvs: List[Tuple[int, int, int]] = field(default_factory=list)   # (peer, lo, hi) of THEIR rows I need
+
+    @classmethod
+    def build(cls, parts, needs, rank):
+        plan = cls(list(parts), list(needs), rank)
+        my_lo, my_hi = parts[rank]
+        for peer, (p_lo, p_hi) in enumerate(parts):
+            if peer == rank:
+                continue
+            lo, hi = max(my_lo, needs[peer][0]), min(my_hi, needs[peer][1])   # what the peer needs of mine
+            if hi > lo:
+                plan.sends.append((peer, lo, hi))
+            lo, hi = max(p_lo, needs[rank][0]), min(p_hi, needs[rank][1])     # what I need of the peer's
+            if hi > lo:
+                plan.recvs.append((peer, lo, hi))
+        return plan
+
+    def halo_doubles_received(self) -> int:
+        return sum(hi - lo for _, lo, hi in self.recvs)
+
+    def allgather_doubles_received(self) -> int:
+        return sum(e - s for r, (s, e) in enumerate(self.parts) if r != self.rank)
+
+
+def exchange_allgather(x: torch.Tensor, plan: ExchangePlan, group=None) -> None:
+    """Refresh every replica of x completely: slice p is broadcast by its owner p."""
+    if len(plan.parts) == 1:
+        return
+    works = [dist.broadcast(x[s:e], src=dist.get_global_rank(group, p) if group is not None else p, group=group, async_op=True)
+             for p, (s, e) in enumerate(plan.parts)]
+    for w in works:
+        w.wait()
+
+
+def exchange_halo(x: torch.Tensor, plan: ExchangePlan, group=None) -> None:
+    """Refresh only the referenced column range of every replica (point-to-point)."""
+    ops = []
+    for peer, lo, hi in plan.recvs:
+        ops.append(dist.P2POp(dist.irecv, x[lo:hi], peer, group))
+    for peer, lo, hi in plan.sends:
+        ops.append(dist.P2POp(dist.isend, x[lo:hi], peer, group))
+    if not ops:
+        return
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+
+
+def gather_needs(local_need: Tuple[int, int], world: int, device, group=None) -> List[Tuple[int, int]]:
+    t = torch.tensor(local_need, dtype=torch.int64, device=device)
+    if world == 1:
+        return [tuple(int(v) for v in t.tolist())]
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    return [tuple(int(v) for v in o.tolist()) for o in out]
+
+
+class _CudaView:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class PowerIteration:
+    """Power method on a synthetic matrix, row-partitioned over the ranks of ``group``."""
+
+    def __init__(self, kind, p0, p1=0, p2=0, seed=0x5EED, exchange="halo", group=None, parts=None):
+        import ctypes as C
+
+        from . import _native as N
+        from . import device, partition, synth
+        self.dev = device
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.exchange = exchange
+        self.parts = parts if parts is not None else partition.synth_partition(kind, p0, p1, p2, self.world)
+        if len(self.parts) != self.world:
+            raise ValueError(f"the nnz-balanced partition produced {len(self.parts)} parts for {self.world} ranks")
+        self.row_begin, self.row_end = self.parts[self.rank]
+        self.A = device.DeviceCSR.synth(kind, p0, p1, p2, seed=seed, row_begin=self.row_begin, row_end=self.row_end)
+        info = self.A.info()
+        self.N, self.rows, self.nnz_local = info.N, info.M, info.nnz
+        self.nnz_global = synth.row_offset(kind, p0, p1, p2, self.parts[-1][1])
+        self.algorithmic_bytes_local = info.algorithmic_bytes
+        cu = torch.device("cuda", torch.cuda.current_device())
+        # referenced column range of the local rows
+        ptrs = [C.c_void_p() for _ in range(3)]
+        N.check(N.lib().spmv_b200_csr_device_arrays(self.A._h, *[C.byref(p) for p in ptrs]))
+        if info.nnz:
+            cols = torch.as_tensor(_CudaView(ptrs[1].value, info.nnz, "<i4"), device=cu)
+            lo, hi = torch.aminmax(cols)
+            need = (int(lo.item()), int(hi.item()) + 1)
+        else:
+            need = (self.row_begin, self.row_begin)
+        self.plan = ExchangePlan.build(self.parts, gather_needs(need, self.world, cu, group), self.rank)
+        self.x = torch.ones(self.N, dtype=torch.float64, device=cu)
+        self.y = torch.zeros(max(self.rows, 1), dtype=torch.float64, device=cu)
+        self.ws = torch.empty(device.vec_ws_doubles(), dtype=torch.float64, device=cu)
+        self.ss = torch.zeros(1, dtype=torch.float64, device=cu)
+        self.launches_per_step = 4 + (2 if info.num_long_rows else 0)
+
+    def reset(self, value=1.0):
+        self.dev.vec_fill(self.x, value)
+
+    def step(self):
+        """One iteration; everything is enqueued on the current stream, nothing synchronises the host."""
+        d = self.dev
+        self.A.spmv(self.x, self.y)
+        d.vec_sumsq(self.y, self.ws, self.ss, n=self.rows)
+        if self.world > 1:
+            dist.all_reduce(self.ss, group=self.group)
+        d.vec_scale_by_inv_norm(self.x[self.row_begin:self.row_end], self.y, self.ss, n=self.rows)
+        if self.world > 1:
+            if self.exchange == "allgather":
+                exchange_allgather(self.x, self.plan, self.group)
+            else:
+                exchange_halo(self.x, self.plan, self.group)
+
+    def eigenvalue_estimate(self) -> float:
+        return float(self.ss.item()) ** 0.5

@@ -1,0 +1,377 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (libspmv_b200.so), against the CPU
+oracle on the same inputs, the committed golden vectors, and -- at BASELINE.json's full sizes --
+size-independent properties.
+
+Tolerance (BASELINE.json north_star): y within 1e-12 relative (fp64) of the reference's serial CSR
+product.  Checked in the cancellation-proof componentwise form |dy_i| <= 1e-12 * sum_j |a_ij x_j|
+and, where the data is positive, as the plain |dy_i| / |y_i|.  Index / value arrays: bit-exact.
+Rows reduced by one thread (threads_per_row = 1) must be BIT-IDENTICAL to the serial oracle.
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_names, load_golden, ramp, random_coo
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+def abs_row_sums(checker, rp, ci, va, x):
+    return checker.spmv_csr_serial(rp, ci, np.abs(va), np.abs(x))
+
+
+def assert_close(y, y_ref, scale, what=""):
+    err = np.abs(y - y_ref)
+    bound = TOL * np.maximum(scale, np.finfo(float).tiny)
+    bad = np.nonzero(err > bound)[0]
+    assert bad.size == 0, f"{what}: {bad.size} rows off, first {bad[:5]}, err {err[bad[:5]]}, scale {scale[bad[:5]]}"
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+    from sparsematrixvectormultiplication_b200 import device
+    assert torch.cuda.is_available()
+    assert device.device_count() >= 1
+    torch.cuda.set_device(0)
+    return device
+
+
+def csr_products(dev, A, x, M):
+    """y from every CSR code path: adaptive tiles, forced one-thread-per-row, vector kernel."""
+    import torch
+    out = {}
+    out["auto"] = A.spmv_host(x)
+    xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    yd = torch.full((max(M, 1),), float("nan"), dtype=torch.float64, device="cuda")
+    A.spmv(xd, yd, algo=dev.ALGO_VECTOR)
+    out["vector"] = yd.cpu().numpy()[:M]
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# golden fixtures (BASELINE config 1 among them)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_fixture_products(dev, checker, name):
+    from sparsematrixvectormultiplication_b200 import host
+    g = load_golden(name)
+    pre = host.read_matrix_market(GOLDEN / "mtx" / f"{name}.mtx")
+    csr = host.convert_in_csr(pre)
+    hll = host.convert_to_hll(pre)
+    A = dev.DeviceCSR.from_host(csr)
+    H = dev.DeviceHLL.from_host(hll)
+    for tag, x in (("ones", np.ones(pre.N)), ("ramp", ramp(pre.N))):
+        y_ref = g[f"y_csr_{tag}"]
+        scale = abs_row_sums(checker, g["row_ptr"], g["col_idx"], g["values"], x)
+        for path, y in csr_products(dev, A, x, pre.M).items():
+            assert_close(y, y_ref, scale, f"{name}/{tag}/csr-{path}")
+        A.replan(threads_per_row=1)
+        assert np.array_equal(bits(A.spmv_host(x)), bits(y_ref)), "one thread per row must be bit-exact"
+        A.replan(threads_per_row=0)
+        assert_close(H.spmv_host(x), y_ref, scale, f"{name}/{tag}/hll")
+    # device image -> host round trip reproduces the reference arrays exactly
+    back = H.download()
+    rows, maxnz, offset, JA, AS = back.flat()
+    assert np.array_equal(rows, g["hll_rows"]) and np.array_equal(maxnz, g["hll_maxnz"])
+    assert np.array_equal(JA, g["hll_JA"]) and np.array_equal(bits(AS), bits(g["hll_AS"]))
+    for b in range(back.num_blocks):
+        assert (back.c.blocks[b].MAXNZ == 0) == (not back.c.blocks[b].JA)
+    i = H.info()
+    assert i.num_hacks == len(g["hll_rows"]) and i.nnz_reference_slots == int(g["hll_offset"][-1])
+
+
+def test_config1_fixture_literal(dev):
+    """expected y for general_matrix.mtx with x = 1."""
+    from sparsematrixvectormultiplication_b200 import host
+    pre = host.read_matrix_market(GOLDEN / "mtx" / "general_matrix.mtx")
+    csr = host.convert_in_csr(pre)
+    y = np.zeros(pre.M)
+    host.csr_matrix_vector_mult(csr.M, csr.row_ptr, csr.col_idx, csr.values, np.ones(pre.N), y)
+    expect = np.array([0, 0.49154282666738891, 0, -0.66141388497577847, 0, 0, 0, 0, 0, 0.6136755441817987])
+    assert np.array_equal(y, expect)
+    hll = host.convert_to_hll(pre)
+    yh = np.full(hll.num_blocks * 32, np.nan)
+    host.spmv_hll_serial(hll, np.ones(pre.N), yh)
+    assert np.array_equal(yh[:pre.M], expect)
+
+
+# ---------------------------------------------------------------------------------------------------
+# random matrices: duplicates, empty rows, ragged shapes
+# ---------------------------------------------------------------------------------------------------
+SHAPES = [(1, 1, 1), (1, 50, 40), (50, 1, 30), (31, 33, 200), (32, 32, 0), (33, 64, 500), (64, 64, 64),
+          (257, 100, 3000), (1000, 1000, 20000), (5000, 300, 9000), (777, 5000, 60000)]
+
+
+@pytest.mark.parametrize("M,N,nz", SHAPES)
+@pytest.mark.parametrize("dup", [False, True])
+def test_random_matrices(dev, checker, M, N, nz, dup):
+    from sparsematrixvectormultiplication_b200 import host
+    rng = np.random.default_rng(M * 7919 + N * 31 + nz + dup)
+    coo = random_coo(rng, M, N, nz, dup=dup)
+    pre = host.PreMatrix(M, N, coo.I, coo.J, coo.val)
+    csr = host.convert_in_csr(pre)
+    hll = host.convert_to_hll(pre)
+    x = rng.standard_normal(N)
+    rp, ci, va = checker.coo_to_csr(coo)
+    assert np.array_equal(csr.col_idx, ci) and np.array_equal(bits(csr.values), bits(va))
+    y_ref = checker.spmv_csr_serial(rp, ci, va, x)
+    scale = abs_row_sums(checker, rp, ci, va, x)
+    A = dev.DeviceCSR.from_host(csr)
+    for path, y in csr_products(dev, A, x, M).items():
+        assert_close(y, y_ref, scale, f"csr-{path}")
+    for tile_items, long_threshold in ((64, 8), (128, 100), (4096, 2048)):
+        for tpr in (0, 1, 4, 32):
+            A.replan(tile_items=tile_items, long_threshold=long_threshold, threads_per_row=tpr)
+            y = A.spmv_host(x)
+            assert_close(y, y_ref, scale, f"csr-tiles D={tile_items} L={long_threshold} tpr={tpr}")
+            if tpr == 1 and A.info().num_long_rows == 0:
+                assert np.array_equal(bits(y), bits(y_ref))
+    H = dev.DeviceHLL.from_host(hll)
+    assert_close(H.spmv_host(x), y_ref, scale, "hll")
+    assert_close(H.spmv_host(x), checker.spmv_hll_serial(checker.coo_to_hll(coo), x, M), scale, "hll-vs-hll-serial")
+    if not dup:  # device-side CSR -> HLL equals convert_to_hll for duplicate-free rows
+        H2 = A.to_hll()
+        rows, maxnz, offset, JA, AS = H2.download().flat()
+        h = checker.coo_to_hll(coo)
+        assert np.array_equal(maxnz, h.maxnz) and np.array_equal(JA, h.JA) and np.array_equal(bits(AS), bits(h.AS))
+        assert_close(H2.spmv_host(x), y_ref, scale, "hll-from-csr")
+        assert H2.info().slots == H.info().slots and H2.info().nnz_reference_slots == H.info().nnz_reference_slots
+
+
+def test_skewed_rows_take_the_long_row_path(dev, checker):
+    """One row far above the long-row threshold (split over several CTAs), a few around it, many short."""
+    rng = np.random.default_rng(42)
+    N = 200_000
+    lengths = np.concatenate([[100_000, 1025, 1024, 9000, 0, 8192, 8193], rng.integers(0, 12, 3000)])
+    M = len(lengths)
+    rp = np.zeros(M + 1, np.int32)
+    np.cumsum(lengths, out=rp[1:])
+    ci = np.concatenate([np.sort(rng.choice(N, n, replace=False)) for n in lengths]).astype(np.int32)
+    va = rng.uniform(0.1, 1.0, rp[-1])
+    x = rng.uniform(0.1, 1.0, N)
+    y_ref = checker.spmv_csr_serial(rp, ci, va, x)
+    A = dev.DeviceCSR.upload(M, N, rp, ci, va)
+    info = A.info()
+    assert info.num_long_rows == 5 and info.num_fragments == 13 + 1 + 2 + 1 + 2
+    for path, y in csr_products(dev, A, x, M).items():
+        assert np.max(np.abs(y - y_ref) / y_ref.clip(1e-300)) <= TOL, path
+    y1, y2 = A.spmv_host(x), A.spmv_host(x)
+    assert np.array_equal(bits(y1), bits(y2)), "long-row combine must be run-to-run deterministic"
+    yacc = rng.standard_normal(M)
+    expect = checker.spmv_csr_serial(rp, ci, va, x, y=yacc.copy())
+    got = A.spmv_host(x, y=yacc.copy(), accumulate=True)
+    assert np.max(np.abs(got - expect)) <= TOL * np.max(np.abs(expect))
+
+
+def test_accumulate_is_the_reference_serial_semantics(dev, checker):
+    """y += A x with one thread per row reproduces csr_matrix_vector_mult bit for bit."""
+    rng = np.random.default_rng(8)
+    coo = random_coo(rng, 900, 700, 12000, dup=True)
+    rp, ci, va = checker.coo_to_csr(coo)
+    x, y0 = rng.standard_normal(700), rng.standard_normal(900)
+    expect = checker.spmv_csr_serial(rp, ci, va, x, y=y0.copy())
+    A = dev.DeviceCSR.upload(900, 700, rp, ci, va).replan(threads_per_row=1)
+    assert np.array_equal(bits(A.spmv_host(x, y=y0.copy(), accumulate=True)), bits(expect))
+
+
+@pytest.mark.parametrize("vec", [0, 1, 2, 4, 8, 16, 32])
+def test_plan_free_vector_kernel_on_raw_device_arrays(dev, checker, vec):
+    import torch
+    rng = np.random.default_rng(vec)
+    coo = random_coo(rng, 2000, 1500, 40000, dup=False)
+    rp, ci, va = checker.coo_to_csr(coo)
+    x = rng.standard_normal(1500)
+    t = [torch.from_numpy(a).cuda() for a in (rp, ci, va, x)]
+    y = torch.empty(2000, dtype=torch.float64, device="cuda")
+    dev.csr_spmv_raw(2000, *t, y, threads_per_row=vec)
+    assert_close(y.cpu().numpy(), checker.spmv_csr_serial(rp, ci, va, x), abs_row_sums(checker, rp, ci, va, x))
+    A = dev.DeviceCSR.wrap(2000, 1500, t[0], t[1], t[2])
+    y2 = torch.zeros(2000, dtype=torch.float64, device="cuda")
+    A.spmv(t[3], y2)
+    assert_close(y2.cpu().numpy(), checker.spmv_csr_serial(rp, ci, va, x), abs_row_sums(checker, rp, ci, va, x))
+    y3 = torch.full((2000,), -7.0, dtype=torch.float64, device="cuda")
+    A.spmv_rows(100, 1234, t[3], y3)
+    got = y3.cpu().numpy()
+    assert (got[:100] == -7.0).all() and (got[1234:] == -7.0).all()
+    assert_close(got[100:1234], checker.spmv_csr_serial(rp, ci, va, x)[100:1234],
+                 abs_row_sums(checker, rp, ci, va, x)[100:1234])
+
+
+# ---------------------------------------------------------------------------------------------------
+# drop-in host entry points (reference signatures, GPU inside)
+# ---------------------------------------------------------------------------------------------------
+def test_drop_in_entry_points(dev, checker):
+    from sparsematrixvectormultiplication_b200 import host
+    rng = np.random.default_rng(77)
+    M, N = 1234, 999
+    coo = random_coo(rng, M, N, 30000, dup=True)
+    pre = host.PreMatrix(M, N, coo.I, coo.J, coo.val)
+    csr, hll = host.convert_in_csr(pre), host.convert_to_hll(pre)
+    x = rng.standard_normal(N)
+    rp, ci, va = checker.coo_to_csr(coo)
+    y_ref = checker.spmv_csr_serial(rp, ci, va, x)
+    scale = abs_row_sums(checker, rp, ci, va, x)
+    y0 = rng.standard_normal(M)
+    y = y0.copy()
+    host.csr_matrix_vector_mult(M, csr.row_ptr, csr.col_idx, csr.values, x, y)  # accumulates
+    assert_close(y, y0 + y_ref, scale + np.abs(y0), "csr_matrix_vector_mult")
+    for T in (1, 3, 8):
+        s, e = host.prepare_thread_distribution(M, csr.row_ptr, T, csr.nz)
+        for fn in (host.spvm_csr_parallel, host.spvm_csr_parallel_simd):
+            y = np.full(M, np.nan)
+            fn(csr.row_ptr, csr.col_idx, csr.values, x, y, len(s), s, e)
+            assert_close(y, y_ref, scale, fn.__name__)
+        bs, be = host.prepare_thread_distribution_hll(hll, T)
+        for fn in (host.spmv_hll, host.spmv_hll_simd):
+            y = np.full(hll.num_blocks * 32, np.nan)
+            fn(hll, x, y, len(bs), bs, be)
+            assert_close(y[:M], y_ref, scale, fn.__name__)
+    y = np.full(hll.num_blocks * 32, np.nan)
+    host.spmv_hll_serial(hll, x, y)
+    assert_close(y[:M], y_ref, scale, "spmv_hll_serial")
+    # a range that covers only part of the rows leaves the others untouched (reference semantics)
+    y = np.full(M, -3.0)
+    host.spvm_csr_parallel(csr.row_ptr, csr.col_idx, csr.values, x, y, 1, np.array([100], np.int32), np.array([200], np.int32))
+    assert (y[:100] == -3.0).all() and (y[200:] == -3.0).all()
+    assert_close(y[100:200], y_ref[100:200], scale[100:200], "partial range")
+
+
+# ---------------------------------------------------------------------------------------------------
+# device generators == numpy twins (bit-exact)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,p0,p1,p2", [("lap2d", 37, 0, 0), ("lap2d", 1, 0, 0), ("lap3d", 11, 0, 0), ("lap3d", 2, 0, 0),
+                                           ("uniform", 1000, 4096, 32), ("uniform", 333, 70, 7)])
+def test_device_generators_match_numpy_twins(dev, checker, kind, p0, p1, p2):
+    from sparsematrixvectormultiplication_b200 import synth
+    if kind == "lap2d":
+        k, twin, M = synth.SYNTH_LAP2D, lambda lo, hi: synth.lap2d_csr(p0, lo, hi), p0 * p0
+    elif kind == "lap3d":
+        k, twin, M = synth.SYNTH_LAP3D, lambda lo, hi: synth.lap3d_csr(p0, lo, hi), p0 ** 3
+    else:
+        k, twin, M = synth.SYNTH_UNIFORM, lambda lo, hi: synth.uniform_csr(p0, p1, p2, synth.DEFAULT_SEED, lo, hi), p0
+    for lo, hi in ((0, M), (M // 3, M - M // 5), (M // 2, M // 2)):
+        A = dev.DeviceCSR.synth(k, p0, p1, p2, seed=synth.DEFAULT_SEED, row_begin=lo, row_end=hi)
+        rp, ci, va = A.download()
+        trp, tci, tva = twin(lo, hi)
+        assert np.array_equal(rp, trp) and np.array_equal(ci, tci) and np.array_equal(bits(va), bits(tva))
+        if hi > lo:
+            N = A.info().N
+            x = synth.hash_vector(N, seed=99)
+            assert_close(A.spmv_host(x), checker.spmv_csr_serial(trp, tci, tva, x), abs_row_sums(checker, trp, tci, tva, x))
+
+
+def test_device_vector_generator_and_helpers(dev):
+    import torch
+    from sparsematrixvectormultiplication_b200 import synth
+    n = 1_000_003
+    x = torch.empty(n, dtype=torch.float64, device="cuda")
+    dev.synth_vector(x, 123)
+    xh = synth.hash_vector(n, 123)
+    assert np.array_equal(bits(x.cpu().numpy()), bits(xh))
+    ws = torch.empty(dev.vec_ws_doubles(), dtype=torch.float64, device="cuda")
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    dev.vec_sumsq(x, ws, out)
+    ss = float(out.item())
+    assert abs(ss - float(np.dot(xh, xh))) <= 1e-13 * ss
+    out2 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    dev.vec_sumsq(x, ws, out2)
+    assert out2.item() == ss  # deterministic
+    z = torch.empty_like(x)
+    dev.vec_scale_by_inv_norm(z, x, out)
+    assert np.array_equal(bits(z.cpu().numpy()), bits(xh / np.sqrt(ss)))
+    dev.vec_fill(z, 1.0)
+    assert (z == 1.0).all().item()
+
+
+def test_power_iteration_matches_the_oracle(dev, port):
+    """BASELINE config 5 semantics on a small 3-D Laplacian: y = A x; lambda = |y|; x = y / lambda."""
+    import torch
+    from sparsematrixvectormultiplication_b200 import synth
+    n, iters = 12, 25
+    rp, ci, va = synth.lap3d_csr(n)
+    x_ref, y_ref, lam_ref = port.power_iteration(rp, ci, va, np.ones(n ** 3), iters)
+    A = dev.DeviceCSR.synth(synth.SYNTH_LAP3D, n)
+    x = torch.ones(n ** 3, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    ws = torch.empty(dev.vec_ws_doubles(), dtype=torch.float64, device="cuda")
+    ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    lam = []
+    for _ in range(iters):
+        A.spmv(x, y)
+        dev.vec_sumsq(y, ws, ss)
+        dev.vec_scale_by_inv_norm(x, y, ss)
+        lam.append(float(ss.item()) ** 0.5)
+    assert np.max(np.abs(np.array(lam) - lam_ref) / lam_ref) <= TOL
+    assert np.max(np.abs(x.cpu().numpy() - x_ref)) <= TOL * np.max(np.abs(x_ref))
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: oracle where it finishes in seconds, otherwise properties
+# ---------------------------------------------------------------------------------------------------
+def test_full_size_lap2d_4096(dev, checker):
+    """Config 2: 16.8 M rows, 83.9 M nnz.  x = 1 gives exact small integers; the ramp vector is checked
+    against the serial oracle on the downloaded arrays (about a second of CPU work)."""
+    import torch
+    from sparsematrixvectormultiplication_b200 import synth
+    n = 4096
+    A = dev.DeviceCSR.synth(synth.SYNTH_LAP2D, n)
+    info = A.info()
+    assert (info.M, info.nnz) == (n * n, 83_869_696) and info.algorithmic_bytes == 83_869_696 * 12 + 4 * (n * n + 1) + 16 * n * n
+    rp, ci, va = A.download()
+    assert rp[-1] == info.nnz
+    x = torch.ones(n * n, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    A.spmv(x, y)
+    assert np.array_equal(y.cpu().numpy(), 5.0 - np.diff(rp))  # 4 - (#neighbours), exact
+    xr = ramp(n * n)
+    y_ref = checker.spmv_csr_serial(rp, ci, va, xr)
+    got = A.spmv_host(xr)
+    assert np.max(np.abs(got - y_ref)) <= TOL * 16.0  # |A||x| <= 8 * 1.75
+    A.replan(threads_per_row=1)
+    assert np.array_equal(bits(A.spmv_host(xr)), bits(y_ref)), "one thread per row: bit-exact with the serial loop"
+    H = A.to_hll()
+    hi = H.info()
+    # MAXNZ is 5 everywhere except the hacks of the first and last grid row (4): SURVEY.md section 8(d)
+    assert hi.slots == 5 * n * n - 2 * n and hi.max_maxnz == 5 and hi.num_hacks == n * n // 32
+    yh = H.spmv_host(xr)
+    assert np.max(np.abs(yh - y_ref)) <= TOL * 16.0
+    yv = torch.empty_like(x)
+    A.spmv(torch.from_numpy(xr).cuda(), yv, algo=dev.ALGO_VECTOR)
+    assert np.max(np.abs(yv.cpu().numpy() - y_ref)) <= TOL * 16.0
+
+
+def test_full_size_uniform_8m_properties(dev, checker):
+    """Config 3: 8.4 M x 8.4 M, 32 nnz/row (268 M nnz, 3.2 GB).  CSR, HLL and the vector kernel must agree
+    within tolerance; sampled row windows are checked exactly against the numpy twin + serial oracle."""
+    import torch
+    from sparsematrixvectormultiplication_b200 import synth
+    M = N = 1 << 23
+    A = dev.DeviceCSR.synth(synth.SYNTH_UNIFORM, M, N, 32)
+    H = A.to_hll()
+    assert A.info().nnz == 268_435_456 and H.info().slots == 268_435_456 and H.info().max_maxnz == 32
+    x = torch.empty(N, dtype=torch.float64, device="cuda")
+    dev.synth_vector(x, 4242)
+    y_csr, y_hll, y_vec = (torch.empty(M, dtype=torch.float64, device="cuda") for _ in range(3))
+    A.spmv(x, y_csr)
+    H.spmv(x, y_hll)
+    A.spmv(x, y_vec, algo=dev.ALGO_VECTOR)
+    # all values are positive: plain relative error is well posed
+    assert float(((y_csr - y_hll).abs() / y_csr).max()) <= TOL
+    assert float(((y_csr - y_vec).abs() / y_csr).max()) <= TOL
+    xh = synth.hash_vector(N, 4242)
+    yc = y_csr.cpu().numpy()
+    for lo in (0, 1_234_567, M - 4096):
+        rp, ci, va = synth.uniform_csr(M, N, 32, synth.DEFAULT_SEED, lo, lo + 4096)
+        y_ref = checker.spmv_csr_serial(rp, ci, va, xh)
+        assert np.max(np.abs(yc[lo:lo + 4096] - y_ref) / y_ref) <= TOL
+    # linearity: A(2x) = 2 A x exactly (power-of-two scaling commutes with rounding)
+    x2 = x * 2.0
+    y2 = torch.empty_like(y_csr)
+    A.spmv(x2, y2)
+    assert torch.equal(y2, y_csr * 2.0)
