@@ -339,7 +339,7 @@ def bench_single_gpu(args):
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "rows": M, "cols": info.N, "nnz": nnz, "format": "csr", "x": "1+(i mod 7)/8",
-                       "kernel": "csr_tile_kernel (adaptive row-binned stream kernel)", "tiles": info.num_tiles,
+                       "kernel": "csr_stream_kernel (persistent row-binned kernel, TMA bulk-copy pipeline)", "tiles": info.num_tiles,
                        "l2": "inputs_exceed_l2 (1.34 GB streamed per product vs 126 MB L2)",
                        "step": "one product y = A x, matrix resident in HBM"},
             "roofline": {"bound": "hbm", "achieved": head["gbs"], "peak": peak, "unit": "GB/s", "frac": head["gbs"] / peak,
@@ -372,10 +372,12 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler):
 
     i2 = A2d.info()
     run("lap2d_4096_csr_vector_kernel", lambda: A2d.spmv(x2d, y2d, algo=device.ALGO_VECTOR), i2.nnz, i2.algorithmic_bytes)
+    run("lap2d_4096_csr_tile_kernel_v1", lambda: A2d.spmv(x2d, y2d, algo=device.ALGO_TILE), i2.nnz, i2.algorithmic_bytes)
     try:
         H = A2d.to_hll()
         hi = H.info()
         run("lap2d_4096_hll", lambda: H.spmv(x2d, y2d), i2.nnz, hi.algorithmic_bytes, {"slots": hi.slots})
+        run("lap2d_4096_hll_slice_kernel_v1", lambda: H.spmv(x2d, y2d, slice_kernel=True), i2.nnz, hi.algorithmic_bytes)
         H.close()
     except Exception as e:  # pragma: no cover
         out["lap2d_4096_hll"] = {"error": repr(e)}
@@ -390,9 +392,11 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler):
         ia = A.info()
         run("uniform_8m_32_csr", lambda: A.spmv(x, y), ia.nnz, ia.algorithmic_bytes)
         run("uniform_8m_32_csr_vector_kernel", lambda: A.spmv(x, y, algo=device.ALGO_VECTOR), ia.nnz, ia.algorithmic_bytes)
+        run("uniform_8m_32_csr_tile_kernel_v1", lambda: A.spmv(x, y, algo=device.ALGO_TILE), ia.nnz, ia.algorithmic_bytes)
         H = A.to_hll()
         hi = H.info()
         run("uniform_8m_32_hll", lambda: H.spmv(x, y), ia.nnz, hi.algorithmic_bytes, {"slots": hi.slots})
+        run("uniform_8m_32_hll_slice_kernel_v1", lambda: H.spmv(x, y, slice_kernel=True), ia.nnz, hi.algorithmic_bytes)
         H.close()
         A.close()
         del x, y
@@ -413,6 +417,7 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler):
         y = torch.empty(Mr, dtype=torch.float64, device="cuda")
         extra = {"max_row_nnz": max_row, "long_rows": ia.num_long_rows, "fragments": ia.num_fragments, "tiles": ia.num_tiles}
         run("rmat_24_16_csr", lambda: A.spmv(x, y), ia.nnz, ia.algorithmic_bytes, extra)
+        run("rmat_24_16_csr_tile_kernel_v1", lambda: A.spmv(x, y, algo=device.ALGO_TILE), ia.nnz, ia.algorithmic_bytes)
         run("rmat_24_16_csr_vector_kernel", lambda: A.spmv(x, y, algo=device.ALGO_VECTOR), ia.nnz, ia.algorithmic_bytes)
         A.close()
         del rp, ci, va, x, y

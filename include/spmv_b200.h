@@ -42,9 +42,10 @@ extern "C" {
 #define SPMV_B200_ERR_NOMEM (-4)
 
 /* CSR kernel selection for spmv_b200_csr_spmv */
-#define SPMV_B200_ALGO_AUTO 0     /* adaptive row-binned tile kernel (+ long-row split)      */
+#define SPMV_B200_ALGO_AUTO 0     /* = STREAM                                                */
 #define SPMV_B200_ALGO_VECTOR 1   /* plain vector-per-row kernel with shuffle reduction      */
-#define SPMV_B200_ALGO_TILE 2     /* force the tile kernel                                   */
+#define SPMV_B200_ALGO_TILE 2     /* row-binned tile kernel, one CTA per tile, direct loads  */
+#define SPMV_B200_ALGO_STREAM 3   /* persistent row-binned kernel, TMA bulk-copy pipeline    */
 
 /* synthetic CSR generators (BASELINE.json configs 2, 3, 5) */
 #define SPMV_B200_SYNTH_LAP2D 1   /* p0 = n   : 5-point Laplacian on an n x n grid           */
@@ -128,6 +129,8 @@ int spmv_b200_hll_info(const spmv_b200_hll *H, spmv_b200_hll_info_t *info);
  * free_hll_matrix); round trip of spmv_b200_hll_upload */
 int spmv_b200_hll_download(const spmv_b200_hll *H, HLLMatrix *out);
 int spmv_b200_hll_spmv(const spmv_b200_hll *H, const double *d_x, double *d_y, void *stream);
+/* the same product with the plain one-warp-per-hack slice kernel (no shared-memory pipeline) */
+int spmv_b200_hll_spmv_slice(const spmv_b200_hll *H, const double *d_x, double *d_y, void *stream);
 int spmv_b200_hll_spmv_host(spmv_b200_hll *H, const double *x, double *y);
 /* product restricted to hacks [hack_begin,hack_end) (reference per-thread block ranges,
  * src/hll_matrix.c:376-408) */

@@ -24,12 +24,11 @@
 #include <new>
 
 #include "common.cuh"
+#include "handles.cuh"
 
 namespace spmv {
 
 constexpr int kTileThreads = 256;
-constexpr int kDefaultTileItems = 3072;     // D: rows + nonzeros per tile
-constexpr int kDefaultLongThreshold = 1024; // L: longer rows leave the tile kernel
 constexpr int kFragNnz = 8192;              // nonzeros per long-row fragment (one CTA)
 constexpr int kFragThreads = 256;
 constexpr int kSmemSlack = 8;
@@ -212,8 +211,10 @@ csr_vector_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, c
 }
 
 // ---- plan construction kernels ------------------------------------------------------------------
-// boundary[r] = 1 when row r opens a tile: first row, a new window of D merge items
-// (row_ptr[r] + r counts the rows and nonzeros that precede row r), or a neighbour of / a long row.
+// boundary[r] = 1 when row r opens a tile: first row, a new window of D stream words (every
+// nonzero streams 12 bytes = 3 words, every row 4 bytes = 1 word of row_ptr, so 3*row_ptr[r] + r
+// counts the 4-byte words that precede row r), or a neighbour of / a long row.  All tiles therefore
+// carry (nearly) the same number of bytes, whatever the row lengths.
 __global__ void plan_flag_kernel(int M, const int *__restrict__ row_ptr, int tile_items, int long_threshold,
                                  unsigned char *__restrict__ boundary, unsigned char *__restrict__ is_long) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -224,7 +225,7 @@ __global__ void plan_flag_kernel(int M, const int *__restrict__ row_ptr, int til
     if (r > 0) {
         const int before = row_ptr[r - 1];
         open = open || (a - before > long_threshold);
-        open = open || ((long long)a + r) / tile_items != ((long long)before + r - 1) / tile_items;
+        open = open || (3LL * a + r) / tile_items != (3LL * before + r - 1) / tile_items;
     }
     boundary[r] = open ? 1 : 0;
     is_long[r] = long_here ? 1 : 0;
@@ -255,28 +256,6 @@ __global__ void plan_fragcount_kernel(int num_long, const int *__restrict__ long
 // ================================================================================================
 // handle
 // ================================================================================================
-struct spmv_b200_csr {
-    int M = 0, N = 0;
-    long long nnz = 0;
-    int *row_ptr = nullptr;
-    int *col_idx = nullptr;
-    double *values = nullptr;
-    bool owns = false;
-    // plan
-    int tile_items = spmv::kDefaultTileItems;
-    int long_threshold = spmv::kDefaultLongThreshold;
-    int forced_tpr = 0;
-    int num_tiles = 0;
-    int2 *tiles = nullptr;
-    int num_long = 0;
-    int *long_rows = nullptr;
-    int *frag_first = nullptr;
-    int num_frag = 0;
-    double *frag_partial = nullptr;
-    // staging vectors of the *_host entry points
-    double *stage_x = nullptr;
-    double *stage_y = nullptr;
-};
 
 namespace spmv {
 
@@ -292,8 +271,8 @@ static void free_plan(spmv_b200_csr *A) {
     A->num_tiles = A->num_long = A->num_frag = 0;
 }
 
-static size_t tile_smem_bytes(const spmv_b200_csr *A) {
-    return (size_t)(A->tile_items + A->long_threshold + kSmemSlack) * sizeof(double);
+static size_t tile_smem_bytes(const spmv_b200_csr *A) {  // products of the largest possible tile
+    return (size_t)(A->tile_items / 3 + A->long_threshold + kSmemSlack) * sizeof(double);
 }
 
 static int build_plan(spmv_b200_csr *A, cudaStream_t stream) {
@@ -329,7 +308,7 @@ static int build_plan(spmv_b200_csr *A, cudaStream_t stream) {
 
     // upper bounds that do not need a counting pass
     const long long max_long = A->nnz / ((long long)A->long_threshold + 1) + 1;
-    const long long max_tiles = (A->nnz + M) / A->tile_items + 2 + 2 * max_long;
+    const long long max_tiles = (3 * A->nnz + M) / A->tile_items + 2 + 2 * max_long;
     PLAN_TRY(cudaMalloc(&boundary, (size_t)M));
     PLAN_TRY(cudaMalloc(&is_long, (size_t)M));
     PLAN_TRY(cudaMalloc(&tile_rows, (size_t)std::min<long long>(max_tiles, M) * sizeof(int)));
@@ -383,7 +362,7 @@ static int build_plan(spmv_b200_csr *A, cudaStream_t stream) {
     PLAN_TRY(cudaStreamSynchronize(stream));
 #undef PLAN_TRY
     cleanup();
-    return SPMV_B200_OK;
+    return stream_prepare_csr(A);
 }
 
 static int pick_vector_width(long long nnz, int M) {
@@ -415,11 +394,16 @@ static int launch_vector(int row_begin, int row_end, const int *row_ptr, const i
     return SPMV_B200_OK;
 }
 
-static int launch_tiles(const spmv_b200_csr *A, const double *x, double *y, int accumulate, cudaStream_t stream) {
+static int launch_tiles(const spmv_b200_csr *A, const double *x, double *y, int accumulate, bool pipelined,
+                        cudaStream_t stream) {
     if (A->num_tiles == 0) return SPMV_B200_OK;
-    csr_tile_kernel<<<A->num_tiles, kTileThreads, tile_smem_bytes(A), stream>>>(
-        A->tiles, A->row_ptr, A->col_idx, A->values, x, y, (int)A->nnz, A->long_threshold, A->forced_tpr, accumulate);
-    SPMV_TRY_CUDA(cudaGetLastError());
+    if (pipelined) {
+        SPMV_TRY(stream_launch_csr(A, x, y, accumulate, stream));
+    } else {
+        csr_tile_kernel<<<A->num_tiles, kTileThreads, tile_smem_bytes(A), stream>>>(
+            A->tiles, A->row_ptr, A->col_idx, A->values, x, y, (int)A->nnz, A->long_threshold, A->forced_tpr, accumulate);
+        SPMV_TRY_CUDA(cudaGetLastError());
+    }
     if (A->num_long > 0) {
         csr_long_fragment_kernel<<<A->num_frag, kFragThreads, 0, stream>>>(A->long_rows, A->frag_first, A->num_long,
                                                                           A->row_ptr, A->col_idx, A->values, x,
@@ -497,9 +481,10 @@ int spmv_b200_csr_wrap_device(int M, int N, long long nnz, const int *d_row_ptr,
     *out = nullptr;
     if (M < 0 || N < 0 || nnz < 0 || nnz > 0x7fffffffLL || !d_row_ptr || (nnz > 0 && (!d_col_idx || !d_values)))
         return fail(SPMV_B200_ERR_INVALID, "csr_wrap_device: bad arguments (M=%d N=%d nnz=%lld)", M, N, nnz);
-    if ((reinterpret_cast<uintptr_t>(d_col_idx) & 15) || (reinterpret_cast<uintptr_t>(d_values) & 31))
-        return fail(SPMV_B200_ERR_INVALID, "csr_wrap_device: col_idx must be 16-byte and values 32-byte aligned "
-                                           "(cudaMalloc'ed arrays are)");
+    if ((reinterpret_cast<uintptr_t>(d_col_idx) & 15) || (reinterpret_cast<uintptr_t>(d_values) & 31) ||
+        (reinterpret_cast<uintptr_t>(d_row_ptr) & 15))
+        return fail(SPMV_B200_ERR_INVALID, "csr_wrap_device: row_ptr / col_idx must be 16-byte and values 32-byte "
+                                           "aligned (cudaMalloc'ed arrays are)");
     SPMV_TRY(check_device());
     spmv_b200_csr *A = new (std::nothrow) spmv_b200_csr();
     if (!A) return fail(SPMV_B200_ERR_NOMEM, "csr_wrap_device: out of host memory");
@@ -532,7 +517,7 @@ int spmv_b200_csr_replan(spmv_b200_csr *A, int tile_items, int long_threshold, i
     if (threads_per_row < 0 || threads_per_row > 32 || (threads_per_row & (threads_per_row - 1)))
         return fail(SPMV_B200_ERR_INVALID, "csr_replan: threads_per_row must be 0 or a power of two <= 32");
     if (tile_items < 0 || long_threshold < 0) return fail(SPMV_B200_ERR_INVALID, "csr_replan: negative parameter");
-    if (tile_items > 0) A->tile_items = std::max(tile_items, 64);
+    if (tile_items > 0) A->tile_items = std::max(tile_items, 96);
     if (long_threshold > 0) A->long_threshold = long_threshold;
     A->forced_tpr = threads_per_row;
     return build_plan(A, as_stream(stream));
@@ -575,8 +560,10 @@ int spmv_b200_csr_spmv(const spmv_b200_csr *A, const double *d_x, double *d_y, i
     if (A->M == 0) return SPMV_B200_OK;
     switch (algo) {
         case SPMV_B200_ALGO_AUTO:
+        case SPMV_B200_ALGO_STREAM:
+            return launch_tiles(A, d_x, d_y, accumulate, true, as_stream(stream));
         case SPMV_B200_ALGO_TILE:
-            return launch_tiles(A, d_x, d_y, accumulate, as_stream(stream));
+            return launch_tiles(A, d_x, d_y, accumulate, false, as_stream(stream));
         case SPMV_B200_ALGO_VECTOR:
             return launch_vector(0, A->M, A->row_ptr, A->col_idx, A->values, d_x, d_y, pick_vector_width(A->nnz, A->M),
                                  accumulate, as_stream(stream));

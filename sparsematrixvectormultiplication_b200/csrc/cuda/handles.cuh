@@ -1,0 +1,77 @@
+// handles.cuh -- the opaque handle types of include/spmv_b200.h (internal layout).
+#pragma once
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace spmv {
+
+constexpr int kDefaultTileItems = 12288;    // D: 4-byte stream words per CSR tile (3 per nonzero + 1 per row) = 48 KB
+constexpr int kDefaultLongThreshold = 512;  // L: longer rows leave the tile kernels
+constexpr int kDefaultStages = 2;           // TMA pipeline depth of the stream kernels
+constexpr int kHllTileSlots = 3072;         // D_h: slots + rows per HLL tile (12 B per slot; stage = 49.5 KB with the wide margin)
+constexpr int kHllWideSlots = 1024;         // hacks with more slots (MAXNZ > 32) are processed straight from HBM
+
+struct HllTile {      // tiles[t] = first hack of tile t and its first slot; tiles[num_tiles] = {num_hacks, slots}
+    int hack;
+    int pad;
+    long long slot;
+};
+
+}  // namespace spmv
+
+struct spmv_b200_csr {
+    int M = 0, N = 0;
+    long long nnz = 0;
+    int *row_ptr = nullptr;
+    int *col_idx = nullptr;
+    double *values = nullptr;
+    bool owns = false;
+    // plan (shared by the tile kernel and the TMA stream kernel)
+    int tile_items = spmv::kDefaultTileItems;
+    int long_threshold = spmv::kDefaultLongThreshold;
+    int forced_tpr = 0;
+    int num_tiles = 0;
+    int2 *tiles = nullptr;
+    int num_long = 0;
+    int *long_rows = nullptr;
+    int *frag_first = nullptr;
+    int num_frag = 0;
+    double *frag_partial = nullptr;
+    // stream kernel launch shape
+    int stages = spmv::kDefaultStages;
+    int consumers = 12;
+    int stream_grid = 0;
+    // staging vectors of the *_host entry points
+    double *stage_x = nullptr;
+    double *stage_y = nullptr;
+};
+
+struct spmv_b200_hll {
+    int M = 0, N = 0, num_hacks = 0, max_width = 0;
+    long long slots = 0, ref_slots = 0;
+    long long *hack_off = nullptr;  // device [num_hacks+1]
+    int *JA = nullptr;              // device [slots]
+    double *AS = nullptr;           // device [slots]
+    std::vector<long long> host_off;
+    // stream kernel plan
+    int tile_slots = spmv::kHllTileSlots;
+    int wide_slots = spmv::kHllWideSlots;
+    int stages = spmv::kDefaultStages;
+    int consumers = 12;
+    int num_tiles = 0;
+    spmv::HllTile *tiles = nullptr;
+    int stream_grid = 0;
+    double *stage_x = nullptr;
+    double *stage_y = nullptr;
+};
+
+namespace spmv {
+// stream.cu
+int stream_prepare_csr(spmv_b200_csr *A);
+int stream_launch_csr(const spmv_b200_csr *A, const double *x, double *y, int accumulate, cudaStream_t stream);
+int stream_plan_hll(spmv_b200_hll *H, cudaStream_t stream);
+int stream_launch_hll(const spmv_b200_hll *H, const double *x, double *y, cudaStream_t stream);
+int env_int(const char *name, int fallback);
+}  // namespace spmv

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "handles.cuh"
 
 namespace spmv {
 
@@ -130,16 +131,6 @@ __global__ void max_int_kernel(const int *__restrict__ v, int n, int *__restrict
 
 }  // namespace spmv
 
-struct spmv_b200_hll {
-    int M = 0, N = 0, num_hacks = 0, max_width = 0;
-    long long slots = 0, ref_slots = 0;
-    long long *hack_off = nullptr;  // device [num_hacks+1]
-    int *JA = nullptr;              // device [slots]
-    double *AS = nullptr;           // device [slots]
-    std::vector<long long> host_off;
-    double *stage_x = nullptr;
-    double *stage_y = nullptr;
-};
 
 // csr.cu
 extern "C" int spmv_b200_csr_device_arrays(const spmv_b200_csr *A, const int **d_row_ptr, const int **d_col_idx,
@@ -225,6 +216,7 @@ int spmv_b200_hll_upload(const HLLMatrix *hll, int M, int N, spmv_b200_hll **out
             return SPMV_B200_OK;
         };
         rc = dev();
+        if (rc == SPMV_B200_OK) rc = stream_plan_hll(H, nullptr);
     }
     std::free(ja);
     std::free(as);
@@ -287,7 +279,7 @@ int spmv_b200_hll_from_csr(const spmv_b200_csr *A, void *stream_, spmv_b200_hll 
             SPMV_TRY_CUDA(cudaGetLastError());
         }
         SPMV_TRY_CUDA(cudaStreamSynchronize(stream));
-        return SPMV_B200_OK;
+        return stream_plan_hll(H, stream);
     };
     int rc = body();
     cudaFree(slots);
@@ -381,6 +373,11 @@ int spmv_b200_hll_download(const spmv_b200_hll *H, HLLMatrix *out) {
 
 int spmv_b200_hll_spmv(const spmv_b200_hll *H, const double *d_x, double *d_y, void *stream) {
     if (!H || !d_y || (H->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "hll_spmv: NULL argument");
+    return stream_launch_hll(H, d_x, d_y, as_stream(stream));
+}
+
+int spmv_b200_hll_spmv_slice(const spmv_b200_hll *H, const double *d_x, double *d_y, void *stream) {
+    if (!H || !d_y || (H->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_slice: NULL argument");
     return hll_launch(H, 0, H->num_hacks, d_x, d_y, as_stream(stream));
 }
 
@@ -397,7 +394,7 @@ int spmv_b200_hll_spmv_host(spmv_b200_hll *H, const double *x, double *y) {
     if (!H->stage_x) SPMV_TRY_CUDA(cudaMalloc(&H->stage_x, std::max<size_t>(H->N, 1) * sizeof(double)));
     if (!H->stage_y) SPMV_TRY_CUDA(cudaMalloc(&H->stage_y, std::max<size_t>(H->M, 1) * sizeof(double)));
     if (H->N) SPMV_TRY_CUDA(cudaMemcpyAsync(H->stage_x, x, (size_t)H->N * sizeof(double), cudaMemcpyHostToDevice, nullptr));
-    SPMV_TRY(hll_launch(H, 0, H->num_hacks, H->stage_x, H->stage_y, nullptr));
+    SPMV_TRY(stream_launch_hll(H, H->stage_x, H->stage_y, nullptr));
     if (H->M) SPMV_TRY_CUDA(cudaMemcpyAsync(y, H->stage_y, (size_t)H->M * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
     SPMV_TRY_CUDA(cudaStreamSynchronize(nullptr));
     return SPMV_B200_OK;
@@ -405,6 +402,7 @@ int spmv_b200_hll_spmv_host(spmv_b200_hll *H, const double *x, double *y) {
 
 void spmv_b200_hll_free(spmv_b200_hll *H) {
     if (!H) return;
+    cudaFree(H->tiles);
     cudaFree(H->hack_off);
     cudaFree(H->JA);
     cudaFree(H->AS);

@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _native as N
 
-ALGO_AUTO, ALGO_VECTOR, ALGO_TILE = 0, 1, 2
+ALGO_AUTO, ALGO_VECTOR, ALGO_TILE, ALGO_STREAM = 0, 1, 2, 3
 SYNTH_LAP2D, SYNTH_LAP3D, SYNTH_UNIFORM = 1, 2, 3
 
 
@@ -200,11 +200,13 @@ class DeviceHLL:
         out.rows_total, out.cols = i.M, i.N
         return out
 
-    def spmv(self, x, y, stream=None):
+    def spmv(self, x, y, stream=None, slice_kernel=False):
+        """y = A x; slice_kernel=True uses the plain one-warp-per-hack kernel instead of the TMA pipeline."""
         i = self.info()
         _check_vec(x, i.N, "x")
         _check_vec(y, i.M, "y")
-        N.check(N.lib().spmv_b200_hll_spmv(self._h, _ptr(x), _ptr(y), _stream(stream)))
+        fn = N.lib().spmv_b200_hll_spmv_slice if slice_kernel else N.lib().spmv_b200_hll_spmv
+        N.check(fn(self._h, _ptr(x), _ptr(y), _stream(stream)))
         return y
 
     def spmv_hacks(self, hack_begin, hack_end, x, y, stream=None):

@@ -43,14 +43,27 @@ def dev():
 
 
 def csr_products(dev, A, x, M):
-    """y from every CSR code path: adaptive tiles, forced one-thread-per-row, vector kernel."""
+    """y from every CSR code path: TMA stream kernel (default), direct tile kernel, vector kernel."""
     import torch
     out = {}
-    out["auto"] = A.spmv_host(x)
+    out["stream-host"] = A.spmv_host(x)
     xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
-    yd = torch.full((max(M, 1),), float("nan"), dtype=torch.float64, device="cuda")
-    A.spmv(xd, yd, algo=dev.ALGO_VECTOR)
-    out["vector"] = yd.cpu().numpy()[:M]
+    for name, algo in (("stream", dev.ALGO_STREAM), ("tile", dev.ALGO_TILE), ("vector", dev.ALGO_VECTOR)):
+        yd = torch.full((max(M, 1),), float("nan"), dtype=torch.float64, device="cuda")
+        A.spmv(xd, yd, algo=algo)
+        out[name] = yd.cpu().numpy()[:M]
+    return out
+
+
+def hll_products(dev, H, x, M):
+    """y from both HLL kernels: TMA stream kernel (default) and the plain one-warp-per-hack slice kernel."""
+    import torch
+    out = {"stream-host": H.spmv_host(x)}
+    xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    for name, flag in (("stream", False), ("slice", True)):
+        yd = torch.full((max(M, 1),), float("nan"), dtype=torch.float64, device="cuda")
+        H.spmv(xd, yd, slice_kernel=flag)
+        out[name] = yd.cpu().numpy()[:M]
     return out
 
 
@@ -74,7 +87,10 @@ def test_golden_fixture_products(dev, checker, name):
         A.replan(threads_per_row=1)
         assert np.array_equal(bits(A.spmv_host(x)), bits(y_ref)), "one thread per row must be bit-exact"
         A.replan(threads_per_row=0)
-        assert_close(H.spmv_host(x), y_ref, scale, f"{name}/{tag}/hll")
+        for path, y in hll_products(dev, H, x, pre.M).items():
+            assert_close(y, y_ref, scale, f"{name}/{tag}/hll-{path}")
+        if H.info().max_maxnz <= 32:  # hacks wider than 32 columns take the split "wide hack" path (tolerance only)
+            assert np.array_equal(bits(H.spmv_host(x)), bits(g[f"y_hll_{tag}"])), "stream kernel sums each row in serial order"
     # device image -> host round trip reproduces the reference arrays exactly
     back = H.download()
     rows, maxnz, offset, JA, AS = back.flat()
@@ -133,8 +149,12 @@ def test_random_matrices(dev, checker, M, N, nz, dup):
             if tpr == 1 and A.info().num_long_rows == 0:
                 assert np.array_equal(bits(y), bits(y_ref))
     H = dev.DeviceHLL.from_host(hll)
-    assert_close(H.spmv_host(x), y_ref, scale, "hll")
-    assert_close(H.spmv_host(x), checker.spmv_hll_serial(checker.coo_to_hll(coo), x, M), scale, "hll-vs-hll-serial")
+    y_hll_ref = checker.spmv_hll_serial(checker.coo_to_hll(coo), x, M)
+    for path, y in hll_products(dev, H, x, M).items():
+        assert_close(y, y_ref, scale, f"hll-{path}")
+        assert_close(y, y_hll_ref, scale, f"hll-{path}-vs-hll-serial")
+    if H.info().max_maxnz <= 32:  # no "wide hack" path: every row is summed in the serial order
+        assert np.array_equal(bits(H.spmv_host(x)), bits(y_hll_ref))
     if not dup:  # device-side CSR -> HLL equals convert_to_hll for duplicate-free rows
         H2 = A.to_hll()
         rows, maxnz, offset, JA, AS = H2.download().flat()
@@ -157,6 +177,7 @@ def test_skewed_rows_take_the_long_row_path(dev, checker):
     x = rng.uniform(0.1, 1.0, N)
     y_ref = checker.spmv_csr_serial(rp, ci, va, x)
     A = dev.DeviceCSR.upload(M, N, rp, ci, va)
+    A.replan(long_threshold=1024)
     info = A.info()
     assert info.num_long_rows == 5 and info.num_fragments == 13 + 1 + 2 + 1 + 2
     for path, y in csr_products(dev, A, x, M).items():
@@ -340,7 +361,13 @@ def test_full_size_lap2d_4096(dev, checker):
     # MAXNZ is 5 everywhere except the hacks of the first and last grid row (4): SURVEY.md section 8(d)
     assert hi.slots == 5 * n * n - 2 * n and hi.max_maxnz == 5 and hi.num_hacks == n * n // 32
     yh = H.spmv_host(xr)
-    assert np.max(np.abs(yh - y_ref)) <= TOL * 16.0
+    assert np.array_equal(bits(yh), bits(y_ref)), "HLL stream kernel sums every row in serial order (padding adds 0.0)"
+    xd = torch.from_numpy(xr).cuda()
+    ys = torch.empty_like(x)
+    H.spmv(xd, ys, slice_kernel=True)
+    assert np.max(np.abs(ys.cpu().numpy() - y_ref)) <= TOL * 16.0
+    A.spmv(xd, ys, algo=dev.ALGO_TILE)
+    assert np.array_equal(bits(ys.cpu().numpy()), bits(y_ref))
     yv = torch.empty_like(x)
     A.spmv(torch.from_numpy(xr).cuda(), yv, algo=dev.ALGO_VECTOR)
     assert np.max(np.abs(yv.cpu().numpy() - y_ref)) <= TOL * 16.0
@@ -361,6 +388,11 @@ def test_full_size_uniform_8m_properties(dev, checker):
     A.spmv(x, y_csr)
     H.spmv(x, y_hll)
     A.spmv(x, y_vec, algo=dev.ALGO_VECTOR)
+    y_alt = torch.empty_like(y_csr)
+    H.spmv(x, y_alt, slice_kernel=True)
+    assert float(((y_hll - y_alt).abs() / y_hll).max()) <= TOL
+    A.spmv(x, y_alt, algo=dev.ALGO_TILE)
+    assert float(((y_csr - y_alt).abs() / y_csr).max()) <= TOL
     # all values are positive: plain relative error is well posed
     assert float(((y_csr - y_hll).abs() / y_csr).max()) <= TOL
     assert float(((y_csr - y_vec).abs() / y_csr).max()) <= TOL
