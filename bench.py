@@ -370,17 +370,28 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler):
             out[name] = {"error": repr(e)}
             log(f"[bench] {name} failed: {e!r}")
 
-    i2 = A2d.info()
-    run("lap2d_4096_csr_vector_kernel", lambda: A2d.spmv(x2d, y2d, algo=device.ALGO_VECTOR), i2.nnz, i2.algorithmic_bytes)
-    run("lap2d_4096_csr_tile_kernel_v1", lambda: A2d.spmv(x2d, y2d, algo=device.ALGO_TILE), i2.nnz, i2.algorithmic_bytes)
-    try:
-        H = A2d.to_hll()
+    def csr_variants(name, A, x, y, with_auto=True):
+        ia = A.info()
+        if with_auto:
+            run(f"{name}_csr", lambda: A.spmv(x, y), ia.nnz, ia.algorithmic_bytes, {"kernel": "automatic choice"})
+        run(f"{name}_csr_stream_kernel", lambda: A.spmv(x, y, algo=device.ALGO_STREAM), ia.nnz, ia.algorithmic_bytes)
+        run(f"{name}_csr_tile_kernel", lambda: A.spmv(x, y, algo=device.ALGO_TILE), ia.nnz, ia.algorithmic_bytes)
+        run(f"{name}_csr_vector_kernel", lambda: A.spmv(x, y, algo=device.ALGO_VECTOR), ia.nnz, ia.algorithmic_bytes)
+
+    def hll_variants(name, A, x, y):
+        ia = A.info()
+        H = A.to_hll()
         hi = H.info()
-        run("lap2d_4096_hll", lambda: H.spmv(x2d, y2d), i2.nnz, hi.algorithmic_bytes, {"slots": hi.slots})
-        run("lap2d_4096_hll_slice_kernel_v1", lambda: H.spmv(x2d, y2d, slice_kernel=True), i2.nnz, hi.algorithmic_bytes)
+        run(f"{name}_hll", lambda: H.spmv(x, y), ia.nnz, hi.algorithmic_bytes, {"slots": hi.slots, "kernel": "automatic choice"})
+        run(f"{name}_hll_stream_kernel", lambda: H.spmv(x, y, slice_kernel=False), ia.nnz, hi.algorithmic_bytes)
+        run(f"{name}_hll_slice_kernel", lambda: H.spmv(x, y, slice_kernel=True), ia.nnz, hi.algorithmic_bytes)
         H.close()
+
+    try:
+        csr_variants("lap2d_4096", A2d, x2d, y2d, with_auto=False)
+        hll_variants("lap2d_4096", A2d, x2d, y2d)
     except Exception as e:  # pragma: no cover
-        out["lap2d_4096_hll"] = {"error": repr(e)}
+        out["lap2d_4096_variants"] = {"error": repr(e)}
 
     # config 3: uniform 8M x 8M, 32 nnz/row, CSR vs HLL hack 32
     try:
@@ -389,15 +400,8 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler):
         x = torch.empty(M, dtype=torch.float64, device="cuda")
         device.synth_vector(x, 4242)
         y = torch.empty(M, dtype=torch.float64, device="cuda")
-        ia = A.info()
-        run("uniform_8m_32_csr", lambda: A.spmv(x, y), ia.nnz, ia.algorithmic_bytes)
-        run("uniform_8m_32_csr_vector_kernel", lambda: A.spmv(x, y, algo=device.ALGO_VECTOR), ia.nnz, ia.algorithmic_bytes)
-        run("uniform_8m_32_csr_tile_kernel_v1", lambda: A.spmv(x, y, algo=device.ALGO_TILE), ia.nnz, ia.algorithmic_bytes)
-        H = A.to_hll()
-        hi = H.info()
-        run("uniform_8m_32_hll", lambda: H.spmv(x, y), ia.nnz, hi.algorithmic_bytes, {"slots": hi.slots})
-        run("uniform_8m_32_hll_slice_kernel_v1", lambda: H.spmv(x, y, slice_kernel=True), ia.nnz, hi.algorithmic_bytes)
-        H.close()
+        csr_variants("uniform_8m_32", A, x, y)
+        hll_variants("uniform_8m_32", A, x, y)
         A.close()
         del x, y
     except Exception as e:  # pragma: no cover
@@ -415,10 +419,10 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler):
         x = torch.empty(Mr, dtype=torch.float64, device="cuda")
         device.synth_vector(x, 777)
         y = torch.empty(Mr, dtype=torch.float64, device="cuda")
-        extra = {"max_row_nnz": max_row, "long_rows": ia.num_long_rows, "fragments": ia.num_fragments, "tiles": ia.num_tiles}
-        run("rmat_24_16_csr", lambda: A.spmv(x, y), ia.nnz, ia.algorithmic_bytes, extra)
-        run("rmat_24_16_csr_tile_kernel_v1", lambda: A.spmv(x, y, algo=device.ALGO_TILE), ia.nnz, ia.algorithmic_bytes)
-        run("rmat_24_16_csr_vector_kernel", lambda: A.spmv(x, y, algo=device.ALGO_VECTOR), ia.nnz, ia.algorithmic_bytes)
+        csr_variants("rmat_24_16", A, x, y)
+        if "rmat_24_16_csr" in out and "error" not in out["rmat_24_16_csr"]:
+            out["rmat_24_16_csr"].update({"max_row_nnz": max_row, "long_rows": ia.num_long_rows,
+                                          "fragments": ia.num_fragments, "tiles": ia.num_tiles})
         A.close()
         del rp, ci, va, x, y
         torch.cuda.empty_cache()

@@ -42,7 +42,7 @@ extern "C" {
 #define SPMV_B200_ERR_NOMEM (-4)
 
 /* CSR kernel selection for spmv_b200_csr_spmv */
-#define SPMV_B200_ALGO_AUTO 0     /* = STREAM                                                */
+#define SPMV_B200_ALGO_AUTO 0     /* STREAM for short rows (<= 12 nnz/row on average), else TILE */
 #define SPMV_B200_ALGO_VECTOR 1   /* plain vector-per-row kernel with shuffle reduction      */
 #define SPMV_B200_ALGO_TILE 2     /* row-binned tile kernel, one CTA per tile, direct loads  */
 #define SPMV_B200_ALGO_STREAM 3   /* persistent row-binned kernel, TMA bulk-copy pipeline    */
@@ -129,8 +129,11 @@ int spmv_b200_hll_info(const spmv_b200_hll *H, spmv_b200_hll_info_t *info);
  * free_hll_matrix); round trip of spmv_b200_hll_upload */
 int spmv_b200_hll_download(const spmv_b200_hll *H, HLLMatrix *out);
 int spmv_b200_hll_spmv(const spmv_b200_hll *H, const double *d_x, double *d_y, void *stream);
-/* the same product with the plain one-warp-per-hack slice kernel (no shared-memory pipeline) */
+/* spmv_b200_hll_spmv picks between the two kernels below from the mean hack width */
+/* one-warp-per-hack slice kernel, 128/256-bit loads straight from HBM */
 int spmv_b200_hll_spmv_slice(const spmv_b200_hll *H, const double *d_x, double *d_y, void *stream);
+/* persistent TMA bulk-copy pipeline (shared-memory staging) */
+int spmv_b200_hll_spmv_stream(const spmv_b200_hll *H, const double *d_x, double *d_y, void *stream);
 int spmv_b200_hll_spmv_host(spmv_b200_hll *H, const double *x, double *y);
 /* product restricted to hacks [hack_begin,hack_end) (reference per-thread block ranges,
  * src/hll_matrix.c:376-408) */

@@ -97,6 +97,7 @@ SIGNATURES = {
     "spmv_b200_hll_download": (_I, [_V, C.POINTER(HLLMatrixStruct)]),
     "spmv_b200_hll_spmv": (_I, [_V, _V, _V, _V]),
     "spmv_b200_hll_spmv_slice": (_I, [_V, _V, _V, _V]),
+    "spmv_b200_hll_spmv_stream": (_I, [_V, _V, _V, _V]),
     "spmv_b200_hll_spmv_host": (_I, [_V, _V, _V]),
     "spmv_b200_hll_spmv_hacks": (_I, [_V, _I, _I, _V, _V, _V]),
     "spmv_b200_hll_free": (None, [_V]),

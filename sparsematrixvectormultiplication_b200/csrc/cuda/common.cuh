@@ -81,6 +81,34 @@ __device__ __forceinline__ int ldg_stream_s32(const int *p) {
 // banded matrices hit the same lines.
 __device__ __forceinline__ double ldg_x(const double *x, int col) { return __ldg(x + col); }
 
+// ---- per-row sums of products parked in shared memory, one warp per chunk of 32 rows ---------------
+constexpr int kLaneRowMax = 64;  // rows up to this length are summed by their own lane, longer ones by the whole warp
+
+// Lane = row [lo, hi) of prod[].  Short rows start at a lane-dependent element and wrap around, so equally long
+// rows (stride = row length) do not pile up on one shared-memory bank; rows longer than kLaneRowMax are summed
+// by all 32 lanes followed by a fixed xor tree.  Every lane of the warp must call this (it shuffles).
+__device__ __forceinline__ double chunk_row_sum(const double *prod, int lo, int hi, int lane) {
+    const int len = hi - lo;
+    double acc = 0.0;
+    if (len <= kLaneRowMax && len > 0) {
+        const int start = lo + lane % len;
+        for (int k = start; k < hi; ++k) acc = __dadd_rn(acc, prod[k]);
+        for (int k = lo; k < start; ++k) acc = __dadd_rn(acc, prod[k]);
+    }
+    unsigned wide = __ballot_sync(0xffffffffu, len > kLaneRowMax);
+    while (wide) {
+        const int owner = __ffs(wide) - 1;
+        wide &= wide - 1;
+        const int wlo = __shfl_sync(0xffffffffu, lo, owner), whi = __shfl_sync(0xffffffffu, hi, owner);
+        double part = 0.0;
+        for (int k = wlo + lane; k < whi; k += 32) part = __dadd_rn(part, prod[k]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part = __dadd_rn(part, __shfl_xor_sync(0xffffffffu, part, off));
+        if (lane == owner) acc = part;
+    }
+    return acc;
+}
+
 // ---- counter-based hash shared by the device generators and their numpy twins -----------------
 __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;

@@ -29,6 +29,7 @@
 namespace spmv {
 
 constexpr int kTileThreads = 256;
+constexpr int kAutoStreamMaxAvg = 12;  // ALGO_AUTO: stream kernel up to this many nonzeros per row on average
 constexpr int kFragNnz = 8192;              // nonzeros per long-row fragment (one CTA)
 constexpr int kFragThreads = 256;
 constexpr int kSmemSlack = 8;
@@ -59,7 +60,7 @@ __device__ __forceinline__ void group_products(const int *__restrict__ col_idx, 
 }
 
 // tiles[t] = {first row of tile t, row_ptr[first row]}, tiles[num_tiles] = {M, nnz}.
-// forced_tpr: 0 = pick the reduction width per tile from its row count, else 1,2,4,...,32.
+// forced_tpr: 1 = one thread per row in the reference's order; anything else = warp per 32-row chunk.
 __global__ void __launch_bounds__(kTileThreads, 4)
 csr_tile_kernel(const int2 *__restrict__ tiles, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
                 const double *__restrict__ values, const double *__restrict__ x, double *__restrict__ y,
@@ -72,20 +73,10 @@ csr_tile_kernel(const int2 *__restrict__ tiles, const int *__restrict__ row_ptr,
     const int n0 = head.y, n1 = tail.y;
     if (rows == 1 && n1 - n0 > long_threshold) return;  // long row: csr_long_* kernels own it
 
-    // reduction width for this tile (power of two)
-    int tpr = forced_tpr;
-    if (tpr == 0) {
-        tpr = 1;
-        while (tpr < 32 && rows * tpr * 2 <= kTileThreads) tpr *= 2;
-    }
-    const int tpr_log = 31 - __clz(tpr);
-    const int rows_per_pass = kTileThreads >> tpr_log;
-    const int sub = tid & (tpr - 1);
-
-    // row bounds of this thread's first row: issued now, consumed after the barrier
-    int my_row = tid >> tpr_log;
+    // row bounds of this thread's first row (one-thread-per-row mode): issued now, consumed after the barrier
+    int my_row = tid;
     int seg_lo = 0, seg_hi = 0;
-    if (my_row < rows) {
+    if (forced_tpr == 1 && my_row < rows) {
         seg_lo = __ldg(row_ptr + r0 + my_row);
         seg_hi = __ldg(row_ptr + r0 + my_row + 1);
     }
@@ -115,10 +106,10 @@ csr_tile_kernel(const int2 *__restrict__ tiles, const int *__restrict__ row_ptr,
     __syncthreads();
 
     // ---- phase B: per-row reduction out of shared memory ---------------------------------------
-    if (tpr == 1) {
+    if (forced_tpr == 1) {  // one thread per row, left to right: bit-identical to the reference's serial loop
         for (; my_row < rows; my_row += kTileThreads) {
             double acc = accumulate ? y[r0 + my_row] : 0.0;
-            for (int k = seg_lo - a0; k < seg_hi - a0; ++k) acc = __dadd_rn(acc, prod[k]);  // left to right
+            for (int k = seg_lo - a0; k < seg_hi - a0; ++k) acc = __dadd_rn(acc, prod[k]);
             y[r0 + my_row] = acc;
             const int next = my_row + kTileThreads;
             if (next < rows) {
@@ -126,20 +117,17 @@ csr_tile_kernel(const int2 *__restrict__ tiles, const int *__restrict__ row_ptr,
                 seg_hi = __ldg(row_ptr + r0 + next + 1);
             }
         }
-    } else {
-        // all 32 lanes of a warp take part in every shuffle: iterate on a warp-uniform bound
-        for (int base = 0; base < rows; base += rows_per_pass) {
-            const int row = base + (tid >> tpr_log);
-            double acc = 0.0;
-            if (row < rows) {
-                if (base != 0) {
-                    seg_lo = __ldg(row_ptr + r0 + row);
-                    seg_hi = __ldg(row_ptr + r0 + row + 1);
-                }
-                for (int k = seg_lo - a0 + sub; k < seg_hi - a0; k += tpr) acc = __dadd_rn(acc, prod[k]);
+    } else {  // one warp per chunk of 32 rows (common.cuh: chunk_row_sum)
+        const int lane = tid & 31;
+        for (int c = tid >> 5; c * 32 < rows; c += kTileThreads / 32) {
+            const int lr = c * 32 + lane;
+            int lo = 0, hi = 0;
+            if (lr < rows) {
+                lo = __ldg(row_ptr + r0 + lr) - a0;
+                hi = __ldg(row_ptr + r0 + lr + 1) - a0;
             }
-            for (int off = tpr >> 1; off > 0; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
-            if (row < rows && sub == 0) y[r0 + row] = accumulate ? __dadd_rn(y[r0 + row], acc) : acc;
+            const double acc = chunk_row_sum(prod, lo, hi, lane);
+            if (lr < rows) y[r0 + lr] = accumulate ? __dadd_rn(y[r0 + lr], acc) : acc;
         }
     }
 }
@@ -560,6 +548,17 @@ int spmv_b200_csr_spmv(const spmv_b200_csr *A, const double *d_x, double *d_y, i
     if (A->M == 0) return SPMV_B200_OK;
     switch (algo) {
         case SPMV_B200_ALGO_AUTO:
+            // Short rows (stencils): the TMA stream kernel runs at the HBM roofline.  Longer rows mean many
+            // gathers of x per streamed byte, bounded by L2 sector throughput and by the latency of gathers that
+            // miss L2: those need the occupancy of the direct-load kernels -- vector-per-row when no row is long,
+            // the row-binned tile kernel (+ long-row split) when the lengths are skewed.  Measured on B200:
+            // profiles/r01b_kernel_selection.md.
+            if (A->nnz <= (long long)kAutoStreamMaxAvg * A->M)
+                return launch_tiles(A, d_x, d_y, accumulate, true, as_stream(stream));
+            if (A->num_long == 0)
+                return launch_vector(0, A->M, A->row_ptr, A->col_idx, A->values, d_x, d_y,
+                                     pick_vector_width(A->nnz, A->M), accumulate, as_stream(stream));
+            return launch_tiles(A, d_x, d_y, accumulate, false, as_stream(stream));
         case SPMV_B200_ALGO_STREAM:
             return launch_tiles(A, d_x, d_y, accumulate, true, as_stream(stream));
         case SPMV_B200_ALGO_TILE:

@@ -371,8 +371,17 @@ int spmv_b200_hll_download(const spmv_b200_hll *H, HLLMatrix *out) {
     return SPMV_B200_OK;
 }
 
+// narrow hacks (stencils): TMA stream kernel; wide hacks are gather bound and need the occupancy of the slice kernel
+static bool hll_prefers_stream(const spmv_b200_hll *H) { return H->slots <= 12LL * 32 * H->num_hacks; }
+
 int spmv_b200_hll_spmv(const spmv_b200_hll *H, const double *d_x, double *d_y, void *stream) {
     if (!H || !d_y || (H->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "hll_spmv: NULL argument");
+    if (hll_prefers_stream(H)) return stream_launch_hll(H, d_x, d_y, as_stream(stream));
+    return hll_launch(H, 0, H->num_hacks, d_x, d_y, as_stream(stream));
+}
+
+int spmv_b200_hll_spmv_stream(const spmv_b200_hll *H, const double *d_x, double *d_y, void *stream) {
+    if (!H || !d_y || (H->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_stream: NULL argument");
     return stream_launch_hll(H, d_x, d_y, as_stream(stream));
 }
 
@@ -394,7 +403,7 @@ int spmv_b200_hll_spmv_host(spmv_b200_hll *H, const double *x, double *y) {
     if (!H->stage_x) SPMV_TRY_CUDA(cudaMalloc(&H->stage_x, std::max<size_t>(H->N, 1) * sizeof(double)));
     if (!H->stage_y) SPMV_TRY_CUDA(cudaMalloc(&H->stage_y, std::max<size_t>(H->M, 1) * sizeof(double)));
     if (H->N) SPMV_TRY_CUDA(cudaMemcpyAsync(H->stage_x, x, (size_t)H->N * sizeof(double), cudaMemcpyHostToDevice, nullptr));
-    SPMV_TRY(stream_launch_hll(H, H->stage_x, H->stage_y, nullptr));
+    SPMV_TRY(spmv_b200_hll_spmv(H, H->stage_x, H->stage_y, nullptr));
     if (H->M) SPMV_TRY_CUDA(cudaMemcpyAsync(y, H->stage_y, (size_t)H->M * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
     SPMV_TRY_CUDA(cudaStreamSynchronize(nullptr));
     return SPMV_B200_OK;

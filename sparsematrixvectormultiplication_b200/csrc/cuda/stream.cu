@@ -80,23 +80,46 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
         : "memory");
 }
 
-// sum_{k = lo, lo+step, ... < hi} v[k] * x[c[k]] with values/columns staged in shared memory; four
-// gathers in flight, products and sums rounded separately and added in index order.
+// sum_{k = lo, lo+step, ... < hi} v[k] * x[c[k]] with values/columns staged in shared memory; U gathers
+// in flight, products and sums rounded separately and added in index order.
+template <int U>
 __device__ __forceinline__ double dot_staged(const double *sv, const int *sc, int lo, int hi, int step,
                                              const double *__restrict__ x, double acc) {
     int k = lo;
-    for (; k + 3 * step < hi; k += 4 * step) {
-        const double v0 = sv[k], v1 = sv[k + step], v2 = sv[k + 2 * step], v3 = sv[k + 3 * step];
-        const double x0 = ldg_x(x, sc[k]), x1 = ldg_x(x, sc[k + step]), x2 = ldg_x(x, sc[k + 2 * step]),
-                     x3 = ldg_x(x, sc[k + 3 * step]);
-        acc = __dadd_rn(acc, __dmul_rn(v0, x0));
-        acc = __dadd_rn(acc, __dmul_rn(v1, x1));
-        acc = __dadd_rn(acc, __dmul_rn(v2, x2));
-        acc = __dadd_rn(acc, __dmul_rn(v3, x3));
+    for (; k + (U - 1) * step < hi; k += U * step) {
+        double v[U], xv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = sv[k + u * step];
+#pragma unroll
+        for (int u = 0; u < U; ++u) xv[u] = ldg_x(x, sc[k + u * step]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
     }
     for (; k < hi; k += step) acc = __dadd_rn(acc, __dmul_rn(sv[k], ldg_x(x, sc[k])));
     return acc;
 }
+
+// sv[k] <- sv[k] * x[sc[k]] for k = lo + lane, lo + lane + 32, ... < hi: conflict-free shared-memory
+// accesses and U independent gathers per lane, whatever the row lengths.
+template <int U>
+__device__ __forceinline__ void products_staged(double *sv, const int *sc, int lo, int hi, int lane,
+                                                const double *__restrict__ x) {
+    int k = lo + lane;
+    for (; k + (U - 1) * 32 < hi; k += U * 32) {
+        double v[U], xv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = sv[k + u * 32];
+#pragma unroll
+        for (int u = 0; u < U; ++u) xv[u] = ldg_x(x, sc[k + u * 32]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) sv[k + u * 32] = __dmul_rn(v[u], xv[u]);
+    }
+    for (; k < hi; k += 32) sv[k] = __dmul_rn(sv[k], ldg_x(x, sc[k]));
+}
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int kSerialRowMax = 12;  // chunks whose longest row is at most this long are summed lane = row, in order
 
 // =================================================================================================
 // CSR
@@ -165,52 +188,57 @@ csr_stream_kernel(const int2 *__restrict__ tiles, int num_tiles, const int *__re
             head = __ldg(&tiles[t + gridDim.x]);
             tail = __ldg(&tiles[t + gridDim.x + 1]);
         }
-        const unsigned char *base = smem_raw + (size_t)s * stage_bytes;
+        unsigned char *base = smem_raw + (size_t)s * stage_bytes;
         const int a0 = n0 & ~3, ra0 = r0 & ~3;
         const int loaded = max(min((n1 + 3) & ~3, nnz_bulk) - a0, 0);
         const int rloaded = max(min((r0 + rows + 4) & ~3, rp_bulk) - ra0, 0);
-        const double *sv = reinterpret_cast<const double *>(base);
+        double *sv = reinterpret_cast<double *>(base);
         const int *sc = reinterpret_cast<const int *>(base + (size_t)loaded * 8);
         const int *srp = reinterpret_cast<const int *>(base + (size_t)loaded * 12);
+        bool wrote = false;
         mbar_wait(&full[s], (uint32_t)(i / stages) & 1u);
         if (!(rows == 1 && n1 - n0 > long_threshold)) {  // long rows belong to the csr_long_* kernels
             auto rp = [&](int r) { return (r - ra0 < rloaded) ? srp[r - ra0] : __ldg(row_ptr + r); };
-            int tpr = forced_tpr;
-            if (tpr == 0) {  // a dozen nonzeros per row or fewer: one lane each; longer: ~len/2 lanes, at most a warp
-                const int avg = (n1 - n0) / rows;
-                tpr = 1;
-                if (avg > 12)
-                    while (tpr < 32 && tpr * 2 < avg) tpr *= 2;
-            }
-            const int tpr_log = 31 - __clz(tpr);
-            const int rows_per_chunk = 32 >> tpr_log;
-            const int nchunks = (rows + rows_per_chunk - 1) >> (5 - tpr_log);
-            const int sub = lane & (tpr - 1);
+            const int nchunks = (rows + 31) >> 5;
             for (int c = (warp - dealt + kConsumerWarps) % kConsumerWarps; c < nchunks; c += kConsumerWarps) {
-                const int lr = c * rows_per_chunk + (lane >> tpr_log);
+                const int lr = c * 32 + lane;
+                const bool live = lr < rows;
+                int lo = 0, hi = 0;
+                if (live) {
+                    lo = rp(r0 + lr) - a0;
+                    hi = rp(r0 + lr + 1) - a0;
+                }
+                const int len = hi - lo;
+                const int maxlen = __reduce_max_sync(0xffffffffu, len);
+                const int chunk_hi = __reduce_max_sync(0xffffffffu, hi);  // offsets grow with the row index
                 double acc = 0.0;
-                if (lr < rows) {
-                    const int lo = rp(r0 + lr) - a0, hi = rp(r0 + lr + 1) - a0;
-                    if (tpr == 1 && accumulate) acc = y[r0 + lr];
+                const bool serial = forced_tpr == 1 || chunk_hi > loaded || (forced_tpr == 0 && maxlen <= kSerialRowMax);
+                if (serial) {
+                    // short rows: lane = row, left to right, mul and add rounded separately (the serial loop's order)
+                    if (live && accumulate) acc = y[r0 + lr];
                     if (hi <= loaded) {
-                        acc = dot_staged(sv, sc, lo + sub, hi, tpr, x, acc);
+                        acc = dot_staged<4>(sv, sc, lo, hi, 1, x, acc);
                     } else {  // ragged end of the arrays (last tile only): the unstaged tail comes from HBM
-                        for (int k = lo + sub; k < hi; k += tpr) {
+                        for (int k = lo; k < hi; ++k) {
                             const double v = k < loaded ? sv[k] : values[(long long)a0 + k];
                             const int col = k < loaded ? sc[k] : col_idx[(long long)a0 + k];
                             acc = __dadd_rn(acc, __dmul_rn(v, ldg_x(x, col)));
                         }
                     }
-                }
-                if (tpr > 1) {
-                    for (int off = tpr >> 1; off > 0; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
-                    if (lr < rows && sub == 0) y[r0 + lr] = accumulate ? __dadd_rn(y[r0 + lr], acc) : acc;
-                } else if (lr < rows) {
-                    y[r0 + lr] = acc;
+                    if (live) y[r0 + lr] = acc;
+                } else {
+                    // longer rows: (A) products in place, lane-strided over the whole chunk; (B) row sums
+                    const int chunk_lo = __shfl_sync(0xffffffffu, lo, 0);
+                    products_staged<8>(sv, sc, chunk_lo, chunk_hi, lane, x);
+                    wrote = true;
+                    __syncwarp();
+                    acc = chunk_row_sum(sv, lo, hi, lane);
+                    if (live) y[r0 + lr] = accumulate ? __dadd_rn(y[r0 + lr], acc) : acc;
                 }
             }
             dealt = (dealt + nchunks) % kConsumerWarps;
         }
+        if (wrote) fence_proxy_async();  // generic-proxy writes to the stage before the async proxy refills it
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
     }
@@ -312,7 +340,7 @@ hll_stream_kernel(const HllTile *__restrict__ tiles, int num_tiles, const long l
                 }
                 const int rel = (int)(o0 - h.slot) + lane;
                 const int hi = rel + (int)(o1 - o0);  // walk j*32 + lane: sequential in j, the serial order
-                const double acc = dot_staged(sv, sc, rel, hi, 32, x, 0.0);
+                const double acc = dot_staged<8>(sv, sc, rel, hi, 32, x, 0.0);
                 const long long row = (long long)(h.hack + lh) * 32 + lane;
                 if (row < M) y[row] = acc;
             }

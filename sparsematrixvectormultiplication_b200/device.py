@@ -200,12 +200,14 @@ class DeviceHLL:
         out.rows_total, out.cols = i.M, i.N
         return out
 
-    def spmv(self, x, y, stream=None, slice_kernel=False):
-        """y = A x; slice_kernel=True uses the plain one-warp-per-hack kernel instead of the TMA pipeline."""
+    def spmv(self, x, y, stream=None, slice_kernel=None):
+        """y = A x.  slice_kernel: None = automatic choice, True = one-warp-per-hack slice kernel,
+        False = persistent TMA stream kernel."""
         i = self.info()
         _check_vec(x, i.N, "x")
         _check_vec(y, i.M, "y")
-        fn = N.lib().spmv_b200_hll_spmv_slice if slice_kernel else N.lib().spmv_b200_hll_spmv
+        fn = {None: N.lib().spmv_b200_hll_spmv, True: N.lib().spmv_b200_hll_spmv_slice,
+              False: N.lib().spmv_b200_hll_spmv_stream}[slice_kernel]
         N.check(fn(self._h, _ptr(x), _ptr(y), _stream(stream)))
         return y
 

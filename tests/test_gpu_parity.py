@@ -43,10 +43,10 @@ def dev():
 
 
 def csr_products(dev, A, x, M):
-    """y from every CSR code path: TMA stream kernel (default), direct tile kernel, vector kernel."""
+    """y from the automatic choice (host round trip) and from every CSR kernel explicitly."""
     import torch
     out = {}
-    out["stream-host"] = A.spmv_host(x)
+    out["auto-host"] = A.spmv_host(x)
     xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
     for name, algo in (("stream", dev.ALGO_STREAM), ("tile", dev.ALGO_TILE), ("vector", dev.ALGO_VECTOR)):
         yd = torch.full((max(M, 1),), float("nan"), dtype=torch.float64, device="cuda")
@@ -56,9 +56,9 @@ def csr_products(dev, A, x, M):
 
 
 def hll_products(dev, H, x, M):
-    """y from both HLL kernels: TMA stream kernel (default) and the plain one-warp-per-hack slice kernel."""
+    """y from the automatic choice (host round trip) and from both HLL kernels explicitly."""
     import torch
-    out = {"stream-host": H.spmv_host(x)}
+    out = {"auto-host": H.spmv_host(x)}
     xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
     for name, flag in (("stream", False), ("slice", True)):
         yd = torch.full((max(M, 1),), float("nan"), dtype=torch.float64, device="cuda")
@@ -87,10 +87,11 @@ def test_golden_fixture_products(dev, checker, name):
         A.replan(threads_per_row=1)
         assert np.array_equal(bits(A.spmv_host(x)), bits(y_ref)), "one thread per row must be bit-exact"
         A.replan(threads_per_row=0)
-        for path, y in hll_products(dev, H, x, pre.M).items():
+        hp = hll_products(dev, H, x, pre.M)
+        for path, y in hp.items():
             assert_close(y, y_ref, scale, f"{name}/{tag}/hll-{path}")
         if H.info().max_maxnz <= 32:  # hacks wider than 32 columns take the split "wide hack" path (tolerance only)
-            assert np.array_equal(bits(H.spmv_host(x)), bits(g[f"y_hll_{tag}"])), "stream kernel sums each row in serial order"
+            assert np.array_equal(bits(hp["stream"]), bits(g[f"y_hll_{tag}"])), "stream kernel sums each row in serial order"
     # device image -> host round trip reproduces the reference arrays exactly
     back = H.download()
     rows, maxnz, offset, JA, AS = back.flat()
@@ -150,11 +151,12 @@ def test_random_matrices(dev, checker, M, N, nz, dup):
                 assert np.array_equal(bits(y), bits(y_ref))
     H = dev.DeviceHLL.from_host(hll)
     y_hll_ref = checker.spmv_hll_serial(checker.coo_to_hll(coo), x, M)
-    for path, y in hll_products(dev, H, x, M).items():
+    hp = hll_products(dev, H, x, M)
+    for path, y in hp.items():
         assert_close(y, y_ref, scale, f"hll-{path}")
         assert_close(y, y_hll_ref, scale, f"hll-{path}-vs-hll-serial")
     if H.info().max_maxnz <= 32:  # no "wide hack" path: every row is summed in the serial order
-        assert np.array_equal(bits(H.spmv_host(x)), bits(y_hll_ref))
+        assert np.array_equal(bits(hp["stream"]), bits(y_hll_ref))
     if not dup:  # device-side CSR -> HLL equals convert_to_hll for duplicate-free rows
         H2 = A.to_hll()
         rows, maxnz, offset, JA, AS = H2.download().flat()
@@ -356,14 +358,18 @@ def test_full_size_lap2d_4096(dev, checker):
     assert np.max(np.abs(got - y_ref)) <= TOL * 16.0  # |A||x| <= 8 * 1.75
     A.replan(threads_per_row=1)
     assert np.array_equal(bits(A.spmv_host(xr)), bits(y_ref)), "one thread per row: bit-exact with the serial loop"
+    A.replan(threads_per_row=0)
+    assert np.array_equal(bits(A.spmv_host(xr)), bits(y_ref)), "5-point rows take the in-order path of the stream kernel anyway"
+    A.replan(threads_per_row=1)
     H = A.to_hll()
     hi = H.info()
     # MAXNZ is 5 everywhere except the hacks of the first and last grid row (4): SURVEY.md section 8(d)
     assert hi.slots == 5 * n * n - 2 * n and hi.max_maxnz == 5 and hi.num_hacks == n * n // 32
-    yh = H.spmv_host(xr)
-    assert np.array_equal(bits(yh), bits(y_ref)), "HLL stream kernel sums every row in serial order (padding adds 0.0)"
     xd = torch.from_numpy(xr).cuda()
     ys = torch.empty_like(x)
+    H.spmv(xd, ys, slice_kernel=False)
+    assert np.array_equal(bits(ys.cpu().numpy()), bits(y_ref)), "HLL stream kernel sums every row in serial order (padding adds 0.0)"
+    assert np.array_equal(bits(H.spmv_host(xr)), bits(y_ref)), "narrow hacks: the automatic choice is the stream kernel"
     H.spmv(xd, ys, slice_kernel=True)
     assert np.max(np.abs(ys.cpu().numpy() - y_ref)) <= TOL * 16.0
     A.spmv(xd, ys, algo=dev.ALGO_TILE)
@@ -389,10 +395,12 @@ def test_full_size_uniform_8m_properties(dev, checker):
     H.spmv(x, y_hll)
     A.spmv(x, y_vec, algo=dev.ALGO_VECTOR)
     y_alt = torch.empty_like(y_csr)
-    H.spmv(x, y_alt, slice_kernel=True)
-    assert float(((y_hll - y_alt).abs() / y_hll).max()) <= TOL
-    A.spmv(x, y_alt, algo=dev.ALGO_TILE)
-    assert float(((y_csr - y_alt).abs() / y_csr).max()) <= TOL
+    for flag in (True, False):
+        H.spmv(x, y_alt, slice_kernel=flag)
+        assert float(((y_hll - y_alt).abs() / y_hll).max()) <= TOL
+    for algo in (dev.ALGO_TILE, dev.ALGO_STREAM):
+        A.spmv(x, y_alt, algo=algo)
+        assert float(((y_csr - y_alt).abs() / y_csr).max()) <= TOL
     # all values are positive: plain relative error is well posed
     assert float(((y_csr - y_hll).abs() / y_csr).max()) <= TOL
     assert float(((y_csr - y_vec).abs() / y_csr).max()) <= TOL
