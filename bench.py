@@ -432,15 +432,23 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler):
 
     # config 5 on ONE GPU: T1 of the multi-GPU scaling series
     try:
-        from sparsematrixvectormultiplication_b200.distributed import PowerIteration
+        from sparsematrixvectormultiplication_b200.distributed import FusedPowerIteration, PowerIteration
+        F = FusedPowerIteration(synth.SYNTH_LAP3D, 512)
+        ms, per = time_device(F.step, steps, warm, sampler)
+        out["lap3d_512_power_1gpu"] = {"gflops": 2.0 * F.nnz_global / (ms * 1e-3) / 1e9, "ms_per_iteration": ms,
+                                       "nnz": F.nnz_global, "launches_per_step": F.launches_per_step,
+                                       "kernel": "fused: product + lazy normalisation + |w|^2 partials in one launch"}
+        log(f"[bench] lap3d_512_power_1gpu (fused): {out['lap3d_512_power_1gpu']['gflops']:.1f} GFLOP/s ({ms:.3f} ms/iteration)")
+        del F
+        torch.cuda.empty_cache()
         P = PowerIteration(synth.SYNTH_LAP3D, 512)
         ms, per = time_device(P.step, steps, warm, sampler)
-        out["lap3d_512_power_1gpu"] = {"gflops": 2.0 * P.nnz_global / (ms * 1e-3) / 1e9, "ms_per_iteration": ms,
-                                       "nnz": P.nnz_global, "launches_per_step": P.launches_per_step}
+        out["lap3d_512_power_1gpu_unfused"] = {"gflops": 2.0 * P.nnz_global / (ms * 1e-3) / 1e9, "ms_per_iteration": ms,
+                                               "nnz": P.nnz_global, "launches_per_step": P.launches_per_step}
         A3 = P.A
         i3 = A3.info()
         run("lap3d_512_csr_product_only", lambda: A3.spmv(P.x, P.y), i3.nnz, i3.algorithmic_bytes)
-        log(f"[bench] lap3d_512_power_1gpu: {out['lap3d_512_power_1gpu']['gflops']:.1f} GFLOP/s ({ms:.3f} ms/iteration)")
+        log(f"[bench] lap3d_512_power_1gpu_unfused: {out['lap3d_512_power_1gpu_unfused']['gflops']:.1f} GFLOP/s ({ms:.3f} ms/iteration)")
         del P
         torch.cuda.empty_cache()
     except Exception as e:  # pragma: no cover
@@ -453,7 +461,7 @@ def bench_multi_gpu(args):
     import torch
     import torch.distributed as dist
     from sparsematrixvectormultiplication_b200 import device, synth
-    from sparsematrixvectormultiplication_b200.distributed import PowerIteration
+    from sparsematrixvectormultiplication_b200.distributed import FusedPowerIteration, PowerIteration
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -464,36 +472,46 @@ def bench_multi_gpu(args):
         sampler.start()
     n = args.lap3d_n
     results = {}
-    for mode in ("halo", "allgather"):
-        P = PowerIteration(synth.SYNTH_LAP3D, n, exchange=mode)
+    for mode in ("fused_peer_stores", "fused_nccl_halo", "halo", "allgather"):
+        if mode == "fused_peer_stores":
+            P = FusedPowerIteration(synth.SYNTH_LAP3D, n, peer_stores=True)
+        elif mode == "fused_nccl_halo":
+            P = FusedPowerIteration(synth.SYNTH_LAP3D, n, peer_stores=False)
+        else:
+            P = PowerIteration(synth.SYNTH_LAP3D, n, exchange=mode)
         P.reset(1.0)
-        steps = args.steps if mode == "halo" else max(3, min(args.steps, 20))
-        ms, per = time_device(P.step, steps, args.warmup, sampler if mode == "halo" else None, world)
+        head = mode == "fused_peer_stores"
+        steps = args.steps if head else max(3, min(args.steps, 20))
+        ms, per = time_device(P.step, steps, args.warmup, sampler if head else None, world)
         lam = P.eigenvalue_estimate()
-        recv = P.plan.halo_doubles_received() if mode == "halo" else P.plan.allgather_doubles_received()
+        recv = P.plan.allgather_doubles_received() if mode == "allgather" else P.plan.halo_doubles_received()
         results[mode] = {"ms_per_step": ms, "gflops": 2.0 * P.nnz_global / (ms * 1e-3) / 1e9, "steps": steps,
                          "lambda": lam, "rows_local": P.rows, "nnz_local": P.nnz_local, "recv_bytes_per_step": 8 * recv,
                          "launches_per_step": P.launches_per_step, "nnz_global": P.nnz_global,
                          "bytes_local": P.algorithmic_bytes_local}
         if rank == 0:
             log(f"[bench] {world} GPUs {mode}: {results[mode]['gflops']:.1f} GFLOP/s, {ms:.3f} ms/iteration, lambda={lam:.12g}")
-        # kernel-only product time on this rank (roofline of the dominant kernel)
-        if mode == "halo":
-            kms, kper = time_device(lambda: P.A.spmv(P.x, P.y), max(5, min(args.steps, 50)), 3, None, world)
+        if head:  # kernel-only product time on this rank (roofline of the dominant kernel)
+            xs, row_begin = P.xs, P.row_begin
+            kms, kper = time_device(lambda: P.A.spmv_fused(xs[0].data_ptr(), xs[1].data_ptr() + 8 * row_begin, partials=P.partials),
+                                    max(5, min(args.steps, 50)), 3, None, world)
             results["product_only_ms"] = kms
+        if hasattr(P, "close"):
+            P.close()
         del P
         torch.cuda.empty_cache()
     if sampler:
         sampler.stop()
     if rank == 0:
-        h = results["halo"]
+        h = results["fused_peer_stores"]
         gbs = h["bytes_local"] / (results["product_only_ms"] * 1e-3) / 1e9
         line = {"metric": "spmv_gflops", "value": h["gflops"], "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": h["ms_per_step"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"lap3d_{n}_power", "rows": n ** 3, "nnz": h["nnz_global"], "format": "csr",
-                           "partition": "contiguous rows balanced by nnz (reference greedy rule)", "exchange": "halo",
-                           "step": "one power iteration: y=Ax, 1-double all-reduce of |y|^2, x=y/|y|, refresh of x",
+                           "partition": "contiguous rows balanced by nnz (reference greedy rule)",
+                           "exchange": "boundary rows stored into the neighbours' x over NVLink peer memory by the product kernel",
+                           "step": "one power iteration, one fused launch: w=(A w_prev)/|w_prev| + |w|^2 partials + peer stores, then an 8-byte all-reduce",
                            "l2": "inputs_exceed_l2"},
                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
                              "peak_source": peak_src, "note": "rank 0's local CSR product alone (max over ranks), algorithmic bytes of its row slice",

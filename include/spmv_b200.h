@@ -106,6 +106,24 @@ int spmv_b200_csr_spmv(const spmv_b200_csr *A, const double *d_x, double *d_y, i
 int spmv_b200_csr_spmv_host(spmv_b200_csr *A, const double *x, double *y, int accumulate, int algo);
 /* product restricted to rows [row_begin,row_end) (the reference's per-thread row ranges,
  * src/csr_matrix.c:294-313); other rows of y are left untouched. Vector kernel. */
+/* ---- fused iterated product (BASELINE config 5; no reference counterpart: the reference only repeats
+ * the same product, main_cuda.cu:159-200).  One launch computes
+ *     y[r] = (A x)[r] / sqrt(*d_prev_sumsq)            (d_prev_sumsq == NULL: no scaling)
+ * writes y, mirrors the rows [lo,hi) listed in `peers` into the peers' buffers (NVLink peer memory obtained
+ * with spmv_b200_ipc_open), and leaves per-CTA partial sums of y[r]^2 in d_partials
+ * (spmv_b200_csr_partials_count doubles; NULL: skipped).  Matrices with long rows are rejected
+ * (SPMV_B200_ERR_INVALID): use spmv_b200_csr_spmv + the vec helpers for those. */
+#define SPMV_B200_MAX_PEERS 7
+typedef struct {
+    int count;
+    double *dst[SPMV_B200_MAX_PEERS]; /* peer pointer that corresponds to local row 0 of y            */
+    int lo[SPMV_B200_MAX_PEERS];      /* local row range [lo,hi) the peer needs                       */
+    int hi[SPMV_B200_MAX_PEERS];
+} spmv_b200_peers_t;
+int spmv_b200_csr_partials_count(const spmv_b200_csr *A);
+int spmv_b200_csr_spmv_fused(const spmv_b200_csr *A, const double *d_x, double *d_y, const double *d_prev_sumsq,
+                             double *d_partials, const spmv_b200_peers_t *peers, void *stream);
+
 int spmv_b200_csr_spmv_rows(const spmv_b200_csr *A, int row_begin, int row_end, const double *d_x,
                             double *d_y, void *stream);
 void spmv_b200_csr_free(spmv_b200_csr *A);
@@ -157,8 +175,17 @@ int spmv_b200_vec_fill(double *d_v, long long n, double value, void *stream);
 int spmv_b200_vec_ws_doubles(void);
 int spmv_b200_vec_sumsq(const double *d_v, long long n, double *d_ws, double *d_out, void *stream);
 /* d_dst[i] = d_src[i] / sqrt(*d_sumsq)   (no host round trip) */
+/* *d_out = sum of n doubles, one CTA, fixed tree (n is small: the per-CTA partials above) */
+int spmv_b200_vec_sum(const double *d_in, int n, double *d_out, void *stream);
 int spmv_b200_vec_scale_by_inv_norm(double *d_dst, const double *d_src, long long n,
                                     const double *d_sumsq, void *stream);
+
+/* ---- peer memory for the fused exchange: device buffers that other ranks (processes) on the same NVLink
+ * domain can map.  handle is an opaque 64-byte token (cudaIpcMemHandle_t) to ship to the peers. ---- */
+int spmv_b200_ipc_alloc(long long bytes, void **d_ptr, unsigned char handle[64]);
+int spmv_b200_ipc_open(const unsigned char handle[64], void **d_peer_ptr);
+int spmv_b200_ipc_close(void *d_peer_ptr);
+int spmv_b200_ipc_free(void *d_ptr);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,10 @@ class HllInfo(C.Structure):  # include/spmv_b200.h spmv_b200_hll_info_t
                 ("algorithmic_bytes", C.c_longlong)]
 
 
+class Peers(C.Structure):  # include/spmv_b200.h spmv_b200_peers_t
+    _fields_ = [("count", C.c_int), ("dst", C.c_void_p * 7), ("lo", C.c_int * 7), ("hi", C.c_int * 7)]
+
+
 _V = C.c_void_p
 _I = C.c_int
 _LL = C.c_longlong
@@ -89,6 +93,13 @@ SIGNATURES = {
     "spmv_b200_csr_spmv": (_I, [_V, _V, _V, _I, _I, _V]),
     "spmv_b200_csr_spmv_host": (_I, [_V, _V, _V, _I, _I]),
     "spmv_b200_csr_spmv_rows": (_I, [_V, _I, _I, _V, _V, _V]),
+    "spmv_b200_csr_partials_count": (_I, [_V]),
+    "spmv_b200_csr_spmv_fused": (_I, [_V, _V, _V, _V, _V, C.POINTER(Peers), _V]),
+    "spmv_b200_vec_sum": (_I, [_V, _I, _V, _V]),
+    "spmv_b200_ipc_alloc": (_I, [_LL, C.POINTER(_V), C.c_char * 64]),
+    "spmv_b200_ipc_open": (_I, [C.c_char * 64, C.POINTER(_V)]),
+    "spmv_b200_ipc_close": (_I, [_V]),
+    "spmv_b200_ipc_free": (_I, [_V]),
     "spmv_b200_csr_free": (None, [_V]),
     "spmv_b200_csr_spmv_raw": (_I, [_I, _LL, _V, _V, _V, _V, _V, _I, _V]),
     "spmv_b200_hll_upload": (_I, [C.POINTER(HLLMatrixStruct), _I, _I, C.POINTER(_V)]),

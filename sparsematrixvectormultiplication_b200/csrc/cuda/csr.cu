@@ -386,7 +386,7 @@ static int launch_tiles(const spmv_b200_csr *A, const double *x, double *y, int 
                         cudaStream_t stream) {
     if (A->num_tiles == 0) return SPMV_B200_OK;
     if (pipelined) {
-        SPMV_TRY(stream_launch_csr(A, x, y, accumulate, stream));
+        SPMV_TRY(stream_launch_csr(A, x, y, accumulate, nullptr, stream));
     } else {
         csr_tile_kernel<<<A->num_tiles, kTileThreads, tile_smem_bytes(A), stream>>>(
             A->tiles, A->row_ptr, A->col_idx, A->values, x, y, (int)A->nnz, A->long_threshold, A->forced_tpr, accumulate);
@@ -553,7 +553,8 @@ int spmv_b200_csr_spmv(const spmv_b200_csr *A, const double *d_x, double *d_y, i
             // miss L2: those need the occupancy of the direct-load kernels -- vector-per-row when no row is long,
             // the row-binned tile kernel (+ long-row split) when the lengths are skewed.  Measured on B200:
             // profiles/r01b_kernel_selection.md.
-            if (A->nnz <= (long long)kAutoStreamMaxAvg * A->M)
+            // threads_per_row == 1 is a request for the reference's summation order: the stream kernel honours it
+            if (A->forced_tpr == 1 || A->nnz <= (long long)kAutoStreamMaxAvg * A->M)
                 return launch_tiles(A, d_x, d_y, accumulate, true, as_stream(stream));
             if (A->num_long == 0)
                 return launch_vector(0, A->M, A->row_ptr, A->col_idx, A->values, d_x, d_y,
@@ -569,6 +570,24 @@ int spmv_b200_csr_spmv(const spmv_b200_csr *A, const double *d_x, double *d_y, i
         default:
             return fail(SPMV_B200_ERR_INVALID, "csr_spmv: unknown algo %d", algo);
     }
+}
+
+int spmv_b200_csr_partials_count(const spmv_b200_csr *A) { return A ? std::max(A->stream_grid, 1) : 0; }
+
+int spmv_b200_csr_spmv_fused(const spmv_b200_csr *A, const double *d_x, double *d_y, const double *d_prev_sumsq,
+                             double *d_partials, const spmv_b200_peers_t *peers, void *stream) {
+    if (!A || !d_y || (A->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused: NULL argument");
+    if (A->num_long > 0)
+        return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused: %d rows exceed the long-row threshold; use csr_spmv", A->num_long);
+    if (peers && (peers->count < 0 || peers->count > SPMV_B200_MAX_PEERS))
+        return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused: bad peer count %d", peers->count);
+    Epilogue ep;
+    ep.prev_sumsq = d_prev_sumsq;
+    ep.partials = d_partials;
+    ep.peers.count = 0;
+    if (peers) ep.peers = *peers;
+    if (A->M == 0) return SPMV_B200_OK;
+    return stream_launch_csr(A, d_x, d_y, 0, &ep, as_stream(stream));
 }
 
 int spmv_b200_csr_spmv_rows(const spmv_b200_csr *A, int row_begin, int row_end, const double *d_x, double *d_y,

@@ -13,6 +13,12 @@ constexpr int kDefaultStages = 2;           // TMA pipeline depth of the stream 
 constexpr int kHllTileSlots = 3072;         // D_h: slots + rows per HLL tile (12 B per slot; stage = 49.5 KB with the wide margin)
 constexpr int kHllWideSlots = 1024;         // hacks with more slots (MAXNZ > 32) are processed straight from HBM
 
+struct Epilogue {                 // optional fused tail of the CSR stream kernel
+    const double *prev_sumsq;     // divide every row by sqrt(*prev_sumsq)
+    double *partials;             // partials[blockIdx.x] = sum of the squares of the rows this CTA produced
+    spmv_b200_peers_t peers;      // rows mirrored into peer memory
+};
+
 struct HllTile {      // tiles[t] = first hack of tile t and its first slot; tiles[num_tiles] = {num_hacks, slots}
     int hack;
     int pad;
@@ -70,7 +76,8 @@ struct spmv_b200_hll {
 namespace spmv {
 // stream.cu
 int stream_prepare_csr(spmv_b200_csr *A);
-int stream_launch_csr(const spmv_b200_csr *A, const double *x, double *y, int accumulate, cudaStream_t stream);
+int stream_launch_csr(const spmv_b200_csr *A, const double *x, double *y, int accumulate, const Epilogue *ep,
+                      cudaStream_t stream);
 int stream_plan_hll(spmv_b200_hll *H, cudaStream_t stream);
 int stream_launch_hll(const spmv_b200_hll *H, const double *x, double *y, cudaStream_t stream);
 int env_int(const char *name, int fallback);

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, (kConsumerWarps >= 
 csr_stream_kernel(const int2 *__restrict__ tiles, int num_tiles, const int *__restrict__ row_ptr,
                   const int *__restrict__ col_idx, const double *__restrict__ values, const double *__restrict__ x,
                   double *__restrict__ y, int M, int nnz_total, int stage_bytes, int stages, int long_threshold,
-                  int forced_tpr, int accumulate) {
+                  int forced_tpr, int accumulate, const Epilogue ep) {
     // a stage is one packed pool: [values: cnt x 8 B][columns: cnt x 4 B][row_ptr slice: rcnt x 4 B]
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)stages * stage_bytes);
@@ -174,6 +174,18 @@ csr_stream_kernel(const int2 *__restrict__ tiles, int num_tiles, const int *__re
     }
 
     // ---------------- consumers: independent warps, lane = row (or a slice of a row) ----------------
+    __shared__ double warp_sq[kConsumerWarps];
+    const bool scaled = ep.prev_sumsq != nullptr;
+    const double prev_norm = scaled ? sqrt(*ep.prev_sumsq) : 1.0;
+    double sq = 0.0;  // sum of the squares of the rows this lane produced
+    // y[row] = v (after the optional scaling), mirrored into the peers that reference the row
+    auto emit = [&](int row, double v) {
+        if (scaled) v = v / prev_norm;
+        y[row] = v;
+        sq = fma(v, v, sq);
+        for (int p = 0; p < ep.peers.count; ++p)
+            if (row >= ep.peers.lo[p] && row < ep.peers.hi[p]) ep.peers.dst[p][row] = v;
+    };
     int2 head = make_int2(0, 0), tail = make_int2(0, 0);
     if ((int)blockIdx.x < num_tiles) {
         head = __ldg(&tiles[blockIdx.x]);
@@ -225,7 +237,7 @@ csr_stream_kernel(const int2 *__restrict__ tiles, int num_tiles, const int *__re
                             acc = __dadd_rn(acc, __dmul_rn(v, ldg_x(x, col)));
                         }
                     }
-                    if (live) y[r0 + lr] = acc;
+                    if (live) emit(r0 + lr, acc);
                 } else {
                     // longer rows: (A) products in place, lane-strided over the whole chunk; (B) row sums
                     const int chunk_lo = __shfl_sync(0xffffffffu, lo, 0);
@@ -233,7 +245,7 @@ csr_stream_kernel(const int2 *__restrict__ tiles, int num_tiles, const int *__re
                     wrote = true;
                     __syncwarp();
                     acc = chunk_row_sum(sv, lo, hi, lane);
-                    if (live) y[r0 + lr] = accumulate ? __dadd_rn(y[r0 + lr], acc) : acc;
+                    if (live) emit(r0 + lr, accumulate ? __dadd_rn(y[r0 + lr], acc) : acc);
                 }
             }
             dealt = (dealt + nchunks) % kConsumerWarps;
@@ -241,6 +253,18 @@ csr_stream_kernel(const int2 *__restrict__ tiles, int num_tiles, const int *__re
         if (wrote) fence_proxy_async();  // generic-proxy writes to the stage before the async proxy refills it
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    if (ep.partials != nullptr) {  // fixed-order CTA sum of squares (consumer warps only: the producer has left)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+        if (lane == 0) warp_sq[warp] = sq;
+        asm volatile("bar.sync 2, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+        if (tid == 0) {
+            double total = 0.0;
+#pragma unroll
+            for (int w = 0; w < kConsumerWarps; ++w) total += warp_sq[w];
+            ep.partials[blockIdx.x] = total;
+        }
     }
 }
 
@@ -437,13 +461,19 @@ int stream_prepare_csr(spmv_b200_csr *A) {
     return rc;
 }
 
-int stream_launch_csr(const spmv_b200_csr *A, const double *x, double *y, int accumulate, cudaStream_t stream) {
+int stream_launch_csr(const spmv_b200_csr *A, const double *x, double *y, int accumulate, const Epilogue *ep,
+                      cudaStream_t stream) {
     if (A->num_tiles == 0) return SPMV_B200_OK;
+    Epilogue none;
+    none.prev_sumsq = nullptr;
+    none.partials = nullptr;
+    none.peers.count = 0;
+    const Epilogue e = ep ? *ep : none;
     const size_t smem = csr_stream_smem(A);
     STREAM_DISPATCH(A->consumers, csr_stream_kernel,
                     (kfn<<<A->stream_grid, (A->consumers + 1) * 32, smem, stream>>>(
                         A->tiles, A->num_tiles, A->row_ptr, A->col_idx, A->values, x, y, A->M, (int)A->nnz,
-                        csr_stage_bytes(A), A->stages, A->long_threshold, A->forced_tpr, accumulate)));
+                        csr_stage_bytes(A), A->stages, A->long_threshold, A->forced_tpr, accumulate, e)));
     SPMV_TRY_CUDA(cudaGetLastError());
     return SPMV_B200_OK;
 }

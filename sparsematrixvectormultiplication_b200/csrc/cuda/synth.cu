@@ -162,6 +162,14 @@ __global__ void __launch_bounds__(kSumsqThreads) sumsq_stage2_kernel(const doubl
     if (threadIdx.x == 0) *out = total;
 }
 
+__global__ void __launch_bounds__(kSumsqThreads) sum_small_kernel(const double *__restrict__ in, int n, double *__restrict__ out) {
+    __shared__ double scratch[kSumsqThreads / 32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += kSumsqThreads) acc += in[i];
+    const double total = block_sum(acc, scratch);
+    if (threadIdx.x == 0) *out = total;
+}
+
 __global__ void scale_by_inv_norm_kernel(double *__restrict__ dst, const double *__restrict__ src, long long n,
                                          const double *__restrict__ sumsq) {
     const double norm = sqrt(*sumsq);
@@ -291,6 +299,47 @@ int spmv_b200_vec_sumsq(const double *d_v, long long n, double *d_ws, double *d_
     SPMV_TRY_CUDA(cudaGetLastError());
     sumsq_stage2_kernel<<<1, kSumsqThreads, 0, as_stream(stream)>>>(d_ws, d_out);
     SPMV_TRY_CUDA(cudaGetLastError());
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_vec_sum(const double *d_in, int n, double *d_out, void *stream) {
+    if (n < 0 || (n > 0 && !d_in) || !d_out) return fail(SPMV_B200_ERR_INVALID, "vec_sum: bad arguments");
+    sum_small_kernel<<<1, kSumsqThreads, 0, as_stream(stream)>>>(d_in, n, d_out);
+    SPMV_TRY_CUDA(cudaGetLastError());
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_ipc_alloc(long long bytes, void **d_ptr, unsigned char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (bytes <= 0 || !d_ptr || !handle) return fail(SPMV_B200_ERR_INVALID, "ipc_alloc: bad arguments");
+    *d_ptr = nullptr;
+    SPMV_TRY_CUDA(cudaMalloc(d_ptr, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *d_ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*d_ptr);
+        *d_ptr = nullptr;
+        return fail(SPMV_B200_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle, &h, 64);
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_ipc_open(const unsigned char handle[64], void **d_peer_ptr) {
+    if (!handle || !d_peer_ptr) return fail(SPMV_B200_ERR_INVALID, "ipc_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    SPMV_TRY_CUDA(cudaIpcOpenMemHandle(d_peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_ipc_close(void *d_peer_ptr) {
+    if (d_peer_ptr) SPMV_TRY_CUDA(cudaIpcCloseMemHandle(d_peer_ptr));
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_ipc_free(void *d_ptr) {
+    if (d_ptr) SPMV_TRY_CUDA(cudaFree(d_ptr));
     return SPMV_B200_OK;
 }
 

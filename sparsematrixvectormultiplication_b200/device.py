@@ -129,6 +129,18 @@ class DeviceCSR:
         N.check(N.lib().spmv_b200_csr_spmv(self._h, _ptr(x), _ptr(y), int(bool(accumulate)), algo, _stream(stream)))
         return y
 
+    def partials_count(self) -> int:
+        return N.lib().spmv_b200_csr_partials_count(self._h)
+
+    def spmv_fused(self, x_ptr, y_ptr, prev_sumsq=None, partials=None, peers=None, stream=None):
+        """y = (A x) / sqrt(*prev_sumsq), partials[cta] = sum y^2, boundary rows mirrored into peer memory.
+        x_ptr / y_ptr are raw device addresses (ints) or tensors."""
+        def raw(v):
+            return C.c_void_p(v) if isinstance(v, int) else _ptr(v)
+        N.check(N.lib().spmv_b200_csr_spmv_fused(self._h, raw(x_ptr), raw(y_ptr), raw(prev_sumsq) if prev_sumsq is not None else None,
+                                                 raw(partials) if partials is not None else None,
+                                                 C.byref(peers) if peers is not None else None, _stream(stream)))
+
     def spmv_rows(self, row_begin, row_end, x, y, stream=None):
         N.check(N.lib().spmv_b200_csr_spmv_rows(self._h, int(row_begin), int(row_end), _ptr(x), _ptr(y), _stream(stream)))
         return y
@@ -256,6 +268,50 @@ def vec_ws_doubles() -> int:
 def vec_sumsq(v, ws, out, n=None, stream=None):
     N.check(N.lib().spmv_b200_vec_sumsq(_ptr(v), int(v.numel() if n is None else n), _ptr(ws), _ptr(out), _stream(stream)))
     return out
+
+
+def vec_sum(src, n, out, stream=None):
+    N.check(N.lib().spmv_b200_vec_sum(_ptr(src), int(n), _ptr(out), _stream(stream)))
+    return out
+
+
+class PeerBuffer:
+    """A device buffer other ranks on the NVLink domain can map (cudaIpc)."""
+
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p()
+        self.handle = (C.c_char * 64)()
+        N.check(N.lib().spmv_b200_ipc_alloc(int(nbytes), C.byref(self.ptr), self.handle))
+        self.nbytes = nbytes
+        self.mapped = []
+
+    def handle_bytes(self) -> bytes:
+        return bytes(self.handle.raw)
+
+    def open_peer(self, handle: bytes) -> int:
+        h = (C.c_char * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        N.check(N.lib().spmv_b200_ipc_open(h, C.byref(p)))
+        self.mapped.append(p)
+        return p.value
+
+    def as_tensor(self, dtype_str="<f8", itemsize=8):
+        import torch
+
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": (self.nbytes // itemsize,), "typestr": dtype_str,
+                                      "data": (self.ptr.value, False), "version": 2}
+        return torch.as_tensor(v, device=torch.device("cuda", torch.cuda.current_device()))
+
+    def close(self):
+        for p in self.mapped:
+            N.lib().spmv_b200_ipc_close(p)
+        self.mapped = []
+        if self.ptr:
+            N.lib().spmv_b200_ipc_free(self.ptr)
+            self.ptr = C.c_void_p()
 
 
 def vec_scale_by_inv_norm(dst, src, sumsq, n=None, stream=None):

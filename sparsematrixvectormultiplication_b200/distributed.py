@@ -96,15 +96,16 @@ class _CudaView:
 class PowerIteration:
     """Power method on a synthetic matrix, row-partitioned over the ranks of ``group``."""
 
-    def __init__(self, kind, p0, p1=0, p2=0, seed=0x5EED, exchange="halo", group=None, parts=None):
+    def __init__(self, kind, p0, p1=0, p2=0, seed=0x5EED, exchange="halo", group=None, parts=None, single=False):
         import ctypes as C
 
         from . import _native as N
         from . import device, partition, synth
         self.dev = device
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        distributed = dist.is_initialized() and not single  # single=True: the whole matrix on this rank alone
+        self.world = dist.get_world_size(group) if distributed else 1
+        self.rank = dist.get_rank(group) if distributed else 0
         self.exchange = exchange
         self.parts = parts if parts is not None else partition.synth_partition(kind, p0, p1, p2, self.world)
         if len(self.parts) != self.world:
@@ -151,3 +152,92 @@ class PowerIteration:
 
     def eigenvalue_estimate(self) -> float:
         return float(self.ss.item()) ** 0.5
+
+
+class FusedPowerIteration(PowerIteration):
+    """The same iteration with everything but an 8-byte all-reduce folded into the product kernel.
+
+    Lazy normalisation: the stored vector is w_k = A v_{k-1} (not normalised); the next launch computes
+    w_{k+1} = (A w_k) / |w_k| in its epilogue (algebraically A v_k), together with the per-CTA partial sums of
+    |w_{k+1}|^2.  So there is no separate norm pass and no scale pass, and y IS the next x: the kernel writes
+    the owned slice of the next x in place.
+    peer_stores=True (needs NVLink peer access, one process per GPU on one node): the kernel also stores the
+    rows a neighbour references straight into that neighbour's next-x buffer (cudaIpc-mapped peer memory), so
+    the refresh of x costs no extra launch and no extra pass; the all-reduce of |w|^2 is the only collective
+    and doubles as the barrier that orders those peer stores before the next product.
+    peer_stores=False: the boundary rows travel with NCCL point-to-point messages instead."""
+
+    def __init__(self, kind, p0, p1=0, p2=0, seed=0x5EED, group=None, parts=None, single=False, peer_stores=True):
+        super().__init__(kind, p0, p1, p2, seed=seed, exchange="halo", group=group, parts=parts, single=single)
+        from . import _native as N
+        d = self.dev
+        if self.A.info().num_long_rows:
+            raise ValueError("FusedPowerIteration needs a matrix without long rows")
+        self.peer_stores = bool(peer_stores) and self.world > 1
+        cu = self.x.device
+        del self.x, self.y
+        nbytes = 8 * self.N
+        if self.peer_stores:
+            self.buf = [d.PeerBuffer(nbytes), d.PeerBuffer(nbytes)]
+            self.xs = [b.as_tensor() for b in self.buf]
+            handles = [None] * self.world
+            dist.all_gather_object(handles, [b.handle_bytes() for b in self.buf], group=self.group)
+            self.peers = []
+            for parity in (0, 1):
+                ps = N.Peers()
+                ps.count = len(self.plan.sends)
+                assert ps.count <= 7
+                for i, (peer, lo, hi) in enumerate(self.plan.sends):
+                    base = self.buf[parity].open_peer(handles[peer][parity])
+                    ps.dst[i] = base + 8 * self.row_begin      # the peer's slot for MY local row 0
+                    ps.lo[i], ps.hi[i] = lo - self.row_begin, hi - self.row_begin
+                self.peers.append(ps)
+        else:
+            self.buf = None
+            self.xs = [torch.empty(self.N, dtype=torch.float64, device=cu) for _ in range(2)]
+            self.peers = [None, None]
+        self.partials = torch.zeros(self.A.partials_count(), dtype=torch.float64, device=cu)
+        self.sumsq = [torch.zeros(1, dtype=torch.float64, device=cu) for _ in range(2)]
+        self.k = 0
+        self.reset(1.0)
+        self.launches_per_step = 2
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def reset(self, value=1.0):
+        for t in self.xs:
+            self.dev.vec_fill(t, value)
+        self.k = 0
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def step(self):
+        cur, nxt = self.k & 1, (self.k & 1) ^ 1
+        x, y = self.xs[cur], self.xs[nxt]
+        self.A.spmv_fused(x.data_ptr(), y.data_ptr() + 8 * self.row_begin,
+                          prev_sumsq=self.sumsq[cur] if self.k > 0 else None, partials=self.partials,
+                          peers=self.peers[nxt])
+        self.dev.vec_sum(self.partials, self.partials.numel(), self.sumsq[nxt])
+        if self.world > 1:
+            dist.all_reduce(self.sumsq[nxt], group=self.group)  # |w|^2; also orders the peer stores
+            if not self.peer_stores:
+                exchange_halo(y, self.plan, self.group)
+        self.k += 1
+
+    def eigenvalue_estimate(self) -> float:
+        return float(self.sumsq[self.k & 1].item()) ** 0.5
+
+    def normalized_x(self) -> torch.Tensor:
+        """v_k = w_k / |w_k| (valid on the owned rows and on the referenced halo)."""
+        return self.xs[self.k & 1] / self.sumsq[self.k & 1].sqrt()
+
+    def close(self):
+        if self.buf:
+            torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier(group=self.group)
+            self.xs = []
+            for b in self.buf:
+                b.close()
+            self.buf = None

@@ -415,3 +415,29 @@ def test_full_size_uniform_8m_properties(dev, checker):
     y2 = torch.empty_like(y_csr)
     A.spmv(x2, y2)
     assert torch.equal(y2, y_csr * 2.0)
+
+
+def test_fused_power_iteration_matches_the_oracle(dev, port):
+    """One launch per iteration (product + lazy normalisation + |w|^2 partials) against the oracle's
+    y = A x; lambda = |y|; x = y / lambda."""
+    import torch
+    from sparsematrixvectormultiplication_b200 import synth
+    from sparsematrixvectormultiplication_b200.distributed import FusedPowerIteration
+    n, iters = 14, 30
+    rp, ci, va = synth.lap3d_csr(n)
+    x_ref, y_ref, lam_ref = port.power_iteration(rp, ci, va, np.ones(n ** 3), iters)
+    F = FusedPowerIteration(synth.SYNTH_LAP3D, n)
+    lam = []
+    for _ in range(iters):
+        F.step()
+        lam.append(F.eigenvalue_estimate())
+    assert np.max(np.abs(np.array(lam) - lam_ref) / lam_ref) <= TOL
+    v = F.normalized_x().cpu().numpy()
+    assert np.max(np.abs(v - x_ref)) <= TOL * np.max(np.abs(x_ref))
+    # the fused entry point with no scaling and no partials is the plain product
+    A = dev.DeviceCSR.synth(synth.SYNTH_LAP3D, n)
+    x = torch.from_numpy(ramp(n ** 3)).cuda()
+    y1, y2 = torch.empty_like(x), torch.empty_like(x)
+    A.spmv(x, y1)
+    A.spmv_fused(x, y2)
+    assert torch.equal(y1, y2)

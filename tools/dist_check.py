@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check, launched with torch.distributed.run (one rank per GPU):
+the row-partitioned power iteration (halo and allgather refresh) must reproduce the single-GPU iteration
+on every rank's owned + referenced part of x.  Rows of the 7-point Laplacian are summed by one lane in
+index order on every rank, so the comparison is BITWISE apart from the norm (an N-rank all-reduce of
+|y|^2 associates differently from the single-GPU sum): x is compared with 1e-13 relative tolerance and
+lambda with 1e-13.  Prints 'DIST_CHECK OK' on rank 0."""
+import os
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from sparsematrixvectormultiplication_b200 import synth  # noqa: E402
+from sparsematrixvectormultiplication_b200.distributed import FusedPowerIteration, PowerIteration  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, iters = int(sys.argv[1]) if len(sys.argv) > 1 else 48, 12
+    ref = PowerIteration(synth.SYNTH_LAP3D, n, single=True)
+    lam_ref = []
+    for _ in range(iters):
+        ref.step()
+        lam_ref.append(ref.eigenvalue_estimate())
+    ok = True
+    for mode in ("halo", "allgather"):
+        P = PowerIteration(synth.SYNTH_LAP3D, n, exchange=mode)
+        lam = []
+        for _ in range(iters):
+            P.step()
+            lam.append(P.eigenvalue_estimate())
+        torch.cuda.synchronize()
+        lo = min([P.row_begin] + [a for _, a, _ in P.plan.recvs]) if mode == "halo" else 0
+        hi = max([P.row_end] + [b for _, _, b in P.plan.recvs]) if mode == "halo" else P.N
+        err = float((P.x[lo:hi] - ref.x[lo:hi]).abs().max() / ref.x.abs().max())
+        lam_err = max(abs(a - b) / b for a, b in zip(lam, lam_ref))
+        # the product itself must be bitwise partition independent: same x in, same y out on the owned rows
+        P.x.copy_(ref.x)
+        P.A.spmv(P.x, P.y)
+        ref.A.spmv(ref.x, ref.y)
+        same = bool(torch.equal(P.y[:P.rows], ref.y[P.row_begin:P.row_end]))
+        good = err <= 1e-13 and lam_err <= 1e-13 and same
+        print(f"rank {rank}/{world} {mode}: rows [{P.row_begin},{P.row_end}) recv {P.plan.halo_doubles_received() if mode == 'halo' else P.plan.allgather_doubles_received()} "
+              f"doubles/iter, x err {err:.2e}, lambda err {lam_err:.2e}, product bitwise {same} -> {'ok' if good else 'FAIL'}", flush=True)
+        ok = ok and good
+    for peer_stores in (True, False):
+        F = FusedPowerIteration(synth.SYNTH_LAP3D, n, peer_stores=peer_stores)
+        lam = []
+        for _ in range(iters):
+            F.step()
+            lam.append(F.eigenvalue_estimate())
+        torch.cuda.synchronize()
+        v = F.normalized_x()
+        lo = min([F.row_begin] + [a for _, a, _ in F.plan.recvs])
+        hi = max([F.row_end] + [b for _, _, b in F.plan.recvs])
+        err = float((v[lo:hi] - ref.x[lo:hi]).abs().max() / ref.x.abs().max())
+        lam_err = max(abs(a - b) / b for a, b in zip(lam, lam_ref))
+        good = err <= 1e-12 and lam_err <= 1e-12
+        print(f"rank {rank}/{world} fused peer_stores={peer_stores}: x err {err:.2e}, lambda err {lam_err:.2e} -> {'ok' if good else 'FAIL'}", flush=True)
+        ok = ok and good
+        F.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("DIST_CHECK OK" if int(flag.item()) else "DIST_CHECK FAILED", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
