@@ -47,6 +47,25 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """Everything that libraries print on fd 1 (NCCL's version banner, the reference's printf()s) goes to
+    stderr; the one JSON line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -275,7 +294,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "GFLOP/s", "cores": len(starts), "kind": chk.kind, "sample": sample},
             "e2e": {"value": value, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def bench_single_gpu(args):
@@ -348,7 +367,7 @@ def bench_single_gpu(args):
                          "kernel_ms_min": min(per), "kernel_ms_median": statistics.median(per)},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "clocks": sampler.summary(), "others": others}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def measure_others(args, A2d, x2d, y2d, peak, sampler):
@@ -521,7 +540,7 @@ def bench_multi_gpu(args):
                         "note": "iterated product: x and y never leave the devices between iterations; see the N=1 line for the host-buffer path"},
                 "gpu_launches": h["launches_per_step"] * args.steps, "clocks": sampler.summary() if sampler else None,
                 "exchange_modes": {k: v for k, v in results.items() if isinstance(v, dict)}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -538,6 +557,7 @@ def main():
     ap.add_argument("--lap3d-n", type=int, default=512)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    capture_stdout()
     if args.impl == "reference":
         return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -124,7 +124,7 @@ constexpr int kSerialRowMax = 12;  // chunks whose longest row is at most this l
 // =================================================================================================
 // CSR
 // =================================================================================================
-template <int kConsumerWarps>
+template <int kConsumerWarps, bool kFused>
 __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, (kConsumerWarps >= 24 ? 1 : 2))
 csr_stream_kernel(const int2 *__restrict__ tiles, int num_tiles, const int *__restrict__ row_ptr,
                   const int *__restrict__ col_idx, const double *__restrict__ values, const double *__restrict__ x,
@@ -175,16 +175,18 @@ csr_stream_kernel(const int2 *__restrict__ tiles, int num_tiles, const int *__re
 
     // ---------------- consumers: independent warps, lane = row (or a slice of a row) ----------------
     __shared__ double warp_sq[kConsumerWarps];
-    const bool scaled = ep.prev_sumsq != nullptr;
+    const bool scaled = kFused && ep.prev_sumsq != nullptr;
     const double prev_norm = scaled ? sqrt(*ep.prev_sumsq) : 1.0;
     double sq = 0.0;  // sum of the squares of the rows this lane produced
-    // y[row] = v (after the optional scaling), mirrored into the peers that reference the row
+    // y[row] = v; the fused instantiation scales it first, accumulates v^2 and mirrors boundary rows into the peers
     auto emit = [&](int row, double v) {
-        if (scaled) v = v / prev_norm;
+        if constexpr (kFused) {
+            if (scaled) v = v / prev_norm;
+            sq = fma(v, v, sq);
+            for (int p = 0; p < ep.peers.count; ++p)
+                if (row >= ep.peers.lo[p] && row < ep.peers.hi[p]) ep.peers.dst[p][row] = v;
+        }
         y[row] = v;
-        sq = fma(v, v, sq);
-        for (int p = 0; p < ep.peers.count; ++p)
-            if (row >= ep.peers.lo[p] && row < ep.peers.hi[p]) ep.peers.dst[p][row] = v;
     };
     int2 head = make_int2(0, 0), tail = make_int2(0, 0);
     if ((int)blockIdx.x < num_tiles) {
@@ -254,7 +256,7 @@ csr_stream_kernel(const int2 *__restrict__ tiles, int num_tiles, const int *__re
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
     }
-    if (ep.partials != nullptr) {  // fixed-order CTA sum of squares (consumer warps only: the producer has left)
+    if (kFused && ep.partials != nullptr) {  // fixed-order CTA sum of squares (consumer warps only: the producer has left)
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
         if (lane == 0) warp_sq[warp] = sq;
@@ -445,6 +447,9 @@ static int pick_consumers(int fallback) {
         default: { auto kfn = KERNEL<12>; EXPR; } break;    \
     }
 
+template <int C> constexpr auto csr_plain_kernel = csr_stream_kernel<C, false>;
+template <int C> constexpr auto csr_fused_kernel = csr_stream_kernel<C, true>;
+
 int stream_prepare_csr(spmv_b200_csr *A) {
     A->stages = std::max(1, std::min(env_int("SPMV_B200_STAGES", kDefaultStages), 8));
     A->stream_grid = 0;
@@ -456,8 +461,13 @@ int stream_prepare_csr(spmv_b200_csr *A) {
     }
     A->consumers = pick_consumers(kDefaultCsrConsumers);
     int rc = SPMV_B200_OK;
-    STREAM_DISPATCH(A->consumers, csr_stream_kernel,
+    STREAM_DISPATCH(A->consumers, csr_plain_kernel,
                     rc = pick_grid(reinterpret_cast<const void *>(kfn), (A->consumers + 1) * 32, smem, A->num_tiles, A->stream_grid));
+    int fused_grid = 0;
+    if (rc == SPMV_B200_OK)
+        STREAM_DISPATCH(A->consumers, csr_fused_kernel,
+                        rc = pick_grid(reinterpret_cast<const void *>(kfn), (A->consumers + 1) * 32, smem, A->num_tiles, fused_grid));
+    if (rc == SPMV_B200_OK) A->stream_grid = std::min(A->stream_grid, fused_grid);
     return rc;
 }
 
@@ -470,10 +480,17 @@ int stream_launch_csr(const spmv_b200_csr *A, const double *x, double *y, int ac
     none.peers.count = 0;
     const Epilogue e = ep ? *ep : none;
     const size_t smem = csr_stream_smem(A);
-    STREAM_DISPATCH(A->consumers, csr_stream_kernel,
-                    (kfn<<<A->stream_grid, (A->consumers + 1) * 32, smem, stream>>>(
-                        A->tiles, A->num_tiles, A->row_ptr, A->col_idx, A->values, x, y, A->M, (int)A->nnz,
-                        csr_stage_bytes(A), A->stages, A->long_threshold, A->forced_tpr, accumulate, e)));
+    if (ep) {
+        STREAM_DISPATCH(A->consumers, csr_fused_kernel,
+                        (kfn<<<A->stream_grid, (A->consumers + 1) * 32, smem, stream>>>(
+                            A->tiles, A->num_tiles, A->row_ptr, A->col_idx, A->values, x, y, A->M, (int)A->nnz,
+                            csr_stage_bytes(A), A->stages, A->long_threshold, A->forced_tpr, accumulate, e)));
+    } else {
+        STREAM_DISPATCH(A->consumers, csr_plain_kernel,
+                        (kfn<<<A->stream_grid, (A->consumers + 1) * 32, smem, stream>>>(
+                            A->tiles, A->num_tiles, A->row_ptr, A->col_idx, A->values, x, y, A->M, (int)A->nnz,
+                            csr_stage_bytes(A), A->stages, A->long_threshold, A->forced_tpr, accumulate, e)));
+    }
     SPMV_TRY_CUDA(cudaGetLastError());
     return SPMV_B200_OK;
 }
