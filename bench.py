@@ -40,7 +40,7 @@ HBM_NOMINAL_GBS = 8000.0   # BASELINE.json quotes fractions of 8 TB/s
 FALLBACK_PEAK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
 # ncu --set full capture (profiles/); None until a capture exists for that kernel.
-NCU_TRAFFIC_BYTES = {"lap2d_4096_csr": None}
+NCU_TRAFFIC_BYTES = {"lap2d_4096_csr": 1308490000}  # profiles/r01c_ncu_full_summary.md
 
 
 def log(*a):
