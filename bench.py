@@ -396,6 +396,7 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler):
         run(f"{name}_csr_stream_kernel", lambda: A.spmv(x, y, algo=device.ALGO_STREAM), ia.nnz, ia.algorithmic_bytes)
         run(f"{name}_csr_tile_kernel", lambda: A.spmv(x, y, algo=device.ALGO_TILE), ia.nnz, ia.algorithmic_bytes)
         run(f"{name}_csr_vector_kernel", lambda: A.spmv(x, y, algo=device.ALGO_VECTOR), ia.nnz, ia.algorithmic_bytes)
+        run(f"{name}_csr_binned_kernel", lambda: A.spmv(x, y, algo=device.ALGO_BINNED), ia.nnz, ia.algorithmic_bytes)
 
     def hll_variants(name, A, x, y):
         ia = A.info()

@@ -42,10 +42,11 @@ extern "C" {
 #define SPMV_B200_ERR_NOMEM (-4)
 
 /* CSR kernel selection for spmv_b200_csr_spmv */
-#define SPMV_B200_ALGO_AUTO 0     /* STREAM for short rows (<= 12 nnz/row on average), else TILE */
+#define SPMV_B200_ALGO_AUTO 0     /* STREAM for short rows (<= 12 nnz/row on average), else VECTOR (even rows) or BINNED (skewed) */
 #define SPMV_B200_ALGO_VECTOR 1   /* plain vector-per-row kernel with shuffle reduction      */
 #define SPMV_B200_ALGO_TILE 2     /* row-binned tile kernel, one CTA per tile, direct loads  */
 #define SPMV_B200_ALGO_STREAM 3   /* persistent row-binned kernel, TMA bulk-copy pipeline    */
+#define SPMV_B200_ALGO_BINNED 4   /* rows binned by length: 1..32 lanes per row, longest rows split */
 
 /* synthetic CSR generators (BASELINE.json configs 2, 3, 5) */
 #define SPMV_B200_SYNTH_LAP2D 1   /* p0 = n   : 5-point Laplacian on an n x n grid           */
@@ -124,6 +125,30 @@ int spmv_b200_csr_partials_count(const spmv_b200_csr *A);
 int spmv_b200_csr_spmv_fused(const spmv_b200_csr *A, const double *d_x, double *d_y, const double *d_prev_sumsq,
                              double *d_partials, const spmv_b200_peers_t *peers, void *stream);
 
+/* The same launch with the exchange of |w|^2 folded in as well -- no collective library call in the loop.
+ * Every rank owns a "mailbox" in peer-mappable memory (spmv_b200_ipc_alloc, SPMV_B200_MAILBOX_BYTES, zeroed):
+ * 2 parities x world slots of {sum, tag}.  Launch k (mail->iteration = k, 0-based):
+ *   start: if k > 0, waits until all `world` slots of parity (k-1)&1 in its OWN mailbox carry tag k (i.e. every rank,
+ *          itself included, has finished launch k-1 and its boundary rows have landed here), adds the sums in rank
+ *          order and divides every row by the square root;
+ *   end:   the last CTA to finish adds the per-CTA partials in a fixed order and writes {sum, tag k+1} into slot
+ *          [k&1][rank] of EVERY rank's mailbox (box[r], NVLink peer stores, release at system scope).
+ * counter: one zeroed unsigned int in local memory (self-resetting).  status: one int in local memory, set to 1 if a
+ * wait gave up after ~2 s (a peer died): results are then invalid, but the kernel never hangs.
+ * Launches of one rank must be stream ordered; ranks must not share a GPU (a launch waits for its peers' previous
+ * launch). */
+#define SPMV_B200_MAX_RANKS 8
+#define SPMV_B200_MAILBOX_BYTES (2 * SPMV_B200_MAX_RANKS * 16)
+typedef struct {
+    int world, rank;
+    unsigned long long iteration;
+    unsigned long long *box[SPMV_B200_MAX_RANKS]; /* box[r] = rank r's mailbox as mapped HERE; box[rank] is local */
+    unsigned int *counter;
+    int *status;
+} spmv_b200_mail_t;
+int spmv_b200_csr_spmv_fused_mail(const spmv_b200_csr *A, const double *d_x, double *d_y, double *d_partials,
+                                  const spmv_b200_peers_t *peers, const spmv_b200_mail_t *mail, void *stream);
+
 int spmv_b200_csr_spmv_rows(const spmv_b200_csr *A, int row_begin, int row_end, const double *d_x,
                             double *d_y, void *stream);
 void spmv_b200_csr_free(spmv_b200_csr *A);
@@ -158,6 +183,15 @@ int spmv_b200_hll_spmv_host(spmv_b200_hll *H, const double *x, double *y);
 int spmv_b200_hll_spmv_hacks(const spmv_b200_hll *H, int hack_begin, int hack_end, const double *d_x,
                              double *d_y, void *stream);
 void spmv_b200_hll_free(spmv_b200_hll *H);
+
+/* ---- timing harness on a resident matrix: the reference driver's protocol (main_cuda.cu:159-200: cudaEvents around
+ * every product, the first `warmup` iterations not counted, mean over the rest) behind one call, so that a C
+ * driver needs no CUDA runtime of its own.  x: host vector, uploaded once (as main_cuda.cu:145); y: host result of
+ * the last product (may be NULL).  kernel for HLL: 0 automatic, 1 slice kernel, 2 stream kernel. ---- */
+int spmv_b200_csr_time(spmv_b200_csr *A, const double *x, double *y, int algo, int warmup, int iters,
+                       double *mean_seconds, double *min_seconds);
+int spmv_b200_hll_time(spmv_b200_hll *H, const double *x, double *y, int kernel, int warmup, int iters,
+                       double *mean_seconds, double *min_seconds);
 
 /* ---- synthetic matrices generated on the device (rows [row_begin,row_end) of the global
  * matrix, global column ids, local row_ptr starting at 0); see SURVEY.md section 8(d) ---- */

@@ -7,11 +7,13 @@ needs it raises ``NativeLibraryMissing``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libspmv_b200.so"
+# SPMV_B200_LIB: another build of the SAME library (tools/ab_variants.py compares compile-time variants on one box)
+LIB_PATH = Path(os.environ.get("SPMV_B200_LIB") or PKG_DIR / "libspmv_b200.so")
 HACK_SIZE = 32
 
 c_int_p = C.POINTER(C.c_int)
@@ -70,6 +72,13 @@ class Peers(C.Structure):  # include/spmv_b200.h spmv_b200_peers_t
     _fields_ = [("count", C.c_int), ("dst", C.c_void_p * 7), ("lo", C.c_int * 7), ("hi", C.c_int * 7)]
 
 
+class Mail(C.Structure):  # include/spmv_b200.h spmv_b200_mail_t
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("iteration", C.c_ulonglong), ("box", C.c_void_p * 8),
+                ("counter", C.c_void_p), ("status", C.c_void_p)]
+
+
+MAILBOX_BYTES = 2 * 8 * 16
+
 _V = C.c_void_p
 _I = C.c_int
 _LL = C.c_longlong
@@ -95,6 +104,7 @@ SIGNATURES = {
     "spmv_b200_csr_spmv_rows": (_I, [_V, _I, _I, _V, _V, _V]),
     "spmv_b200_csr_partials_count": (_I, [_V]),
     "spmv_b200_csr_spmv_fused": (_I, [_V, _V, _V, _V, _V, C.POINTER(Peers), _V]),
+    "spmv_b200_csr_spmv_fused_mail": (_I, [_V, _V, _V, _V, C.POINTER(Peers), C.POINTER(Mail), _V]),
     "spmv_b200_vec_sum": (_I, [_V, _I, _V, _V]),
     "spmv_b200_ipc_alloc": (_I, [_LL, C.POINTER(_V), C.c_char * 64]),
     "spmv_b200_ipc_open": (_I, [C.c_char * 64, C.POINTER(_V)]),
@@ -110,6 +120,8 @@ SIGNATURES = {
     "spmv_b200_hll_spmv_slice": (_I, [_V, _V, _V, _V]),
     "spmv_b200_hll_spmv_stream": (_I, [_V, _V, _V, _V]),
     "spmv_b200_hll_spmv_host": (_I, [_V, _V, _V]),
+    "spmv_b200_csr_time": (_I, [_V, _V, _V, _I, _I, _I, c_dbl_p, c_dbl_p]),
+    "spmv_b200_hll_time": (_I, [_V, _V, _V, _I, _I, _I, c_dbl_p, c_dbl_p]),
     "spmv_b200_hll_spmv_hacks": (_I, [_V, _I, _I, _V, _V, _V]),
     "spmv_b200_hll_free": (None, [_V]),
     "spmv_b200_synth_csr": (_I, [_I, _LL, _LL, _I, _ULL, _LL, _LL, _V, C.POINTER(_V)]),

@@ -78,8 +78,25 @@ __device__ __forceinline__ int ldg_stream_s32(const int *p) {
 }
 
 // x is gathered through the read-only path (LDG.CONSTANT), allocating in L1: neighbouring rows of
-// banded matrices hit the same lines.
-__device__ __forceinline__ double ldg_x(const double *x, int col) { return __ldg(x + col); }
+// banded matrices hit the same lines -- and, more important, a gather that misses needs an L1 line while it is in
+// flight: with L1::no_allocate the same kernels ran 3x slower on random columns (profiles/r01d_kernel_selection.md).
+// SPMV_X_EVICT_LAST (off: measured +-1 %): the gathers also carry an L2 evict-last policy
+// (createpolicy + ld.global.nc.L2::cache_hint), so that x outlives the once-read matrix stream in L2.
+__device__ __forceinline__ unsigned long long policy_evict_last() {
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));  // pure: hoisted out of loops
+    return p;
+}
+
+__device__ __forceinline__ double ldg_x(const double *x, int col) {
+#if defined(SPMV_X_EVICT_LAST)
+    double r;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(x + col), "l"(policy_evict_last()));
+    return r;
+#else
+    return __ldg(x + col);
+#endif
+}
 
 // ---- per-row sums of products parked in shared memory, one warp per chunk of 32 rows ---------------
 constexpr int kLaneRowMax = 64;  // rows up to this length are summed by their own lane, longer ones by the whole warp

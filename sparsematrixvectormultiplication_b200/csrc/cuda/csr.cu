@@ -33,6 +33,7 @@ constexpr int kAutoStreamMaxAvg = 12;  // ALGO_AUTO: stream kernel up to this ma
 constexpr int kFragNnz = 8192;              // nonzeros per long-row fragment (one CTA)
 constexpr int kFragThreads = 256;
 constexpr int kSmemSlack = 8;
+constexpr int kVecBatch = 4;                // independent column -> gather chains per lane of the vector kernel
 
 // ================================================================================================
 // kernels
@@ -73,17 +74,10 @@ csr_tile_kernel(const int2 *__restrict__ tiles, const int *__restrict__ row_ptr,
     const int n0 = head.y, n1 = tail.y;
     if (rows == 1 && n1 - n0 > long_threshold) return;  // long row: csr_long_* kernels own it
 
-    // row bounds of this thread's first row (one-thread-per-row mode): issued now, consumed after the barrier
-    int my_row = tid;
-    int seg_lo = 0, seg_hi = 0;
-    if (forced_tpr == 1 && my_row < rows) {
-        seg_lo = __ldg(row_ptr + r0 + my_row);
-        seg_hi = __ldg(row_ptr + r0 + my_row + 1);
-    }
-
-    // ---- phase A: stream the tile, park the products ------------------------------------------
     const int a0 = n0 & ~3;  // 16 B (columns) / 32 B (values) aligned start
     const int ngroups = (n1 - a0 + 3) >> 2;
+
+    // ---- phase A: stream the tile, park the products ------------------------------------------
     int g = tid;
     for (; g + kTileThreads < ngroups; g += 2 * kTileThreads) {  // two groups in flight per thread
         double p0[4], p1[4];
@@ -107,15 +101,11 @@ csr_tile_kernel(const int2 *__restrict__ tiles, const int *__restrict__ row_ptr,
 
     // ---- phase B: per-row reduction out of shared memory ---------------------------------------
     if (forced_tpr == 1) {  // one thread per row, left to right: bit-identical to the reference's serial loop
-        for (; my_row < rows; my_row += kTileThreads) {
+        for (int my_row = tid; my_row < rows; my_row += kTileThreads) {
             double acc = accumulate ? y[r0 + my_row] : 0.0;
-            for (int k = seg_lo - a0; k < seg_hi - a0; ++k) acc = __dadd_rn(acc, prod[k]);
+            const int seg_lo = __ldg(row_ptr + r0 + my_row) - a0, seg_hi = __ldg(row_ptr + r0 + my_row + 1) - a0;
+            for (int k = seg_lo; k < seg_hi; ++k) acc = __dadd_rn(acc, prod[k]);
             y[r0 + my_row] = acc;
-            const int next = my_row + kTileThreads;
-            if (next < rows) {
-                seg_lo = __ldg(row_ptr + r0 + next);
-                seg_hi = __ldg(row_ptr + r0 + next + 1);
-            }
         }
     } else {  // one warp per chunk of 32 rows (common.cuh: chunk_row_sum)
         const int lane = tid & 31;
@@ -149,9 +139,21 @@ csr_long_fragment_kernel(const int *__restrict__ long_rows, const int *__restric
     const long long begin = (long long)__ldg(row_ptr + row) + (long long)(f - __ldg(frag_first + lo)) * kFragNnz;
     const long long row_end = __ldg(row_ptr + row + 1);
     const long long end = begin + kFragNnz < row_end ? begin + kFragNnz : row_end;
+    // batches of kVecBatch: all column / value loads, then all gathers, then the fmas (one round trip per batch)
     double acc = 0.0;
-    for (long long k = begin + threadIdx.x; k < end; k += kFragThreads)
-        acc = fma(ldg_stream_f64(values + k), ldg_x(x, ldg_stream_s32(col_idx + k)), acc);
+    for (long long k = begin + threadIdx.x; k < end; k += (long long)kVecBatch * kFragThreads) {
+        int c[kVecBatch];
+        double v[kVecBatch], xv[kVecBatch];
+#pragma unroll
+        for (int u = 0; u < kVecBatch; ++u) c[u] = k + u * kFragThreads < end ? ldg_stream_s32(col_idx + k + u * kFragThreads) : -1;
+#pragma unroll
+        for (int u = 0; u < kVecBatch; ++u) v[u] = k + u * kFragThreads < end ? ldg_stream_f64(values + k + u * kFragThreads) : 0.0;
+#pragma unroll
+        for (int u = 0; u < kVecBatch; ++u) xv[u] = c[u] >= 0 ? ldg_x(x, c[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < kVecBatch; ++u)
+            if (c[u] >= 0) acc = fma(v[u], xv[u], acc);
+    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = acc;
@@ -190,12 +192,114 @@ csr_vector_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, c
         lo = __ldg(row_ptr + row);
         hi = __ldg(row_ptr + row + 1);
     }
+    // kVecBatch column/value loads are issued before the first gather and the gathers before the first fma: the
+    // column -> x dependency costs one round trip per batch instead of one per element
     double acc = 0.0;
-    for (int k = lo + lane; k < hi; k += VEC)
-        acc = fma(ldg_stream_f64(values + k), ldg_x(x, ldg_stream_s32(col_idx + k)), acc);
+    for (int k = lo + lane; k < hi; k += kVecBatch * VEC) {
+        int c[kVecBatch];
+        double v[kVecBatch], xv[kVecBatch];
+#pragma unroll
+        for (int u = 0; u < kVecBatch; ++u) c[u] = k + u * VEC < hi ? ldg_stream_s32(col_idx + k + u * VEC) : -1;
+#pragma unroll
+        for (int u = 0; u < kVecBatch; ++u) v[u] = k + u * VEC < hi ? ldg_stream_f64(values + k + u * VEC) : 0.0;
+#pragma unroll
+        for (int u = 0; u < kVecBatch; ++u) xv[u] = c[u] >= 0 ? ldg_x(x, c[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < kVecBatch; ++u)
+            if (c[u] >= 0) acc = fma(v[u], xv[u], acc);
+    }
 #pragma unroll
     for (int off = VEC >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (live && lane == 0) y[row] = accumulate ? y[row] + acc : acc;
+}
+
+// ---- row-binned vector kernel (skewed matrices) ------------------------------------------------------
+// Rows are binned by length at plan time; bin b < 6 gives every row 2^b lanes (about a quarter of its length, so
+// each lane owns one batch of kVecBatch gathers), the rows of one bin are processed in ascending row order, and all
+// bins run in ONE launch (a CTA finds its bin from block_start[]).  No shared memory: the whole L1 stays available
+// to the gathers of x -- on this chip the number of gathers in flight is bounded by L1 lines, and gather-heavy
+// kernels lose more to a smaller L1 than they gain from staging (profiles/r01d_kernel_selection.md).
+constexpr int kBinLongThreshold = 2048;  // rows above this are split into kFragNnz fragments (csr_long_* kernels)
+
+__host__ __device__ __forceinline__ int bin_of(int len) {
+    if (len <= 6) return 0;
+    if (len <= 12) return 1;
+    if (len <= 24) return 2;
+    if (len <= 48) return 3;
+    if (len <= 96) return 4;
+    return len <= kBinLongThreshold ? 5 : 6;
+}
+
+struct BinLaunch {
+    int offset[kBins + 1];
+    int block_start[kBins];
+};
+
+template <int VEC>
+__device__ __forceinline__ void binned_rows(int local_block, int first, int count, const int *__restrict__ bin_rows,
+                                            const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                                            const double *__restrict__ values, const double *__restrict__ x,
+                                            double *__restrict__ y, int accumulate) {
+    const int idx = (local_block * 256 + (int)threadIdx.x) / VEC;
+    const int lane = threadIdx.x & (VEC - 1);
+    const bool live = idx < count;
+    int row = 0, lo = 0, hi = 0;
+    if (live) {
+        row = __ldg(bin_rows + first + idx);
+        lo = __ldg(row_ptr + row);
+        hi = __ldg(row_ptr + row + 1);
+    }
+    double acc = 0.0;
+    for (int k = lo + lane; k < hi; k += kVecBatch * VEC) {
+        int c[kVecBatch];
+        double v[kVecBatch], xv[kVecBatch];
+#pragma unroll
+        for (int u = 0; u < kVecBatch; ++u) c[u] = k + u * VEC < hi ? ldg_stream_s32(col_idx + k + u * VEC) : -1;
+#pragma unroll
+        for (int u = 0; u < kVecBatch; ++u) v[u] = k + u * VEC < hi ? ldg_stream_f64(values + k + u * VEC) : 0.0;
+#pragma unroll
+        for (int u = 0; u < kVecBatch; ++u) xv[u] = c[u] >= 0 ? ldg_x(x, c[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < kVecBatch; ++u)
+            if (c[u] >= 0) acc = fma(v[u], xv[u], acc);
+    }
+#pragma unroll
+    for (int off = VEC >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (live && lane == 0) y[row] = accumulate ? y[row] + acc : acc;
+}
+
+__global__ void __launch_bounds__(256)
+csr_binned_kernel(const BinLaunch plan, const int *__restrict__ bin_rows, const int *__restrict__ row_ptr,
+                  const int *__restrict__ col_idx, const double *__restrict__ values, const double *__restrict__ x,
+                  double *__restrict__ y, int accumulate) {
+    int bin = 0;
+    while (bin < kBins - 2 && (int)blockIdx.x >= plan.block_start[bin + 1]) ++bin;  // CTA-uniform
+    const int local_block = blockIdx.x - plan.block_start[bin];
+    const int first = plan.offset[bin], count = plan.offset[bin + 1] - first;
+    switch (bin) {
+        case 0: binned_rows<1>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
+        case 1: binned_rows<2>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
+        case 2: binned_rows<4>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
+        case 3: binned_rows<8>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
+        case 4: binned_rows<16>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
+        default: binned_rows<32>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
+    }
+}
+
+__global__ void bin_key_kernel(int M, const int *__restrict__ row_ptr, unsigned char *__restrict__ keys,
+                               int *__restrict__ ids, int *__restrict__ counts) {
+    __shared__ int local[kBins];
+    if (threadIdx.x < kBins) local[threadIdx.x] = 0;
+    __syncthreads();
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < M) {
+        const int b = bin_of(row_ptr[r + 1] - row_ptr[r]);
+        keys[r] = (unsigned char)b;
+        ids[r] = (int)r;
+        atomicAdd(&local[b], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < kBins && local[threadIdx.x]) atomicAdd(&counts[threadIdx.x], local[threadIdx.x]);  // integer: order independent
 }
 
 // ---- plan construction kernels ------------------------------------------------------------------
@@ -247,7 +351,15 @@ __global__ void plan_fragcount_kernel(int num_long, const int *__restrict__ long
 
 namespace spmv {
 
+static void free_bins(spmv_b200_csr *A) {
+    cudaFree(A->bins.rows);
+    cudaFree(A->bins.frag_first);
+    cudaFree(A->bins.frag_partial);
+    A->bins = BinPlan();
+}
+
 static void free_plan(spmv_b200_csr *A) {
+    free_bins(A);
     cudaFree(A->tiles);
     cudaFree(A->long_rows);
     cudaFree(A->frag_first);
@@ -259,12 +371,16 @@ static void free_plan(spmv_b200_csr *A) {
     A->num_tiles = A->num_long = A->num_frag = 0;
 }
 
-static size_t tile_smem_bytes(const spmv_b200_csr *A) {  // products of the largest possible tile
+// products of the largest possible tile.  Kept small on purpose: shared memory is carved out of the L1 that the
+// gathers of x need for their lines in flight (a 55 KB variant that also staged row_ptr ran 2.4x slower).
+static size_t tile_smem_bytes(const spmv_b200_csr *A) {
     return (size_t)(A->tile_items / 3 + A->long_threshold + kSmemSlack) * sizeof(double);
 }
 
 static int build_plan(spmv_b200_csr *A, cudaStream_t stream) {
     free_plan(A);
+    host_pipe_free(A->pipe);  // the row windows of the host entry point follow the tiles
+    A->pipe = nullptr;
     const int M = A->M;
     if (M == 0) return SPMV_B200_OK;
     if (tile_smem_bytes(A) > 200 * 1024) return fail(SPMV_B200_ERR_INVALID, "tile_items + long_threshold too large for shared memory");
@@ -353,13 +469,16 @@ static int build_plan(spmv_b200_csr *A, cudaStream_t stream) {
     return stream_prepare_csr(A);
 }
 
+// lanes per row: about a quarter of the mean row length, so that every lane owns one full batch of kVecBatch gathers
 static int pick_vector_width(long long nnz, int M) {
+    const int forced = env_int("SPMV_B200_VECTOR_WIDTH", 0);
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
     const double avg = M > 0 ? (double)nnz / M : 0.0;
-    if (avg <= 2.0) return 1;
-    if (avg <= 4.0) return 2;
-    if (avg <= 8.0) return 4;
-    if (avg <= 16.0) return 8;
-    if (avg <= 32.0) return 16;
+    if (avg <= 6.0) return 1;
+    if (avg <= 12.0) return 2;
+    if (avg <= 24.0) return 4;
+    if (avg <= 48.0) return 8;
+    if (avg <= 96.0) return 16;
     return 32;
 }
 
@@ -382,17 +501,21 @@ static int launch_vector(int row_begin, int row_end, const int *row_ptr, const i
     return SPMV_B200_OK;
 }
 
+// tiles [tile_begin, tile_end) of the plan; the long rows (if any) ride with the call that covers the last tile
 static int launch_tiles(const spmv_b200_csr *A, const double *x, double *y, int accumulate, bool pipelined,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, int tile_begin = 0, int tile_end = -1) {
     if (A->num_tiles == 0) return SPMV_B200_OK;
+    if (tile_end < 0) tile_end = A->num_tiles;
+    if (tile_end <= tile_begin) return SPMV_B200_OK;
     if (pipelined) {
-        SPMV_TRY(stream_launch_csr(A, x, y, accumulate, nullptr, stream));
+        SPMV_TRY(stream_launch_csr(A, x, y, accumulate, nullptr, stream, tile_begin, tile_end - tile_begin));
     } else {
-        csr_tile_kernel<<<A->num_tiles, kTileThreads, tile_smem_bytes(A), stream>>>(
-            A->tiles, A->row_ptr, A->col_idx, A->values, x, y, (int)A->nnz, A->long_threshold, A->forced_tpr, accumulate);
+        csr_tile_kernel<<<tile_end - tile_begin, kTileThreads, tile_smem_bytes(A), stream>>>(
+            A->tiles + tile_begin, A->row_ptr, A->col_idx, A->values, x, y, (int)A->nnz, A->long_threshold, A->forced_tpr,
+            accumulate);
         SPMV_TRY_CUDA(cudaGetLastError());
     }
-    if (A->num_long > 0) {
+    if (A->num_long > 0 && tile_end == A->num_tiles) {
         csr_long_fragment_kernel<<<A->num_frag, kFragThreads, 0, stream>>>(A->long_rows, A->frag_first, A->num_long,
                                                                           A->row_ptr, A->col_idx, A->values, x,
                                                                           A->frag_partial);
@@ -403,6 +526,123 @@ static int launch_tiles(const spmv_b200_csr *A, const double *x, double *y, int 
         SPMV_TRY_CUDA(cudaGetLastError());
     }
     return SPMV_B200_OK;
+}
+
+// Bin plan: stable sort of the row ids by bin (radix sort on 3-bit keys), bin offsets, fragments of the longest rows.
+static int build_bins(spmv_b200_csr *A, cudaStream_t stream) {
+    free_bins(A);
+    const int M = A->M;
+    BinPlan &B = A->bins;
+    unsigned char *keys = nullptr, *keys_sorted = nullptr;
+    int *ids = nullptr, *d_counts = nullptr, *frag_counts = nullptr;
+    void *temp = nullptr;
+    auto body = [&]() -> int {
+        SPMV_TRY_CUDA(cudaMalloc(&keys, (size_t)M));
+        SPMV_TRY_CUDA(cudaMalloc(&keys_sorted, (size_t)M));
+        SPMV_TRY_CUDA(cudaMalloc(&ids, (size_t)M * sizeof(int)));
+        SPMV_TRY_CUDA(cudaMalloc(&B.rows, (size_t)M * sizeof(int)));
+        SPMV_TRY_CUDA(cudaMalloc(&d_counts, kBins * sizeof(int)));
+        SPMV_TRY_CUDA(cudaMemsetAsync(d_counts, 0, kBins * sizeof(int), stream));
+        bin_key_kernel<<<blocks_for(M, 256), 256, 0, stream>>>(M, A->row_ptr, keys, ids, d_counts);
+        SPMV_TRY_CUDA(cudaGetLastError());
+        size_t temp_bytes = 0;
+        SPMV_TRY_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys, keys_sorted, ids, B.rows, M, 0, 3, stream));
+        SPMV_TRY_CUDA(cudaMalloc(&temp, temp_bytes ? temp_bytes : 1));
+        SPMV_TRY_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_sorted, ids, B.rows, M, 0, 3, stream));
+        int counts[kBins];
+        SPMV_TRY_CUDA(cudaMemcpyAsync(counts, d_counts, sizeof counts, cudaMemcpyDeviceToHost, stream));
+        SPMV_TRY_CUDA(cudaStreamSynchronize(stream));
+        B.offset[0] = 0;
+        for (int b = 0; b < kBins; ++b) B.offset[b + 1] = B.offset[b] + counts[b];
+        long long blocks = 0;
+        for (int b = 0; b < kBins - 1; ++b) {
+            B.block_start[b] = (int)blocks;
+            blocks += ((long long)counts[b] * (1 << b) + 255) / 256;
+        }
+        if (blocks > 0x7fffffffLL) return fail(SPMV_B200_ERR_INVALID, "bin plan: too many CTAs");
+        B.block_start[kBins - 1] = (int)blocks;
+        B.num_long = counts[kBins - 1];
+        if (B.num_long > 0) {
+            const int *long_rows = B.rows + B.offset[kBins - 1];
+            SPMV_TRY_CUDA(cudaMalloc(&frag_counts, (size_t)(B.num_long + 1) * sizeof(int)));
+            SPMV_TRY_CUDA(cudaMalloc(&B.frag_first, (size_t)(B.num_long + 1) * sizeof(int)));
+            plan_fragcount_kernel<<<blocks_for(B.num_long + 1, 256), 256, 0, stream>>>(B.num_long, long_rows, A->row_ptr, frag_counts);
+            SPMV_TRY_CUDA(cudaGetLastError());
+            size_t scan_bytes = 0;
+            SPMV_TRY_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, frag_counts, B.frag_first, B.num_long + 1, stream));
+            if (scan_bytes > temp_bytes) {
+                cudaFree(temp);
+                temp = nullptr;
+                SPMV_TRY_CUDA(cudaMalloc(&temp, scan_bytes));
+                temp_bytes = scan_bytes;
+            }
+            SPMV_TRY_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, frag_counts, B.frag_first, B.num_long + 1, stream));
+            SPMV_TRY_CUDA(cudaMemcpyAsync(&B.num_frag, B.frag_first + B.num_long, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            SPMV_TRY_CUDA(cudaStreamSynchronize(stream));
+            SPMV_TRY_CUDA(cudaMalloc(&B.frag_partial, (size_t)std::max(B.num_frag, 1) * sizeof(double)));
+        }
+        B.built = true;
+        return SPMV_B200_OK;
+    };
+    const int rc = body();
+    cudaFree(keys);
+    cudaFree(keys_sorted);
+    cudaFree(ids);
+    cudaFree(d_counts);
+    cudaFree(frag_counts);
+    cudaFree(temp);
+    if (rc != SPMV_B200_OK) free_bins(A);
+    return rc;
+}
+
+static int launch_binned(const spmv_b200_csr *A, const double *x, double *y, int accumulate, cudaStream_t stream) {
+    if (A->M == 0) return SPMV_B200_OK;
+    if (!A->bins.built) SPMV_TRY(build_bins(const_cast<spmv_b200_csr *>(A), stream));  // lazily, once per plan
+    const BinPlan &B = A->bins;
+    BinLaunch L;
+    for (int b = 0; b <= kBins; ++b) L.offset[b] = B.offset[b];
+    for (int b = 0; b < kBins; ++b) L.block_start[b] = B.block_start[b];
+    if (B.block_start[kBins - 1] > 0) {
+        csr_binned_kernel<<<B.block_start[kBins - 1], 256, 0, stream>>>(L, B.rows, A->row_ptr, A->col_idx, A->values, x, y, accumulate);
+        SPMV_TRY_CUDA(cudaGetLastError());
+    }
+    if (B.num_long > 0) {
+        const int *long_rows = B.rows + B.offset[kBins - 1];
+        csr_long_fragment_kernel<<<B.num_frag, kFragThreads, 0, stream>>>(long_rows, B.frag_first, B.num_long, A->row_ptr,
+                                                                         A->col_idx, A->values, x, B.frag_partial);
+        SPMV_TRY_CUDA(cudaGetLastError());
+        csr_long_combine_kernel<<<blocks_for(B.num_long, 128), 128, 0, stream>>>(long_rows, B.frag_first, B.num_long,
+                                                                                B.frag_partial, y, accumulate);
+        SPMV_TRY_CUDA(cudaGetLastError());
+    }
+    return SPMV_B200_OK;
+}
+
+// Which kernel a request resolves to.  AUTO: short rows (stencils) -> the TMA stream kernel, which runs at the HBM
+// roofline; longer rows mean many gathers of x per streamed byte, bounded by the L1TEX/L2 sector rate and by
+// the latency of gathers that miss L2 -- those need the occupancy of the direct-load kernels: vector-per-row when no
+// row is long, the row-binned tile kernel (+ long-row split) when the lengths are skewed
+// (profiles/r01c_ncu_full_summary.md).  threads_per_row == 1 is a request for the reference's summation order,
+// which the stream kernel honours.
+CsrPath csr_resolve(const spmv_b200_csr *A, int algo) {
+    switch (algo) {
+        case SPMV_B200_ALGO_STREAM: return kPathStream;
+        case SPMV_B200_ALGO_TILE: return kPathTile;
+        case SPMV_B200_ALGO_VECTOR: return kPathVector;
+        case SPMV_B200_ALGO_BINNED: return kPathBinned;
+        default:
+            if (A->forced_tpr == 1 || A->nnz <= (long long)kAutoStreamMaxAvg * A->M) return kPathStream;
+            return A->num_long == 0 ? kPathVector : kPathBinned;
+    }
+}
+
+int csr_launch_window(const spmv_b200_csr *A, CsrPath path, int unit_begin, int unit_end, const double *x, double *y,
+                      int accumulate, cudaStream_t stream) {
+    if (path == kPathBinned) return launch_binned(A, x, y, accumulate, stream);  // whole matrix: rows are permuted
+    if (path == kPathVector)
+        return launch_vector(unit_begin, unit_end, A->row_ptr, A->col_idx, A->values, x, y, pick_vector_width(A->nnz, A->M),
+                             accumulate, stream);
+    return launch_tiles(A, x, y, accumulate, path == kPathStream, stream, unit_begin, unit_end);
 }
 
 static int check_device() {
@@ -546,30 +786,9 @@ int spmv_b200_csr_download(const spmv_b200_csr *A, int *row_ptr, int *col_idx, d
 int spmv_b200_csr_spmv(const spmv_b200_csr *A, const double *d_x, double *d_y, int accumulate, int algo, void *stream) {
     if (!A || !d_y || (A->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "csr_spmv: NULL argument");
     if (A->M == 0) return SPMV_B200_OK;
-    switch (algo) {
-        case SPMV_B200_ALGO_AUTO:
-            // Short rows (stencils): the TMA stream kernel runs at the HBM roofline.  Longer rows mean many
-            // gathers of x per streamed byte, bounded by L2 sector throughput and by the latency of gathers that
-            // miss L2: those need the occupancy of the direct-load kernels -- vector-per-row when no row is long,
-            // the row-binned tile kernel (+ long-row split) when the lengths are skewed.  Measured on B200:
-            // profiles/r01b_kernel_selection.md.
-            // threads_per_row == 1 is a request for the reference's summation order: the stream kernel honours it
-            if (A->forced_tpr == 1 || A->nnz <= (long long)kAutoStreamMaxAvg * A->M)
-                return launch_tiles(A, d_x, d_y, accumulate, true, as_stream(stream));
-            if (A->num_long == 0)
-                return launch_vector(0, A->M, A->row_ptr, A->col_idx, A->values, d_x, d_y,
-                                     pick_vector_width(A->nnz, A->M), accumulate, as_stream(stream));
-            return launch_tiles(A, d_x, d_y, accumulate, false, as_stream(stream));
-        case SPMV_B200_ALGO_STREAM:
-            return launch_tiles(A, d_x, d_y, accumulate, true, as_stream(stream));
-        case SPMV_B200_ALGO_TILE:
-            return launch_tiles(A, d_x, d_y, accumulate, false, as_stream(stream));
-        case SPMV_B200_ALGO_VECTOR:
-            return launch_vector(0, A->M, A->row_ptr, A->col_idx, A->values, d_x, d_y, pick_vector_width(A->nnz, A->M),
-                                 accumulate, as_stream(stream));
-        default:
-            return fail(SPMV_B200_ERR_INVALID, "csr_spmv: unknown algo %d", algo);
-    }
+    if (algo < SPMV_B200_ALGO_AUTO || algo > SPMV_B200_ALGO_BINNED) return fail(SPMV_B200_ERR_INVALID, "csr_spmv: unknown algo %d", algo);
+    const CsrPath path = csr_resolve(A, algo);
+    return csr_launch_window(A, path, 0, path == kPathVector ? A->M : A->num_tiles, d_x, d_y, accumulate, as_stream(stream));
 }
 
 int spmv_b200_csr_partials_count(const spmv_b200_csr *A) { return A ? std::max(A->stream_grid, 1) : 0; }
@@ -585,8 +804,31 @@ int spmv_b200_csr_spmv_fused(const spmv_b200_csr *A, const double *d_x, double *
     ep.prev_sumsq = d_prev_sumsq;
     ep.partials = d_partials;
     ep.peers.count = 0;
+    ep.mail.world = 0;
     if (peers) ep.peers = *peers;
     if (A->M == 0) return SPMV_B200_OK;
+    return stream_launch_csr(A, d_x, d_y, 0, &ep, as_stream(stream));
+}
+
+int spmv_b200_csr_spmv_fused_mail(const spmv_b200_csr *A, const double *d_x, double *d_y, double *d_partials,
+                                  const spmv_b200_peers_t *peers, const spmv_b200_mail_t *mail, void *stream) {
+    if (!A || !d_y || !d_partials || !mail || (A->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_mail: NULL argument");
+    if (A->num_long > 0)
+        return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_mail: %d rows exceed the long-row threshold; use csr_spmv", A->num_long);
+    if (A->M == 0 || A->num_tiles == 0) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_mail: a rank without rows cannot take part in the exchange");
+    if (peers && (peers->count < 0 || peers->count > SPMV_B200_MAX_PEERS))
+        return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_mail: bad peer count %d", peers->count);
+    if (mail->world < 1 || mail->world > SPMV_B200_MAX_RANKS || mail->rank < 0 || mail->rank >= mail->world || !mail->counter ||
+        !mail->status)
+        return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_mail: bad mailbox description (world %d, rank %d)", mail->world, mail->rank);
+    for (int r = 0; r < mail->world; ++r)
+        if (!mail->box[r]) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_mail: mailbox of rank %d is NULL", r);
+    Epilogue ep;
+    ep.prev_sumsq = nullptr;
+    ep.partials = d_partials;
+    ep.peers.count = 0;
+    if (peers) ep.peers = *peers;
+    ep.mail = *mail;
     return stream_launch_csr(A, d_x, d_y, 0, &ep, as_stream(stream));
 }
 
@@ -606,19 +848,6 @@ int spmv_b200_csr_spmv_raw(int M, long long nnz, const int *d_row_ptr, const int
     return launch_vector(0, M, d_row_ptr, d_col_idx, d_values, d_x, d_y, vec, 0, as_stream(stream));
 }
 
-int spmv_b200_csr_spmv_host(spmv_b200_csr *A, const double *x, double *y, int accumulate, int algo) {
-    if (!A || !y || (A->N > 0 && !x)) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_host: NULL argument");
-    if (!A->stage_x) SPMV_TRY_CUDA(cudaMalloc(&A->stage_x, std::max<size_t>(A->N, 1) * sizeof(double)));
-    if (!A->stage_y) SPMV_TRY_CUDA(cudaMalloc(&A->stage_y, std::max<size_t>(A->M, 1) * sizeof(double)));
-    if (A->N) SPMV_TRY_CUDA(cudaMemcpyAsync(A->stage_x, x, (size_t)A->N * sizeof(double), cudaMemcpyHostToDevice, nullptr));
-    if (accumulate && A->M)
-        SPMV_TRY_CUDA(cudaMemcpyAsync(A->stage_y, y, (size_t)A->M * sizeof(double), cudaMemcpyHostToDevice, nullptr));
-    SPMV_TRY(spmv_b200_csr_spmv(A, A->stage_x, A->stage_y, accumulate, algo, nullptr));
-    if (A->M) SPMV_TRY_CUDA(cudaMemcpyAsync(y, A->stage_y, (size_t)A->M * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
-    SPMV_TRY_CUDA(cudaStreamSynchronize(nullptr));
-    return SPMV_B200_OK;
-}
-
 void spmv_b200_csr_free(spmv_b200_csr *A) {
     if (!A) return;
     free_plan(A);
@@ -629,6 +858,7 @@ void spmv_b200_csr_free(spmv_b200_csr *A) {
     }
     cudaFree(A->stage_x);
     cudaFree(A->stage_y);
+    host_pipe_free(A->pipe);
     delete A;
 }
 

@@ -17,7 +17,24 @@ struct Epilogue {                 // optional fused tail of the CSR stream kerne
     const double *prev_sumsq;     // divide every row by sqrt(*prev_sumsq)
     double *partials;             // partials[blockIdx.x] = sum of the squares of the rows this CTA produced
     spmv_b200_peers_t peers;      // rows mirrored into peer memory
+    spmv_b200_mail_t mail;        // world > 0: |w|^2 travels through peer mailboxes instead of prev_sumsq (spmv_b200.h)
 };
+
+constexpr int kBins = 7;  // rows binned by length: 1, 2, 4, 8, 16, 32 lanes per row, and "long" (split into fragments)
+
+struct BinPlan {                 // csr.cu: row-binned vector kernel for skewed matrices (built on first use)
+    int *rows = nullptr;         // device [M]: row ids sorted by bin, ascending inside a bin
+    int offset[kBins + 1] = {};  // rows of bin b are rows[offset[b] .. offset[b+1])
+    int block_start[kBins] = {}; // first CTA of bins 0..5 in the single launch; block_start[6] = total CTAs
+    int num_long = 0;            // rows of the last bin
+    int *frag_first = nullptr;   // device [num_long+1]
+    int num_frag = 0;
+    double *frag_partial = nullptr;
+    bool built = false;
+};
+
+struct HostPipe;  // hostpath.cu: streams, events and the row-window plan of the *_spmv_host entry points
+void host_pipe_free(HostPipe *p);
 
 struct HllTile {      // tiles[t] = first hack of tile t and its first slot; tiles[num_tiles] = {num_hacks, slots}
     int hack;
@@ -45,6 +62,7 @@ struct spmv_b200_csr {
     int *frag_first = nullptr;
     int num_frag = 0;
     double *frag_partial = nullptr;
+    spmv::BinPlan bins;
     // stream kernel launch shape
     int stages = spmv::kDefaultStages;
     int consumers = 12;
@@ -52,6 +70,7 @@ struct spmv_b200_csr {
     // staging vectors of the *_host entry points
     double *stage_x = nullptr;
     double *stage_y = nullptr;
+    spmv::HostPipe *pipe = nullptr;
 };
 
 struct spmv_b200_hll {
@@ -71,14 +90,25 @@ struct spmv_b200_hll {
     int stream_grid = 0;
     double *stage_x = nullptr;
     double *stage_y = nullptr;
+    spmv::HostPipe *pipe = nullptr;
 };
 
 namespace spmv {
 // stream.cu
 int stream_prepare_csr(spmv_b200_csr *A);
+// tile_count < 0: every tile; otherwise the tiles [tile_begin, tile_begin + tile_count) only
 int stream_launch_csr(const spmv_b200_csr *A, const double *x, double *y, int accumulate, const Epilogue *ep,
-                      cudaStream_t stream);
+                      cudaStream_t stream, int tile_begin = 0, int tile_count = -1);
 int stream_plan_hll(spmv_b200_hll *H, cudaStream_t stream);
-int stream_launch_hll(const spmv_b200_hll *H, const double *x, double *y, cudaStream_t stream);
+int stream_launch_hll(const spmv_b200_hll *H, const double *x, double *y, cudaStream_t stream, int tile_begin = 0,
+                      int tile_count = -1);
+// csr.cu / hll.cu: which kernel the automatic choice resolves to, and launches restricted to a window
+enum CsrPath { kPathStream, kPathTile, kPathVector, kPathBinned };
+CsrPath csr_resolve(const spmv_b200_csr *A, int algo);
+int csr_launch_window(const spmv_b200_csr *A, CsrPath path, int unit_begin, int unit_end, const double *x, double *y,
+                      int accumulate, cudaStream_t stream);  // units: tiles (stream/tile paths) or rows (vector path)
+bool hll_prefers_stream(const spmv_b200_hll *H);
+int hll_launch_window(const spmv_b200_hll *H, bool stream_kernel, int unit_begin, int unit_end, const double *x, double *y,
+                      cudaStream_t stream);  // units: tiles (stream kernel) or hacks (slice kernel)
 int env_int(const char *name, int fallback);
 }  // namespace spmv

@@ -155,6 +155,17 @@ static int hll_alloc_arena(spmv_b200_hll *H) {
     return SPMV_B200_OK;
 }
 
+namespace spmv {
+// narrow hacks (stencils): TMA stream kernel; wide hacks are gather bound and need the occupancy of the slice kernel
+bool hll_prefers_stream(const spmv_b200_hll *H) { return H->slots <= 12LL * 32 * H->num_hacks; }
+
+int hll_launch_window(const spmv_b200_hll *H, bool stream_kernel, int unit_begin, int unit_end, const double *x, double *y,
+                      cudaStream_t stream) {
+    if (stream_kernel) return stream_launch_hll(H, x, y, stream, unit_begin, unit_end - unit_begin);
+    return hll_launch(H, unit_begin, unit_end, x, y, stream);
+}
+}  // namespace spmv
+
 extern "C" {
 
 int spmv_b200_hll_upload(const HLLMatrix *hll, int M, int N, spmv_b200_hll **out) {
@@ -371,8 +382,6 @@ int spmv_b200_hll_download(const spmv_b200_hll *H, HLLMatrix *out) {
     return SPMV_B200_OK;
 }
 
-// narrow hacks (stencils): TMA stream kernel; wide hacks are gather bound and need the occupancy of the slice kernel
-static bool hll_prefers_stream(const spmv_b200_hll *H) { return H->slots <= 12LL * 32 * H->num_hacks; }
 
 int spmv_b200_hll_spmv(const spmv_b200_hll *H, const double *d_x, double *d_y, void *stream) {
     if (!H || !d_y || (H->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "hll_spmv: NULL argument");
@@ -398,17 +407,6 @@ int spmv_b200_hll_spmv_hacks(const spmv_b200_hll *H, int hack_begin, int hack_en
     return hll_launch(H, hack_begin, hack_end, d_x, d_y, as_stream(stream));
 }
 
-int spmv_b200_hll_spmv_host(spmv_b200_hll *H, const double *x, double *y) {
-    if (!H || !y || (H->N > 0 && !x)) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_host: NULL argument");
-    if (!H->stage_x) SPMV_TRY_CUDA(cudaMalloc(&H->stage_x, std::max<size_t>(H->N, 1) * sizeof(double)));
-    if (!H->stage_y) SPMV_TRY_CUDA(cudaMalloc(&H->stage_y, std::max<size_t>(H->M, 1) * sizeof(double)));
-    if (H->N) SPMV_TRY_CUDA(cudaMemcpyAsync(H->stage_x, x, (size_t)H->N * sizeof(double), cudaMemcpyHostToDevice, nullptr));
-    SPMV_TRY(spmv_b200_hll_spmv(H, H->stage_x, H->stage_y, nullptr));
-    if (H->M) SPMV_TRY_CUDA(cudaMemcpyAsync(y, H->stage_y, (size_t)H->M * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
-    SPMV_TRY_CUDA(cudaStreamSynchronize(nullptr));
-    return SPMV_B200_OK;
-}
-
 void spmv_b200_hll_free(spmv_b200_hll *H) {
     if (!H) return;
     cudaFree(H->tiles);
@@ -417,6 +415,7 @@ void spmv_b200_hll_free(spmv_b200_hll *H) {
     cudaFree(H->AS);
     cudaFree(H->stage_x);
     cudaFree(H->stage_y);
+    host_pipe_free(H->pipe);
     delete H;
 }
 

@@ -99,23 +99,76 @@ __device__ __forceinline__ double dot_staged(const double *sv, const int *sc, in
     return acc;
 }
 
-// sv[k] <- sv[k] * x[sc[k]] for k = lo + lane, lo + lane + 32, ... < hi: conflict-free shared-memory
-// accesses and U independent gathers per lane, whatever the row lengths.
+// sv[k] <- sv[k] * x[sc[k]] for k = lo + first, lo + first + step, ... < hi (first = lane, step = 32 for one warp;
+// first = thread, step = all consumer threads for a whole CTA): conflict-free shared-memory accesses and U
+// independent gathers per lane, whatever the row lengths.
 template <int U>
-__device__ __forceinline__ void products_staged(double *sv, const int *sc, int lo, int hi, int lane,
+__device__ __forceinline__ void products_staged(double *sv, const int *sc, int lo, int hi, int first, int step,
                                                 const double *__restrict__ x) {
-    int k = lo + lane;
-    for (; k + (U - 1) * 32 < hi; k += U * 32) {
+    // guarded batches: every pass issues its U column reads, then its U gathers, then the U products -- also for the
+    // last, partial pass (a scalar remainder loop would serialise one gather latency per element)
+    for (int k = lo + first; k < hi; k += U * step) {
+        int c[U];
         double v[U], xv[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = sv[k + u * 32];
+        for (int u = 0; u < U; ++u) c[u] = k + u * step < hi ? sc[k + u * step] : -1;
 #pragma unroll
-        for (int u = 0; u < U; ++u) xv[u] = ldg_x(x, sc[k + u * 32]);
+        for (int u = 0; u < U; ++u) v[u] = c[u] >= 0 ? sv[k + u * step] : 0.0;
 #pragma unroll
-        for (int u = 0; u < U; ++u) sv[k + u * 32] = __dmul_rn(v[u], xv[u]);
+        for (int u = 0; u < U; ++u) xv[u] = c[u] >= 0 ? ldg_x(x, c[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (c[u] >= 0) sv[k + u * step] = __dmul_rn(v[u], xv[u]);
     }
-    for (; k < hi; k += 32) sv[k] = __dmul_rn(sv[k], ldg_x(x, sc[k]));
 }
+
+// Sum of one row of products parked in shared memory by G lanes (G a power of two, the same in the whole warp;
+// every lane of the warp must call this).  Lane `sub` of the group adds the elements e = sub (mod G) of its row.
+// When G divides the row length the walk starts at element (c * row_id) mod len, c = (G - len) mod 16, and wraps:
+// rows of equal length then start len + c = G (mod 16) doubles apart, i.e. the groups of a half-warp fall into
+// distinct banks.  Rows longer than kLaneRowMax elements per lane are summed by the whole warp, one after the other.
+// Fixed order (partial sums, then an xor tree): deterministic.  The sum is returned in every lane of the group.
+__device__ __forceinline__ double group_row_sum(const double *prod, int lo, int hi, int G, int lane, int row_id) {
+    const int len = hi - lo, sub = lane & (G - 1);
+    const bool wide = len > kLaneRowMax * G;
+    double acc = 0.0;
+    if (!wide && len > 0) {
+        int st = 0;
+        if ((len & (G - 1)) == 0) st = (((G - len) & 15) * row_id) % len;
+        for (int k = lo + st + sub; k < hi; k += G) acc = __dadd_rn(acc, prod[k]);
+        for (int k = lo + sub; k < lo + st; k += G) acc = __dadd_rn(acc, prod[k]);
+    }
+    for (int off = G >> 1; off > 0; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+    unsigned pending = __ballot_sync(0xffffffffu, wide && sub == 0);
+    while (pending) {
+        const int owner = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const int wlo = __shfl_sync(0xffffffffu, lo, owner), whi = __shfl_sync(0xffffffffu, hi, owner);
+        double part = 0.0;
+        for (int k = wlo + lane; k < whi; k += 32) part = __dadd_rn(part, prod[k]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part = __dadd_rn(part, __shfl_xor_sync(0xffffffffu, part, off));
+        if ((lane & ~(G - 1)) == owner) acc = part;
+    }
+    return acc;
+}
+
+// ---- system-scope mailbox accesses (peer memory over NVLink) -------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+constexpr long long kMailSpinCycles = 4000000000LL;  // ~2 s at 1.9 GHz: a peer that has not answered by then is gone
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -175,8 +228,42 @@ csr_stream_kernel(const int2 *__restrict__ tiles, int num_tiles, const int *__re
 
     // ---------------- consumers: independent warps, lane = row (or a slice of a row) ----------------
     __shared__ double warp_sq[kConsumerWarps];
-    const bool scaled = kFused && ep.prev_sumsq != nullptr;
-    const double prev_norm = scaled ? sqrt(*ep.prev_sumsq) : 1.0;
+    __shared__ double mail_total;
+    bool scaled = false;
+    double prev_norm = 1.0;
+    if constexpr (kFused) {
+        if (ep.mail.world > 0) {
+            if (ep.mail.iteration > 0) {
+                // wait for every rank's previous launch: its |w|^2 is in my mailbox and its boundary rows are in my x
+                if (warp == 0) {
+                    const unsigned long long want = ep.mail.iteration;  // tag of launch k-1 is k
+                    const int parity = (int)((ep.mail.iteration - 1) & 1);
+                    double mine = 0.0;
+                    if (lane < ep.mail.world) {
+                        const unsigned long long *slot = ep.mail.box[ep.mail.rank] + 2 * (parity * ep.mail.world + lane);
+                        const long long t0 = clock64();
+                        while (ld_acquire_sys(slot + 1) != want) {
+                            if (clock64() - t0 > kMailSpinCycles) {
+                                *ep.mail.status = 1;
+                                break;
+                            }
+                            __nanosleep(40);
+                        }
+                        mine = __longlong_as_double((long long)ld_acquire_sys(slot));
+                    }
+                    double total = 0.0;
+                    for (int r = 0; r < ep.mail.world; ++r) total += __shfl_sync(0xffffffffu, mine, r);  // rank order
+                    if (lane == 0) mail_total = total;
+                }
+                asm volatile("bar.sync 2, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+                scaled = true;
+                prev_norm = sqrt(mail_total);
+            }
+        } else {
+            scaled = ep.prev_sumsq != nullptr;
+            prev_norm = scaled ? sqrt(*ep.prev_sumsq) : 1.0;
+        }
+    }
     double sq = 0.0;  // sum of the squares of the rows this lane produced
     // y[row] = v; the fused instantiation scales it first, accumulates v^2 and mirrors boundary rows into the peers
     auto emit = [&](int row, double v) {
@@ -214,6 +301,29 @@ csr_stream_kernel(const int2 *__restrict__ tiles, int num_tiles, const int *__re
         if (!(rows == 1 && n1 - n0 > long_threshold)) {  // long rows belong to the csr_long_* kernels
             auto rp = [&](int r) { return (r - ra0 < rloaded) ? srp[r - ra0] : __ldg(row_ptr + r); };
             const int nchunks = (rows + 31) >> 5;
+            if (nchunks < kConsumerWarps && forced_tpr != 1 && n1 - a0 <= loaded) {
+                // Few rows in the tile, i.e. longer rows: 32-row chunks would leave most warps without work.
+                // (A) every consumer thread multiplies a strided share of the whole tile in place, (B) after a
+                // consumer-only barrier the rows are summed by G lanes each, G chosen so that all lanes have a row.
+                constexpr int kLanes = kConsumerWarps * 32;
+                products_staged<8>(sv, sc, n0 - a0, n1 - a0, tid, kLanes, x);
+                wrote = true;
+                asm volatile("bar.sync 3, %0;" ::"n"(kLanes) : "memory");
+                int G = 1;
+                while (G < 32 && rows * (2 * G) <= kLanes) G <<= 1;
+                const int per_pass = kLanes / G;
+                for (int first = 0; first < rows; first += per_pass) {  // warp-uniform trip count
+                    const int lr = first + tid / G;
+                    const bool live = lr < rows;
+                    int lo = 0, hi = 0;
+                    if (live) {
+                        lo = rp(r0 + lr) - a0;
+                        hi = rp(r0 + lr + 1) - a0;
+                    }
+                    const double acc = group_row_sum(sv, lo, hi, G, lane, lr);
+                    if (live && (lane & (G - 1)) == 0) emit(r0 + lr, accumulate ? __dadd_rn(y[r0 + lr], acc) : acc);
+                }
+            } else
             for (int c = (warp - dealt + kConsumerWarps) % kConsumerWarps; c < nchunks; c += kConsumerWarps) {
                 const int lr = c * 32 + lane;
                 const bool live = lr < rows;
@@ -243,14 +353,14 @@ csr_stream_kernel(const int2 *__restrict__ tiles, int num_tiles, const int *__re
                 } else {
                     // longer rows: (A) products in place, lane-strided over the whole chunk; (B) row sums
                     const int chunk_lo = __shfl_sync(0xffffffffu, lo, 0);
-                    products_staged<8>(sv, sc, chunk_lo, chunk_hi, lane, x);
+                    products_staged<8>(sv, sc, chunk_lo, chunk_hi, lane, 32, x);
                     wrote = true;
                     __syncwarp();
                     acc = chunk_row_sum(sv, lo, hi, lane);
                     if (live) emit(r0 + lr, accumulate ? __dadd_rn(y[r0 + lr], acc) : acc);
                 }
             }
-            dealt = (dealt + nchunks) % kConsumerWarps;
+            if (nchunks >= kConsumerWarps || forced_tpr == 1 || n1 - a0 > loaded) dealt = (dealt + nchunks) % kConsumerWarps;
         }
         if (wrote) fence_proxy_async();  // generic-proxy writes to the stage before the async proxy refills it
         __syncwarp();
@@ -266,6 +376,32 @@ csr_stream_kernel(const int2 *__restrict__ tiles, int num_tiles, const int *__re
 #pragma unroll
             for (int w = 0; w < kConsumerWarps; ++w) total += warp_sq[w];
             ep.partials[blockIdx.x] = total;
+        }
+        if (ep.mail.world > 0) {
+            __threadfence_system();  // this thread's rows (local and peer stores) before the flag below
+            asm volatile("bar.sync 2, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+            if (warp == 0) {
+                unsigned int arrived = 0;
+                if (lane == 0) {
+                    __threadfence();
+                    arrived = atomicAdd(ep.mail.counter, 1u);
+                }
+                arrived = __shfl_sync(0xffffffffu, arrived, 0);
+                if (arrived == gridDim.x - 1) {  // the last CTA of this launch publishes the rank's |w|^2
+                    __threadfence();
+                    double part = 0.0;
+                    for (int i = lane; i < (int)gridDim.x; i += 32) part += __ldcg(ep.partials + i);
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+                    if (lane < ep.mail.world) {
+                        unsigned long long *slot =
+                            ep.mail.box[lane] + 2 * ((int)(ep.mail.iteration & 1) * ep.mail.world + ep.mail.rank);
+                        st_relaxed_sys(slot, (unsigned long long)__double_as_longlong(part));
+                        st_release_sys(slot + 1, ep.mail.iteration + 1);
+                    }
+                    if (lane == 0) *ep.mail.counter = 0;
+                }
+            }
         }
     }
 }
@@ -472,23 +608,30 @@ int stream_prepare_csr(spmv_b200_csr *A) {
 }
 
 int stream_launch_csr(const spmv_b200_csr *A, const double *x, double *y, int accumulate, const Epilogue *ep,
-                      cudaStream_t stream) {
-    if (A->num_tiles == 0) return SPMV_B200_OK;
+                      cudaStream_t stream, int tile_begin, int tile_count) {
+    if (tile_count < 0) {
+        tile_begin = 0;
+        tile_count = A->num_tiles;
+    }
+    if (tile_count == 0) return SPMV_B200_OK;
+    const int2 *tiles = A->tiles + tile_begin;
+    const int grid = std::min(A->stream_grid, tile_count);
     Epilogue none;
     none.prev_sumsq = nullptr;
     none.partials = nullptr;
     none.peers.count = 0;
+    none.mail.world = 0;
     const Epilogue e = ep ? *ep : none;
     const size_t smem = csr_stream_smem(A);
     if (ep) {
         STREAM_DISPATCH(A->consumers, csr_fused_kernel,
-                        (kfn<<<A->stream_grid, (A->consumers + 1) * 32, smem, stream>>>(
-                            A->tiles, A->num_tiles, A->row_ptr, A->col_idx, A->values, x, y, A->M, (int)A->nnz,
+                        (kfn<<<grid, (A->consumers + 1) * 32, smem, stream>>>(
+                            tiles, tile_count, A->row_ptr, A->col_idx, A->values, x, y, A->M, (int)A->nnz,
                             csr_stage_bytes(A), A->stages, A->long_threshold, A->forced_tpr, accumulate, e)));
     } else {
         STREAM_DISPATCH(A->consumers, csr_plain_kernel,
-                        (kfn<<<A->stream_grid, (A->consumers + 1) * 32, smem, stream>>>(
-                            A->tiles, A->num_tiles, A->row_ptr, A->col_idx, A->values, x, y, A->M, (int)A->nnz,
+                        (kfn<<<grid, (A->consumers + 1) * 32, smem, stream>>>(
+                            tiles, tile_count, A->row_ptr, A->col_idx, A->values, x, y, A->M, (int)A->nnz,
                             csr_stage_bytes(A), A->stages, A->long_threshold, A->forced_tpr, accumulate, e)));
     }
     SPMV_TRY_CUDA(cudaGetLastError());
@@ -550,14 +693,19 @@ int stream_plan_hll(spmv_b200_hll *H, cudaStream_t stream) {
     return rc;
 }
 
-int stream_launch_hll(const spmv_b200_hll *H, const double *x, double *y, cudaStream_t stream) {
-    if (H->num_tiles == 0) return SPMV_B200_OK;
+int stream_launch_hll(const spmv_b200_hll *H, const double *x, double *y, cudaStream_t stream, int tile_begin,
+                      int tile_count) {
+    if (tile_count < 0) {
+        tile_begin = 0;
+        tile_count = H->num_tiles;
+    }
+    if (tile_count == 0) return SPMV_B200_OK;
     int cap;
     const size_t smem = hll_stream_smem(H, cap);
+    const int grid = std::min(H->stream_grid, tile_count);
     STREAM_DISPATCH(H->consumers, hll_stream_kernel,
-                    (kfn<<<H->stream_grid, (H->consumers + 1) * 32, smem, stream>>>(H->tiles, H->num_tiles, H->hack_off, H->JA,
-                                                                                  H->AS, x, y, H->M, cap, H->stages,
-                                                                                  H->wide_slots)));
+                    (kfn<<<grid, (H->consumers + 1) * 32, smem, stream>>>(H->tiles + tile_begin, tile_count, H->hack_off, H->JA,
+                                                                         H->AS, x, y, H->M, cap, H->stages, H->wide_slots)));
     SPMV_TRY_CUDA(cudaGetLastError());
     return SPMV_B200_OK;
 }

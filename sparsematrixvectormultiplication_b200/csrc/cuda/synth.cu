@@ -313,7 +313,10 @@ int spmv_b200_ipc_alloc(long long bytes, void **d_ptr, unsigned char handle[64])
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     if (bytes <= 0 || !d_ptr || !handle) return fail(SPMV_B200_ERR_INVALID, "ipc_alloc: bad arguments");
     *d_ptr = nullptr;
-    SPMV_TRY_CUDA(cudaMalloc(d_ptr, (size_t)bytes));
+    // cudaMalloc packs small requests into shared 2 MiB blocks and an IPC handle maps the whole block from its base:
+    // round up so that the buffer IS the block and the peer's pointer is the buffer's first byte
+    const size_t granule = (size_t)2 << 20;
+    SPMV_TRY_CUDA(cudaMalloc(d_ptr, ((size_t)bytes + granule - 1) / granule * granule));
     cudaIpcMemHandle_t h;
     cudaError_t e = cudaIpcGetMemHandle(&h, *d_ptr);
     if (e != cudaSuccess) {

@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _native as N
 
-ALGO_AUTO, ALGO_VECTOR, ALGO_TILE, ALGO_STREAM = 0, 1, 2, 3
+ALGO_AUTO, ALGO_VECTOR, ALGO_TILE, ALGO_STREAM, ALGO_BINNED = 0, 1, 2, 3, 4
 SYNTH_LAP2D, SYNTH_LAP3D, SYNTH_UNIFORM = 1, 2, 3
 
 
@@ -140,6 +140,14 @@ class DeviceCSR:
         N.check(N.lib().spmv_b200_csr_spmv_fused(self._h, raw(x_ptr), raw(y_ptr), raw(prev_sumsq) if prev_sumsq is not None else None,
                                                  raw(partials) if partials is not None else None,
                                                  C.byref(peers) if peers is not None else None, _stream(stream)))
+
+    def spmv_fused_mail(self, x_ptr, y_ptr, partials, mail, peers=None, stream=None):
+        """The fused launch with the |w|^2 exchange through peer mailboxes (spmv_b200_csr_spmv_fused_mail)."""
+        def raw(v):
+            return C.c_void_p(v) if isinstance(v, int) else _ptr(v)
+        N.check(N.lib().spmv_b200_csr_spmv_fused_mail(self._h, raw(x_ptr), raw(y_ptr), raw(partials),
+                                                      C.byref(peers) if peers is not None else None, C.byref(mail),
+                                                      _stream(stream)))
 
     def spmv_rows(self, row_begin, row_end, x, y, stream=None):
         N.check(N.lib().spmv_b200_csr_spmv_rows(self._h, int(row_begin), int(row_end), _ptr(x), _ptr(y), _stream(stream)))

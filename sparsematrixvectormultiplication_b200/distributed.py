@@ -165,15 +165,22 @@ class FusedPowerIteration(PowerIteration):
     rows a neighbour references straight into that neighbour's next-x buffer (cudaIpc-mapped peer memory), so
     the refresh of x costs no extra launch and no extra pass; the all-reduce of |w|^2 is the only collective
     and doubles as the barrier that orders those peer stores before the next product.
-    peer_stores=False: the boundary rows travel with NCCL point-to-point messages instead."""
+    peer_stores=False: the boundary rows travel with NCCL point-to-point messages instead.
+    mailbox=True (implies peer stores): the all-reduce goes too.  The last CTA of every launch writes the rank's
+    |w|^2 and an iteration tag into a mailbox slot of every rank (NVLink peer stores, release at system scope); the
+    next launch starts by waiting for the tags of all ranks in its own mailbox, which also proves that the boundary
+    rows have landed, and adds the sums in rank order (identical on every rank).  ONE launch per iteration, no
+    collective library call in the loop (include/spmv_b200.h: spmv_b200_csr_spmv_fused_mail)."""
 
-    def __init__(self, kind, p0, p1=0, p2=0, seed=0x5EED, group=None, parts=None, single=False, peer_stores=True):
+    def __init__(self, kind, p0, p1=0, p2=0, seed=0x5EED, group=None, parts=None, single=False, peer_stores=True,
+                 mailbox=False):
         super().__init__(kind, p0, p1, p2, seed=seed, exchange="halo", group=group, parts=parts, single=single)
         from . import _native as N
         d = self.dev
         if self.A.info().num_long_rows:
             raise ValueError("FusedPowerIteration needs a matrix without long rows")
-        self.peer_stores = bool(peer_stores) and self.world > 1
+        self.mailbox = bool(mailbox)
+        self.peer_stores = (bool(peer_stores) or self.mailbox) and self.world > 1
         cu = self.x.device
         del self.x, self.y
         nbytes = 8 * self.N
@@ -199,8 +206,25 @@ class FusedPowerIteration(PowerIteration):
         self.partials = torch.zeros(self.A.partials_count(), dtype=torch.float64, device=cu)
         self.sumsq = [torch.zeros(1, dtype=torch.float64, device=cu) for _ in range(2)]
         self.k = 0
+        self.box = None
+        if self.mailbox:
+            self.box = d.PeerBuffer(N.MAILBOX_BYTES)
+            self.box_t = self.box.as_tensor("<i8", 8)
+            self.box_t.zero_()
+            self.sync = torch.zeros(2, dtype=torch.int32, device=cu)   # [0] CTA counter, [1] status
+            self.mail = N.Mail()
+            self.mail.world, self.mail.rank = self.world, self.rank
+            self.mail.counter = self.sync.data_ptr()
+            self.mail.status = self.sync.data_ptr() + 4
+            if self.world > 1:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, self.box.handle_bytes(), group=self.group)
+                for r in range(self.world):
+                    self.mail.box[r] = self.box.ptr.value if r == self.rank else self.box.open_peer(handles[r])
+            else:
+                self.mail.box[0] = self.box.ptr.value
         self.reset(1.0)
-        self.launches_per_step = 2
+        self.launches_per_step = 1 if self.mailbox else 2
         if self.world > 1:
             dist.barrier(group=self.group)
 
@@ -208,6 +232,12 @@ class FusedPowerIteration(PowerIteration):
         for t in self.xs:
             self.dev.vec_fill(t, value)
         self.k = 0
+        if self.box is not None:
+            torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier(group=self.group)   # nobody may still be writing tags of the previous run
+            self.box_t.zero_()
+            self.sync.zero_()
         torch.cuda.synchronize()
         if self.world > 1:
             dist.barrier(group=self.group)
@@ -215,6 +245,12 @@ class FusedPowerIteration(PowerIteration):
     def step(self):
         cur, nxt = self.k & 1, (self.k & 1) ^ 1
         x, y = self.xs[cur], self.xs[nxt]
+        if self.mailbox:
+            self.mail.iteration = self.k
+            self.A.spmv_fused_mail(x.data_ptr(), y.data_ptr() + 8 * self.row_begin, self.partials, self.mail,
+                                   peers=self.peers[nxt])
+            self.k += 1
+            return
         self.A.spmv_fused(x.data_ptr(), y.data_ptr() + 8 * self.row_begin,
                           prev_sumsq=self.sumsq[cur] if self.k > 0 else None, partials=self.partials,
                           peers=self.peers[nxt])
@@ -225,11 +261,32 @@ class FusedPowerIteration(PowerIteration):
                 exchange_halo(y, self.plan, self.group)
         self.k += 1
 
+    def _mail_total(self) -> float:
+        """|w_k|^2 as the next launch will see it: the slots of parity (k-1)&1 of MY mailbox, added in rank order."""
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)   # every rank's last launch has finished, so every tag has landed
+        if int(self.sync[1].item()) != 0:
+            raise RuntimeError("a mailbox wait timed out: a peer rank did not finish its launch")
+        first = 2 * ((self.k - 1) & 1) * self.world
+        slots = self.box_t[first: first + 2 * self.world].view(self.world, 2)
+        tags = slots[:, 1].tolist()
+        if any(t != self.k for t in tags):
+            raise RuntimeError(f"mailbox tags {tags} do not match iteration {self.k}")
+        total = 0.0
+        for v in slots[:, 0].contiguous().view(torch.float64).tolist():
+            total += v
+        return total
+
     def eigenvalue_estimate(self) -> float:
+        if self.mailbox:
+            return self._mail_total() ** 0.5
         return float(self.sumsq[self.k & 1].item()) ** 0.5
 
     def normalized_x(self) -> torch.Tensor:
         """v_k = w_k / |w_k| (valid on the owned rows and on the referenced halo)."""
+        if self.mailbox:
+            return self.xs[self.k & 1] / (self._mail_total() ** 0.5)
         return self.xs[self.k & 1] / self.sumsq[self.k & 1].sqrt()
 
     def close(self):
@@ -241,3 +298,10 @@ class FusedPowerIteration(PowerIteration):
             for b in self.buf:
                 b.close()
             self.buf = None
+        if self.box is not None:
+            torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier(group=self.group)
+            self.box_t = None
+            self.box.close()
+            self.box = None

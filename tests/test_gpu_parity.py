@@ -48,7 +48,8 @@ def csr_products(dev, A, x, M):
     out = {}
     out["auto-host"] = A.spmv_host(x)
     xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
-    for name, algo in (("stream", dev.ALGO_STREAM), ("tile", dev.ALGO_TILE), ("vector", dev.ALGO_VECTOR)):
+    for name, algo in (("stream", dev.ALGO_STREAM), ("tile", dev.ALGO_TILE), ("vector", dev.ALGO_VECTOR),
+                       ("binned", dev.ALGO_BINNED)):
         yd = torch.full((max(M, 1),), float("nan"), dtype=torch.float64, device="cuda")
         A.spmv(xd, yd, algo=algo)
         out[name] = yd.cpu().numpy()[:M]
@@ -441,3 +442,88 @@ def test_fused_power_iteration_matches_the_oracle(dev, port):
     A.spmv(x, y1)
     A.spmv_fused(x, y2)
     assert torch.equal(y1, y2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the pipelined host entry point: any number of row windows gives the bits of the resident product
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("windows", [1, 3, 16])
+@pytest.mark.parametrize("kind", ["banded", "random", "skewed"])
+def test_host_pipeline_windows(dev, checker, monkeypatch, windows, kind):
+    """spmv_b200_{csr,hll}_spmv_host cut the rows into windows and overlap upload / product / download
+    (csrc/cuda/hostpath.cu).  The result must not depend on the number of windows, for banded matrices (windows
+    start before all of x has landed), random columns (every window waits for the last chunk) and plans with
+    long rows (single window)."""
+    import torch
+    monkeypatch.setenv("SPMV_B200_HOST_WINDOWS", str(windows))
+    rng = np.random.default_rng(windows * 10 + len(kind))
+    M = N = 6000
+    if kind == "banded":
+        offs = np.array([-70, -1, 0, 1, 70])
+        rows = np.repeat(np.arange(M), len(offs))
+        cols = rows + np.tile(offs, M)
+        keep = (cols >= 0) & (cols < N)
+        rows, cols = rows[keep], cols[keep]
+    elif kind == "random":
+        rows = np.repeat(np.arange(M), 20)
+        cols = rng.integers(0, N, rows.size)
+    else:
+        lengths = np.concatenate([[5000, 3000], rng.integers(0, 9, M - 2)])
+        rows = np.repeat(np.arange(M), lengths)
+        cols = np.concatenate([np.sort(rng.choice(N, n, replace=False)) for n in lengths])
+    order = np.lexsort((cols, rows))
+    rows, cols = rows[order], cols[order]
+    rp = np.zeros(M + 1, np.int32)
+    np.cumsum(np.bincount(rows, minlength=M), out=rp[1:])
+    ci = cols.astype(np.int32)
+    va = rng.uniform(0.5, 1.5, ci.size)
+    x = rng.uniform(0.5, 1.5, N)
+    y_ref = checker.spmv_csr_serial(rp, ci, va, x)
+    scale = abs_row_sums(checker, rp, ci, va, x)
+    xd = torch.from_numpy(x).cuda()
+    for algo in (dev.ALGO_AUTO, dev.ALGO_STREAM, dev.ALGO_TILE, dev.ALGO_VECTOR, dev.ALGO_BINNED):
+        A = dev.DeviceCSR.upload(M, N, rp, ci, va)   # fresh handle: the window plan is made on the first host call
+        yd = torch.empty(M, dtype=torch.float64, device="cuda")
+        A.spmv(xd, yd, algo=algo)
+        resident = yd.cpu().numpy()
+        assert_close(resident, y_ref, scale, f"{kind}/algo{algo}")
+        got = A.spmv_host(x, algo=algo)
+        assert np.array_equal(bits(got), bits(resident)), f"{kind}/algo{algo}/W{windows}: host pipeline differs from the resident product"
+        y0 = rng.standard_normal(M)
+        A.spmv(xd, yd.copy_(torch.from_numpy(y0)), accumulate=True, algo=algo)
+        got = A.spmv_host(x, y=y0.copy(), accumulate=True, algo=algo)
+        assert np.array_equal(bits(got), bits(yd.cpu().numpy())), f"{kind}/algo{algo}/W{windows}: accumulate"
+        if kind != "skewed":
+            H = A.to_hll()
+            for flag in (False, True):
+                H.spmv(xd, yd, slice_kernel=flag)
+            got = H.spmv_host(x)
+            auto = torch.empty(M, dtype=torch.float64, device="cuda")
+            H.spmv(xd, auto)
+            assert np.array_equal(bits(got), bits(auto.cpu().numpy())), f"{kind}/hll/W{windows}"
+            H.close()
+        A.close()
+
+
+def test_main_style_driver_writes_the_csv(dev, tmp_path):
+    """tools/spmv_driver.c: parser -> converters -> upload -> timed products of every kernel -> self-check against the
+    serial-order product -> one CSV row per matrix (the reference driver's loop, main_cuda.cu:40-720)."""
+    import csv
+    import subprocess
+    import sparsematrixvectormultiplication_b200 as pkg
+    exe = pkg.LIB_PATH.parent / "spmv_driver"
+    assert exe.exists(), "build() makes the driver next to the library"
+    out_csv = tmp_path / "result_b200.csv"
+    files = [str(GOLDEN / "mtx" / f"{n}.mtx") for n in ("general_matrix", "rand_symmetric_64x64", "rand_longrow_65x3000")]
+    run = subprocess.run([str(exe), "--csv", str(out_csv), "--iters", "7", "--warmup", "2", "--lap2d", "300", *files],
+                         capture_output=True, text=True)
+    assert run.returncode == 0, run.stdout[-3000:] + run.stderr[-3000:]
+    rows = list(csv.DictReader(open(out_csv)))
+    assert [r["matrix_name"] for r in rows] == ["general_matrix.mtx", "rand_symmetric_64x64.mtx", "rand_longrow_65x3000.mtx", "lap2d_300"]
+    assert rows[0]["rows"] == "10" and rows[0]["nonzeros"] == "5"
+    assert rows[3]["rows"] == "90000" and rows[3]["nonzeros"] == str(5 * 90000 - 4 * 300)
+    for r in rows:
+        for k in ("csr_auto", "csr_stream", "csr_tile", "csr_vector", "hll_auto", "hll_stream", "hll_slice"):
+            assert float(r[f"time_{k}"]) > 0 and float(r[f"flops_{k}"]) > 0
+            assert float(r[f"relative_error_{k}"]) <= 1e-12 and float(r[f"absolute_error_{k}"]) <= 1e-9
+        assert float(r["time_e2e_csr_host"]) > 0 and r["ngpus"] == "1"

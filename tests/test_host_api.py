@@ -151,3 +151,24 @@ def test_harness_matches_oracle(checker, port):
     assert abs(host.calculate_csr_bytes(M, M, nnz) / 1e9 - 1.342) < 1e-3
     v = np.zeros(7)
     assert (host.init_vector_at_one(v) == 1.0).all()
+
+
+def test_driver_fails_loudly_without_a_gpu(tmp_path):
+    """tools/spmv_driver.c (the main()-style driver) has no CPU fallback: on a machine without a CUDA device it must
+    stop with exit status 3 and say why; on a GPU box the same command is covered by tests/test_gpu_parity.py."""
+    import subprocess
+    import sparsematrixvectormultiplication_b200 as pkg
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("CUDA device present")
+    except ImportError:
+        pass
+    exe = pkg.LIB_PATH.parent / "spmv_driver"
+    if not exe.exists():
+        pkg.build()
+    out = subprocess.run([str(exe), "--csv", str(tmp_path / "r.csv"), str(GOLDEN / "mtx" / "general_matrix.mtx")],
+                         capture_output=True, text=True)
+    assert out.returncode == 3, out.stdout + out.stderr
+    assert "no CUDA device" in out.stderr and "no CPU fallback" in out.stderr
+    assert not (tmp_path / "r.csv").exists()

@@ -35,11 +35,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("report")
     ap.add_argument("--pick", type=int, default=1, help="keep the last of every N consecutive launches")
+    ap.add_argument("--select", default="", help="comma separated launch indices to keep (applied before --pick)")
     ap.add_argument("--labels", nargs="*", default=[], help="column labels, in launch order after --pick")
     args = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", args.report, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
+    if args.select:
+        data = [data[int(i)] for i in args.select.split(",")]
     if args.pick > 1:
         data = [r for i, r in enumerate(data) if i % args.pick == args.pick - 1]
     name_i = hdr.index("Kernel Name")

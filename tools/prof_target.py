@@ -30,8 +30,8 @@ def main(names):
         elif kind == "uniform":
             A = device.DeviceCSR.synth(synth.SYNTH_UNIFORM, 1 << 23, 1 << 23, 32)
         elif kind == "rmat":
-            rp, ci, va = synth.rmat_csr_device(22, 16)
-            A = device.DeviceCSR.wrap(1 << 22, 1 << 22, rp, ci, va)
+            rp, ci, va = synth.rmat_csr_device(24, 16)
+            A = device.DeviceCSR.wrap(1 << 24, 1 << 24, rp, ci, va)
         else:
             raise SystemExit(f"unknown workload {name}")
         info = A.info()
