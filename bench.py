@@ -453,11 +453,12 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler):
     # config 5 on ONE GPU: T1 of the multi-GPU scaling series
     try:
         from sparsematrixvectormultiplication_b200.distributed import FusedPowerIteration, PowerIteration
-        F = FusedPowerIteration(synth.SYNTH_LAP3D, 512)
+        F = FusedPowerIteration(synth.SYNTH_LAP3D, 512, mailbox=True)
         ms, per = time_device(F.step, steps, warm, sampler)
         out["lap3d_512_power_1gpu"] = {"gflops": 2.0 * F.nnz_global / (ms * 1e-3) / 1e9, "ms_per_iteration": ms,
                                        "nnz": F.nnz_global, "launches_per_step": F.launches_per_step,
-                                       "kernel": "fused: product + lazy normalisation + |w|^2 partials in one launch"}
+                                       "kernel": "fused: product + lazy normalisation + |w|^2 (mailbox) in one launch"}
+        F.close()
         log(f"[bench] lap3d_512_power_1gpu (fused): {out['lap3d_512_power_1gpu']['gflops']:.1f} GFLOP/s ({ms:.3f} ms/iteration)")
         del F
         torch.cuda.empty_cache()
@@ -492,15 +493,33 @@ def bench_multi_gpu(args):
         sampler.start()
     n = args.lap3d_n
     results = {}
-    for mode in ("fused_peer_stores", "fused_nccl_halo", "halo", "allgather"):
-        if mode == "fused_peer_stores":
+    # T1 of the strong-scaling series, measured in the same run: rank 0 alone iterates on the WHOLE matrix
+    # (11.8 GB at 512^3: fits one GPU) while the other ranks wait at the barrier below
+    t1 = None
+    if rank == 0 and not args.no_t1:
+        try:
+            F1 = FusedPowerIteration(synth.SYNTH_LAP3D, n, single=True, mailbox=True)
+            ms1, _ = time_device(F1.step, max(5, min(args.steps, 30)), args.warmup, None, 1)
+            t1 = {"ms_per_step": ms1, "gflops": 2.0 * F1.nnz_global / (ms1 * 1e-3) / 1e9, "launches_per_step": F1.launches_per_step,
+                  "note": "same workload and kernel on ONE GPU (rank 0 alone, whole matrix), measured in this run"}
+            log(f"[bench] 1 GPU same workload: {t1['gflops']:.1f} GFLOP/s, {ms1:.3f} ms/iteration")
+            F1.close()
+            del F1
+            torch.cuda.empty_cache()
+        except Exception as e:  # pragma: no cover
+            log(f"[bench] single-GPU leg failed: {e!r}")
+    dist.barrier()
+    for mode in ("fused_mailbox", "fused_peer_stores", "fused_nccl_halo", "halo", "allgather"):
+        if mode == "fused_mailbox":
+            P = FusedPowerIteration(synth.SYNTH_LAP3D, n, mailbox=True)
+        elif mode == "fused_peer_stores":
             P = FusedPowerIteration(synth.SYNTH_LAP3D, n, peer_stores=True)
         elif mode == "fused_nccl_halo":
             P = FusedPowerIteration(synth.SYNTH_LAP3D, n, peer_stores=False)
         else:
             P = PowerIteration(synth.SYNTH_LAP3D, n, exchange=mode)
         P.reset(1.0)
-        head = mode == "fused_peer_stores"
+        head = mode == "fused_mailbox"
         steps = args.steps if head else max(3, min(args.steps, 20))
         ms, per = time_device(P.step, steps, args.warmup, sampler if head else None, world)
         lam = P.eigenvalue_estimate()
@@ -523,15 +542,15 @@ def bench_multi_gpu(args):
     if sampler:
         sampler.stop()
     if rank == 0:
-        h = results["fused_peer_stores"]
+        h = results["fused_mailbox"]
         gbs = h["bytes_local"] / (results["product_only_ms"] * 1e-3) / 1e9
         line = {"metric": "spmv_gflops", "value": h["gflops"], "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": h["ms_per_step"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"lap3d_{n}_power", "rows": n ** 3, "nnz": h["nnz_global"], "format": "csr",
                            "partition": "contiguous rows balanced by nnz (reference greedy rule)",
-                           "exchange": "boundary rows stored into the neighbours' x over NVLink peer memory by the product kernel",
-                           "step": "one power iteration, one fused launch: w=(A w_prev)/|w_prev| + |w|^2 partials + peer stores, then an 8-byte all-reduce",
+                           "exchange": "boundary rows AND |w|^2 stored into the peers' buffers / mailboxes over NVLink peer memory by the product kernel; no collective call in the loop",
+                           "step": "one power iteration = ONE launch: wait for the peers' tags, w=(A w_prev)/|w_prev|, |w|^2 partials, peer stores of boundary rows, last CTA publishes |w|^2 + tag",
                            "l2": "inputs_exceed_l2"},
                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
                              "peak_source": peak_src, "note": "rank 0's local CSR product alone (max over ranks), algorithmic bytes of its row slice",
@@ -540,6 +559,7 @@ def bench_multi_gpu(args):
                 "e2e": {"value": h["gflops"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                         "note": "iterated product: x and y never leave the devices between iterations; see the N=1 line for the host-buffer path"},
                 "gpu_launches": h["launches_per_step"] * args.steps, "clocks": sampler.summary() if sampler else None,
+                "single_gpu_same_workload": t1,
                 "exchange_modes": {k: v for k, v in results.items() if isinstance(v, dict)}}
         emit(line)
     dist.barrier()
@@ -556,6 +576,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--lap3d-n", type=int, default=512)
+    ap.add_argument("--no-t1", action="store_true", help="multi-GPU: skip the single-GPU leg of the same workload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     capture_stdout()

@@ -99,6 +99,9 @@ __device__ __forceinline__ double ldg_x(const double *x, int col) {
 }
 
 // ---- per-row sums of products parked in shared memory, one warp per chunk of 32 rows ---------------
+constexpr int kSerialRowMax = 12;  // rows up to this length are always summed by ONE lane, left to right: the stream and
+                                   // tile kernels reproduce the reference's serial loop bit for bit on such rows, whatever
+                                   // tile, path or GPU partition they fall into
 constexpr int kLaneRowMax = 64;  // rows up to this length are summed by their own lane, longer ones by the whole warp
 
 // Lane = row [lo, hi) of prod[].  Short rows start at a lane-dependent element and wrap around, so equally long
@@ -108,7 +111,7 @@ __device__ __forceinline__ double chunk_row_sum(const double *prod, int lo, int 
     const int len = hi - lo;
     double acc = 0.0;
     if (len <= kLaneRowMax && len > 0) {
-        const int start = lo + lane % len;
+        const int start = len <= kSerialRowMax ? lo : lo + lane % len;
         for (int k = start; k < hi; ++k) acc = __dadd_rn(acc, prod[k]);
         for (int k = lo; k < start; ++k) acc = __dadd_rn(acc, prod[k]);
     }

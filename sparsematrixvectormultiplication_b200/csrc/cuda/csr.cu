@@ -194,7 +194,7 @@ csr_vector_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, c
     }
     // kVecBatch column/value loads are issued before the first gather and the gathers before the first fma: the
     // column -> x dependency costs one round trip per batch instead of one per element
-    double acc = 0.0;
+    double acc = (VEC == 1 && accumulate && live) ? y[row] : 0.0;  // one lane per row: y += A x in the serial loop's order
     for (int k = lo + lane; k < hi; k += kVecBatch * VEC) {
         int c[kVecBatch];
         double v[kVecBatch], xv[kVecBatch];
@@ -206,11 +206,14 @@ csr_vector_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, c
         for (int u = 0; u < kVecBatch; ++u) xv[u] = c[u] >= 0 ? ldg_x(x, c[u]) : 0.0;
 #pragma unroll
         for (int u = 0; u < kVecBatch; ++u)
-            if (c[u] >= 0) acc = fma(v[u], xv[u], acc);
+            if (c[u] >= 0) {
+                if constexpr (VEC == 1) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));  // one lane, index order: the serial loop
+                else acc = fma(v[u], xv[u], acc);
+            }
     }
 #pragma unroll
     for (int off = VEC >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (live && lane == 0) y[row] = accumulate ? y[row] + acc : acc;
+    if (live && lane == 0) y[row] = (accumulate && VEC > 1) ? y[row] + acc : acc;
 }
 
 // ---- row-binned vector kernel (skewed matrices) ------------------------------------------------------
@@ -249,7 +252,7 @@ __device__ __forceinline__ void binned_rows(int local_block, int first, int coun
         lo = __ldg(row_ptr + row);
         hi = __ldg(row_ptr + row + 1);
     }
-    double acc = 0.0;
+    double acc = (VEC == 1 && accumulate && live) ? y[row] : 0.0;
     for (int k = lo + lane; k < hi; k += kVecBatch * VEC) {
         int c[kVecBatch];
         double v[kVecBatch], xv[kVecBatch];
@@ -261,11 +264,14 @@ __device__ __forceinline__ void binned_rows(int local_block, int first, int coun
         for (int u = 0; u < kVecBatch; ++u) xv[u] = c[u] >= 0 ? ldg_x(x, c[u]) : 0.0;
 #pragma unroll
         for (int u = 0; u < kVecBatch; ++u)
-            if (c[u] >= 0) acc = fma(v[u], xv[u], acc);
+            if (c[u] >= 0) {
+                if constexpr (VEC == 1) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));  // one lane, index order: the serial loop
+                else acc = fma(v[u], xv[u], acc);
+            }
     }
 #pragma unroll
     for (int off = VEC >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (live && lane == 0) y[row] = accumulate ? y[row] + acc : acc;
+    if (live && lane == 0) y[row] = (accumulate && VEC > 1) ? y[row] + acc : acc;
 }
 
 __global__ void __launch_bounds__(256)

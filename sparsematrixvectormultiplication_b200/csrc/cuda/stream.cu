@@ -132,7 +132,12 @@ __device__ __forceinline__ double group_row_sum(const double *prod, int lo, int 
     const int len = hi - lo, sub = lane & (G - 1);
     const bool wide = len > kLaneRowMax * G;
     double acc = 0.0;
-    if (!wide && len > 0) {
+    if (len <= kSerialRowMax) {
+        // short rows keep the serial order whatever path their tile takes (bit-identical to the reference's loop and
+        // independent of how the rows are partitioned over tiles and GPUs); the other lanes of the group add +0.0
+        if (sub == 0)
+            for (int k = lo; k < hi; ++k) acc = __dadd_rn(acc, prod[k]);
+    } else if (!wide) {
         int st = 0;
         if ((len & (G - 1)) == 0) st = (((G - len) & 15) * row_id) % len;
         for (int k = lo + st + sub; k < hi; k += G) acc = __dadd_rn(acc, prod[k]);
@@ -172,7 +177,6 @@ constexpr long long kMailSpinCycles = 4000000000LL;  // ~2 s at 1.9 GHz: a peer 
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-constexpr int kSerialRowMax = 12;  // chunks whose longest row is at most this long are summed lane = row, in order
 
 // =================================================================================================
 // CSR

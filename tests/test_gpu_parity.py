@@ -527,3 +527,36 @@ def test_main_style_driver_writes_the_csv(dev, tmp_path):
             assert float(r[f"time_{k}"]) > 0 and float(r[f"flops_{k}"]) > 0
             assert float(r[f"relative_error_{k}"]) <= 1e-12 and float(r[f"absolute_error_{k}"]) <= 1e-9
         assert float(r["time_e2e_csr_host"]) > 0 and r["ngpus"] == "1"
+
+
+def test_short_rows_are_summed_in_serial_order_on_every_path(dev, checker):
+    """Rows of up to 12 nonzeros are reduced by one lane, left to right, with mul and add rounded separately -- the
+    reference's serial loop (src/csr_matrix.c:134-138) bit for bit -- in the stream and tile kernels whatever tile,
+    path (per-chunk or CTA-wide two-phase) or row partition they fall into; the binned kernel does so for its
+    one-lane class (<= 6 nonzeros).  Longer rows: tolerance."""
+    import torch
+    rng = np.random.default_rng(2024)
+    M, N = 9000, 7000
+    lengths = rng.choice([0, 1, 3, 5, 6, 7, 12, 13, 40, 200, 700], size=M, p=[.05, .1, .2, .2, .1, .1, .1, .05, .05, .03, .02])
+    rp = np.zeros(M + 1, np.int32)
+    np.cumsum(lengths, out=rp[1:])
+    ci = np.concatenate([np.sort(rng.choice(N, n, replace=False)) for n in lengths]).astype(np.int32)
+    va = rng.standard_normal(rp[-1])
+    x = rng.standard_normal(N)
+    y_ref = checker.spmv_csr_serial(rp, ci, va, x)
+    scale = abs_row_sums(checker, rp, ci, va, x)
+    short, tiny = lengths <= 12, lengths <= 6
+    xd = torch.from_numpy(x).cuda()
+    for lo, hi in ((0, M), (1234, 7777), (8990, M)):          # the whole matrix and two row blocks of it ("ranks")
+        sub_rp = (rp[lo:hi + 1] - rp[lo]).astype(np.int32)
+        A = dev.DeviceCSR.upload(hi - lo, N, sub_rp, ci[rp[lo]:rp[hi]], va[rp[lo]:rp[hi]])
+        for D, L in ((0, 0), (96, 16), (600, 64), (3000, 512)):
+            A.replan(tile_items=D, long_threshold=L)
+            for name, algo in (("stream", dev.ALGO_STREAM), ("tile", dev.ALGO_TILE), ("binned", dev.ALGO_BINNED), ("auto", dev.ALGO_AUTO)):
+                yd = torch.full((hi - lo,), float("nan"), dtype=torch.float64, device="cuda")
+                A.spmv(xd, yd, algo=algo)
+                y = yd.cpu().numpy()
+                assert_close(y, y_ref[lo:hi], scale[lo:hi], f"{name} rows[{lo},{hi}) D={D} L={L}")
+                exact = tiny[lo:hi] if name in ("binned", "auto") else short[lo:hi]
+                assert np.array_equal(bits(y[exact]), bits(y_ref[lo:hi][exact])), f"{name} rows[{lo},{hi}) D={D} L={L}: short rows not bit-exact"
+        A.close()

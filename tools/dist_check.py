@@ -49,8 +49,8 @@ def main():
         print(f"rank {rank}/{world} {mode}: rows [{P.row_begin},{P.row_end}) recv {P.plan.halo_doubles_received() if mode == 'halo' else P.plan.allgather_doubles_received()} "
               f"doubles/iter, x err {err:.2e}, lambda err {lam_err:.2e}, product bitwise {same} -> {'ok' if good else 'FAIL'}", flush=True)
         ok = ok and good
-    for peer_stores in (True, False):
-        F = FusedPowerIteration(synth.SYNTH_LAP3D, n, peer_stores=peer_stores)
+    for peer_stores, mailbox in ((True, False), (False, False), (True, True)):
+        F = FusedPowerIteration(synth.SYNTH_LAP3D, n, peer_stores=peer_stores, mailbox=mailbox)
         lam = []
         for _ in range(iters):
             F.step()
@@ -62,7 +62,7 @@ def main():
         err = float((v[lo:hi] - ref.x[lo:hi]).abs().max() / ref.x.abs().max())
         lam_err = max(abs(a - b) / b for a, b in zip(lam, lam_ref))
         good = err <= 1e-12 and lam_err <= 1e-12
-        print(f"rank {rank}/{world} fused peer_stores={peer_stores}: x err {err:.2e}, lambda err {lam_err:.2e} -> {'ok' if good else 'FAIL'}", flush=True)
+        print(f"rank {rank}/{world} fused peer_stores={peer_stores} mailbox={mailbox}: x err {err:.2e}, lambda err {lam_err:.2e} -> {'ok' if good else 'FAIL'}", flush=True)
         ok = ok and good
         F.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
