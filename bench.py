@@ -358,7 +358,8 @@ def bench_single_gpu(args):
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "rows": M, "cols": info.N, "nnz": nnz, "format": "csr", "x": "1+(i mod 7)/8",
-                       "kernel": "csr_stream_kernel (persistent row-binned kernel, TMA bulk-copy pipeline)", "tiles": info.num_tiles,
+                       "kernel": device.ALGO_NAMES[info.auto_algo] + " (automatic choice)", "row_batch": info.row_batch,
+                       "max_row_nnz": info.max_row_nnz, "tiles": info.num_tiles,
                        "l2": "inputs_exceed_l2 (1.34 GB streamed per product vs 126 MB L2)",
                        "step": "one product y = A x, matrix resident in HBM"},
             "roofline": {"bound": "hbm", "achieved": head["gbs"], "peak": peak, "unit": "GB/s", "frac": head["gbs"] / peak,
@@ -397,6 +398,10 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler):
         run(f"{name}_csr_tile_kernel", lambda: A.spmv(x, y, algo=device.ALGO_TILE), ia.nnz, ia.algorithmic_bytes)
         run(f"{name}_csr_vector_kernel", lambda: A.spmv(x, y, algo=device.ALGO_VECTOR), ia.nnz, ia.algorithmic_bytes)
         run(f"{name}_csr_binned_kernel", lambda: A.spmv(x, y, algo=device.ALGO_BINNED), ia.nnz, ia.algorithmic_bytes)
+        if ia.max_row_nnz <= 64:  # one thread per row is only meaningful without long rows
+            run(f"{name}_csr_row_kernel", lambda: A.spmv(x, y, algo=device.ALGO_ROW), ia.nnz, ia.algorithmic_bytes, {"row_batch": ia.row_batch})
+        if f"{name}_csr" in out and "error" not in out[f"{name}_csr"]:
+            out[f"{name}_csr"]["kernel"] = "automatic choice: " + device.ALGO_NAMES[ia.auto_algo]
 
     def hll_variants(name, A, x, y):
         ia = A.info()
@@ -405,6 +410,10 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler):
         run(f"{name}_hll", lambda: H.spmv(x, y), ia.nnz, hi.algorithmic_bytes, {"slots": hi.slots, "kernel": "automatic choice"})
         run(f"{name}_hll_stream_kernel", lambda: H.spmv(x, y, slice_kernel=False), ia.nnz, hi.algorithmic_bytes)
         run(f"{name}_hll_slice_kernel", lambda: H.spmv(x, y, slice_kernel=True), ia.nnz, hi.algorithmic_bytes)
+        if hi.max_maxnz <= 64:
+            run(f"{name}_hll_row_kernel", lambda: H.spmv(x, y, slice_kernel="rows"), ia.nnz, hi.algorithmic_bytes, {"row_batch": hi.row_batch})
+        if f"{name}_hll" in out and "error" not in out[f"{name}_hll"]:
+            out[f"{name}_hll"]["kernel"] = "automatic choice: " + device.HLL_KERNEL_NAMES[hi.auto_kernel]
         H.close()
 
     try:
@@ -412,6 +421,48 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler):
         hll_variants("lap2d_4096", A2d, x2d, y2d)
     except Exception as e:  # pragma: no cover
         out["lap2d_4096_variants"] = {"error": repr(e)}
+
+    # the reference's own GPU kernels, recompiled unmodified for sm_100a, on the headline matrix ("existing kernel" bar)
+    try:
+        from oracle import oracle as O
+        if O.reference_cuda_available():
+            import ctypes as C
+            ref = O.ReferenceCuda()
+            ia = A2d.info()
+            ptrs = [C.c_void_p() for _ in range(3)]
+            from sparsematrixvectormultiplication_b200 import _native as N
+            N.check(N.lib().spmv_b200_csr_device_arrays(A2d._h, *[C.byref(p) for p in ptrs]))
+
+            class _Raw:
+                def __init__(self, p):
+                    self.p = p
+
+                def data_ptr(self):
+                    return self.p
+            rp, ci, va = (_Raw(p.value) for p in ptrs)
+            yr = torch.empty_like(y2d)
+            A2d.spmv(x2d, y2d)
+            for which, kname in enumerate(O.ReferenceCuda.CSR_KERNELS):
+                run(f"lap2d_4096_reference_{kname}", lambda: ref.csr_spmv(which, ia.M, ia.N, rp, ci, va, x2d, yr), ia.nnz,
+                    ia.algorithmic_bytes, {"kernel": f"reference {kname}, unmodified, recompiled for sm_100a (cuda_src/csr_matrix_cuda.cu)"})
+                err = float((yr - y2d).abs().max().item())
+                out[f"lap2d_4096_reference_{kname}"]["max_abs_diff_vs_ours"] = err
+            H = A2d.to_hll()
+            hi = H.info()
+            host_hll = H.download()
+            handle = ref.hll_upload(C.byref(host_hll.c), ia.M)
+            for which, kname in enumerate(O.ReferenceCuda.HLL_KERNELS):
+                run(f"lap2d_4096_reference_{kname}", lambda: ref.hll_spmv(handle, which, x2d, yr), ia.nnz, hi.algorithmic_bytes,
+                    {"kernel": f"reference {kname}, unmodified, recompiled for sm_100a (cuda_src/hll_matrix.cu); reference row-major block layout in one arena"})
+                out[f"lap2d_4096_reference_{kname}"]["max_abs_diff_vs_ours"] = float((yr - y2d).abs().max().item())
+            ref.hll_free(handle)
+            H.close()
+            del host_hll, yr
+        else:
+            out["lap2d_4096_reference_kernels"] = {"skipped": "oracle/_ref/libspmv_ref_cuda.so not present"}
+    except Exception as e:  # pragma: no cover
+        out["lap2d_4096_reference_kernels"] = {"error": repr(e)}
+        log(f"[bench] reference CUDA kernels failed: {e!r}")
 
     # config 3: uniform 8M x 8M, 32 nnz/row, CSR vs HLL hack 32
     try:
@@ -553,7 +604,7 @@ def bench_multi_gpu(args):
                            "step": "one power iteration = ONE launch: wait for the peers' tags, w=(A w_prev)/|w_prev|, |w|^2 partials, peer stores of boundary rows, last CTA publishes |w|^2 + tag",
                            "l2": "inputs_exceed_l2"},
                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
-                             "peak_source": peak_src, "note": "rank 0's local CSR product alone (max over ranks), algorithmic bytes of its row slice",
+                             "peak_source": peak_src, "note": "rank 0's local CSR product alone (max over ranks); algorithmic bytes of its row slice = 12 nnz_local + 4 (rows+1) + 8 rows + 8 x (referenced columns of x)",
                              "algorithmic_bytes_per_launch": int(h["bytes_local"])},
                 "cpu_baseline": None,
                 "e2e": {"value": h["gflops"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,

@@ -42,11 +42,12 @@ extern "C" {
 #define SPMV_B200_ERR_NOMEM (-4)
 
 /* CSR kernel selection for spmv_b200_csr_spmv */
-#define SPMV_B200_ALGO_AUTO 0     /* STREAM for short rows (<= 12 nnz/row on average), else VECTOR (even rows) or BINNED (skewed) */
+#define SPMV_B200_ALGO_AUTO 0     /* ROW when no row exceeds 16 nonzeros, STREAM for <= 12 nnz/row on average, else VECTOR (even rows) or BINNED (skewed) */
 #define SPMV_B200_ALGO_VECTOR 1   /* plain vector-per-row kernel with shuffle reduction      */
 #define SPMV_B200_ALGO_TILE 2     /* row-binned tile kernel, one CTA per tile, direct loads  */
 #define SPMV_B200_ALGO_STREAM 3   /* persistent row-binned kernel, TMA bulk-copy pipeline    */
 #define SPMV_B200_ALGO_BINNED 4   /* rows binned by length: 1..32 lanes per row, longest rows split */
+#define SPMV_B200_ALGO_ROW 5      /* one thread per row, serial order (bit-identical to the reference loop) */
 
 /* synthetic CSR generators (BASELINE.json configs 2, 3, 5) */
 #define SPMV_B200_SYNTH_LAP2D 1   /* p0 = n   : 5-point Laplacian on an n x n grid           */
@@ -66,6 +67,9 @@ typedef struct {
     int tile_items;      /* D: rows+nnz per tile                                             */
     int long_threshold;  /* L: rows longer than this are "long"                              */
     long long algorithmic_bytes; /* nnz*12 + 4*(M+1) + 8*M + 8*N     */
+    int max_row_nnz;     /* longest row                                                      */
+    int auto_algo;       /* the SPMV_B200_ALGO_* that SPMV_B200_ALGO_AUTO resolves to        */
+    int row_batch;       /* batch of the thread-per-row kernel (tuned at plan time)          */
 } spmv_b200_csr_info_t;
 
 typedef struct {
@@ -75,6 +79,8 @@ typedef struct {
     long long slots;        /* sum_b 32*MAXNZ_b (device image: rows padded to 32)            */
     long long nnz_reference_slots; /* sum_b rows_b*MAXNZ_b (reference host layout)           */
     long long algorithmic_bytes;   /* slots*12 + 8*(num_hacks+1) + 8*M + 8*N                 */
+    int auto_kernel;        /* automatic choice: 0 slice, 1 stream, 2 rows                   */
+    int row_batch;          /* batch of the lane-per-row kernel (tuned at plan time)         */
 } spmv_b200_hll_info_t;
 
 /* ---- library / device ---------------------------------------------------------------- */
@@ -175,6 +181,8 @@ int spmv_b200_hll_spmv(const spmv_b200_hll *H, const double *d_x, double *d_y, v
 /* spmv_b200_hll_spmv picks between the two kernels below from the mean hack width */
 /* one-warp-per-hack slice kernel, 128/256-bit loads straight from HBM */
 int spmv_b200_hll_spmv_slice(const spmv_b200_hll *H, const double *d_x, double *d_y, void *stream);
+/* one warp per hack, lane = row, in the order of spmv_hll_serial (bit-identical), no shared memory */
+int spmv_b200_hll_spmv_rows(const spmv_b200_hll *H, const double *d_x, double *d_y, void *stream);
 /* persistent TMA bulk-copy pipeline (shared-memory staging) */
 int spmv_b200_hll_spmv_stream(const spmv_b200_hll *H, const double *d_x, double *d_y, void *stream);
 int spmv_b200_hll_spmv_host(spmv_b200_hll *H, const double *x, double *y);

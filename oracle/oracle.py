@@ -482,3 +482,49 @@ class Reference:
 def best_available():
     """The real reference when its .so exists (this container / shipped with gpurun), else the port."""
     return Reference() if reference_available() else Restated()
+
+
+# ---- the reference's own GPU kernels, recompiled for sm_100a (oracle/_ref/libspmv_ref_cuda.so) -----------------
+def reference_cuda_available() -> bool:
+    return (HERE / "_ref" / "libspmv_ref_cuda.so").exists()
+
+
+class ReferenceCuda:
+    """Launches the UNMODIFIED reference kernels (cuda_src/csr_matrix_cuda.cu:122-241, cuda_src/hll_matrix.cu:346-479)
+    through oracle/ref_cuda_shim.cu, with the launch shapes of the reference driver.  The "existing kernel" bar of
+    bench.py and a second checker for the GPU parity tests.  Arguments are CUDA tensors (anything with data_ptr())."""
+    CSR_KERNELS = ("spmv_csr_naive_kernel", "spmv_csr_warp_kernel", "spmv_csr_warp_shared_memory_kernel")
+    HLL_KERNELS = ("spmv_hll_naive_kernel", "spmv_hll_warp_kernel", "spmv_hll_warp_shared_kernel_v1")
+
+    def __init__(self):
+        self.lib = C.CDLL(str(HERE / "_ref" / "libspmv_ref_cuda.so"))
+        self.lib.ref_cuda_csr_spmv.restype = C.c_int
+        self.lib.ref_cuda_csr_spmv.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
+        self.lib.ref_cuda_hll_upload.restype = C.c_int
+        self.lib.ref_cuda_hll_upload.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        self.lib.ref_cuda_hll_spmv.restype = C.c_int
+        self.lib.ref_cuda_hll_spmv.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.lib.ref_cuda_hll_free.restype = None
+        self.lib.ref_cuda_hll_free.argtypes = [C.c_void_p]
+
+    def csr_spmv(self, which, M, N, row_ptr, col_idx, values, x, y, stream=None):
+        rc = self.lib.ref_cuda_csr_spmv(int(which), int(M), int(N), row_ptr.data_ptr(), col_idx.data_ptr(), values.data_ptr(),
+                                        x.data_ptr(), y.data_ptr(), stream)
+        if rc != 0:
+            raise OracleError(f"reference CUDA CSR kernel {which} failed")
+        return y
+
+    def hll_upload(self, host_hll_struct_ptr, M):
+        """host_hll_struct_ptr: ctypes pointer to a host HLLMatrix in the reference layout (row-major blocks)."""
+        h = C.c_void_p()
+        if self.lib.ref_cuda_hll_upload(host_hll_struct_ptr, int(M), C.byref(h)) != 0:
+            raise OracleError("reference CUDA HLL upload failed")
+        return h
+
+    def hll_spmv(self, handle, which, x, y, stream=None):
+        if self.lib.ref_cuda_hll_spmv(handle, int(which), x.data_ptr(), y.data_ptr(), stream) != 0:
+            raise OracleError(f"reference CUDA HLL kernel {which} failed")
+        return y
+
+    def hll_free(self, handle):
+        self.lib.ref_cuda_hll_free(handle)

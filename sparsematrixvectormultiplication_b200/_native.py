@@ -59,13 +59,14 @@ class DiffMetricsStruct(C.Structure):  # reference libs/performance_calculate.h:
 class CsrInfo(C.Structure):  # include/spmv_b200.h spmv_b200_csr_info_t
     _fields_ = [("M", C.c_int), ("N", C.c_int), ("nnz", C.c_longlong), ("num_tiles", C.c_int),
                 ("num_long_rows", C.c_int), ("num_fragments", C.c_int), ("threads_per_row", C.c_int),
-                ("tile_items", C.c_int), ("long_threshold", C.c_int), ("algorithmic_bytes", C.c_longlong)]
+                ("tile_items", C.c_int), ("long_threshold", C.c_int), ("algorithmic_bytes", C.c_longlong),
+                ("max_row_nnz", C.c_int), ("auto_algo", C.c_int), ("row_batch", C.c_int)]
 
 
 class HllInfo(C.Structure):  # include/spmv_b200.h spmv_b200_hll_info_t
     _fields_ = [("M", C.c_int), ("N", C.c_int), ("num_hacks", C.c_int), ("max_maxnz", C.c_int),
                 ("slots", C.c_longlong), ("nnz_reference_slots", C.c_longlong),
-                ("algorithmic_bytes", C.c_longlong)]
+                ("algorithmic_bytes", C.c_longlong), ("auto_kernel", C.c_int), ("row_batch", C.c_int)]
 
 
 class Peers(C.Structure):  # include/spmv_b200.h spmv_b200_peers_t
@@ -120,6 +121,7 @@ SIGNATURES = {
     "spmv_b200_hll_spmv_slice": (_I, [_V, _V, _V, _V]),
     "spmv_b200_hll_spmv_stream": (_I, [_V, _V, _V, _V]),
     "spmv_b200_hll_spmv_host": (_I, [_V, _V, _V]),
+    "spmv_b200_hll_spmv_rows": (_I, [_V, _V, _V, _V]),
     "spmv_b200_csr_time": (_I, [_V, _V, _V, _I, _I, _I, c_dbl_p, c_dbl_p]),
     "spmv_b200_hll_time": (_I, [_V, _V, _V, _I, _I, _I, c_dbl_p, c_dbl_p]),
     "spmv_b200_hll_spmv_hacks": (_I, [_V, _I, _I, _V, _V, _V]),

@@ -34,6 +34,23 @@ constexpr int kFragNnz = 8192;              // nonzeros per long-row fragment (o
 constexpr int kFragThreads = 256;
 constexpr int kSmemSlack = 8;
 constexpr int kVecBatch = 4;                // independent column -> gather chains per lane of the vector kernel
+constexpr long long kAutotuneMinNnz = 1 << 22;  // plan-time timing of the row-kernel batch only pays on large matrices
+constexpr int kRowBatch = 4;                // the same with ONE lane per row (bin 0 of the binned kernel)
+
+// Matrix stream loads of the vector kernels.  Several lanes per row: consecutive lanes read consecutive elements, every
+// sector is consumed by one instruction -> no L1 allocation.  ONE lane per row: lane i walks its own row, a warp's
+// loads are strided by the row length and a sector is consumed over several iterations -> it must live in L1 in
+// between (plain read-only loads; measured on lap2d 4096^2: 5.1 TB/s without allocation, 6.0 TB/s with).
+template <int VEC>
+__device__ __forceinline__ int load_col(const int *p) {
+    if constexpr (VEC == 1) return __ldg(p);
+    else return ldg_stream_s32(p);
+}
+template <int VEC>
+__device__ __forceinline__ double load_val(const double *p) {
+    if constexpr (VEC == 1) return __ldg(p);
+    else return ldg_stream_f64(p);
+}
 
 // ================================================================================================
 // kernels
@@ -195,17 +212,18 @@ csr_vector_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, c
     // kVecBatch column/value loads are issued before the first gather and the gathers before the first fma: the
     // column -> x dependency costs one round trip per batch instead of one per element
     double acc = (VEC == 1 && accumulate && live) ? y[row] : 0.0;  // one lane per row: y += A x in the serial loop's order
-    for (int k = lo + lane; k < hi; k += kVecBatch * VEC) {
-        int c[kVecBatch];
-        double v[kVecBatch], xv[kVecBatch];
+    constexpr int kBatch = VEC == 1 ? kRowBatch : kVecBatch;
+    for (int k = lo + lane; k < hi; k += kBatch * VEC) {
+        int c[kBatch];
+        double v[kBatch], xv[kBatch];
 #pragma unroll
-        for (int u = 0; u < kVecBatch; ++u) c[u] = k + u * VEC < hi ? ldg_stream_s32(col_idx + k + u * VEC) : -1;
+        for (int u = 0; u < kBatch; ++u) c[u] = k + u * VEC < hi ? load_col<VEC>(col_idx + k + u * VEC) : -1;
 #pragma unroll
-        for (int u = 0; u < kVecBatch; ++u) v[u] = k + u * VEC < hi ? ldg_stream_f64(values + k + u * VEC) : 0.0;
+        for (int u = 0; u < kBatch; ++u) v[u] = k + u * VEC < hi ? load_val<VEC>(values + k + u * VEC) : 0.0;
 #pragma unroll
-        for (int u = 0; u < kVecBatch; ++u) xv[u] = c[u] >= 0 ? ldg_x(x, c[u]) : 0.0;
+        for (int u = 0; u < kBatch; ++u) xv[u] = c[u] >= 0 ? ldg_x(x, c[u]) : 0.0;
 #pragma unroll
-        for (int u = 0; u < kVecBatch; ++u)
+        for (int u = 0; u < kBatch; ++u)
             if (c[u] >= 0) {
                 if constexpr (VEC == 1) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));  // one lane, index order: the serial loop
                 else acc = fma(v[u], xv[u], acc);
@@ -214,6 +232,36 @@ csr_vector_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, c
 #pragma unroll
     for (int off = VEC >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (live && lane == 0) y[row] = (accumulate && VEC > 1) ? y[row] + acc : acc;
+}
+
+// One THREAD per row (stencil-like matrices, every row short).  Lane i walks row i: a warp's loads are strided by the
+// row length, so a sector is consumed over several iterations and must live in L1 in between -- plain read-only
+// loads that allocate, no shared memory (all 256 KB are L1), 8 CTAs x 256 threads per SM.  BATCH column/value loads
+// are issued before the first gather.  One lane, index order, mul and add rounded separately: every row is bit-identical
+// to the reference's serial loop (src/csr_matrix.c:134-138) -- and it is the reference's own thread-per-row idea
+// (cuda_src/csr_matrix_cuda.cu:122-146), which at 6.0 TB/s on lap2d 4096^2 is the kernel to beat on this chip.
+template <int BATCH>
+__global__ void __launch_bounds__(256, 8)
+csr_row_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+               const double *__restrict__ values, const double *__restrict__ x, double *__restrict__ y, int accumulate) {
+    const long long row = row_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= row_end) return;
+    const int lo = __ldg(row_ptr + row), hi = __ldg(row_ptr + row + 1);
+    double acc = accumulate ? y[row] : 0.0;
+    for (int k = lo; k < hi; k += BATCH) {
+        int c[BATCH];
+        double v[BATCH], xv[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) c[u] = k + u < hi ? __ldg(col_idx + k + u) : -1;
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) v[u] = k + u < hi ? __ldg(values + k + u) : 0.0;
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u)
+            if (c[u] >= 0) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+    }
+    y[row] = acc;
 }
 
 // ---- row-binned vector kernel (skewed matrices) ------------------------------------------------------
@@ -225,7 +273,7 @@ csr_vector_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, c
 constexpr int kBinLongThreshold = 2048;  // rows above this are split into kFragNnz fragments (csr_long_* kernels)
 
 __host__ __device__ __forceinline__ int bin_of(int len) {
-    if (len <= 6) return 0;
+    if (len <= 8) return 0;
     if (len <= 12) return 1;
     if (len <= 24) return 2;
     if (len <= 48) return 3;
@@ -253,17 +301,18 @@ __device__ __forceinline__ void binned_rows(int local_block, int first, int coun
         hi = __ldg(row_ptr + row + 1);
     }
     double acc = (VEC == 1 && accumulate && live) ? y[row] : 0.0;
-    for (int k = lo + lane; k < hi; k += kVecBatch * VEC) {
-        int c[kVecBatch];
-        double v[kVecBatch], xv[kVecBatch];
+    constexpr int kBatch = VEC == 1 ? kRowBatch : kVecBatch;
+    for (int k = lo + lane; k < hi; k += kBatch * VEC) {
+        int c[kBatch];
+        double v[kBatch], xv[kBatch];
 #pragma unroll
-        for (int u = 0; u < kVecBatch; ++u) c[u] = k + u * VEC < hi ? ldg_stream_s32(col_idx + k + u * VEC) : -1;
+        for (int u = 0; u < kBatch; ++u) c[u] = k + u * VEC < hi ? load_col<VEC>(col_idx + k + u * VEC) : -1;
 #pragma unroll
-        for (int u = 0; u < kVecBatch; ++u) v[u] = k + u * VEC < hi ? ldg_stream_f64(values + k + u * VEC) : 0.0;
+        for (int u = 0; u < kBatch; ++u) v[u] = k + u * VEC < hi ? load_val<VEC>(values + k + u * VEC) : 0.0;
 #pragma unroll
-        for (int u = 0; u < kVecBatch; ++u) xv[u] = c[u] >= 0 ? ldg_x(x, c[u]) : 0.0;
+        for (int u = 0; u < kBatch; ++u) xv[u] = c[u] >= 0 ? ldg_x(x, c[u]) : 0.0;
 #pragma unroll
-        for (int u = 0; u < kVecBatch; ++u)
+        for (int u = 0; u < kBatch; ++u)
             if (c[u] >= 0) {
                 if constexpr (VEC == 1) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));  // one lane, index order: the serial loop
                 else acc = fma(v[u], xv[u], acc);
@@ -314,8 +363,13 @@ __global__ void bin_key_kernel(int M, const int *__restrict__ row_ptr, unsigned 
 // counts the 4-byte words that precede row r), or a neighbour of / a long row.  All tiles therefore
 // carry (nearly) the same number of bytes, whatever the row lengths.
 __global__ void plan_flag_kernel(int M, const int *__restrict__ row_ptr, int tile_items, int long_threshold,
-                                 unsigned char *__restrict__ boundary, unsigned char *__restrict__ is_long) {
+                                 unsigned char *__restrict__ boundary, unsigned char *__restrict__ is_long,
+                                 int *__restrict__ max_row) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int len = 0;
+    if (r < M) len = row_ptr[r + 1] - row_ptr[r];
+    const int warp_max = __reduce_max_sync(0xffffffffu, len);
+    if ((threadIdx.x & 31) == 0 && warp_max > 0) atomicMax(max_row, warp_max);  // integer max: order independent
     if (r >= M) return;
     const int a = row_ptr[r], b = row_ptr[r + 1];
     const bool long_here = b - a > long_threshold;
@@ -383,6 +437,9 @@ static size_t tile_smem_bytes(const spmv_b200_csr *A) {
     return (size_t)(A->tile_items / 3 + A->long_threshold + kSmemSlack) * sizeof(double);
 }
 
+static int launch_rows(int row_begin, int row_end, const int *row_ptr, const int *col_idx, const double *values,
+                       const double *x, double *y, int batch, int accumulate, cudaStream_t stream);
+
 static int build_plan(spmv_b200_csr *A, cudaStream_t stream) {
     free_plan(A);
     host_pipe_free(A->pipe);  // the row windows of the host entry point follow the tiles
@@ -423,9 +480,10 @@ static int build_plan(spmv_b200_csr *A, cudaStream_t stream) {
     PLAN_TRY(cudaMalloc(&is_long, (size_t)M));
     PLAN_TRY(cudaMalloc(&tile_rows, (size_t)std::min<long long>(max_tiles, M) * sizeof(int)));
     PLAN_TRY(cudaMalloc(&A->long_rows, (size_t)std::min<long long>(max_long, M) * sizeof(int)));
-    PLAN_TRY(cudaMalloc(&d_selected, 2 * sizeof(int)));
+    PLAN_TRY(cudaMalloc(&d_selected, 3 * sizeof(int)));
+    PLAN_TRY(cudaMemsetAsync(d_selected, 0, 3 * sizeof(int), stream));
     plan_flag_kernel<<<blocks_for(M, 256), 256, 0, stream>>>(M, A->row_ptr, A->tile_items, A->long_threshold,
-                                                             boundary, is_long);
+                                                             boundary, is_long, d_selected + 2);
     PLAN_TRY(cudaGetLastError());
 
     thrust::counting_iterator<int> row_ids(0);
@@ -436,11 +494,12 @@ static int build_plan(spmv_b200_csr *A, cudaStream_t stream) {
     PLAN_TRY(cudaMalloc(&temp, temp_bytes ? temp_bytes : 1));
     PLAN_TRY(cub::DeviceSelect::Flagged(temp, temp_bytes, row_ids, boundary, tile_rows, d_selected, M, stream));
     PLAN_TRY(cub::DeviceSelect::Flagged(temp, temp_bytes, row_ids, is_long, A->long_rows, d_selected + 1, M, stream));
-    int selected[2] = {0, 0};
+    int selected[3] = {0, 0, 0};
     PLAN_TRY(cudaMemcpyAsync(selected, d_selected, sizeof selected, cudaMemcpyDeviceToHost, stream));
     PLAN_TRY(cudaStreamSynchronize(stream));
     A->num_tiles = selected[0];
     A->num_long = selected[1];
+    A->max_row = selected[2];
 
     PLAN_TRY(cudaMalloc(&A->tiles, (size_t)(A->num_tiles + 1) * sizeof(int2)));
     plan_tiles_kernel<<<blocks_for(A->num_tiles + 1, 256), 256, 0, stream>>>(A->num_tiles, M, tile_rows, A->row_ptr,
@@ -472,6 +531,17 @@ static int build_plan(spmv_b200_csr *A, cudaStream_t stream) {
     PLAN_TRY(cudaStreamSynchronize(stream));
 #undef PLAN_TRY
     cleanup();
+    // batch of the thread-per-row kernel: about the mean row length; on large matrices the candidates are timed
+    // (a few products on scratch vectors) -- the best batch depends on how rows, lines and L1 capacity interact
+    const int forced_batch = env_int("SPMV_B200_ROW_BATCH", 0);
+    A->row_batch = std::max(2, std::min(6, (int)((A->nnz + M - 1) / std::max(M, 1))));
+    if (forced_batch >= 1 && forced_batch <= 8) {
+        A->row_batch = forced_batch;
+    } else if (A->max_row <= kRowKernelMaxLen && A->nnz >= kAutotuneMinNnz && env_int("SPMV_B200_AUTOTUNE", 1)) {
+        A->row_batch = tune_batch(M, A->N, A->row_batch, stream, [&](int batch, double *x, double *y) {
+            return launch_rows(0, M, A->row_ptr, A->col_idx, A->values, x, y, batch, 0, stream);
+        });
+    }
     return stream_prepare_csr(A);
 }
 
@@ -480,7 +550,7 @@ static int pick_vector_width(long long nnz, int M) {
     const int forced = env_int("SPMV_B200_VECTOR_WIDTH", 0);
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
     const double avg = M > 0 ? (double)nnz / M : 0.0;
-    if (avg <= 6.0) return 1;
+    if (avg <= 8.0) return 1;
     if (avg <= 12.0) return 2;
     if (avg <= 24.0) return 4;
     if (avg <= 48.0) return 8;
@@ -488,10 +558,26 @@ static int pick_vector_width(long long nnz, int M) {
     return 32;
 }
 
+static int launch_rows(int row_begin, int row_end, const int *row_ptr, const int *col_idx, const double *values,
+                       const double *x, double *y, int batch, int accumulate, cudaStream_t stream) {
+    const long long rows = (long long)row_end - row_begin;
+    if (rows <= 0) return SPMV_B200_OK;
+    const unsigned int g = blocks_for(rows, 256);
+#define ROW_CASE(B) case B: csr_row_kernel<B><<<g, 256, 0, stream>>>(row_begin, row_end, row_ptr, col_idx, values, x, y, accumulate); break;
+    switch (batch) {
+        ROW_CASE(1) ROW_CASE(2) ROW_CASE(3) ROW_CASE(5) ROW_CASE(6) ROW_CASE(7) ROW_CASE(8)
+        default: csr_row_kernel<4><<<g, 256, 0, stream>>>(row_begin, row_end, row_ptr, col_idx, values, x, y, accumulate); break;
+    }
+#undef ROW_CASE
+    SPMV_TRY_CUDA(cudaGetLastError());
+    return SPMV_B200_OK;
+}
+
 static int launch_vector(int row_begin, int row_end, const int *row_ptr, const int *col_idx, const double *values,
                          const double *x, double *y, int vec, int accumulate, cudaStream_t stream) {
     const long long rows = (long long)row_end - row_begin;
     if (rows <= 0) return SPMV_B200_OK;
+    if (vec == 1) return launch_rows(row_begin, row_end, row_ptr, col_idx, values, x, y, env_int("SPMV_B200_ROW_BATCH", 4), accumulate, stream);
     const unsigned int grid = blocks_for(rows * vec, 256);
 #define VEC_CASE(V)                                                                                              \
     case V:                                                                                                      \
@@ -636,7 +722,10 @@ CsrPath csr_resolve(const spmv_b200_csr *A, int algo) {
         case SPMV_B200_ALGO_TILE: return kPathTile;
         case SPMV_B200_ALGO_VECTOR: return kPathVector;
         case SPMV_B200_ALGO_BINNED: return kPathBinned;
+        case SPMV_B200_ALGO_ROW: return kPathRow;
         default:
+            // every row short: one thread per row (serial order, so forced_tpr == 1 is honoured as well)
+            if (A->max_row <= kRowKernelMaxLen) return kPathRow;
             if (A->forced_tpr == 1 || A->nnz <= (long long)kAutoStreamMaxAvg * A->M) return kPathStream;
             return A->num_long == 0 ? kPathVector : kPathBinned;
     }
@@ -645,6 +734,8 @@ CsrPath csr_resolve(const spmv_b200_csr *A, int algo) {
 int csr_launch_window(const spmv_b200_csr *A, CsrPath path, int unit_begin, int unit_end, const double *x, double *y,
                       int accumulate, cudaStream_t stream) {
     if (path == kPathBinned) return launch_binned(A, x, y, accumulate, stream);  // whole matrix: rows are permuted
+    if (path == kPathRow)
+        return launch_rows(unit_begin, unit_end, A->row_ptr, A->col_idx, A->values, x, y, A->row_batch, accumulate, stream);
     if (path == kPathVector)
         return launch_vector(unit_begin, unit_end, A->row_ptr, A->col_idx, A->values, x, y, pick_vector_width(A->nnz, A->M),
                              accumulate, stream);
@@ -769,6 +860,15 @@ int spmv_b200_csr_info(const spmv_b200_csr *A, spmv_b200_csr_info_t *info) {
     info->tile_items = A->tile_items;
     info->long_threshold = A->long_threshold;
     info->algorithmic_bytes = A->nnz * 12 + 4LL * ((long long)A->M + 1) + 8LL * A->M + 8LL * A->N;
+    info->max_row_nnz = A->max_row;
+    switch (csr_resolve(A, SPMV_B200_ALGO_AUTO)) {
+        case kPathRow: info->auto_algo = SPMV_B200_ALGO_ROW; break;
+        case kPathStream: info->auto_algo = SPMV_B200_ALGO_STREAM; break;
+        case kPathVector: info->auto_algo = SPMV_B200_ALGO_VECTOR; break;
+        case kPathBinned: info->auto_algo = SPMV_B200_ALGO_BINNED; break;
+        default: info->auto_algo = SPMV_B200_ALGO_TILE; break;
+    }
+    info->row_batch = A->row_batch;
     return SPMV_B200_OK;
 }
 
@@ -792,9 +892,10 @@ int spmv_b200_csr_download(const spmv_b200_csr *A, int *row_ptr, int *col_idx, d
 int spmv_b200_csr_spmv(const spmv_b200_csr *A, const double *d_x, double *d_y, int accumulate, int algo, void *stream) {
     if (!A || !d_y || (A->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "csr_spmv: NULL argument");
     if (A->M == 0) return SPMV_B200_OK;
-    if (algo < SPMV_B200_ALGO_AUTO || algo > SPMV_B200_ALGO_BINNED) return fail(SPMV_B200_ERR_INVALID, "csr_spmv: unknown algo %d", algo);
+    if (algo < SPMV_B200_ALGO_AUTO || algo > SPMV_B200_ALGO_ROW) return fail(SPMV_B200_ERR_INVALID, "csr_spmv: unknown algo %d", algo);
     const CsrPath path = csr_resolve(A, algo);
-    return csr_launch_window(A, path, 0, path == kPathVector ? A->M : A->num_tiles, d_x, d_y, accumulate, as_stream(stream));
+    const bool by_rows = path == kPathVector || path == kPathRow;
+    return csr_launch_window(A, path, 0, by_rows ? A->M : A->num_tiles, d_x, d_y, accumulate, as_stream(stream));
 }
 
 int spmv_b200_csr_partials_count(const spmv_b200_csr *A) { return A ? std::max(A->stream_grid, 1) : 0; }

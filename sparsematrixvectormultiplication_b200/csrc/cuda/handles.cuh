@@ -63,6 +63,8 @@ struct spmv_b200_csr {
     int num_frag = 0;
     double *frag_partial = nullptr;
     spmv::BinPlan bins;
+    int max_row = 0;     // longest row (plan time)
+    int row_batch = 4;   // csr_row_kernel: column/value/gather batch per thread (tuned at plan time on large matrices)
     // stream kernel launch shape
     int stages = spmv::kDefaultStages;
     int consumers = 12;
@@ -88,6 +90,7 @@ struct spmv_b200_hll {
     int num_tiles = 0;
     spmv::HllTile *tiles = nullptr;
     int stream_grid = 0;
+    int row_batch = 4;   // hll_row_kernel batch (tuned at plan time on large matrices)
     double *stage_x = nullptr;
     double *stage_y = nullptr;
     spmv::HostPipe *pipe = nullptr;
@@ -103,12 +106,45 @@ int stream_plan_hll(spmv_b200_hll *H, cudaStream_t stream);
 int stream_launch_hll(const spmv_b200_hll *H, const double *x, double *y, cudaStream_t stream, int tile_begin = 0,
                       int tile_count = -1);
 // csr.cu / hll.cu: which kernel the automatic choice resolves to, and launches restricted to a window
-enum CsrPath { kPathStream, kPathTile, kPathVector, kPathBinned };
+enum CsrPath { kPathStream, kPathTile, kPathVector, kPathBinned, kPathRow };
+constexpr int kRowKernelMaxLen = 16;  // AUTO: one thread per row when no row is longer than this
 CsrPath csr_resolve(const spmv_b200_csr *A, int algo);
 int csr_launch_window(const spmv_b200_csr *A, CsrPath path, int unit_begin, int unit_end, const double *x, double *y,
                       int accumulate, cudaStream_t stream);  // units: tiles (stream/tile paths) or rows (vector path)
-bool hll_prefers_stream(const spmv_b200_hll *H);
-int hll_launch_window(const spmv_b200_hll *H, bool stream_kernel, int unit_begin, int unit_end, const double *x, double *y,
-                      cudaStream_t stream);  // units: tiles (stream kernel) or hacks (slice kernel)
+enum HllPath { kHllSlice = 0, kHllStream = 1, kHllRows = 2 };
+HllPath hll_resolve(const spmv_b200_hll *H);
+int hll_launch_window(const spmv_b200_hll *H, HllPath path, int unit_begin, int unit_end, const double *x, double *y,
+                      cudaStream_t stream);  // units: tiles (stream kernel) or hacks (slice and row kernels)
 int env_int(const char *name, int fallback);
+// Times launch(batch) for every candidate batch on scratch vectors and returns the fastest (plan time, large matrices).
+template <class Launch>
+int tune_batch(long long M, long long N, int fallback, cudaStream_t stream, Launch launch) {
+    double *x = nullptr, *y = nullptr;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int best = fallback;
+    if (cudaMalloc(&x, (size_t)(N > 0 ? N : 1) * sizeof(double)) == cudaSuccess &&
+        cudaMalloc(&y, (size_t)(M > 0 ? M : 1) * sizeof(double)) == cudaSuccess &&
+        cudaMemsetAsync(x, 0, (size_t)(N > 0 ? N : 1) * sizeof(double), stream) == cudaSuccess &&
+        cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) {
+        float best_ms = 0.0f;
+        for (int batch = 2; batch <= 7; ++batch) {
+            bool ok = launch(batch, x, y) == SPMV_B200_OK;  // warm-up
+            ok = ok && cudaEventRecord(a, stream) == cudaSuccess;
+            for (int rep = 0; rep < 3 && ok; ++rep) ok = launch(batch, x, y) == SPMV_B200_OK;
+            ok = ok && cudaEventRecord(b, stream) == cudaSuccess && cudaEventSynchronize(b) == cudaSuccess;
+            float ms = 0.0f;
+            if (!ok || cudaEventElapsedTime(&ms, a, b) != cudaSuccess) break;
+            if (batch == 2 || ms < best_ms) {
+                best_ms = ms;
+                best = batch;
+            }
+        }
+    }
+    cudaGetLastError();  // a failed scratch allocation is not an error of the plan: the fallback batch stands
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+    cudaFree(x);
+    cudaFree(y);
+    return best;
+}
 }  // namespace spmv

@@ -77,6 +77,38 @@ hll_slice_kernel(int hack_begin, int hack_end, const long long *__restrict__ hac
     }
 }
 
+// Row kernel for narrow hacks (stencils): one warp per hack, lane = row, the column-major image makes every load of a
+// warp one contiguous 128 B (JA) / 256 B (AS) segment -- no shared memory, no reliance on L1 for the stream.  BATCH
+// slots are requested before the first gather.  One lane per row, sequential in j, mul and add rounded separately:
+// bit-identical to the reference's spmv_hll_serial (src/hll_matrix.c:294-306), padding slots (x 0.0) included.
+template <int BATCH>
+__global__ void __launch_bounds__(256, 8)
+hll_row_kernel(int hack_begin, int hack_end, const long long *__restrict__ hack_off, const int *__restrict__ JA,
+               const double *__restrict__ AS, const double *__restrict__ x, double *__restrict__ y, int M) {
+    const int hack = hack_begin + blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (hack >= hack_end) return;  // warp-uniform
+    const int lane = threadIdx.x & 31;
+    const long long off = __ldg(hack_off + hack);
+    const int width = (int)((__ldg(hack_off + hack + 1) - off) >> 5);
+    const long long base = off + lane;
+    double acc = 0.0;
+    for (int j = 0; j < width; j += BATCH) {
+        int c[BATCH];
+        double v[BATCH], xv[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) c[u] = j + u < width ? ldg_stream_s32(JA + base + (long long)(j + u) * kHack) : -1;
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) v[u] = j + u < width ? ldg_stream_f64(AS + base + (long long)(j + u) * kHack) : 0.0;
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) xv[u] = c[u] >= 0 ? ldg_x(x, c[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u)
+            if (c[u] >= 0) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+    }
+    const long long row = (long long)hack * kHack + lane;
+    if (row < M) y[row] = acc;
+}
+
 // ---- CSR -> HLL on the device ----------------------------------------------------------------------
 __global__ void hll_width_kernel(int M, int num_hacks, const int *__restrict__ row_ptr, long long *__restrict__ slots,
                                  int *__restrict__ widths) {
@@ -139,6 +171,20 @@ extern "C" int spmv_b200_csr_info(const spmv_b200_csr *A, spmv_b200_csr_info_t *
 
 using namespace spmv;
 
+static int hll_launch_rows(const spmv_b200_hll *H, int hack_begin, int hack_end, const double *d_x, double *d_y,
+                           cudaStream_t stream) {
+    if (hack_end <= hack_begin) return SPMV_B200_OK;
+    const unsigned int g = blocks_for(hack_end - hack_begin, 8);
+#define HROW_CASE(B) case B: hll_row_kernel<B><<<g, 256, 0, stream>>>(hack_begin, hack_end, H->hack_off, H->JA, H->AS, d_x, d_y, H->M); break;
+    switch (H->row_batch) {
+        HROW_CASE(1) HROW_CASE(2) HROW_CASE(3) HROW_CASE(5) HROW_CASE(6) HROW_CASE(7) HROW_CASE(8)
+        default: hll_row_kernel<4><<<g, 256, 0, stream>>>(hack_begin, hack_end, H->hack_off, H->JA, H->AS, d_x, d_y, H->M); break;
+    }
+#undef HROW_CASE
+    SPMV_TRY_CUDA(cudaGetLastError());
+    return SPMV_B200_OK;
+}
+
 static int hll_launch(const spmv_b200_hll *H, int hack_begin, int hack_end, const double *d_x, double *d_y,
                       cudaStream_t stream) {
     if (hack_end <= hack_begin) return SPMV_B200_OK;
@@ -156,13 +202,36 @@ static int hll_alloc_arena(spmv_b200_hll *H) {
 }
 
 namespace spmv {
-// narrow hacks (stencils): TMA stream kernel; wide hacks are gather bound and need the occupancy of the slice kernel
-bool hll_prefers_stream(const spmv_b200_hll *H) { return H->slots <= 12LL * 32 * H->num_hacks; }
+// no hack wider than 16 columns (stencils): lane-per-row kernel, coalesced by the column-major layout; narrow on
+// average: TMA stream kernel; wide hacks are gather bound and need the occupancy of the slice kernel
+HllPath hll_resolve(const spmv_b200_hll *H) {
+    if (H->max_width <= kRowKernelMaxLen) return kHllRows;
+    return H->slots <= 12LL * 32 * H->num_hacks ? kHllStream : kHllSlice;
+}
 
-int hll_launch_window(const spmv_b200_hll *H, bool stream_kernel, int unit_begin, int unit_end, const double *x, double *y,
+int hll_launch_window(const spmv_b200_hll *H, HllPath path, int unit_begin, int unit_end, const double *x, double *y,
                       cudaStream_t stream) {
-    if (stream_kernel) return stream_launch_hll(H, x, y, stream, unit_begin, unit_end - unit_begin);
+    if (path == kHllStream) return stream_launch_hll(H, x, y, stream, unit_begin, unit_end - unit_begin);
+    if (path == kHllRows) return hll_launch_rows(H, unit_begin, unit_end, x, y, stream);
     return hll_launch(H, unit_begin, unit_end, x, y, stream);
+}
+
+// batch of the lane-per-row kernel: the hack width when it is uniform and small; timed at plan time on large images
+static void hll_pick_row_batch(spmv_b200_hll *H, cudaStream_t stream) {
+    const int forced = env_int("SPMV_B200_HLL_ROW_BATCH", 0);
+    const long long mean = H->num_hacks > 0 ? (H->slots / 32 + H->num_hacks - 1) / H->num_hacks : 4;
+    H->row_batch = (int)std::max<long long>(2, std::min<long long>(7, mean));
+    if (forced >= 1 && forced <= 8) {
+        H->row_batch = forced;
+    } else if (H->max_width <= kRowKernelMaxLen && H->slots >= (1 << 22) && env_int("SPMV_B200_AUTOTUNE", 1)) {
+        H->row_batch = tune_batch(H->M, H->N, H->row_batch, stream, [&](int batch, double *x, double *y) {
+            const int keep = H->row_batch;
+            H->row_batch = batch;
+            const int rc = hll_launch_rows(H, 0, H->num_hacks, x, y, stream);
+            H->row_batch = keep;
+            return rc;
+        });
+    }
 }
 }  // namespace spmv
 
@@ -228,6 +297,7 @@ int spmv_b200_hll_upload(const HLLMatrix *hll, int M, int N, spmv_b200_hll **out
         };
         rc = dev();
         if (rc == SPMV_B200_OK) rc = stream_plan_hll(H, nullptr);
+        if (rc == SPMV_B200_OK) hll_pick_row_batch(H, nullptr);
     }
     std::free(ja);
     std::free(as);
@@ -290,7 +360,9 @@ int spmv_b200_hll_from_csr(const spmv_b200_csr *A, void *stream_, spmv_b200_hll 
             SPMV_TRY_CUDA(cudaGetLastError());
         }
         SPMV_TRY_CUDA(cudaStreamSynchronize(stream));
-        return stream_plan_hll(H, stream);
+        SPMV_TRY(stream_plan_hll(H, stream));
+        hll_pick_row_batch(H, stream);
+        return SPMV_B200_OK;
     };
     int rc = body();
     cudaFree(slots);
@@ -314,6 +386,8 @@ int spmv_b200_hll_info(const spmv_b200_hll *H, spmv_b200_hll_info_t *info) {
     info->slots = H->slots;
     info->nnz_reference_slots = H->ref_slots;
     info->algorithmic_bytes = H->slots * 12 + 8LL * ((long long)H->num_hacks + 1) + 8LL * H->M + 8LL * H->N;
+    info->auto_kernel = (int)hll_resolve(H);
+    info->row_batch = H->row_batch;
     return SPMV_B200_OK;
 }
 
@@ -385,13 +459,18 @@ int spmv_b200_hll_download(const spmv_b200_hll *H, HLLMatrix *out) {
 
 int spmv_b200_hll_spmv(const spmv_b200_hll *H, const double *d_x, double *d_y, void *stream) {
     if (!H || !d_y || (H->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "hll_spmv: NULL argument");
-    if (hll_prefers_stream(H)) return stream_launch_hll(H, d_x, d_y, as_stream(stream));
-    return hll_launch(H, 0, H->num_hacks, d_x, d_y, as_stream(stream));
+    const HllPath path = hll_resolve(H);
+    return hll_launch_window(H, path, 0, path == kHllStream ? H->num_tiles : H->num_hacks, d_x, d_y, as_stream(stream));
 }
 
 int spmv_b200_hll_spmv_stream(const spmv_b200_hll *H, const double *d_x, double *d_y, void *stream) {
     if (!H || !d_y || (H->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_stream: NULL argument");
     return stream_launch_hll(H, d_x, d_y, as_stream(stream));
+}
+
+int spmv_b200_hll_spmv_rows(const spmv_b200_hll *H, const double *d_x, double *d_y, void *stream) {
+    if (!H || !d_y || (H->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_rows: NULL argument");
+    return hll_launch_rows(H, 0, H->num_hacks, d_x, d_y, as_stream(stream));
 }
 
 int spmv_b200_hll_spmv_slice(const spmv_b200_hll *H, const double *d_x, double *d_y, void *stream) {

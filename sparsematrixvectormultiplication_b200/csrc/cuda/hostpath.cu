@@ -179,7 +179,7 @@ static void abort_pipeline(HostPipe *p) {  // after an error: nothing of this ca
 // ---- CSR --------------------------------------------------------------------------------------------------------
 static int csr_plan_windows(spmv_b200_csr *A, CsrPath path) {
     HostPipe *p = A->pipe;
-    const bool by_tiles = path != kPathVector;
+    const bool by_tiles = path != kPathVector && path != kPathRow;
     // long rows are computed after every tile (they need all of x and are written last), the binned kernel walks the
     // rows in bin order: one window
     const int units = by_tiles ? A->num_tiles : A->M;
@@ -248,7 +248,7 @@ extern "C" {
 
 int spmv_b200_csr_spmv_host(spmv_b200_csr *A, const double *x, double *y, int accumulate, int algo) {
     if (!A || (A->M > 0 && !y) || (A->N > 0 && A->nnz > 0 && !x)) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_host: NULL argument");
-    if (algo < SPMV_B200_ALGO_AUTO || algo > SPMV_B200_ALGO_BINNED) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_host: unknown algo %d", algo);
+    if (algo < SPMV_B200_ALGO_AUTO || algo > SPMV_B200_ALGO_ROW) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_host: unknown algo %d", algo);
     if (A->M == 0) return SPMV_B200_OK;
     if (!A->stage_x) SPMV_TRY_CUDA(cudaMalloc(&A->stage_x, std::max<size_t>(A->N, 1) * sizeof(double)));
     if (!A->stage_y) SPMV_TRY_CUDA(cudaMalloc(&A->stage_y, std::max<size_t>(A->M, 1) * sizeof(double)));
@@ -269,9 +269,10 @@ int spmv_b200_hll_spmv_host(spmv_b200_hll *H, const double *x, double *y) {
     if (!H->stage_x) SPMV_TRY_CUDA(cudaMalloc(&H->stage_x, std::max<size_t>(H->N, 1) * sizeof(double)));
     if (!H->stage_y) SPMV_TRY_CUDA(cudaMalloc(&H->stage_y, std::max<size_t>(H->M, 1) * sizeof(double)));
     if (!H->pipe) SPMV_TRY(pipe_create(&H->pipe));
-    const bool stream_kernel = hll_prefers_stream(H);
+    const HllPath path = hll_resolve(H);
+    const bool stream_kernel = path == kHllStream;
     HostPipe *p = H->pipe;
-    if (p->path != (int)stream_kernel) {
+    if (p->path != (int)path) {
         const int units = stream_kernel ? H->num_tiles : H->num_hacks;
         const int W = pick_windows(H->M, H->N, units);
         p->windows = W;
@@ -290,10 +291,10 @@ int spmv_b200_hll_spmv_host(spmv_b200_hll *H, const double *x, double *y) {
             elem[w] = H->host_off[hack];
         }
         SPMV_TRY(plan_needs(p, H->JA, elem));
-        p->path = (int)stream_kernel;
+        p->path = (int)path;
     }
     const int rc = run_pipeline(p, H->M, x ? H->N : 0, x, y, H->stage_x, H->stage_y, false, [&](int w) {
-        return hll_launch_window(H, stream_kernel, p->unit[w], p->unit[w + 1], H->stage_x, H->stage_y, p->compute);
+        return hll_launch_window(H, path, p->unit[w], p->unit[w + 1], H->stage_x, H->stage_y, p->compute);
     });
     if (rc != SPMV_B200_OK) abort_pipeline(p);
     return rc;

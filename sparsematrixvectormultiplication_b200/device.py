@@ -12,7 +12,9 @@ import numpy as np
 
 from . import _native as N
 
-ALGO_AUTO, ALGO_VECTOR, ALGO_TILE, ALGO_STREAM, ALGO_BINNED = 0, 1, 2, 3, 4
+ALGO_AUTO, ALGO_VECTOR, ALGO_TILE, ALGO_STREAM, ALGO_BINNED, ALGO_ROW = 0, 1, 2, 3, 4, 5
+ALGO_NAMES = {0: "auto", 1: "csr_vector_kernel", 2: "csr_tile_kernel", 3: "csr_stream_kernel", 4: "csr_binned_kernel", 5: "csr_row_kernel"}
+HLL_KERNEL_NAMES = {0: "hll_slice_kernel", 1: "hll_stream_kernel", 2: "hll_row_kernel"}
 SYNTH_LAP2D, SYNTH_LAP3D, SYNTH_UNIFORM = 1, 2, 3
 
 
@@ -222,12 +224,12 @@ class DeviceHLL:
 
     def spmv(self, x, y, stream=None, slice_kernel=None):
         """y = A x.  slice_kernel: None = automatic choice, True = one-warp-per-hack slice kernel,
-        False = persistent TMA stream kernel."""
+        False = persistent TMA stream kernel, "rows" = lane-per-row kernel in the serial order."""
         i = self.info()
         _check_vec(x, i.N, "x")
         _check_vec(y, i.M, "y")
         fn = {None: N.lib().spmv_b200_hll_spmv, True: N.lib().spmv_b200_hll_spmv_slice,
-              False: N.lib().spmv_b200_hll_spmv_stream}[slice_kernel]
+              False: N.lib().spmv_b200_hll_spmv_stream, "rows": N.lib().spmv_b200_hll_spmv_rows}[slice_kernel]
         N.check(fn(self._h, _ptr(x), _ptr(y), _stream(stream)))
         return y
 

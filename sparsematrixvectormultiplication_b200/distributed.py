@@ -127,6 +127,8 @@ class PowerIteration:
         else:
             need = (self.row_begin, self.row_begin)
         self.plan = ExchangePlan.build(self.parts, gather_needs(need, self.world, cu, group), self.rank)
+        # algorithmic bytes of the LOCAL product: the rank streams its rows and reads only the referenced part of x
+        self.algorithmic_bytes_local = 12 * info.nnz + 4 * (info.M + 1) + 8 * info.M + 8 * (need[1] - need[0])
         self.x = torch.ones(self.N, dtype=torch.float64, device=cu)
         self.y = torch.zeros(max(self.rows, 1), dtype=torch.float64, device=cu)
         self.ws = torch.empty(device.vec_ws_doubles(), dtype=torch.float64, device=cu)

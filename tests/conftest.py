@@ -37,8 +37,11 @@ def pytest_collection_modifyitems(config, items):
 def _built():
     """Make sure the native library and the oracle exist (cheap no-ops when up to date)."""
     import sparsematrixvectormultiplication_b200 as pkg
-    if not pkg.LIB_PATH.exists():
-        pkg.build()
+    try:
+        pkg.build()   # make: a no-op when the library is newer than every source, a rebuild when it is stale
+    except Exception:
+        if not pkg.LIB_PATH.exists():   # a box without nvcc uses the library that travelled with the snapshot
+            raise
     from oracle import oracle as O
     if not (O.HERE / "liboracle.so").exists():
         O.build()

@@ -43,7 +43,7 @@ def main():
         if name != "rmat":
             H = A.to_hll()
             hb = H.info().algorithmic_bytes / 1e6
-            for label, flag in (("hll-auto", None), ("hll-stream", False), ("hll-slice", True)):
+            for label, flag in (("hll-auto", None), ("hll-stream", False), ("hll-slice", True), ("hll-rows", "rows")):
                 t = min(timeit(lambda: H.spmv(x, y, slice_kernel=flag), 20, 3) for _ in range(3))
                 out.append(f"{label} {t*1e3:.1f} us {hb/t:.0f} GB/s")
             H.close()
