@@ -535,14 +535,20 @@ static int build_plan(spmv_b200_csr *A, cudaStream_t stream) {
     // (a few products on scratch vectors) -- the best batch depends on how rows, lines and L1 capacity interact
     const int forced_batch = env_int("SPMV_B200_ROW_BATCH", 0);
     A->row_batch = std::max(2, std::min(6, (int)((A->nnz + M - 1) / std::max(M, 1))));
+    A->short_rows_stream = false;
+    SPMV_TRY(stream_prepare_csr(A));
     if (forced_batch >= 1 && forced_batch <= 8) {
         A->row_batch = forced_batch;
     } else if (A->max_row <= kRowKernelMaxLen && A->nnz >= kAutotuneMinNnz && env_int("SPMV_B200_AUTOTUNE", 1)) {
-        A->row_batch = tune_batch(M, A->N, A->row_batch, stream, [&](int batch, double *x, double *y) {
+        // candidates: row kernel with batch 2..7 and (0) the TMA stream kernel; all give the same bits on such rows
+        const int best = tune_batch(M, A->N, A->row_batch, stream, [&](int batch, double *x, double *y) {
+            if (batch == 0) return stream_launch_csr(A, x, y, 0, nullptr, stream);
             return launch_rows(0, M, A->row_ptr, A->col_idx, A->values, x, y, batch, 0, stream);
-        });
+        }, 0);
+        if (best == 0) A->short_rows_stream = true;
+        else A->row_batch = best;
     }
-    return stream_prepare_csr(A);
+    return SPMV_B200_OK;
 }
 
 // lanes per row: about a quarter of the mean row length, so that every lane owns one full batch of kVecBatch gathers
@@ -725,7 +731,7 @@ CsrPath csr_resolve(const spmv_b200_csr *A, int algo) {
         case SPMV_B200_ALGO_ROW: return kPathRow;
         default:
             // every row short: one thread per row (serial order, so forced_tpr == 1 is honoured as well)
-            if (A->max_row <= kRowKernelMaxLen) return kPathRow;
+            if (A->max_row <= kRowKernelMaxLen) return A->short_rows_stream ? kPathStream : kPathRow;
             if (A->forced_tpr == 1 || A->nnz <= (long long)kAutoStreamMaxAvg * A->M) return kPathStream;
             return A->num_long == 0 ? kPathVector : kPathBinned;
     }

@@ -65,6 +65,7 @@ struct spmv_b200_csr {
     spmv::BinPlan bins;
     int max_row = 0;     // longest row (plan time)
     int row_batch = 4;   // csr_row_kernel: column/value/gather batch per thread (tuned at plan time on large matrices)
+    bool short_rows_stream = false;  // plan-time timing found the stream kernel faster than every row-kernel batch
     // stream kernel launch shape
     int stages = spmv::kDefaultStages;
     int consumers = 12;
@@ -91,6 +92,7 @@ struct spmv_b200_hll {
     spmv::HllTile *tiles = nullptr;
     int stream_grid = 0;
     int row_batch = 4;   // hll_row_kernel batch (tuned at plan time on large matrices)
+    bool narrow_stream = false;  // plan-time timing found the stream kernel faster than every row-kernel batch
     double *stage_x = nullptr;
     double *stage_y = nullptr;
     spmv::HostPipe *pipe = nullptr;
@@ -107,7 +109,8 @@ int stream_launch_hll(const spmv_b200_hll *H, const double *x, double *y, cudaSt
                       int tile_count = -1);
 // csr.cu / hll.cu: which kernel the automatic choice resolves to, and launches restricted to a window
 enum CsrPath { kPathStream, kPathTile, kPathVector, kPathBinned, kPathRow };
-constexpr int kRowKernelMaxLen = 16;  // AUTO: one thread per row when no row is longer than this
+constexpr int kRowKernelMaxLen = 12;  // AUTO: one thread per row when no row is longer than this (= kSerialRowMax: the
+                                      // stream kernel then gives the same bits, so plan-time timing may pick either)
 CsrPath csr_resolve(const spmv_b200_csr *A, int algo);
 int csr_launch_window(const spmv_b200_csr *A, CsrPath path, int unit_begin, int unit_end, const double *x, double *y,
                       int accumulate, cudaStream_t stream);  // units: tiles (stream/tile paths) or rows (vector path)
@@ -116,9 +119,10 @@ HllPath hll_resolve(const spmv_b200_hll *H);
 int hll_launch_window(const spmv_b200_hll *H, HllPath path, int unit_begin, int unit_end, const double *x, double *y,
                       cudaStream_t stream);  // units: tiles (stream kernel) or hacks (slice and row kernels)
 int env_int(const char *name, int fallback);
-// Times launch(batch) for every candidate batch on scratch vectors and returns the fastest (plan time, large matrices).
+// Times launch(candidate) for candidate = first .. 7 on scratch vectors and returns the fastest (plan time, large
+// matrices).  Candidates 2..7 are batches of the row kernels; 0 (first = 0 only, 1 is skipped) stands for the stream kernel.
 template <class Launch>
-int tune_batch(long long M, long long N, int fallback, cudaStream_t stream, Launch launch) {
+int tune_batch(long long M, long long N, int fallback, cudaStream_t stream, Launch launch, int first = 2) {
     double *x = nullptr, *y = nullptr;
     cudaEvent_t a = nullptr, b = nullptr;
     int best = fallback;
@@ -126,15 +130,16 @@ int tune_batch(long long M, long long N, int fallback, cudaStream_t stream, Laun
         cudaMalloc(&y, (size_t)(M > 0 ? M : 1) * sizeof(double)) == cudaSuccess &&
         cudaMemsetAsync(x, 0, (size_t)(N > 0 ? N : 1) * sizeof(double), stream) == cudaSuccess &&
         cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) {
-        float best_ms = 0.0f;
-        for (int batch = 2; batch <= 7; ++batch) {
+        float best_ms = -1.0f;
+        for (int batch = first; batch <= 7; ++batch) {
+            if (batch == 1) continue;
             bool ok = launch(batch, x, y) == SPMV_B200_OK;  // warm-up
             ok = ok && cudaEventRecord(a, stream) == cudaSuccess;
-            for (int rep = 0; rep < 3 && ok; ++rep) ok = launch(batch, x, y) == SPMV_B200_OK;
+            for (int rep = 0; rep < 5 && ok; ++rep) ok = launch(batch, x, y) == SPMV_B200_OK;
             ok = ok && cudaEventRecord(b, stream) == cudaSuccess && cudaEventSynchronize(b) == cudaSuccess;
             float ms = 0.0f;
             if (!ok || cudaEventElapsedTime(&ms, a, b) != cudaSuccess) break;
-            if (batch == 2 || ms < best_ms) {
+            if (best_ms < 0.0f || ms < best_ms) {
                 best_ms = ms;
                 best = batch;
             }

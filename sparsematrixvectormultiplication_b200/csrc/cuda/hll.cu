@@ -205,7 +205,7 @@ namespace spmv {
 // no hack wider than 16 columns (stencils): lane-per-row kernel, coalesced by the column-major layout; narrow on
 // average: TMA stream kernel; wide hacks are gather bound and need the occupancy of the slice kernel
 HllPath hll_resolve(const spmv_b200_hll *H) {
-    if (H->max_width <= kRowKernelMaxLen) return kHllRows;
+    if (H->max_width <= kRowKernelMaxLen) return H->narrow_stream ? kHllStream : kHllRows;
     return H->slots <= 12LL * 32 * H->num_hacks ? kHllStream : kHllSlice;
 }
 
@@ -219,18 +219,22 @@ int hll_launch_window(const spmv_b200_hll *H, HllPath path, int unit_begin, int 
 // batch of the lane-per-row kernel: the hack width when it is uniform and small; timed at plan time on large images
 static void hll_pick_row_batch(spmv_b200_hll *H, cudaStream_t stream) {
     const int forced = env_int("SPMV_B200_HLL_ROW_BATCH", 0);
+    H->narrow_stream = false;
     const long long mean = H->num_hacks > 0 ? (H->slots / 32 + H->num_hacks - 1) / H->num_hacks : 4;
     H->row_batch = (int)std::max<long long>(2, std::min<long long>(7, mean));
     if (forced >= 1 && forced <= 8) {
         H->row_batch = forced;
     } else if (H->max_width <= kRowKernelMaxLen && H->slots >= (1 << 22) && env_int("SPMV_B200_AUTOTUNE", 1)) {
-        H->row_batch = tune_batch(H->M, H->N, H->row_batch, stream, [&](int batch, double *x, double *y) {
+        const int best = tune_batch(H->M, H->N, H->row_batch, stream, [&](int batch, double *x, double *y) {
+            if (batch == 0) return stream_launch_hll(H, x, y, stream);
             const int keep = H->row_batch;
             H->row_batch = batch;
             const int rc = hll_launch_rows(H, 0, H->num_hacks, x, y, stream);
             H->row_batch = keep;
             return rc;
-        });
+        }, 0);
+        if (best == 0) H->narrow_stream = true;
+        else H->row_batch = best;
     }
 }
 }  // namespace spmv

@@ -38,10 +38,14 @@ def _built():
     """Make sure the native library and the oracle exist (cheap no-ops when up to date)."""
     import sparsematrixvectormultiplication_b200 as pkg
     try:
-        pkg.build()   # make: a no-op when the library is newer than every source, a rebuild when it is stale
+        import torch
+        on_gpu_box = torch.cuda.is_available()
     except Exception:
-        if not pkg.LIB_PATH.exists():   # a box without nvcc uses the library that travelled with the snapshot
-            raise
+        on_gpu_box = False
+    # development container (no GPU): run make, a no-op when the library is newer than every source and a rebuild when
+    # it is stale.  GPU box: the library that travelled with the snapshot is the one under test.
+    if not on_gpu_box or not pkg.LIB_PATH.exists():
+        pkg.build()
     from oracle import oracle as O
     if not (O.HERE / "liboracle.so").exists():
         O.build()
