@@ -98,6 +98,64 @@ __device__ __forceinline__ double ldg_x(const double *x, int col) {
 #endif
 }
 
+// ---- mailbox exchange of |w|^2 between ranks (spmv_b200_mail_t, include/spmv_b200.h): system-scope accesses to
+// peer memory over NVLink.  Used by the fused stream kernel (stream.cu) and the fused row kernel (csr.cu). -------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+constexpr long long kMailSpinCycles = 4000000000LL;  // ~2 s at 1.9 GHz: a peer that has not answered by then is gone
+
+// Launch k > 0, one whole warp: wait until every rank's slot of parity (k-1)&1 in MY mailbox carries tag k (launch k-1
+// of that rank has finished: its |w|^2 is here and its boundary rows are in my x), then add the sums in rank order.
+// Returns the total in every lane.
+__device__ __forceinline__ double mail_wait_total(const spmv_b200_mail_t &m, int lane) {
+    const unsigned long long want = m.iteration;
+    const int parity = (int)((m.iteration - 1) & 1);
+    double mine = 0.0;
+    if (lane < m.world) {
+        const unsigned long long *slot = m.box[m.rank] + 2 * (parity * m.world + lane);
+        const long long t0 = clock64();
+        while (ld_acquire_sys(slot + 1) != want) {
+            if (clock64() - t0 > kMailSpinCycles) {
+                *m.status = 1;
+                break;
+            }
+            __nanosleep(40);
+        }
+        mine = __longlong_as_double((long long)ld_acquire_sys(slot));
+    }
+    double total = 0.0;
+    for (int r = 0; r < m.world; ++r) total += __shfl_sync(0xffffffffu, mine, r);
+    return total;
+}
+
+// One whole warp of the LAST CTA of launch k (after a device-scope fence): add the per-CTA partials in a fixed order
+// and write {sum, tag k+1} into slot [k&1][rank] of every rank's mailbox; reset the CTA counter for the next launch.
+__device__ __forceinline__ void mail_publish(const spmv_b200_mail_t &m, const double *partials, int count, int lane) {
+    __threadfence();
+    double part = 0.0;
+    for (int i = lane; i < count; i += 32) part += __ldcg(partials + i);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if (lane < m.world) {
+        unsigned long long *slot = m.box[lane] + 2 * ((int)(m.iteration & 1) * m.world + m.rank);
+        st_relaxed_sys(slot, (unsigned long long)__double_as_longlong(part));
+        st_release_sys(slot + 1, m.iteration + 1);
+    }
+    if (lane == 0) *m.counter = 0;
+}
+
 // ---- per-row sums of products parked in shared memory, one warp per chunk of 32 rows ---------------
 constexpr int kSerialRowMax = 12;  // rows up to this length are always summed by ONE lane, left to right: the stream and
                                    // tile kernels reproduce the reference's serial loop bit for bit on such rows, whatever

@@ -264,6 +264,83 @@ csr_row_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, cons
     y[row] = acc;
 }
 
+// The thread-per-row kernel with the fused tail of the iterated product (Epilogue, handles.cuh): every row is divided by
+// |w_prev|, squared into a per-thread sum, stored, and mirrored into the peers that reference it; per-CTA partial sums
+// in a fixed order; with a mailbox the launch first waits for the peers' previous launch and its last CTA publishes
+// |w|^2 (common.cuh).  A fixed grid walks the rows in 256-row chunks (grid-stride), so the number of partials -- and the
+// order of the sum of squares -- does not depend on the matrix size.
+template <int BATCH>
+__global__ void __launch_bounds__(256, 8)
+csr_row_fused_kernel(int M, const int *__restrict__ row_ptr, const int *__restrict__ col_idx, const double *__restrict__ values,
+                     const double *__restrict__ x, double *__restrict__ y, const Epilogue ep) {
+    __shared__ double warp_sq[8];
+    __shared__ double mail_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool scaled = false;
+    double prev_norm = 1.0;
+    if (ep.mail.world > 0) {
+        if (ep.mail.iteration > 0) {
+            if (warp == 0) {
+                const double total = mail_wait_total(ep.mail, lane);
+                if (lane == 0) mail_total = total;
+            }
+            __syncthreads();
+            scaled = true;
+            prev_norm = sqrt(mail_total);
+        }
+    } else if (ep.prev_sumsq != nullptr) {
+        scaled = true;
+        prev_norm = sqrt(*ep.prev_sumsq);
+    }
+    const double inv_norm = 1.0 / prev_norm;  // one division per thread, one multiplication per row (1 ulp from a division)
+    double sq = 0.0;
+    for (long long row = (long long)blockIdx.x * 256 + threadIdx.x; row < M; row += (long long)gridDim.x * 256) {
+        const int lo = __ldg(row_ptr + row), hi = __ldg(row_ptr + row + 1);
+        double acc = 0.0;
+        for (int k = lo; k < hi; k += BATCH) {
+            int c[BATCH];
+            double v[BATCH], xv[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) c[u] = k + u < hi ? __ldg(col_idx + k + u) : -1;
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) v[u] = k + u < hi ? __ldg(values + k + u) : 0.0;
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u)
+                if (c[u] >= 0) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+        }
+        if (scaled) acc *= inv_norm;
+        sq = fma(acc, acc, sq);
+        for (int p = 0; p < ep.peers.count; ++p)
+            if (row >= ep.peers.lo[p] && row < ep.peers.hi[p]) ep.peers.dst[p][row] = acc;
+        y[row] = acc;
+    }
+    if (ep.partials == nullptr) return;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    if (lane == 0) warp_sq[warp] = sq;
+    if (ep.mail.world > 0) __threadfence_system();  // this thread's rows (local and peer stores) before the flag below
+    __syncthreads();
+    if (warp == 0) {
+        unsigned int arrived = 0;
+        if (lane == 0) {
+            double total = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) total += warp_sq[w];
+            ep.partials[blockIdx.x] = total;
+            if (ep.mail.world > 0) {
+                __threadfence();
+                arrived = atomicAdd(ep.mail.counter, 1u);
+            }
+        }
+        if (ep.mail.world > 0) {
+            arrived = __shfl_sync(0xffffffffu, arrived, 0);
+            if (arrived == gridDim.x - 1) mail_publish(ep.mail, ep.partials, (int)gridDim.x, lane);
+        }
+    }
+}
+
 // ---- row-binned vector kernel (skewed matrices) ------------------------------------------------------
 // Rows are binned by length at plan time; bin b < 6 gives every row 2^b lanes (about a quarter of its length, so
 // each lane owns one batch of kVecBatch gathers), the rows of one bin are processed in ascending row order, and all
@@ -439,6 +516,8 @@ static size_t tile_smem_bytes(const spmv_b200_csr *A) {
 
 static int launch_rows(int row_begin, int row_end, const int *row_ptr, const int *col_idx, const double *values,
                        const double *x, double *y, int batch, int accumulate, cudaStream_t stream);
+static int launch_fused(const spmv_b200_csr *A, const double *x, double *y, const Epilogue &ep, cudaStream_t stream, int batch);
+static int fused_row_grid(const spmv_b200_csr *A);
 
 static int build_plan(spmv_b200_csr *A, cudaStream_t stream) {
     free_plan(A);
@@ -536,6 +615,7 @@ static int build_plan(spmv_b200_csr *A, cudaStream_t stream) {
     const int forced_batch = env_int("SPMV_B200_ROW_BATCH", 0);
     A->row_batch = std::max(2, std::min(6, (int)((A->nnz + M - 1) / std::max(M, 1))));
     A->short_rows_stream = false;
+    A->fused_batch = 0;
     SPMV_TRY(stream_prepare_csr(A));
     if (forced_batch >= 1 && forced_batch <= 8) {
         A->row_batch = forced_batch;
@@ -547,6 +627,23 @@ static int build_plan(spmv_b200_csr *A, cudaStream_t stream) {
         }, 0);
         if (best == 0) A->short_rows_stream = true;
         else A->row_batch = best;
+        // the fused iterated product (scale + |w|^2 partials in the tail): fused stream kernel (0) or fused row kernel
+        if (A->num_long == 0) {
+            double *partials = nullptr;
+            const int count = std::max(std::max(A->stream_grid, fused_row_grid(A)), 1);
+            if (cudaMalloc(&partials, (size_t)count * sizeof(double)) == cudaSuccess) {
+                Epilogue ep;
+                ep.prev_sumsq = nullptr;
+                ep.partials = partials;
+                ep.peers.count = 0;
+                ep.mail.world = 0;
+                A->fused_batch = tune_batch(M, A->N, 0, stream, [&](int batch, double *x, double *y) {
+                    return launch_fused(A, x, y, ep, stream, batch);
+                }, 0);
+            }
+            cudaGetLastError();
+            cudaFree(partials);
+        }
     }
     return SPMV_B200_OK;
 }
@@ -748,6 +845,29 @@ int csr_launch_window(const spmv_b200_csr *A, CsrPath path, int unit_begin, int 
     return launch_tiles(A, x, y, accumulate, path == kPathStream, stream, unit_begin, unit_end);
 }
 
+// grid of the fused row kernel: 8 CTAs of 256 threads per SM, whatever the matrix size
+static int fused_row_grid(const spmv_b200_csr *A) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int)std::max<long long>(1, std::min<long long>(8LL * sms, ((long long)A->M + 255) / 256));
+}
+
+static int launch_fused(const spmv_b200_csr *A, const double *x, double *y, const Epilogue &ep, cudaStream_t stream,
+                        int batch) {
+    if (batch < 0) batch = env_int("SPMV_B200_FUSED_BATCH", A->fused_batch);
+    if (batch == 0) return stream_launch_csr(A, x, y, 0, &ep, stream);
+    const int g = fused_row_grid(A);
+#define FROW_CASE(B) case B: csr_row_fused_kernel<B><<<g, 256, 0, stream>>>(A->M, A->row_ptr, A->col_idx, A->values, x, y, ep); break;
+    switch (batch) {
+        FROW_CASE(2) FROW_CASE(3) FROW_CASE(5) FROW_CASE(6) FROW_CASE(7)
+        default: csr_row_fused_kernel<4><<<g, 256, 0, stream>>>(A->M, A->row_ptr, A->col_idx, A->values, x, y, ep); break;
+    }
+#undef FROW_CASE
+    SPMV_TRY_CUDA(cudaGetLastError());
+    return SPMV_B200_OK;
+}
+
 static int check_device() {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -904,7 +1024,10 @@ int spmv_b200_csr_spmv(const spmv_b200_csr *A, const double *d_x, double *d_y, i
     return csr_launch_window(A, path, 0, by_rows ? A->M : A->num_tiles, d_x, d_y, accumulate, as_stream(stream));
 }
 
-int spmv_b200_csr_partials_count(const spmv_b200_csr *A) { return A ? std::max(A->stream_grid, 1) : 0; }
+int spmv_b200_csr_partials_count(const spmv_b200_csr *A) {
+    if (!A) return 0;
+    return std::max(std::max(A->stream_grid, fused_row_grid(A)), 1);
+}
 
 int spmv_b200_csr_spmv_fused(const spmv_b200_csr *A, const double *d_x, double *d_y, const double *d_prev_sumsq,
                              double *d_partials, const spmv_b200_peers_t *peers, void *stream) {
@@ -920,7 +1043,7 @@ int spmv_b200_csr_spmv_fused(const spmv_b200_csr *A, const double *d_x, double *
     ep.mail.world = 0;
     if (peers) ep.peers = *peers;
     if (A->M == 0) return SPMV_B200_OK;
-    return stream_launch_csr(A, d_x, d_y, 0, &ep, as_stream(stream));
+    return launch_fused(A, d_x, d_y, ep, as_stream(stream), -1);
 }
 
 int spmv_b200_csr_spmv_fused_mail(const spmv_b200_csr *A, const double *d_x, double *d_y, double *d_partials,
@@ -942,7 +1065,7 @@ int spmv_b200_csr_spmv_fused_mail(const spmv_b200_csr *A, const double *d_x, dou
     ep.peers.count = 0;
     if (peers) ep.peers = *peers;
     ep.mail = *mail;
-    return stream_launch_csr(A, d_x, d_y, 0, &ep, as_stream(stream));
+    return launch_fused(A, d_x, d_y, ep, as_stream(stream), -1);
 }
 
 int spmv_b200_csr_spmv_rows(const spmv_b200_csr *A, int row_begin, int row_end, const double *d_x, double *d_y,

@@ -66,6 +66,7 @@ struct spmv_b200_csr {
     int max_row = 0;     // longest row (plan time)
     int row_batch = 4;   // csr_row_kernel: column/value/gather batch per thread (tuned at plan time on large matrices)
     bool short_rows_stream = false;  // plan-time timing found the stream kernel faster than every row-kernel batch
+    int fused_batch = 0;             // fused iterated product: 0 = fused stream kernel, else batch of the fused row kernel
     // stream kernel launch shape
     int stages = spmv::kDefaultStages;
     int consumers = 12;

@@ -158,23 +158,6 @@ __device__ __forceinline__ double group_row_sum(const double *prod, int lo, int 
     return acc;
 }
 
-// ---- system-scope mailbox accesses (peer memory over NVLink) -------------------------------------------------
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-constexpr long long kMailSpinCycles = 4000000000LL;  // ~2 s at 1.9 GHz: a peer that has not answered by then is gone
-
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 
@@ -240,23 +223,7 @@ csr_stream_kernel(const int2 *__restrict__ tiles, int num_tiles, const int *__re
             if (ep.mail.iteration > 0) {
                 // wait for every rank's previous launch: its |w|^2 is in my mailbox and its boundary rows are in my x
                 if (warp == 0) {
-                    const unsigned long long want = ep.mail.iteration;  // tag of launch k-1 is k
-                    const int parity = (int)((ep.mail.iteration - 1) & 1);
-                    double mine = 0.0;
-                    if (lane < ep.mail.world) {
-                        const unsigned long long *slot = ep.mail.box[ep.mail.rank] + 2 * (parity * ep.mail.world + lane);
-                        const long long t0 = clock64();
-                        while (ld_acquire_sys(slot + 1) != want) {
-                            if (clock64() - t0 > kMailSpinCycles) {
-                                *ep.mail.status = 1;
-                                break;
-                            }
-                            __nanosleep(40);
-                        }
-                        mine = __longlong_as_double((long long)ld_acquire_sys(slot));
-                    }
-                    double total = 0.0;
-                    for (int r = 0; r < ep.mail.world; ++r) total += __shfl_sync(0xffffffffu, mine, r);  // rank order
+                    const double total = mail_wait_total(ep.mail, lane);
                     if (lane == 0) mail_total = total;
                 }
                 asm volatile("bar.sync 2, %0;" ::"n"(kConsumerWarps * 32) : "memory");
@@ -268,11 +235,12 @@ csr_stream_kernel(const int2 *__restrict__ tiles, int num_tiles, const int *__re
             prev_norm = scaled ? sqrt(*ep.prev_sumsq) : 1.0;
         }
     }
+    const double inv_norm = 1.0 / prev_norm;  // one division per thread, one multiplication per row (1 ulp from a division)
     double sq = 0.0;  // sum of the squares of the rows this lane produced
     // y[row] = v; the fused instantiation scales it first, accumulates v^2 and mirrors boundary rows into the peers
     auto emit = [&](int row, double v) {
         if constexpr (kFused) {
-            if (scaled) v = v / prev_norm;
+            if (scaled) v *= inv_norm;
             sq = fma(v, v, sq);
             for (int p = 0; p < ep.peers.count; ++p)
                 if (row >= ep.peers.lo[p] && row < ep.peers.hi[p]) ep.peers.dst[p][row] = v;
@@ -391,20 +359,7 @@ csr_stream_kernel(const int2 *__restrict__ tiles, int num_tiles, const int *__re
                     arrived = atomicAdd(ep.mail.counter, 1u);
                 }
                 arrived = __shfl_sync(0xffffffffu, arrived, 0);
-                if (arrived == gridDim.x - 1) {  // the last CTA of this launch publishes the rank's |w|^2
-                    __threadfence();
-                    double part = 0.0;
-                    for (int i = lane; i < (int)gridDim.x; i += 32) part += __ldcg(ep.partials + i);
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-                    if (lane < ep.mail.world) {
-                        unsigned long long *slot =
-                            ep.mail.box[lane] + 2 * ((int)(ep.mail.iteration & 1) * ep.mail.world + ep.mail.rank);
-                        st_relaxed_sys(slot, (unsigned long long)__double_as_longlong(part));
-                        st_release_sys(slot + 1, ep.mail.iteration + 1);
-                    }
-                    if (lane == 0) *ep.mail.counter = 0;
-                }
+                if (arrived == gridDim.x - 1) mail_publish(ep.mail, ep.partials, (int)gridDim.x, lane);  // last CTA of the launch
             }
         }
     }
