@@ -422,6 +422,24 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler):
     except Exception as e:  # pragma: no cover
         out["lap2d_4096_variants"] = {"error": repr(e)}
 
+    # fp32 storage / fp64 arithmetic on the headline matrix: reported, never the headline
+    try:
+        A2d.enable_f32()
+        x32, y32 = x2d.to(torch.float32), torch.empty(y2d.numel(), dtype=torch.float32, device="cuda")
+        ia = A2d.info()
+        run("lap2d_4096_csr_f32", lambda: A2d.spmv_f32(x32, y32), ia.nnz, A2d.algorithmic_bytes_f32(),
+            {"dtype": "f32 storage (values, x, y), f64 arithmetic", "bytes_formula": "8 nnz + 4 (M+1) + 4 M + 4 N"})
+        A2d.spmv(x2d, y2d)
+        out["lap2d_4096_csr_f32"]["max_rel_diff_vs_f64"] = float(((y32.double() - y2d).abs() / (8.0 * 1.75)).max().item())
+        H32 = A2d.to_hll().enable_f32()
+        run("lap2d_4096_hll_f32", lambda: H32.spmv_f32(x32, y32), ia.nnz, H32.algorithmic_bytes_f32(),
+            {"dtype": "f32 storage (values, x, y), f64 arithmetic"})
+        H32.close()
+        del x32, y32
+    except Exception as e:  # pragma: no cover
+        out["lap2d_4096_csr_f32"] = {"error": repr(e)}
+        log(f"[bench] fp32 leg failed: {e!r}")
+
     # the reference's own GPU kernels, recompiled unmodified for sm_100a, on the headline matrix ("existing kernel" bar)
     try:
         from oracle import oracle as O

@@ -99,6 +99,15 @@ int spmv_b200_csr_upload(int M, int N, long long nnz, const int *row_ptr, const 
 int spmv_b200_csr_wrap_device(int M, int N, long long nnz, const int *d_row_ptr,
                               const int *d_col_idx, const double *d_values, void *stream,
                               spmv_b200_csr **out);
+/* COO -> resident CSR built on the device (one stable radix sort of (row, column) keys).  I / J / val as PreMatrix
+ * holds them (0-based; reference libs/matrix_parser.h:6-14).  Identical to convert_in_csr + upload for matrices
+ * without repeated coordinates; repeated coordinates keep their input order (the reference's order inside such a
+ * row is whatever its quicksort leaves, src/utility.c:38-91).  Replaces reference src/csr_matrix.c:63-126 for data
+ * that is generated or already resident on the GPU. */
+int spmv_b200_csr_from_coo(int M, int N, long long nz, const int *I, const int *J, const double *val,
+                           spmv_b200_csr **out);
+int spmv_b200_csr_from_coo_device(int M, int N, long long nz, const int *d_I, const int *d_J, const double *d_val,
+                                  void *stream, spmv_b200_csr **out);
 /* tuning knobs for the plan (0 keeps the default); rebuilds the plan */
 int spmv_b200_csr_replan(spmv_b200_csr *A, int tile_items, int long_threshold, int threads_per_row,
                          void *stream);
@@ -191,6 +200,17 @@ int spmv_b200_hll_spmv_host(spmv_b200_hll *H, const double *x, double *y);
 int spmv_b200_hll_spmv_hacks(const spmv_b200_hll *H, int hack_begin, int hack_end, const double *d_x,
                              double *d_y, void *stream);
 void spmv_b200_hll_free(spmv_b200_hll *H);
+
+/* ---- fp32 storage with fp64 arithmetic (BASELINE.json: y within 1e-5 relative of the serial fp64 product).  The value
+ * stream, x and y are float (algorithmic bytes 8 nnz + 4 (M+1) + 4 M + 4 N instead of 12 nnz + ...); every product is
+ * formed and summed in double and rounded once on the store.  enable_f32 adds a float copy of the values to the
+ * resident matrix (the indices, plans and the fp64 values stay).  CSR algo: AUTO, ROW, VECTOR or BINNED. ---- */
+int spmv_b200_csr_enable_f32(spmv_b200_csr *A, void *stream);
+int spmv_b200_csr_spmv_f32(const spmv_b200_csr *A, const float *d_x, float *d_y, int accumulate, int algo, void *stream);
+int spmv_b200_csr_spmv_host_f32(spmv_b200_csr *A, const float *x, float *y);
+int spmv_b200_hll_enable_f32(spmv_b200_hll *H, void *stream);
+int spmv_b200_hll_spmv_f32(const spmv_b200_hll *H, const float *d_x, float *d_y, void *stream);
+int spmv_b200_hll_spmv_host_f32(spmv_b200_hll *H, const float *x, float *y);
 
 /* ---- timing harness on a resident matrix: the reference driver's protocol (main_cuda.cu:159-200: cudaEvents around
  * every product, the first `warmup` iterations not counted, mean over the rest) behind one call, so that a C

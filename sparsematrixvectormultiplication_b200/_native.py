@@ -102,6 +102,8 @@ SIGNATURES = {
     "spmv_b200_csr_download": (_I, [_V, _V, _V, _V]),
     "spmv_b200_csr_spmv": (_I, [_V, _V, _V, _I, _I, _V]),
     "spmv_b200_csr_spmv_host": (_I, [_V, _V, _V, _I, _I]),
+    "spmv_b200_csr_from_coo": (_I, [_I, _I, _LL, _V, _V, _V, C.POINTER(_V)]),
+    "spmv_b200_csr_from_coo_device": (_I, [_I, _I, _LL, _V, _V, _V, _V, C.POINTER(_V)]),
     "spmv_b200_csr_spmv_rows": (_I, [_V, _I, _I, _V, _V, _V]),
     "spmv_b200_csr_partials_count": (_I, [_V]),
     "spmv_b200_csr_spmv_fused": (_I, [_V, _V, _V, _V, _V, C.POINTER(Peers), _V]),
@@ -122,6 +124,12 @@ SIGNATURES = {
     "spmv_b200_hll_spmv_stream": (_I, [_V, _V, _V, _V]),
     "spmv_b200_hll_spmv_host": (_I, [_V, _V, _V]),
     "spmv_b200_hll_spmv_rows": (_I, [_V, _V, _V, _V]),
+    "spmv_b200_csr_enable_f32": (_I, [_V, _V]),
+    "spmv_b200_csr_spmv_f32": (_I, [_V, _V, _V, _I, _I, _V]),
+    "spmv_b200_csr_spmv_host_f32": (_I, [_V, _V, _V]),
+    "spmv_b200_hll_enable_f32": (_I, [_V, _V]),
+    "spmv_b200_hll_spmv_f32": (_I, [_V, _V, _V, _V]),
+    "spmv_b200_hll_spmv_host_f32": (_I, [_V, _V, _V]),
     "spmv_b200_csr_time": (_I, [_V, _V, _V, _I, _I, _I, c_dbl_p, c_dbl_p]),
     "spmv_b200_hll_time": (_I, [_V, _V, _V, _I, _I, _I, c_dbl_p, c_dbl_p]),
     "spmv_b200_hll_spmv_hacks": (_I, [_V, _I, _I, _V, _V, _V]),

@@ -71,6 +71,13 @@ __device__ __forceinline__ double ldg_stream_f64(const double *p) {
     return r;
 }
 
+// float twins of the scalar loads (fp32 storage, fp64 arithmetic: SURVEY.md section 8(f).3); all return double
+__device__ __forceinline__ double ldg_stream_f64(const float *p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return (double)r;
+}
+
 __device__ __forceinline__ int ldg_stream_s32(const int *p) {
     int r;
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
@@ -97,6 +104,8 @@ __device__ __forceinline__ double ldg_x(const double *x, int col) {
     return __ldg(x + col);
 #endif
 }
+
+__device__ __forceinline__ double ldg_x(const float *x, int col) { return (double)__ldg(x + col); }
 
 // ---- mailbox exchange of |w|^2 between ranks (spmv_b200_mail_t, include/spmv_b200.h): system-scope accesses to
 // peer memory over NVLink.  Used by the fused stream kernel (stream.cu) and the fused row kernel (csr.cu). -------

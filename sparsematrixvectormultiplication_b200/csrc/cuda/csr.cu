@@ -46,9 +46,9 @@ __device__ __forceinline__ int load_col(const int *p) {
     if constexpr (VEC == 1) return __ldg(p);
     else return ldg_stream_s32(p);
 }
-template <int VEC>
-__device__ __forceinline__ double load_val(const double *p) {
-    if constexpr (VEC == 1) return __ldg(p);
+template <int VEC, typename V>
+__device__ __forceinline__ double load_val(const V *p) {
+    if constexpr (VEC == 1) return (double)__ldg(p);
     else return ldg_stream_f64(p);
 }
 
@@ -140,10 +140,11 @@ csr_tile_kernel(const int2 *__restrict__ tiles, const int *__restrict__ row_ptr,
 }
 
 // One CTA per fragment of a long row; partial[f] = sum over the fragment (fixed tree).
+template <typename V>
 __global__ void __launch_bounds__(kFragThreads)
 csr_long_fragment_kernel(const int *__restrict__ long_rows, const int *__restrict__ frag_first, int num_long,
                          const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
-                         const double *__restrict__ values, const double *__restrict__ x,
+                         const V *__restrict__ values, const V *__restrict__ x,
                          double *__restrict__ partial) {
     __shared__ double warp_sum[kFragThreads / 32];
     const int f = blockIdx.x;
@@ -183,22 +184,23 @@ csr_long_fragment_kernel(const int *__restrict__ long_rows, const int *__restric
     }
 }
 
+template <typename V>
 __global__ void csr_long_combine_kernel(const int *__restrict__ long_rows, const int *__restrict__ frag_first,
-                                        int num_long, const double *__restrict__ partial, double *__restrict__ y,
+                                        int num_long, const double *__restrict__ partial, V *__restrict__ y,
                                         int accumulate) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= num_long) return;
     const int row = long_rows[i];
-    double acc = accumulate ? y[row] : 0.0;
+    double acc = accumulate ? (double)y[row] : 0.0;
     for (int f = frag_first[i]; f < frag_first[i + 1]; ++f) acc += partial[f];  // fixed order
-    y[row] = acc;
+    y[row] = (V)acc;
 }
 
 // Plain vector-per-row kernel: VEC lanes per row, lane-strided loop, xor-shuffle reduction.
-template <int VEC>
+template <int VEC, typename V>
 __global__ void __launch_bounds__(256)
 csr_vector_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
-                  const double *__restrict__ values, const double *__restrict__ x, double *__restrict__ y,
+                  const V *__restrict__ values, const V *__restrict__ x, V *__restrict__ y,
                   int accumulate) {
     const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long row = row_begin + gt / VEC;
@@ -211,7 +213,7 @@ csr_vector_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, c
     }
     // kVecBatch column/value loads are issued before the first gather and the gathers before the first fma: the
     // column -> x dependency costs one round trip per batch instead of one per element
-    double acc = (VEC == 1 && accumulate && live) ? y[row] : 0.0;  // one lane per row: y += A x in the serial loop's order
+    double acc = (VEC == 1 && accumulate && live) ? (double)y[row] : 0.0;  // one lane per row: y += A x in the serial loop's order
     constexpr int kBatch = VEC == 1 ? kRowBatch : kVecBatch;
     for (int k = lo + lane; k < hi; k += kBatch * VEC) {
         int c[kBatch];
@@ -219,7 +221,7 @@ csr_vector_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, c
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) c[u] = k + u * VEC < hi ? load_col<VEC>(col_idx + k + u * VEC) : -1;
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u) v[u] = k + u * VEC < hi ? load_val<VEC>(values + k + u * VEC) : 0.0;
+        for (int u = 0; u < kBatch; ++u) v[u] = k + u * VEC < hi ? load_val<VEC, V>(values + k + u * VEC) : 0.0;
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) xv[u] = c[u] >= 0 ? ldg_x(x, c[u]) : 0.0;
 #pragma unroll
@@ -231,7 +233,7 @@ csr_vector_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, c
     }
 #pragma unroll
     for (int off = VEC >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (live && lane == 0) y[row] = (accumulate && VEC > 1) ? y[row] + acc : acc;
+    if (live && lane == 0) y[row] = (V)((accumulate && VEC > 1) ? (double)y[row] + acc : acc);
 }
 
 // One THREAD per row (stencil-like matrices, every row short).  Lane i walks row i: a warp's loads are strided by the
@@ -240,28 +242,28 @@ csr_vector_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, c
 // are issued before the first gather.  One lane, index order, mul and add rounded separately: every row is bit-identical
 // to the reference's serial loop (src/csr_matrix.c:134-138) -- and it is the reference's own thread-per-row idea
 // (cuda_src/csr_matrix_cuda.cu:122-146), which at 6.0 TB/s on lap2d 4096^2 is the kernel to beat on this chip.
-template <int BATCH>
+template <int BATCH, typename V>
 __global__ void __launch_bounds__(256, 8)
 csr_row_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
-               const double *__restrict__ values, const double *__restrict__ x, double *__restrict__ y, int accumulate) {
+               const V *__restrict__ values, const V *__restrict__ x, V *__restrict__ y, int accumulate) {
     const long long row = row_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= row_end) return;
     const int lo = __ldg(row_ptr + row), hi = __ldg(row_ptr + row + 1);
-    double acc = accumulate ? y[row] : 0.0;
+    double acc = accumulate ? (double)y[row] : 0.0;
     for (int k = lo; k < hi; k += BATCH) {
         int c[BATCH];
         double v[BATCH], xv[BATCH];
 #pragma unroll
         for (int u = 0; u < BATCH; ++u) c[u] = k + u < hi ? __ldg(col_idx + k + u) : -1;
 #pragma unroll
-        for (int u = 0; u < BATCH; ++u) v[u] = k + u < hi ? __ldg(values + k + u) : 0.0;
+        for (int u = 0; u < BATCH; ++u) v[u] = k + u < hi ? (double)__ldg(values + k + u) : 0.0;
 #pragma unroll
-        for (int u = 0; u < BATCH; ++u) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
+        for (int u = 0; u < BATCH; ++u) xv[u] = c[u] >= 0 ? (double)__ldg(x + c[u]) : 0.0;
 #pragma unroll
         for (int u = 0; u < BATCH; ++u)
             if (c[u] >= 0) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
     }
-    y[row] = acc;
+    y[row] = (V)acc;
 }
 
 // The thread-per-row kernel with the fused tail of the iterated product (Epilogue, handles.cuh): every row is divided by
@@ -363,11 +365,11 @@ struct BinLaunch {
     int block_start[kBins];
 };
 
-template <int VEC>
+template <int VEC, typename V>
 __device__ __forceinline__ void binned_rows(int local_block, int first, int count, const int *__restrict__ bin_rows,
                                             const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
-                                            const double *__restrict__ values, const double *__restrict__ x,
-                                            double *__restrict__ y, int accumulate) {
+                                            const V *__restrict__ values, const V *__restrict__ x,
+                                            V *__restrict__ y, int accumulate) {
     const int idx = (local_block * 256 + (int)threadIdx.x) / VEC;
     const int lane = threadIdx.x & (VEC - 1);
     const bool live = idx < count;
@@ -377,7 +379,7 @@ __device__ __forceinline__ void binned_rows(int local_block, int first, int coun
         lo = __ldg(row_ptr + row);
         hi = __ldg(row_ptr + row + 1);
     }
-    double acc = (VEC == 1 && accumulate && live) ? y[row] : 0.0;
+    double acc = (VEC == 1 && accumulate && live) ? (double)y[row] : 0.0;
     constexpr int kBatch = VEC == 1 ? kRowBatch : kVecBatch;
     for (int k = lo + lane; k < hi; k += kBatch * VEC) {
         int c[kBatch];
@@ -385,7 +387,7 @@ __device__ __forceinline__ void binned_rows(int local_block, int first, int coun
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) c[u] = k + u * VEC < hi ? load_col<VEC>(col_idx + k + u * VEC) : -1;
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u) v[u] = k + u * VEC < hi ? load_val<VEC>(values + k + u * VEC) : 0.0;
+        for (int u = 0; u < kBatch; ++u) v[u] = k + u * VEC < hi ? load_val<VEC, V>(values + k + u * VEC) : 0.0;
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) xv[u] = c[u] >= 0 ? ldg_x(x, c[u]) : 0.0;
 #pragma unroll
@@ -397,24 +399,25 @@ __device__ __forceinline__ void binned_rows(int local_block, int first, int coun
     }
 #pragma unroll
     for (int off = VEC >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (live && lane == 0) y[row] = (accumulate && VEC > 1) ? y[row] + acc : acc;
+    if (live && lane == 0) y[row] = (V)((accumulate && VEC > 1) ? (double)y[row] + acc : acc);
 }
 
+template <typename V>
 __global__ void __launch_bounds__(256)
 csr_binned_kernel(const BinLaunch plan, const int *__restrict__ bin_rows, const int *__restrict__ row_ptr,
-                  const int *__restrict__ col_idx, const double *__restrict__ values, const double *__restrict__ x,
-                  double *__restrict__ y, int accumulate) {
+                  const int *__restrict__ col_idx, const V *__restrict__ values, const V *__restrict__ x,
+                  V *__restrict__ y, int accumulate) {
     int bin = 0;
     while (bin < kBins - 2 && (int)blockIdx.x >= plan.block_start[bin + 1]) ++bin;  // CTA-uniform
     const int local_block = blockIdx.x - plan.block_start[bin];
     const int first = plan.offset[bin], count = plan.offset[bin + 1] - first;
     switch (bin) {
-        case 0: binned_rows<1>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
-        case 1: binned_rows<2>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
-        case 2: binned_rows<4>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
-        case 3: binned_rows<8>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
-        case 4: binned_rows<16>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
-        default: binned_rows<32>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
+        case 0: binned_rows<1, V>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
+        case 1: binned_rows<2, V>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
+        case 2: binned_rows<4, V>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
+        case 3: binned_rows<8, V>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
+        case 4: binned_rows<16, V>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
+        default: binned_rows<32, V>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
     }
 }
 
@@ -432,6 +435,11 @@ __global__ void bin_key_kernel(int M, const int *__restrict__ row_ptr, unsigned 
     }
     __syncthreads();
     if (threadIdx.x < kBins && local[threadIdx.x]) atomicAdd(&counts[threadIdx.x], local[threadIdx.x]);  // integer: order independent
+}
+
+__global__ void to_f32_kernel(const double *__restrict__ in, float *__restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];  // round to nearest even
 }
 
 // ---- plan construction kernels ------------------------------------------------------------------
@@ -514,8 +522,9 @@ static size_t tile_smem_bytes(const spmv_b200_csr *A) {
     return (size_t)(A->tile_items / 3 + A->long_threshold + kSmemSlack) * sizeof(double);
 }
 
-static int launch_rows(int row_begin, int row_end, const int *row_ptr, const int *col_idx, const double *values,
-                       const double *x, double *y, int batch, int accumulate, cudaStream_t stream);
+template <typename V>
+static int launch_rows(int row_begin, int row_end, const int *row_ptr, const int *col_idx, const V *values,
+                       const V *x, V *y, int batch, int accumulate, cudaStream_t stream);
 static int launch_fused(const spmv_b200_csr *A, const double *x, double *y, const Epilogue &ep, cudaStream_t stream, int batch);
 static int fused_row_grid(const spmv_b200_csr *A);
 
@@ -661,30 +670,32 @@ static int pick_vector_width(long long nnz, int M) {
     return 32;
 }
 
-static int launch_rows(int row_begin, int row_end, const int *row_ptr, const int *col_idx, const double *values,
-                       const double *x, double *y, int batch, int accumulate, cudaStream_t stream) {
+template <typename V>
+static int launch_rows(int row_begin, int row_end, const int *row_ptr, const int *col_idx, const V *values,
+                       const V *x, V *y, int batch, int accumulate, cudaStream_t stream) {
     const long long rows = (long long)row_end - row_begin;
     if (rows <= 0) return SPMV_B200_OK;
     const unsigned int g = blocks_for(rows, 256);
-#define ROW_CASE(B) case B: csr_row_kernel<B><<<g, 256, 0, stream>>>(row_begin, row_end, row_ptr, col_idx, values, x, y, accumulate); break;
+#define ROW_CASE(B) case B: csr_row_kernel<B, V><<<g, 256, 0, stream>>>(row_begin, row_end, row_ptr, col_idx, values, x, y, accumulate); break;
     switch (batch) {
         ROW_CASE(1) ROW_CASE(2) ROW_CASE(3) ROW_CASE(5) ROW_CASE(6) ROW_CASE(7) ROW_CASE(8)
-        default: csr_row_kernel<4><<<g, 256, 0, stream>>>(row_begin, row_end, row_ptr, col_idx, values, x, y, accumulate); break;
+        default: csr_row_kernel<4, V><<<g, 256, 0, stream>>>(row_begin, row_end, row_ptr, col_idx, values, x, y, accumulate); break;
     }
 #undef ROW_CASE
     SPMV_TRY_CUDA(cudaGetLastError());
     return SPMV_B200_OK;
 }
 
-static int launch_vector(int row_begin, int row_end, const int *row_ptr, const int *col_idx, const double *values,
-                         const double *x, double *y, int vec, int accumulate, cudaStream_t stream) {
+template <typename V>
+static int launch_vector(int row_begin, int row_end, const int *row_ptr, const int *col_idx, const V *values,
+                         const V *x, V *y, int vec, int accumulate, cudaStream_t stream) {
     const long long rows = (long long)row_end - row_begin;
     if (rows <= 0) return SPMV_B200_OK;
     if (vec == 1) return launch_rows(row_begin, row_end, row_ptr, col_idx, values, x, y, env_int("SPMV_B200_ROW_BATCH", 4), accumulate, stream);
     const unsigned int grid = blocks_for(rows * vec, 256);
-#define VEC_CASE(V)                                                                                              \
-    case V:                                                                                                      \
-        csr_vector_kernel<V><<<grid, 256, 0, stream>>>(row_begin, row_end, row_ptr, col_idx, values, x, y, accumulate); \
+#define VEC_CASE(W)                                                                                                 \
+    case W:                                                                                                         \
+        csr_vector_kernel<W, V><<<grid, 256, 0, stream>>>(row_begin, row_end, row_ptr, col_idx, values, x, y, accumulate); \
         break;
     switch (vec) {
         VEC_CASE(1) VEC_CASE(2) VEC_CASE(4) VEC_CASE(8) VEC_CASE(16) VEC_CASE(32)
@@ -711,11 +722,11 @@ static int launch_tiles(const spmv_b200_csr *A, const double *x, double *y, int 
         SPMV_TRY_CUDA(cudaGetLastError());
     }
     if (A->num_long > 0 && tile_end == A->num_tiles) {
-        csr_long_fragment_kernel<<<A->num_frag, kFragThreads, 0, stream>>>(A->long_rows, A->frag_first, A->num_long,
+        csr_long_fragment_kernel<double><<<A->num_frag, kFragThreads, 0, stream>>>(A->long_rows, A->frag_first, A->num_long,
                                                                           A->row_ptr, A->col_idx, A->values, x,
                                                                           A->frag_partial);
         SPMV_TRY_CUDA(cudaGetLastError());
-        csr_long_combine_kernel<<<blocks_for(A->num_long, 128), 128, 0, stream>>>(A->long_rows, A->frag_first,
+        csr_long_combine_kernel<double><<<blocks_for(A->num_long, 128), 128, 0, stream>>>(A->long_rows, A->frag_first,
                                                                                  A->num_long, A->frag_partial, y,
                                                                                  accumulate);
         SPMV_TRY_CUDA(cudaGetLastError());
@@ -790,7 +801,8 @@ static int build_bins(spmv_b200_csr *A, cudaStream_t stream) {
     return rc;
 }
 
-static int launch_binned(const spmv_b200_csr *A, const double *x, double *y, int accumulate, cudaStream_t stream) {
+template <typename V>
+static int launch_binned(const spmv_b200_csr *A, const V *values, const V *x, V *y, int accumulate, cudaStream_t stream) {
     if (A->M == 0) return SPMV_B200_OK;
     if (!A->bins.built) SPMV_TRY(build_bins(const_cast<spmv_b200_csr *>(A), stream));  // lazily, once per plan
     const BinPlan &B = A->bins;
@@ -798,16 +810,16 @@ static int launch_binned(const spmv_b200_csr *A, const double *x, double *y, int
     for (int b = 0; b <= kBins; ++b) L.offset[b] = B.offset[b];
     for (int b = 0; b < kBins; ++b) L.block_start[b] = B.block_start[b];
     if (B.block_start[kBins - 1] > 0) {
-        csr_binned_kernel<<<B.block_start[kBins - 1], 256, 0, stream>>>(L, B.rows, A->row_ptr, A->col_idx, A->values, x, y, accumulate);
+        csr_binned_kernel<V><<<B.block_start[kBins - 1], 256, 0, stream>>>(L, B.rows, A->row_ptr, A->col_idx, values, x, y, accumulate);
         SPMV_TRY_CUDA(cudaGetLastError());
     }
     if (B.num_long > 0) {
         const int *long_rows = B.rows + B.offset[kBins - 1];
-        csr_long_fragment_kernel<<<B.num_frag, kFragThreads, 0, stream>>>(long_rows, B.frag_first, B.num_long, A->row_ptr,
-                                                                         A->col_idx, A->values, x, B.frag_partial);
+        csr_long_fragment_kernel<V><<<B.num_frag, kFragThreads, 0, stream>>>(long_rows, B.frag_first, B.num_long, A->row_ptr,
+                                                                            A->col_idx, values, x, B.frag_partial);
         SPMV_TRY_CUDA(cudaGetLastError());
-        csr_long_combine_kernel<<<blocks_for(B.num_long, 128), 128, 0, stream>>>(long_rows, B.frag_first, B.num_long,
-                                                                                B.frag_partial, y, accumulate);
+        csr_long_combine_kernel<V><<<blocks_for(B.num_long, 128), 128, 0, stream>>>(long_rows, B.frag_first, B.num_long,
+                                                                                   B.frag_partial, y, accumulate);
         SPMV_TRY_CUDA(cudaGetLastError());
     }
     return SPMV_B200_OK;
@@ -836,7 +848,7 @@ CsrPath csr_resolve(const spmv_b200_csr *A, int algo) {
 
 int csr_launch_window(const spmv_b200_csr *A, CsrPath path, int unit_begin, int unit_end, const double *x, double *y,
                       int accumulate, cudaStream_t stream) {
-    if (path == kPathBinned) return launch_binned(A, x, y, accumulate, stream);  // whole matrix: rows are permuted
+    if (path == kPathBinned) return launch_binned<double>(A, A->values, x, y, accumulate, stream);  // whole matrix: rows are permuted
     if (path == kPathRow)
         return launch_rows(unit_begin, unit_end, A->row_ptr, A->col_idx, A->values, x, y, A->row_batch, accumulate, stream);
     if (path == kPathVector)
@@ -1084,6 +1096,55 @@ int spmv_b200_csr_spmv_raw(int M, long long nnz, const int *d_row_ptr, const int
     return launch_vector(0, M, d_row_ptr, d_col_idx, d_values, d_x, d_y, vec, 0, as_stream(stream));
 }
 
+// ---- fp32 storage, fp64 arithmetic (BASELINE.json: y within 1e-5 relative) ----------------
+int spmv_b200_csr_enable_f32(spmv_b200_csr *A, void *stream) {
+    if (!A) return fail(SPMV_B200_ERR_INVALID, "csr_enable_f32: NULL matrix");
+    if (A->values32) return SPMV_B200_OK;
+    const size_t padded = std::max<size_t>(((size_t)A->nnz + 3) & ~(size_t)3, 4);
+    SPMV_TRY_CUDA(cudaMalloc(&A->values32, padded * sizeof(float)));
+    SPMV_TRY_CUDA(cudaMemsetAsync(A->values32, 0, padded * sizeof(float), as_stream(stream)));
+    if (A->nnz) {
+        to_f32_kernel<<<blocks_for(A->nnz, 256), 256, 0, as_stream(stream)>>>(A->values, A->values32, A->nnz);
+        SPMV_TRY_CUDA(cudaGetLastError());
+    }
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_csr_spmv_f32(const spmv_b200_csr *A, const float *d_x, float *d_y, int accumulate, int algo, void *stream) {
+    if (!A || !d_y || (A->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_f32: NULL argument");
+    if (!A->values32) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_f32: call spmv_b200_csr_enable_f32 first");
+    if (A->M == 0) return SPMV_B200_OK;
+    CsrPath path;
+    switch (algo) {
+        case SPMV_B200_ALGO_AUTO:
+            path = A->max_row <= kRowKernelMaxLen ? kPathRow : (A->num_long == 0 ? kPathVector : kPathBinned);
+            break;
+        case SPMV_B200_ALGO_ROW: path = kPathRow; break;
+        case SPMV_B200_ALGO_VECTOR: path = kPathVector; break;
+        case SPMV_B200_ALGO_BINNED: path = kPathBinned; break;
+        default: return fail(SPMV_B200_ERR_INVALID, "csr_spmv_f32: algo %d has no fp32 kernel (AUTO, VECTOR, BINNED, ROW)", algo);
+    }
+    cudaStream_t s = as_stream(stream);
+    if (path == kPathRow) return launch_rows<float>(0, A->M, A->row_ptr, A->col_idx, A->values32, d_x, d_y, A->row_batch, accumulate, s);
+    if (path == kPathVector)
+        return launch_vector<float>(0, A->M, A->row_ptr, A->col_idx, A->values32, d_x, d_y, pick_vector_width(A->nnz, A->M), accumulate, s);
+    return launch_binned<float>(A, A->values32, d_x, d_y, accumulate, s);
+}
+
+int spmv_b200_csr_spmv_host_f32(spmv_b200_csr *A, const float *x, float *y) {
+    if (!A || (A->M > 0 && !y) || (A->N > 0 && A->nnz > 0 && !x)) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_host_f32: NULL argument");
+    if (A->M == 0) return SPMV_B200_OK;
+    SPMV_TRY(spmv_b200_csr_enable_f32(A, nullptr));
+    if (!A->stage_x) SPMV_TRY_CUDA(cudaMalloc(&A->stage_x, std::max<size_t>(A->N, 1) * sizeof(double)));
+    if (!A->stage_y) SPMV_TRY_CUDA(cudaMalloc(&A->stage_y, std::max<size_t>(A->M, 1) * sizeof(double)));
+    float *dx = reinterpret_cast<float *>(A->stage_x), *dy = reinterpret_cast<float *>(A->stage_y);
+    if (A->N && x) SPMV_TRY_CUDA(cudaMemcpyAsync(dx, x, (size_t)A->N * sizeof(float), cudaMemcpyHostToDevice, nullptr));
+    SPMV_TRY(spmv_b200_csr_spmv_f32(A, dx, dy, 0, SPMV_B200_ALGO_AUTO, nullptr));
+    SPMV_TRY_CUDA(cudaMemcpyAsync(y, dy, (size_t)A->M * sizeof(float), cudaMemcpyDeviceToHost, nullptr));
+    SPMV_TRY_CUDA(cudaStreamSynchronize(nullptr));
+    return SPMV_B200_OK;
+}
+
 void spmv_b200_csr_free(spmv_b200_csr *A) {
     if (!A) return;
     free_plan(A);
@@ -1094,6 +1155,7 @@ void spmv_b200_csr_free(spmv_b200_csr *A) {
     }
     cudaFree(A->stage_x);
     cudaFree(A->stage_y);
+    cudaFree(A->values32);
     host_pipe_free(A->pipe);
     delete A;
 }

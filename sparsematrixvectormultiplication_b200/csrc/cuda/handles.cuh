@@ -50,6 +50,7 @@ struct spmv_b200_csr {
     int *row_ptr = nullptr;
     int *col_idx = nullptr;
     double *values = nullptr;
+    float *values32 = nullptr;  // fp32 copy of the values (spmv_b200_csr_enable_f32): fp32 storage, fp64 arithmetic
     bool owns = false;
     // plan (shared by the tile kernel and the TMA stream kernel)
     int tile_items = spmv::kDefaultTileItems;
@@ -83,6 +84,7 @@ struct spmv_b200_hll {
     long long *hack_off = nullptr;  // device [num_hacks+1]
     int *JA = nullptr;              // device [slots]
     double *AS = nullptr;           // device [slots]
+    float *AS32 = nullptr;          // fp32 copy of AS (spmv_b200_hll_enable_f32)
     std::vector<long long> host_off;
     // stream kernel plan
     int tile_slots = spmv::kHllTileSlots;

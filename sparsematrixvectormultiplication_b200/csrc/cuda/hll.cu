@@ -33,8 +33,18 @@ constexpr int kHack = HACK_SIZE;
 constexpr int kHllThreads = 256;
 constexpr int kHllWarps = kHllThreads / 32;
 
-__device__ __forceinline__ void hll_step(const int *__restrict__ JA, const double *__restrict__ AS,
-                                         const double *__restrict__ x, long long slot, double (&acc)[4]) {
+__device__ __forceinline__ void ldg_stream_f64x4(const float *p, double (&v)[4]) {  // fp32 storage: one 128-bit load
+    float4 f;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "l"(p));
+    v[0] = f.x;
+    v[1] = f.y;
+    v[2] = f.z;
+    v[3] = f.w;
+}
+
+template <typename V>
+__device__ __forceinline__ void hll_step(const int *__restrict__ JA, const V *__restrict__ AS,
+                                         const V *__restrict__ x, long long slot, double (&acc)[4]) {
     const int4 c = ldg_stream_s32x4(JA + slot);
     double v[4];
     ldg_stream_f64x4(AS + slot, v);
@@ -44,9 +54,10 @@ __device__ __forceinline__ void hll_step(const int *__restrict__ JA, const doubl
     acc[3] = fma(v[3], ldg_x(x, c.w), acc[3]);
 }
 
+template <typename V>
 __global__ void __launch_bounds__(kHllThreads)
 hll_slice_kernel(int hack_begin, int hack_end, const long long *__restrict__ hack_off, const int *__restrict__ JA,
-                 const double *__restrict__ AS, const double *__restrict__ x, double *__restrict__ y, int M) {
+                 const V *__restrict__ AS, const V *__restrict__ x, V *__restrict__ y, int M) {
     const int hack = hack_begin + blockIdx.x * kHllWarps + (threadIdx.x >> 5);
     if (hack >= hack_end) return;  // warp-uniform
     const int lane = threadIdx.x & 31;
@@ -73,7 +84,7 @@ hll_slice_kernel(int hack_begin, int hack_end, const long long *__restrict__ hac
         const int row = hack * kHack + 4 * q;
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-            if (row + e < M) y[row + e] = acc[e];
+            if (row + e < M) y[row + e] = (V)acc[e];
     }
 }
 
@@ -81,10 +92,10 @@ hll_slice_kernel(int hack_begin, int hack_end, const long long *__restrict__ hac
 // warp one contiguous 128 B (JA) / 256 B (AS) segment -- no shared memory, no reliance on L1 for the stream.  BATCH
 // slots are requested before the first gather.  One lane per row, sequential in j, mul and add rounded separately:
 // bit-identical to the reference's spmv_hll_serial (src/hll_matrix.c:294-306), padding slots (x 0.0) included.
-template <int BATCH>
+template <int BATCH, typename V>
 __global__ void __launch_bounds__(256, 8)
 hll_row_kernel(int hack_begin, int hack_end, const long long *__restrict__ hack_off, const int *__restrict__ JA,
-               const double *__restrict__ AS, const double *__restrict__ x, double *__restrict__ y, int M) {
+               const V *__restrict__ AS, const V *__restrict__ x, V *__restrict__ y, int M) {
     const int hack = hack_begin + blockIdx.x * 8 + (threadIdx.x >> 5);
     if (hack >= hack_end) return;  // warp-uniform
     const int lane = threadIdx.x & 31;
@@ -106,7 +117,7 @@ hll_row_kernel(int hack_begin, int hack_end, const long long *__restrict__ hack_
             if (c[u] >= 0) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
     }
     const long long row = (long long)hack * kHack + lane;
-    if (row < M) y[row] = acc;
+    if (row < M) y[row] = (V)acc;
 }
 
 // ---- CSR -> HLL on the device ----------------------------------------------------------------------
@@ -171,24 +182,30 @@ extern "C" int spmv_b200_csr_info(const spmv_b200_csr *A, spmv_b200_csr_info_t *
 
 using namespace spmv;
 
-static int hll_launch_rows(const spmv_b200_hll *H, int hack_begin, int hack_end, const double *d_x, double *d_y,
-                           cudaStream_t stream) {
+template <typename V>
+static int hll_launch_rows_t(const spmv_b200_hll *H, const V *AS, int hack_begin, int hack_end, const V *d_x, V *d_y,
+                             cudaStream_t stream) {
     if (hack_end <= hack_begin) return SPMV_B200_OK;
     const unsigned int g = blocks_for(hack_end - hack_begin, 8);
-#define HROW_CASE(B) case B: hll_row_kernel<B><<<g, 256, 0, stream>>>(hack_begin, hack_end, H->hack_off, H->JA, H->AS, d_x, d_y, H->M); break;
+#define HROW_CASE(B) case B: hll_row_kernel<B, V><<<g, 256, 0, stream>>>(hack_begin, hack_end, H->hack_off, H->JA, AS, d_x, d_y, H->M); break;
     switch (H->row_batch) {
         HROW_CASE(1) HROW_CASE(2) HROW_CASE(3) HROW_CASE(5) HROW_CASE(6) HROW_CASE(7) HROW_CASE(8)
-        default: hll_row_kernel<4><<<g, 256, 0, stream>>>(hack_begin, hack_end, H->hack_off, H->JA, H->AS, d_x, d_y, H->M); break;
+        default: hll_row_kernel<4, V><<<g, 256, 0, stream>>>(hack_begin, hack_end, H->hack_off, H->JA, AS, d_x, d_y, H->M); break;
     }
 #undef HROW_CASE
     SPMV_TRY_CUDA(cudaGetLastError());
     return SPMV_B200_OK;
 }
 
+static int hll_launch_rows(const spmv_b200_hll *H, int hack_begin, int hack_end, const double *d_x, double *d_y,
+                           cudaStream_t stream) {
+    return hll_launch_rows_t<double>(H, H->AS, hack_begin, hack_end, d_x, d_y, stream);
+}
+
 static int hll_launch(const spmv_b200_hll *H, int hack_begin, int hack_end, const double *d_x, double *d_y,
                       cudaStream_t stream) {
     if (hack_end <= hack_begin) return SPMV_B200_OK;
-    hll_slice_kernel<<<blocks_for(hack_end - hack_begin, kHllWarps), kHllThreads, 0, stream>>>(
+    hll_slice_kernel<double><<<blocks_for(hack_end - hack_begin, kHllWarps), kHllThreads, 0, stream>>>(
         hack_begin, hack_end, H->hack_off, H->JA, H->AS, d_x, d_y, H->M);
     SPMV_TRY_CUDA(cudaGetLastError());
     return SPMV_B200_OK;
@@ -490,8 +507,53 @@ int spmv_b200_hll_spmv_hacks(const spmv_b200_hll *H, int hack_begin, int hack_en
     return hll_launch(H, hack_begin, hack_end, d_x, d_y, as_stream(stream));
 }
 
+// ---- fp32 storage, fp64 arithmetic --------------------------------------------------------------------------------
+__global__ void hll_to_f32_kernel(const double *__restrict__ in, float *__restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+
+int spmv_b200_hll_enable_f32(spmv_b200_hll *H, void *stream) {
+    if (!H) return fail(SPMV_B200_ERR_INVALID, "hll_enable_f32: NULL matrix");
+    if (H->AS32) return SPMV_B200_OK;
+    const size_t n = (size_t)std::max<long long>(H->slots, 32);
+    SPMV_TRY_CUDA(cudaMalloc(&H->AS32, n * sizeof(float)));
+    SPMV_TRY_CUDA(cudaMemsetAsync(H->AS32, 0, n * sizeof(float), as_stream(stream)));
+    if (H->slots) {
+        hll_to_f32_kernel<<<blocks_for(H->slots, 256), 256, 0, as_stream(stream)>>>(H->AS, H->AS32, H->slots);
+        SPMV_TRY_CUDA(cudaGetLastError());
+    }
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_hll_spmv_f32(const spmv_b200_hll *H, const float *d_x, float *d_y, void *stream) {
+    if (!H || !d_y || (H->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_f32: NULL argument");
+    if (!H->AS32) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_f32: call spmv_b200_hll_enable_f32 first");
+    if (H->num_hacks == 0) return SPMV_B200_OK;
+    if (H->max_width <= kRowKernelMaxLen) return hll_launch_rows_t<float>(H, H->AS32, 0, H->num_hacks, d_x, d_y, as_stream(stream));
+    hll_slice_kernel<float><<<blocks_for(H->num_hacks, kHllWarps), kHllThreads, 0, as_stream(stream)>>>(
+        0, H->num_hacks, H->hack_off, H->JA, H->AS32, d_x, d_y, H->M);
+    SPMV_TRY_CUDA(cudaGetLastError());
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_hll_spmv_host_f32(spmv_b200_hll *H, const float *x, float *y) {
+    if (!H || (H->M > 0 && !y) || (H->N > 0 && H->slots > 0 && !x)) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_host_f32: NULL argument");
+    if (H->M == 0) return SPMV_B200_OK;
+    SPMV_TRY(spmv_b200_hll_enable_f32(H, nullptr));
+    if (!H->stage_x) SPMV_TRY_CUDA(cudaMalloc(&H->stage_x, std::max<size_t>(H->N, 1) * sizeof(double)));
+    if (!H->stage_y) SPMV_TRY_CUDA(cudaMalloc(&H->stage_y, std::max<size_t>(H->M, 1) * sizeof(double)));
+    float *dx = reinterpret_cast<float *>(H->stage_x), *dy = reinterpret_cast<float *>(H->stage_y);
+    if (H->N && x) SPMV_TRY_CUDA(cudaMemcpyAsync(dx, x, (size_t)H->N * sizeof(float), cudaMemcpyHostToDevice, nullptr));
+    SPMV_TRY(spmv_b200_hll_spmv_f32(H, dx, dy, nullptr));
+    SPMV_TRY_CUDA(cudaMemcpyAsync(y, dy, (size_t)H->M * sizeof(float), cudaMemcpyDeviceToHost, nullptr));
+    SPMV_TRY_CUDA(cudaStreamSynchronize(nullptr));
+    return SPMV_B200_OK;
+}
+
 void spmv_b200_hll_free(spmv_b200_hll *H) {
     if (!H) return;
+    cudaFree(H->AS32);
     cudaFree(H->tiles);
     cudaFree(H->hack_off);
     cudaFree(H->JA);

@@ -6,8 +6,8 @@
  * entry stored immediately after each off-diagonal entry; 0 on success, -1 with a message on
  * stdout otherwise -- but the body of the file is slurped once and tokenised in memory with
  * strtol/strtod (which accept exactly what fscanf's %d / %lf accept) instead of one fscanf call
- * per entry.  This is row (f).4 of SURVEY.md section 8: the fscanf loop is the end-to-end
- * bottleneck on real files.
+ * per entry, and bodies of 1 MB or more are tokenised by all OpenMP threads at once.  This is row
+ * (f).4 of SURVEY.md section 8: the fscanf loop is the end-to-end bottleneck on real files.
  */
 #include "matrix_parser.h"
 
@@ -17,6 +17,16 @@
 #include <string.h>
 
 #include "utility.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* bodies at least this long are tokenised in parallel (SPMV_B200_PARSER_PARALLEL_MIN_BYTES overrides: tests) */
+static size_t parallel_min_bytes(void) {
+    const char *v = getenv("SPMV_B200_PARSER_PARALLEL_MIN_BYTES");
+    if (v && *v) return (size_t)strtoull(v, NULL, 10);
+    return (size_t)1 << 20;
+}
 
 void init_pre_matrix(PreMatrix *mat) {
     memset(mat, 0, sizeof *mat);
@@ -82,6 +92,110 @@ static int take_double(const char **cursor, double *out) {
     return 1;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Parallel tokenizer for large bodies.  Same result as the serial loop
+ * below, which stays the reference for every irregular input: the parallel pass only accepts a
+ * body made of at least `declared` x k white-space separated tokens (k = 2 for pattern files, else
+ * 3) in which strtol / strtod consume every index / value token COMPLETELY and every index is in
+ * bounds.  Anything else -- short file, "12abc", an index out of range -- returns 0 and the caller
+ * re-parses serially, so messages and partial-read semantics are the reference's by construction.
+ * Tokens, not lines, are the unit: fscanf("%d %d %lf") does not care about line breaks either.
+ * ---------------------------------------------------------------------------------------- */
+static int is_space(char ch) { return ch == ' ' || ch == '\n' || ch == '\t' || ch == '\r' || ch == '\v' || ch == '\f'; }
+
+static int parse_body_parallel(const char *text, size_t len, int declared, int pattern, int M, int N, int *I,
+                               int *J, double *V) {
+    const int k = pattern ? 2 : 3;
+    int threads = 1;
+#ifdef _OPENMP
+    threads = omp_get_max_threads();
+#endif
+    if (threads > 64) threads = 64;
+    if (threads < 2 || declared <= 0) return 0;
+    size_t begin[65];
+    long long first_token[65];
+    /* chunk boundaries moved forward to the start of a token (or the end of the text) */
+    for (int t = 0; t <= threads; ++t) {
+        size_t at = t == threads ? len : len / (size_t)threads * (size_t)t;
+        if (t > 0 && t < threads) {
+            while (at < len && !is_space(text[at - 1])) ++at; /* do not split a token */
+        }
+        begin[t] = at;
+    }
+    long long counts[64];
+#pragma omp parallel for num_threads(threads) schedule(static, 1)
+    for (int t = 0; t < threads; ++t) {
+        long long n = 0;
+        int in_token = 0;
+        for (size_t p = begin[t]; p < begin[t + 1]; ++p) {
+            const int sp = is_space(text[p]);
+            if (!sp && !in_token) ++n;
+            in_token = !sp;
+        }
+        counts[t] = n;
+    }
+    first_token[0] = 0;
+    for (int t = 0; t < threads; ++t) first_token[t + 1] = first_token[t] + counts[t];
+    const long long needed = (long long)declared * k;
+    if (first_token[threads] < needed) return 0; /* short body: the serial loop reports the entry */
+    int bad = 0;
+#pragma omp parallel for num_threads(threads) schedule(static, 1) reduction(| : bad)
+    for (int t = 0; t < threads; ++t) {
+        long long tok = first_token[t];
+        size_t p = begin[t];
+        const size_t stop = begin[t + 1];
+        while (p < stop && tok < needed && !bad) {
+            while (p < stop && is_space(text[p])) ++p;
+            if (p >= stop) break;
+            size_t q = p;
+            while (q < stop && !is_space(text[q])) ++q;
+            const long long entry = tok / k;
+            const int field = (int)(tok % k);
+            char *end;
+            if (field < 2) {
+                const char *d = text + p;
+                if (*d == '+' || *d == '-') ++d;
+                if (*d < '0' || *d > '9') { bad = 1; break; }
+                errno = 0;
+                const long v = strtol(text + p, &end, 10);
+                if (end != text + q || errno == ERANGE || v < 1 || v > (field == 0 ? M : N)) { bad = 1; break; }
+                (field == 0 ? I : J)[entry] = (int)v - 1;
+            } else {
+                const double v = strtod(text + p, &end);
+                if (end != text + q) { bad = 1; break; }
+                V[entry] = v;
+            }
+            ++tok;
+            p = q;
+        }
+    }
+    if (bad) return 0;
+    if (pattern) {
+#pragma omp parallel for num_threads(threads)
+        for (int e = 0; e < declared; ++e) V[e] = 1.0;
+    }
+    return 1;
+}
+
+/* in-place expansion of a symmetric body: entry e moves to e + (#off-diagonal entries before e), its
+ * mirror right behind it (reference src/matrix_parser.c:100-118 stores the pair in this order) */
+static size_t mirror_in_place(int declared, int *I, int *J, double *V) {
+    size_t extra = 0;
+    for (int e = 0; e < declared; ++e) extra += I[e] != J[e];
+    size_t out = (size_t)declared + extra;
+    for (int e = declared - 1; e >= 0; --e) { /* back to front: never overwrites an unread entry */
+        const int r = I[e], c = J[e];
+        const double v = V[e];
+        if (r != c) {
+            --out;
+            I[out] = c; J[out] = r; V[out] = v;
+        }
+        --out;
+        I[out] = r; J[out] = c; V[out] = v;
+    }
+    return (size_t)declared + extra;
+}
+
 int read_matrix_market(const char *filename, PreMatrix *mat) {
     FILE *f = fopen(filename, "r");
     if (!f) {
@@ -124,7 +238,12 @@ int read_matrix_market(const char *filename, PreMatrix *mat) {
         status = -1;
     }
     const char *cur = text;
-    for (int e = 0; status == 0 && e < declared; ++e) {
+    int done = 0;
+    if (status == 0 && len >= parallel_min_bytes()) {
+        done = parse_body_parallel(text, len, declared, pattern, mat->M, mat->N, I, J, V);
+        if (done) n = mirror ? mirror_in_place(declared, I, J, V) : (size_t)declared;
+    }
+    for (int e = 0; !done && status == 0 && e < declared; ++e) {
         int r, c;
         double v = 1.0;
         int fields = take_int(&cur, &r);

@@ -73,6 +73,21 @@ class DeviceCSR:
         return cls(h)
 
     @classmethod
+    def from_coo(cls, M, N_, I, J, val, stream=None):
+        """COO -> CSR built on the device (spmv_b200_csr_from_coo[_device]).  I / J / val: numpy arrays (copied up) or
+        CUDA tensors (used in place).  Replaces convert_in_csr (reference src/csr_matrix.c:63-126) for resident data."""
+        h = C.c_void_p()
+        if isinstance(I, np.ndarray):
+            I = np.ascontiguousarray(I, np.int32)
+            J = np.ascontiguousarray(J, np.int32)
+            val = np.ascontiguousarray(val, np.float64)
+            N.check(N.lib().spmv_b200_csr_from_coo(int(M), int(N_), int(len(I)), _ptr(I), _ptr(J), _ptr(val), C.byref(h)))
+        else:
+            N.check(N.lib().spmv_b200_csr_from_coo_device(int(M), int(N_), int(I.numel()), _ptr(I), _ptr(J), _ptr(val),
+                                                          _stream(stream), C.byref(h)))
+        return cls(h)
+
+    @classmethod
     def from_host(cls, csr):
         """From a host.CSRMatrix produced by convert_in_csr."""
         return cls.upload(csr.M, csr.N, csr.row_ptr, csr.col_idx, csr.values)
@@ -168,6 +183,28 @@ class DeviceCSR:
         """Same, on raw host addresses (e.g. pinned torch tensors' data_ptr())."""
         N.check(N.lib().spmv_b200_csr_spmv_host(self._h, C.c_void_p(x_ptr), C.c_void_p(y_ptr), int(bool(accumulate)), algo))
 
+    # -- fp32 storage, fp64 arithmetic (SURVEY.md section 8(f).3) ----------------------------------------------
+    def enable_f32(self, stream=None):
+        N.check(N.lib().spmv_b200_csr_enable_f32(self._h, _stream(stream)))
+        return self
+
+    def spmv_f32(self, x, y, accumulate=False, algo=ALGO_AUTO, stream=None):
+        """y = A x on float32 CUDA tensors (float values, x, y; products and sums in double)."""
+        N.check(N.lib().spmv_b200_csr_spmv_f32(self._h, _ptr(x), _ptr(y), int(bool(accumulate)), algo, _stream(stream)))
+        return y
+
+    def spmv_host_f32(self, x, y=None):
+        i = self.info()
+        x = np.ascontiguousarray(x, np.float32)
+        if y is None:
+            y = np.zeros(i.M, np.float32)
+        N.check(N.lib().spmv_b200_csr_spmv_host_f32(self._h, _ptr(x), _ptr(y)))
+        return y
+
+    def algorithmic_bytes_f32(self) -> int:
+        i = self.info()
+        return 8 * i.nnz + 4 * (i.M + 1) + 4 * i.M + 4 * i.N
+
     def to_hll(self, stream=None) -> "DeviceHLL":
         h = C.c_void_p()
         N.check(N.lib().spmv_b200_hll_from_csr(self._h, _stream(stream), C.byref(h)))
@@ -232,6 +269,26 @@ class DeviceHLL:
               False: N.lib().spmv_b200_hll_spmv_stream, "rows": N.lib().spmv_b200_hll_spmv_rows}[slice_kernel]
         N.check(fn(self._h, _ptr(x), _ptr(y), _stream(stream)))
         return y
+
+    def enable_f32(self, stream=None):
+        N.check(N.lib().spmv_b200_hll_enable_f32(self._h, _stream(stream)))
+        return self
+
+    def spmv_f32(self, x, y, stream=None):
+        N.check(N.lib().spmv_b200_hll_spmv_f32(self._h, _ptr(x), _ptr(y), _stream(stream)))
+        return y
+
+    def spmv_host_f32(self, x, y=None):
+        i = self.info()
+        x = np.ascontiguousarray(x, np.float32)
+        if y is None:
+            y = np.zeros(i.M, np.float32)
+        N.check(N.lib().spmv_b200_hll_spmv_host_f32(self._h, _ptr(x), _ptr(y)))
+        return y
+
+    def algorithmic_bytes_f32(self) -> int:
+        i = self.info()
+        return 8 * i.slots + 8 * (i.num_hacks + 1) + 4 * i.M + 4 * i.N
 
     def spmv_hacks(self, hack_begin, hack_end, x, y, stream=None):
         N.check(N.lib().spmv_b200_hll_spmv_hacks(self._h, int(hack_begin), int(hack_end), _ptr(x), _ptr(y), _stream(stream)))

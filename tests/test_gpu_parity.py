@@ -610,3 +610,101 @@ def test_reference_cuda_kernels_agree(dev, checker):
             for oname, yo in ours.items():
                 err = np.abs(yo - yr)
                 assert np.all(err <= 2 * TOL * np.maximum(scale, np.finfo(float).tiny)), f"{oname} vs reference {rname}"
+
+
+@pytest.mark.parametrize("M,N,nz", [(1, 1, 1), (40, 1, 25), (1, 300, 120), (33, 65, 700), (1000, 1000, 30000), (4000, 123, 50000),
+                                    (64, 64, 0)])
+@pytest.mark.parametrize("dup", [False, True])
+def test_device_coo_to_csr(dev, checker, M, N, nz, dup):
+    """spmv_b200_csr_from_coo: duplicate-free COO gives convert_in_csr's arrays bit for bit (and then CSR -> HLL on the
+    device gives convert_to_hll's); with repeated coordinates the rows hold the same (column, value) multiset, sorted
+    by column, and the product agrees within tolerance.  Host arrays and device tensors."""
+    import torch
+    from sparsematrixvectormultiplication_b200 import host
+    rng = np.random.default_rng(M * 13 + N * 7 + nz + dup)
+    coo = random_coo(rng, M, N, nz, dup=dup)
+    nz = len(coo.I)
+    rp, ci, va = checker.coo_to_csr(coo)
+    x = rng.standard_normal(N)
+    y_ref = checker.spmv_csr_serial(rp, ci, va, x)
+    scale = abs_row_sums(checker, rp, ci, va, x)
+    built = [dev.DeviceCSR.from_coo(M, N, coo.I, coo.J, coo.val)]
+    if nz:
+        t = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (coo.I, coo.J, coo.val)]
+        built.append(dev.DeviceCSR.from_coo(M, N, *t))
+    for A in built:
+        drp, dci, dva = A.download()
+        assert np.array_equal(drp, rp)
+        if not dup:
+            assert np.array_equal(dci, ci) and np.array_equal(bits(dva), bits(va))
+            h = checker.coo_to_hll(coo)
+            rows, maxnz, offset, JA, AS = A.to_hll().download().flat()
+            assert np.array_equal(maxnz, h.maxnz) and np.array_equal(JA, h.JA) and np.array_equal(bits(AS), bits(h.AS))
+        else:
+            assert np.array_equal(dci, ci), "columns are sorted inside every row in both"
+            for r in range(M):   # same multiset of (column, value) per row
+                a = sorted(zip(dci[drp[r]:drp[r + 1]].tolist(), dva[drp[r]:drp[r + 1]].tolist()))
+                b = sorted(zip(ci[rp[r]:rp[r + 1]].tolist(), va[rp[r]:rp[r + 1]].tolist()))
+                assert a == b, f"row {r}"
+        assert_close(A.spmv_host(x), y_ref, scale, "product of the device-built CSR")
+    with pytest.raises(Exception):
+        dev.DeviceCSR.from_coo(3, 3, np.array([0, 3], np.int32), np.array([0, 0], np.int32), np.array([1.0, 2.0]))
+
+
+# ---------------------------------------------------------------------------------------------------
+# fp32 storage, fp64 arithmetic: y within 1e-5 relative of the serial fp64 product (BASELINE.json north star)
+# ---------------------------------------------------------------------------------------------------
+TOL32 = 1e-5
+
+
+@pytest.mark.parametrize("kind", ["stencil", "random", "skewed"])
+def test_fp32_path_within_1e_5(dev, checker, kind):
+    """Values, x and y stored as float32, every product formed and summed in double and rounded once on the store:
+    |dy_i| <= 1e-5 * sum_j |a_ij x_j| against csr_matrix_vector_mult on the ORIGINAL fp64 data, for the row kernel
+    (stencil), the vector kernel (even rows) and the binned kernel with long-row fragments (skewed); CSR and HLL."""
+    import torch
+    rng = np.random.default_rng(len(kind))
+    if kind == "stencil":
+        from sparsematrixvectormultiplication_b200 import synth
+        rp, ci, va = synth.lap2d_csr(70)
+        M = N = 4900
+        va = va * rng.uniform(0.5, 1.5, va.size)
+    else:
+        M, N = 6000, 5000
+        lengths = rng.integers(20, 40, M) if kind == "random" else np.concatenate([[9000, 3000, 600], rng.integers(0, 30, M - 3)])
+        lengths = np.minimum(lengths, N)
+        rp = np.zeros(M + 1, np.int32)
+        np.cumsum(lengths, out=rp[1:])
+        ci = np.concatenate([np.sort(rng.choice(N, n, replace=False)) for n in lengths]).astype(np.int32)
+        va = rng.standard_normal(rp[-1])
+    x = rng.standard_normal(N)
+    y_ref = checker.spmv_csr_serial(rp, ci, va, x)
+    scale = abs_row_sums(checker, rp, ci, va, x)
+    A = dev.DeviceCSR.upload(M, N, rp, ci, va).enable_f32()
+    if kind == "skewed":
+        A.replan(long_threshold=512)
+    x32 = torch.from_numpy(x.astype(np.float32)).cuda()
+    algos = [dev.ALGO_AUTO, dev.ALGO_VECTOR, dev.ALGO_BINNED] + ([dev.ALGO_ROW] if kind != "skewed" else [])
+    for algo in algos:
+        y32 = torch.full((M,), float("nan"), dtype=torch.float32, device="cuda")
+        A.spmv_f32(x32, y32, algo=algo)
+        err = np.abs(y32.cpu().numpy().astype(np.float64) - y_ref)
+        assert np.all(err <= TOL32 * np.maximum(scale, np.finfo(np.float32).tiny)), f"{kind} csr algo {algo}: max {err.max():.3g}"
+        assert err.max() > 0 or kind == "stencil", "fp32 storage cannot be exact on random data"
+    yh = A.spmv_host_f32(x)
+    assert yh.dtype == np.float32 and np.all(np.abs(yh.astype(np.float64) - y_ref) <= TOL32 * np.maximum(scale, 1e-30))
+    acc0 = rng.standard_normal(M).astype(np.float32)
+    yacc = torch.from_numpy(acc0.copy()).cuda()
+    A.spmv_f32(x32, yacc, accumulate=True)
+    assert np.all(np.abs(yacc.cpu().numpy().astype(np.float64) - (acc0 + y_ref)) <= TOL32 * (scale + np.abs(acc0) + 1e-30))
+    with pytest.raises(Exception):
+        A.spmv_f32(x32, yacc, algo=dev.ALGO_STREAM)     # no fp32 stream kernel: fails loudly
+    if kind != "skewed":
+        H = A.to_hll().enable_f32()
+        y32 = torch.full((M,), float("nan"), dtype=torch.float32, device="cuda")
+        H.spmv_f32(x32, y32)
+        assert np.all(np.abs(y32.cpu().numpy().astype(np.float64) - y_ref) <= TOL32 * np.maximum(scale, 1e-30)), f"{kind} hll"
+        assert np.all(np.abs(H.spmv_host_f32(x).astype(np.float64) - y_ref) <= TOL32 * np.maximum(scale, 1e-30))
+    B = dev.DeviceCSR.upload(M, N, rp, ci, va)
+    with pytest.raises(Exception):
+        B.spmv_f32(x32, yacc)                            # enable_f32 not called

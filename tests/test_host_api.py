@@ -1,6 +1,7 @@
 """Drop-in host API (libspmv_b200.so) vs the reference: golden vectors + the oracle on random COO.
 Bit-exact for every index and value array."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -172,3 +173,90 @@ def test_driver_fails_loudly_without_a_gpu(tmp_path):
     assert out.returncode == 3, out.stdout + out.stderr
     assert "no CUDA device" in out.stderr and "no CPU fallback" in out.stderr
     assert not (tmp_path / "r.csv").exists()
+
+
+# ---------------------------------------------------------------------------------------------------
+# parallel tokenizer of read_matrix_market: same bits as the serial path
+# ---------------------------------------------------------------------------------------------------
+def _same_pre(a, b):
+    return (a.M, a.N, a.nz) == (b.M, b.N, b.nz) and np.array_equal(a.I, b.I) and np.array_equal(a.J, b.J) \
+        and np.array_equal(a.val.view(np.uint64), b.val.view(np.uint64)) and bytes(a.c.type) == bytes(b.c.type)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_parallel_parser_equals_serial_on_fixtures(name, monkeypatch):
+    path = GOLDEN / "mtx" / f"{name}.mtx"
+    monkeypatch.setenv("SPMV_B200_PARSER_PARALLEL_MIN_BYTES", str(1 << 40))
+    serial = host.read_matrix_market(path)
+    monkeypatch.setenv("SPMV_B200_PARSER_PARALLEL_MIN_BYTES", "0")
+    for threads in ("2", "3", "16"):
+        monkeypatch.setenv("OMP_NUM_THREADS", threads)
+        assert _same_pre(host.read_matrix_market(path), serial), f"{name} with {threads} threads"
+
+
+@pytest.mark.parametrize("kind,field", [("general", "real"), ("symmetric", "real"), ("general", "pattern"),
+                                        ("symmetric", "pattern"), ("general", "integer"), ("skew-symmetric", "real")])
+def test_parallel_parser_on_a_large_file(tmp_path, reference, kind, field):
+    """A 300k-entry file (6-9 MB: above the 1 MB default threshold) with ragged white space, entries spanning lines and
+    exponents: default (parallel) parse == forced-serial parse == the reference's fscanf parser."""
+    rng = np.random.default_rng(len(kind) * 31 + len(field))
+    M, N, nz = 5000, 4000 if kind == "general" else 5000, 300_000
+    I = rng.integers(1, M + 1, nz)
+    J = rng.integers(1, N + 1, nz)
+    if kind != "general":
+        I, J = np.maximum(I, J), np.minimum(I, J)
+    lines = [f"%%MatrixMarket matrix coordinate {field} {kind}", "% generated by the test", f"{M} {N} {nz}"]
+    vals = rng.standard_normal(nz) * 10.0 ** rng.integers(-8, 9, nz)
+    seps = ["  ", "\t", " ", "\n", " \t "]
+    for k in range(nz):
+        sep = seps[k % len(seps)]
+        if field == "pattern":
+            lines.append(f"{I[k]}{sep}{J[k]}")
+        elif field == "integer":
+            lines.append(f"{I[k]}{sep}{J[k]} {int(vals[k]) % 1000 - 500}")
+        else:
+            lines.append(f"{I[k]}{sep}{J[k]} {vals[k]:.17e}" if k % 3 else f"{I[k]} {J[k]}\n{float(vals[k])!r}")
+    path = tmp_path / "big.mtx"
+    path.write_text("\n".join(lines) + "\n")
+    assert path.stat().st_size > (1 << 20)
+    fast = host.read_matrix_market(path)
+    os.environ["SPMV_B200_PARSER_PARALLEL_MIN_BYTES"] = str(1 << 40)
+    try:
+        slow = host.read_matrix_market(path)
+    finally:
+        del os.environ["SPMV_B200_PARSER_PARALLEL_MIN_BYTES"]
+    assert _same_pre(fast, slow)
+    ref = reference.read_matrix_market(path)
+    assert (ref.M, ref.N, ref.nz) == (fast.M, fast.N, fast.nz)
+    assert np.array_equal(ref.I, fast.I) and np.array_equal(ref.J, fast.J)
+    assert np.array_equal(np.asarray(ref.val).view(np.uint64), fast.val.view(np.uint64))
+
+
+@pytest.mark.parametrize("damage", ["truncated", "out_of_range", "junk_index", "glued_value"])
+def test_parallel_parser_falls_back_on_irregular_bodies(tmp_path, monkeypatch, capfd, damage):
+    """Whatever the parallel pass cannot vouch for is re-parsed by the serial loop, so errors (and the odd accepted
+    input, e.g. '7abc' = index 7 followed by a token the NEXT field chokes on) behave as without it."""
+    body = [f"{1 + k % 50} {1 + (7 * k) % 40} {k * 0.5}" for k in range(2000)]
+    if damage == "truncated":
+        body = body[:1500]
+    elif damage == "out_of_range":
+        body[1234] = "51 3 1.0"
+    elif damage == "junk_index":
+        body[777] = "x7 3 1.0"
+    else:
+        body[999] = "7 3 1.5abc"
+    path = tmp_path / "bad.mtx"
+    path.write_text("%%MatrixMarket matrix coordinate real general\n50 40 2000\n" + "\n".join(body) + "\n")
+    results = []
+    for threshold in ("0", str(1 << 40)):
+        monkeypatch.setenv("SPMV_B200_PARSER_PARALLEL_MIN_BYTES", threshold)
+        try:
+            pre = host.read_matrix_market(path)
+            results.append(("ok", pre.nz, pre.I.copy(), pre.J.copy(), pre.val.copy()))
+        except host.HostApiError:
+            results.append(("error",))
+        results[-1] = results[-1] + (capfd.readouterr().out,)
+    assert results[0][0] == results[1][0]
+    assert results[0][-1] == results[1][-1], "same message on stdout"
+    if results[0][0] == "ok":
+        assert all(np.array_equal(a, b) for a, b in zip(results[0][1:-1], results[1][1:-1]))
