@@ -40,7 +40,7 @@ HBM_NOMINAL_GBS = 8000.0   # BASELINE.json quotes fractions of 8 TB/s
 FALLBACK_PEAK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
 # ncu --set full capture (profiles/); None until a capture exists for that kernel.
-NCU_TRAFFIC_BYTES = {"lap2d_4096_csr": 1308490000}  # profiles/r01c_ncu_full_summary.md
+NCU_TRAFFIC_BYTES = {"lap2d_4096_csr": 1337700000}  # csr_row_kernel<5,double>, profiles/r01e_ncu_full_summary.md
 
 
 def log(*a):
@@ -551,7 +551,7 @@ def bench_multi_gpu(args):
     import torch
     import torch.distributed as dist
     from sparsematrixvectormultiplication_b200 import device, synth
-    from sparsematrixvectormultiplication_b200.distributed import FusedPowerIteration, PowerIteration
+    from sparsematrixvectormultiplication_b200.distributed import AsyncPowerIteration, FusedPowerIteration, PowerIteration
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -578,8 +578,10 @@ def bench_multi_gpu(args):
         except Exception as e:  # pragma: no cover
             log(f"[bench] single-GPU leg failed: {e!r}")
     dist.barrier()
-    for mode in ("fused_mailbox", "fused_peer_stores", "fused_nccl_halo", "halo", "allgather"):
-        if mode == "fused_mailbox":
+    for mode in ("fused_async", "fused_mailbox", "fused_peer_stores", "fused_nccl_halo", "halo", "allgather"):
+        if mode == "fused_async":
+            P = AsyncPowerIteration(synth.SYNTH_LAP3D, n)
+        elif mode == "fused_mailbox":
             P = FusedPowerIteration(synth.SYNTH_LAP3D, n, mailbox=True)
         elif mode == "fused_peer_stores":
             P = FusedPowerIteration(synth.SYNTH_LAP3D, n, peer_stores=True)

@@ -78,7 +78,14 @@ class Mail(C.Structure):  # include/spmv_b200.h spmv_b200_mail_t
                 ("counter", C.c_void_p), ("status", C.c_void_p)]
 
 
+class Async(C.Structure):  # include/spmv_b200.h spmv_b200_async_t
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("iteration", C.c_ulonglong), ("box", C.c_void_p * 8),
+                ("num_recv", C.c_int), ("recv_from", C.c_int * 7), ("send_to", C.c_int * 7),
+                ("counter", C.c_void_p), ("bcounter", C.c_void_p), ("status", C.c_void_p)]
+
+
 MAILBOX_BYTES = 2 * 8 * 16
+ASYNC_MAILBOX_BYTES = 4 * 8 * 16 + 8 * 8
 
 _V = C.c_void_p
 _I = C.c_int
@@ -108,6 +115,7 @@ SIGNATURES = {
     "spmv_b200_csr_partials_count": (_I, [_V]),
     "spmv_b200_csr_spmv_fused": (_I, [_V, _V, _V, _V, _V, C.POINTER(Peers), _V]),
     "spmv_b200_csr_spmv_fused_mail": (_I, [_V, _V, _V, _V, C.POINTER(Peers), C.POINTER(Mail), _V]),
+    "spmv_b200_csr_spmv_fused_async": (_I, [_V, _V, _V, _V, C.POINTER(Peers), C.POINTER(Async), _V]),
     "spmv_b200_vec_sum": (_I, [_V, _I, _V, _V]),
     "spmv_b200_ipc_alloc": (_I, [_LL, C.POINTER(_V), C.c_char * 64]),
     "spmv_b200_ipc_open": (_I, [C.c_char * 64, C.POINTER(_V)]),
@@ -130,6 +138,8 @@ SIGNATURES = {
     "spmv_b200_hll_enable_f32": (_I, [_V, _V]),
     "spmv_b200_hll_spmv_f32": (_I, [_V, _V, _V, _V]),
     "spmv_b200_hll_spmv_host_f32": (_I, [_V, _V, _V]),
+    "spmv_b200_resident_cache": (_I, [_I]),
+    "spmv_b200_resident_drop": (None, []),
     "spmv_b200_csr_time": (_I, [_V, _V, _V, _I, _I, _I, c_dbl_p, c_dbl_p]),
     "spmv_b200_hll_time": (_I, [_V, _V, _V, _I, _I, _I, c_dbl_p, c_dbl_p]),
     "spmv_b200_hll_spmv_hacks": (_I, [_V, _I, _I, _V, _V, _V]),

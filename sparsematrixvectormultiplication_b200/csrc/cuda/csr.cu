@@ -22,6 +22,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 #include "handles.cuh"
@@ -339,6 +341,143 @@ csr_row_fused_kernel(int M, const int *__restrict__ row_ptr, const int *__restri
         if (ep.mail.world > 0) {
             arrived = __shfl_sync(0xffffffffu, arrived, 0);
             if (arrived == gridDim.x - 1) mail_publish(ep.mail, ep.partials, (int)gridDim.x, lane);
+        }
+    }
+}
+
+// Asynchronous fused product (spmv_b200_csr_spmv_fused_async, spmv_b200.h): the fused row kernel with (1) the chunks
+// that hold rows a neighbour references moved to the front of the walk and a per-neighbour halo tag raised as soon as
+// they are stored, (2) the scale factor taken from the sums of launch k-2, (3) waits only on things that finished a
+// launch ago.  Chunk = 256 consecutive rows; q-th chunk of the walk -> row chunk through the boundary intervals.
+struct ChunkOrder {
+    int count;                      // boundary intervals (ascending, disjoint), in chunks
+    int lo[SPMV_B200_MAX_PEERS], hi[SPMV_B200_MAX_PEERS];
+    int boundary_chunks;            // sum of the interval lengths
+};
+
+__device__ __forceinline__ int chunk_of(const ChunkOrder &o, int q) {
+    if (q < o.boundary_chunks) {
+        for (int i = 0; i < o.count; ++i) {
+            const int len = o.hi[i] - o.lo[i];
+            if (q < len) return o.lo[i] + q;
+            q -= len;
+        }
+    }
+    int chunk = q - o.boundary_chunks;
+    for (int i = 0; i < o.count; ++i)
+        if (chunk >= o.lo[i]) chunk += o.hi[i] - o.lo[i];
+    return chunk;
+}
+
+template <int BATCH>
+__global__ void __launch_bounds__(256, 8)
+csr_row_async_kernel(int M, const int *__restrict__ row_ptr, const int *__restrict__ col_idx, const double *__restrict__ values,
+                     const double *__restrict__ x, double *__restrict__ y, double *__restrict__ partials,
+                     const spmv_b200_peers_t peers, const spmv_b200_async_t as, const ChunkOrder order) {
+    __shared__ double warp_sq[8];
+    __shared__ double s_scale;
+    __shared__ unsigned int s_arrived;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long k = as.iteration;
+    // ---- start: sums of launch k-2 (slot (k-2)%4, tag k-1) and halo tags >= k from the ranks I read from ----
+    if (warp == 0) {
+        double mine = 0.0;
+        const long long t0 = clock64();
+        if (k >= 2 && lane < as.world) {
+            const unsigned long long *slot = as.box[as.rank] + 2 * ((int)((k - 2) & 3) * as.world + lane);
+            while (ld_acquire_sys(slot + 1) != k - 1) {
+                if (clock64() - t0 > kMailSpinCycles) {
+                    *as.status = 1;
+                    break;
+                }
+                __nanosleep(40);
+            }
+            mine = __longlong_as_double((long long)ld_acquire_sys(slot));
+        }
+        if (k >= 1 && lane < as.num_recv) {
+            const unsigned long long *halo = as.box[as.rank] + 2 * 4 * as.world + as.recv_from[lane];
+            while (ld_acquire_sys(halo) < k) {
+                if (clock64() - t0 > kMailSpinCycles) {
+                    *as.status = 2;
+                    break;
+                }
+                __nanosleep(40);
+            }
+        }
+        double total = 0.0;
+        for (int r = 0; r < as.world; ++r) total += __shfl_sync(0xffffffffu, mine, r);
+        if (lane == 0) s_scale = k >= 2 ? 1.0 / sqrt(total) : 1.0;
+    }
+    __syncthreads();
+    const double scale = s_scale;
+    const int chunks = (M + 255) >> 8;
+    double sq = 0.0;
+    for (int q = blockIdx.x; q < chunks; q += gridDim.x) {
+        const long long row = (long long)chunk_of(order, q) * 256 + threadIdx.x;
+        if (row < M) {
+            const int lo = __ldg(row_ptr + row), hi = __ldg(row_ptr + row + 1);
+            double acc = 0.0;
+            for (int e = lo; e < hi; e += BATCH) {
+                int c[BATCH];
+                double v[BATCH], xv[BATCH];
+#pragma unroll
+                for (int u = 0; u < BATCH; ++u) c[u] = e + u < hi ? __ldg(col_idx + e + u) : -1;
+#pragma unroll
+                for (int u = 0; u < BATCH; ++u) v[u] = e + u < hi ? __ldg(values + e + u) : 0.0;
+#pragma unroll
+                for (int u = 0; u < BATCH; ++u) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
+#pragma unroll
+                for (int u = 0; u < BATCH; ++u)
+                    if (c[u] >= 0) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+            }
+            acc *= scale;
+            sq = fma(acc, acc, sq);
+            y[row] = acc;
+            if (q < order.boundary_chunks)
+                for (int p = 0; p < peers.count; ++p)
+                    if (row >= peers.lo[p] && row < peers.hi[p]) peers.dst[p][row] = acc;
+        }
+        if (q < order.boundary_chunks) {  // CTA-uniform: this chunk feeds a neighbour
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) s_arrived = atomicAdd(as.bcounter, 1u);
+            __syncthreads();
+            if (s_arrived == (unsigned int)order.boundary_chunks - 1 && warp == 0) {  // every boundary row is stored
+                __threadfence();
+                if (lane < peers.count) st_release_sys(as.box[as.send_to[lane]] + 2 * 4 * as.world + as.rank, k + 1);
+                if (lane == 0) *as.bcounter = 0;
+            }
+        }
+    }
+    // ---- end: per-CTA partial, last CTA publishes the rank's sum for launch k in slot k%4 with tag k+1 ----
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    if (lane == 0) warp_sq[warp] = sq;
+    __threadfence_system();
+    __syncthreads();
+    if (warp == 0) {
+        unsigned int arrived = 0;
+        if (lane == 0) {
+            double total = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) total += warp_sq[w];
+            partials[blockIdx.x] = total;
+            __threadfence();
+            arrived = atomicAdd(as.counter, 1u);
+        }
+        arrived = __shfl_sync(0xffffffffu, arrived, 0);
+        if (arrived == gridDim.x - 1) {
+            __threadfence();
+            double part = 0.0;
+            for (int i = lane; i < (int)gridDim.x; i += 32) part += __ldcg(partials + i);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+            if (lane < as.world) {
+                unsigned long long *slot = as.box[lane] + 2 * ((int)(k & 3) * as.world + as.rank);
+                st_relaxed_sys(slot, (unsigned long long)__double_as_longlong(part));
+                st_release_sys(slot + 1, k + 1);
+            }
+            if (lane == 0) *as.counter = 0;
         }
     }
 }
@@ -1078,6 +1217,53 @@ int spmv_b200_csr_spmv_fused_mail(const spmv_b200_csr *A, const double *d_x, dou
     if (peers) ep.peers = *peers;
     ep.mail = *mail;
     return launch_fused(A, d_x, d_y, ep, as_stream(stream), -1);
+}
+
+int spmv_b200_csr_spmv_fused_async(const spmv_b200_csr *A, const double *d_x, double *d_y, double *d_partials,
+                                   const spmv_b200_peers_t *peers, const spmv_b200_async_t *as, void *stream) {
+    if (!A || !d_y || !d_partials || !as || (A->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_async: NULL argument");
+    if (A->max_row > kRowKernelMaxLen) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_async: rows of up to %d nonzeros only (longest row: %d)", kRowKernelMaxLen, A->max_row);
+    if (A->M == 0) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_async: a rank without rows cannot take part in the exchange");
+    if (as->world < 1 || as->world > SPMV_B200_MAX_RANKS || as->rank < 0 || as->rank >= as->world || !as->counter || !as->bcounter ||
+        !as->status || as->num_recv < 0 || as->num_recv > SPMV_B200_MAX_PEERS)
+        return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_async: bad exchange description (world %d, rank %d)", as->world, as->rank);
+    for (int r = 0; r < as->world; ++r)
+        if (!as->box[r]) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_async: mailbox of rank %d is NULL", r);
+    spmv_b200_peers_t ps;
+    ps.count = 0;
+    if (peers) ps = *peers;
+    if (ps.count < 0 || ps.count > SPMV_B200_MAX_PEERS) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_async: bad peer count %d", ps.count);
+    // boundary chunk intervals: the union of the peers' row ranges, in 256-row chunks, ascending and disjoint
+    ChunkOrder order;
+    order.count = 0;
+    order.boundary_chunks = 0;
+    std::vector<std::pair<int, int>> iv;
+    for (int p = 0; p < ps.count; ++p) {
+        if (ps.lo[p] < 0 || ps.hi[p] > A->M || ps.lo[p] > ps.hi[p] || as->send_to[p] < 0 || as->send_to[p] >= as->world)
+            return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_async: peer %d: bad row range or rank", p);
+        if (ps.hi[p] > ps.lo[p]) iv.emplace_back(ps.lo[p] >> 8, (ps.hi[p] + 255) >> 8);
+    }
+    std::sort(iv.begin(), iv.end());
+    for (const auto &r : iv) {
+        if (order.count > 0 && r.first <= order.hi[order.count - 1]) {
+            order.hi[order.count - 1] = std::max(order.hi[order.count - 1], r.second);
+        } else {
+            order.lo[order.count] = r.first;
+            order.hi[order.count] = r.second;
+            ++order.count;
+        }
+    }
+    for (int i = 0; i < order.count; ++i) order.boundary_chunks += order.hi[i] - order.lo[i];
+    const int g = fused_row_grid(A);
+    cudaStream_t st = as_stream(stream);
+#define AROW_CASE(B) case B: csr_row_async_kernel<B><<<g, 256, 0, st>>>(A->M, A->row_ptr, A->col_idx, A->values, d_x, d_y, d_partials, ps, *as, order); break;
+    switch (A->fused_batch > 0 ? A->fused_batch : A->row_batch) {
+        AROW_CASE(2) AROW_CASE(3) AROW_CASE(5) AROW_CASE(6) AROW_CASE(7)
+        default: csr_row_async_kernel<4><<<g, 256, 0, st>>>(A->M, A->row_ptr, A->col_idx, A->values, d_x, d_y, d_partials, ps, *as, order); break;
+    }
+#undef AROW_CASE
+    SPMV_TRY_CUDA(cudaGetLastError());
+    return SPMV_B200_OK;
 }
 
 int spmv_b200_csr_spmv_rows(const spmv_b200_csr *A, int row_begin, int row_end, const double *d_x, double *d_y,

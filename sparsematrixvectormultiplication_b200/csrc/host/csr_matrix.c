@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "resident.h"
 #include "spmv_b200.h"
 #include "utility.h"
 
@@ -25,6 +26,7 @@ void init_csr_matrix(CSRMatrix *mat) {
 }
 
 void free_csr_matrix(CSRMatrix *mat) {
+    resident_forget_csr(mat->row_ptr); /* a cached device copy of these arrays dies with them */
     FREE_CHECK(mat->row_ptr);
     FREE_CHECK(mat->col_idx);
     FREE_CHECK(mat->values);
@@ -199,9 +201,10 @@ void csr_matrix_vector_mult(int num_row, const int *row_ptr, const int *col_idx,
     if (num_row <= 0) return;
     const long long nnz = row_ptr[num_row];
     spmv_b200_csr *A = NULL;
-    int rc = spmv_b200_csr_upload(num_row, columns_referenced(col_idx, nnz), nnz, row_ptr, col_idx, values, &A);
+    int borrowed = 0;
+    int rc = resident_csr(num_row, columns_referenced(col_idx, nnz), nnz, row_ptr, col_idx, values, &A, &borrowed);
     if (rc == SPMV_B200_OK) rc = spmv_b200_csr_spmv_host(A, x, y, /*accumulate=*/1, SPMV_B200_ALGO_AUTO);
-    spmv_b200_csr_free(A);
+    if (!borrowed) spmv_b200_csr_free(A);
     if (rc != SPMV_B200_OK) poison(y, 0, num_row, "csr_matrix_vector_mult");
 }
 
@@ -215,11 +218,12 @@ static void ranged_product(const char *who, const int *row_ptr, const int *col_i
     const long long nnz = row_ptr[M];
     const int N = columns_referenced(col_idx, nnz);
     spmv_b200_csr *A = NULL;
-    int rc = spmv_b200_csr_upload(M, N, nnz, row_ptr, col_idx, values, &A);
+    int borrowed = 0;
+    int rc = resident_csr(M, N, nnz, row_ptr, col_idx, values, &A, &borrowed);
     double *full = rc == SPMV_B200_OK ? malloc((size_t)M * sizeof(double)) : NULL;
     if (rc == SPMV_B200_OK && !full) rc = SPMV_B200_ERR_NOMEM;
     if (rc == SPMV_B200_OK) rc = spmv_b200_csr_spmv_host(A, x, full, 0, SPMV_B200_ALGO_AUTO);
-    spmv_b200_csr_free(A);
+    if (!borrowed) spmv_b200_csr_free(A);
     for (int t = 0; t < num_threads; ++t) { /* only rows inside a range are written */
         if (rc == SPMV_B200_OK) memcpy(y + lo[t], full + lo[t], (size_t)(hi[t] - lo[t]) * sizeof(double));
         else poison(y, lo[t], hi[t], who);

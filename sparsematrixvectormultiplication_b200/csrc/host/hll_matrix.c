@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "resident.h"
 #include "spmv_b200.h"
 #include "utility.h"
 
@@ -28,6 +29,7 @@ void init_hll_matrix(HLLMatrix *hll) {
 
 void free_hll_matrix(HLLMatrix *hll) {
     if (!hll) return;
+    resident_forget_hll(hll->blocks); /* a cached device copy of these blocks dies with them */
     if (hll->blocks) {
         for (int b = 0; b < hll->num_blocks; ++b) {
             FREE_CHECK(hll->blocks[b].JA);
@@ -244,13 +246,13 @@ int prepare_thread_distribution_hll(const HLLMatrix *matrix, int num_threads, in
  * ---------------------------------------------------------------------------------------- */
 static int run_blocks(const ELLPACKBlock *blocks, int count, const double *x, double *y_out) {
     if (count <= 0) return SPMV_B200_OK;
-    HLLMatrix view = {count, (ELLPACKBlock *)blocks};
     long long rows = 0;
     for (int b = 0; b < count; ++b) rows += blocks[b].M;
     spmv_b200_hll *H = NULL;
-    int rc = spmv_b200_hll_upload(&view, (int)rows, blocks[0].N, &H);
+    int borrowed = 0;
+    int rc = resident_hll(blocks, count, (int)rows, blocks[0].N, &H, &borrowed);
     if (rc == SPMV_B200_OK) rc = spmv_b200_hll_spmv_host(H, x, y_out);
-    spmv_b200_hll_free(H);
+    if (!borrowed) spmv_b200_hll_free(H);
     if (rc != SPMV_B200_OK) {
         fprintf(stderr, "spmv_hll: GPU product failed: %s\n", spmv_b200_last_error());
         for (long long i = 0; i < rows; ++i) y_out[i] = NAN;
@@ -262,10 +264,35 @@ void spmv_hll_serial(int num_blocks, const ELLPACKBlock *blocks, const double *x
     run_blocks(blocks, num_blocks, x, y);
 }
 
+/* One upload and one product for the union of the per-thread block ranges (the reference's partitions tile
+ * [0, num_blocks) without gaps, src/hll_matrix.c:471-498); only rows inside a range are written. */
 static void ranged_blocks(const ELLPACKBlock *blocks, const double *x, double *y, int num_threads,
                           const int *lo, const int *hi) {
-    for (int t = 0; t < num_threads; ++t) /* rows of block b live at y[32 b ...] */
-        run_blocks(blocks + lo[t], hi[t] - lo[t], x, y + (size_t)lo[t] * HACK_SIZE);
+    if (num_threads <= 0) return;
+    int first = lo[0], last = hi[0];
+    for (int t = 1; t < num_threads; ++t) {
+        if (lo[t] < first) first = lo[t];
+        if (hi[t] > last) last = hi[t];
+    }
+    if (last <= first) return;
+    if (first != 0) { /* unusual: ranges that do not start at block 0 keep the simple path */
+        for (int t = 0; t < num_threads; ++t) run_blocks(blocks + lo[t], hi[t] - lo[t], x, y + (size_t)lo[t] * HACK_SIZE);
+        return;
+    }
+    double *full = malloc((size_t)last * HACK_SIZE * sizeof(double));
+    if (!full) {
+        for (int t = 0; t < num_threads; ++t)
+            for (size_t i = (size_t)lo[t] * HACK_SIZE; i < (size_t)hi[t] * HACK_SIZE; ++i) y[i] = NAN;
+        fprintf(stderr, "spmv_hll: out of host memory\n");
+        return;
+    }
+    run_blocks(blocks, last, x, full);
+    for (int t = 0; t < num_threads; ++t) {
+        size_t rows = 0;
+        for (int b = lo[t]; b < hi[t]; ++b) rows += (size_t)blocks[b].M;
+        memcpy(y + (size_t)lo[t] * HACK_SIZE, full + (size_t)lo[t] * HACK_SIZE, rows * sizeof(double));
+    }
+    free(full);
 }
 
 void spmv_hll(const ELLPACKBlock *blocks, const double *x, double *y, int num_threads,

@@ -166,6 +166,14 @@ class DeviceCSR:
                                                       C.byref(peers) if peers is not None else None, C.byref(mail),
                                                       _stream(stream)))
 
+    def spmv_fused_async(self, x_ptr, y_ptr, partials, exchange, peers=None, stream=None):
+        """The asynchronous fused launch (spmv_b200_csr_spmv_fused_async): boundary rows first, lagged scale."""
+        def raw(v):
+            return C.c_void_p(v) if isinstance(v, int) else _ptr(v)
+        N.check(N.lib().spmv_b200_csr_spmv_fused_async(self._h, raw(x_ptr), raw(y_ptr), raw(partials),
+                                                       C.byref(peers) if peers is not None else None, C.byref(exchange),
+                                                       _stream(stream)))
+
     def spmv_rows(self, row_begin, row_end, x, y, stream=None):
         N.check(N.lib().spmv_b200_csr_spmv_rows(self._h, int(row_begin), int(row_end), _ptr(x), _ptr(y), _stream(stream)))
         return y

@@ -307,3 +307,123 @@ class FusedPowerIteration(PowerIteration):
             self.box_t = None
             self.box.close()
             self.box = None
+
+
+class AsyncPowerIteration(PowerIteration):
+    """The fused iteration without any per-iteration rendezvous (include/spmv_b200.h: spmv_b200_csr_spmv_fused_async).
+
+    x lives in a ring of three peer-mappable buffers; a launch computes the rows its neighbours reference first and
+    raises a halo tag in their mailboxes as soon as those rows are stored; the scale factor lags one launch
+    (launch k multiplies by 1/sqrt(S[k-2]), S[j] = |output of launch j|^2 over all ranks), so a launch only ever waits
+    for things that finished a whole launch ago.  The iterate keeps the direction of the power method and stays bounded:
+        lambda_K = sqrt(S[K-1] * S[K-3] / S[K-2]),   v_K = x_K / sqrt(S[K-1])        (K >= 3 launches)
+    One launch per iteration, no collective call, no rank-to-rank wait on the critical path."""
+
+    def __init__(self, kind, p0, p1=0, p2=0, seed=0x5EED, group=None, parts=None, single=False):
+        super().__init__(kind, p0, p1, p2, seed=seed, exchange="halo", group=group, parts=parts, single=single)
+        from . import _native as N
+        d = self.dev
+        cu = self.x.device
+        del self.x, self.y
+        nbytes = 8 * self.N
+        self.buf = [d.PeerBuffer(nbytes) for _ in range(3)]
+        self.xs = [b.as_tensor() for b in self.buf]
+        self.box = d.PeerBuffer(N.ASYNC_MAILBOX_BYTES)
+        self.box_t = self.box.as_tensor("<i8", 8)
+        self.sync = torch.zeros(4, dtype=torch.int32, device=cu)   # [0] CTA counter, [1] boundary counter, [2] status
+        self.ex = N.Async()
+        self.ex.world, self.ex.rank = self.world, self.rank
+        self.ex.counter = self.sync.data_ptr()
+        self.ex.bcounter = self.sync.data_ptr() + 4
+        self.ex.status = self.sync.data_ptr() + 8
+        senders = sorted({peer for peer, _, _ in self.plan.recvs})
+        self.ex.num_recv = len(senders)
+        for i, peer in enumerate(senders):
+            self.ex.recv_from[i] = peer
+        self.peers = [N.Peers() for _ in range(3)]
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, ([b.handle_bytes() for b in self.buf], self.box.handle_bytes()), group=self.group)
+            for r in range(self.world):
+                self.ex.box[r] = self.box.ptr.value if r == self.rank else self.box.open_peer(handles[r][1])
+            assert len(self.plan.sends) <= 7
+            for slot in range(3):
+                ps = self.peers[slot]
+                ps.count = len(self.plan.sends)
+                for i, (peer, lo, hi) in enumerate(self.plan.sends):
+                    base = self.buf[slot].open_peer(handles[peer][0][slot])
+                    ps.dst[i] = base + 8 * self.row_begin
+                    ps.lo[i], ps.hi[i] = lo - self.row_begin, hi - self.row_begin
+                    self.ex.send_to[i] = peer
+        else:
+            self.ex.box[0] = self.box.ptr.value
+        self.partials = torch.zeros(self.A.partials_count(), dtype=torch.float64, device=cu)
+        self.k = 0
+        self.launches_per_step = 1
+        self.reset(1.0)
+
+    def reset(self, value=1.0):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)   # nobody may still be writing tags or rows of the previous run
+        for t in self.xs:
+            self.dev.vec_fill(t, value)
+        self.box_t.zero_()
+        self.sync.zero_()
+        self.k = 0
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def step(self):
+        cur, nxt = self.k % 3, (self.k + 1) % 3
+        self.ex.iteration = self.k
+        self.A.spmv_fused_async(self.xs[cur].data_ptr(), self.xs[nxt].data_ptr() + 8 * self.row_begin, self.partials, self.ex,
+                                peers=self.peers[nxt])
+        self.k += 1
+
+    def _sums(self):
+        """S[K-1], S[K-2], S[K-3] (0.0 where K is too small), each added in rank order from MY mailbox."""
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        if int(self.sync[2].item()) != 0:
+            raise RuntimeError("an exchange wait timed out: a peer rank did not finish its launch")
+        flat = self.box_t.tolist()
+        out = []
+        for back in (1, 2, 3):
+            j = self.k - back
+            if j < 0:
+                out.append(0.0)
+                continue
+            total = 0.0
+            for r in range(self.world):
+                at = 2 * ((j & 3) * self.world + r)
+                if flat[at + 1] != j + 1:
+                    raise RuntimeError(f"mailbox slot of launch {j}, rank {r} carries tag {flat[at + 1]}")
+                total += torch.tensor(flat[at], dtype=torch.int64).view(torch.float64).item()
+            out.append(total)
+        return out
+
+    def eigenvalue_estimate(self) -> float:
+        s1, s2, s3 = self._sums()
+        if self.k >= 3:
+            return (s1 * s3 / s2) ** 0.5
+        if self.k == 2:
+            return (s1 / s2) ** 0.5       # no scaling yet: |u_2| / |u_1|
+        raise ValueError("eigenvalue_estimate needs at least two iterations")
+
+    def normalized_x(self) -> torch.Tensor:
+        s1, _, _ = self._sums()
+        return self.xs[self.k % 3] / (s1 ** 0.5)
+
+    def close(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        self.xs = []
+        self.box_t = None
+        for b in self.buf:
+            b.close()
+        self.box.close()
+        self.buf = []

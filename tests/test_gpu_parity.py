@@ -708,3 +708,51 @@ def test_fp32_path_within_1e_5(dev, checker, kind):
     B = dev.DeviceCSR.upload(M, N, rp, ci, va)
     with pytest.raises(Exception):
         B.spmv_f32(x32, yacc)                            # enable_f32 not called
+
+
+def test_resident_cache_of_the_drop_in_api(dev, checker):
+    """The reference's stateless product signatures upload the matrix on every call; with the opt-in cache
+    (spmv_b200_resident_cache) the second call on the same arrays reuses the device copy.  Same results, the
+    cached copy dies with free_csr_matrix / free_hll_matrix, new arrays are detected."""
+    import time
+    from sparsematrixvectormultiplication_b200 import _native as N
+    from sparsematrixvectormultiplication_b200 import host
+    rng = np.random.default_rng(5)
+    M = Ncols = 200_000
+    coo = random_coo(rng, M, Ncols, 2_000_000, dup=False)
+    pre = host.PreMatrix(M, Ncols, coo.I, coo.J, coo.val)
+    csr = host.convert_in_csr(pre)
+    hll = host.convert_to_hll(pre)
+    x = rng.standard_normal(Ncols)
+    y_ref = checker.spmv_csr_serial(csr.row_ptr, csr.col_idx, csr.values, x)
+    scale = abs_row_sums(checker, csr.row_ptr, csr.col_idx, csr.values, x)
+    before = N.lib().spmv_b200_resident_cache(1)
+    try:
+        times = []
+        for _ in range(3):
+            y = np.zeros(M)
+            t0 = time.perf_counter()
+            host.csr_matrix_vector_mult(csr.M, csr.row_ptr, csr.col_idx, csr.values, x, y)
+            times.append(time.perf_counter() - t0)
+            assert_close(y, y_ref, scale, "cached csr_matrix_vector_mult")
+        assert min(times[1:]) < times[0], f"cached calls are not faster: {times}"
+        starts, ends = host.prepare_thread_distribution(csr.M, csr.row_ptr, 8, csr.nz)
+        y = np.full(M, np.nan)
+        host.spvm_csr_parallel(csr.row_ptr, csr.col_idx, csr.values, x, y, len(starts), starts, ends)
+        assert_close(y, y_ref, scale, "cached spvm_csr_parallel")
+        yh = np.full(hll.num_blocks * 32, np.nan)
+        for _ in range(2):
+            host.spmv_hll_serial(hll, x, yh)
+            assert_close(yh[:M], y_ref, scale, "cached spmv_hll_serial")
+        bs, be = host.prepare_thread_distribution_hll(hll, 8)
+        yh[:] = np.nan
+        host.spmv_hll(hll, x, yh, len(bs), bs, be)
+        assert_close(yh[:M], y_ref, scale, "cached spmv_hll over 8 block ranges: one upload, one product")
+        # another matrix in NEW arrays is not confused with the cached one
+        csr2 = host.convert_in_csr(host.PreMatrix(M, Ncols, coo.I, coo.J, -coo.val))
+        y = np.zeros(M)
+        host.csr_matrix_vector_mult(csr2.M, csr2.row_ptr, csr2.col_idx, csr2.values, x, y)
+        assert_close(y, -y_ref, scale, "a different matrix after a cached one")
+    finally:
+        N.lib().spmv_b200_resident_cache(before)
+        N.lib().spmv_b200_resident_drop()
