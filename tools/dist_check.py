@@ -92,6 +92,22 @@ def main():
     print(f"rank {rank}/{world} async free-running 40 launches: lambda {lam_free:.15g} vs {ref.eigenvalue_estimate():.15g} -> {'ok' if good else 'FAIL'}", flush=True)
     ok = ok and good
     G.close()
+    # stress: short launches (small grid), many of them, no host synchronisation: a halo row or a sum that was read
+    # before it landed would throw lambda off
+    small = 24
+    S = AsyncPowerIteration(synth.SYNTH_LAP3D, small)
+    R = PowerIteration(synth.SYNTH_LAP3D, small, single=True)
+    for _ in range(600):
+        S.step()
+    for _ in range(600):
+        R.step()
+    good = abs(S.eigenvalue_estimate() - R.eigenvalue_estimate()) / R.eigenvalue_estimate() <= 1e-12
+    vs, lo, hi = S.normalized_x(), S.row_begin, S.row_end
+    xerr = float((vs[lo:hi] - R.x[lo:hi]).abs().max() / R.x.abs().max())
+    good = good and xerr <= 1e-11
+    print(f"rank {rank}/{world} async stress {small}^3 x 600 launches: lambda {S.eigenvalue_estimate():.15g} vs {R.eigenvalue_estimate():.15g}, x err {xerr:.2e} -> {'ok' if good else 'FAIL'}", flush=True)
+    ok = ok and good
+    S.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

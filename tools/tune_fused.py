@@ -12,7 +12,7 @@ from tune import timeit  # noqa: E402
 
 torch.cuda.set_device(0)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 384
-for batch in (0, 2, 5):
+for batch in (2, 5):
     os.environ["SPMV_B200_ROW_BATCH"] = str(batch)
     os.environ["SPMV_B200_FUSED_BATCH"] = str(batch)
     A = device.DeviceCSR.synth(synth.SYNTH_LAP3D, n)
