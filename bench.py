@@ -335,7 +335,7 @@ def bench_single_gpu(args):
     assert torch.equal(yh.cuda(), y), "end-to-end result differs from the resident product"
     e2e = {"value": 2.0 * nnz / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * info.N, "d2h_bytes_per_step": 8 * M,
            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-           "api": "spmv_b200_csr_spmv_host (pinned host x -> device, product, device -> pinned host y, synchronous)"}
+           "api": "spmv_b200_csr_spmv_host (one synchronous C-ABI call: pinned host x -> device, product, device -> pinned host y; upload, product and download pipelined over row windows on three streams)"}
     log(f"[bench] e2e: {e2e['value']:.1f} GFLOP/s ({e2e_s*1e3:.2f} ms/step)")
 
     others = {}

@@ -420,6 +420,87 @@ def test_full_size_uniform_8m_properties(dev, checker):
     assert torch.equal(y2, y_csr * 2.0)
 
 
+def test_full_size_rmat_24_properties(dev, checker):
+    """Config 4: R-MAT scale 24, 16 edges per row on average, longest row > 100 000 (skewed-row load balancing).
+    The automatic choice (row-binned kernel + long-row fragments) against an independent fp64 reference built from
+    torch ops (index_add of values * x[cols] by row), the other kernels within tolerance, sampled rows exactly
+    against the serial oracle, linearity, run-to-run determinism."""
+    import torch
+    from sparsematrixvectormultiplication_b200 import synth
+    scale = 24
+    M = 1 << scale
+    rp, ci, va = synth.rmat_csr_device(scale, 16)
+    lengths = rp[1:] - rp[:-1]
+    assert int(lengths.max()) > 100_000 and int(rp[-1]) > 200_000_000
+    A = dev.DeviceCSR.wrap(M, M, rp, ci, va)
+    info = A.info()
+    assert info.auto_algo == dev.ALGO_BINNED and info.max_row_nnz == int(lengths.max())
+    x = torch.empty(M, dtype=torch.float64, device="cuda")
+    dev.synth_vector(x, 777)                                    # x in (0, 1], values in (0, 1]: everything positive
+    y = torch.empty(M, dtype=torch.float64, device="cuda")
+    A.spmv(x, y)
+    rows = torch.repeat_interleave(torch.arange(M, device="cuda"), lengths.long())
+    ref = torch.zeros(M, dtype=torch.float64, device="cuda").index_add_(0, rows, va * x[ci.long()])
+    del rows
+    nonempty = ref > 0
+    assert float(((y - ref).abs()[nonempty] / ref[nonempty]).max()) <= 4 * TOL, "binned kernel vs torch index_add reference"
+    assert bool((y[~nonempty] == 0).all()), "empty rows give exactly 0"
+    y2 = torch.empty_like(y)
+    A.spmv(x, y2)
+    assert torch.equal(y, y2), "run-to-run deterministic (fixed-order long-row combine, no atomics)"
+    for algo in (dev.ALGO_TILE, dev.ALGO_STREAM):
+        A.spmv(x, y2, algo=algo)
+        assert float(((y - y2).abs()[nonempty] / ref[nonempty]).max()) <= 4 * TOL, f"algo {algo}"
+    A.spmv(x * 2.0, y2)
+    assert torch.equal(y2, y * 2.0), "linearity under power-of-two scaling is exact"
+    # sampled rows (the longest, a few random ones) exactly against the serial oracle on the downloaded rows
+    xh = x.cpu().numpy()
+    picks = [int(lengths.argmax())] + [int(v) for v in torch.randint(0, M, (40,), generator=torch.Generator().manual_seed(1))]
+    for r in picks:
+        a, b = int(rp[r]), int(rp[r + 1])
+        cols, vals = ci[a:b].cpu().numpy(), va[a:b].cpu().numpy()
+        y_ref = checker.spmv_csr_serial(np.array([0, b - a], np.int32), cols, vals, xh)[0]
+        assert abs(float(y[r]) - y_ref) <= TOL * max(y_ref, 1e-300), f"row {r} ({b - a} nonzeros)"
+    A.close()
+
+
+def test_full_size_lap3d_512(dev, checker):
+    """Config 5's matrix on ONE GPU: 134 M rows, 938 M nnz (11.8 GB).  x = 1 gives exact small integers (6 - number of
+    neighbours); with the ramp vector the automatic choice, the row kernel and the stream kernel must agree bit for bit
+    (all sum rows of 7 in the serial order), HLL too; a window of rows is checked against the serial oracle."""
+    import torch
+    from sparsematrixvectormultiplication_b200 import synth
+    n = 512
+    A = dev.DeviceCSR.synth(synth.SYNTH_LAP3D, n)
+    info = A.info()
+    assert (info.M, info.nnz) == (n ** 3, 937_951_232) and info.max_row_nnz == 7
+    x = torch.ones(n ** 3, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    A.spmv(x, y)
+    # 6 on the diagonal, -1 per neighbour: the row sum is the number of missing neighbours (0..3), exact
+    idx = torch.arange(n ** 3, device="cuda")
+    i, j, k = idx // (n * n), (idx // n) % n, idx % n
+    missing = sum(((c == 0).long() + (c == n - 1).long()) for c in (i, j, k)).double()
+    assert torch.equal(y, missing)
+    del idx, i, j, k, missing
+    xr = 1.0 + (torch.arange(n ** 3, device="cuda") % 7).double() / 8.0
+    y_auto, y_alt = torch.empty_like(x), torch.empty_like(x)
+    A.spmv(xr, y_auto)
+    for algo in (dev.ALGO_ROW, dev.ALGO_STREAM):
+        A.spmv(xr, y_alt, algo=algo)
+        assert torch.equal(y_auto, y_alt), f"algo {algo}: rows of 7 are summed in the serial order by every stencil kernel"
+    lo = 77 * n * n + 5
+    rp, ci, va = synth.lap3d_csr(n, lo, lo + 5000)            # numpy twin of the device generator, rows [lo, lo + 5000)
+    y_ref = checker.spmv_csr_serial(rp, ci, va, xr.cpu().numpy())
+    assert np.array_equal(bits(y_auto[lo:lo + 5000].cpu().numpy()), bits(y_ref)), "bit-exact with csr_matrix_vector_mult"
+    H = A.to_hll()
+    assert H.info().max_maxnz == 7
+    H.spmv(xr, y_alt)
+    assert torch.equal(y_auto, y_alt), "HLL (padding adds 0.0) gives the same bits"
+    H.close()
+    A.close()
+
+
 def test_fused_power_iteration_matches_the_oracle(dev, port):
     """One launch per iteration (product + lazy normalisation + |w|^2 partials) against the oracle's
     y = A x; lambda = |y|; x = y / lambda."""
