@@ -65,9 +65,20 @@ __device__ __forceinline__ void ldg_stream_s32x8(const int *p, int (&c)[8]) {
                  : "l"(p));
 }
 
+// SPMV_STREAM_EVICT_FIRST: the scalar stream loads also carry an L2 evict-first policy (createpolicy + cache_hint)
+__device__ __forceinline__ unsigned long long policy_stream() {
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));  // pure: hoisted out of loops
+    return p;
+}
+
 __device__ __forceinline__ double ldg_stream_f64(const double *p) {
     double r;
+#ifdef SPMV_STREAM_EVICT_FIRST
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(policy_stream()));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+#endif
     return r;
 }
 
@@ -80,7 +91,11 @@ __device__ __forceinline__ double ldg_stream_f64(const float *p) {
 
 __device__ __forceinline__ int ldg_stream_s32(const int *p) {
     int r;
+#ifdef SPMV_STREAM_EVICT_FIRST
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(policy_stream()));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+#endif
     return r;
 }
 

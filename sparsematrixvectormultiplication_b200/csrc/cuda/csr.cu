@@ -1328,6 +1328,14 @@ int spmv_b200_csr_enable_f32(spmv_b200_csr *A, void *stream) {
         to_f32_kernel<<<blocks_for(A->nnz, 256), 256, 0, as_stream(stream)>>>(A->values, A->values32, A->nnz);
         SPMV_TRY_CUDA(cudaGetLastError());
     }
+    A->row_batch32 = A->row_batch;
+    if (A->max_row <= kRowKernelMaxLen && A->nnz >= kAutotuneMinNnz && env_int("SPMV_B200_AUTOTUNE", 1) &&
+        env_int("SPMV_B200_ROW_BATCH", 0) == 0) {  // the best batch differs with the element size: time it again
+        A->row_batch32 = tune_batch(A->M, A->N, A->row_batch, as_stream(stream), [&](int batch, double *x, double *y) {
+            return launch_rows<float>(0, A->M, A->row_ptr, A->col_idx, A->values32, reinterpret_cast<const float *>(x),
+                                      reinterpret_cast<float *>(y), batch, 0, as_stream(stream));
+        });
+    }
     return SPMV_B200_OK;
 }
 
@@ -1346,7 +1354,7 @@ int spmv_b200_csr_spmv_f32(const spmv_b200_csr *A, const float *d_x, float *d_y,
         default: return fail(SPMV_B200_ERR_INVALID, "csr_spmv_f32: algo %d has no fp32 kernel (AUTO, VECTOR, BINNED, ROW)", algo);
     }
     cudaStream_t s = as_stream(stream);
-    if (path == kPathRow) return launch_rows<float>(0, A->M, A->row_ptr, A->col_idx, A->values32, d_x, d_y, A->row_batch, accumulate, s);
+    if (path == kPathRow) return launch_rows<float>(0, A->M, A->row_ptr, A->col_idx, A->values32, d_x, d_y, A->row_batch32, accumulate, s);
     if (path == kPathVector)
         return launch_vector<float>(0, A->M, A->row_ptr, A->col_idx, A->values32, d_x, d_y, pick_vector_width(A->nnz, A->M), accumulate, s);
     return launch_binned<float>(A, A->values32, d_x, d_y, accumulate, s);

@@ -66,6 +66,7 @@ struct spmv_b200_csr {
     spmv::BinPlan bins;
     int max_row = 0;     // longest row (plan time)
     int row_batch = 4;   // csr_row_kernel: column/value/gather batch per thread (tuned at plan time on large matrices)
+    int row_batch32 = 4; // the same for fp32 storage (tuned by spmv_b200_csr_enable_f32)
     bool short_rows_stream = false;  // plan-time timing found the stream kernel faster than every row-kernel batch
     int fused_batch = 0;             // fused iterated product: 0 = fused stream kernel, else batch of the fused row kernel
     // stream kernel launch shape
@@ -95,6 +96,7 @@ struct spmv_b200_hll {
     spmv::HllTile *tiles = nullptr;
     int stream_grid = 0;
     int row_batch = 4;   // hll_row_kernel batch (tuned at plan time on large matrices)
+    int row_batch32 = 4; // the same for fp32 storage (tuned by spmv_b200_hll_enable_f32)
     bool narrow_stream = false;  // plan-time timing found the stream kernel faster than every row-kernel batch
     double *stage_x = nullptr;
     double *stage_y = nullptr;

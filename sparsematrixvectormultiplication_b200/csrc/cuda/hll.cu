@@ -184,11 +184,12 @@ using namespace spmv;
 
 template <typename V>
 static int hll_launch_rows_t(const spmv_b200_hll *H, const V *AS, int hack_begin, int hack_end, const V *d_x, V *d_y,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, int batch = -1) {
     if (hack_end <= hack_begin) return SPMV_B200_OK;
+    if (batch < 0) batch = sizeof(V) == 4 ? H->row_batch32 : H->row_batch;
     const unsigned int g = blocks_for(hack_end - hack_begin, 8);
 #define HROW_CASE(B) case B: hll_row_kernel<B, V><<<g, 256, 0, stream>>>(hack_begin, hack_end, H->hack_off, H->JA, AS, d_x, d_y, H->M); break;
-    switch (H->row_batch) {
+    switch (batch) {
         HROW_CASE(1) HROW_CASE(2) HROW_CASE(3) HROW_CASE(5) HROW_CASE(6) HROW_CASE(7) HROW_CASE(8)
         default: hll_row_kernel<4, V><<<g, 256, 0, stream>>>(hack_begin, hack_end, H->hack_off, H->JA, AS, d_x, d_y, H->M); break;
     }
@@ -522,6 +523,14 @@ int spmv_b200_hll_enable_f32(spmv_b200_hll *H, void *stream) {
     if (H->slots) {
         hll_to_f32_kernel<<<blocks_for(H->slots, 256), 256, 0, as_stream(stream)>>>(H->AS, H->AS32, H->slots);
         SPMV_TRY_CUDA(cudaGetLastError());
+    }
+    H->row_batch32 = H->row_batch;
+    if (H->max_width <= kRowKernelMaxLen && H->slots >= (1 << 22) && env_int("SPMV_B200_AUTOTUNE", 1) &&
+        env_int("SPMV_B200_HLL_ROW_BATCH", 0) == 0) {
+        H->row_batch32 = tune_batch(H->M, H->N, H->row_batch, as_stream(stream), [&](int batch, double *x, double *y) {
+            return hll_launch_rows_t<float>(H, H->AS32, 0, H->num_hacks, reinterpret_cast<const float *>(x),
+                                            reinterpret_cast<float *>(y), as_stream(stream), batch);
+        });
     }
     return SPMV_B200_OK;
 }
