@@ -99,6 +99,10 @@ int spmv_b200_device_info(char *name, int len, int *sm_count, long long *l2_byte
  * spmv_b200_resident_drop() (a sampled fingerprint cannot see every change).  Also switched on by the environment
  * variable SPMV_B200_RESIDENT=1. */
 int spmv_b200_resident_cache(int enable); /* returns the previous setting */
+/* Plan-time timing of kernel candidates (a few products on scratch vectors when a large matrix is uploaded; only
+ * candidates that give the same bits compete).  On by default; SPMV_B200_AUTOTUNE=0 or this switch turns it off, e.g. for
+ * a matrix that is used once.  Returns the previous setting. */
+int spmv_b200_autotune(int enable);
 void spmv_b200_resident_drop(void);       /* forget every cached device copy */
 
 /* ---- CSR ----------------------------------------------------------------------------- */

@@ -139,6 +139,7 @@ SIGNATURES = {
     "spmv_b200_hll_spmv_f32": (_I, [_V, _V, _V, _V]),
     "spmv_b200_hll_spmv_host_f32": (_I, [_V, _V, _V]),
     "spmv_b200_resident_cache": (_I, [_I]),
+    "spmv_b200_autotune": (_I, [_I]),
     "spmv_b200_resident_drop": (None, []),
     "spmv_b200_csr_time": (_I, [_V, _V, _V, _I, _I, _I, c_dbl_p, c_dbl_p]),
     "spmv_b200_hll_time": (_I, [_V, _V, _V, _I, _I, _I, c_dbl_p, c_dbl_p]),

@@ -1,20 +1,21 @@
-// csr.cu -- CSR y = A*x for sm_100a (B200): kernels, plan builder and the C-ABI entry points.
+// csr.cu -- CSR y = A*x for sm_100a (B200): kernels, plans and the C-ABI entry points.
 //
 // Replaces the reference's spmv_csr_{naive,warp,warp_shared_memory}_kernel
 // (reference cuda_src/csr_matrix_cuda.cu:122-241, launched from main_cuda.cu:166,238,317).
 //
-// Design: SpMV is an HBM-bound gather (0.15 flop/B), so no tensor cores.
-//   * csr_tile_kernel   -- adaptive row-binned "stream" kernel.  Rows are binned at plan time into
-//       tiles of ~D merge items (rows + nonzeros).  A CTA streams its tile's values/columns with
-//       coalesced 256-bit / 128-bit no-allocate, evict-first loads, gathers x through the
-//       read-only path, parks the products in shared memory, then reduces them per row: one thread
-//       per row for short rows (sequential, left-to-right, no FMA contraction => bit-identical to
-//       the reference's serial loop), or 2..32 lanes per row with a shuffle reduction when a tile
-//       holds few, longer rows.
-//   * csr_long_* kernels -- rows longer than L are split into fixed 8192-nonzero fragments, one
-//       CTA each, combined in a fixed order by a second tiny kernel (deterministic, no atomics).
-//   * csr_vector_kernel -- the plain vector-per-row kernel with shuffle reduction; needs no plan,
-//       works on raw device arrays (drop-in for the reference's warp kernel launch).
+// SpMV is an HBM-bound gather (0.15 flop/B): no tensor cores.  Kernels in this file:
+//   * csr_row_kernel<BATCH,V>     -- one THREAD per row, L1-resident stream, serial order (bit-identical to the reference's
+//       loop).  The automatic choice when no row exceeds 12 nonzeros (stencils); BATCH is timed at plan time.
+//   * csr_row_fused_kernel / csr_row_async_kernel -- the same with the fused tail of the iterated product (scale,
+//       |w|^2 partials, NVLink peer stores, mailbox / asynchronous exchange).
+//   * csr_vector_kernel<VEC,V>    -- VEC lanes per row, batched gathers, shuffle reduction; needs no plan, works on raw
+//       device arrays (drop-in for the reference's warp kernel launch).  Automatic choice for longer, even rows.
+//   * csr_binned_kernel<V> + csr_long_fragment_kernel + csr_long_combine_kernel -- rows sorted by length class, 1..32
+//       lanes per row in one launch; rows above 2048 nonzeros split into 8192-nonzero fragments combined in a fixed
+//       order (deterministic, no atomics).  Automatic choice for skewed rows.
+//   * csr_tile_kernel             -- first-generation row-binned tile kernel (products parked in shared memory);
+//       explicit SPMV_B200_ALGO_TILE only.
+// V = storage type (double, or float with double arithmetic).  The TMA-pipelined stream kernels live in stream.cu.
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 

@@ -26,6 +26,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "handles.cuh"
@@ -501,7 +502,10 @@ __global__ void hll_tiles_kernel(int num_tiles, int num_hacks, const int *__rest
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
+static int g_autotune = -1;  // -1: follow SPMV_B200_AUTOTUNE (default on)
+
 int env_int(const char *name, int fallback) {
+    if (g_autotune >= 0 && std::strcmp(name, "SPMV_B200_AUTOTUNE") == 0) return g_autotune;
     const char *v = std::getenv(name);
     if (!v || !*v) return fallback;
     return std::atoi(v);
@@ -671,3 +675,9 @@ int stream_launch_hll(const spmv_b200_hll *H, const double *x, double *y, cudaSt
 }
 
 }  // namespace spmv
+
+extern "C" int spmv_b200_autotune(int enable) {
+    const int before = spmv::env_int("SPMV_B200_AUTOTUNE", 1) ? 1 : 0;
+    spmv::g_autotune = enable ? 1 : 0;
+    return before;
+}

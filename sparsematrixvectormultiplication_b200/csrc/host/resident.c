@@ -68,7 +68,12 @@ void spmv_b200_resident_drop(void) {
 int resident_csr(int M, int N, long long nnz, const int *row_ptr, const int *col_idx, const double *values,
                  spmv_b200_csr **out, int *borrowed) {
     *borrowed = 0;
-    if (!enabled()) return spmv_b200_csr_upload(M, N, nnz, row_ptr, col_idx, values, out);
+    if (!enabled()) { /* used once: timing kernel candidates at upload would cost more than it can save */
+        const int tune = spmv_b200_autotune(0);
+        const int rc = spmv_b200_csr_upload(M, N, nnz, row_ptr, col_idx, values, out);
+        spmv_b200_autotune(tune);
+        return rc;
+    }
     const uint64_t print = mix(sample_arrays(col_idx, values, nnz), (uint64_t)(uint32_t)row_ptr[M]);
     if (g_csr.handle && g_csr.row_ptr == row_ptr && g_csr.col_idx == col_idx && g_csr.values == values && g_csr.M == M &&
         g_csr.N == N && g_csr.nnz == nnz && g_csr.print == print) {
@@ -106,7 +111,12 @@ static uint64_t sample_blocks(const ELLPACKBlock *blocks, int count) {
 int resident_hll(const ELLPACKBlock *blocks, int count, int rows, int N, spmv_b200_hll **out, int *borrowed) {
     *borrowed = 0;
     HLLMatrix view = {count, (ELLPACKBlock *)blocks};
-    if (!enabled()) return spmv_b200_hll_upload(&view, rows, N, out);
+    if (!enabled()) {
+        const int tune = spmv_b200_autotune(0);
+        const int rc = spmv_b200_hll_upload(&view, rows, N, out);
+        spmv_b200_autotune(tune);
+        return rc;
+    }
     const uint64_t print = sample_blocks(blocks, count);
     if (g_hll.handle && g_hll.blocks == blocks && g_hll.count == count && g_hll.rows == rows && g_hll.N == N &&
         g_hll.print == print) {
