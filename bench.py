@@ -606,10 +606,58 @@ def bench_multi_gpu(args):
             kms, kper = time_device(lambda: P.A.spmv_fused(xs[0].data_ptr(), xs[1].data_ptr() + 8 * row_begin, partials=P.partials),
                                     max(5, min(args.steps, 50)), 3, None, world)
             results["product_only_ms"] = kms
+            if getattr(P, "peers", None) and P.peers[1] is not None:   # the same launch with the NVLink peer stores of the boundary rows
+                pms, _ = time_device(lambda: P.A.spmv_fused(xs[0].data_ptr(), xs[1].data_ptr() + 8 * row_begin, partials=P.partials,
+                                                            peers=P.peers[1]), max(5, min(args.steps, 50)), 3, None, world)
+                results["product_with_peer_stores_ms"] = pms
+                if rank == 0:
+                    log(f"[bench] {world} GPUs local fused product alone {kms:.3f} ms, with peer stores {pms:.3f} ms")
         if hasattr(P, "close"):
             P.close()
         del P
         torch.cuda.empty_cache()
+    # ---- the plain product y = A x, row-partitioned (no exchange: x is replicated), CSR and HLL, for the other
+    # single-GPU shapes: every rank owns an nnz-balanced row range (HLL: cut on 32-row hack boundaries, as the
+    # reference cuts HLL work, src/hll_matrix.c:471-498); a step is one product on every rank, time = max over ranks.
+    partitioned = {}
+    try:
+        from sparsematrixvectormultiplication_b200 import partition
+        for name, kind, p0 in (("lap2d_4096", synth.SYNTH_LAP2D, 4096), (f"lap3d_{n}", synth.SYNTH_LAP3D, n)):
+            parts = partition.hack_aligned(partition.synth_partition(kind, p0, 0, 0, world),
+                                           p0 * p0 if kind == synth.SYNTH_LAP2D else p0 ** 3)
+            if len(parts) != world:
+                continue
+            lo, hi = parts[rank]
+            A = device.DeviceCSR.synth(kind, p0, row_begin=lo, row_end=hi)
+            ia = A.info()
+            x = torch.ones(ia.N, dtype=torch.float64, device="cuda")
+            y = torch.empty(ia.M, dtype=torch.float64, device="cuda")
+            nnz_global = synth.row_offset(kind, p0, 0, 0, parts[-1][1])
+            steps = max(5, min(args.steps, 50))
+            ms, _ = time_device(lambda: A.spmv(x, y), steps, args.warmup, None, world)
+            H = A.to_hll()
+            hi_ = H.info()
+            ms_h, _ = time_device(lambda: H.spmv(x, y), steps, args.warmup, None, world)
+            # bytes a rank really streams: its rows + the referenced part of x (about rows + 2 halo planes)
+            local_csr = 12 * ia.nnz + 4 * (ia.M + 1) + 8 * ia.M + 8 * min(ia.N, ia.M + 2 * (p0 if kind == synth.SYNTH_LAP2D else p0 * p0))
+            local_hll = local_csr - 12 * ia.nnz - 4 * (ia.M + 1) + 12 * hi_.slots + 8 * (hi_.num_hacks + 1)
+            partitioned[name] = {
+                "csr": {"ms_per_product": ms, "gflops": 2.0 * nnz_global / (ms * 1e-3) / 1e9, "rank0_gbs": local_csr / (ms * 1e-3) / 1e9,
+                        "kernel": device.ALGO_NAMES[ia.auto_algo]},
+                "hll": {"ms_per_product": ms_h, "gflops": 2.0 * nnz_global / (ms_h * 1e-3) / 1e9, "rank0_gbs": local_hll / (ms_h * 1e-3) / 1e9,
+                        "kernel": device.HLL_KERNEL_NAMES[hi_.auto_kernel]},
+                "rows_rank0": ia.M, "nnz_global": nnz_global}
+            if rank == 0:
+                log(f"[bench] {world} GPUs {name} row-partitioned product: CSR {partitioned[name]['csr']['gflops']:.0f} GFLOP/s ({ms*1e3:.1f} us), "
+                    f"HLL {partitioned[name]['hll']['gflops']:.0f} GFLOP/s ({ms_h*1e3:.1f} us)")
+            H.close()
+            A.close()
+            del x, y
+            torch.cuda.empty_cache()
+    except Exception as e:  # pragma: no cover
+        partitioned["error"] = repr(e)
+        if rank == 0:
+            log(f"[bench] partitioned products failed: {e!r}")
     if sampler:
         sampler.stop()
     if rank == 0:
@@ -631,6 +679,7 @@ def bench_multi_gpu(args):
                         "note": "iterated product: x and y never leave the devices between iterations; see the N=1 line for the host-buffer path"},
                 "gpu_launches": h["launches_per_step"] * args.steps, "clocks": sampler.summary() if sampler else None,
                 "single_gpu_same_workload": t1,
+                "partitioned_products": partitioned,
                 "exchange_modes": {k: v for k, v in results.items() if isinstance(v, dict)}}
         emit(line)
     dist.barrier()

@@ -299,7 +299,13 @@ csr_row_fused_kernel(int M, const int *__restrict__ row_ptr, const int *__restri
     }
     const double inv_norm = 1.0 / prev_norm;  // one division per thread, one multiplication per row (1 ulp from a division)
     double sq = 0.0;
-    for (long long row = (long long)blockIdx.x * 256 + threadIdx.x; row < M; row += (long long)gridDim.x * 256) {
+    for (long long chunk_lo = (long long)blockIdx.x * 256; chunk_lo < M; chunk_lo += (long long)gridDim.x * 256) {
+        // peer stores: a CTA-uniform test on the chunk first (uniform datapath), the per-row range test only inside --
+        // done per row for every row it cost 30 us per peer per 56 M rows
+        bool boundary = false;
+        for (int p = 0; p < ep.peers.count; ++p) boundary |= chunk_lo < ep.peers.hi[p] && chunk_lo + 256 > ep.peers.lo[p];
+        const long long row = chunk_lo + threadIdx.x;
+        if (row >= M) continue;
         const int lo = __ldg(row_ptr + row), hi = __ldg(row_ptr + row + 1);
         double acc = 0.0;
         for (int k = lo; k < hi; k += BATCH) {
@@ -317,16 +323,17 @@ csr_row_fused_kernel(int M, const int *__restrict__ row_ptr, const int *__restri
         }
         if (scaled) acc *= inv_norm;
         sq = fma(acc, acc, sq);
-        for (int p = 0; p < ep.peers.count; ++p)
-            if (row >= ep.peers.lo[p] && row < ep.peers.hi[p]) ep.peers.dst[p][row] = acc;
         y[row] = acc;
+        if (boundary)
+            for (int p = 0; p < ep.peers.count; ++p)
+                if (row >= ep.peers.lo[p] && row < ep.peers.hi[p]) ep.peers.dst[p][row] = acc;
     }
     if (ep.partials == nullptr) return;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
     if (lane == 0) warp_sq[warp] = sq;
-    __syncthreads();  // every row of this CTA (local and peer stores) is issued: ONE system-scope fence by thread 0 orders them
-    if (warp == 0) {  // (cumulative through the barrier) before the counter and, through it, before the last CTA's tag
+    __syncthreads();  // every row of this CTA (local and peer stores) is issued: a device-scope fence by thread 0 (cumulative
+    if (warp == 0) {  // through the barrier) orders them before the counter and, through it, before the last CTA's sys release
         unsigned int arrived = 0;
         if (lane == 0) {
             double total = 0.0;
@@ -334,7 +341,7 @@ csr_row_fused_kernel(int M, const int *__restrict__ row_ptr, const int *__restri
             for (int w = 0; w < 8; ++w) total += warp_sq[w];
             ep.partials[blockIdx.x] = total;
             if (ep.mail.world > 0) {
-                __threadfence_system();
+                __threadfence();  // device scope; the system-scope fence is paid once, by the CTA that publishes (mail_publish)
                 arrived = atomicAdd(ep.mail.counter, 1u);
             }
         }
@@ -492,10 +499,7 @@ csr_row_async_kernel(int M, const int *__restrict__ row_ptr, const int *__restri
             __threadfence();
             if (order.boundary_chunks == 0 && lane < peers.count)  // experiment / degenerate ranges: tags at the end
                 st_release_sys(as.box[as.send_to[lane]] + 2 * 4 * as.world + as.rank, k + 1);
-            double part = 0.0;
-            for (int i = lane; i < (int)gridDim.x; i += 32) part += __ldcg(partials + i);
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+            const double part = warp_sum_partials(partials, (int)gridDim.x, lane);
             if (lane < as.world) {
                 unsigned long long *slot = as.box[lane] + 2 * ((int)(k & 3) * as.world + as.rank);
                 st_relaxed_sys(slot, (unsigned long long)__double_as_longlong(part));

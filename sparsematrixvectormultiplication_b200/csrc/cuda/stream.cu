@@ -351,13 +351,14 @@ csr_stream_kernel(const int2 *__restrict__ tiles, int num_tiles, const int *__re
             ep.partials[blockIdx.x] = total;
         }
         if (ep.mail.world > 0) {
-            // every consumer's rows (local and peer stores) are issued before the barrier; ONE system-scope fence by
-            // thread 0 (cumulative through the barrier) orders them before the counter and the last CTA's tag
+            // every consumer's rows (local and peer stores) are issued before the barrier; a device-scope fence by
+            // thread 0 (cumulative through the barrier) orders them before the counter; the CTA that completes the count
+            // pays the one system-scope fence before it publishes the tag (mail_publish)
             asm volatile("bar.sync 2, %0;" ::"n"(kConsumerWarps * 32) : "memory");
             if (warp == 0) {
                 unsigned int arrived = 0;
                 if (lane == 0) {
-                    __threadfence_system();
+                    __threadfence();
                     arrived = atomicAdd(ep.mail.counter, 1u);
                 }
                 arrived = __shfl_sync(0xffffffffu, arrived, 0);
