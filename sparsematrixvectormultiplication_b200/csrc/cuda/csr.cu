@@ -200,7 +200,7 @@ __global__ void csr_long_combine_kernel(const int *__restrict__ long_rows, const
 }
 
 // Plain vector-per-row kernel: VEC lanes per row, lane-strided loop, xor-shuffle reduction.
-template <int VEC, typename V>
+template <int VEC, typename V, int BATCH = kVecBatch>
 __global__ void __launch_bounds__(256)
 csr_vector_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
                   const V *__restrict__ values, const V *__restrict__ x, V *__restrict__ y,
@@ -217,7 +217,7 @@ csr_vector_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, c
     // kVecBatch column/value loads are issued before the first gather and the gathers before the first fma: the
     // column -> x dependency costs one round trip per batch instead of one per element
     double acc = (VEC == 1 && accumulate && live) ? (double)y[row] : 0.0;  // one lane per row: y += A x in the serial loop's order
-    constexpr int kBatch = VEC == 1 ? kRowBatch : kVecBatch;
+    constexpr int kBatch = VEC == 1 ? kRowBatch : BATCH;
     for (int k = lo + lane; k < hi; k += kBatch * VEC) {
         int c[kBatch];
         double v[kBatch], xv[kBatch];
@@ -864,6 +864,8 @@ static int launch_vector(int row_begin, int row_end, const int *row_ptr, const i
     if (rows <= 0) return SPMV_B200_OK;
     if (vec == 1) return launch_rows(row_begin, row_end, row_ptr, col_idx, values, x, y, env_int("SPMV_B200_ROW_BATCH", 4), accumulate, stream);
     const unsigned int grid = blocks_for(rows * vec, 256);
+    // (8 lanes x 4 gathers per lane is the measured optimum on 32 nonzeros per row: 1208 us; 8 x 8: 1246, 4 x 8: 1415,
+    //  16 x 4: 1369 -- profiles/r01d_kernel_selection.md)
 #define VEC_CASE(W)                                                                                                 \
     case W:                                                                                                         \
         csr_vector_kernel<W, V><<<grid, 256, 0, stream>>>(row_begin, row_end, row_ptr, col_idx, values, x, y, accumulate); \
