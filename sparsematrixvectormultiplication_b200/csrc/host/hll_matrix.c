@@ -14,6 +14,9 @@
 #include "hll_matrix.h"
 
 #include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -91,6 +94,50 @@ int convert_to_hll(const PreMatrix *pre, HLLMatrix *hll) {
     int status = (hll->blocks && first && fill && arena && scratch) ? 0 : -1;
     if (status != 0) printf("convert_to_hll: out of memory\n");
 
+    /* Counting scatter by row.  Large, well-formed inputs: every thread owns a range of rows and scans the whole COO
+     * list for them (sequential reads; the entries of a row keep their file order, so the result is bit-identical to
+     * the serial loops below, which remain for small inputs and for anything with an out-of-range index, whose
+     * messages must come out in file order). */
+    int threads = 1;
+#ifdef _OPENMP
+    if (status == 0 && nz >= (1 << 20) && M >= 64) {
+        int clean = 1;
+#pragma omp parallel for reduction(& : clean)
+        for (int k = 0; k < nz; ++k) clean &= pre->I[k] >= 0 && pre->I[k] < M && pre->J[k] >= 0 && pre->J[k] < N;
+        if (clean) threads = omp_get_max_threads() < 64 ? omp_get_max_threads() : 64;
+    }
+#endif
+    if (threads > 1) {
+#pragma omp parallel num_threads(threads)
+        {
+            const int t = omp_get_thread_num(), T = omp_get_num_threads();
+            const int r0 = (int)((long long)M * t / T), r1 = (int)((long long)M * (t + 1) / T);
+            for (int k = 0; k < nz; ++k) {
+                const int r = pre->I[k];
+                if (r >= r0 && r < r1) first[r + 1]++;
+            }
+        }
+        for (int r = 0; r < M; ++r) first[r + 1] += first[r];
+#pragma omp parallel num_threads(threads)
+        {
+            const int t = omp_get_thread_num(), T = omp_get_num_threads();
+            const long long lo_target = (long long)nz * t / T, hi_target = (long long)nz * (t + 1) / T;
+            int a = 0, b = M;
+            while (a < b) { const int m = (a + b) / 2; if (first[m] < lo_target) a = m + 1; else b = m; }
+            const int r0 = t == 0 ? 0 : a;
+            a = 0; b = M;
+            while (a < b) { const int m = (a + b) / 2; if (first[m] < hi_target) a = m + 1; else b = m; }
+            const int r1 = t == T - 1 ? M : a;
+            for (int k = 0; k < nz; ++k) {
+                const int r = pre->I[k];
+                if (r >= r0 && r < r1) {
+                    Entry *slot = &arena[first[r] + fill[r]++];
+                    slot->col = pre->J[k];
+                    slot->val = pre->val[k];
+                }
+            }
+        }
+    } else {
     for (int k = 0; status == 0 && k < nz; ++k) {
         const int r = pre->I[k];
         if (r < 0 || r >= M) {
@@ -112,6 +159,7 @@ int convert_to_hll(const PreMatrix *pre, HLLMatrix *hll) {
             slot->col = c;
             slot->val = pre->val[k];
         }
+    }
     }
 
     int failed = 0;

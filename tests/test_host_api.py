@@ -189,9 +189,15 @@ def test_parallel_parser_equals_serial_on_fixtures(name, monkeypatch):
     monkeypatch.setenv("SPMV_B200_PARSER_PARALLEL_MIN_BYTES", str(1 << 40))
     serial = host.read_matrix_market(path)
     monkeypatch.setenv("SPMV_B200_PARSER_PARALLEL_MIN_BYTES", "0")
-    for threads in ("2", "3", "16"):
-        monkeypatch.setenv("OMP_NUM_THREADS", threads)
-        assert _same_pre(host.read_matrix_market(path), serial), f"{name} with {threads} threads"
+    import ctypes
+    gomp = ctypes.CDLL("libgomp.so.1")            # OMP_NUM_THREADS is only read when the runtime starts
+    before = gomp.omp_get_max_threads()
+    try:
+        for threads in (2, 3, 16):
+            gomp.omp_set_num_threads(threads)
+            assert _same_pre(host.read_matrix_market(path), serial), f"{name} with {threads} threads"
+    finally:
+        gomp.omp_set_num_threads(before)
 
 
 @pytest.mark.parametrize("kind,field", [("general", "real"), ("symmetric", "real"), ("general", "pattern"),
@@ -260,3 +266,29 @@ def test_parallel_parser_falls_back_on_irregular_bodies(tmp_path, monkeypatch, c
     assert results[0][-1] == results[1][-1], "same message on stdout"
     if results[0][0] == "ok":
         assert all(np.array_equal(a, b) for a, b in zip(results[0][1:-1], results[1][1:-1]))
+
+
+@pytest.mark.parametrize("dup", [False, True])
+def test_large_inputs_take_the_parallel_scatter(reference, dup, monkeypatch):
+    """Above 2^20 entries convert_in_csr / convert_to_hll spread the counting scatter over the OpenMP threads (every
+    thread owns a range of rows and scans the whole COO list): same arrays as the reference, bit for bit, for any
+    thread count, duplicates included."""
+    rng = np.random.default_rng(99 + dup)
+    M, N, nz = 70_001, 50_000, 1_300_000
+    coo = random_coo(rng, M, N, nz, dup=dup)
+    rp, ci, va = reference.coo_to_csr(coo)
+    h = reference.coo_to_hll(coo)
+    import ctypes
+    gomp = ctypes.CDLL("libgomp.so.1")            # the OpenMP runtime the library is linked against
+    before = gomp.omp_get_max_threads()
+    for threads in (1, 3, 8):
+        gomp.omp_set_num_threads(threads)          # (OMP_NUM_THREADS is only read when the runtime starts)
+        assert gomp.omp_get_max_threads() == threads
+        pre = host.PreMatrix(M, N, coo.I, coo.J, coo.val)
+        csr = host.convert_in_csr(pre)
+        assert np.array_equal(csr.row_ptr, rp) and np.array_equal(csr.col_idx, ci)
+        assert np.array_equal(csr.values.view(np.uint64), va.view(np.uint64)), f"{threads} threads"
+        rows, maxnz, offset, JA, AS = host.convert_to_hll(pre).flat()
+        assert np.array_equal(maxnz, h.maxnz) and np.array_equal(JA, h.JA)
+        assert np.array_equal(AS.view(np.uint64), h.AS.view(np.uint64)), f"{threads} threads"
+    gomp.omp_set_num_threads(before)
