@@ -671,7 +671,9 @@ def bench_multi_gpu(args):
                            "exchange": "boundary rows AND |w|^2 stored into the peers' buffers / mailboxes over NVLink peer memory by the product kernel; no collective call in the loop",
                            "step": "one power iteration = ONE launch: wait for the peers' tags, w=(A w_prev)/|w_prev|, |w|^2 partials, peer stores of boundary rows, last CTA publishes |w|^2 + tag",
                            "l2": "inputs_exceed_l2"},
-                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                             # ncu of the fused kernel at the per-rank size of the 8-GPU run (profiles/r01g_ncu_fused_rank_size.md)
+                             "traffic": 1737000000 if (world == 8 and n == 512) else None,
                              "peak_source": peak_src, "note": "rank 0's local CSR product alone (max over ranks); algorithmic bytes of its row slice = 12 nnz_local + 4 (rows+1) + 8 rows + 8 x (referenced columns of x)",
                              "algorithmic_bytes_per_launch": int(h["bytes_local"])},
                 "cpu_baseline": None,
