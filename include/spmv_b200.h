@@ -42,7 +42,8 @@ extern "C" {
 #define SPMV_B200_ERR_NOMEM (-4)
 
 /* CSR kernel selection for spmv_b200_csr_spmv */
-#define SPMV_B200_ALGO_AUTO 0     /* ROW when no row exceeds 16 nonzeros, STREAM for <= 12 nnz/row on average, else VECTOR (even rows) or BINNED (skewed) */
+#define SPMV_B200_ALGO_AUTO 0     /* ROW (or STREAM: timed at plan time, same bits) when no row exceeds 12 nonzeros; STREAM for
+                                     <= 12 nnz/row on average; else VECTOR (even rows) or BINNED (skewed rows) */
 #define SPMV_B200_ALGO_VECTOR 1   /* plain vector-per-row kernel with shuffle reduction      */
 #define SPMV_B200_ALGO_TILE 2     /* row-binned tile kernel, one CTA per tile, direct loads  */
 #define SPMV_B200_ALGO_STREAM 3   /* persistent row-binned kernel, TMA bulk-copy pipeline    */
@@ -99,11 +100,11 @@ int spmv_b200_device_info(char *name, int len, int *sm_count, long long *l2_byte
  * spmv_b200_resident_drop() (a sampled fingerprint cannot see every change).  Also switched on by the environment
  * variable SPMV_B200_RESIDENT=1. */
 int spmv_b200_resident_cache(int enable); /* returns the previous setting */
+void spmv_b200_resident_drop(void);       /* forget every cached device copy */
 /* Plan-time timing of kernel candidates (a few products on scratch vectors when a large matrix is uploaded; only
  * candidates that give the same bits compete).  On by default; SPMV_B200_AUTOTUNE=0 or this switch turns it off, e.g. for
  * a matrix that is used once.  Returns the previous setting. */
 int spmv_b200_autotune(int enable);
-void spmv_b200_resident_drop(void);       /* forget every cached device copy */
 
 /* ---- CSR ----------------------------------------------------------------------------- */
 /* host arrays (reference CSRMatrix fields, libs/csr_matrix.h:8-16) -> resident device copy */
@@ -133,10 +134,10 @@ int spmv_b200_csr_download(const spmv_b200_csr *A, int *row_ptr, int *col_idx, d
 /* y = A x  (accumulate != 0: y += A x, the reference's serial semantics, src/csr_matrix.c:136) */
 int spmv_b200_csr_spmv(const spmv_b200_csr *A, const double *d_x, double *d_y, int accumulate,
                        int algo, void *stream);
-/* host x[N] -> device, product, device -> host y[M]; synchronous */
+/* host x[N] -> device, product, device -> host y[M]; one synchronous call.  Inside, the rows are cut into up to 16
+ * windows and the upload of x, the products and the download of y overlap on three streams (hostpath.cu); pinned or
+ * cudaHostRegister'ed buffers give the overlap, pageable ones work but serialise. */
 int spmv_b200_csr_spmv_host(spmv_b200_csr *A, const double *x, double *y, int accumulate, int algo);
-/* product restricted to rows [row_begin,row_end) (the reference's per-thread row ranges,
- * src/csr_matrix.c:294-313); other rows of y are left untouched. Vector kernel. */
 /* ---- fused iterated product (BASELINE config 5; no reference counterpart: the reference only repeats
  * the same product, main_cuda.cu:159-200).  One launch computes
  *     y[r] = (A x)[r] / sqrt(*d_prev_sumsq)            (d_prev_sumsq == NULL: no scaling)
@@ -206,6 +207,8 @@ typedef struct {
 int spmv_b200_csr_spmv_fused_async(const spmv_b200_csr *A, const double *d_x, double *d_y, double *d_partials,
                                    const spmv_b200_peers_t *peers, const spmv_b200_async_t *async, void *stream);
 
+/* product restricted to rows [row_begin,row_end) (the reference's per-thread row ranges,
+ * src/csr_matrix.c:294-313); other rows of y are left untouched.  Vector kernel. */
 int spmv_b200_csr_spmv_rows(const spmv_b200_csr *A, int row_begin, int row_end, const double *d_x,
                             double *d_y, void *stream);
 void spmv_b200_csr_free(spmv_b200_csr *A);
