@@ -1015,7 +1015,12 @@ CsrPath csr_resolve(const spmv_b200_csr *A, int algo) {
             // every row short: one thread per row (serial order, so forced_tpr == 1 is honoured as well)
             if (A->max_row <= kRowKernelMaxLen) return A->short_rows_stream ? kPathStream : kPathRow;
             if (A->forced_tpr == 1 || A->nnz <= (long long)kAutoStreamMaxAvg * A->M) return kPathStream;
-            return A->num_long == 0 ? kPathVector : kPathBinned;
+            {   // longer rows: one lane count for all rows (vector kernel) only while the lengths are even; a longest row
+                // far above the mean (or above the long-row threshold) means skew -> lanes per row by length class
+                const long long mean = A->M > 0 ? (A->nnz + A->M - 1) / A->M : 0;
+                const bool skewed = A->num_long > 0 || A->max_row > 4 * std::max<long long>(mean, 8);
+                return skewed ? kPathBinned : kPathVector;
+            }
     }
 }
 
@@ -1353,7 +1358,8 @@ int spmv_b200_csr_spmv_f32(const spmv_b200_csr *A, const float *d_x, float *d_y,
     CsrPath path;
     switch (algo) {
         case SPMV_B200_ALGO_AUTO:
-            path = A->max_row <= kRowKernelMaxLen ? kPathRow : (A->num_long == 0 ? kPathVector : kPathBinned);
+            path = A->max_row <= kRowKernelMaxLen ? kPathRow : csr_resolve(A, SPMV_B200_ALGO_AUTO);
+            if (path == kPathStream || path == kPathTile) path = kPathBinned;  // no fp32 stream / tile kernels
             break;
         case SPMV_B200_ALGO_ROW: path = kPathRow; break;
         case SPMV_B200_ALGO_VECTOR: path = kPathVector; break;
