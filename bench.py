@@ -205,7 +205,7 @@ def ramp_vector(n, device):
 # ---------------------------------------------------------------------------------------------------
 # CPU baseline (the reference's own CPU path on the host cores)
 # ---------------------------------------------------------------------------------------------------
-def cpu_baseline_lap2d(n, rp, ci, va, budget_s=20.0):
+def cpu_baseline_lap2d(n, rp, ci, va, budget_s=20.0, hll_budget_s=5.0):
     """oracle/_ref (kind 'reference') or the oracle port, OpenMP over all host cores + the serial loop,
     on the full workload matrix; a bounded number of products."""
     from oracle import oracle as O
@@ -227,10 +227,74 @@ def cpu_baseline_lap2d(n, rp, ci, va, budget_s=20.0):
         chk.spmv_csr_parallel(rp, ci, va, x, starts, ends, y=y)
         times.append(time.perf_counter() - t0)
     mean_s = sum(times) / len(times)
-    return {"value": 2.0 * nnz / mean_s / 1e9, "unit": "GFLOP/s", "cores": len(starts), "kind": chk.kind,
-            "sample": f"full lap2d_4096 matrix ({nnz} nnz), {len(times)} timed OpenMP CSR products (spvm_csr_parallel) "
-                      f"after 1 warm-up, mean; host has {cores} logical cores",
-            "serial_gflops": 2.0 * nnz / serial_s / 1e9, "best_gflops": 2.0 * nnz / min(times) / 1e9}
+    out = {"value": 2.0 * nnz / mean_s / 1e9, "unit": "GFLOP/s", "cores": len(starts), "kind": chk.kind,
+           "sample": f"full lap2d_{n} matrix ({nnz} nnz), {len(times)} timed OpenMP CSR products (spvm_csr_parallel) "
+                     f"after 1 warm-up, mean; host has {cores} logical cores",
+           "serial_gflops": 2.0 * nnz / serial_s / 1e9, "best_gflops": 2.0 * nnz / min(times) / 1e9, "cpu_model": cpu_model()}
+    # thread sweep of the OpenMP CSR product (the reference sweeps {2,4,8,16,32,40}, main.c:18) and the HLL paths
+    try:
+        sweep = {}
+        t = 1
+        while t <= cores:
+            st, en = chk.partition_rows(rp, t)
+            chk.spmv_csr_parallel(rp, ci, va, x, st, en, y=y)
+            reps = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                chk.spmv_csr_parallel(rp, ci, va, x, st, en, y=y)
+                reps.append(time.perf_counter() - t0)
+            sweep[str(len(st))] = 2.0 * nnz / min(reps) / 1e9
+            t *= 2
+        out["csr_openmp_gflops_by_threads"] = sweep
+        if hll_budget_s > 0:
+            out.update(cpu_baseline_hll(chk, n, rp, ci, va, x, nnz, cores, hll_budget_s))
+    except Exception as e:  # pragma: no cover
+        out["sweep_error"] = repr(e)
+    return out
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_baseline_hll(chk, n, rp, ci, va, x, nnz, cores, budget_s):
+    """The reference's spmv_hll_serial and spmv_hll (OpenMP over its own block partition) on the same matrix.  The HLL
+    blocks are built by this repo's host converter (bit-identical to the reference's, tests/test_host_api.py)."""
+    import ctypes as C
+    from sparsematrixvectormultiplication_b200 import host
+    N = n * n
+    rows = np.repeat(np.arange(N, dtype=np.int32), np.diff(rp))
+    hll = host.convert_to_hll(host.PreMatrix(N, N, rows, ci, va))
+    del rows
+    xs = np.ascontiguousarray(x, np.float64)
+    y = np.zeros(hll.num_blocks * 32, np.float64)
+    xp, yp = xs.ctypes.data_as(C.POINTER(C.c_double)), y.ctypes.data_as(C.POINTER(C.c_double))
+    lib = chk.lib                                   # the checker's library: the reference .so when it was built
+    blocks = C.cast(hll.c.blocks, C.c_void_p)       # same struct layout as the reference's ELLPACKBlock
+    lib.spmv_hll_serial.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.spmv_hll_serial.restype = None
+    t0 = time.perf_counter()
+    lib.spmv_hll_serial(hll.num_blocks, blocks, xp, yp)
+    serial_s = time.perf_counter() - t0
+    bs, be = host.prepare_thread_distribution_hll(hll, cores)
+    bs, be = np.ascontiguousarray(bs, np.int32), np.ascontiguousarray(be, np.int32)
+    lib.spmv_hll.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_void_p, C.c_void_p]
+    lib.spmv_hll.restype = None
+    call = lambda: lib.spmv_hll(blocks, xp, yp, len(bs), bs.ctypes.data_as(C.c_void_p), be.ctypes.data_as(C.c_void_p))  # noqa: E731
+    call()
+    times, t_begin = [], time.perf_counter()
+    while len(times) < 30 and (time.perf_counter() - t_begin) < budget_s:
+        t0 = time.perf_counter()
+        call()
+        times.append(time.perf_counter() - t0)
+    return {"hll_serial_gflops": 2.0 * nnz / serial_s / 1e9, "hll_openmp_gflops": 2.0 * nnz / (sum(times) / len(times)) / 1e9,
+            "hll_openmp_threads": len(bs), "hll_sample": f"{len(times)} timed spmv_hll products on {len(bs)} block ranges"}
 
 
 # ---------------------------------------------------------------------------------------------------
