@@ -26,7 +26,7 @@
 
 namespace spmv {
 
-constexpr int kMaxWindows = 16;
+constexpr int kMaxWindows = 16;  // measured on lap2d 4096^2: 4 -> 3.93 ms, 8 -> 3.49, 16 -> 3.42, 24 -> 3.91, 32 -> 3.65, 48 -> 3.89
 constexpr long long kMinWindowBytes = 2LL << 20;  // below 2 MB of x + y per window the launch overheads win
 
 struct HostPipe {
