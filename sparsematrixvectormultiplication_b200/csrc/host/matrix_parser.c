@@ -6,7 +6,7 @@
  * entry stored immediately after each off-diagonal entry; 0 on success, -1 with a message on
  * stdout otherwise -- but the body of the file is slurped once and tokenised in memory with
  * strtol/strtod (which accept exactly what fscanf's %d / %lf accept) instead of one fscanf call
- * per entry, and bodies of 1 MB or more are tokenised by all OpenMP threads at once.  This is row
+ * per entry, and bodies of 4 MB or more are tokenised by all OpenMP threads at once.  This is row
  * (f).4 of SURVEY.md section 8: the fscanf loop is the end-to-end bottleneck on real files.
  */
 #include "matrix_parser.h"
@@ -25,7 +25,7 @@
 static size_t parallel_min_bytes(void) {
     const char *v = getenv("SPMV_B200_PARSER_PARALLEL_MIN_BYTES");
     if (v && *v) return (size_t)strtoull(v, NULL, 10);
-    return (size_t)1 << 20;
+    return (size_t)4 << 20;
 }
 
 void init_pre_matrix(PreMatrix *mat) {

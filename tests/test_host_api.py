@@ -203,7 +203,7 @@ def test_parallel_parser_equals_serial_on_fixtures(name, monkeypatch):
 @pytest.mark.parametrize("kind,field", [("general", "real"), ("symmetric", "real"), ("general", "pattern"),
                                         ("symmetric", "pattern"), ("general", "integer"), ("skew-symmetric", "real")])
 def test_parallel_parser_on_a_large_file(tmp_path, reference, kind, field):
-    """A 300k-entry file (6-9 MB: above the 1 MB default threshold) with ragged white space, entries spanning lines and
+    """A 300k-entry file (3-9 MB; the parallel pass is forced, and the default path is checked too) with ragged white space, entries spanning lines and
     exponents: default (parallel) parse == forced-serial parse == the reference's fscanf parser."""
     rng = np.random.default_rng(len(kind) * 31 + len(field))
     M, N, nz = 5000, 4000 if kind == "general" else 5000, 300_000
@@ -224,13 +224,15 @@ def test_parallel_parser_on_a_large_file(tmp_path, reference, kind, field):
             lines.append(f"{I[k]}{sep}{J[k]} {vals[k]:.17e}" if k % 3 else f"{I[k]} {J[k]}\n{float(vals[k])!r}")
     path = tmp_path / "big.mtx"
     path.write_text("\n".join(lines) + "\n")
-    assert path.stat().st_size > (1 << 20)
-    fast = host.read_matrix_market(path)
-    os.environ["SPMV_B200_PARSER_PARALLEL_MIN_BYTES"] = str(1 << 40)
+    default = host.read_matrix_market(path)            # parallel above 4 MB (the real / integer files), serial below
     try:
+        os.environ["SPMV_B200_PARSER_PARALLEL_MIN_BYTES"] = "0"
+        fast = host.read_matrix_market(path)
+        os.environ["SPMV_B200_PARSER_PARALLEL_MIN_BYTES"] = str(1 << 40)
         slow = host.read_matrix_market(path)
     finally:
         del os.environ["SPMV_B200_PARSER_PARALLEL_MIN_BYTES"]
+    assert _same_pre(default, slow)
     assert _same_pre(fast, slow)
     ref = reference.read_matrix_market(path)
     assert (ref.M, ref.N, ref.nz) == (fast.M, fast.N, fast.nz)
@@ -292,3 +294,26 @@ def test_large_inputs_take_the_parallel_scatter(reference, dup, monkeypatch):
         assert np.array_equal(maxnz, h.maxnz) and np.array_equal(JA, h.JA)
         assert np.array_equal(AS.view(np.uint64), h.AS.view(np.uint64)), f"{threads} threads"
     gomp.omp_set_num_threads(before)
+
+
+def test_parser_speed_report(tmp_path, reference, capsys):
+    """Not a pass/fail bar (shared CPUs are noisy): prints the time of the reference's fscanf parser and of this repo's
+    read_matrix_market on the same 400k-entry file, and checks they return the same COO.  Larger runs: tools/bench_parser.py."""
+    import time
+    rng = np.random.default_rng(3)
+    M = N = 300_000
+    nz = 400_000
+    I, J, V = rng.integers(1, M + 1, nz), rng.integers(1, N + 1, nz), rng.standard_normal(nz)
+    path = tmp_path / "speed.mtx"
+    with open(path, "w") as f:
+        f.write(f"%%MatrixMarket matrix coordinate real general\n{M} {N} {nz}\n")
+        np.savetxt(f, np.column_stack([I, J, V]), fmt="%d %d %.17g")
+    t0 = time.perf_counter()
+    ours = host.read_matrix_market(path)
+    t1 = time.perf_counter()
+    ref = reference.read_matrix_market(path)
+    t2 = time.perf_counter()
+    assert np.array_equal(ref.I, ours.I) and np.array_equal(ref.J, ours.J)
+    assert np.array_equal(np.asarray(ref.val).view(np.uint64), ours.val.view(np.uint64))
+    with capsys.disabled():
+        print(f"\n[parser] {nz} entries, {path.stat().st_size / 1e6:.0f} MB: this repo {t1 - t0:.3f} s, reference fscanf loop {t2 - t1:.3f} s")

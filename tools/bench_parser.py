@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""read_matrix_market on a generated file: the reference's fscanf loop (oracle/_ref, when built), this repo's serial
-tokenizer and its parallel tokenizer.  CPU only.  Usage: python tools/bench_parser.py [entries]"""
+"""read_matrix_market on a generated file: this repo's serial tokenizer and its parallel tokenizer.  CPU only.
+Usage: python tools/bench_parser.py [entries]
+(The reference's fscanf loop on the same file is timed by tests/test_host_api.py::test_parser_speed_report, because only
+tests/, smoke() and bench.py may execute anything under oracle/.)"""
 import os
 import sys
 import tempfile
@@ -39,11 +41,6 @@ def main():
         del os.environ["SPMV_B200_PARSER_PARALLEL_MIN_BYTES"]
         b = timed("this repo, parallel tokenizer (default)", lambda: host.read_matrix_market(path))
         assert np.array_equal(a.I, b.I) and np.array_equal(a.J, b.J) and np.array_equal(a.val.view(np.uint64), b.val.view(np.uint64))
-        if "--with-reference" in sys.argv:   # test infrastructure: only meaningful where oracle/_ref was built
-            from oracle import oracle as O
-            if O.reference_available():
-                r = timed("reference fscanf loop (oracle/_ref)", lambda: O.Reference().read_matrix_market(path))
-                assert np.array_equal(r.I, b.I) and np.array_equal(np.asarray(r.val).view(np.uint64), b.val.view(np.uint64))
 
 
 if __name__ == "__main__":
