@@ -30,6 +30,8 @@ void free_csr_matrix(CSRMatrix *mat);
 /* reference src/csr_matrix.c:63-126 (matrix_name is unused, as in the reference) */
 int convert_in_csr(const PreMatrix *pre, CSRMatrix *csr, const char *matrix_name);
 void print_csr_matrix(const CSRMatrix *mat);
+/* reference libs/csr_matrix.h:23, src/csr_matrix.c:28-61 */
+void write_memory_stats_to_csv(const char *matrix_name, int nz, size_t total_memory_bytes);
 
 /* y += A x (reference src/csr_matrix.c:130-139) -- GPU */
 void csr_matrix_vector_mult(int num_row, const int *row_ptr, const int *col_idx, const double *values,

@@ -98,8 +98,10 @@ int spmv_b200_device_info(char *name, int len, int *sm_count, long long *l2_byte
  * and reused while the array POINTERS, sizes and a sampled fingerprint of the contents are unchanged; free_csr_matrix /
  * free_hll_matrix drop it.  Contract: do not modify the arrays in place between calls without calling
  * spmv_b200_resident_drop() (a sampled fingerprint cannot see every change).  Also switched on by the environment
- * variable SPMV_B200_RESIDENT=1. */
-int spmv_b200_resident_cache(int enable); /* returns the previous setting */
+ * variable SPMV_B200_RESIDENT=1.  enable = 2 (SPMV_B200_RESIDENT=2) is the strict mode: every element of the index and
+ * value arrays is hashed on every call (one parallel pass over the host arrays), so no in-place change and no free +
+ * malloc at the same addresses can go unnoticed. */
+int spmv_b200_resident_cache(int enable); /* 0 off, 1 sampled, 2 strict; returns the previous setting */
 void spmv_b200_resident_drop(void);       /* forget every cached device copy */
 /* Plan-time timing of kernel candidates (a few products on scratch vectors when a large matrix is uploaded; only
  * candidates that give the same bits compete).  On by default; SPMV_B200_AUTOTUNE=0 or this switch turns it off, e.g. for

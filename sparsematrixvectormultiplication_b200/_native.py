@@ -162,6 +162,7 @@ SIGNATURES = {
     "free_csr_matrix": (None, [C.POINTER(CSRMatrixStruct)]),
     "convert_in_csr": (_I, [C.POINTER(PreMatrixStruct), C.POINTER(CSRMatrixStruct), C.c_char_p]),
     "print_csr_matrix": (None, [C.POINTER(CSRMatrixStruct)]),
+    "write_memory_stats_to_csv": (None, [C.c_char_p, _I, C.c_size_t]),
     "csr_matrix_vector_mult": (None, [_I, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p]),
     "prepare_thread_distribution": (_I, [_I, c_int_p, _I, _LL, C.POINTER(c_int_p), C.POINTER(c_int_p)]),
     "spvm_csr_parallel": (None, [c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p, _I, c_int_p, c_int_p]),
@@ -203,6 +204,8 @@ SIGNATURES = {
     "sort_row": (None, [c_int_p, c_dbl_p, C.c_size_t, C.c_size_t]),
     "clear_cache": (None, [C.c_size_t]),
     "process_matrix_file": (_I, [C.c_char_p, C.POINTER(PreMatrixStruct)]),
+    "create_directory": (None, [C.c_char_p]),
+    "write_results_to_csv": (None, [C.c_char_p, _I, _I, _I, _I] + [_D] * 6 + [DiffMetricsStruct] * 4 + [_D] * 14 + [C.c_char_p]),
     # ---- mmio.h ----
     "mm_read_banner": (_I, [_V, C.POINTER(C.c_char * 4)]),
     "mm_read_mtx_crd_size": (_I, [_V, c_int_p, c_int_p, c_int_p]),

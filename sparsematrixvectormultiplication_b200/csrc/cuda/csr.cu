@@ -298,6 +298,7 @@ csr_row_fused_kernel(int M, const int *__restrict__ row_ptr, const int *__restri
         prev_norm = sqrt(*ep.prev_sumsq);
     }
     const double inv_norm = 1.0 / prev_norm;  // one division per thread, one multiplication per row (1 ulp from a division)
+    zero_partials_tail(ep);
     double sq = 0.0;
     for (long long chunk_lo = (long long)blockIdx.x * 256; chunk_lo < M; chunk_lo += (long long)gridDim.x * 256) {
         // peer stores: a CTA-uniform test on the chunk first (uniform datapath), the per-row range test only inside --
@@ -813,10 +814,8 @@ static int build_plan(spmv_b200_csr *A, cudaStream_t stream) {
             const int count = std::max(std::max(A->stream_grid, fused_row_grid(A)), 1);
             if (cudaMalloc(&partials, (size_t)count * sizeof(double)) == cudaSuccess) {
                 Epilogue ep;
-                ep.prev_sumsq = nullptr;
                 ep.partials = partials;
-                ep.peers.count = 0;
-                ep.mail.world = 0;
+                ep.partials_total = count;
                 A->fused_batch = tune_batch(M, A->N, 0, stream, [&](int batch, double *x, double *y) {
                     return launch_fused(A, x, y, ep, stream, batch);
                 }, 0);
@@ -1229,8 +1228,7 @@ int spmv_b200_csr_spmv_fused(const spmv_b200_csr *A, const double *d_x, double *
     Epilogue ep;
     ep.prev_sumsq = d_prev_sumsq;
     ep.partials = d_partials;
-    ep.peers.count = 0;
-    ep.mail.world = 0;
+    ep.partials_total = spmv_b200_csr_partials_count(A);
     if (peers) ep.peers = *peers;
     if (A->M == 0) return SPMV_B200_OK;
     return launch_fused(A, d_x, d_y, ep, as_stream(stream), -1);
@@ -1250,9 +1248,8 @@ int spmv_b200_csr_spmv_fused_mail(const spmv_b200_csr *A, const double *d_x, dou
     for (int r = 0; r < mail->world; ++r)
         if (!mail->box[r]) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_mail: mailbox of rank %d is NULL", r);
     Epilogue ep;
-    ep.prev_sumsq = nullptr;
     ep.partials = d_partials;
-    ep.peers.count = 0;
+    ep.partials_total = spmv_b200_csr_partials_count(A);
     if (peers) ep.peers = *peers;
     ep.mail = *mail;
     return launch_fused(A, d_x, d_y, ep, as_stream(stream), -1);

@@ -13,12 +13,20 @@ constexpr int kDefaultStages = 2;           // TMA pipeline depth of the stream 
 constexpr int kHllTileSlots = 3072;         // D_h: slots + rows per HLL tile (12 B per slot; stage = 49.5 KB with the wide margin)
 constexpr int kHllWideSlots = 1024;         // hacks with more slots (MAXNZ > 32) are processed straight from HBM
 
-struct Epilogue {                 // optional fused tail of the CSR stream kernel
-    const double *prev_sumsq;     // divide every row by sqrt(*prev_sumsq)
-    double *partials;             // partials[blockIdx.x] = sum of the squares of the rows this CTA produced
-    spmv_b200_peers_t peers;      // rows mirrored into peer memory
-    spmv_b200_mail_t mail;        // world > 0: |w|^2 travels through peer mailboxes instead of prev_sumsq (spmv_b200.h)
+struct Epilogue {                 // optional fused tail of the CSR stream / row kernels and the HLL row kernel
+    const double *prev_sumsq = nullptr;  // divide every row by sqrt(*prev_sumsq)
+    double *partials = nullptr;   // partials[blockIdx.x] = sum of the squares of the rows this CTA produced
+    int partials_total = 0;       // size of the caller's buffer (spmv_b200_csr_partials_count): CTA 0 zeroes the entries
+                                  // [gridDim.x, partials_total) so that a caller may always sum the whole buffer
+    spmv_b200_peers_t peers = {}; // rows mirrored into peer memory
+    spmv_b200_mail_t mail = {};   // world > 0: |w|^2 travels through peer mailboxes instead of prev_sumsq (spmv_b200.h)
 };
+
+// entries of the partials buffer that this launch does not write (the buffer is sized for the largest fused grid)
+__device__ __forceinline__ void zero_partials_tail(const Epilogue &ep) {
+    if (blockIdx.x == 0 && ep.partials != nullptr)
+        for (int i = (int)gridDim.x + (int)threadIdx.x; i < ep.partials_total; i += (int)blockDim.x) ep.partials[i] = 0.0;
+}
 
 constexpr int kBins = 7;  // rows binned by length: 1, 2, 4, 8, 16, 32 lanes per row, and "long" (split into fragments)
 

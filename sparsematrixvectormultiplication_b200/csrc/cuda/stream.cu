@@ -237,6 +237,7 @@ csr_stream_kernel(const int2 *__restrict__ tiles, int num_tiles, const int *__re
         }
     }
     const double inv_norm = 1.0 / prev_norm;  // one division per thread, one multiplication per row (1 ulp from a division)
+    if constexpr (kFused) zero_partials_tail(ep);
     double sq = 0.0;  // sum of the squares of the rows this lane produced
     // y[row] = v; the fused instantiation scales it first, accumulates v^2 and mirrors boundary rows into the peers
     auto emit = [&](int row, double v) {
@@ -521,11 +522,15 @@ static size_t csr_stream_smem(const spmv_b200_csr *A) {
     return (size_t)A->stages * (size_t)csr_stage_bytes(A) + (size_t)A->stages * 16 + 16;
 }
 
+constexpr int kMaxStreamSmem = 220 * 1024;  // the plans shrink their stage count until they fit below this
+
 static int pick_grid(const void *kernel, int threads, size_t smem, int num_tiles, int &grid) {
     int dev = 0, sms = 0, per_sm = 0;
     SPMV_TRY_CUDA(cudaGetDevice(&dev));
     SPMV_TRY_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    SPMV_TRY_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the limit is per kernel and device, not per handle: always the largest size any plan may ask for, so that a second
+    // handle planned with smaller stages can never lower it below what an older live handle passes at launch
+    SPMV_TRY_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStreamSmem));
     SPMV_TRY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     if (per_sm < 1) return fail(SPMV_B200_ERR_INVALID, "stream kernel does not fit: %zu bytes of shared memory per CTA", smem);
     const int want = env_int("SPMV_B200_CTAS_PER_SM", 0);
@@ -582,10 +587,6 @@ int stream_launch_csr(const spmv_b200_csr *A, const double *x, double *y, int ac
     const int2 *tiles = A->tiles + tile_begin;
     const int grid = std::min(A->stream_grid, tile_count);
     Epilogue none;
-    none.prev_sumsq = nullptr;
-    none.partials = nullptr;
-    none.peers.count = 0;
-    none.mail.world = 0;
     const Epilogue e = ep ? *ep : none;
     const size_t smem = csr_stream_smem(A);
     if (ep) {

@@ -36,6 +36,21 @@ void free_csr_matrix(CSRMatrix *mat) {
     init_csr_matrix(mat);
 }
 
+/* Appends "name, nnz, MiB" to ../result/matrix_memory_stats_csr.csv (reference src/csr_matrix.c:28-61: the path is
+ * hard-coded there too; defined but never called by either driver).  Kept so that the header is a complete drop-in. */
+void write_memory_stats_to_csv(const char *matrix_name, int nz, size_t total_memory_bytes) {
+    static const char target[] = "../result/matrix_memory_stats_csr.csv";
+    FILE *out = fopen(target, "a+");
+    if (!out) {
+        printf("write_memory_stats_to_csv: cannot open %s\n", target);
+        return;
+    }
+    fseek(out, 0, SEEK_END);
+    if (ftell(out) == 0) fputs("Matrix Name,Non-Zero Elements,Memory Size (MB)\n", out);
+    fprintf(out, "%s,%d,%.4f\n", matrix_name, nz, (double)total_memory_bytes / 1048576.0);
+    fclose(out);
+}
+
 /* ------------------------------------------------------------------------------------------
  * Row ordering.
  *

@@ -112,13 +112,14 @@ static int parse_body_parallel(const char *text, size_t len, int declared, int p
 #endif
     if (threads > 64) threads = 64;
     if (threads < 2 || declared <= 0) return 0;
+    if (len < 2 * (size_t)threads) return 0; /* a tiny body: chunks would be empty (and chunk starts would sit at 0) */
     size_t begin[65];
     long long first_token[65];
     /* chunk boundaries moved forward to the start of a token (or the end of the text) */
     for (int t = 0; t <= threads; ++t) {
         size_t at = t == threads ? len : len / (size_t)threads * (size_t)t;
         if (t > 0 && t < threads) {
-            while (at < len && !is_space(text[at - 1])) ++at; /* do not split a token */
+            while (at > 0 && at < len && !is_space(text[at - 1])) ++at; /* do not split a token */
         }
         begin[t] = at;
     }

@@ -10,10 +10,13 @@
 
 static int g_enabled = -1; /* -1: not decided yet (environment) */
 
+/* 0 off, 1 sampled fingerprint (the documented contract: call spmv_b200_resident_drop() after changing the arrays in
+ * place), 2 strict: every element of the index and value arrays is hashed on every call, so an in-place change or a
+ * free + malloc at the same addresses can never go unnoticed (costs one pass over the host arrays per product). */
 static int enabled(void) {
     if (g_enabled < 0) {
         const char *v = getenv("SPMV_B200_RESIDENT");
-        g_enabled = (v && *v && strcmp(v, "0") != 0) ? 1 : 0;
+        g_enabled = (v && *v && strcmp(v, "0") != 0) ? (strcmp(v, "2") == 0 ? 2 : 1) : 0;
     }
     return g_enabled;
 }
@@ -21,9 +24,31 @@ static int enabled(void) {
 /* 64 evenly spaced samples of the index and value arrays, mixed FNV-style */
 static uint64_t mix(uint64_t h, uint64_t v) { return (h ^ v) * 0x100000001B3ULL; }
 
+static uint64_t hash_span(const int *idx, const double *val, long long lo, long long hi) {
+    uint64_t h = 0xCBF29CE484222325ULL;
+    for (long long k = lo; k < hi; ++k) {
+        uint64_t bits;
+        memcpy(&bits, &val[k], sizeof bits);
+        h = mix(mix(h, (uint64_t)(uint32_t)idx[k]), bits);
+    }
+    return h;
+}
+
 static uint64_t sample_arrays(const int *idx, const double *val, long long n) {
     uint64_t h = 0xCBF29CE484222325ULL;
     if (n <= 0) return h;
+    if (enabled() == 2) { /* strict: all of it, in fixed 1 Mi-element spans hashed in parallel and chained in order */
+        const long long span = 1LL << 20, spans = (n + span - 1) / span;
+        uint64_t *part = malloc((size_t)spans * sizeof *part);
+        if (part) {
+#pragma omp parallel for schedule(static)
+            for (long long c = 0; c < spans; ++c) part[c] = hash_span(idx, val, c * span, (c + 1) * span < n ? (c + 1) * span : n);
+            for (long long c = 0; c < spans; ++c) h = mix(h, part[c]);
+            free(part);
+            return h;
+        }
+        return hash_span(idx, val, 0, n);
+    }
     const long long step = n > 64 ? n / 64 : 1;
     for (long long k = 0; k < n; k += step) {
         uint64_t bits;
@@ -53,7 +78,7 @@ static struct {
 
 int spmv_b200_resident_cache(int enable) {
     const int before = enabled();
-    g_enabled = enable ? 1 : 0;
+    g_enabled = enable ? (enable == 2 ? 2 : 1) : 0;
     if (!g_enabled) spmv_b200_resident_drop();
     return before;
 }
@@ -99,7 +124,7 @@ int resident_csr(int M, int N, long long nnz, const int *row_ptr, const int *col
 
 static uint64_t sample_blocks(const ELLPACKBlock *blocks, int count) {
     uint64_t h = 0xCBF29CE484222325ULL;
-    const int step = count > 16 ? count / 16 : 1;
+    const int step = (count > 16 && enabled() != 2) ? count / 16 : 1;
     for (int b = 0; b < count; b += step) {
         const ELLPACKBlock *blk = &blocks[b];
         h = mix(mix(mix(h, (uint64_t)blk->M), (uint64_t)blk->MAXNZ), (uint64_t)(uintptr_t)blk->JA);

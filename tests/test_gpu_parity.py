@@ -834,6 +834,21 @@ def test_resident_cache_of_the_drop_in_api(dev, checker):
         y = np.zeros(M)
         host.csr_matrix_vector_mult(csr2.M, csr2.row_ptr, csr2.col_idx, csr2.values, x, y)
         assert_close(y, -y_ref, scale, "a different matrix after a cached one")
+        # strict mode (2): every element is hashed, so an in-place change at a position the sampled fingerprint never
+        # looks at is seen and the device copy is rebuilt
+        N.lib().spmv_b200_resident_cache(2)
+        y = np.zeros(M)
+        host.csr_matrix_vector_mult(csr.M, csr.row_ptr, csr.col_idx, csr.values, x, y)
+        assert_close(y, y_ref, scale, "strict cache, first call")
+        k = 12345                                        # not a multiple of nnz // 64: unsampled
+        row = int(np.searchsorted(csr.row_ptr, k, side="right") - 1)
+        old = float(csr.values[k])
+        csr.values[k] = old + 1000.0
+        y = np.zeros(M)
+        host.csr_matrix_vector_mult(csr.M, csr.row_ptr, csr.col_idx, csr.values, x, y)
+        assert abs((y[row] - y_ref[row]) - 1000.0 * x[csr.col_idx[k]]) <= 1e-9 * (1.0 + abs(1000.0 * x[csr.col_idx[k]])), \
+            "strict cache must notice an in-place change"
+        csr.values[k] = old
     finally:
         N.lib().spmv_b200_resident_cache(before)
         N.lib().spmv_b200_resident_drop()
