@@ -38,9 +38,20 @@ import numpy as np  # noqa: E402
 
 HBM_NOMINAL_GBS = 8000.0   # BASELINE.json quotes fractions of 8 TB/s
 FALLBACK_PEAK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
-# ncu --set full capture (profiles/); None until a capture exists for that kernel.
-NCU_TRAFFIC_BYTES = {"lap2d_4096_csr": 1337700000}  # csr_row_kernel<5,double>, profiles/r01e_ncu_full_summary.md
+
+
+def ncu_traffic(workload: str, kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` on `workload` from the committed ncu --set full
+    captures: profiles/ncu_traffic.json, keyed "<workload>|<kernel incl. template arguments>" (written by
+    tools/ncu_summary.py --traffic-json).  None when that exact kernel (e.g. another plan-time batch) was never captured."""
+    try:
+        table = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+    except (OSError, ValueError):
+        return None, None
+    hit = table.get(f"{workload}|{kernel}")
+    if not hit:
+        return None, None
+    return int(hit["dram_bytes"]), hit.get("source")
 
 
 def log(*a):
@@ -300,8 +311,23 @@ def cpu_baseline_hll(chk, n, rp, ci, va, x, nnz, cores, budget_s):
 # ---------------------------------------------------------------------------------------------------
 # arms
 # ---------------------------------------------------------------------------------------------------
+def workload_config(n_gpus, lap3d_n=512):
+    """The `config` object BOTH arms print (same keys, same values: the driver compares them)."""
+    if n_gpus == 1:
+        n = 4096
+        return {"workload": "lap2d_4096_csr", "rows": n * n, "cols": n * n, "nnz": 5 * n * n - 4 * n, "format": "csr",
+                "x": "1+(i mod 7)/8", "step": "one product y = A x, matrix resident",
+                "l2": "inputs_exceed_l2 (1.34 GB streamed per product vs 126 MB L2)"}
+    n = lap3d_n
+    return {"workload": f"lap3d_{n}_power", "rows": n ** 3, "cols": n ** 3, "nnz": 7 * n ** 3 - 6 * n * n, "format": "csr",
+            "x": "x0 = ones", "step": "one power iteration: y = A x; lambda = |y|_2; x = y / lambda",
+            "l2": "inputs_exceed_l2"}
+
+
 def run_reference(args):
-    """The reference's CPU implementation of the path on the host cores, on our arm's config/metric."""
+    """The reference's CPU implementation of the path on the host cores, on our arm's config/metric: at N = 1 one OpenMP
+    CSR product of the full lap2d matrix per step; at N > 1 one power iteration on the FULL lap3d matrix per step
+    (reference spvm_csr_parallel for the product, norm + scale in an OpenMP region of the oracle)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -309,9 +335,9 @@ def run_reference(args):
     from oracle import oracle as O
     chk = O.best_available()
     cores = os.cpu_count() or 1
+    config = workload_config(args.gpus, args.lap3d_n)
     if args.gpus == 1:
         n = 4096
-        workload = "lap2d_4096_csr"
         log("[reference] generating lap2d 4096^2 on the host (numpy twin) ...")
         rp, ci, va = synth.lap2d_csr(n)
         x = 1.0 + (np.arange(n * n) % 7) / 8.0
@@ -322,29 +348,26 @@ def run_reference(args):
         def step():
             chk.spmv_csr_parallel(rp, ci, va, x, starts, ends, y=y)
         sample = f"full lap2d_4096 matrix, one OpenMP CSR product (spvm_csr_parallel) per step on {len(starts)} threads"
-        config = {"workload": workload, "rows": n * n, "nnz": nnz, "format": "csr", "l2": "inputs_exceed_l2"}
         scaling = "weak"
     else:
-        # power iteration on a bounded 3-D Laplacian sample (the 512^3 matrix needs 11.8 GB and ~2 s per
-        # serial product): 256^3, same stencil, same per-iteration algorithm, OpenMP product.
-        n = 256
-        workload = "lap3d_512_power"
-        log("[reference] generating lap3d 256^3 sample on the host ...")
-        rp, ci, va = synth.lap3d_csr(n)
+        n = args.lap3d_n
+        log(f"[reference] generating the full lap3d {n}^3 matrix on the host (OpenMP generator of the oracle) ...")
+        t0 = time.perf_counter()
+        rp, ci, va = O.lap3d_csr_host(n)
         nnz = int(rp[-1])
+        log(f"[reference] {nnz} nnz in {time.perf_counter() - t0:.1f} s")
         starts, ends = chk.partition_rows(rp, cores)
-        state = {"x": np.ones(n ** 3)}
+        x = np.ones(n ** 3)
         y = np.zeros(n ** 3)
+        lam = [0.0]
 
         def step():
-            chk.spmv_csr_parallel(rp, ci, va, state["x"], starts, ends, y=y)
-            lam = float(np.sqrt(np.dot(y, y)))
-            state["x"] = y / lam
-        sample = (f"bounded sample: 256^3 7-point Laplacian ({nnz} nnz, 1/8 of the 512^3 workload), one power iteration "
-                  f"(OpenMP CSR product + norm + scale) per step on {len(starts)} threads; GFLOPS = 2 nnz / t is size independent")
-        config = {"workload": workload, "rows": 512 ** 3, "nnz": 937951232, "format": "csr", "exchange": "none (single host)",
-                  "sample_rows": n ** 3, "l2": "inputs_exceed_l2"}
+            chk.spmv_csr_parallel(rp, ci, va, x, starts, ends, y=y)
+            lam[0] = O.norm_scale(y, x, len(starts))
+        sample = (f"FULL {n}^3 7-point Laplacian ({nnz} nnz), one power iteration per step: reference spvm_csr_parallel on "
+                  f"{len(starts)} threads + norm and scale in an OpenMP region (oracle.c orc_norm_scale)")
         scaling = "strong"
+    assert nnz == config["nnz"], (nnz, config["nnz"])
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -358,6 +381,8 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "GFLOP/s", "cores": len(starts), "kind": chk.kind, "sample": sample},
             "e2e": {"value": value, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if args.gpus > 1:
+        line["lambda"] = lam[0]
     emit(line)
 
 
@@ -404,7 +429,7 @@ def bench_single_gpu(args):
 
     others = {}
     if not args.quick:
-        others = measure_others(args, A, x, y, peak, sampler)
+        others = measure_others(args, A, x, y, peak, sampler, head)
 
     # ---- CPU baseline on the host cores (bounded) ----
     cpu = None
@@ -418,16 +443,18 @@ def bench_single_gpu(args):
             log(f"[bench] cpu baseline failed: {e!r}")
     sampler.stop()
 
+    config = workload_config(1)
+    assert (config["rows"], config["cols"], config["nnz"]) == (M, info.N, nnz)
+    kernel_name = (f"csr_row_kernel<{info.row_batch},double>" if info.auto_algo == device.ALGO_ROW
+                   else device.ALGO_NAMES[info.auto_algo])
+    traffic, traffic_src = ncu_traffic(workload, kernel_name)
     line = {"metric": "spmv_gflops", "value": head["gflops"], "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "rows": M, "cols": info.N, "nnz": nnz, "format": "csr", "x": "1+(i mod 7)/8",
-                       "kernel": device.ALGO_NAMES[info.auto_algo] + " (automatic choice)", "row_batch": info.row_batch,
-                       "max_row_nnz": info.max_row_nnz, "tiles": info.num_tiles,
-                       "l2": "inputs_exceed_l2 (1.34 GB streamed per product vs 126 MB L2)",
-                       "step": "one product y = A x, matrix resident in HBM"},
+            "dtype": "f64", "data": "synthetic", "config": config,
+            "implementation": {"kernel": device.ALGO_NAMES[info.auto_algo] + " (automatic choice)", "kernel_symbol": kernel_name,
+                               "row_batch": info.row_batch, "max_row_nnz": info.max_row_nnz, "tiles": info.num_tiles},
             "roofline": {"bound": "hbm", "achieved": head["gbs"], "peak": peak, "unit": "GB/s", "frac": head["gbs"] / peak,
-                         "traffic": NCU_TRAFFIC_BYTES.get(workload), "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel_name,
                          "algorithmic_bytes_per_launch": int(bytes_alg), "frac_of_8tbs": head["frac_of_8tbs"],
                          "kernel_ms_min": min(per), "kernel_ms_median": statistics.median(per)},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
@@ -435,11 +462,11 @@ def bench_single_gpu(args):
     emit(line)
 
 
-def measure_others(args, A2d, x2d, y2d, peak, sampler):
+def measure_others(args, A2d, x2d, y2d, peak, sampler, head):
     """The remaining single-GPU configs of BASELINE.json -- reported, not the headline."""
     import torch
     from sparsematrixvectormultiplication_b200 import device, synth
-    out = {}
+    out = {"lap2d_4096_csr": dict(head, kernel="the headline product (automatic choice), repeated here for the ratios below")}
     steps, warm = max(5, min(args.steps, 100)), max(3, min(args.warmup, 10))
 
     def run(name, fn, nnz, bytes_alg, extra=None):
@@ -504,16 +531,19 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler):
         out["lap2d_4096_csr_f32"] = {"error": repr(e)}
         log(f"[bench] fp32 leg failed: {e!r}")
 
-    # the reference's own GPU kernels, recompiled unmodified for sm_100a, on the headline matrix ("existing kernel" bar)
-    try:
-        from oracle import oracle as O
-        if O.reference_cuda_available():
+    # the reference's own GPU kernels, recompiled unmodified for sm_100a ("existing kernel" bar), on every single-GPU shape
+    def reference_kernels(name, A, x, y, with_hll=True):
+        try:
+            from oracle import oracle as O
+            if not O.reference_cuda_available():
+                out[f"{name}_reference_kernels"] = {"skipped": "oracle/_ref/libspmv_ref_cuda.so not present"}
+                return
             import ctypes as C
-            ref = O.ReferenceCuda()
-            ia = A2d.info()
-            ptrs = [C.c_void_p() for _ in range(3)]
             from sparsematrixvectormultiplication_b200 import _native as N
-            N.check(N.lib().spmv_b200_csr_device_arrays(A2d._h, *[C.byref(p) for p in ptrs]))
+            ref = O.ReferenceCuda()
+            ia = A.info()
+            ptrs = [C.c_void_p() for _ in range(3)]
+            N.check(N.lib().spmv_b200_csr_device_arrays(A._h, *[C.byref(p) for p in ptrs]))
 
             class _Raw:
                 def __init__(self, p):
@@ -522,29 +552,63 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler):
                 def data_ptr(self):
                     return self.p
             rp, ci, va = (_Raw(p.value) for p in ptrs)
-            yr = torch.empty_like(y2d)
-            A2d.spmv(x2d, y2d)
+            yr = torch.empty_like(y)
+            A.spmv(x, y)
+            scale = float(y.abs().max().item()) or 1.0
+            best = None
             for which, kname in enumerate(O.ReferenceCuda.CSR_KERNELS):
-                run(f"lap2d_4096_reference_{kname}", lambda: ref.csr_spmv(which, ia.M, ia.N, rp, ci, va, x2d, yr), ia.nnz,
-                    ia.algorithmic_bytes, {"kernel": f"reference {kname}, unmodified, recompiled for sm_100a (cuda_src/csr_matrix_cuda.cu)"})
-                err = float((yr - y2d).abs().max().item())
-                out[f"lap2d_4096_reference_{kname}"]["max_abs_diff_vs_ours"] = err
-            H = A2d.to_hll()
-            hi = H.info()
-            host_hll = H.download()
-            handle = ref.hll_upload(C.byref(host_hll.c), ia.M)
-            for which, kname in enumerate(O.ReferenceCuda.HLL_KERNELS):
-                run(f"lap2d_4096_reference_{kname}", lambda: ref.hll_spmv(handle, which, x2d, yr), ia.nnz, hi.algorithmic_bytes,
-                    {"kernel": f"reference {kname}, unmodified, recompiled for sm_100a (cuda_src/hll_matrix.cu); reference row-major block layout in one arena"})
-                out[f"lap2d_4096_reference_{kname}"]["max_abs_diff_vs_ours"] = float((yr - y2d).abs().max().item())
-            ref.hll_free(handle)
-            H.close()
-            del host_hll, yr
-        else:
-            out["lap2d_4096_reference_kernels"] = {"skipped": "oracle/_ref/libspmv_ref_cuda.so not present"}
-    except Exception as e:  # pragma: no cover
-        out["lap2d_4096_reference_kernels"] = {"error": repr(e)}
-        log(f"[bench] reference CUDA kernels failed: {e!r}")
+                key = f"{name}_reference_{kname}"
+                run(key, lambda: ref.csr_spmv(which, ia.M, ia.N, rp, ci, va, x, yr), ia.nnz, ia.algorithmic_bytes,
+                    {"kernel": f"reference {kname}, unmodified, recompiled for sm_100a (cuda_src/csr_matrix_cuda.cu)"})
+                if "error" not in out[key]:
+                    out[key]["max_rel_diff_vs_ours"] = float((yr - y).abs().max().item()) / scale
+                    best = min(best, out[key]["ms"]) if best else out[key]["ms"]
+            if best and f"{name}_csr" in out and "ms" in out[f"{name}_csr"]:
+                out[f"{name}_csr"]["speedup_vs_best_reference_csr_kernel"] = best / out[f"{name}_csr"]["ms"]
+            if with_hll:
+                H = A.to_hll()
+                hi = H.info()
+                host_hll = H.download()
+                handle = ref.hll_upload(C.byref(host_hll.c), ia.M)
+                best = None
+                for which, kname in enumerate(O.ReferenceCuda.HLL_KERNELS):
+                    key = f"{name}_reference_{kname}"
+                    run(key, lambda: ref.hll_spmv(handle, which, x, yr), ia.nnz, hi.algorithmic_bytes,
+                        {"kernel": f"reference {kname}, unmodified, recompiled for sm_100a (cuda_src/hll_matrix.cu); reference row-major block layout in one arena"})
+                    if "error" not in out[key]:
+                        out[key]["max_rel_diff_vs_ours"] = float((yr - y).abs().max().item()) / scale
+                        best = min(best, out[key]["ms"]) if best else out[key]["ms"]
+                if best and f"{name}_hll" in out and "ms" in out[f"{name}_hll"]:
+                    out[f"{name}_hll"]["speedup_vs_best_reference_hll_kernel"] = best / out[f"{name}_hll"]["ms"]
+                ref.hll_free(handle)
+                H.close()
+                del host_hll
+            del yr
+        except Exception as e:  # pragma: no cover
+            out[f"{name}_reference_kernels"] = {"error": repr(e)}
+            log(f"[bench] reference CUDA kernels on {name} failed: {e!r}")
+
+    def e2e_host(name, A, x):
+        """The C-ABI host call (pinned host x -> device, product, device -> pinned host y) on another shape."""
+        try:
+            ia = A.info()
+            xh = torch.empty(ia.N, dtype=torch.float64).pin_memory()
+            xh.copy_(x.cpu())
+            yh = torch.empty(ia.M, dtype=torch.float64).pin_memory()
+            for _ in range(2):
+                A.spmv_host_ptr(xh.data_ptr(), yh.data_ptr())
+            t0 = time.perf_counter()
+            reps = 5
+            for _ in range(reps):
+                A.spmv_host_ptr(xh.data_ptr(), yh.data_ptr())
+            dt = (time.perf_counter() - t0) / reps
+            out[f"{name}_csr_e2e_host"] = {"gflops": 2.0 * ia.nnz / dt / 1e9, "ms": dt * 1e3, "h2d_bytes": 8 * ia.N, "d2h_bytes": 8 * ia.M,
+                                          "api": "spmv_b200_csr_spmv_host"}
+            log(f"[bench] {name} e2e host call: {out[f'{name}_csr_e2e_host']['gflops']:.1f} GFLOP/s ({dt*1e3:.2f} ms)")
+        except Exception as e:  # pragma: no cover
+            out[f"{name}_csr_e2e_host"] = {"error": repr(e)}
+
+    reference_kernels("lap2d_4096", A2d, x2d, y2d)
 
     # config 3: uniform 8M x 8M, 32 nnz/row, CSR vs HLL hack 32
     try:
@@ -555,6 +619,13 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler):
         y = torch.empty(M, dtype=torch.float64, device="cuda")
         csr_variants("uniform_8m_32", A, x, y)
         hll_variants("uniform_8m_32", A, x, y)
+        for knob in ("0", "1"):   # persisting-L2 window on x (SPMV_B200_L2_PERSIST) off / on, same kernels
+            os.environ["SPMV_B200_L2_PERSIST"] = knob
+            ia = A.info()
+            run(f"uniform_8m_32_csr_vector_kernel_l2persist{knob}", lambda: A.spmv(x, y, algo=device.ALGO_VECTOR), ia.nnz, ia.algorithmic_bytes)
+        os.environ.pop("SPMV_B200_L2_PERSIST", None)
+        reference_kernels("uniform_8m_32", A, x, y)
+        e2e_host("uniform_8m_32", A, x)
         A.close()
         del x, y
     except Exception as e:  # pragma: no cover
@@ -573,6 +644,7 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler):
         device.synth_vector(x, 777)
         y = torch.empty(Mr, dtype=torch.float64, device="cuda")
         csr_variants("rmat_24_16", A, x, y)
+        reference_kernels("rmat_24_16", A, x, y, with_hll=False)
         if "rmat_24_16_csr" in out and "error" not in out["rmat_24_16_csr"]:
             out["rmat_24_16_csr"].update({"max_row_nnz": max_row, "long_rows": ia.num_long_rows,
                                           "fragments": ia.num_fragments, "tiles": ia.num_tiles})
@@ -611,58 +683,136 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler):
     return out
 
 
+PARITY_ITERS = 12
+PARITY_TOL = 1e-12   # tools/dist_check.py: x and lambda of every exchange mode vs the single-GPU iteration
+
+
 def bench_multi_gpu(args):
     import torch
     import torch.distributed as dist
     from sparsematrixvectormultiplication_b200 import device, synth
-    from sparsematrixvectormultiplication_b200.distributed import AsyncPowerIteration, FusedPowerIteration, PowerIteration
+    from sparsematrixvectormultiplication_b200.distributed import (AllgatherPowerIteration, AsyncPowerIteration,
+                                                                   FusedPowerIteration, PowerIteration)
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cu = torch.device("cuda", local)
     peak, peak_src = measured_peak()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     n = args.lap3d_n
+    N_rows = n ** 3
     results = {}
-    # T1 of the strong-scaling series, measured in the same run: rank 0 alone iterates on the WHOLE matrix
-    # (11.8 GB at 512^3: fits one GPU) while the other ranks wait at the barrier below
+    # ---- rank 0 alone on the WHOLE matrix (11.8 GB at 512^3: fits one GPU): (1) T1 of the strong-scaling series,
+    # measured in the same run; (2) the parity reference: x and lambda after PARITY_ITERS iterations of the single-GPU
+    # iteration, which every exchange mode below must reproduce on its owned + referenced rows.
     t1 = None
-    if rank == 0 and not args.no_t1:
+    x_ref = torch.empty(N_rows if not args.no_parity else 1, dtype=torch.float64, device=cu)
+    lam_ref = torch.zeros(1, dtype=torch.float64, device=cu)
+    if rank == 0 and not (args.no_t1 and args.no_parity):
         try:
             F1 = FusedPowerIteration(synth.SYNTH_LAP3D, n, single=True, mailbox=True)
-            ms1, _ = time_device(F1.step, max(5, min(args.steps, 30)), args.warmup, None, 1)
-            t1 = {"ms_per_step": ms1, "gflops": 2.0 * F1.nnz_global / (ms1 * 1e-3) / 1e9, "launches_per_step": F1.launches_per_step,
-                  "note": "same workload and kernel on ONE GPU (rank 0 alone, whole matrix), measured in this run"}
-            log(f"[bench] 1 GPU same workload: {t1['gflops']:.1f} GFLOP/s, {ms1:.3f} ms/iteration")
+            if not args.no_parity:
+                for _ in range(PARITY_ITERS):
+                    F1.step()
+                lam_ref[0] = F1.eigenvalue_estimate()
+                x_ref.copy_(F1.normalized_x())
+                F1.reset(1.0)
+            if not args.no_t1:
+                ms1, _ = time_device(F1.step, max(5, min(args.steps, 30)), args.warmup, None, 1)
+                t1 = {"ms_per_step": ms1, "gflops": 2.0 * F1.nnz_global / (ms1 * 1e-3) / 1e9, "launches_per_step": F1.launches_per_step,
+                      "note": "same workload and kernel on ONE GPU (rank 0 alone, whole matrix), measured in this run"}
+                log(f"[bench] 1 GPU same workload: {t1['gflops']:.1f} GFLOP/s, {ms1:.3f} ms/iteration")
             F1.close()
             del F1
             torch.cuda.empty_cache()
         except Exception as e:  # pragma: no cover
             log(f"[bench] single-GPU leg failed: {e!r}")
+            lam_ref[0] = float("nan")
     dist.barrier()
-    for mode in ("fused_async", "fused_mailbox", "fused_peer_stores", "fused_nccl_halo", "halo", "allgather"):
+    if not args.no_parity:
+        dist.broadcast(x_ref, src=0)
+        dist.broadcast(lam_ref, src=0)
+    lam_ref_v = float(lam_ref.item())
+    x_scale = float(x_ref.abs().max().item()) if not args.no_parity else 1.0
+
+    def parity_of(P, mode):
+        """PARITY_ITERS iterations from x0 = 1; x on the owned + referenced rows and lambda against the single-GPU leg."""
+        P.reset(1.0)
+        for _ in range(PARITY_ITERS):
+            P.step()
+        lam = P.eigenvalue_estimate()
+        v = P.normalized_x() if hasattr(P, "normalized_x") else P.x
+        lo = min([P.row_begin] + [a_ for _, a_, _ in P.plan.recvs])
+        hi = max([P.row_end] + [b_ for _, _, b_ in P.plan.recvs])
+        if mode.startswith("allgather"):
+            lo, hi = 0, N_rows            # the whole replica is refreshed
+        err = torch.tensor([float((v[lo:hi] - x_ref[lo:hi]).abs().max().item()) / x_scale,
+                            abs(lam - lam_ref_v) / abs(lam_ref_v)], dtype=torch.float64, device=cu)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        x_err, lam_err = float(err[0].item()), float(err[1].item())
+        ok = bool(x_err <= PARITY_TOL and lam_err <= PARITY_TOL)   # NaN compares false
+        P.reset(1.0)
+        return {"x_err": x_err, "lambda_err": lam_err, "lambda": lam, "ok": ok}
+
+    modes = ("fused_mailbox", "fused_mailbox_hll", "fused_mailbox_csr_hack_aligned", "fused_async", "fused_peer_stores",
+             "fused_nccl_halo", "halo", "allgather", "allgather_broadcasts")
+    if args.modes:
+        modes = tuple(m for m in modes if m in args.modes.split(",") or m == "fused_mailbox")
+    parity = {}
+    for mode in modes:
         if mode == "fused_async":
             P = AsyncPowerIteration(synth.SYNTH_LAP3D, n)
         elif mode == "fused_mailbox":
             P = FusedPowerIteration(synth.SYNTH_LAP3D, n, mailbox=True)
+        elif mode == "fused_mailbox_hll":
+            P = FusedPowerIteration(synth.SYNTH_LAP3D, n, mailbox=True, fmt="hll")
+        elif mode == "fused_mailbox_csr_hack_aligned":
+            # the CSR twin of the HLL mode on the same 32-row-aligned partition, forced onto the fused ROW kernel (the
+            # plan-time choice may be the fused stream kernel, which groups the partial sums differently)
+            os.environ["SPMV_B200_FUSED_BATCH"] = os.environ.get("SPMV_B200_FUSED_BATCH", "5")
+            P = FusedPowerIteration(synth.SYNTH_LAP3D, n, mailbox=True, hack_aligned=True)
         elif mode == "fused_peer_stores":
             P = FusedPowerIteration(synth.SYNTH_LAP3D, n, peer_stores=True)
         elif mode == "fused_nccl_halo":
             P = FusedPowerIteration(synth.SYNTH_LAP3D, n, peer_stores=False)
+        elif mode == "allgather":
+            P = AllgatherPowerIteration(synth.SYNTH_LAP3D, n)
+        elif mode == "allgather_broadcasts":
+            P = PowerIteration(synth.SYNTH_LAP3D, n, exchange="allgather")
         else:
             P = PowerIteration(synth.SYNTH_LAP3D, n, exchange=mode)
+        if not args.no_parity:
+            parity[mode] = parity_of(P, mode)
+            if rank == 0:
+                log(f"[bench] {world} GPUs {mode}: parity after {PARITY_ITERS} iterations: x {parity[mode]['x_err']:.2e}, "
+                    f"lambda {parity[mode]['lambda_err']:.2e} -> {'ok' if parity[mode]['ok'] else 'FAIL'}")
         P.reset(1.0)
         head = mode == "fused_mailbox"
         steps = args.steps if head else max(3, min(args.steps, 20))
         ms, per = time_device(P.step, steps, args.warmup, sampler if head else None, world)
         lam = P.eigenvalue_estimate()
-        recv = P.plan.allgather_doubles_received() if mode == "allgather" else P.plan.halo_doubles_received()
+        if mode == "allgather":
+            recv = P.recv_bytes // 8
+        else:
+            recv = P.plan.allgather_doubles_received() if mode.startswith("allgather") else P.plan.halo_doubles_received()
         results[mode] = {"ms_per_step": ms, "gflops": 2.0 * P.nnz_global / (ms * 1e-3) / 1e9, "steps": steps,
                          "lambda": lam, "rows_local": P.rows, "nnz_local": P.nnz_local, "recv_bytes_per_step": 8 * recv,
                          "launches_per_step": P.launches_per_step, "nnz_global": P.nnz_global,
                          "bytes_local": P.algorithmic_bytes_local}
+        if mode.startswith("allgather"):   # the whole-vector refresh is NVLink bound: say how fast the links ran
+            results[mode]["nvlink_ingress_gbs_if_all_of_the_step"] = 8 * recv / (ms * 1e-3) / 1e9
+        if mode == "allgather":
+            results[mode]["collective"] = ("ONE in-place ncclAllGather (dist.all_gather_into_tensor) over a padded rank-major x, "
+                                           f"stride {P.stride} doubles; interior rows [{P.interior[0]},{P.interior[1]}) of {P.rows} multiplied while it is in flight")
+            try:   # the collective alone, same buffers
+                ams, _ = time_device(lambda: dist.all_gather_into_tensor(P.xg, P.own), 10, 3, None, world)
+                results[mode]["allgather_alone_ms"] = ams
+                results[mode]["allgather_alone_ingress_gbs"] = 8 * recv / (ams * 1e-3) / 1e9
+            except Exception as e:  # pragma: no cover
+                results[mode]["allgather_alone_error"] = repr(e)
         if rank == 0:
             log(f"[bench] {world} GPUs {mode}: {results[mode]['gflops']:.1f} GFLOP/s, {ms:.3f} ms/iteration, lambda={lam:.12g}")
         if head:  # kernel-only product time on this rank (roofline of the dominant kernel)
@@ -670,6 +820,7 @@ def bench_multi_gpu(args):
             kms, kper = time_device(lambda: P.A.spmv_fused(xs[0].data_ptr(), xs[1].data_ptr() + 8 * row_begin, partials=P.partials),
                                     max(5, min(args.steps, 50)), 3, None, world)
             results["product_only_ms"] = kms
+            results["fused_batch"] = int(os.environ.get("SPMV_B200_FUSED_BATCH", "0")) or None
             if getattr(P, "peers", None) and P.peers[1] is not None:   # the same launch with the NVLink peer stores of the boundary rows
                 pms, _ = time_device(lambda: P.A.spmv_fused(xs[0].data_ptr(), xs[1].data_ptr() + 8 * row_begin, partials=P.partials,
                                                             peers=P.peers[1]), max(5, min(args.steps, 50)), 3, None, world)
@@ -679,7 +830,16 @@ def bench_multi_gpu(args):
         if hasattr(P, "close"):
             P.close()
         del P
+        if mode == "fused_mailbox_csr_hack_aligned":
+            os.environ.pop("SPMV_B200_FUSED_BATCH", None)
         torch.cuda.empty_cache()
+    del x_ref
+    torch.cuda.empty_cache()
+    # HLL and CSR iterations on the same hack-aligned partition must agree bit for bit (lambda after the timed run too)
+    if "fused_mailbox_hll" in parity and "fused_mailbox_csr_hack_aligned" in parity:
+        same = parity["fused_mailbox_hll"]["lambda"] == parity["fused_mailbox_csr_hack_aligned"]["lambda"]
+        parity["fused_mailbox_hll"]["lambda_bitwise_equal_to_csr_on_the_same_partition"] = bool(same)
+        parity["fused_mailbox_hll"]["ok"] = parity["fused_mailbox_hll"]["ok"] and bool(same)
     # ---- the plain product y = A x, row-partitioned (no exchange: x is replicated), CSR and HLL, for the other
     # single-GPU shapes: every rank owns an nnz-balanced row range (HLL: cut on 32-row hack boundaries, as the
     # reference cuts HLL work, src/hll_matrix.c:471-498); a step is one product on every rank, time = max over ranks.
@@ -724,20 +884,27 @@ def bench_multi_gpu(args):
             log(f"[bench] partitioned products failed: {e!r}")
     if sampler:
         sampler.stop()
+    parity_ok = all(v["ok"] for v in parity.values()) if parity else None
     if rank == 0:
         h = results["fused_mailbox"]
         gbs = h["bytes_local"] / (results["product_only_ms"] * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic(f"lap3d_{n}_power_rank_of_{world}", "csr_row_fused_kernel")
+        eff = (t1["ms_per_step"] / (world * h["ms_per_step"])) if t1 else None
         line = {"metric": "spmv_gflops", "value": h["gflops"], "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": h["ms_per_step"], "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"lap3d_{n}_power", "rows": n ** 3, "nnz": h["nnz_global"], "format": "csr",
-                           "partition": "contiguous rows balanced by nnz (reference greedy rule)",
-                           "exchange": "boundary rows AND |w|^2 stored into the peers' buffers / mailboxes over NVLink peer memory by the product kernel; no collective call in the loop",
-                           "step": "one power iteration = ONE launch: wait for the peers' tags, w=(A w_prev)/|w_prev|, |w|^2 partials, peer stores of boundary rows, last CTA publishes |w|^2 + tag",
-                           "l2": "inputs_exceed_l2"},
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world, n),
+                "implementation": {
+                    "partition": "contiguous rows balanced by nnz (reference greedy rule)",
+                    "exchange": "boundary rows AND |w|^2 stored into the peers' buffers / mailboxes over NVLink peer memory by the product kernel; no collective call in the loop",
+                    "step": "one power iteration = ONE launch: wait for the peers' tags, w=(A w_prev)/|w_prev|, |w|^2 partials, peer stores of boundary rows, last CTA publishes |w|^2 + tag"},
+                # T1 / (N * T_N) with T1 = the SAME workload and kernel on one GPU, measured in this run (the driver's own
+                # curve divides by the N=1 line of `bench.py --gpus 1`, which is another workload: lap2d single product)
+                "efficiency_same_workload": eff,
+                "parity": {"ok": parity_ok, "iters": PARITY_ITERS, "tolerance": PARITY_TOL,
+                           "reference": "single-GPU fused iteration on rank 0 (whole matrix), x on every rank's owned + referenced rows (max abs error / max |x|) and lambda (relative), max over ranks",
+                           "modes": parity},
                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                             # ncu of the fused kernel at the per-rank size of the 8-GPU run (profiles/r01g_ncu_fused_rank_size.md)
-                             "traffic": 1737000000 if (world == 8 and n == 512) else None,
+                             "traffic": traffic, "traffic_source": traffic_src,
                              "peak_source": peak_src, "note": "rank 0's local CSR product alone (max over ranks); algorithmic bytes of its row slice = 12 nnz_local + 4 (rows+1) + 8 rows + 8 x (referenced columns of x)",
                              "algorithmic_bytes_per_launch": int(h["bytes_local"])},
                 "cpu_baseline": None,
@@ -750,6 +917,9 @@ def bench_multi_gpu(args):
         emit(line)
     dist.barrier()
     dist.destroy_process_group()
+    if parity_ok is False:
+        log("[bench] PARITY FAILED: a multi-GPU exchange mode does not reproduce the single-GPU iteration")
+        sys.exit(1)
 
 
 def main():
@@ -763,6 +933,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--lap3d-n", type=int, default=512)
     ap.add_argument("--no-t1", action="store_true", help="multi-GPU: skip the single-GPU leg of the same workload")
+    ap.add_argument("--no-parity", action="store_true", help="multi-GPU: skip the parity check of every exchange mode against the single-GPU iteration")
+    ap.add_argument("--modes", default="", help="multi-GPU: comma-separated subset of the exchange modes (fused_mailbox always runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     capture_stdout()

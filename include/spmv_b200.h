@@ -213,6 +213,17 @@ int spmv_b200_csr_spmv_fused_async(const spmv_b200_csr *A, const double *d_x, do
  * src/csr_matrix.c:294-313); other rows of y are left untouched.  Vector kernel. */
 int spmv_b200_csr_spmv_rows(const spmv_b200_csr *A, int row_begin, int row_end, const double *d_x,
                             double *d_y, void *stream);
+/* ---- support for the literal "NCCL allgather of x" refresh (BASELINE config 5; no reference counterpart).  One
+ * ncclAllGather needs equal slices, the nnz-balanced row ranges differ by a few rows: x is therefore kept in a PADDED
+ * rank-major layout, part p's entries at [p*stride, p*stride + rows_p), and the column indices of the resident matrix
+ * are rewritten once: c in [starts[p], starts[p+1]) -> p*stride + (c - starts[p]) (monotonic, rows stay sorted).  The
+ * matrix must own its arrays (upload / synth / from_coo); N becomes nparts*stride (the kernel plan does not depend on
+ * column ids and stays). */
+int spmv_b200_csr_remap_columns(spmv_b200_csr *A, int nparts, const long long *starts, long long stride, void *stream);
+/* largest contiguous row range around the middle row whose columns all lie in [col_lo, col_hi): the rows a rank can
+ * multiply BEFORE the refresh of x has landed (their columns are its own slice), overlapping the collective */
+int spmv_b200_csr_interior_rows(const spmv_b200_csr *A, long long col_lo, long long col_hi, int *row_lo, int *row_hi,
+                                void *stream);
 void spmv_b200_csr_free(spmv_b200_csr *A);
 
 /* plan-free launch on raw device arrays: drop-in for
@@ -230,6 +241,9 @@ int spmv_b200_hll_upload(const HLLMatrix *hll, int M, int N, spmv_b200_hll **out
  * convert_to_hll + upload for duplicate-free rows */
 int spmv_b200_hll_from_csr(const spmv_b200_csr *A, void *stream, spmv_b200_hll **out);
 int spmv_b200_hll_info(const spmv_b200_hll *H, spmv_b200_hll_info_t *info);
+/* the column-major device image: hack b owns slots [d_hack_off[b], d_hack_off[b+1]) of d_JA / d_AS, slot(b, r, j) =
+ * d_hack_off[b] + 32 j + r (replaces the reference's array of per-block device pointers, main_cuda.cu:369-402) */
+int spmv_b200_hll_device_arrays(const spmv_b200_hll *H, const long long **d_hack_off, const int **d_JA, const double **d_AS);
 /* device image -> freshly malloc'ed host HLLMatrix in the reference layout (free it with
  * free_hll_matrix); round trip of spmv_b200_hll_upload */
 int spmv_b200_hll_download(const spmv_b200_hll *H, HLLMatrix *out);
@@ -246,6 +260,16 @@ int spmv_b200_hll_spmv_host(spmv_b200_hll *H, const double *x, double *y);
  * src/hll_matrix.c:376-408) */
 int spmv_b200_hll_spmv_hacks(const spmv_b200_hll *H, int hack_begin, int hack_end, const double *d_x,
                              double *d_y, void *stream);
+/* ---- fused iterated product on the HLL image: the twins of spmv_b200_csr_spmv_fused / _fused_mail (same Epilogue:
+ * y = (A x) / sqrt(*d_prev_sumsq) or the mailbox sum, per-CTA partials of y^2 in d_partials, boundary rows mirrored into
+ * `peers`, last CTA publishes |w|^2).  The reference splits HLL work by block ranges (src/hll_matrix.c:376-408,471-498):
+ * a rank owns a contiguous range of hacks, so its local row 0 is a multiple of 32 rows of the global matrix.  For the
+ * same row partition the results are bitwise those of the CSR iteration. ---- */
+int spmv_b200_hll_partials_count(const spmv_b200_hll *H);
+int spmv_b200_hll_spmv_fused(const spmv_b200_hll *H, const double *d_x, double *d_y, const double *d_prev_sumsq,
+                             double *d_partials, const spmv_b200_peers_t *peers, void *stream);
+int spmv_b200_hll_spmv_fused_mail(const spmv_b200_hll *H, const double *d_x, double *d_y, double *d_partials,
+                                  const spmv_b200_peers_t *peers, const spmv_b200_mail_t *mail, void *stream);
 void spmv_b200_hll_free(spmv_b200_hll *H);
 
 /* ---- fp32 storage with fp64 arithmetic (BASELINE.json: y within 1e-5 relative of the serial fp64 product).  The value

@@ -409,3 +409,74 @@ void orc_power_iteration(int M, const int *row_ptr, const int *col_idx, const do
         for (int r = 0; r < M; ++r) x[r] = y[r] / lam;
     }
 }
+
+/* ---- support for bench.py --impl reference at N > 1 (BASELINE config 5 at FULL size on the host) ---------------- */
+
+/* The 7-point Laplacian on an n^3 grid, row r = (i n + j) n + k, columns r-n^2, r-n, r-1, r, r+1, r+n, r+n^2 where they
+ * exist, values -1 x6 and 6 -- the same arrays as synth.lap3d_csr / the device generator
+ * (tests/test_oracle_pinned.py compares them), written by all host threads: 938 M nonzeros in a few seconds instead of
+ * minutes of numpy temporaries.  row_ptr[n^3 + 1]; col_idx / values sized by a first call with col_idx == NULL, which
+ * only fills row_ptr and returns the number of nonzeros. */
+long long orc_lap3d_csr(int n, int *row_ptr, int *col_idx, double *values) {
+    const long long n2 = (long long)n * n, M = n2 * n;
+    row_ptr[0] = 0;
+    /* nnz of row (i, j, k) = 7 - faces touched; the prefix over a whole j-line is closed form, so every i-plane can
+     * be numbered independently: rows before plane i hold 7 n^2 - 4 n (interior planes) or 6 n^2 - 4 n ... simpler and
+     * still exact: count plane by plane (n numbers), then fill the planes in parallel. */
+    long long *plane = malloc(((size_t)n + 1) * sizeof *plane);
+    if (!plane) return -1;
+    plane[0] = 0;
+    for (int i = 0; i < n; ++i) {
+        const long long per_plane = 7 * n2 - 2 * n /* j faces */ - 2 * n /* k faces */ - ((i == 0) + (i == n - 1)) * n2;
+        plane[i + 1] = plane[i] + per_plane;
+    }
+    const long long nnz = plane[n];
+    if (nnz > 0x7fffffffLL) {
+        free(plane);
+        return -1;
+    }
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+        long long at = plane[i];
+        for (int j = 0; j < n; ++j)
+            for (int k = 0; k < n; ++k) {
+                const long long r = ((long long)i * n + j) * n + k;
+                const long long cand[7] = {r - n2, r - n, r - 1, r, r + 1, r + n, r + n2};
+                const int on[7] = {i > 0, j > 0, k > 0, 1, k < n - 1, j < n - 1, i < n - 1};
+                for (int e = 0; e < 7; ++e)
+                    if (on[e]) {
+                        if (col_idx) {
+                            col_idx[at] = (int)cand[e];
+                            values[at] = e == 3 ? 6.0 : -1.0;
+                        }
+                        ++at;
+                    }
+                row_ptr[r + 1] = (int)at;
+            }
+    }
+    free(plane);
+    (void)M;
+    return nnz;
+}
+
+/* lambda = ||y||_2 ; x = y / lambda on all host threads (the norm and scale of one power iteration; the product is the
+ * reference's own spvm_csr_parallel).  Fixed chunking, so the sum does not depend on the thread schedule. */
+double orc_norm_scale(const double *y, double *x, long long n, int threads) {
+    enum { CHUNKS = 1024 };
+    double part[CHUNKS];
+    const long long per = (n + CHUNKS - 1) / CHUNKS;
+    if (threads < 1) threads = 1;
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (int c = 0; c < CHUNKS; ++c) {
+        const long long lo = c * per, hi = lo + per < n ? lo + per : n;
+        double s = 0.0;
+        for (long long r = lo; r < hi; ++r) s += y[r] * y[r];
+        part[c] = s;
+    }
+    double ss = 0.0;
+    for (int c = 0; c < CHUNKS; ++c) ss += part[c];
+    const double lam = sqrt(ss);
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (long long r = 0; r < n; ++r) x[r] = y[r] / lam;
+    return lam;
+}

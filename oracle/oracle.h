@@ -90,6 +90,11 @@ void orc_diff_metrics_cuda(const double *ref, const double *res, int n,
 void orc_power_iteration(int M, const int *row_ptr, const int *col_idx, const double *values,
                          double *x, double *y, int iters, double *lambdas);
 
+/* bench.py --impl reference at N > 1: the full-size 7-point Laplacian written by all host threads (returns nnz; with
+ * col_idx == NULL only row_ptr is filled) and the norm + scale of one power iteration in an OpenMP region. */
+long long orc_lap3d_csr(int n, int *row_ptr, int *col_idx, double *values);
+double orc_norm_scale(const double *y, double *x, long long n, int threads);
+
 #ifdef __cplusplus
 }
 #endif

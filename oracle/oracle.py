@@ -293,6 +293,29 @@ class _DiffMetrics(C.Structure):
     _fields_ = [("mean_abs_err", C.c_double), ("mean_rel_err", C.c_double), ("significant_diffs", C.c_int)]
 
 
+def lap3d_csr_host(n: int):
+    """The n^3 7-point Laplacian (same arrays as synth.lap3d_csr), written by all host threads; bench.py's reference arm."""
+    lib = Restated().lib
+    lib.orc_lap3d_csr.restype = C.c_longlong
+    lib.orc_lap3d_csr.argtypes = [C.c_int, c_int_p, c_int_p, c_dbl_p]
+    M = n ** 3
+    row_ptr = np.empty(M + 1, np.int32)
+    nnz = int(lib.orc_lap3d_csr(n, _ip(row_ptr), None, None))
+    if nnz < 0:
+        raise OracleError("lap3d too large for int32 indices")
+    col_idx, values = np.empty(nnz, np.int32), np.empty(nnz, np.float64)
+    lib.orc_lap3d_csr(n, _ip(row_ptr), _ip(col_idx), _dp(values))
+    return row_ptr, col_idx, values
+
+
+def norm_scale(y, x, threads: int) -> float:
+    """lambda = |y|_2, x = y / lambda on `threads` host threads (OpenMP region of oracle.c)."""
+    lib = Restated().lib
+    lib.orc_norm_scale.restype = C.c_double
+    lib.orc_norm_scale.argtypes = [c_dbl_p, c_dbl_p, C.c_longlong, C.c_int]
+    return float(lib.orc_norm_scale(_dp(y), _dp(x), len(y), int(threads)))
+
+
 def reference_available() -> bool:
     return (HERE / "_ref" / "libspmv_ref.so").exists()
 

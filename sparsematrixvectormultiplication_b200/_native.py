@@ -113,6 +113,8 @@ SIGNATURES = {
     "spmv_b200_csr_from_coo_device": (_I, [_I, _I, _LL, _V, _V, _V, _V, C.POINTER(_V)]),
     "spmv_b200_csr_spmv_rows": (_I, [_V, _I, _I, _V, _V, _V]),
     "spmv_b200_csr_partials_count": (_I, [_V]),
+    "spmv_b200_csr_remap_columns": (_I, [_V, _I, c_ll_p, _LL, _V]),
+    "spmv_b200_csr_interior_rows": (_I, [_V, _LL, _LL, c_int_p, c_int_p, _V]),
     "spmv_b200_csr_spmv_fused": (_I, [_V, _V, _V, _V, _V, C.POINTER(Peers), _V]),
     "spmv_b200_csr_spmv_fused_mail": (_I, [_V, _V, _V, _V, C.POINTER(Peers), C.POINTER(Mail), _V]),
     "spmv_b200_csr_spmv_fused_async": (_I, [_V, _V, _V, _V, C.POINTER(Peers), C.POINTER(Async), _V]),
@@ -127,6 +129,7 @@ SIGNATURES = {
     "spmv_b200_hll_from_csr": (_I, [_V, _V, C.POINTER(_V)]),
     "spmv_b200_hll_info": (_I, [_V, C.POINTER(HllInfo)]),
     "spmv_b200_hll_download": (_I, [_V, C.POINTER(HLLMatrixStruct)]),
+    "spmv_b200_hll_device_arrays": (_I, [_V, C.POINTER(_V), C.POINTER(_V), C.POINTER(_V)]),
     "spmv_b200_hll_spmv": (_I, [_V, _V, _V, _V]),
     "spmv_b200_hll_spmv_slice": (_I, [_V, _V, _V, _V]),
     "spmv_b200_hll_spmv_stream": (_I, [_V, _V, _V, _V]),
@@ -145,6 +148,9 @@ SIGNATURES = {
     "spmv_b200_hll_time": (_I, [_V, _V, _V, _I, _I, _I, c_dbl_p, c_dbl_p]),
     "spmv_b200_hll_spmv_hacks": (_I, [_V, _I, _I, _V, _V, _V]),
     "spmv_b200_hll_free": (None, [_V]),
+    "spmv_b200_hll_partials_count": (_I, [_V]),
+    "spmv_b200_hll_spmv_fused": (_I, [_V, _V, _V, _V, _V, C.POINTER(Peers), _V]),
+    "spmv_b200_hll_spmv_fused_mail": (_I, [_V, _V, _V, _V, C.POINTER(Peers), C.POINTER(Mail), _V]),
     "spmv_b200_synth_csr": (_I, [_I, _LL, _LL, _I, _ULL, _LL, _LL, _V, C.POINTER(_V)]),
     "spmv_b200_synth_row_offset": (_LL, [_I, _LL, _LL, _I, _LL]),
     "spmv_b200_synth_vector": (_I, [_V, _LL, _ULL, _V]),

@@ -39,6 +39,7 @@ constexpr int kSmemSlack = 8;
 constexpr int kVecBatch = 4;                // independent column -> gather chains per lane of the vector kernel
 constexpr long long kAutotuneMinNnz = 1 << 22;  // plan-time timing of the row-kernel batch only pays on large matrices
 constexpr int kRowBatch = 4;                // the same with ONE lane per row (bin 0 of the binned kernel)
+constexpr int kL2PersistDefault = 0;        // persisting-L2 window on x for the gather-bound kernels (SPMV_B200_L2_PERSIST)
 
 // Matrix stream loads of the vector kernels.  Several lanes per row: consecutive lanes read consecutive elements, every
 // sector is consumed by one instruction -> no L1 allocation.  ONE lane per row: lane i walks its own row, a warp's
@@ -142,15 +143,13 @@ csr_tile_kernel(const int2 *__restrict__ tiles, const int *__restrict__ row_ptr,
     }
 }
 
-// One CTA per fragment of a long row; partial[f] = sum over the fragment (fixed tree).
+// One CTA per fragment of a long row; partial[f] = sum over the fragment (fixed tree).  Every thread of the CTA calls it.
 template <typename V>
-__global__ void __launch_bounds__(kFragThreads)
-csr_long_fragment_kernel(const int *__restrict__ long_rows, const int *__restrict__ frag_first, int num_long,
-                         const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
-                         const V *__restrict__ values, const V *__restrict__ x,
-                         double *__restrict__ partial) {
+__device__ __forceinline__ void long_fragment(int f, const int *__restrict__ long_rows, const int *__restrict__ frag_first,
+                                              int num_long, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                                              const V *__restrict__ values, const V *__restrict__ x,
+                                              double *__restrict__ partial) {
     __shared__ double warp_sum[kFragThreads / 32];
-    const int f = blockIdx.x;
     int lo = 0, hi = num_long;  // last long row whose first fragment is <= f
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
@@ -185,6 +184,15 @@ csr_long_fragment_kernel(const int *__restrict__ long_rows, const int *__restric
         for (int w = 0; w < kFragThreads / 32; ++w) total += warp_sum[w];
         partial[f] = total;
     }
+}
+
+template <typename V>
+__global__ void __launch_bounds__(kFragThreads)
+csr_long_fragment_kernel(const int *__restrict__ long_rows, const int *__restrict__ frag_first, int num_long,
+                         const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                         const V *__restrict__ values, const V *__restrict__ x,
+                         double *__restrict__ partial) {
+    long_fragment<V>((int)blockIdx.x, long_rows, frag_first, num_long, row_ptr, col_idx, values, x, partial);
 }
 
 template <typename V>
@@ -280,31 +288,13 @@ csr_row_fused_kernel(int M, const int *__restrict__ row_ptr, const int *__restri
                      const double *__restrict__ x, double *__restrict__ y, const Epilogue ep) {
     __shared__ double warp_sq[8];
     __shared__ double mail_total;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    bool scaled = false;
-    double prev_norm = 1.0;
-    if (ep.mail.world > 0) {
-        if (ep.mail.iteration > 0) {
-            if (warp == 0) {
-                const double total = mail_wait_total(ep.mail, lane);
-                if (lane == 0) mail_total = total;
-            }
-            __syncthreads();
-            scaled = true;
-            prev_norm = sqrt(mail_total);
-        }
-    } else if (ep.prev_sumsq != nullptr) {
-        scaled = true;
-        prev_norm = sqrt(*ep.prev_sumsq);
-    }
-    const double inv_norm = 1.0 / prev_norm;  // one division per thread, one multiplication per row (1 ulp from a division)
-    zero_partials_tail(ep);
+    bool scaled;
+    const double inv_norm = fused_inv_norm(ep, scaled, &mail_total);
     double sq = 0.0;
     for (long long chunk_lo = (long long)blockIdx.x * 256; chunk_lo < M; chunk_lo += (long long)gridDim.x * 256) {
         // peer stores: a CTA-uniform test on the chunk first (uniform datapath), the per-row range test only inside --
         // done per row for every row it cost 30 us per peer per 56 M rows
-        bool boundary = false;
-        for (int p = 0; p < ep.peers.count; ++p) boundary |= chunk_lo < ep.peers.hi[p] && chunk_lo + 256 > ep.peers.lo[p];
+        const bool boundary = fused_chunk_is_boundary(ep, chunk_lo);
         const long long row = chunk_lo + threadIdx.x;
         if (row >= M) continue;
         const int lo = __ldg(row_ptr + row), hi = __ldg(row_ptr + row + 1);
@@ -325,32 +315,9 @@ csr_row_fused_kernel(int M, const int *__restrict__ row_ptr, const int *__restri
         if (scaled) acc *= inv_norm;
         sq = fma(acc, acc, sq);
         y[row] = acc;
-        if (boundary)
-            for (int p = 0; p < ep.peers.count; ++p)
-                if (row >= ep.peers.lo[p] && row < ep.peers.hi[p]) ep.peers.dst[p][row] = acc;
+        if (boundary) fused_peer_store(ep, row, acc);
     }
-    if (ep.partials == nullptr) return;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
-    if (lane == 0) warp_sq[warp] = sq;
-    __syncthreads();  // every row of this CTA (local and peer stores) is issued: a device-scope fence by thread 0 (cumulative
-    if (warp == 0) {  // through the barrier) orders them before the counter and, through it, before the last CTA's sys release
-        unsigned int arrived = 0;
-        if (lane == 0) {
-            double total = 0.0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) total += warp_sq[w];
-            ep.partials[blockIdx.x] = total;
-            if (ep.mail.world > 0) {
-                __threadfence();  // device scope; the system-scope fence is paid once, by the CTA that publishes (mail_publish)
-                arrived = atomicAdd(ep.mail.counter, 1u);
-            }
-        }
-        if (ep.mail.world > 0) {
-            arrived = __shfl_sync(0xffffffffu, arrived, 0);
-            if (arrived == gridDim.x - 1) mail_publish(ep.mail, ep.partials, (int)gridDim.x, lane);
-        }
-    }
+    fused_finish(ep, sq, warp_sq);
 }
 
 // Asynchronous fused product (spmv_b200_csr_spmv_fused_async, spmv_b200.h): the fused row kernel with (1) the chunks
@@ -535,6 +502,10 @@ __host__ __device__ __forceinline__ int bin_of(int len) {
 struct BinLaunch {
     int offset[kBins + 1];
     int block_start[kBins];
+    int frag_blocks;            // CTAs [0, frag_blocks) of the launch own one fragment of a long row each (heaviest work first)
+    int num_long;
+    const int *frag_first;
+    double *frag_partial;
 };
 
 template <int VEC, typename V>
@@ -576,12 +547,18 @@ __device__ __forceinline__ void binned_rows(int local_block, int first, int coun
 
 template <typename V>
 __global__ void __launch_bounds__(256)
-csr_binned_kernel(const BinLaunch plan, const int *__restrict__ bin_rows, const int *__restrict__ row_ptr,
+csr_binned_kernel(const __grid_constant__ BinLaunch plan, const int *__restrict__ bin_rows, const int *__restrict__ row_ptr,
                   const int *__restrict__ col_idx, const V *__restrict__ values, const V *__restrict__ x,
                   V *__restrict__ y, int accumulate) {
+    if ((int)blockIdx.x < plan.frag_blocks) {  // CTA-uniform: a fragment of one of the longest rows (combined afterwards)
+        long_fragment<V>((int)blockIdx.x, bin_rows + plan.offset[kBins - 1], plan.frag_first, plan.num_long, row_ptr, col_idx,
+                         values, x, plan.frag_partial);
+        return;
+    }
+    const int block = (int)blockIdx.x - plan.frag_blocks;
     int bin = 0;
-    while (bin < kBins - 2 && (int)blockIdx.x >= plan.block_start[bin + 1]) ++bin;  // CTA-uniform
-    const int local_block = blockIdx.x - plan.block_start[bin];
+    while (bin < kBins - 2 && block >= plan.block_start[bin + 1]) ++bin;  // CTA-uniform
+    const int local_block = block - plan.block_start[bin];
     const int first = plan.offset[bin], count = plan.offset[bin + 1] - first;
     switch (bin) {
         case 0: binned_rows<1, V>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
@@ -607,6 +584,35 @@ __global__ void bin_key_kernel(int M, const int *__restrict__ row_ptr, unsigned 
     }
     __syncthreads();
     if (threadIdx.x < kBins && local[threadIdx.x]) atomicAdd(&counts[threadIdx.x], local[threadIdx.x]);  // integer: order independent
+}
+
+struct RemapTable {
+    int nparts;
+    long long starts[SPMV_B200_MAX_RANKS + 1];
+    long long stride;
+};
+
+__global__ void remap_columns_kernel(long long nnz, int *__restrict__ col_idx, const __grid_constant__ RemapTable t) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nnz) return;
+    const long long c = col_idx[k];
+    int p = 0;
+    while (p + 1 < t.nparts && c >= t.starts[p + 1]) ++p;
+    col_idx[k] = (int)(p * t.stride + (c - t.starts[p]));
+}
+
+// out[0] = 1 + last row below `mid` that references a column outside [col_lo, col_hi) (0 if none);
+// out[1] = first such row at or above `mid` (M if none).  Integer max / min: order independent.
+__global__ void interior_rows_kernel(int M, int mid, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                                     long long col_lo, long long col_hi, int *__restrict__ out) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= M) return;
+    const int lo = row_ptr[r], hi = row_ptr[r + 1];
+    bool outside = false;
+    if (hi > lo) outside = col_idx[lo] < col_lo || col_idx[hi - 1] >= col_hi;  // rows are column-sorted
+    if (!outside) return;
+    if (r < mid) atomicMax(out, (int)r + 1);
+    else atomicMin(out + 1, (int)r);
 }
 
 __global__ void to_f32_kernel(const double *__restrict__ in, float *__restrict__ out, long long n) {
@@ -858,16 +864,18 @@ static int launch_rows(int row_begin, int row_end, const int *row_ptr, const int
 
 template <typename V>
 static int launch_vector(int row_begin, int row_end, const int *row_ptr, const int *col_idx, const V *values,
-                         const V *x, V *y, int vec, int accumulate, cudaStream_t stream) {
+                         const V *x, V *y, int vec, int accumulate, cudaStream_t stream, size_t x_bytes = 0) {
     const long long rows = (long long)row_end - row_begin;
     if (rows <= 0) return SPMV_B200_OK;
     if (vec == 1) return launch_rows(row_begin, row_end, row_ptr, col_idx, values, x, y, env_int("SPMV_B200_ROW_BATCH", 4), accumulate, stream);
     const unsigned int grid = blocks_for(rows * vec, 256);
     // (8 lanes x 4 gathers per lane is the measured optimum on 32 nonzeros per row: 1208 us; 8 x 8: 1246, 4 x 8: 1415,
     //  16 x 4: 1369 -- profiles/r01d_kernel_selection.md)
+    const XPolicy policy = x_policy(x, x_bytes);
 #define VEC_CASE(W)                                                                                                 \
     case W:                                                                                                         \
-        csr_vector_kernel<W, V><<<grid, 256, 0, stream>>>(row_begin, row_end, row_ptr, col_idx, values, x, y, accumulate); \
+        SPMV_TRY_CUDA(launch_x(csr_vector_kernel<W, V>, grid, 256, 0, stream, policy, row_begin, row_end, row_ptr, col_idx, \
+                               values, x, y, accumulate));                                                          \
         break;
     switch (vec) {
         VEC_CASE(1) VEC_CASE(2) VEC_CASE(4) VEC_CASE(8) VEC_CASE(16) VEC_CASE(32)
@@ -981,15 +989,20 @@ static int launch_binned(const spmv_b200_csr *A, const V *values, const V *x, V 
     BinLaunch L;
     for (int b = 0; b <= kBins; ++b) L.offset[b] = B.offset[b];
     for (int b = 0; b < kBins; ++b) L.block_start[b] = B.block_start[b];
-    if (B.block_start[kBins - 1] > 0) {
-        csr_binned_kernel<V><<<B.block_start[kBins - 1], 256, 0, stream>>>(L, B.rows, A->row_ptr, A->col_idx, values, x, y, accumulate);
-        SPMV_TRY_CUDA(cudaGetLastError());
+    // the fragments of the longest rows ride in the same launch, as its first CTAs (round 1 ran them as a second
+    // launch behind the binned one: 0.29 ms serialised on R-MAT scale 24)
+    L.frag_blocks = B.num_long > 0 ? B.num_frag : 0;
+    L.num_long = B.num_long;
+    L.frag_first = B.frag_first;
+    L.frag_partial = B.frag_partial;
+    const long long blocks = (long long)B.block_start[kBins - 1] + L.frag_blocks;
+    if (blocks > 0x7fffffffLL) return fail(SPMV_B200_ERR_INVALID, "bin plan: too many CTAs");
+    if (blocks > 0) {
+        SPMV_TRY_CUDA(launch_x(csr_binned_kernel<V>, (unsigned int)blocks, 256, 0, stream, x_policy(x, (size_t)A->N * sizeof(V)),
+                               L, B.rows, A->row_ptr, A->col_idx, values, x, y, accumulate));
     }
     if (B.num_long > 0) {
         const int *long_rows = B.rows + B.offset[kBins - 1];
-        csr_long_fragment_kernel<V><<<B.num_frag, kFragThreads, 0, stream>>>(long_rows, B.frag_first, B.num_long, A->row_ptr,
-                                                                            A->col_idx, values, x, B.frag_partial);
-        SPMV_TRY_CUDA(cudaGetLastError());
         csr_long_combine_kernel<V><<<blocks_for(B.num_long, 128), 128, 0, stream>>>(long_rows, B.frag_first, B.num_long,
                                                                                    B.frag_partial, y, accumulate);
         SPMV_TRY_CUDA(cudaGetLastError());
@@ -1030,7 +1043,7 @@ int csr_launch_window(const spmv_b200_csr *A, CsrPath path, int unit_begin, int 
         return launch_rows(unit_begin, unit_end, A->row_ptr, A->col_idx, A->values, x, y, A->row_batch, accumulate, stream);
     if (path == kPathVector)
         return launch_vector(unit_begin, unit_end, A->row_ptr, A->col_idx, A->values, x, y, pick_vector_width(A->nnz, A->M),
-                             accumulate, stream);
+                             accumulate, stream, (size_t)A->N * sizeof(double));
     return launch_tiles(A, x, y, accumulate, path == kPathStream, stream, unit_begin, unit_end);
 }
 
@@ -1055,6 +1068,46 @@ static int launch_fused(const spmv_b200_csr *A, const double *x, double *y, cons
 #undef FROW_CASE
     SPMV_TRY_CUDA(cudaGetLastError());
     return SPMV_B200_OK;
+}
+
+// Per-launch access-policy window over x (handles.cuh).  The device-wide persisting carve-out is raised once per device.
+XPolicy x_policy(const void *x, size_t bytes) {
+    XPolicy p;
+    if (!x || bytes == 0 || env_int("SPMV_B200_L2_PERSIST", kL2PersistDefault) == 0) return p;
+    static int ready[64];
+    static size_t carve[64], max_window[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return p;
+    if (!ready[dev]) {
+        int max_persist = 0, max_win = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        size_t want = (size_t)std::max(max_persist, 0);
+        const int mb = env_int("SPMV_B200_L2_PERSIST_MB", 0);
+        if (mb > 0) want = std::min(want, (size_t)mb << 20);
+        size_t got = 0;
+        if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
+            cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
+        carve[dev] = got;
+        max_window[dev] = (size_t)std::max(max_win, 0);
+        ready[dev] = 1;
+        cudaGetLastError();
+    }
+    if (carve[dev] == 0 || max_window[dev] == 0) return p;
+    const size_t window = std::min(bytes, max_window[dev]);
+    float ratio = window <= carve[dev] ? 1.0f : (float)((double)carve[dev] / (double)window);
+    const int pct = env_int("SPMV_B200_L2_HIT_PCT", 0);
+    if (pct > 0 && pct <= 100) ratio = std::min(ratio, pct / 100.0f);
+    cudaAccessPolicyWindow w = {};
+    w.base_ptr = const_cast<void *>(x);
+    w.num_bytes = window;
+    w.hitRatio = ratio;
+    w.hitProp = cudaAccessPropertyPersisting;
+    w.missProp = env_int("SPMV_B200_L2_MISS_NORMAL", 0) ? cudaAccessPropertyNormal : cudaAccessPropertyStreaming;
+    p.attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    p.attr[0].val.accessPolicyWindow = w;
+    p.count = 1;
+    return p;
 }
 
 static int check_device() {
@@ -1310,13 +1363,61 @@ int spmv_b200_csr_spmv_fused_async(const spmv_b200_csr *A, const double *d_x, do
     return SPMV_B200_OK;
 }
 
+int spmv_b200_csr_remap_columns(spmv_b200_csr *A, int nparts, const long long *starts, long long stride, void *stream) {
+    if (!A || !starts) return fail(SPMV_B200_ERR_INVALID, "csr_remap_columns: NULL argument");
+    if (!A->owns) return fail(SPMV_B200_ERR_INVALID, "csr_remap_columns: the matrix wraps arrays it does not own");
+    if (nparts < 1 || nparts > SPMV_B200_MAX_RANKS || stride < 1 || (long long)nparts * stride > 0x7fffffffLL)
+        return fail(SPMV_B200_ERR_INVALID, "csr_remap_columns: bad layout (%d parts, stride %lld)", nparts, stride);
+    RemapTable t;
+    t.nparts = nparts;
+    t.stride = stride;
+    for (int p = 0; p <= nparts; ++p) {
+        t.starts[p] = starts[p];
+        if (p > 0 && (starts[p] < starts[p - 1] || starts[p] - starts[p - 1] > stride))
+            return fail(SPMV_B200_ERR_INVALID, "csr_remap_columns: part %d does not fit the stride", p - 1);
+    }
+    if (starts[0] != 0 || starts[nparts] != A->N) return fail(SPMV_B200_ERR_INVALID, "csr_remap_columns: the parts must cover [0, N)");
+    if (A->nnz > 0) {
+        remap_columns_kernel<<<blocks_for(A->nnz, 256), 256, 0, as_stream(stream)>>>(A->nnz, A->col_idx, t);
+        SPMV_TRY_CUDA(cudaGetLastError());
+    }
+    A->N = (int)(nparts * stride);  // plans, tiles and the fp32 copy of the values do not depend on the column ids
+    SPMV_TRY_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_csr_interior_rows(const spmv_b200_csr *A, long long col_lo, long long col_hi, int *row_lo, int *row_hi,
+                                void *stream) {
+    if (!A || !row_lo || !row_hi) return fail(SPMV_B200_ERR_INVALID, "csr_interior_rows: NULL argument");
+    *row_lo = 0;
+    *row_hi = A->M;
+    if (A->M == 0) return SPMV_B200_OK;
+    int *d_out = nullptr, out[2] = {0, A->M};
+    SPMV_TRY_CUDA(cudaMalloc(&d_out, sizeof out));
+    cudaError_t e = cudaMemcpyAsync(d_out, out, sizeof out, cudaMemcpyHostToDevice, as_stream(stream));
+    if (e == cudaSuccess) {
+        interior_rows_kernel<<<blocks_for(A->M, 256), 256, 0, as_stream(stream)>>>(A->M, A->M / 2, A->row_ptr, A->col_idx, col_lo,
+                                                                                 col_hi, d_out);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof out, cudaMemcpyDeviceToHost, as_stream(stream));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(as_stream(stream));
+    cudaFree(d_out);
+    SPMV_TRY_CUDA(e);
+    *row_lo = out[0];
+    *row_hi = std::max(out[0], out[1]);
+    return SPMV_B200_OK;
+}
+
 int spmv_b200_csr_spmv_rows(const spmv_b200_csr *A, int row_begin, int row_end, const double *d_x, double *d_y,
                             void *stream) {
     if (!A || !d_y || !d_x) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_rows: NULL argument");
     if (row_begin < 0 || row_end > A->M || row_begin > row_end)
         return fail(SPMV_B200_ERR_INVALID, "csr_spmv_rows: range [%d,%d) outside [0,%d)", row_begin, row_end, A->M);
+    if (A->max_row <= kRowKernelMaxLen)  // stencils: the thread-per-row kernel with the batch tuned at plan time (serial order)
+        return launch_rows(row_begin, row_end, A->row_ptr, A->col_idx, A->values, d_x, d_y, A->row_batch, 0, as_stream(stream));
     return launch_vector(row_begin, row_end, A->row_ptr, A->col_idx, A->values, d_x, d_y,
-                         pick_vector_width(A->nnz, A->M), 0, as_stream(stream));
+                         pick_vector_width(A->nnz, A->M), 0, as_stream(stream), (size_t)A->N * sizeof(double));
 }
 
 int spmv_b200_csr_spmv_raw(int M, long long nnz, const int *d_row_ptr, const int *d_col_idx, const double *d_values,
@@ -1366,7 +1467,8 @@ int spmv_b200_csr_spmv_f32(const spmv_b200_csr *A, const float *d_x, float *d_y,
     cudaStream_t s = as_stream(stream);
     if (path == kPathRow) return launch_rows<float>(0, A->M, A->row_ptr, A->col_idx, A->values32, d_x, d_y, A->row_batch32, accumulate, s);
     if (path == kPathVector)
-        return launch_vector<float>(0, A->M, A->row_ptr, A->col_idx, A->values32, d_x, d_y, pick_vector_width(A->nnz, A->M), accumulate, s);
+        return launch_vector<float>(0, A->M, A->row_ptr, A->col_idx, A->values32, d_x, d_y, pick_vector_width(A->nnz, A->M), accumulate, s,
+                                    (size_t)A->N * sizeof(float));
     return launch_binned<float>(A, A->values32, d_x, d_y, accumulate, s);
 }
 

@@ -28,6 +28,71 @@ __device__ __forceinline__ void zero_partials_tail(const Epilogue &ep) {
         for (int i = (int)gridDim.x + (int)threadIdx.x; i < ep.partials_total; i += (int)blockDim.x) ep.partials[i] = 0.0;
 }
 
+// ---- the fused tail of the iterated product, shared by csr_row_fused_kernel (csr.cu) and hll_row_fused_kernel (hll.cu):
+// 256 threads per CTA, thread t of a CTA owns row chunk*256 + t of every chunk the CTA walks, so both formats produce
+// the same per-CTA partial sums in the same order (bitwise equal |w|^2 for the same partition). ----
+// start of a launch: 1/|w_prev| (from the mailbox, or from *prev_sumsq, or 1)
+__device__ __forceinline__ double fused_inv_norm(const Epilogue &ep, bool &scaled, double *mail_total_smem) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    scaled = false;
+    double prev_norm = 1.0;
+    if (ep.mail.world > 0) {
+        if (ep.mail.iteration > 0) {
+            if (warp == 0) {
+                const double total = mail_wait_total(ep.mail, lane);
+                if (lane == 0) *mail_total_smem = total;
+            }
+            __syncthreads();
+            scaled = true;
+            prev_norm = sqrt(*mail_total_smem);
+        }
+    } else if (ep.prev_sumsq != nullptr) {
+        scaled = true;
+        prev_norm = sqrt(*ep.prev_sumsq);
+    }
+    zero_partials_tail(ep);
+    return 1.0 / prev_norm;  // one division per thread, one multiplication per row (1 ulp from a division)
+}
+
+// does any peer reference a row of the 256-row chunk that starts at chunk_lo?  (CTA-uniform)
+__device__ __forceinline__ bool fused_chunk_is_boundary(const Epilogue &ep, long long chunk_lo) {
+    bool boundary = false;
+    for (int p = 0; p < ep.peers.count; ++p) boundary |= chunk_lo < ep.peers.hi[p] && chunk_lo + 256 > ep.peers.lo[p];
+    return boundary;
+}
+
+__device__ __forceinline__ void fused_peer_store(const Epilogue &ep, long long row, double v) {
+    for (int p = 0; p < ep.peers.count; ++p)
+        if (row >= ep.peers.lo[p] && row < ep.peers.hi[p]) ep.peers.dst[p][row] = v;
+}
+
+// end of a launch: per-CTA partial of the squares (fixed order); with a mailbox the last CTA publishes the rank's sum
+__device__ __forceinline__ void fused_finish(const Epilogue &ep, double sq, double *warp_sq_smem) {
+    if (ep.partials == nullptr) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    if (lane == 0) warp_sq_smem[warp] = sq;
+    __syncthreads();  // every row of this CTA (local and peer stores) is issued: a device-scope fence by thread 0 (cumulative
+    if (warp == 0) {  // through the barrier) orders them before the counter and, through it, before the last CTA's sys release
+        unsigned int arrived = 0;
+        if (lane == 0) {
+            double total = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) total += warp_sq_smem[w];
+            ep.partials[blockIdx.x] = total;
+            if (ep.mail.world > 0) {
+                __threadfence();  // device scope; the system-scope fence is paid once, by the CTA that publishes (mail_publish)
+                arrived = atomicAdd(ep.mail.counter, 1u);
+            }
+        }
+        if (ep.mail.world > 0) {
+            arrived = __shfl_sync(0xffffffffu, arrived, 0);
+            if (arrived == gridDim.x - 1) mail_publish(ep.mail, ep.partials, (int)gridDim.x, lane);
+        }
+    }
+}
+
 constexpr int kBins = 7;  // rows binned by length: 1, 2, 4, 8, 16, 32 lanes per row, and "long" (split into fragments)
 
 struct BinPlan {                 // csr.cu: row-binned vector kernel for skewed matrices (built on first use)
@@ -105,6 +170,7 @@ struct spmv_b200_hll {
     int stream_grid = 0;
     int row_batch = 4;   // hll_row_kernel batch (tuned at plan time on large matrices)
     int row_batch32 = 4; // the same for fp32 storage (tuned by spmv_b200_hll_enable_f32)
+    int fused_batch = 0; // hll_row_fused_kernel batch (tuned at plan time; 0 = row_batch)
     bool narrow_stream = false;  // plan-time timing found the stream kernel faster than every row-kernel batch
     double *stage_x = nullptr;
     double *stage_y = nullptr;
@@ -132,6 +198,32 @@ HllPath hll_resolve(const spmv_b200_hll *H);
 int hll_launch_window(const spmv_b200_hll *H, HllPath path, int unit_begin, int unit_end, const double *x, double *y,
                       cudaStream_t stream);  // units: tiles (stream kernel) or hacks (slice and row kernels)
 int env_int(const char *name, int fallback);
+
+// ---- persisting-L2 window on x (csr.cu) -------------------------------------------------------------------------
+// Gather-bound products (uniform 32/row, R-MAT) re-read x from DRAM because the once-read matrix stream keeps pushing
+// it out of L2 (ncu, round 1: DRAM traffic 1.4-1.6x the algorithmic bytes).  The launches of the gather-bound kernels
+// therefore carry a per-launch access-policy window over x (cudaLaunchAttributeAccessPolicyWindow): hits are
+// "persisting", the rest of the window "streaming"; the device's persisting carve-out (cudaLimitPersistingL2CacheSize)
+// is raised once per device to its maximum.  hitRatio = 1 when x fits the carve-out, else carve-out / bytes, so the
+// persisting lines never thrash among themselves.  SPMV_B200_L2_PERSIST=0 switches it off (plain launches).
+struct XPolicy {
+    cudaLaunchAttribute attr[1];
+    unsigned int count = 0;
+};
+XPolicy x_policy(const void *x, size_t bytes);
+
+template <typename... Params, typename... Args>
+inline cudaError_t launch_x(void (*kernel)(Params...), unsigned int grid, unsigned int block, size_t smem,
+                            cudaStream_t stream, const XPolicy &policy, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cfg.attrs = const_cast<cudaLaunchAttribute *>(policy.attr);
+    cfg.numAttrs = policy.count;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
 // Times launch(candidate) for candidate = first .. 7 on scratch vectors and returns the fastest (plan time, large
 // matrices).  Candidates 2..7 are batches of the row kernels; 0 (first = 0 only, 1 is skipped) stands for the stream kernel.
 template <class Launch>

@@ -120,6 +120,54 @@ hll_row_kernel(int hack_begin, int hack_end, const long long *__restrict__ hack_
     if (row < M) y[row] = (V)acc;
 }
 
+// The lane-per-row kernel with the fused tail of the iterated product (Epilogue, handles.cuh): the HLL twin of
+// csr_row_fused_kernel.  A fixed grid walks the hacks in chunks of 8 (= 256 rows, one warp per hack, thread t of the CTA
+// owns row chunk*256 + t exactly as in the CSR kernel), so for the same row partition both formats produce the same
+// per-CTA partials: |w|^2, lambda and x are bitwise equal to the CSR iteration on rows without padding effects (a
+// padding slot adds v*x = +0.0, which leaves every finite sum unchanged).  Reference: spmv_hll (src/hll_matrix.c:376-408)
+// computes the per-block-range product; the scale / norm / exchange tail has no reference counterpart (BASELINE config 5).
+template <int BATCH>
+__global__ void __launch_bounds__(256, 8)
+hll_row_fused_kernel(int num_hacks, const long long *__restrict__ hack_off, const int *__restrict__ JA,
+                     const double *__restrict__ AS, const double *__restrict__ x, double *__restrict__ y, int M,
+                     const Epilogue ep) {
+    __shared__ double warp_sq[8];
+    __shared__ double mail_total;
+    bool scaled;
+    const double inv_norm = fused_inv_norm(ep, scaled, &mail_total);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double sq = 0.0;
+    for (long long chunk_lo = (long long)blockIdx.x * 256; chunk_lo < M; chunk_lo += (long long)gridDim.x * 256) {
+        const bool boundary = fused_chunk_is_boundary(ep, chunk_lo);
+        const int hack = (int)(chunk_lo >> 5) + warp;
+        if (hack >= num_hacks) continue;  // warp-uniform
+        const long long off = __ldg(hack_off + hack);
+        const int width = (int)((__ldg(hack_off + hack + 1) - off) >> 5);
+        const long long base = off + lane;
+        double acc = 0.0;
+        for (int j = 0; j < width; j += BATCH) {
+            int c[BATCH];
+            double v[BATCH], xv[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) c[u] = j + u < width ? ldg_stream_s32(JA + base + (long long)(j + u) * kHack) : -1;
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) v[u] = j + u < width ? ldg_stream_f64(AS + base + (long long)(j + u) * kHack) : 0.0;
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u)
+                if (c[u] >= 0) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+        }
+        const long long row = chunk_lo + threadIdx.x;
+        if (row >= M) continue;
+        if (scaled) acc *= inv_norm;
+        sq = fma(acc, acc, sq);
+        y[row] = acc;
+        if (boundary) fused_peer_store(ep, row, acc);
+    }
+    fused_finish(ep, sq, warp_sq);
+}
+
 // ---- CSR -> HLL on the device ----------------------------------------------------------------------
 __global__ void hll_width_kernel(int M, int num_hacks, const int *__restrict__ row_ptr, long long *__restrict__ slots,
                                  int *__restrict__ widths) {
@@ -198,6 +246,28 @@ static int hll_launch_rows_t(const spmv_b200_hll *H, const V *AS, int hack_begin
     return SPMV_B200_OK;
 }
 
+// grid of the fused row kernel: 8 CTAs of 256 threads per SM, whatever the matrix size (same rule as the CSR kernel)
+static int hll_fused_grid(const spmv_b200_hll *H) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int)std::max<long long>(1, std::min<long long>(8LL * sms, ((long long)H->M + 255) / 256));
+}
+
+static int hll_launch_fused(const spmv_b200_hll *H, const double *d_x, double *d_y, const Epilogue &ep, cudaStream_t stream,
+                            int batch = -1) {
+    if (batch < 0) batch = env_int("SPMV_B200_HLL_FUSED_BATCH", H->fused_batch > 0 ? H->fused_batch : H->row_batch);
+    const int g = hll_fused_grid(H);
+#define HFUSED_CASE(B) case B: hll_row_fused_kernel<B><<<g, 256, 0, stream>>>(H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep); break;
+    switch (batch) {
+        HFUSED_CASE(2) HFUSED_CASE(3) HFUSED_CASE(5) HFUSED_CASE(6) HFUSED_CASE(7)
+        default: hll_row_fused_kernel<4><<<g, 256, 0, stream>>>(H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep); break;
+    }
+#undef HFUSED_CASE
+    SPMV_TRY_CUDA(cudaGetLastError());
+    return SPMV_B200_OK;
+}
+
 static int hll_launch_rows(const spmv_b200_hll *H, int hack_begin, int hack_end, const double *d_x, double *d_y,
                            cudaStream_t stream) {
     return hll_launch_rows_t<double>(H, H->AS, hack_begin, hack_end, d_x, d_y, stream);
@@ -206,9 +276,9 @@ static int hll_launch_rows(const spmv_b200_hll *H, int hack_begin, int hack_end,
 static int hll_launch(const spmv_b200_hll *H, int hack_begin, int hack_end, const double *d_x, double *d_y,
                       cudaStream_t stream) {
     if (hack_end <= hack_begin) return SPMV_B200_OK;
-    hll_slice_kernel<double><<<blocks_for(hack_end - hack_begin, kHllWarps), kHllThreads, 0, stream>>>(
-        hack_begin, hack_end, H->hack_off, H->JA, H->AS, d_x, d_y, H->M);
-    SPMV_TRY_CUDA(cudaGetLastError());
+    SPMV_TRY_CUDA(launch_x(hll_slice_kernel<double>, blocks_for(hack_end - hack_begin, kHllWarps), kHllThreads, 0, stream,
+                           x_policy(d_x, (size_t)H->N * sizeof(double)), hack_begin, hack_end, H->hack_off, H->JA, H->AS, d_x,
+                           d_y, H->M));
     return SPMV_B200_OK;
 }
 
@@ -253,6 +323,19 @@ static void hll_pick_row_batch(spmv_b200_hll *H, cudaStream_t stream) {
         }, 0);
         if (best == 0) H->narrow_stream = true;
         else H->row_batch = best;
+        // the fused iterated product (scale + |w|^2 partials in the tail) has its own best batch
+        double *partials = nullptr;
+        const int count = hll_fused_grid(H);
+        if (cudaMalloc(&partials, (size_t)count * sizeof(double)) == cudaSuccess) {
+            Epilogue ep;
+            ep.partials = partials;
+            ep.partials_total = count;
+            H->fused_batch = tune_batch(H->M, H->N, H->row_batch, stream, [&](int batch, double *x, double *y) {
+                return hll_launch_fused(H, x, y, ep, stream, batch);
+            });
+        }
+        cudaGetLastError();
+        cudaFree(partials);
     }
 }
 }  // namespace spmv
@@ -413,6 +496,14 @@ int spmv_b200_hll_info(const spmv_b200_hll *H, spmv_b200_hll_info_t *info) {
     return SPMV_B200_OK;
 }
 
+int spmv_b200_hll_device_arrays(const spmv_b200_hll *H, const long long **d_hack_off, const int **d_JA, const double **d_AS) {
+    if (!H) return fail(SPMV_B200_ERR_INVALID, "hll_device_arrays: NULL matrix");
+    if (d_hack_off) *d_hack_off = H->hack_off;
+    if (d_JA) *d_JA = H->JA;
+    if (d_AS) *d_AS = H->AS;
+    return SPMV_B200_OK;
+}
+
 int spmv_b200_hll_download(const spmv_b200_hll *H, HLLMatrix *out) {
     if (!H || !out) return fail(SPMV_B200_ERR_INVALID, "hll_download: NULL argument");
     const int nb = H->num_hacks;
@@ -500,6 +591,41 @@ int spmv_b200_hll_spmv_slice(const spmv_b200_hll *H, const double *d_x, double *
     return hll_launch(H, 0, H->num_hacks, d_x, d_y, as_stream(stream));
 }
 
+int spmv_b200_hll_partials_count(const spmv_b200_hll *H) { return H ? hll_fused_grid(H) : 0; }
+
+int spmv_b200_hll_spmv_fused(const spmv_b200_hll *H, const double *d_x, double *d_y, const double *d_prev_sumsq,
+                             double *d_partials, const spmv_b200_peers_t *peers, void *stream) {
+    if (!H || !d_y || (H->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_fused: NULL argument");
+    if (peers && (peers->count < 0 || peers->count > SPMV_B200_MAX_PEERS))
+        return fail(SPMV_B200_ERR_INVALID, "hll_spmv_fused: bad peer count %d", peers->count);
+    if (H->M == 0) return SPMV_B200_OK;
+    Epilogue ep;
+    ep.prev_sumsq = d_prev_sumsq;
+    ep.partials = d_partials;
+    ep.partials_total = hll_fused_grid(H);
+    if (peers) ep.peers = *peers;
+    return hll_launch_fused(H, d_x, d_y, ep, as_stream(stream));
+}
+
+int spmv_b200_hll_spmv_fused_mail(const spmv_b200_hll *H, const double *d_x, double *d_y, double *d_partials,
+                                  const spmv_b200_peers_t *peers, const spmv_b200_mail_t *mail, void *stream) {
+    if (!H || !d_y || !d_partials || !mail || (H->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_fused_mail: NULL argument");
+    if (H->M == 0) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_fused_mail: a rank without rows cannot take part in the exchange");
+    if (peers && (peers->count < 0 || peers->count > SPMV_B200_MAX_PEERS))
+        return fail(SPMV_B200_ERR_INVALID, "hll_spmv_fused_mail: bad peer count %d", peers->count);
+    if (mail->world < 1 || mail->world > SPMV_B200_MAX_RANKS || mail->rank < 0 || mail->rank >= mail->world || !mail->counter ||
+        !mail->status)
+        return fail(SPMV_B200_ERR_INVALID, "hll_spmv_fused_mail: bad mailbox description (world %d, rank %d)", mail->world, mail->rank);
+    for (int r = 0; r < mail->world; ++r)
+        if (!mail->box[r]) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_fused_mail: mailbox of rank %d is NULL", r);
+    Epilogue ep;
+    ep.partials = d_partials;
+    ep.partials_total = hll_fused_grid(H);
+    if (peers) ep.peers = *peers;
+    ep.mail = *mail;
+    return hll_launch_fused(H, d_x, d_y, ep, as_stream(stream));
+}
+
 int spmv_b200_hll_spmv_hacks(const spmv_b200_hll *H, int hack_begin, int hack_end, const double *d_x, double *d_y,
                              void *stream) {
     if (!H || !d_y || !d_x) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_hacks: NULL argument");
@@ -540,9 +666,9 @@ int spmv_b200_hll_spmv_f32(const spmv_b200_hll *H, const float *d_x, float *d_y,
     if (!H->AS32) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_f32: call spmv_b200_hll_enable_f32 first");
     if (H->num_hacks == 0) return SPMV_B200_OK;
     if (H->max_width <= kRowKernelMaxLen) return hll_launch_rows_t<float>(H, H->AS32, 0, H->num_hacks, d_x, d_y, as_stream(stream));
-    hll_slice_kernel<float><<<blocks_for(H->num_hacks, kHllWarps), kHllThreads, 0, as_stream(stream)>>>(
-        0, H->num_hacks, H->hack_off, H->JA, H->AS32, d_x, d_y, H->M);
-    SPMV_TRY_CUDA(cudaGetLastError());
+    SPMV_TRY_CUDA(launch_x(hll_slice_kernel<float>, blocks_for(H->num_hacks, kHllWarps), kHllThreads, 0, as_stream(stream),
+                           x_policy(d_x, (size_t)H->N * sizeof(float)), 0, H->num_hacks, H->hack_off, H->JA, H->AS32, d_x, d_y,
+                           H->M));
     return SPMV_B200_OK;
 }
 

@@ -4,6 +4,7 @@
  * quicksort used by convert_in_csr (:25-91), write_results_to_csv (:95-138), clear_cache
  * (:141-159), process_matrix_file (:160-172) and create_directory (:200-216).
  */
+#define _DEFAULT_SOURCE /* lstat */
 #include "utility.h"
 
 #include <errno.h>
@@ -85,7 +86,7 @@ int process_matrix_file(const char *filepath, PreMatrix *pre_mat) {
 
 /* One row of the OpenMP driver's result file (reference src/utility.c:95-138, called from main.c:441-450).  The file
  * is opened for appending; an empty file first receives the header.  Column names, column order and the number
- * format ("%.15f") are the reference's -- they are the contract of whatever reads result/*.csv afterwards. */
+ * format ("%.15f") are the reference's -- they are the contract of whatever reads the result CSVs afterwards. */
 void write_results_to_csv(const char *matrix_name, const int num_rows, const int num_cols, const int nz,
                           const int num_threads, const double time_serial, const double time_serial_hll,
                           const double time_parallel, const double time_parallel_simd, const double time_parallel_hll,

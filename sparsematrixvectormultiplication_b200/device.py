@@ -174,6 +174,20 @@ class DeviceCSR:
                                                        C.byref(peers) if peers is not None else None, C.byref(exchange),
                                                        _stream(stream)))
 
+    def remap_columns(self, starts, stride, stream=None):
+        """In place: column c owned by part p (starts[p] <= c < starts[p+1]) becomes p*stride + c - starts[p]; the matrix
+        then has len(starts)-1 times stride columns (spmv_b200_csr_remap_columns: the padded x of the one-collective
+        allgather refresh)."""
+        arr = (C.c_longlong * len(starts))(*[int(v) for v in starts])
+        N.check(N.lib().spmv_b200_csr_remap_columns(self._h, len(starts) - 1, arr, int(stride), _stream(stream)))
+        return self
+
+    def interior_rows(self, col_lo, col_hi, stream=None):
+        """[lo, hi): a contiguous row range whose columns all lie in [col_lo, col_hi) (largest one around the middle row)."""
+        lo, hi = C.c_int(), C.c_int()
+        N.check(N.lib().spmv_b200_csr_interior_rows(self._h, int(col_lo), int(col_hi), C.byref(lo), C.byref(hi), _stream(stream)))
+        return lo.value, hi.value
+
     def spmv_rows(self, row_begin, row_end, x, y, stream=None):
         N.check(N.lib().spmv_b200_csr_spmv_rows(self._h, int(row_begin), int(row_end), _ptr(x), _ptr(y), _stream(stream)))
         return y
@@ -297,6 +311,24 @@ class DeviceHLL:
     def algorithmic_bytes_f32(self) -> int:
         i = self.info()
         return 8 * i.slots + 8 * (i.num_hacks + 1) + 4 * i.M + 4 * i.N
+
+    # -- fused iterated product (twins of DeviceCSR.spmv_fused / spmv_fused_mail) -------------------------------
+    def partials_count(self) -> int:
+        return N.lib().spmv_b200_hll_partials_count(self._h)
+
+    def spmv_fused(self, x_ptr, y_ptr, prev_sumsq=None, partials=None, peers=None, stream=None):
+        def raw(v):
+            return C.c_void_p(v) if isinstance(v, int) else _ptr(v)
+        N.check(N.lib().spmv_b200_hll_spmv_fused(self._h, raw(x_ptr), raw(y_ptr), raw(prev_sumsq) if prev_sumsq is not None else None,
+                                                 raw(partials) if partials is not None else None,
+                                                 C.byref(peers) if peers is not None else None, _stream(stream)))
+
+    def spmv_fused_mail(self, x_ptr, y_ptr, partials, mail, peers=None, stream=None):
+        def raw(v):
+            return C.c_void_p(v) if isinstance(v, int) else _ptr(v)
+        N.check(N.lib().spmv_b200_hll_spmv_fused_mail(self._h, raw(x_ptr), raw(y_ptr), raw(partials),
+                                                      C.byref(peers) if peers is not None else None, C.byref(mail),
+                                                      _stream(stream)))
 
     def spmv_hacks(self, hack_begin, hack_end, x, y, stream=None):
         N.check(N.lib().spmv_b200_hll_spmv_hacks(self._h, int(hack_begin), int(hack_end), _ptr(x), _ptr(y), _stream(stream)))

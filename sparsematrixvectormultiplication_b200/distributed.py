@@ -96,7 +96,8 @@ class _CudaView:
 class PowerIteration:
     """Power method on a synthetic matrix, row-partitioned over the ranks of ``group``."""
 
-    def __init__(self, kind, p0, p1=0, p2=0, seed=0x5EED, exchange="halo", group=None, parts=None, single=False):
+    def __init__(self, kind, p0, p1=0, p2=0, seed=0x5EED, exchange="halo", group=None, parts=None, single=False,
+                 hack_aligned=False):
         import ctypes as C
 
         from . import _native as N
@@ -108,6 +109,8 @@ class PowerIteration:
         self.rank = dist.get_rank(group) if distributed else 0
         self.exchange = exchange
         self.parts = parts if parts is not None else partition.synth_partition(kind, p0, p1, p2, self.world)
+        if hack_aligned:   # HLL work is cut on 32-row block boundaries (reference src/hll_matrix.c:471-498)
+            self.parts = partition.hack_aligned(self.parts, self.parts[-1][1])
         if len(self.parts) != self.world:
             raise ValueError(f"the nnz-balanced partition produced {len(self.parts)} parts for {self.world} ranks")
         self.row_begin, self.row_end = self.parts[self.rank]
@@ -175,12 +178,31 @@ class FusedPowerIteration(PowerIteration):
     collective library call in the loop (include/spmv_b200.h: spmv_b200_csr_spmv_fused_mail)."""
 
     def __init__(self, kind, p0, p1=0, p2=0, seed=0x5EED, group=None, parts=None, single=False, peer_stores=True,
-                 mailbox=False):
-        super().__init__(kind, p0, p1, p2, seed=seed, exchange="halo", group=group, parts=parts, single=single)
+                 mailbox=False, fmt="csr", hack_aligned=None):
+        """fmt="hll": the same iteration on the column-major HLL image (hll_row_fused_kernel); the row ranges are then cut
+        on 32-row hack boundaries as the reference cuts HLL work.  hack_aligned=True with fmt="csr" gives the CSR iteration
+        on exactly that partition (its results are bitwise those of the HLL iteration)."""
+        if hack_aligned is None:
+            hack_aligned = fmt == "hll"
+        super().__init__(kind, p0, p1, p2, seed=seed, exchange="halo", group=group, parts=parts, single=single,
+                         hack_aligned=hack_aligned)
         from . import _native as N
         d = self.dev
         if self.A.info().num_long_rows:
             raise ValueError("FusedPowerIteration needs a matrix without long rows")
+        self.fmt = fmt
+        self.csr = self.A
+        if fmt == "hll":
+            if self.row_begin % 32:
+                raise ValueError("the HLL iteration needs row ranges that start on a hack boundary")
+            self.H = self.csr.to_hll()
+            hi = self.H.info()
+            self.algorithmic_bytes_local += 12 * hi.slots + 8 * (hi.num_hacks + 1) - 12 * self.nnz_local - 4 * (self.rows + 1)
+            self.csr.close()          # only the HLL image stays resident
+            self.csr = None
+            self.A = self.H           # same fused entry points (DeviceHLL.spmv_fused / spmv_fused_mail / partials_count)
+        elif fmt != "csr":
+            raise ValueError(f"unknown format {fmt!r}")
         self.mailbox = bool(mailbox)
         self.peer_stores = (bool(peer_stores) or self.mailbox) and self.world > 1
         cu = self.x.device
@@ -427,3 +449,65 @@ class AsyncPowerIteration(PowerIteration):
             b.close()
         self.box.close()
         self.buf = []
+
+
+class AllgatherPowerIteration(PowerIteration):
+    """The literal reading of BASELINE config 5: x refreshed by ONE NCCL all-gather per iteration.
+
+    ncclAllGather needs equal slices while the nnz-balanced row ranges differ by a few rows (0.2 % at 512^3), so x is
+    kept in a padded rank-major layout: part p's entries live at [p*stride, p*stride + rows_p), stride = the largest
+    part rounded up to 32, and the column indices of the resident matrix are rewritten once on the device
+    (spmv_b200_csr_remap_columns).  The collective is then in place (every rank's send buffer is its own slice of the
+    receive buffer) and moves exactly (world-1)*stride doubles into every GPU -- the NVLink floor of a whole-vector
+    refresh.  Overlap: the rows whose columns all lie in the rank's own slice (everything but the two boundary planes
+    of a stencil) are multiplied WHILE the all-gather is in flight; the boundary rows follow once it has landed.
+
+        step k:   [NCCL stream] all-gather of x_k           |  [compute stream] y = A x_k on the interior rows
+                  boundary rows of y; |y|^2 -> 1-double all-reduce; own slice of x_{k+1} = y / |y|
+
+    Rows are summed by the thread-per-row kernel in index order, so y, lambda and x match the other exchange modes
+    bit for bit apart from the association of the N-rank sum of |y|^2."""
+
+    def __init__(self, kind, p0, p1=0, p2=0, seed=0x5EED, group=None, parts=None, overlap=True):
+        super().__init__(kind, p0, p1, p2, seed=seed, exchange="allgather", group=group, parts=parts)
+        cu = self.x.device
+        rows_max = max(e - s for s, e in self.parts)
+        self.stride = (rows_max + 31) // 32 * 32
+        starts = [s for s, _ in self.parts] + [self.parts[-1][1]]
+        # interior rows first (on the ORIGINAL column ids: own slice = [row_begin, row_end))
+        self.interior = self.A.interior_rows(self.row_begin, self.row_end) if overlap and self.world > 1 else (0, self.rows)
+        self.A.remap_columns(starts, self.stride)
+        del self.x
+        self.xg = torch.ones(self.world * self.stride, dtype=torch.float64, device=cu)   # padded, rank-major
+        self.own = self.xg[self.rank * self.stride: (self.rank + 1) * self.stride]        # send buffer == its slot of xg
+        self.launches_per_step = 5 if self.world > 1 else 3
+        self.recv_bytes = 8 * (self.world - 1) * self.stride
+
+    def reset(self, value=1.0):
+        self.dev.vec_fill(self.xg, value)
+
+    def step(self):
+        d = self.dev
+        lo, hi = self.interior
+        if self.world > 1:
+            work = dist.all_gather_into_tensor(self.xg, self.own, group=self.group, async_op=True)
+            if hi > lo:
+                self.A.spmv_rows(lo, hi, self.xg, self.y)          # reads the own slice only: overlaps the collective
+            work.wait()                                            # compute stream waits for the NCCL stream (no host block)
+            if lo > 0:
+                self.A.spmv_rows(0, lo, self.xg, self.y)
+            if hi < self.rows:
+                self.A.spmv_rows(hi, self.rows, self.xg, self.y)
+        else:
+            self.A.spmv(self.xg, self.y)
+        d.vec_sumsq(self.y, self.ws, self.ss, n=self.rows)
+        if self.world > 1:
+            dist.all_reduce(self.ss, group=self.group)
+        d.vec_scale_by_inv_norm(self.own[:self.rows], self.y, self.ss, n=self.rows)
+
+    def normalized_x(self) -> torch.Tensor:
+        """x in the ORIGINAL (unpadded) index space.  After a step only the own slice is current (the other slices are
+        refreshed by the next step's all-gather), so they are gathered here."""
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.xg, self.own, group=self.group)
+        return torch.cat([self.xg[p * self.stride: p * self.stride + (e - s)] for p, (s, e) in enumerate(self.parts)])

@@ -383,8 +383,10 @@ def test_full_size_lap2d_4096(dev, checker):
 
 
 def test_full_size_uniform_8m_properties(dev, checker):
-    """Config 3: 8.4 M x 8.4 M, 32 nnz/row (268 M nnz, 3.2 GB).  CSR, HLL and the vector kernel must agree
-    within tolerance; sampled row windows are checked exactly against the numpy twin + serial oracle."""
+    """Config 3: 8.4 M x 8.4 M, 32 nnz/row (268 M nnz, 3.2 GB).  EVERY kernel (automatic choice, vector, binned, tile,
+    stream; HLL automatic, slice, stream) against the serial oracle (reference src/csr_matrix.c:130-139) on the WHOLE
+    matrix, componentwise |dy_i| <= 1e-12 * sum_j |a_ij x_j| (all terms are positive, so that sum is y_ref_i itself);
+    three row windows of the downloaded arrays are also checked against the numpy twin of the generator."""
     import torch
     from sparsematrixvectormultiplication_b200 import synth
     M = N = 1 << 23
@@ -408,11 +410,39 @@ def test_full_size_uniform_8m_properties(dev, checker):
     assert float(((y_csr - y_hll).abs() / y_csr).max()) <= TOL
     assert float(((y_csr - y_vec).abs() / y_csr).max()) <= TOL
     xh = synth.hash_vector(N, 4242)
-    yc = y_csr.cpu().numpy()
-    for lo in (0, 1_234_567, M - 4096):
+    assert np.array_equal(x.cpu().numpy(), xh)
+    rp_all, ci_all, va_all = A.download()
+    for lo in (0, 1_234_567, M - 4096):                          # the device generator == its numpy twin
         rp, ci, va = synth.uniform_csr(M, N, 32, synth.DEFAULT_SEED, lo, lo + 4096)
-        y_ref = checker.spmv_csr_serial(rp, ci, va, xh)
-        assert np.max(np.abs(yc[lo:lo + 4096] - y_ref) / y_ref) <= TOL
+        assert np.array_equal(ci_all[32 * lo: 32 * (lo + 4096)], ci) and np.array_equal(va_all[32 * lo: 32 * (lo + 4096)], va)
+        assert np.array_equal(rp_all[lo: lo + 4097] - rp_all[lo], rp)
+    y_ref = checker.spmv_csr_serial(rp_all, ci_all, va_all, xh)   # the whole matrix through the serial oracle
+    del rp_all, ci_all, va_all
+    assert y_ref.min() > 0
+    y_ref_d = torch.from_numpy(y_ref).cuda()
+
+    def whole(y_dev, what):
+        worst = float(((y_dev - y_ref_d).abs() / y_ref_d).max())
+        assert worst <= TOL, f"{what}: max componentwise error {worst:.3e} vs the serial oracle on all {M} rows"
+
+    whole(y_csr, "CSR automatic choice")
+    whole(y_hll, "HLL automatic choice")
+    whole(y_vec, "CSR vector kernel")
+    for algo in (dev.ALGO_BINNED, dev.ALGO_TILE, dev.ALGO_STREAM):
+        A.spmv(x, y_alt, algo=algo)
+        whole(y_alt, f"CSR algo {algo}")
+    for flag in (True, False):
+        H.spmv(x, y_alt, slice_kernel=flag)
+        whole(y_alt, f"HLL slice_kernel={flag}")
+    import os
+    os.environ["SPMV_B200_L2_PERSIST"] = "1"                      # the persisting-L2 window changes no bit
+    try:
+        A.spmv(x, y_alt, algo=dev.ALGO_VECTOR)
+        assert torch.equal(y_alt, y_vec)
+        H.spmv(x, y_alt, slice_kernel=True)
+        whole(y_alt, "HLL slice kernel with the L2 window")
+    finally:
+        os.environ.pop("SPMV_B200_L2_PERSIST", None)
     # linearity: A(2x) = 2 A x exactly (power-of-two scaling commutes with rounding)
     x2 = x * 2.0
     y2 = torch.empty_like(y_csr)
@@ -422,9 +452,10 @@ def test_full_size_uniform_8m_properties(dev, checker):
 
 def test_full_size_rmat_24_properties(dev, checker):
     """Config 4: R-MAT scale 24, 16 edges per row on average, longest row > 100 000 (skewed-row load balancing).
-    The automatic choice (row-binned kernel + long-row fragments) against an independent fp64 reference built from
-    torch ops (index_add of values * x[cols] by row), the other kernels within tolerance, sampled rows exactly
-    against the serial oracle, linearity, run-to-run determinism."""
+    The automatic choice (row-binned kernel, long-row fragments in the same launch) and the tile / stream kernels against
+    the serial oracle (reference src/csr_matrix.c:130-139) on the WHOLE matrix, componentwise
+    |dy_i| <= 1e-12 * sum_j |a_ij x_j| (all terms positive: that sum is y_ref_i); an independent torch index_add
+    reference, linearity and run-to-run determinism on top."""
     import torch
     from sparsematrixvectormultiplication_b200 import synth
     scale = 24
@@ -453,14 +484,17 @@ def test_full_size_rmat_24_properties(dev, checker):
         assert float(((y - y2).abs()[nonempty] / ref[nonempty]).max()) <= 4 * TOL, f"algo {algo}"
     A.spmv(x * 2.0, y2)
     assert torch.equal(y2, y * 2.0), "linearity under power-of-two scaling is exact"
-    # sampled rows (the longest, a few random ones) exactly against the serial oracle on the downloaded rows
-    xh = x.cpu().numpy()
-    picks = [int(lengths.argmax())] + [int(v) for v in torch.randint(0, M, (40,), generator=torch.Generator().manual_seed(1))]
-    for r in picks:
-        a, b = int(rp[r]), int(rp[r + 1])
-        cols, vals = ci[a:b].cpu().numpy(), va[a:b].cpu().numpy()
-        y_ref = checker.spmv_csr_serial(np.array([0, b - a], np.int32), cols, vals, xh)[0]
-        assert abs(float(y[r]) - y_ref) <= TOL * max(y_ref, 1e-300), f"row {r} ({b - a} nonzeros)"
+    # the whole matrix through the serial oracle
+    y_ref = checker.spmv_csr_serial(rp.cpu().numpy(), ci.cpu().numpy(), va.cpu().numpy(), x.cpu().numpy())
+    y_ref_d = torch.from_numpy(y_ref).cuda()
+    assert bool(((y_ref_d > 0) == nonempty).all())
+    for algo, what in ((dev.ALGO_AUTO, "automatic choice (binned)"), (dev.ALGO_TILE, "tile"), (dev.ALGO_STREAM, "stream")):
+        A.spmv(x, y2, algo=algo)
+        worst = float(((y2 - y_ref_d).abs()[nonempty] / y_ref_d[nonempty]).max())
+        assert worst <= TOL, f"{what}: max componentwise error {worst:.3e} vs the serial oracle on all {M} rows"
+        assert bool((y2[~nonempty] == 0).all())
+    longest = int(lengths.argmax())
+    assert abs(float(y[longest]) - y_ref[longest]) <= TOL * y_ref[longest], f"longest row ({int(lengths.max())} nonzeros)"
     A.close()
 
 
@@ -525,6 +559,83 @@ def test_fused_power_iteration_matches_the_oracle(dev, port):
     A.spmv(x, y1)
     A.spmv_fused(x, y2)
     assert torch.equal(y1, y2)
+
+
+@pytest.mark.parametrize("mailbox", [False, True])
+def test_hll_fused_power_iteration_is_bitwise_the_csr_iteration(dev, port, mailbox, monkeypatch):
+    """The HLL twin of the fused iterated product (hll_row_fused_kernel): against the oracle's power iteration within
+    1e-12, and BITWISE against the CSR iteration (same thread -> row mapping, same partial sums; padding slots add +0.0).
+    n = 15: 3375 rows = 105 full hacks + one short hack of 15 rows, rows of 4..7 nonzeros, hacks of width 6 and 7."""
+    import torch
+    from sparsematrixvectormultiplication_b200 import synth
+    from sparsematrixvectormultiplication_b200.distributed import FusedPowerIteration
+    n, iters = 15, 25
+    rp, ci, va = synth.lap3d_csr(n)
+    x_ref, _, lam_ref = port.power_iteration(rp, ci, va, np.ones(n ** 3), iters)
+    monkeypatch.setenv("SPMV_B200_FUSED_BATCH", "4")   # the CSR side: fused ROW kernel (small matrices default to the fused stream kernel, whose partials are grouped differently)
+    Fh = FusedPowerIteration(synth.SYNTH_LAP3D, n, fmt="hll", mailbox=mailbox)
+    Fc = FusedPowerIteration(synth.SYNTH_LAP3D, n, fmt="csr", mailbox=mailbox)
+    for _ in range(iters):
+        Fh.step()
+        Fc.step()
+        assert Fh.eigenvalue_estimate() == Fc.eigenvalue_estimate()
+    assert abs(Fh.eigenvalue_estimate() - lam_ref[-1]) <= TOL * lam_ref[-1]
+    vh, vc = Fh.normalized_x(), Fc.normalized_x()
+    assert torch.equal(vh, vc)
+    assert np.max(np.abs(vh.cpu().numpy() - x_ref)) <= TOL * np.max(np.abs(x_ref))
+    # no scaling, no partials: the plain HLL product in the order of spmv_hll_serial
+    A = dev.DeviceCSR.synth(synth.SYNTH_LAP3D, n)
+    H = A.to_hll()
+    x = torch.from_numpy(ramp(n ** 3)).cuda()
+    y1, y2 = torch.empty_like(x), torch.full_like(x, float("nan"))
+    H.spmv(x, y1, slice_kernel="rows")
+    H.spmv_fused(x, y2)
+    assert torch.equal(y1, y2)
+    # the partials buffer may be larger than the grid of this launch: the tail is zeroed by the launch itself
+    partials = torch.full((H.partials_count() + 7,), float("nan"), dtype=torch.float64, device="cuda")
+    H.spmv_fused(x, y2, partials=partials[:H.partials_count()])
+    assert bool(torch.isfinite(partials[:H.partials_count()]).all())
+    assert abs(float(partials[:H.partials_count()].sum()) - float((y1 * y1).sum())) <= 1e-12 * float((y1 * y1).sum())
+    pc = torch.full((A.partials_count(),), float("nan"), dtype=torch.float64, device="cuda")
+    A.spmv_fused(x, y2, partials=pc)
+    assert bool(torch.isfinite(pc).all()), "entries the fused launch does not own must be zeroed, not left as they were"
+    assert abs(float(pc.sum()) - float((y1 * y1).sum())) <= 1e-12 * float((y1 * y1).sum())
+
+
+def test_padded_allgather_layout_remap_and_interior_rows(dev, checker):
+    """The one-collective allgather refresh keeps x in a padded rank-major layout and rewrites the column indices once
+    (spmv_b200_csr_remap_columns); the product on the remapped matrix with the padded x gives the bits of the original
+    product, and interior_rows finds the rows that only touch the rank's own slice."""
+    import torch
+    from sparsematrixvectormultiplication_b200 import partition, synth
+    n, world = 12, 3
+    parts = partition.synth_partition(synth.SYNTH_LAP3D, n, 0, 0, world)
+    starts = [s for s, _ in parts] + [n ** 3]
+    stride = (max(e - s for s, e in parts) + 31) // 32 * 32
+    xfull = ramp(n ** 3)
+    xpad = np.zeros(world * stride)
+    for p, (s, e) in enumerate(parts):
+        xpad[p * stride: p * stride + e - s] = xfull[s:e]
+    for rank, (lo, hi) in enumerate(parts):
+        rp, ci, va = synth.lap3d_csr(n, lo, hi)
+        y_ref = checker.spmv_csr_serial(rp, ci, va, xfull)
+        A = dev.DeviceCSR.synth(synth.SYNTH_LAP3D, n, row_begin=lo, row_end=hi)
+        ilo, ihi = A.interior_rows(lo, hi)
+        inside = np.array([ci[rp[r]] >= lo and ci[rp[r + 1] - 1] < hi for r in range(hi - lo)])
+        assert inside[ilo:ihi].all() and (ilo == 0 or not inside[ilo - 1]) and (ihi == hi - lo or not inside[ihi])
+        assert ihi - ilo >= (hi - lo) - 2 * n * n              # all but one plane on each side
+        A.remap_columns(starts, stride)
+        assert A.info().N == world * stride
+        _, ci2, _ = A.download()
+        owner = np.searchsorted(np.array(starts), ci, side="right") - 1
+        assert np.array_equal(ci2, owner * stride + ci - np.array(starts)[owner])
+        y = torch.full((hi - lo,), float("nan"), dtype=torch.float64, device="cuda")
+        A.spmv(torch.from_numpy(xpad).cuda(), y)
+        assert np.array_equal(bits(y.cpu().numpy()), bits(y_ref))
+        y.fill_(float("nan"))
+        A.spmv_rows(ilo, ihi, torch.from_numpy(xpad).cuda(), y)
+        got = y.cpu().numpy()
+        assert np.array_equal(bits(got[ilo:ihi]), bits(y_ref[ilo:ihi])) and np.isnan(got[:ilo]).all() and np.isnan(got[ihi:]).all()
 
 
 # ---------------------------------------------------------------------------------------------------

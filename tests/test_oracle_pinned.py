@@ -92,3 +92,19 @@ def test_port_harness_matches_reference(port, reference):
     b = a + rng.standard_normal(500) * (rng.random(500) < 0.2) * 1e-3
     assert port.diff_metrics_c(a, b) == reference.diff_metrics_c(a, b)
     assert port.calculate_flops(12345, 0.5) == reference.calculate_flops(12345, 0.5)
+
+
+def test_host_generator_and_norm_scale_of_the_reference_arm():
+    """bench.py --impl reference at N > 1 builds the FULL 512^3 Laplacian on the host with the oracle's OpenMP generator and
+    does norm + scale in an OpenMP region: both against their numpy definitions."""
+    from oracle import oracle as O
+    from sparsematrixvectormultiplication_b200 import synth
+    for n in (1, 2, 3, 7, 20):
+        got, want = O.lap3d_csr_host(n), synth.lap3d_csr(n)
+        assert all(np.array_equal(a, b) and a.dtype == b.dtype for a, b in zip(got, want)), n
+    rng = np.random.default_rng(3)
+    y = rng.standard_normal(100_003)
+    x = np.empty_like(y)
+    lam = O.norm_scale(y, x, 4)
+    assert abs(lam - np.linalg.norm(y)) <= 1e-13 * lam and np.array_equal(x, y / lam)
+    assert O.norm_scale(y, x, 1) == lam          # fixed chunking: the sum does not depend on the thread count
