@@ -619,11 +619,14 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler, head):
         y = torch.empty(M, dtype=torch.float64, device="cuda")
         csr_variants("uniform_8m_32", A, x, y)
         hll_variants("uniform_8m_32", A, x, y)
+        Hp = A.to_hll()
         for knob in ("0", "1"):   # persisting-L2 window on x (SPMV_B200_L2_PERSIST) off / on, same kernels
             os.environ["SPMV_B200_L2_PERSIST"] = knob
             ia = A.info()
             run(f"uniform_8m_32_csr_vector_kernel_l2persist{knob}", lambda: A.spmv(x, y, algo=device.ALGO_VECTOR), ia.nnz, ia.algorithmic_bytes)
+            run(f"uniform_8m_32_hll_slice_kernel_l2persist{knob}", lambda: Hp.spmv(x, y, slice_kernel=True), ia.nnz, Hp.info().algorithmic_bytes)
         os.environ.pop("SPMV_B200_L2_PERSIST", None)
+        Hp.close()
         reference_kernels("uniform_8m_32", A, x, y)
         e2e_host("uniform_8m_32", A, x)
         A.close()
@@ -644,6 +647,11 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler, head):
         device.synth_vector(x, 777)
         y = torch.empty(Mr, dtype=torch.float64, device="cuda")
         csr_variants("rmat_24_16", A, x, y)
+        for knob, miss in (("0", "0"), ("1", "0"), ("1", "1")):   # x (128 MiB) exceeds the carve-out: hitRatio < 1
+            os.environ["SPMV_B200_L2_PERSIST"], os.environ["SPMV_B200_L2_MISS_NORMAL"] = knob, miss
+            run(f"rmat_24_16_csr_binned_kernel_l2persist{knob}_missnormal{miss}", lambda: A.spmv(x, y, algo=device.ALGO_BINNED), ia.nnz, ia.algorithmic_bytes)
+        os.environ.pop("SPMV_B200_L2_PERSIST", None)
+        os.environ.pop("SPMV_B200_L2_MISS_NORMAL", None)
         reference_kernels("rmat_24_16", A, x, y, with_hll=False)
         if "rmat_24_16_csr" in out and "error" not in out["rmat_24_16_csr"]:
             out["rmat_24_16_csr"].update({"max_row_nnz": max_row, "long_rows": ia.num_long_rows,

@@ -71,6 +71,7 @@ typedef struct {
     int max_row_nnz;     /* longest row                                                      */
     int auto_algo;       /* the SPMV_B200_ALGO_* that SPMV_B200_ALGO_AUTO resolves to        */
     int row_batch;       /* batch of the thread-per-row kernel (tuned at plan time)          */
+    int fused_batch;     /* fused iterated product: 0 = fused stream kernel, else batch of the fused row kernel */
 } spmv_b200_csr_info_t;
 
 typedef struct {
@@ -319,6 +320,49 @@ int spmv_b200_ipc_alloc(long long bytes, void **d_ptr, unsigned char handle[64])
 int spmv_b200_ipc_open(const unsigned char handle[64], void **d_peer_ptr);
 int spmv_b200_ipc_close(void *d_peer_ptr);
 int spmv_b200_ipc_free(void *d_ptr);
+
+/* ---- 1..8 GPUs of one box from plain C: the row-partitioned product and the iterated product (power method, BASELINE
+ * config 5).  ONE process, one host thread, peer access between the devices (multi.cu); devices 0 .. ngpus-1.  The
+ * reference has no multi-GPU path (main_cuda.cu:128-200 drives device 0 only); the partition is its own rule for OpenMP
+ * threads -- contiguous row ranges balanced by nnz (src/csr_matrix.c:167-266), cut on 32-row block boundaries for HLL
+ * (src/hll_matrix.c:471-498) -- with GPUs in the role of threads (fewer GPUs are used when the rule yields fewer
+ * non-empty ranges).  Every GPU holds its rows and a replica of x in a padded rank-major layout (part p at
+ * [p*stride, p*stride + rows_p)); the column indices are rewritten once on the device.
+ *   spmv_b200_multi_iterate(ctx, iters, exchange, &lambda, &ms): iters times  y = A x; lambda = |y|_2; x = y / lambda
+ *     SPMV_B200_EXCHANGE_MAILBOX    ONE fused launch per GPU per iteration, boundary rows and |w|^2 travel through NVLink
+ *                                   peer stores and mailboxes (spmv_b200_csr_spmv_fused_mail / _hll_), no collective
+ *     SPMV_B200_EXCHANGE_ALLGATHER  product, |y|^2, 1-double ncclAllReduce, scale, ONE in-place ncclAllGather of x
+ *                                   (NCCL resolved with dlopen at first use; works for skewed matrices too)
+ *   ms = device time per iteration, cudaEvents on every GPU's stream, maximum over the GPUs.  lambda = |A v_{k-1}| of
+ *   the last iteration.  The iterate continues across calls; spmv_b200_multi_reset starts again from x0 (NULL: ones)
+ *   and is required before switching the exchange mode. ---- */
+#define SPMV_B200_FORMAT_CSR 0
+#define SPMV_B200_FORMAT_HLL 1
+#define SPMV_B200_EXCHANGE_MAILBOX 0
+#define SPMV_B200_EXCHANGE_ALLGATHER 1
+typedef struct spmv_b200_multi spmv_b200_multi;
+typedef struct {
+    int ngpus, format;
+    long long M, N, nnz;
+    long long stride;                               /* slot size of the padded x                                   */
+    int fused_ok;                                   /* 0: rows above the long-row threshold, MAILBOX is refused     */
+    long long row_begin[SPMV_B200_MAX_RANKS], row_end[SPMV_B200_MAX_RANKS], nnz_part[SPMV_B200_MAX_RANKS];
+    long long halo_doubles[SPMV_B200_MAX_RANKS];    /* doubles a GPU receives from its neighbours per iteration     */
+} spmv_b200_multi_info_t;
+/* synthetic matrix generated on the devices (kinds and parameters of spmv_b200_synth_csr) */
+int spmv_b200_multi_init_synth(int ngpus, int format, int kind, long long p0, long long p1, int p2, unsigned long long seed,
+                               spmv_b200_multi **out);
+/* host CSR arrays (reference CSRMatrix fields); partitioned with prepare_thread_distribution, uploaded slice by slice */
+int spmv_b200_multi_init_csr(int ngpus, int format, int M, int N, long long nnz, const int *row_ptr, const int *col_idx,
+                             const double *values, spmv_b200_multi **out);
+int spmv_b200_multi_info(const spmv_b200_multi *ctx, spmv_b200_multi_info_t *info);
+int spmv_b200_multi_reset(spmv_b200_multi *ctx, const double *x0);
+int spmv_b200_multi_iterate(spmv_b200_multi *ctx, int iters, int exchange, double *lambda, double *ms_per_iteration);
+/* the normalised iterate v_k (host, N doubles, original numbering) */
+int spmv_b200_multi_get_x(spmv_b200_multi *ctx, double *x_host);
+/* one row-partitioned product y = A x on host vectors (x: N doubles, y: M doubles) */
+int spmv_b200_multi_spmv(spmv_b200_multi *ctx, const double *x_host, double *y_host);
+void spmv_b200_multi_free(spmv_b200_multi *ctx);
 
 #ifdef __cplusplus
 }

@@ -60,7 +60,7 @@ class CsrInfo(C.Structure):  # include/spmv_b200.h spmv_b200_csr_info_t
     _fields_ = [("M", C.c_int), ("N", C.c_int), ("nnz", C.c_longlong), ("num_tiles", C.c_int),
                 ("num_long_rows", C.c_int), ("num_fragments", C.c_int), ("threads_per_row", C.c_int),
                 ("tile_items", C.c_int), ("long_threshold", C.c_int), ("algorithmic_bytes", C.c_longlong),
-                ("max_row_nnz", C.c_int), ("auto_algo", C.c_int), ("row_batch", C.c_int)]
+                ("max_row_nnz", C.c_int), ("auto_algo", C.c_int), ("row_batch", C.c_int), ("fused_batch", C.c_int)]
 
 
 class HllInfo(C.Structure):  # include/spmv_b200.h spmv_b200_hll_info_t
@@ -82,6 +82,12 @@ class Async(C.Structure):  # include/spmv_b200.h spmv_b200_async_t
     _fields_ = [("world", C.c_int), ("rank", C.c_int), ("iteration", C.c_ulonglong), ("box", C.c_void_p * 8),
                 ("num_recv", C.c_int), ("recv_from", C.c_int * 7), ("send_to", C.c_int * 7),
                 ("counter", C.c_void_p), ("bcounter", C.c_void_p), ("status", C.c_void_p)]
+
+
+class MultiInfo(C.Structure):  # include/spmv_b200.h spmv_b200_multi_info_t
+    _fields_ = [("ngpus", C.c_int), ("format", C.c_int), ("M", C.c_longlong), ("N", C.c_longlong), ("nnz", C.c_longlong),
+                ("stride", C.c_longlong), ("fused_ok", C.c_int), ("row_begin", C.c_longlong * 8), ("row_end", C.c_longlong * 8),
+                ("nnz_part", C.c_longlong * 8), ("halo_doubles", C.c_longlong * 8)]
 
 
 MAILBOX_BYTES = 2 * 8 * 16
@@ -158,6 +164,14 @@ SIGNATURES = {
     "spmv_b200_vec_ws_doubles": (_I, []),
     "spmv_b200_vec_sumsq": (_I, [_V, _LL, _V, _V, _V]),
     "spmv_b200_vec_scale_by_inv_norm": (_I, [_V, _V, _LL, _V, _V]),
+    "spmv_b200_multi_init_synth": (_I, [_I, _I, _I, _LL, _LL, _I, _ULL, C.POINTER(_V)]),
+    "spmv_b200_multi_init_csr": (_I, [_I, _I, _I, _I, _LL, _V, _V, _V, C.POINTER(_V)]),
+    "spmv_b200_multi_info": (_I, [_V, C.POINTER(MultiInfo)]),
+    "spmv_b200_multi_reset": (_I, [_V, _V]),
+    "spmv_b200_multi_iterate": (_I, [_V, _I, _I, c_dbl_p, c_dbl_p]),
+    "spmv_b200_multi_get_x": (_I, [_V, _V]),
+    "spmv_b200_multi_spmv": (_I, [_V, _V, _V]),
+    "spmv_b200_multi_free": (None, [_V]),
     # ---- matrix_parser.h ----
     "init_pre_matrix": (None, [C.POINTER(PreMatrixStruct)]),
     "free_pre_matrix": (None, [C.POINTER(PreMatrixStruct)]),

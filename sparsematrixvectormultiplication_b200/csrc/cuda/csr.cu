@@ -39,7 +39,17 @@ constexpr int kSmemSlack = 8;
 constexpr int kVecBatch = 4;                // independent column -> gather chains per lane of the vector kernel
 constexpr long long kAutotuneMinNnz = 1 << 22;  // plan-time timing of the row-kernel batch only pays on large matrices
 constexpr int kRowBatch = 4;                // the same with ONE lane per row (bin 0 of the binned kernel)
+constexpr int kVec4Default = 2;              // vector kernel: aligned groups of four, two groups in flight per lane (SPMV_B200_VEC4)
 constexpr int kL2PersistDefault = 0;        // persisting-L2 window on x for the gather-bound kernels (SPMV_B200_L2_PERSIST)
+
+__device__ __forceinline__ void ldg_stream_f64x4(const float *p, double (&v)[4]) {  // fp32 storage: one 128-bit load
+    float4 f;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "l"(p));
+    v[0] = f.x;
+    v[1] = f.y;
+    v[2] = f.z;
+    v[3] = f.w;
+}
 
 // Matrix stream loads of the vector kernels.  Several lanes per row: consecutive lanes read consecutive elements, every
 // sector is consumed by one instruction -> no L1 allocation.  ONE lane per row: lane i walks its own row, a warp's
@@ -245,6 +255,74 @@ csr_vector_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, c
 #pragma unroll
     for (int off = VEC >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (live && lane == 0) y[row] = (V)((accumulate && VEC > 1) ? (double)y[row] + acc : acc);
+}
+
+// The same with 128-bit column / 256-bit value loads: every lane owns whole ALIGNED groups of four consecutive nonzeros
+// (group g = the elements [4g, 4g+4) of the arrays; the first and last group of a row are masked to the row).  One
+// LDG.128 + one LDG.256 + four gathers per four nonzeros instead of eight scalar loads + four gathers: on uniform 32/row
+// the scalar kernel sat at 86-90 % L1TEX (LSU instruction issue) while the HLL slice kernel, which already loads like
+// this, was 15 % faster on the same data (gather_bench, profiles/r02a_gather_bench.md).  GROUPS groups per lane are in
+// flight per step.  safe_nnz: elements that vector loads may touch (the arrays of owned matrices are padded to a
+// multiple of four; a wrapped array is only read up to nnz & ~3 this way, the ragged end goes element by element).
+template <typename V>
+__device__ __forceinline__ void load_group(const int *__restrict__ col_idx, const V *__restrict__ values, int g, int lo, int hi,
+                                           int safe_nnz, int (&c)[4], double (&v)[4]) {
+    if (g + 4 <= safe_nnz) {
+        const int4 cc = ldg_stream_s32x4(col_idx + g);
+        ldg_stream_f64x4(values + g, v);
+        c[0] = cc.x; c[1] = cc.y; c[2] = cc.z; c[3] = cc.w;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (g + e < lo || g + e >= hi) c[e] = -1;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const bool on = g + e >= lo && g + e < hi;
+            c[e] = on ? ldg_stream_s32(col_idx + g + e) : -1;
+            v[e] = on ? ldg_stream_f64(values + g + e) : 0.0;
+        }
+    }
+}
+
+template <int VEC, int GROUPS, typename V>
+__global__ void __launch_bounds__(256)
+csr_vector4_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                   const V *__restrict__ values, const V *__restrict__ x, V *__restrict__ y, int accumulate, int safe_nnz) {
+    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long row = row_begin + gt / VEC;
+    const int lane = threadIdx.x & (VEC - 1);
+    const bool live = row < row_end;
+    int lo = 0, hi = 0;
+    if (live) {
+        lo = __ldg(row_ptr + row);
+        hi = __ldg(row_ptr + row + 1);
+    }
+    double acc = 0.0;
+    for (int g = (lo & ~3) + 4 * lane; g < hi; g += 4 * VEC * GROUPS) {
+        int c[GROUPS][4];
+        double v[GROUPS][4], xv[GROUPS][4];
+#pragma unroll
+        for (int u = 0; u < GROUPS; ++u) {
+            if (g + 4 * VEC * u < hi) {
+                load_group(col_idx, values, g + 4 * VEC * u, lo, hi, safe_nnz, c[u], v[u]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) c[u][e] = -1;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < GROUPS; ++u)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) xv[u][e] = c[u][e] >= 0 ? ldg_x(x, c[u][e]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < GROUPS; ++u)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (c[u][e] >= 0) acc = fma(v[u][e], xv[u][e], acc);
+    }
+#pragma unroll
+    for (int off = VEC >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (live && lane == 0) y[row] = (V)(accumulate ? (double)y[row] + acc : acc);
 }
 
 // One THREAD per row (stencil-like matrices, every row short).  Lane i walks row i: a warp's loads are strided by the
@@ -503,6 +581,7 @@ struct BinLaunch {
     int offset[kBins + 1];
     int block_start[kBins];
     int frag_blocks;            // CTAs [0, frag_blocks) of the launch own one fragment of a long row each (heaviest work first)
+    int safe_nnz;               // >= 0: multi-lane classes use aligned groups of four (elements vector loads may touch)
     int num_long;
     const int *frag_first;
     double *frag_partial;
@@ -545,6 +624,37 @@ __device__ __forceinline__ void binned_rows(int local_block, int first, int coun
     if (live && lane == 0) y[row] = (V)((accumulate && VEC > 1) ? (double)y[row] + acc : acc);
 }
 
+// the same rows with aligned groups of four (load_group): one LDG.128 + one LDG.256 per four nonzeros
+template <int VEC, typename V>
+__device__ __forceinline__ void binned_rows4(int local_block, int first, int count, const int *__restrict__ bin_rows,
+                                             const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                                             const V *__restrict__ values, const V *__restrict__ x,
+                                             V *__restrict__ y, int accumulate, int safe_nnz) {
+    const int idx = (local_block * 256 + (int)threadIdx.x) / VEC;
+    const int lane = threadIdx.x & (VEC - 1);
+    const bool live = idx < count;
+    int row = 0, lo = 0, hi = 0;
+    if (live) {
+        row = __ldg(bin_rows + first + idx);
+        lo = __ldg(row_ptr + row);
+        hi = __ldg(row_ptr + row + 1);
+    }
+    double acc = 0.0;
+    for (int g = (lo & ~3) + 4 * lane; g < hi; g += 4 * VEC) {
+        int c[4];
+        double v[4], xv[4];
+        load_group(col_idx, values, g, lo, hi, safe_nnz, c, v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) xv[e] = c[e] >= 0 ? ldg_x(x, c[e]) : 0.0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (c[e] >= 0) acc = fma(v[e], xv[e], acc);
+    }
+#pragma unroll
+    for (int off = VEC >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (live && lane == 0) y[row] = (V)(accumulate ? (double)y[row] + acc : acc);
+}
+
 template <typename V>
 __global__ void __launch_bounds__(256)
 csr_binned_kernel(const __grid_constant__ BinLaunch plan, const int *__restrict__ bin_rows, const int *__restrict__ row_ptr,
@@ -560,6 +670,16 @@ csr_binned_kernel(const __grid_constant__ BinLaunch plan, const int *__restrict_
     while (bin < kBins - 2 && block >= plan.block_start[bin + 1]) ++bin;  // CTA-uniform
     const int local_block = block - plan.block_start[bin];
     const int first = plan.offset[bin], count = plan.offset[bin + 1] - first;
+    if (plan.safe_nnz >= 0 && bin > 0) {  // CTA-uniform: aligned-group loads for the multi-lane classes
+        switch (bin) {
+            case 1: binned_rows4<2, V>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate, plan.safe_nnz); break;
+            case 2: binned_rows4<4, V>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate, plan.safe_nnz); break;
+            case 3: binned_rows4<8, V>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate, plan.safe_nnz); break;
+            case 4: binned_rows4<16, V>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate, plan.safe_nnz); break;
+            default: binned_rows4<32, V>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate, plan.safe_nnz); break;
+        }
+        return;
+    }
     switch (bin) {
         case 0: binned_rows<1, V>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
         case 1: binned_rows<2, V>(local_block, first, count, bin_rows, row_ptr, col_idx, values, x, y, accumulate); break;
@@ -703,6 +823,7 @@ static size_t tile_smem_bytes(const spmv_b200_csr *A) {
 template <typename V>
 static int launch_rows(int row_begin, int row_end, const int *row_ptr, const int *col_idx, const V *values,
                        const V *x, V *y, int batch, int accumulate, cudaStream_t stream);
+static int safe_vector_nnz(const spmv_b200_csr *A);
 static int launch_fused(const spmv_b200_csr *A, const double *x, double *y, const Epilogue &ep, cudaStream_t stream, int batch);
 static int fused_row_grid(const spmv_b200_csr *A);
 
@@ -833,6 +954,11 @@ static int build_plan(spmv_b200_csr *A, cudaStream_t stream) {
     return SPMV_B200_OK;
 }
 
+// elements of col_idx / values that 128/256-bit loads may touch: owned arrays are padded to a multiple of four
+static int safe_vector_nnz(const spmv_b200_csr *A) {
+    return (int)(A->owns ? ((A->nnz + 3) & ~3LL) : (A->nnz & ~3LL));
+}
+
 // lanes per row: about a quarter of the mean row length, so that every lane owns one full batch of kVecBatch gathers
 static int pick_vector_width(long long nnz, int M) {
     const int forced = env_int("SPMV_B200_VECTOR_WIDTH", 0);
@@ -864,10 +990,37 @@ static int launch_rows(int row_begin, int row_end, const int *row_ptr, const int
 
 template <typename V>
 static int launch_vector(int row_begin, int row_end, const int *row_ptr, const int *col_idx, const V *values,
-                         const V *x, V *y, int vec, int accumulate, cudaStream_t stream, size_t x_bytes = 0) {
+                         const V *x, V *y, int vec, int accumulate, cudaStream_t stream, size_t x_bytes = 0, int safe_nnz = -1) {
     const long long rows = (long long)row_end - row_begin;
     if (rows <= 0) return SPMV_B200_OK;
     if (vec == 1) return launch_rows(row_begin, row_end, row_ptr, col_idx, values, x, y, env_int("SPMV_B200_ROW_BATCH", 4), accumulate, stream);
+    // aligned-group kernel (128/256-bit stream loads) for matrices with a plan; lanes per row = an eighth of the mean row
+    // length with two groups in flight per lane (SPMV_B200_VEC4: 0 = scalar kernel, 1 = one group in flight per lane)
+    const int vec4 = env_int("SPMV_B200_VEC4", kVec4Default);
+    if (safe_nnz >= 0 && vec4 != 0 && vec >= 2) {
+        const XPolicy policy4 = x_policy(x, x_bytes);
+        const int groups = vec4 == 1 ? 1 : 2;
+        const int lanes = std::max(1, vec / groups);   // vec = mean/4 lanes of the scalar kernel -> the same elements per step
+        const unsigned int grid4 = blocks_for(rows * lanes, 256);
+#define VEC4_CASE(W, G)                                                                                                     \
+    case W:                                                                                                                 \
+        SPMV_TRY_CUDA(launch_x(csr_vector4_kernel<W, G, V>, grid4, 256, 0, stream, policy4, row_begin, row_end, row_ptr, col_idx, \
+                               values, x, y, accumulate, safe_nnz));                                                        \
+        break;
+        if (groups == 1) {
+            switch (lanes) {
+                VEC4_CASE(1, 1) VEC4_CASE(2, 1) VEC4_CASE(4, 1) VEC4_CASE(8, 1) VEC4_CASE(16, 1) VEC4_CASE(32, 1)
+                default: return fail(SPMV_B200_ERR_INVALID, "bad lane count %d", lanes);
+            }
+        } else {
+            switch (lanes) {
+                VEC4_CASE(1, 2) VEC4_CASE(2, 2) VEC4_CASE(4, 2) VEC4_CASE(8, 2) VEC4_CASE(16, 2)
+                default: return fail(SPMV_B200_ERR_INVALID, "bad lane count %d", lanes);
+            }
+        }
+#undef VEC4_CASE
+        return SPMV_B200_OK;
+    }
     const unsigned int grid = blocks_for(rows * vec, 256);
     // (8 lanes x 4 gathers per lane is the measured optimum on 32 nonzeros per row: 1208 us; 8 x 8: 1246, 4 x 8: 1415,
     //  16 x 4: 1369 -- profiles/r01d_kernel_selection.md)
@@ -991,7 +1144,10 @@ static int launch_binned(const spmv_b200_csr *A, const V *values, const V *x, V 
     for (int b = 0; b < kBins; ++b) L.block_start[b] = B.block_start[b];
     // the fragments of the longest rows ride in the same launch, as its first CTAs (round 1 ran them as a second
     // launch behind the binned one: 0.29 ms serialised on R-MAT scale 24)
-    L.frag_blocks = B.num_long > 0 ? B.num_frag : 0;
+    // SPMV_B200_BINNED_SPLIT=1: the fragments as a launch of their own behind the binned one (round-1 shape, kept for A/B)
+    const bool split = env_int("SPMV_B200_BINNED_SPLIT", 0) != 0;
+    L.frag_blocks = (B.num_long > 0 && !split) ? B.num_frag : 0;
+    L.safe_nnz = env_int("SPMV_B200_VEC4", kVec4Default) != 0 ? safe_vector_nnz(A) : -1;
     L.num_long = B.num_long;
     L.frag_first = B.frag_first;
     L.frag_partial = B.frag_partial;
@@ -1000,6 +1156,11 @@ static int launch_binned(const spmv_b200_csr *A, const V *values, const V *x, V 
     if (blocks > 0) {
         SPMV_TRY_CUDA(launch_x(csr_binned_kernel<V>, (unsigned int)blocks, 256, 0, stream, x_policy(x, (size_t)A->N * sizeof(V)),
                                L, B.rows, A->row_ptr, A->col_idx, values, x, y, accumulate));
+    }
+    if (B.num_long > 0 && split) {
+        csr_long_fragment_kernel<V><<<B.num_frag, kFragThreads, 0, stream>>>(B.rows + B.offset[kBins - 1], B.frag_first, B.num_long,
+                                                                            A->row_ptr, A->col_idx, values, x, B.frag_partial);
+        SPMV_TRY_CUDA(cudaGetLastError());
     }
     if (B.num_long > 0) {
         const int *long_rows = B.rows + B.offset[kBins - 1];
@@ -1043,7 +1204,7 @@ int csr_launch_window(const spmv_b200_csr *A, CsrPath path, int unit_begin, int 
         return launch_rows(unit_begin, unit_end, A->row_ptr, A->col_idx, A->values, x, y, A->row_batch, accumulate, stream);
     if (path == kPathVector)
         return launch_vector(unit_begin, unit_end, A->row_ptr, A->col_idx, A->values, x, y, pick_vector_width(A->nnz, A->M),
-                             accumulate, stream, (size_t)A->N * sizeof(double));
+                             accumulate, stream, (size_t)A->N * sizeof(double), safe_vector_nnz(A));
     return launch_tiles(A, x, y, accumulate, path == kPathStream, stream, unit_begin, unit_end);
 }
 
@@ -1237,6 +1398,7 @@ int spmv_b200_csr_info(const spmv_b200_csr *A, spmv_b200_csr_info_t *info) {
         default: info->auto_algo = SPMV_B200_ALGO_TILE; break;
     }
     info->row_batch = A->row_batch;
+    info->fused_batch = A->fused_batch;
     return SPMV_B200_OK;
 }
 
@@ -1417,7 +1579,7 @@ int spmv_b200_csr_spmv_rows(const spmv_b200_csr *A, int row_begin, int row_end, 
     if (A->max_row <= kRowKernelMaxLen)  // stencils: the thread-per-row kernel with the batch tuned at plan time (serial order)
         return launch_rows(row_begin, row_end, A->row_ptr, A->col_idx, A->values, d_x, d_y, A->row_batch, 0, as_stream(stream));
     return launch_vector(row_begin, row_end, A->row_ptr, A->col_idx, A->values, d_x, d_y,
-                         pick_vector_width(A->nnz, A->M), 0, as_stream(stream), (size_t)A->N * sizeof(double));
+                         pick_vector_width(A->nnz, A->M), 0, as_stream(stream), (size_t)A->N * sizeof(double), safe_vector_nnz(A));
 }
 
 int spmv_b200_csr_spmv_raw(int M, long long nnz, const int *d_row_ptr, const int *d_col_idx, const double *d_values,
@@ -1468,7 +1630,7 @@ int spmv_b200_csr_spmv_f32(const spmv_b200_csr *A, const float *d_x, float *d_y,
     if (path == kPathRow) return launch_rows<float>(0, A->M, A->row_ptr, A->col_idx, A->values32, d_x, d_y, A->row_batch32, accumulate, s);
     if (path == kPathVector)
         return launch_vector<float>(0, A->M, A->row_ptr, A->col_idx, A->values32, d_x, d_y, pick_vector_width(A->nnz, A->M), accumulate, s,
-                                    (size_t)A->N * sizeof(float));
+                                    (size_t)A->N * sizeof(float), safe_vector_nnz(A));
     return launch_binned<float>(A, A->values32, d_x, d_y, accumulate, s);
 }
 

@@ -26,7 +26,8 @@
 
 namespace spmv {
 
-constexpr int kMaxWindows = 16;  // measured on lap2d 4096^2: 4 -> 3.93 ms, 8 -> 3.49, 16 -> 3.42, 24 -> 3.91, 32 -> 3.65, 48 -> 3.89
+constexpr int kMaxWindows = 64;  // events; the automatic choice stops at kAutoWindows.  Round 1, equal windows, measured on lap2d 4096^2: 4 -> 3.93 ms, 8 -> 3.49, 16 -> 3.42, 24 -> 3.91, 32 -> 3.65, 48 -> 3.89
+constexpr int kAutoWindows = 16;
 constexpr long long kMinWindowBytes = 2LL << 20;  // below 2 MB of x + y per window the launch overheads win
 
 struct HostPipe {
@@ -125,7 +126,7 @@ static int plan_needs(HostPipe *p, const int *d_idx, const std::vector<long long
 static int pick_windows(long long M, long long N, int units) {
     const int forced = env_int("SPMV_B200_HOST_WINDOWS", 0);
     long long w = forced > 0 ? forced : (8 * (M + N)) / kMinWindowBytes;
-    w = std::max<long long>(1, std::min<long long>(w, kMaxWindows));
+    w = std::max<long long>(1, std::min<long long>(w, forced > 0 ? kMaxWindows : kAutoWindows));
     return (int)std::max<long long>(1, std::min<long long>(w, units));
 }
 
