@@ -39,7 +39,7 @@ constexpr int kSmemSlack = 8;
 constexpr int kVecBatch = 4;                // independent column -> gather chains per lane of the vector kernel
 constexpr long long kAutotuneMinNnz = 1 << 22;  // plan-time timing of the row-kernel batch only pays on large matrices
 constexpr int kRowBatch = 4;                // the same with ONE lane per row (bin 0 of the binned kernel)
-constexpr int kVec4Default = 2;              // vector kernel: aligned groups of four, two groups in flight per lane (SPMV_B200_VEC4)
+constexpr int kVec4Default = 1;              // vector / binned kernels: aligned groups of four nonzeros per lane (SPMV_B200_VEC4)
 constexpr int kL2PersistDefault = 0;        // persisting-L2 window on x for the gather-bound kernels (SPMV_B200_L2_PERSIST)
 
 __device__ __forceinline__ void ldg_stream_f64x4(const float *p, double (&v)[4]) {  // fp32 storage: one 128-bit load
@@ -994,13 +994,15 @@ static int launch_vector(int row_begin, int row_end, const int *row_ptr, const i
     const long long rows = (long long)row_end - row_begin;
     if (rows <= 0) return SPMV_B200_OK;
     if (vec == 1) return launch_rows(row_begin, row_end, row_ptr, col_idx, values, x, y, env_int("SPMV_B200_ROW_BATCH", 4), accumulate, stream);
-    // aligned-group kernel (128/256-bit stream loads) for matrices with a plan; lanes per row = an eighth of the mean row
-    // length with two groups in flight per lane (SPMV_B200_VEC4: 0 = scalar kernel, 1 = one group in flight per lane)
+    // aligned-group kernel (128/256-bit stream loads) for matrices with a plan.  SPMV_B200_VEC4: 0 = scalar kernel,
+    // 1 = one group of four per lane and step (default), 2 = two groups in flight per lane.  Lanes per row = an eighth
+    // of the mean row length, i.e. a lane walks two groups: measured on uniform 32/row (tools/r02_diag.py, 3 rounds):
+    // 4 lanes x 1 group 1.24 ms, 8 x 1 1.27, 4 x 2 1.36, scalar 8 lanes x 4 1.21 cold / 1.37 sustained, HLL slice 1.23.
     const int vec4 = env_int("SPMV_B200_VEC4", kVec4Default);
     if (safe_nnz >= 0 && vec4 != 0 && vec >= 2) {
         const XPolicy policy4 = x_policy(x, x_bytes);
         const int groups = vec4 == 1 ? 1 : 2;
-        const int lanes = std::max(1, vec / groups);   // vec = mean/4 lanes of the scalar kernel -> the same elements per step
+        const int lanes = env_int("SPMV_B200_VECTOR_WIDTH", 0) > 0 ? std::max(1, vec / groups) : std::max(2, vec / 2);
         const unsigned int grid4 = blocks_for(rows * lanes, 256);
 #define VEC4_CASE(W, G)                                                                                                     \
     case W:                                                                                                                 \

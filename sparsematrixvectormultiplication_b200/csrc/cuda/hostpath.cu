@@ -6,11 +6,20 @@
 // PCIe link, not by HBM: 8 bytes up per column and 8 bytes down per row against 12 bytes per nonzero streamed at
 // ~100x the speed.  The link is full duplex, so the call is organised to keep BOTH directions busy:
 //
-//   * the rows are cut into W windows (whole tiles of the plan, i.e. equal bytes of matrix stream);
-//   * x travels in W chunks on an upload stream; window w is launched on a compute stream as soon as the chunk that
-//     holds its largest referenced column has landed (need[w] = running maximum of max(col)+1 over windows 0..w,
-//     found once per matrix by a reduction over col_idx / JA);
+//   * the rows are cut into W windows (whole tiles of the plan / rows / hacks);
+//   * x travels in pieces on an upload stream, piece w ending exactly where window w's referenced columns end
+//     (need[w] = running maximum of max(col)+1 over windows 0..w, found once per matrix by a reduction over col_idx /
+//     JA, rounded up to 256 KB), so window w is launched on a compute stream the moment ITS piece has landed;
 //   * the rows of window w are copied back on a download stream as soon as its kernel is done.
+//
+// Window sizes (round 2; measured on the B200 box, tools/r02_diag.py): one direction alone runs at 55.4 GB/s, both at
+// once at 47.9 GB/s each, so 128 MiB up + 128 MiB down cannot take less than 2.80 ms.  Equal windows lose to that
+// floor at both ends -- nothing comes down until the first window has its x (round 1: TWO equal chunks, because a
+// window's halo reached into the next chunk) and nothing goes up while the last window drains -- and every extra copy
+// costs ~3.5 us of engine turnaround, so more equal windows do not help (16 -> 3.41 ms, 32 -> 3.66, 64 -> 3.74).
+// Copies whose boundaries are not multiples of a large power of two are slower on top (12 windows 3.67 ms, 24 -> 3.87):
+// that was the "non-monotonic" sweep of round 1.  Hence TAPERED windows on 2 MiB boundaries: 1, 1, 2, 4, 8 units of
+// 2 MiB at the start, 16-unit windows in the middle, 8, 4, 2, 1, 1 at the end.
 //
 // For banded matrices (stencils, FEM) the upload of chunk w+1, the product of window w and the download of window
 // w-1 overlap, and the call takes max(upload, download) instead of their sum.  For matrices whose rows reference
@@ -28,6 +37,8 @@ namespace spmv {
 
 constexpr int kMaxWindows = 64;  // events; the automatic choice stops at kAutoWindows.  Round 1, equal windows, measured on lap2d 4096^2: 4 -> 3.93 ms, 8 -> 3.49, 16 -> 3.42, 24 -> 3.91, 32 -> 3.65, 48 -> 3.89
 constexpr int kAutoWindows = 16;
+constexpr long long kUnitRows = (2LL << 20) / 8;      // 2 MiB of y
+constexpr long long kPieceAlign = (256LL << 10) / 8;  // upload pieces end on 256 KB boundaries of x
 constexpr long long kMinWindowBytes = 2LL << 20;  // below 2 MB of x + y per window the launch overheads win
 
 struct HostPipe {
@@ -41,6 +52,7 @@ struct HostPipe {
     std::vector<int> unit;        // W+1: first tile / row / hack of every window
     std::vector<long long> row;   // W+1: first row of every window
     std::vector<long long> need;  // W: doubles of x that must be resident before window w starts (running maximum)
+    std::vector<long long> piece; // W: upload piece w ends here (need[w] rounded up to kPieceAlign, <= N; non-decreasing)
 };
 
 void host_pipe_free(HostPipe *p) {
@@ -123,11 +135,49 @@ static int plan_needs(HostPipe *p, const int *d_idx, const std::vector<long long
     return SPMV_B200_OK;
 }
 
+// upload pieces: piece w ends where window w's referenced prefix of x ends, rounded up to a 256 KB boundary
+static void plan_pieces(HostPipe *p, long long N) {
+    p->piece.assign(p->windows, 0);
+    for (int w = 0; w < p->windows; ++w)
+        p->piece[w] = std::min(N, (p->need[w] + kPieceAlign - 1) / kPieceAlign * kPieceAlign);
+}
+
 static int pick_windows(long long M, long long N, int units) {
     const int forced = env_int("SPMV_B200_HOST_WINDOWS", 0);
     long long w = forced > 0 ? forced : (8 * (M + N)) / kMinWindowBytes;
     w = std::max<long long>(1, std::min<long long>(w, forced > 0 ? kMaxWindows : kAutoWindows));
     return (int)std::max<long long>(1, std::min<long long>(w, units));
+}
+
+
+// Row boundaries of the windows, bounds[0] = 0 .. bounds[W] = M.  Tapered on 2 MiB units (see the header) when the
+// vector is large enough and no window count is forced; equal windows otherwise.
+static std::vector<long long> window_rows(long long M, long long N, int units) {
+    std::vector<long long> bounds;
+    const long long total = (M + kUnitRows - 1) / kUnitRows;
+    if (env_int("SPMV_B200_HOST_WINDOWS", 0) > 0 || env_int("SPMV_B200_HOST_TAPER", 1) == 0 || total < 16 || units < 16) {
+        const int W = pick_windows(M, N, units);
+        for (int w = 0; w <= W; ++w) bounds.push_back(M * w / W);
+        return bounds;
+    }
+    const long long ramp[5] = {1, 1, 2, 4, 8};
+    int steps = 0;
+    long long ramp_sum = 0;
+    while (steps < 5 && 2 * (ramp_sum + ramp[steps]) <= total / 2) ramp_sum += ramp[steps++];
+    const long long middle = total - 2 * ramp_sum;
+    long long mid_size = 16;
+    while ((middle + mid_size - 1) / mid_size > kMaxWindows - 12) mid_size *= 2;
+    std::vector<long long> sizes(ramp, ramp + steps);
+    for (long long left = middle; left > 0; left -= mid_size) sizes.push_back(std::min(mid_size, left));
+    for (int i = steps - 1; i >= 0; --i) sizes.push_back(ramp[i]);
+    long long at = 0;
+    bounds.push_back(0);
+    for (long long sz : sizes) {
+        at = std::min(M, at + sz * kUnitRows);
+        if (at > bounds.back()) bounds.push_back(at);
+    }
+    bounds.back() = M;
+    return bounds;
 }
 
 // The pass itself.  launch(w) enqueues the kernel(s) of window w on p->compute.
@@ -140,20 +190,25 @@ static int run_pipeline(HostPipe *p, long long M, long long N, const double *x, 
         SPMV_TRY_CUDA(cudaMemcpyAsync(d_y, y, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, p->up));
         SPMV_TRY_CUDA(cudaEventRecord(p->y_landed, p->up));
     }
-    const long long chunk = W > 0 ? (N + W - 1) / W : N;
-    int chunks = 0;
-    for (long long at = 0; at < N; at += chunk, ++chunks) {
-        const long long n = std::min(chunk, N - at);
-        SPMV_TRY_CUDA(cudaMemcpyAsync(d_x + at, x + at, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, p->up));
-        SPMV_TRY_CUDA(cudaEventRecord(p->landed[chunks], p->up));
+    // piece w of x ends where window w's columns end; a window that needs nothing new reuses the previous event.
+    // Columns no window references are never uploaded.
+    std::vector<int> gate(W, -1);
+    long long at = 0;
+    int last = -1;
+    for (int w = 0; w < W; ++w) {
+        const long long upto = std::min(N, p->piece[w]);
+        if (upto > at) {
+            SPMV_TRY_CUDA(cudaMemcpyAsync(d_x + at, x + at, (size_t)(upto - at) * sizeof(double), cudaMemcpyHostToDevice, p->up));
+            SPMV_TRY_CUDA(cudaEventRecord(p->landed[w], p->up));
+            last = w;
+            at = upto;
+        }
+        gate[w] = last;
     }
-    // (2) products: window w waits for the chunk that completes its referenced prefix of x
+    // (2) products: window w waits for its piece
     for (int w = 0; w < W; ++w) {
         if (accumulate && M && w == 0) SPMV_TRY_CUDA(cudaStreamWaitEvent(p->compute, p->y_landed, 0));
-        if (chunks > 0 && p->need[w] > 0) {
-            const int c = (int)std::min<long long>((p->need[w] - 1) / chunk, chunks - 1);
-            SPMV_TRY_CUDA(cudaStreamWaitEvent(p->compute, p->landed[c], 0));
-        }
+        if (gate[w] >= 0 && (w == 0 || gate[w] != gate[w - 1])) SPMV_TRY_CUDA(cudaStreamWaitEvent(p->compute, p->landed[gate[w]], 0));
         SPMV_TRY(launch(w));
         SPMV_TRY_CUDA(cudaEventRecord(p->done[w], p->compute));
     }
@@ -184,26 +239,46 @@ static int csr_plan_windows(spmv_b200_csr *A, CsrPath path) {
     // long rows are computed after every tile (they need all of x and are written last), the binned kernel walks the
     // rows in bin order: one window
     const int units = by_tiles ? A->num_tiles : A->M;
-    int W = ((by_tiles && A->num_long > 0) || path == kPathBinned) ? 1 : pick_windows(A->M, A->N, units);
-    p->windows = W;
-    p->unit.assign(W + 1, 0);
-    p->row.assign(W + 1, 0);
-    std::vector<long long> elem(W + 1, 0);
-    for (int w = 0; w <= W; ++w) p->unit[w] = (int)((long long)units * w / W);
-    for (int w = 0; w <= W; ++w) {
-        if (by_tiles) {
-            int2 t;
-            SPMV_TRY_CUDA(cudaMemcpy(&t, A->tiles + p->unit[w], sizeof t, cudaMemcpyDeviceToHost));
-            p->row[w] = t.x;
-            elem[w] = t.y;
-        } else {
-            int off = 0;
-            SPMV_TRY_CUDA(cudaMemcpy(&off, A->row_ptr + p->unit[w], sizeof off, cudaMemcpyDeviceToHost));
-            p->row[w] = p->unit[w];
-            elem[w] = off;
-        }
+    std::vector<long long> bounds;
+    if ((by_tiles && A->num_long > 0) || path == kPathBinned) bounds = {0, A->M};
+    else bounds = window_rows(A->M, A->N, units);
+    std::vector<int2> tiles_host;
+    if (by_tiles && bounds.size() > 2) {  // row boundary -> the first tile that starts at or after it
+        tiles_host.resize((size_t)A->num_tiles + 1);
+        SPMV_TRY_CUDA(cudaMemcpy(tiles_host.data(), A->tiles, tiles_host.size() * sizeof(int2), cudaMemcpyDeviceToHost));
     }
+    p->unit.clear();
+    p->row.clear();
+    std::vector<long long> elem;
+    for (size_t w = 0; w < bounds.size(); ++w) {
+        int unit;
+        long long row, at;
+        if (by_tiles) {
+            if (w == 0) unit = 0;
+            else if (w + 1 == bounds.size()) unit = A->num_tiles;
+            else unit = (int)(std::lower_bound(tiles_host.begin(), tiles_host.end(), bounds[w],
+                                               [](const int2 &t, long long r) { return t.x < r; }) - tiles_host.begin());
+            int2 t;
+            if (!tiles_host.empty()) t = tiles_host[unit];
+            else SPMV_TRY_CUDA(cudaMemcpy(&t, A->tiles + unit, sizeof t, cudaMemcpyDeviceToHost));
+            row = t.x;
+            at = t.y;
+        } else {
+            unit = (int)bounds[w];
+            int off = 0;
+            SPMV_TRY_CUDA(cudaMemcpy(&off, A->row_ptr + unit, sizeof off, cudaMemcpyDeviceToHost));
+            row = unit;
+            at = off;
+        }
+        if (!p->unit.empty() && unit <= p->unit.back() && w + 1 != bounds.size()) continue;  // an empty window
+        p->unit.push_back(unit);
+        p->row.push_back(row);
+        elem.push_back(at);
+    }
+    const int W = (int)p->unit.size() - 1;
+    p->windows = W;
     SPMV_TRY(plan_needs(p, A->col_idx, elem));
+    plan_pieces(p, A->N);
     p->path = (int)path;
     return SPMV_B200_OK;
 }
@@ -275,23 +350,34 @@ int spmv_b200_hll_spmv_host(spmv_b200_hll *H, const double *x, double *y) {
     HostPipe *p = H->pipe;
     if (p->path != (int)path) {
         const int units = stream_kernel ? H->num_tiles : H->num_hacks;
-        const int W = pick_windows(H->M, H->N, units);
-        p->windows = W;
-        p->unit.assign(W + 1, 0);
-        p->row.assign(W + 1, 0);
-        std::vector<long long> elem(W + 1, 0);
-        for (int w = 0; w <= W; ++w) {
-            p->unit[w] = (int)((long long)units * w / W);
-            int hack = p->unit[w];
-            if (stream_kernel) {
-                HllTile t;
-                SPMV_TRY_CUDA(cudaMemcpy(&t, H->tiles + p->unit[w], sizeof t, cudaMemcpyDeviceToHost));
-                hack = t.hack;
-            }
-            p->row[w] = std::min<long long>((long long)hack * HACK_SIZE, H->M);
-            elem[w] = H->host_off[hack];
+        const std::vector<long long> bounds = window_rows(H->M, H->N, units);
+        std::vector<HllTile> tiles_host;
+        if (stream_kernel) {
+            tiles_host.resize((size_t)H->num_tiles + 1);
+            SPMV_TRY_CUDA(cudaMemcpy(tiles_host.data(), H->tiles, tiles_host.size() * sizeof(HllTile), cudaMemcpyDeviceToHost));
         }
+        p->unit.clear();
+        p->row.clear();
+        std::vector<long long> elem;
+        for (size_t w = 0; w < bounds.size(); ++w) {
+            const long long want_hack = w + 1 == bounds.size() ? H->num_hacks : bounds[w] / HACK_SIZE;  // 2 MiB units are whole hacks
+            int unit, hack;
+            if (stream_kernel) {
+                unit = (int)(std::lower_bound(tiles_host.begin(), tiles_host.end(), want_hack,
+                                              [](const HllTile &t, long long h) { return t.hack < h; }) - tiles_host.begin());
+                hack = tiles_host[unit].hack;
+            } else {
+                unit = hack = (int)want_hack;
+            }
+            if (!p->unit.empty() && unit <= p->unit.back() && w + 1 != bounds.size()) continue;
+            p->unit.push_back(unit);
+            p->row.push_back(std::min<long long>((long long)hack * HACK_SIZE, H->M));
+            elem.push_back(H->host_off[hack]);
+        }
+        const int W = (int)p->unit.size() - 1;
+        p->windows = W;
         SPMV_TRY(plan_needs(p, H->JA, elem));
+        plan_pieces(p, H->N);
         p->path = (int)path;
     }
     const int rc = run_pipeline(p, H->M, x ? H->N : 0, x, y, H->stage_x, H->stage_y, false, [&](int w) {

@@ -699,6 +699,40 @@ def test_host_pipeline_windows(dev, checker, monkeypatch, windows, kind):
         A.close()
 
 
+@pytest.mark.parametrize("kind", ["lap2d", "uniform8"])
+def test_host_pipeline_tapered_windows(dev, checker, kind):
+    """Vectors of 16+ units of 2 MiB take the tapered window schedule of hostpath.cu (1, 1, 2, 4, 8, 16 ..., 8, 4, 2, 1, 1
+    units, upload pieces ending at each window's last referenced column).  Banded columns (lap2d: windows start as soon
+    as their piece lands) and random columns (every window needs all of x): the host call gives the bits of the resident
+    product and matches the serial oracle."""
+    import torch
+    from sparsematrixvectormultiplication_b200 import synth
+    if kind == "lap2d":
+        n = 2100                                     # 4.41 M rows = 17 units
+        A = dev.DeviceCSR.synth(synth.SYNTH_LAP2D, n)
+    else:
+        M = 17 * 262144 + 777
+        A = dev.DeviceCSR.synth(synth.SYNTH_UNIFORM, M, M, 8)
+    info = A.info()
+    x = ramp(info.N)
+    rp, ci, va = A.download()
+    y_ref = checker.spmv_csr_serial(rp, ci, va, x)
+    scale = abs_row_sums(checker, rp, ci, va, x)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.full((info.M,), float("nan"), dtype=torch.float64, device="cuda")
+    A.spmv(xd, yd)
+    resident = yd.cpu().numpy()
+    assert_close(resident, y_ref, scale, kind)
+    for _ in range(2):                               # the second call reuses the window plan
+        got = A.spmv_host(x, np.full(info.M, np.nan))
+        assert np.array_equal(bits(got), bits(resident)), f"{kind}: tapered host pipeline differs from the resident product"
+    H = A.to_hll()
+    H.spmv(xd, yd)
+    got = H.spmv_host(x, np.full(info.M, np.nan))
+    assert np.array_equal(bits(got), bits(yd.cpu().numpy())), f"{kind}: HLL host pipeline"
+    assert_close(got, y_ref, scale, kind + " hll")
+
+
 def test_main_style_driver_writes_the_csv(dev, tmp_path):
     """tools/spmv_driver.c: parser -> converters -> upload -> timed products of every kernel -> self-check against the
     serial-order product -> one CSV row per matrix (the reference driver's loop, main_cuda.cu:40-720)."""
