@@ -486,7 +486,6 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler, head):
         if with_auto:
             run(f"{name}_csr", lambda: A.spmv(x, y), ia.nnz, ia.algorithmic_bytes, {"kernel": "automatic choice"})
         run(f"{name}_csr_stream_kernel", lambda: A.spmv(x, y, algo=device.ALGO_STREAM), ia.nnz, ia.algorithmic_bytes)
-        run(f"{name}_csr_tile_kernel", lambda: A.spmv(x, y, algo=device.ALGO_TILE), ia.nnz, ia.algorithmic_bytes)
         run(f"{name}_csr_vector_kernel", lambda: A.spmv(x, y, algo=device.ALGO_VECTOR), ia.nnz, ia.algorithmic_bytes)
         run(f"{name}_csr_binned_kernel", lambda: A.spmv(x, y, algo=device.ALGO_BINNED), ia.nnz, ia.algorithmic_bytes)
         if ia.max_row_nnz <= 64:  # one thread per row is only meaningful without long rows
@@ -816,7 +815,7 @@ def bench_multi_gpu(args):
             results[mode]["collective"] = ("ONE in-place ncclAllGather (dist.all_gather_into_tensor) over a padded rank-major x, "
                                            f"stride {P.stride} doubles; interior rows [{P.interior[0]},{P.interior[1]}) of {P.rows} multiplied while it is in flight")
             try:   # the collective alone, same buffers
-                ams, _ = time_device(lambda: dist.all_gather_into_tensor(P.xg, P.own), 10, 3, None, world)
+                ams, _ = time_device(lambda: dist.all_gather_into_tensor(P.xg, P.own, group=P.ag_group), 10, 3, None, world)
                 results[mode]["allgather_alone_ms"] = ams
                 results[mode]["allgather_alone_ingress_gbs"] = 8 * recv / (ams * 1e-3) / 1e9
             except Exception as e:  # pragma: no cover

@@ -45,7 +45,7 @@ extern "C" {
 #define SPMV_B200_ALGO_AUTO 0     /* ROW (or STREAM: timed at plan time, same bits) when no row exceeds 12 nonzeros; STREAM for
                                      <= 12 nnz/row on average; else VECTOR (even rows) or BINNED (skewed rows) */
 #define SPMV_B200_ALGO_VECTOR 1   /* plain vector-per-row kernel with shuffle reduction      */
-#define SPMV_B200_ALGO_TILE 2     /* row-binned tile kernel, one CTA per tile, direct loads  */
+#define SPMV_B200_ALGO_TILE 2     /* retired (round 2): accepted for compatibility, runs STREAM */
 #define SPMV_B200_ALGO_STREAM 3   /* persistent row-binned kernel, TMA bulk-copy pipeline    */
 #define SPMV_B200_ALGO_BINNED 4   /* rows binned by length: 1..32 lanes per row, longest rows split */
 #define SPMV_B200_ALGO_ROW 5      /* one thread per row, serial order (bit-identical to the reference loop) */
@@ -287,7 +287,7 @@ int spmv_b200_hll_spmv_host_f32(spmv_b200_hll *H, const float *x, float *y);
 /* ---- timing harness on a resident matrix: the reference driver's protocol (main_cuda.cu:159-200: cudaEvents around
  * every product, the first `warmup` iterations not counted, mean over the rest) behind one call, so that a C
  * driver needs no CUDA runtime of its own.  x: host vector, uploaded once (as main_cuda.cu:145); y: host result of
- * the last product (may be NULL).  kernel for HLL: 0 automatic, 1 slice kernel, 2 stream kernel. ---- */
+ * the last product (may be NULL).  kernel for HLL: 0 automatic, 1 slice kernel, 2 stream kernel, 3 lane-per-row kernel. ---- */
 int spmv_b200_csr_time(spmv_b200_csr *A, const double *x, double *y, int algo, int warmup, int iters,
                        double *mean_seconds, double *min_seconds);
 int spmv_b200_hll_time(spmv_b200_hll *H, const double *x, double *y, int kernel, int warmup, int iters,

@@ -13,8 +13,6 @@
 //   * csr_binned_kernel<V> + csr_long_fragment_kernel + csr_long_combine_kernel -- rows sorted by length class, 1..32
 //       lanes per row in one launch; rows above 2048 nonzeros split into 8192-nonzero fragments combined in a fixed
 //       order (deterministic, no atomics).  Automatic choice for skewed rows.
-//   * csr_tile_kernel             -- first-generation row-binned tile kernel (products parked in shared memory);
-//       explicit SPMV_B200_ALGO_TILE only.
 // V = storage type (double, or float with double arithmetic).  The TMA-pipelined stream kernels live in stream.cu.
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
@@ -31,11 +29,9 @@
 
 namespace spmv {
 
-constexpr int kTileThreads = 256;
 constexpr int kAutoStreamMaxAvg = 12;  // ALGO_AUTO: stream kernel up to this many nonzeros per row on average
 constexpr int kFragNnz = 8192;              // nonzeros per long-row fragment (one CTA)
 constexpr int kFragThreads = 256;
-constexpr int kSmemSlack = 8;
 constexpr int kVecBatch = 4;                // independent column -> gather chains per lane of the vector kernel
 constexpr long long kAutotuneMinNnz = 1 << 22;  // plan-time timing of the row-kernel batch only pays on large matrices
 constexpr int kRowBatch = 4;                // the same with ONE lane per row (bin 0 of the binned kernel)
@@ -69,89 +65,6 @@ __device__ __forceinline__ double load_val(const V *p) {
 // ================================================================================================
 // kernels
 // ================================================================================================
-
-// Products of one aligned group of four nonzeros.
-__device__ __forceinline__ void group_products(const int *__restrict__ col_idx, const double *__restrict__ values,
-                                               const double *__restrict__ x, int idx, int nnz_total,
-                                               double (&p)[4]) {
-    if (idx + 4 <= nnz_total) {
-        const int4 c = ldg_stream_s32x4(col_idx + idx);
-        double v[4];
-        ldg_stream_f64x4(values + idx, v);
-        p[0] = __dmul_rn(v[0], ldg_x(x, c.x));
-        p[1] = __dmul_rn(v[1], ldg_x(x, c.y));
-        p[2] = __dmul_rn(v[2], ldg_x(x, c.z));
-        p[3] = __dmul_rn(v[3], ldg_x(x, c.w));
-    } else {  // ragged end of the arrays: never read past nnz_total
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int k = idx + e;
-            p[e] = k < nnz_total ? __dmul_rn(ldg_stream_f64(values + k), ldg_x(x, ldg_stream_s32(col_idx + k))) : 0.0;
-        }
-    }
-}
-
-// tiles[t] = {first row of tile t, row_ptr[first row]}, tiles[num_tiles] = {M, nnz}.
-// forced_tpr: 1 = one thread per row in the reference's order; anything else = warp per 32-row chunk.
-__global__ void __launch_bounds__(kTileThreads, 4)
-csr_tile_kernel(const int2 *__restrict__ tiles, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
-                const double *__restrict__ values, const double *__restrict__ x, double *__restrict__ y,
-                int nnz_total, int long_threshold, int forced_tpr, int accumulate) {
-    extern __shared__ __align__(32) double prod[];
-    const int tid = threadIdx.x;
-    const int2 head = tiles[blockIdx.x];
-    const int2 tail = tiles[blockIdx.x + 1];
-    const int r0 = head.x, rows = tail.x - head.x;
-    const int n0 = head.y, n1 = tail.y;
-    if (rows == 1 && n1 - n0 > long_threshold) return;  // long row: csr_long_* kernels own it
-
-    const int a0 = n0 & ~3;  // 16 B (columns) / 32 B (values) aligned start
-    const int ngroups = (n1 - a0 + 3) >> 2;
-
-    // ---- phase A: stream the tile, park the products ------------------------------------------
-    int g = tid;
-    for (; g + kTileThreads < ngroups; g += 2 * kTileThreads) {  // two groups in flight per thread
-        double p0[4], p1[4];
-        group_products(col_idx, values, x, a0 + 4 * g, nnz_total, p0);
-        group_products(col_idx, values, x, a0 + 4 * (g + kTileThreads), nnz_total, p1);
-        double2 *d0 = reinterpret_cast<double2 *>(prod + 4 * g);
-        double2 *d1 = reinterpret_cast<double2 *>(prod + 4 * (g + kTileThreads));
-        d0[0] = make_double2(p0[0], p0[1]);
-        d0[1] = make_double2(p0[2], p0[3]);
-        d1[0] = make_double2(p1[0], p1[1]);
-        d1[1] = make_double2(p1[2], p1[3]);
-    }
-    if (g < ngroups) {
-        double p0[4];
-        group_products(col_idx, values, x, a0 + 4 * g, nnz_total, p0);
-        double2 *d0 = reinterpret_cast<double2 *>(prod + 4 * g);
-        d0[0] = make_double2(p0[0], p0[1]);
-        d0[1] = make_double2(p0[2], p0[3]);
-    }
-    __syncthreads();
-
-    // ---- phase B: per-row reduction out of shared memory ---------------------------------------
-    if (forced_tpr == 1) {  // one thread per row, left to right: bit-identical to the reference's serial loop
-        for (int my_row = tid; my_row < rows; my_row += kTileThreads) {
-            double acc = accumulate ? y[r0 + my_row] : 0.0;
-            const int seg_lo = __ldg(row_ptr + r0 + my_row) - a0, seg_hi = __ldg(row_ptr + r0 + my_row + 1) - a0;
-            for (int k = seg_lo; k < seg_hi; ++k) acc = __dadd_rn(acc, prod[k]);
-            y[r0 + my_row] = acc;
-        }
-    } else {  // one warp per chunk of 32 rows (common.cuh: chunk_row_sum)
-        const int lane = tid & 31;
-        for (int c = tid >> 5; c * 32 < rows; c += kTileThreads / 32) {
-            const int lr = c * 32 + lane;
-            int lo = 0, hi = 0;
-            if (lr < rows) {
-                lo = __ldg(row_ptr + r0 + lr) - a0;
-                hi = __ldg(row_ptr + r0 + lr + 1) - a0;
-            }
-            const double acc = chunk_row_sum(prod, lo, hi, lane);
-            if (lr < rows) y[r0 + lr] = accumulate ? __dadd_rn(y[r0 + lr], acc) : acc;
-        }
-    }
-}
 
 // One CTA per fragment of a long row; partial[f] = sum over the fragment (fixed tree).  Every thread of the CTA calls it.
 template <typename V>
@@ -363,16 +276,18 @@ csr_row_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, cons
 template <int BATCH>
 __global__ void __launch_bounds__(256, 8)
 csr_row_fused_kernel(int M, const int *__restrict__ row_ptr, const int *__restrict__ col_idx, const double *__restrict__ values,
-                     const double *__restrict__ x, double *__restrict__ y, const Epilogue ep) {
+                     const double *__restrict__ x, double *__restrict__ y, const __grid_constant__ Epilogue ep) {
     __shared__ double warp_sq[8];
     __shared__ double mail_total;
     bool scaled;
     const double inv_norm = fused_inv_norm(ep, scaled, &mail_total);
     double sq = 0.0;
-    for (long long chunk_lo = (long long)blockIdx.x * 256; chunk_lo < M; chunk_lo += (long long)gridDim.x * 256) {
-        // peer stores: a CTA-uniform test on the chunk first (uniform datapath), the per-row range test only inside --
-        // done per row for every row it cost 30 us per peer per 56 M rows
-        const bool boundary = fused_chunk_is_boundary(ep, chunk_lo);
+    const int chunks = (M + 255) >> 8;
+    for (int q = blockIdx.x; q < chunks; q += gridDim.x) {
+        // boundary chunks first (ChunkOrder); peer stores: a CTA-uniform test on the chunk (uniform datapath), the per-row
+        // range test only inside -- done per row for every row it cost 30 us per peer per 56 M rows
+        const long long chunk_lo = (long long)ordered_chunk(ep.order, q) * 256;
+        const bool boundary = ep.order.boundary_chunks > 0 ? q < ep.order.boundary_chunks : fused_chunk_is_boundary(ep, chunk_lo);
         const long long row = chunk_lo + threadIdx.x;
         if (row >= M) continue;
         const int lo = __ldg(row_ptr + row), hi = __ldg(row_ptr + row + 1);
@@ -402,12 +317,6 @@ csr_row_fused_kernel(int M, const int *__restrict__ row_ptr, const int *__restri
 // that hold rows a neighbour references moved to the front of the walk and a per-neighbour halo tag raised as soon as
 // they are stored, (2) the scale factor taken from the sums of launch k-2, (3) waits only on things that finished a
 // launch ago.  Chunk = 256 consecutive rows; q-th chunk of the walk -> row chunk through the boundary intervals.
-struct ChunkOrder {
-    int count;                      // boundary intervals (ascending, disjoint), in chunks
-    int lo[SPMV_B200_MAX_PEERS], hi[SPMV_B200_MAX_PEERS];
-    int boundary_chunks;            // sum of the interval lengths
-};
-
 struct AsyncArgs {  // one by-value kernel parameter, read through the constant bank (never address-taken: a copy on the
     spmv_b200_peers_t peers;   // local-memory stack would put two extra loads per row on the LSU)
     spmv_b200_async_t as;
@@ -814,12 +723,6 @@ static void free_plan(spmv_b200_csr *A) {
     A->num_tiles = A->num_long = A->num_frag = 0;
 }
 
-// products of the largest possible tile.  Kept small on purpose: shared memory is carved out of the L1 that the
-// gathers of x need for their lines in flight (a 55 KB variant that also staged row_ptr ran 2.4x slower).
-static size_t tile_smem_bytes(const spmv_b200_csr *A) {
-    return (size_t)(A->tile_items / 3 + A->long_threshold + kSmemSlack) * sizeof(double);
-}
-
 template <typename V>
 static int launch_rows(int row_begin, int row_end, const int *row_ptr, const int *col_idx, const V *values,
                        const V *x, V *y, int batch, int accumulate, cudaStream_t stream);
@@ -833,9 +736,6 @@ static int build_plan(spmv_b200_csr *A, cudaStream_t stream) {
     A->pipe = nullptr;
     const int M = A->M;
     if (M == 0) return SPMV_B200_OK;
-    if (tile_smem_bytes(A) > 200 * 1024) return fail(SPMV_B200_ERR_INVALID, "tile_items + long_threshold too large for shared memory");
-    SPMV_TRY_CUDA(cudaFuncSetAttribute(csr_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)tile_smem_bytes(A)));
     unsigned char *boundary = nullptr, *is_long = nullptr;
     int *tile_rows = nullptr, *counts = nullptr, *d_selected = nullptr;
     void *temp = nullptr;
@@ -1048,14 +948,10 @@ static int launch_tiles(const spmv_b200_csr *A, const double *x, double *y, int 
     if (A->num_tiles == 0) return SPMV_B200_OK;
     if (tile_end < 0) tile_end = A->num_tiles;
     if (tile_end <= tile_begin) return SPMV_B200_OK;
-    if (pipelined) {
-        SPMV_TRY(stream_launch_csr(A, x, y, accumulate, nullptr, stream, tile_begin, tile_end - tile_begin));
-    } else {
-        csr_tile_kernel<<<tile_end - tile_begin, kTileThreads, tile_smem_bytes(A), stream>>>(
-            A->tiles + tile_begin, A->row_ptr, A->col_idx, A->values, x, y, (int)A->nnz, A->long_threshold, A->forced_tpr,
-            accumulate);
-        SPMV_TRY_CUDA(cudaGetLastError());
-    }
+    (void)pipelined;  // the first-generation tile kernel (products parked in shared memory, one CTA per tile) was retired in
+                      // round 2: it lost to the stream kernel on every shape measured (lap2d 0.34 vs 0.24 ms, uniform 1.87 vs
+                      // 1.31 ms vector, R-MAT 1.87 vs 1.60 ms binned); SPMV_B200_ALGO_TILE now runs the stream kernel
+    SPMV_TRY(stream_launch_csr(A, x, y, accumulate, nullptr, stream, tile_begin, tile_end - tile_begin));
     if (A->num_long > 0 && tile_end == A->num_tiles) {
         csr_long_fragment_kernel<double><<<A->num_frag, kFragThreads, 0, stream>>>(A->long_rows, A->frag_first, A->num_long,
                                                                           A->row_ptr, A->col_idx, A->values, x,
@@ -1230,6 +1126,28 @@ static int launch_fused(const spmv_b200_csr *A, const double *x, double *y, cons
     }
 #undef FROW_CASE
     SPMV_TRY_CUDA(cudaGetLastError());
+    return SPMV_B200_OK;
+}
+
+int boundary_first_order(const spmv_b200_peers_t &peers, int M, ChunkOrder &order) {
+    order = ChunkOrder();
+    std::vector<std::pair<int, int>> iv;
+    for (int p = 0; p < peers.count; ++p) {
+        if (peers.lo[p] < 0 || peers.hi[p] > M || peers.lo[p] > peers.hi[p])
+            return fail(SPMV_B200_ERR_INVALID, "fused product: peer %d: bad row range [%d,%d) of %d rows", p, peers.lo[p], peers.hi[p], M);
+        if (peers.hi[p] > peers.lo[p]) iv.emplace_back(peers.lo[p] >> 8, (peers.hi[p] + 255) >> 8);
+    }
+    std::sort(iv.begin(), iv.end());
+    for (const auto &r : iv) {
+        if (order.count > 0 && r.first <= order.hi[order.count - 1]) {
+            order.hi[order.count - 1] = std::max(order.hi[order.count - 1], r.second);
+        } else {
+            order.lo[order.count] = r.first;
+            order.hi[order.count] = r.second;
+            ++order.count;
+        }
+    }
+    for (int i = 0; i < order.count; ++i) order.boundary_chunks += order.hi[i] - order.lo[i];
     return SPMV_B200_OK;
 }
 
@@ -1448,6 +1366,7 @@ int spmv_b200_csr_spmv_fused(const spmv_b200_csr *A, const double *d_x, double *
     ep.partials_total = spmv_b200_csr_partials_count(A);
     if (peers) ep.peers = *peers;
     if (A->M == 0) return SPMV_B200_OK;
+    if (peers && env_int("SPMV_B200_FUSED_BOUNDARY_FIRST", 1)) SPMV_TRY(boundary_first_order(ep.peers, A->M, ep.order));
     return launch_fused(A, d_x, d_y, ep, as_stream(stream), -1);
 }
 
@@ -1469,6 +1388,7 @@ int spmv_b200_csr_spmv_fused_mail(const spmv_b200_csr *A, const double *d_x, dou
     ep.partials_total = spmv_b200_csr_partials_count(A);
     if (peers) ep.peers = *peers;
     ep.mail = *mail;
+    if (peers && env_int("SPMV_B200_FUSED_BOUNDARY_FIRST", 1)) SPMV_TRY(boundary_first_order(ep.peers, A->M, ep.order));
     return launch_fused(A, d_x, d_y, ep, as_stream(stream), -1);
 }
 
@@ -1486,27 +1406,10 @@ int spmv_b200_csr_spmv_fused_async(const spmv_b200_csr *A, const double *d_x, do
     ps.count = 0;
     if (peers) ps = *peers;
     if (ps.count < 0 || ps.count > SPMV_B200_MAX_PEERS) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_async: bad peer count %d", ps.count);
-    // boundary chunk intervals: the union of the peers' row ranges, in 256-row chunks, ascending and disjoint
     ChunkOrder order;
-    order.count = 0;
-    order.boundary_chunks = 0;
-    std::vector<std::pair<int, int>> iv;
-    for (int p = 0; p < ps.count; ++p) {
-        if (ps.lo[p] < 0 || ps.hi[p] > A->M || ps.lo[p] > ps.hi[p] || as->send_to[p] < 0 || as->send_to[p] >= as->world)
-            return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_async: peer %d: bad row range or rank", p);
-        if (ps.hi[p] > ps.lo[p]) iv.emplace_back(ps.lo[p] >> 8, (ps.hi[p] + 255) >> 8);
-    }
-    std::sort(iv.begin(), iv.end());
-    for (const auto &r : iv) {
-        if (order.count > 0 && r.first <= order.hi[order.count - 1]) {
-            order.hi[order.count - 1] = std::max(order.hi[order.count - 1], r.second);
-        } else {
-            order.lo[order.count] = r.first;
-            order.hi[order.count] = r.second;
-            ++order.count;
-        }
-    }
-    for (int i = 0; i < order.count; ++i) order.boundary_chunks += order.hi[i] - order.lo[i];
+    for (int p = 0; p < ps.count; ++p)
+        if (as->send_to[p] < 0 || as->send_to[p] >= as->world) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_async: peer %d: bad rank", p);
+    SPMV_TRY(boundary_first_order(ps, A->M, order));
     if (env_int("SPMV_B200_ASYNC_NO_REORDER", 0)) {  // experiment: rows in their natural order, halo tags at the end
         order.count = 0;
         order.boundary_chunks = 0;

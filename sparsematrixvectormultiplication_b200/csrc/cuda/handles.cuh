@@ -13,6 +13,33 @@ constexpr int kDefaultStages = 2;           // TMA pipeline depth of the stream 
 constexpr int kHllTileSlots = 3072;         // D_h: slots + rows per HLL tile (12 B per slot; stage = 49.5 KB with the wide margin)
 constexpr int kHllWideSlots = 1024;         // hacks with more slots (MAXNZ > 32) are processed straight from HBM
 
+// Walk order of the fused row kernels: the 256-row chunks that hold rows a neighbour references come FIRST, so that their
+// NVLink peer stores are long acknowledged when the launch ends (at the natural position -- the first and last planes of
+// the row range -- the last wave of the launch issues them and the launch end waits for them: +45 us per iteration on
+// 2 GPUs, +17 us on 8, profiles/r02c_bench_n2.json).  Chunk = 256 consecutive rows.
+struct ChunkOrder {
+    int count = 0;                  // boundary intervals (ascending, disjoint), in chunks
+    int lo[SPMV_B200_MAX_PEERS] = {}, hi[SPMV_B200_MAX_PEERS] = {};
+    int boundary_chunks = 0;        // sum of the interval lengths; 0 = natural order
+};
+
+__device__ __forceinline__ int ordered_chunk(const ChunkOrder &o, int q) {  // q-th chunk of the walk -> row chunk
+    if (o.boundary_chunks == 0) return q;
+    if (q < o.boundary_chunks) {
+        int left = q;
+        for (int i = 0; i < o.count; ++i) {
+            const int len = o.hi[i] - o.lo[i];
+            if (left < len) return o.lo[i] + left;
+            left -= len;
+        }
+        return q;
+    }
+    int chunk = q - o.boundary_chunks;
+    for (int i = 0; i < o.count; ++i)
+        if (chunk >= o.lo[i]) chunk += o.hi[i] - o.lo[i];
+    return chunk;
+}
+
 struct Epilogue {                 // optional fused tail of the CSR stream / row kernels and the HLL row kernel
     const double *prev_sumsq = nullptr;  // divide every row by sqrt(*prev_sumsq)
     double *partials = nullptr;   // partials[blockIdx.x] = sum of the squares of the rows this CTA produced
@@ -20,7 +47,11 @@ struct Epilogue {                 // optional fused tail of the CSR stream / row
                                   // [gridDim.x, partials_total) so that a caller may always sum the whole buffer
     spmv_b200_peers_t peers = {}; // rows mirrored into peer memory
     spmv_b200_mail_t mail = {};   // world > 0: |w|^2 travels through peer mailboxes instead of prev_sumsq (spmv_b200.h)
+    ChunkOrder order;             // row kernels only: boundary chunks first (filled by boundary_first_order)
 };
+
+// the union of the peers' row ranges in 256-row chunks, ascending and disjoint (host side)
+int boundary_first_order(const spmv_b200_peers_t &peers, int M, ChunkOrder &order);
 
 // entries of the partials buffer that this launch does not write (the buffer is sized for the largest fused grid)
 __device__ __forceinline__ void zero_partials_tail(const Epilogue &ep) {

@@ -130,15 +130,17 @@ template <int BATCH>
 __global__ void __launch_bounds__(256, 8)
 hll_row_fused_kernel(int num_hacks, const long long *__restrict__ hack_off, const int *__restrict__ JA,
                      const double *__restrict__ AS, const double *__restrict__ x, double *__restrict__ y, int M,
-                     const Epilogue ep) {
+                     const __grid_constant__ Epilogue ep) {
     __shared__ double warp_sq[8];
     __shared__ double mail_total;
     bool scaled;
     const double inv_norm = fused_inv_norm(ep, scaled, &mail_total);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double sq = 0.0;
-    for (long long chunk_lo = (long long)blockIdx.x * 256; chunk_lo < M; chunk_lo += (long long)gridDim.x * 256) {
-        const bool boundary = fused_chunk_is_boundary(ep, chunk_lo);
+    const int chunks = (M + 255) >> 8;
+    for (int q = blockIdx.x; q < chunks; q += gridDim.x) {  // boundary chunks first, exactly as csr_row_fused_kernel walks them
+        const long long chunk_lo = (long long)ordered_chunk(ep.order, q) * 256;
+        const bool boundary = ep.order.boundary_chunks > 0 ? q < ep.order.boundary_chunks : fused_chunk_is_boundary(ep, chunk_lo);
         const int hack = (int)(chunk_lo >> 5) + warp;
         if (hack >= num_hacks) continue;  // warp-uniform
         const long long off = __ldg(hack_off + hack);
@@ -604,6 +606,7 @@ int spmv_b200_hll_spmv_fused(const spmv_b200_hll *H, const double *d_x, double *
     ep.partials = d_partials;
     ep.partials_total = hll_fused_grid(H);
     if (peers) ep.peers = *peers;
+    if (peers && env_int("SPMV_B200_FUSED_BOUNDARY_FIRST", 1)) SPMV_TRY(boundary_first_order(ep.peers, H->M, ep.order));
     return hll_launch_fused(H, d_x, d_y, ep, as_stream(stream));
 }
 
@@ -623,6 +626,7 @@ int spmv_b200_hll_spmv_fused_mail(const spmv_b200_hll *H, const double *d_x, dou
     ep.partials_total = hll_fused_grid(H);
     if (peers) ep.peers = *peers;
     ep.mail = *mail;
+    if (peers && env_int("SPMV_B200_FUSED_BOUNDARY_FIRST", 1)) SPMV_TRY(boundary_first_order(ep.peers, H->M, ep.order));
     return hll_launch_fused(H, d_x, d_y, ep, as_stream(stream));
 }
 

@@ -37,6 +37,7 @@ namespace spmv {
 
 constexpr int kMaxWindows = 64;  // events; the automatic choice stops at kAutoWindows.  Round 1, equal windows, measured on lap2d 4096^2: 4 -> 3.93 ms, 8 -> 3.49, 16 -> 3.42, 24 -> 3.91, 32 -> 3.65, 48 -> 3.89
 constexpr int kAutoWindows = 16;
+constexpr int kZeroCopyDefault = 1;
 constexpr long long kUnitRows = (2LL << 20) / 8;      // 2 MiB of y
 constexpr long long kPieceAlign = (256LL << 10) / 8;  // upload pieces end on 256 KB boundaries of x
 constexpr long long kMinWindowBytes = 2LL << 20;  // below 2 MB of x + y per window the launch overheads win
@@ -180,11 +181,27 @@ static std::vector<long long> window_rows(long long M, long long N, int units) {
     return bounds;
 }
 
-// The pass itself.  launch(w) enqueues the kernel(s) of window w on p->compute.
+// A host y that the device can address (pinned or registered, unified addressing): the products can store their rows
+// straight into it over PCIe and the download copies -- with their event hand-overs -- disappear.
+static double *device_alias_of_host(double *y) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, y) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (attr.type != cudaMemoryTypeHost || attr.devicePointer == nullptr) return nullptr;
+    return static_cast<double *>(attr.devicePointer);
+}
+
+// The pass itself.  launch(w, y_base) enqueues the kernel(s) of window w on p->compute; they write rows r of the matrix
+// to y_base[r].  zero_copy_ok: every row is written exactly once and never read back by the kernels of this path.
 template <class Launch>
 static int run_pipeline(HostPipe *p, long long M, long long N, const double *x, double *y, double *d_x, double *d_y,
-                        bool accumulate, Launch launch) {
+                        bool accumulate, bool zero_copy_ok, Launch launch) {
     const int W = p->windows;
+    // SPMV_B200_HOST_ZEROCOPY (default on): kernels store y directly into the caller's pinned buffer
+    double *y_alias = (zero_copy_ok && !accumulate && M && env_int("SPMV_B200_HOST_ZEROCOPY", kZeroCopyDefault)) ? device_alias_of_host(y) : nullptr;
+    double *y_base = y_alias ? y_alias : d_y;
     // (1) uploads: the old y first (accumulate), then x in W chunks
     if (accumulate && M) {
         SPMV_TRY_CUDA(cudaMemcpyAsync(d_y, y, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, p->up));
@@ -209,11 +226,11 @@ static int run_pipeline(HostPipe *p, long long M, long long N, const double *x, 
     for (int w = 0; w < W; ++w) {
         if (accumulate && M && w == 0) SPMV_TRY_CUDA(cudaStreamWaitEvent(p->compute, p->y_landed, 0));
         if (gate[w] >= 0 && (w == 0 || gate[w] != gate[w - 1])) SPMV_TRY_CUDA(cudaStreamWaitEvent(p->compute, p->landed[gate[w]], 0));
-        SPMV_TRY(launch(w));
-        SPMV_TRY_CUDA(cudaEventRecord(p->done[w], p->compute));
+        SPMV_TRY(launch(w, y_base));
+        if (!y_alias) SPMV_TRY_CUDA(cudaEventRecord(p->done[w], p->compute));
     }
-    // (3) downloads, window by window
-    for (int w = 0; w < W; ++w) {
+    // (3) downloads, window by window (none when the kernels wrote into the host buffer themselves)
+    for (int w = 0; w < W && !y_alias; ++w) {
         const long long r0 = p->row[w], r1 = p->row[w + 1];
         if (r1 <= r0) continue;
         SPMV_TRY_CUDA(cudaStreamWaitEvent(p->down, p->done[w], 0));
@@ -332,8 +349,10 @@ int spmv_b200_csr_spmv_host(spmv_b200_csr *A, const double *x, double *y, int ac
     const CsrPath path = csr_resolve(A, algo);
     if (A->pipe->path != (int)path) SPMV_TRY(csr_plan_windows(A, path));
     HostPipe *p = A->pipe;
-    const int rc = run_pipeline(p, A->M, x ? A->N : 0, x, y, A->stage_x, A->stage_y, accumulate != 0, [&](int w) {
-        return csr_launch_window(A, path, p->unit[w], p->unit[w + 1], A->stage_x, A->stage_y, accumulate, p->compute);
+    // the binned kernel's long rows are combined by a second kernel that may read y (accumulate); tiles with long rows too
+    const bool zero_copy_ok = path != kPathBinned && A->num_long == 0;
+    const int rc = run_pipeline(p, A->M, x ? A->N : 0, x, y, A->stage_x, A->stage_y, accumulate != 0, zero_copy_ok, [&](int w, double *y_base) {
+        return csr_launch_window(A, path, p->unit[w], p->unit[w + 1], A->stage_x, y_base, accumulate, p->compute);
     });
     if (rc != SPMV_B200_OK) abort_pipeline(p);
     return rc;
@@ -380,8 +399,8 @@ int spmv_b200_hll_spmv_host(spmv_b200_hll *H, const double *x, double *y) {
         plan_pieces(p, H->N);
         p->path = (int)path;
     }
-    const int rc = run_pipeline(p, H->M, x ? H->N : 0, x, y, H->stage_x, H->stage_y, false, [&](int w) {
-        return hll_launch_window(H, path, p->unit[w], p->unit[w + 1], H->stage_x, H->stage_y, p->compute);
+    const int rc = run_pipeline(p, H->M, x ? H->N : 0, x, y, H->stage_x, H->stage_y, false, true, [&](int w, double *y_base) {
+        return hll_launch_window(H, path, p->unit[w], p->unit[w + 1], H->stage_x, y_base, p->compute);
     });
     if (rc != SPMV_B200_OK) abort_pipeline(p);
     return rc;
@@ -399,12 +418,13 @@ int spmv_b200_csr_time(spmv_b200_csr *A, const double *x, double *y, int algo, i
 int spmv_b200_hll_time(spmv_b200_hll *H, const double *x, double *y, int kernel, int warmup, int iters, double *mean_seconds,
                        double *min_seconds) {
     if (!H || (H->N > 0 && H->slots > 0 && !x)) return fail(SPMV_B200_ERR_INVALID, "hll_time: NULL argument");
-    if (kernel < 0 || kernel > 2) return fail(SPMV_B200_ERR_INVALID, "hll_time: kernel must be 0, 1 or 2");
+    if (kernel < 0 || kernel > 3) return fail(SPMV_B200_ERR_INVALID, "hll_time: kernel must be 0, 1, 2 or 3");
     if (!H->stage_x) SPMV_TRY_CUDA(cudaMalloc(&H->stage_x, std::max<size_t>(H->N, 1) * sizeof(double)));
     if (!H->stage_y) SPMV_TRY_CUDA(cudaMalloc(&H->stage_y, std::max<size_t>(H->M, 1) * sizeof(double)));
     return time_products(H->M, H->N, x, y, H->stage_x, H->stage_y, warmup, iters, mean_seconds, min_seconds, [&]() {
         if (kernel == 1) return spmv_b200_hll_spmv_slice(H, H->stage_x, H->stage_y, nullptr);
         if (kernel == 2) return spmv_b200_hll_spmv_stream(H, H->stage_x, H->stage_y, nullptr);
+        if (kernel == 3) return spmv_b200_hll_spmv_rows(H, H->stage_x, H->stage_y, nullptr);
         return spmv_b200_hll_spmv(H, H->stage_x, H->stage_y, nullptr);
     });
 }

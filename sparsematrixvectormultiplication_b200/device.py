@@ -13,7 +13,7 @@ import numpy as np
 from . import _native as N
 
 ALGO_AUTO, ALGO_VECTOR, ALGO_TILE, ALGO_STREAM, ALGO_BINNED, ALGO_ROW = 0, 1, 2, 3, 4, 5
-ALGO_NAMES = {0: "auto", 1: "csr_vector_kernel", 2: "csr_tile_kernel", 3: "csr_stream_kernel", 4: "csr_binned_kernel", 5: "csr_row_kernel"}
+ALGO_NAMES = {0: "auto", 1: "csr_vector_kernel", 2: "csr_stream_kernel (ALGO_TILE is retired)", 3: "csr_stream_kernel", 4: "csr_binned_kernel", 5: "csr_row_kernel"}
 HLL_KERNEL_NAMES = {0: "hll_slice_kernel", 1: "hll_stream_kernel", 2: "hll_row_kernel"}
 SYNTH_LAP2D, SYNTH_LAP3D, SYNTH_UNIFORM = 1, 2, 3
 

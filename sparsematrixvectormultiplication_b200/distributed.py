@@ -482,6 +482,18 @@ class AllgatherPowerIteration(PowerIteration):
         self.own = self.xg[self.rank * self.stride: (self.rank + 1) * self.stride]        # send buffer == its slot of xg
         self.launches_per_step = 5 if self.world > 1 else 3
         self.recv_bytes = 8 * (self.world - 1) * self.stride
+        # The all-gather must run WHILE the interior product runs.  Both are ready at the same moment and the product's
+        # grid (hundreds of thousands of small CTAs) keeps refilling every SM slot that frees up, so NCCL's few large CTAs
+        # only got onto the SMs when the product had drained (measured on 2 GPUs: step = all-gather + product, no
+        # overlap).  A communicator of its own on a HIGH-PRIORITY stream makes the block scheduler place NCCL's CTAs first.
+        self.ag_group = group
+        if self.world > 1 and dist.get_backend(group) == "nccl":
+            try:
+                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+                ranks = dist.get_process_group_ranks(group) if group is not None else list(range(dist.get_world_size()))
+                self.ag_group = dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
+            except Exception:   # older torch: keep the default communicator (correct, just not overlapped)
+                self.ag_group = group
 
     def reset(self, value=1.0):
         self.dev.vec_fill(self.xg, value)
@@ -490,7 +502,7 @@ class AllgatherPowerIteration(PowerIteration):
         d = self.dev
         lo, hi = self.interior
         if self.world > 1:
-            work = dist.all_gather_into_tensor(self.xg, self.own, group=self.group, async_op=True)
+            work = dist.all_gather_into_tensor(self.xg, self.own, group=self.ag_group, async_op=True)
             if hi > lo:
                 self.A.spmv_rows(lo, hi, self.xg, self.y)          # reads the own slice only: overlaps the collective
             work.wait()                                            # compute stream waits for the NCCL stream (no host block)

@@ -705,6 +705,7 @@ def test_host_pipeline_tapered_windows(dev, checker, kind):
     units, upload pieces ending at each window's last referenced column).  Banded columns (lap2d: windows start as soon
     as their piece lands) and random columns (every window needs all of x): the host call gives the bits of the resident
     product and matches the serial oracle."""
+    import os
     import torch
     from sparsematrixvectormultiplication_b200 import synth
     if kind == "lap2d":
@@ -726,11 +727,23 @@ def test_host_pipeline_tapered_windows(dev, checker, kind):
     for _ in range(2):                               # the second call reuses the window plan
         got = A.spmv_host(x, np.full(info.M, np.nan))
         assert np.array_equal(bits(got), bits(resident)), f"{kind}: tapered host pipeline differs from the resident product"
+    # pinned host buffers: the kernels store y straight into the caller's buffer (no download copies); and the same call
+    # with that path switched off
+    xh = torch.from_numpy(x).pin_memory()
+    for knob in ("1", "0"):
+        os.environ["SPMV_B200_HOST_ZEROCOPY"] = knob
+        yh = torch.full((info.M,), float("nan"), dtype=torch.float64).pin_memory()
+        A.spmv_host_ptr(xh.data_ptr(), yh.data_ptr())
+        assert np.array_equal(bits(yh.numpy()), bits(resident)), f"{kind}: pinned host call, zero-copy {knob}"
+    os.environ.pop("SPMV_B200_HOST_ZEROCOPY", None)
     H = A.to_hll()
     H.spmv(xd, yd)
     got = H.spmv_host(x, np.full(info.M, np.nan))
     assert np.array_equal(bits(got), bits(yd.cpu().numpy())), f"{kind}: HLL host pipeline"
     assert_close(got, y_ref, scale, kind + " hll")
+    yh = torch.full((info.M,), float("nan"), dtype=torch.float64).pin_memory()
+    H.spmv_host_ptr(xh.data_ptr(), yh.data_ptr())
+    assert np.array_equal(bits(yh.numpy()), bits(yd.cpu().numpy())), f"{kind}: HLL pinned host call"
 
 
 def test_main_style_driver_writes_the_csv(dev, tmp_path):
@@ -751,10 +764,10 @@ def test_main_style_driver_writes_the_csv(dev, tmp_path):
     assert rows[0]["rows"] == "10" and rows[0]["nonzeros"] == "5"
     assert rows[3]["rows"] == "90000" and rows[3]["nonzeros"] == str(5 * 90000 - 4 * 300)
     for r in rows:
-        for k in ("csr_auto", "csr_stream", "csr_tile", "csr_vector", "hll_auto", "hll_stream", "hll_slice"):
+        for k in ("csr_auto", "csr_row", "csr_stream", "csr_vector", "csr_binned", "hll_auto", "hll_rows", "hll_stream", "hll_slice"):
             assert float(r[f"time_{k}"]) > 0 and float(r[f"flops_{k}"]) > 0
             assert float(r[f"relative_error_{k}"]) <= 1e-12 and float(r[f"absolute_error_{k}"]) <= 1e-9
-        assert float(r["time_e2e_csr_host"]) > 0 and r["ngpus"] == "1"
+        assert float(r["time_e2e_csr_host"]) > 0 and r["ngpus"] == "1" and r["check_baseline"] == "gpu_serial_order_kernel"
 
 
 def test_short_rows_are_summed_in_serial_order_on_every_path(dev, checker):

@@ -179,18 +179,21 @@ if "e2e" in what:
     xh.copy_(1.0 + (torch.arange(M) % 7).double() / 8.0)
     yh = torch.empty(M, dtype=torch.float64).pin_memory()
     for rnd in range(2):
-        for windows in (0, 4, 8, 12, 16, 20, 24, 32, 48, 64):
-            if windows:
-                os.environ["SPMV_B200_HOST_WINDOWS"] = str(windows)
-            else:
-                os.environ.pop("SPMV_B200_HOST_WINDOWS", None)
-            A.replan()
-            for _ in range(2):
-                A.spmv_host_ptr(xh.data_ptr(), yh.data_ptr())
-            t0 = time.perf_counter()
-            for _ in range(10):
-                A.spmv_host_ptr(xh.data_ptr(), yh.data_ptr())
-            dt = (time.perf_counter() - t0) / 10
-            print(f"round {rnd}: windows {windows or 'auto'}: {dt*1e3:.3f} ms")
+        for zero in ("1", "0"):
+            os.environ["SPMV_B200_HOST_ZEROCOPY"] = zero
+            for windows in (0, 4, 8, 16, 32, 64):
+                if windows:
+                    os.environ["SPMV_B200_HOST_WINDOWS"] = str(windows)
+                else:
+                    os.environ.pop("SPMV_B200_HOST_WINDOWS", None)
+                A.replan()
+                for _ in range(2):
+                    A.spmv_host_ptr(xh.data_ptr(), yh.data_ptr())
+                t0 = time.perf_counter()
+                for _ in range(10):
+                    A.spmv_host_ptr(xh.data_ptr(), yh.data_ptr())
+                dt = (time.perf_counter() - t0) / 10
+                print(f"round {rnd}: zero-copy y {zero} windows {windows or 'auto (tapered)'}: {dt*1e3:.3f} ms")
+    os.environ.pop("SPMV_B200_HOST_ZEROCOPY", None)
     os.environ.pop("SPMV_B200_HOST_WINDOWS", None)
     A.close()

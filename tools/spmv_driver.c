@@ -37,8 +37,8 @@ typedef struct {
     int ran;
 } KernelRow;
 
-enum { K_CSR_AUTO, K_CSR_STREAM, K_CSR_TILE, K_CSR_VECTOR, K_HLL_AUTO, K_HLL_STREAM, K_HLL_SLICE, K_COUNT };
-static const char *kNames[K_COUNT] = {"csr_auto", "csr_stream", "csr_tile", "csr_vector", "hll_auto", "hll_stream", "hll_slice"};
+enum { K_CSR_AUTO, K_CSR_ROW, K_CSR_STREAM, K_CSR_VECTOR, K_CSR_BINNED, K_HLL_AUTO, K_HLL_ROWS, K_HLL_STREAM, K_HLL_SLICE, K_COUNT };
+static const char *kNames[K_COUNT] = {"csr_auto", "csr_row", "csr_stream", "csr_vector", "csr_binned", "hll_auto", "hll_rows", "hll_stream", "hll_slice"};
 
 typedef struct {
     const char *csv;
@@ -66,7 +66,7 @@ static void write_csv(const Options *opt, const char *matrix, int M, int N, long
         for (int i = 0; i < K_COUNT; ++i) fprintf(fp, ",gbs_%s", kNames[i]);
         for (int i = 0; i < K_COUNT; ++i) fprintf(fp, ",roofline_%s", kNames[i]);
         for (int i = 0; i < K_COUNT; ++i) fprintf(fp, ",relative_error_%s,absolute_error_%s", kNames[i], kNames[i]);
-        fprintf(fp, ",time_e2e_csr_host,time_e2e_hll_host,peak_gbs,ngpus\n");
+        fprintf(fp, ",time_e2e_csr_host,time_e2e_hll_host,peak_gbs,ngpus,check_baseline\n");
     }
     fprintf(fp, "%s,%d,%d,%lld", matrix, M, N, nz);
     for (int i = 0; i < K_COUNT; ++i) fprintf(fp, ",%.15f", k[i].time);
@@ -74,7 +74,9 @@ static void write_csv(const Options *opt, const char *matrix, int M, int N, long
     for (int i = 0; i < K_COUNT; ++i) fprintf(fp, ",%.6f", k[i].gbs);
     for (int i = 0; i < K_COUNT; ++i) fprintf(fp, ",%.6f", k[i].roofline);
     for (int i = 0; i < K_COUNT; ++i) fprintf(fp, ",%.15f,%.15f", k[i].err.mean_rel_err, k[i].err.mean_abs_err);
-    fprintf(fp, ",%.15f,%.15f,%.1f,1\n", e2e_csr, e2e_hll, opt->peak_gbs);
+    /* the error columns compare with this library's one-thread-per-row kernel in the reference's summation order (bit-identical
+     * to csr_matrix_vector_mult, tests/test_gpu_parity.py) -- NOT with a CPU product: the library has no CPU path */
+    fprintf(fp, ",%.15f,%.15f,%.1f,1,gpu_serial_order_kernel\n", e2e_csr, e2e_hll, opt->peak_gbs);
     fclose(fp);
 }
 
@@ -105,8 +107,8 @@ static int run_resident(const Options *opt, const char *name, spmv_b200_csr *A, 
 
     KernelRow k[K_COUNT];
     memset(k, 0, sizeof k);
-    const int csr_algo[4] = {SPMV_B200_ALGO_AUTO, SPMV_B200_ALGO_STREAM, SPMV_B200_ALGO_TILE, SPMV_B200_ALGO_VECTOR};
-    const int hll_kernel[3] = {0, 2, 1};
+    const int csr_algo[K_HLL_AUTO] = {SPMV_B200_ALGO_AUTO, SPMV_B200_ALGO_ROW, SPMV_B200_ALGO_STREAM, SPMV_B200_ALGO_VECTOR, SPMV_B200_ALGO_BINNED};
+    const int hll_kernel[K_COUNT - K_HLL_AUTO] = {0, 3, 2, 1};
     int bad = 0;
     printf("\n=== %s: %d x %d, %lld nonzeros, %d hacks, %lld HLL slots ===\n", name, M, N, ci.nnz, hi.num_hacks, hi.slots);
     for (int i = 0; i < K_COUNT; ++i) {
