@@ -36,6 +36,7 @@ constexpr int kVecBatch = 4;                // independent column -> gather chai
 constexpr long long kAutotuneMinNnz = 1 << 22;  // plan-time timing of the row-kernel batch only pays on large matrices
 constexpr int kRowBatch = 4;                // the same with ONE lane per row (bin 0 of the binned kernel)
 constexpr int kVec4Default = 1;              // vector / binned kernels: aligned groups of four nonzeros per lane (SPMV_B200_VEC4)
+constexpr int kFusedCtasPerSm = 8;          // grid of the fused row kernels per SM (SPMV_B200_FUSED_CTAS_PER_SM)
 constexpr int kL2PersistDefault = 0;        // persisting-L2 window on x for the gather-bound kernels (SPMV_B200_L2_PERSIST)
 
 __device__ __forceinline__ void ldg_stream_f64x4(const float *p, double (&v)[4]) {  // fp32 storage: one 128-bit load
@@ -1106,12 +1107,14 @@ int csr_launch_window(const spmv_b200_csr *A, CsrPath path, int unit_begin, int 
     return launch_tiles(A, x, y, accumulate, path == kPathStream, stream, unit_begin, unit_end);
 }
 
-// grid of the fused row kernel: 8 CTAs of 256 threads per SM, whatever the matrix size
+// grid of the fused row kernel: a fixed number of CTAs of 256 threads per SM (8 are resident), whatever the matrix size
+int fused_ctas_per_sm() { return std::max(1, std::min(env_int("SPMV_B200_FUSED_CTAS_PER_SM", kFusedCtasPerSm), 256)); }
+
 static int fused_row_grid(const spmv_b200_csr *A) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return (int)std::max<long long>(1, std::min<long long>(8LL * sms, ((long long)A->M + 255) / 256));
+    return (int)std::max<long long>(1, std::min<long long>((long long)fused_ctas_per_sm() * sms, ((long long)A->M + 255) / 256));
 }
 
 static int launch_fused(const spmv_b200_csr *A, const double *x, double *y, const Epilogue &ep, cudaStream_t stream,
@@ -1366,7 +1369,7 @@ int spmv_b200_csr_spmv_fused(const spmv_b200_csr *A, const double *d_x, double *
     ep.partials_total = spmv_b200_csr_partials_count(A);
     if (peers) ep.peers = *peers;
     if (A->M == 0) return SPMV_B200_OK;
-    if (peers && env_int("SPMV_B200_FUSED_BOUNDARY_FIRST", 1)) SPMV_TRY(boundary_first_order(ep.peers, A->M, ep.order));
+    if (peers && env_int("SPMV_B200_FUSED_BOUNDARY_FIRST", 0)) SPMV_TRY(boundary_first_order(ep.peers, A->M, ep.order));
     return launch_fused(A, d_x, d_y, ep, as_stream(stream), -1);
 }
 
@@ -1388,7 +1391,7 @@ int spmv_b200_csr_spmv_fused_mail(const spmv_b200_csr *A, const double *d_x, dou
     ep.partials_total = spmv_b200_csr_partials_count(A);
     if (peers) ep.peers = *peers;
     ep.mail = *mail;
-    if (peers && env_int("SPMV_B200_FUSED_BOUNDARY_FIRST", 1)) SPMV_TRY(boundary_first_order(ep.peers, A->M, ep.order));
+    if (peers && env_int("SPMV_B200_FUSED_BOUNDARY_FIRST", 0)) SPMV_TRY(boundary_first_order(ep.peers, A->M, ep.order));
     return launch_fused(A, d_x, d_y, ep, as_stream(stream), -1);
 }
 

@@ -13,10 +13,11 @@ constexpr int kDefaultStages = 2;           // TMA pipeline depth of the stream 
 constexpr int kHllTileSlots = 3072;         // D_h: slots + rows per HLL tile (12 B per slot; stage = 49.5 KB with the wide margin)
 constexpr int kHllWideSlots = 1024;         // hacks with more slots (MAXNZ > 32) are processed straight from HBM
 
-// Walk order of the fused row kernels: the 256-row chunks that hold rows a neighbour references come FIRST, so that their
-// NVLink peer stores are long acknowledged when the launch ends (at the natural position -- the first and last planes of
-// the row range -- the last wave of the launch issues them and the launch end waits for them: +45 us per iteration on
-// 2 GPUs, +17 us on 8, profiles/r02c_bench_n2.json).  Chunk = 256 consecutive rows.
+// Optional walk order of the fused row kernels (SPMV_B200_FUSED_BOUNDARY_FIRST=1): the 256-row chunks that hold rows a
+// neighbour references come FIRST, so that their NVLink peer stores are long acknowledged when the launch ends.
+// Measured neutral on 2 GPUs (1.155 vs 1.156 ms per iteration, row kernel 1.263 vs 1.265: profiles/r02d_*): the 20-50 us
+// the peer stores cost are not an end-of-launch wait.  Off by default; the asynchronous form always uses it.
+// Chunk = 256 consecutive rows.
 struct ChunkOrder {
     int count = 0;                  // boundary intervals (ascending, disjoint), in chunks
     int lo[SPMV_B200_MAX_PEERS] = {}, hi[SPMV_B200_MAX_PEERS] = {};
@@ -229,6 +230,7 @@ HllPath hll_resolve(const spmv_b200_hll *H);
 int hll_launch_window(const spmv_b200_hll *H, HllPath path, int unit_begin, int unit_end, const double *x, double *y,
                       cudaStream_t stream);  // units: tiles (stream kernel) or hacks (slice and row kernels)
 int env_int(const char *name, int fallback);
+int fused_ctas_per_sm();  // csr.cu: CTAs per SM in the grid of the fused row kernels (CSR and HLL use the same value)
 
 // ---- persisting-L2 window on x (csr.cu) -------------------------------------------------------------------------
 // Gather-bound products (uniform 32/row, R-MAT) re-read x from DRAM because the once-read matrix stream keeps pushing

@@ -253,7 +253,7 @@ static int hll_fused_grid(const spmv_b200_hll *H) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return (int)std::max<long long>(1, std::min<long long>(8LL * sms, ((long long)H->M + 255) / 256));
+    return (int)std::max<long long>(1, std::min<long long>((long long)fused_ctas_per_sm() * sms, ((long long)H->M + 255) / 256));
 }
 
 static int hll_launch_fused(const spmv_b200_hll *H, const double *d_x, double *d_y, const Epilogue &ep, cudaStream_t stream,
@@ -606,7 +606,7 @@ int spmv_b200_hll_spmv_fused(const spmv_b200_hll *H, const double *d_x, double *
     ep.partials = d_partials;
     ep.partials_total = hll_fused_grid(H);
     if (peers) ep.peers = *peers;
-    if (peers && env_int("SPMV_B200_FUSED_BOUNDARY_FIRST", 1)) SPMV_TRY(boundary_first_order(ep.peers, H->M, ep.order));
+    if (peers && env_int("SPMV_B200_FUSED_BOUNDARY_FIRST", 0)) SPMV_TRY(boundary_first_order(ep.peers, H->M, ep.order));
     return hll_launch_fused(H, d_x, d_y, ep, as_stream(stream));
 }
 
@@ -626,7 +626,7 @@ int spmv_b200_hll_spmv_fused_mail(const spmv_b200_hll *H, const double *d_x, dou
     ep.partials_total = hll_fused_grid(H);
     if (peers) ep.peers = *peers;
     ep.mail = *mail;
-    if (peers && env_int("SPMV_B200_FUSED_BOUNDARY_FIRST", 1)) SPMV_TRY(boundary_first_order(ep.peers, H->M, ep.order));
+    if (peers && env_int("SPMV_B200_FUSED_BOUNDARY_FIRST", 0)) SPMV_TRY(boundary_first_order(ep.peers, H->M, ep.order));
     return hll_launch_fused(H, d_x, d_y, ep, as_stream(stream));
 }
 

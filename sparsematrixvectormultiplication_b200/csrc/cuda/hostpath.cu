@@ -12,21 +12,19 @@
 //     JA, rounded up to 256 KB), so window w is launched on a compute stream the moment ITS piece has landed;
 //   * the rows of window w are copied back on a download stream as soon as its kernel is done.
 //
-// Window sizes (round 2; measured on the B200 box, tools/r02_diag.py): one direction alone runs at 55.4 GB/s, both at
-// once at 47.9 GB/s each, so 128 MiB up + 128 MiB down cannot take less than 2.80 ms.  Equal windows lose to that
-// floor at both ends -- nothing comes down until the first window has its x (round 1: TWO equal chunks, because a
-// window's halo reached into the next chunk) and nothing goes up while the last window drains -- and every extra copy
-// costs ~3.5 us of engine turnaround, so more equal windows do not help (16 -> 3.41 ms, 32 -> 3.66, 64 -> 3.74).
-// Copies whose boundaries are not multiples of a large power of two are slower on top (12 windows 3.67 ms, 24 -> 3.87):
-// that was the "non-monotonic" sweep of round 1.  Hence TAPERED windows on 2 MiB boundaries: 1, 1, 2, 4, 8 units of
-// 2 MiB at the start, 16-unit windows in the middle, 8, 4, 2, 1, 1 at the end.
-//
-// For banded matrices (stencils, FEM) the upload of chunk w+1, the product of window w and the download of window
-// w-1 overlap, and the call takes max(upload, download) instead of their sum.  For matrices whose rows reference
-// the whole of x (random columns) the windows all wait for the last chunk: the upload is serial, the downloads
-// still overlap the products.  Results do not depend on W: a window launch runs the same kernel over a sub-range
-// of the same tiles.  Pageable host buffers work but serialise (cudaMemcpyAsync stages them); pinned or
-// cudaHostRegister'ed buffers give the overlap.
+// Measured on the B200 box (round 2, tools/r02_diag.py, profiles/r02d_diag_e2e.log), lap2d 4096^2 = 128 MiB each way:
+//   * one direction alone runs at 55.4 GB/s (2.42 ms); both at once, started together, 2.80 ms; but the download of a
+//     window can only start when its x has landed and, while the upload is still running, the device-to-host direction
+//     gets the smaller share (~42 vs ~52 GB/s), so the pipelined call cannot reach 2.80 ms: ~3.1 ms is its floor;
+//   * round 1 (equal chunks of x, a window's halo reaching into the NEXT chunk): 16 windows 3.41 ms, and copies whose
+//     boundaries were not multiples of a large power of two were slower still (12 windows 3.67, 24 -> 3.87): that was
+//     the "non-monotonic sweep";
+//   * upload pieces that end exactly where a window's columns end (256 KB aligned): 8 windows 3.25 ms, 16 -> 3.30;
+//   * kernels storing y straight into the caller's pinned buffer (zero-copy, no download copies and no kernel ->
+//     copy hand-over): 16 or 32 windows 3.21 ms  <- the default;
+//   * tapered windows (small first / last windows, 32 MiB in the middle) are SLOWER, 3.36 ms with copies and 3.58 ms
+//     zero-copy: large windows serialise the two directions more than the small ends save (SPMV_B200_HOST_TAPER=1/2
+//     keeps them for experiments).
 #include <algorithm>
 #include <vector>
 
@@ -38,6 +36,7 @@ namespace spmv {
 constexpr int kMaxWindows = 64;  // events; the automatic choice stops at kAutoWindows.  Round 1, equal windows, measured on lap2d 4096^2: 4 -> 3.93 ms, 8 -> 3.49, 16 -> 3.42, 24 -> 3.91, 32 -> 3.65, 48 -> 3.89
 constexpr int kAutoWindows = 16;
 constexpr int kZeroCopyDefault = 1;
+constexpr int kTaperDefault = 0;  // equal windows: the tapered schedules measured slower (see the header)
 constexpr long long kUnitRows = (2LL << 20) / 8;      // 2 MiB of y
 constexpr long long kPieceAlign = (256LL << 10) / 8;  // upload pieces end on 256 KB boundaries of x
 constexpr long long kMinWindowBytes = 2LL << 20;  // below 2 MB of x + y per window the launch overheads win
@@ -156,21 +155,29 @@ static int pick_windows(long long M, long long N, int units) {
 static std::vector<long long> window_rows(long long M, long long N, int units) {
     std::vector<long long> bounds;
     const long long total = (M + kUnitRows - 1) / kUnitRows;
-    if (env_int("SPMV_B200_HOST_WINDOWS", 0) > 0 || env_int("SPMV_B200_HOST_TAPER", 1) == 0 || total < 16 || units < 16) {
+    const int taper = env_int("SPMV_B200_HOST_TAPER", kTaperDefault);
+    if (env_int("SPMV_B200_HOST_WINDOWS", 0) > 0 || taper == 0 || total < 16 || units < 16) {
         const int W = pick_windows(M, N, units);
-        for (int w = 0; w <= W; ++w) bounds.push_back(M * w / W);
+        for (int w = 0; w <= W; ++w) {  // equal windows, on 256 KB boundaries when the vector is large
+            long long r = M * w / W;
+            if (w > 0 && w < W && M / W >= 8 * kPieceAlign) r = r / kPieceAlign * kPieceAlign;
+            bounds.push_back(r);
+        }
         return bounds;
     }
+    // taper 1: ramp 1, 1, 2, 4, 8 units up, 16-unit windows, ramp down; taper 2: ramp 1, 1, 2 up, then 4-unit (8 MiB) windows
     const long long ramp[5] = {1, 1, 2, 4, 8};
+    const int max_steps = taper == 2 ? 3 : 5;
     int steps = 0;
     long long ramp_sum = 0;
-    while (steps < 5 && 2 * (ramp_sum + ramp[steps]) <= total / 2) ramp_sum += ramp[steps++];
-    const long long middle = total - 2 * ramp_sum;
-    long long mid_size = 16;
+    while (steps < max_steps && 2 * (ramp_sum + ramp[steps]) <= total / 2) ramp_sum += ramp[steps++];
+    const long long middle = total - (taper == 2 ? 1 : 2) * ramp_sum;
+    long long mid_size = taper == 2 ? 4 : 16;
     while ((middle + mid_size - 1) / mid_size > kMaxWindows - 12) mid_size *= 2;
     std::vector<long long> sizes(ramp, ramp + steps);
     for (long long left = middle; left > 0; left -= mid_size) sizes.push_back(std::min(mid_size, left));
-    for (int i = steps - 1; i >= 0; --i) sizes.push_back(ramp[i]);
+    if (taper != 2)
+        for (int i = steps - 1; i >= 0; --i) sizes.push_back(ramp[i]);
     long long at = 0;
     bounds.push_back(0);
     for (long long sz : sizes) {

@@ -37,6 +37,9 @@ def main():
     ap.add_argument("--pick", type=int, default=1, help="keep the last of every N consecutive launches")
     ap.add_argument("--select", default="", help="comma separated launch indices to keep (applied before --pick)")
     ap.add_argument("--labels", nargs="*", default=[], help="column labels, in launch order after --pick")
+    ap.add_argument("--traffic-json", default="", help="update this JSON file (profiles/ncu_traffic.json) with the DRAM bytes per "
+                    "launch of every kept launch, keyed '<workload>|<kernel>'; bench.py reads roofline.traffic from it")
+    ap.add_argument("--workload", default="", help="workload name for --traffic-json (bench.py's config.workload)")
     args = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", args.report, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -77,6 +80,17 @@ def main():
             t = float(r[jr]) * scale.get(units[jr], 1.0) + float(r[jw]) * scale.get(units[jw], 1.0)
             cells.append(f"{t:.6g}")
         print("| **DRAM traffic per launch (read + written, bytes)** | " + " | ".join(cells) + " |")
+        if args.traffic_json and args.workload:
+            import json
+            import re
+            from pathlib import Path
+            path = Path(args.traffic_json)
+            table = json.loads(path.read_text()) if path.exists() else {}
+            for r, cell in zip(data, cells):
+                kernel = r[name_i].split("(")[0] if "<" not in r[name_i] else r[name_i][: r[name_i].rfind(">") + 1]
+                kernel = re.sub(r"\(int\)|void |spmv::|\s", "", kernel)
+                table[f"{args.workload}|{kernel}"] = {"dram_bytes": int(float(cell)), "source": str(Path(args.report).name)}
+            path.write_text(json.dumps(table, indent=1, sort_keys=True) + "\n")
 
 
 if __name__ == "__main__":

@@ -74,6 +74,39 @@ if "lap3d" in what:
     del F
     torch.cuda.empty_cache()
 
+if "fusedgrid" in what:
+    section("lap3d: plain row kernel vs the persistent fused row kernel, grid = CTAs per SM x 148")
+    n = int(os.environ.get("DIAG_LAP3D_N", "512"))
+    for ctas in (8, 16, 32, 64):
+        os.environ["SPMV_B200_FUSED_CTAS_PER_SM"] = str(ctas)
+        A = device.DeviceCSR.synth(synth.SYNTH_LAP3D, n)
+        i = A.info()
+        x = torch.ones(i.N, dtype=torch.float64, device="cuda")
+        y = torch.empty(i.M, dtype=torch.float64, device="cuda")
+        part = torch.zeros(A.partials_count(), dtype=torch.float64, device="cuda")
+        ss = torch.ones(1, dtype=torch.float64, device="cuda")
+        print(f"ctas/SM {ctas}: plan row_batch {i.row_batch} fused_batch {i.fused_batch}, partials {A.partials_count()}")
+        if ctas == 8:
+            for batch in (2, 4, 5):
+                os.environ["SPMV_B200_ROW_BATCH"] = str(batch)
+                A.replan()
+                print(f"  plain row kernel batch {batch}: {timeit(lambda: A.spmv(x, y, algo=device.ALGO_ROW))*1e3:.1f} us")
+            os.environ.pop("SPMV_B200_ROW_BATCH")
+        for batch in (2, 4, 5):
+            os.environ["SPMV_B200_FUSED_BATCH"] = str(batch)
+            a = timeit(lambda: A.spmv_fused(x, y))
+            b = timeit(lambda: A.spmv_fused(x, y, prev_sumsq=ss, partials=part))
+            print(f"  fused row kernel batch {batch}: loop only {a*1e3:.1f} us, with scale + partials {b*1e3:.1f} us")
+        os.environ.pop("SPMV_B200_FUSED_BATCH")
+        H = A.to_hll()
+        hp = torch.zeros(H.partials_count(), dtype=torch.float64, device="cuda")
+        print(f"  hll: plain rows {timeit(lambda: H.spmv(x, y))*1e3:.1f} us, fused {timeit(lambda: H.spmv_fused(x, y, prev_sumsq=ss, partials=hp))*1e3:.1f} us")
+        H.close()
+        A.close()
+        del x, y
+        torch.cuda.empty_cache()
+    os.environ.pop("SPMV_B200_FUSED_CTAS_PER_SM")
+
 if "rmat" in what:
     section("R-MAT 24/16: binned kernel launch shapes")
     rp, ci, va = synth.rmat_csr_device(24, 16)
@@ -179,9 +212,21 @@ if "e2e" in what:
     xh.copy_(1.0 + (torch.arange(M) % 7).double() / 8.0)
     yh = torch.empty(M, dtype=torch.float64).pin_memory()
     for rnd in range(2):
-        for zero in ("1", "0"):
+        for taper in ("0", "2"):
+            for zero in ("1", "0"):
+                os.environ["SPMV_B200_HOST_TAPER"], os.environ["SPMV_B200_HOST_ZEROCOPY"] = taper, zero
+                os.environ.pop("SPMV_B200_HOST_WINDOWS", None)
+                A.replan()
+                for _ in range(2):
+                    A.spmv_host_ptr(xh.data_ptr(), yh.data_ptr())
+                t0 = time.perf_counter()
+                for _ in range(10):
+                    A.spmv_host_ptr(xh.data_ptr(), yh.data_ptr())
+                print(f"round {rnd}: taper {taper} zero-copy {zero}: {(time.perf_counter() - t0) / 10 * 1e3:.3f} ms")
+        os.environ.pop("SPMV_B200_HOST_TAPER", None)
+        for zero in ("1",):
             os.environ["SPMV_B200_HOST_ZEROCOPY"] = zero
-            for windows in (0, 4, 8, 16, 32, 64):
+            for windows in (12, 16, 24, 32):
                 if windows:
                     os.environ["SPMV_B200_HOST_WINDOWS"] = str(windows)
                 else:
