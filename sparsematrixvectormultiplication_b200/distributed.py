@@ -88,6 +88,26 @@ def gather_needs(local_need: Tuple[int, int], world: int, device, group=None) ->
     return [tuple(int(v) for v in o.tolist()) for o in out]
 
 
+# ---- the padded rank-major layout of x behind the one-collective all-gather (host logic; the device twin of
+# remap_columns_host is spmv_b200_csr_remap_columns) ---------------------------------------------------------------
+def padded_layout(parts: List[Tuple[int, int]]) -> Tuple[List[int], int]:
+    """(starts, stride): part p's entries live at [p*stride, p*stride + rows_p); stride = largest part rounded up to 32."""
+    rows_max = max(e - s for s, e in parts)
+    return [s for s, _ in parts] + [parts[-1][1]], (rows_max + 31) // 32 * 32
+
+
+def remap_columns_host(cols, starts, stride):
+    """Column c owned by part p (starts[p] <= c < starts[p+1]) -> p*stride + (c - starts[p])."""
+    import numpy as np
+    st = np.asarray(starts, dtype=np.int64)
+    owner = np.searchsorted(st, np.asarray(cols, dtype=np.int64), side="right") - 1
+    return (owner * stride + np.asarray(cols, dtype=np.int64) - st[owner]).astype(np.int32)
+
+
+def unpad(xg: torch.Tensor, parts: List[Tuple[int, int]], stride: int) -> torch.Tensor:
+    return torch.cat([xg[p * stride: p * stride + (e - s)] for p, (s, e) in enumerate(parts)])
+
+
 class _CudaView:
     def __init__(self, ptr, n, typestr):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
@@ -471,9 +491,7 @@ class AllgatherPowerIteration(PowerIteration):
     def __init__(self, kind, p0, p1=0, p2=0, seed=0x5EED, group=None, parts=None, overlap=True):
         super().__init__(kind, p0, p1, p2, seed=seed, exchange="allgather", group=group, parts=parts)
         cu = self.x.device
-        rows_max = max(e - s for s, e in self.parts)
-        self.stride = (rows_max + 31) // 32 * 32
-        starts = [s for s, _ in self.parts] + [self.parts[-1][1]]
+        starts, self.stride = padded_layout(self.parts)
         # interior rows first (on the ORIGINAL column ids: own slice = [row_begin, row_end))
         self.interior = self.A.interior_rows(self.row_begin, self.row_end) if overlap and self.world > 1 else (0, self.rows)
         self.A.remap_columns(starts, self.stride)
@@ -522,4 +540,4 @@ class AllgatherPowerIteration(PowerIteration):
         refreshed by the next step's all-gather), so they are gathered here."""
         if self.world > 1:
             dist.all_gather_into_tensor(self.xg, self.own, group=self.group)
-        return torch.cat([self.xg[p * self.stride: p * self.stride + (e - s)] for p, (s, e) in enumerate(self.parts)])
+        return unpad(self.xg, self.parts, self.stride)

@@ -12,7 +12,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from sparsematrixvectormultiplication_b200 import host, partition, synth
-from sparsematrixvectormultiplication_b200.distributed import ExchangePlan, exchange_allgather, exchange_halo, gather_needs
+from sparsematrixvectormultiplication_b200.distributed import (ExchangePlan, exchange_allgather, exchange_halo, gather_needs,
+                                                               padded_layout, remap_columns_host, unpad)
 
 
 def test_closed_form_partition_is_the_reference_greedy_rule(checker):
@@ -73,6 +74,21 @@ def _worker(rank, world, port, kind, p0, iters, mode, out_dir):
         rp, ci, va = twin(p0, lo, hi)
         need = (int(ci.min()), int(ci.max()) + 1)
         plan = ExchangePlan.build(parts, gather_needs(need, world, "cpu"), rank)
+        if mode == "padded":   # AllgatherPowerIteration's host logic: padded rank-major x, remapped columns, ONE in-place all-gather
+            starts, stride = padded_layout(parts)
+            ci_pad = remap_columns_host(ci, starts, stride)
+            xg = torch.ones(world * stride, dtype=torch.float64)
+            own = xg[rank * stride: (rank + 1) * stride]
+            for _ in range(iters):
+                dist.all_gather_into_tensor(xg, own)           # refresh first, as the GPU class does
+                y = torch.from_numpy(chk.spmv_csr_serial(rp, ci_pad, va, xg.numpy()))
+                ss = (y * y).sum().reshape(1)
+                dist.all_reduce(ss)
+                own[:hi - lo] = y / ss.sqrt()
+            dist.all_gather_into_tensor(xg, own)
+            np.save(os.path.join(out_dir, f"x_{rank}.npy"), unpad(xg, parts, stride).numpy())
+            np.save(os.path.join(out_dir, f"need_{rank}.npy"), np.array(need))
+            return
         x = torch.ones(M, dtype=torch.float64)
         for _ in range(iters):
             y = torch.from_numpy(chk.spmv_csr_serial(rp, ci, va, x.numpy()))
@@ -86,7 +102,7 @@ def _worker(rank, world, port, kind, p0, iters, mode, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,mode", [(2, "allgather"), (2, "halo"), (3, "halo")])
+@pytest.mark.parametrize("world,mode", [(2, "allgather"), (2, "halo"), (3, "halo"), (2, "padded"), (3, "padded")])
 def test_power_iteration_two_and_three_ranks_gloo(tmp_path, port, world, mode):
     kind, p0, iters = synth.SYNTH_LAP3D, 7, 6
     mp.spawn(_worker, args=(world, _free_port(), kind, p0, iters, mode, str(tmp_path)), nprocs=world, join=True)
@@ -95,6 +111,6 @@ def test_power_iteration_two_and_three_ranks_gloo(tmp_path, port, world, mode):
     parts = partition.synth_partition(kind, p0, 0, 0, world)
     for r in range(world):
         x = np.load(tmp_path / f"x_{r}.npy")
-        lo, hi = np.load(tmp_path / f"need_{r}.npy") if mode == "halo" else (0, p0 ** 3)
+        lo, hi = np.load(tmp_path / f"need_{r}.npy") if mode == "halo" else (0, p0 ** 3)   # allgather / padded: whole vector
         lo, hi = min(lo, parts[r][0]), max(hi, parts[r][1])
         assert np.max(np.abs(x[lo:hi] - x_ref[lo:hi])) <= 1e-12 * np.max(np.abs(x_ref)), (r, mode)
