@@ -764,7 +764,7 @@ def bench_multi_gpu(args):
         P.reset(1.0)
         return {"x_err": x_err, "lambda_err": lam_err, "lambda": lam, "ok": ok}
 
-    modes = ("fused_mailbox", "fused_mailbox_hll", "fused_mailbox_csr_hack_aligned", "fused_async", "fused_peer_stores",
+    modes = ("fused_mailbox", "fused_split", "fused_split_hll", "fused_mailbox_hll", "fused_mailbox_csr_hack_aligned", "fused_async", "fused_peer_stores",
              "fused_nccl_halo", "halo", "allgather", "allgather_broadcasts")
     if args.modes:
         modes = tuple(m for m in modes if m in args.modes.split(",") or m == "fused_mailbox")
@@ -774,6 +774,10 @@ def bench_multi_gpu(args):
             P = AsyncPowerIteration(synth.SYNTH_LAP3D, n)
         elif mode == "fused_mailbox":
             P = FusedPowerIteration(synth.SYNTH_LAP3D, n, mailbox=True)
+        elif mode == "fused_split":
+            P = FusedPowerIteration(synth.SYNTH_LAP3D, n, split=True)
+        elif mode == "fused_split_hll":
+            P = FusedPowerIteration(synth.SYNTH_LAP3D, n, split=True, fmt="hll")
         elif mode == "fused_mailbox_hll":
             P = FusedPowerIteration(synth.SYNTH_LAP3D, n, mailbox=True, fmt="hll")
         elif mode == "fused_mailbox_csr_hack_aligned":

@@ -72,6 +72,7 @@ typedef struct {
     int auto_algo;       /* the SPMV_B200_ALGO_* that SPMV_B200_ALGO_AUTO resolves to        */
     int row_batch;       /* batch of the thread-per-row kernel (tuned at plan time)          */
     int fused_batch;     /* fused iterated product: 0 = fused stream kernel, else batch of the fused row kernel */
+    int flat_batch, flat_chunks; /* the FLAT fused row kernel of the two-launch iterated product (plan-time choice) */
 } spmv_b200_csr_info_t;
 
 typedef struct {
@@ -83,6 +84,7 @@ typedef struct {
     long long algorithmic_bytes;   /* slots*12 + 8*(num_hacks+1) + 8*M + 8*N                 */
     int auto_kernel;        /* automatic choice: 0 slice, 1 stream, 2 rows                   */
     int row_batch;          /* batch of the lane-per-row kernel (tuned at plan time)         */
+    int fused_batch, flat_batch, flat_chunks; /* plan-time choices of the fused iterated product (grid-stride / FLAT) */
 } spmv_b200_hll_info_t;
 
 /* ---- library / device ---------------------------------------------------------------- */
@@ -183,6 +185,23 @@ typedef struct {
 int spmv_b200_csr_spmv_fused_mail(const spmv_b200_csr *A, const double *d_x, double *d_y, double *d_partials,
                                   const spmv_b200_peers_t *peers, const spmv_b200_mail_t *mail, void *stream);
 
+/* The iterated product as TWO launches per iteration (round 2) -- the fastest form measured:
+ *   spmv_b200_csr_spmv_fused_flat   the fused product on a grid as large as the matrix (C consecutive 256-row chunks per
+ *       CTA, batch and C timed at plan time): y = (A x) / sqrt(*d_prev_sumsq) (NULL: no scaling), boundary rows mirrored
+ *       into `peers`, one partial sum of y^2 per CTA in d_partials (spmv_b200_csr_flat_partials_count doubles).  It
+ *       never waits for anything, so the block scheduler balances the SMs as it does for the plain product.  Rows of
+ *       up to 12 nonzeros only (one thread per row, the reference's summation order).
+ *   spmv_b200_mail_exchange         one CTA: adds the partials in a fixed order, publishes {sum, tag k+1} into slot
+ *       [k&1][rank] of every rank's mailbox (mail->iteration = k; same mailbox layout and tag numbering as
+ *       spmv_b200_csr_spmv_fused_mail), waits for the tags of all ranks in its own mailbox -- which also proves their
+ *       boundary rows have landed -- and leaves |w_k|^2 (ranks added in rank order) in *d_sumsq_out for the next
+ *       product launch.  mail->counter is not used.  Launches of one rank must be stream ordered.
+ * The HLL twins: spmv_b200_hll_spmv_fused_flat / spmv_b200_hll_flat_partials_count. */
+int spmv_b200_csr_flat_partials_count(const spmv_b200_csr *A);
+int spmv_b200_csr_spmv_fused_flat(const spmv_b200_csr *A, const double *d_x, double *d_y, const double *d_prev_sumsq,
+                                  double *d_partials, const spmv_b200_peers_t *peers, void *stream);
+int spmv_b200_mail_exchange(const double *d_partials, int count, const spmv_b200_mail_t *mail, double *d_sumsq_out, void *stream);
+
 /* The asynchronous form of the fused iterated product: no rank ever waits for the CURRENT launch of another rank.
  *   - x lives in a ring of THREE buffers (launch k reads ring[k%3], writes ring[(k+1)%3], own rows locally and the
  *     boundary rows into the neighbours' ring[(k+1)%3]); the caller passes d_x, d_y and peers->dst accordingly;
@@ -271,6 +290,10 @@ int spmv_b200_hll_spmv_fused(const spmv_b200_hll *H, const double *d_x, double *
                              double *d_partials, const spmv_b200_peers_t *peers, void *stream);
 int spmv_b200_hll_spmv_fused_mail(const spmv_b200_hll *H, const double *d_x, double *d_y, double *d_partials,
                                   const spmv_b200_peers_t *peers, const spmv_b200_mail_t *mail, void *stream);
+/* the two-launch form (see spmv_b200_csr_spmv_fused_flat; the exchange kernel spmv_b200_mail_exchange is shared) */
+int spmv_b200_hll_flat_partials_count(const spmv_b200_hll *H);
+int spmv_b200_hll_spmv_fused_flat(const spmv_b200_hll *H, const double *d_x, double *d_y, const double *d_prev_sumsq,
+                                  double *d_partials, const spmv_b200_peers_t *peers, void *stream);
 void spmv_b200_hll_free(spmv_b200_hll *H);
 
 /* ---- fp32 storage with fp64 arithmetic (BASELINE.json: y within 1e-5 relative of the serial fp64 product).  The value

@@ -60,13 +60,15 @@ class CsrInfo(C.Structure):  # include/spmv_b200.h spmv_b200_csr_info_t
     _fields_ = [("M", C.c_int), ("N", C.c_int), ("nnz", C.c_longlong), ("num_tiles", C.c_int),
                 ("num_long_rows", C.c_int), ("num_fragments", C.c_int), ("threads_per_row", C.c_int),
                 ("tile_items", C.c_int), ("long_threshold", C.c_int), ("algorithmic_bytes", C.c_longlong),
-                ("max_row_nnz", C.c_int), ("auto_algo", C.c_int), ("row_batch", C.c_int), ("fused_batch", C.c_int)]
+                ("max_row_nnz", C.c_int), ("auto_algo", C.c_int), ("row_batch", C.c_int), ("fused_batch", C.c_int),
+                ("flat_batch", C.c_int), ("flat_chunks", C.c_int)]
 
 
 class HllInfo(C.Structure):  # include/spmv_b200.h spmv_b200_hll_info_t
     _fields_ = [("M", C.c_int), ("N", C.c_int), ("num_hacks", C.c_int), ("max_maxnz", C.c_int),
                 ("slots", C.c_longlong), ("nnz_reference_slots", C.c_longlong),
-                ("algorithmic_bytes", C.c_longlong), ("auto_kernel", C.c_int), ("row_batch", C.c_int)]
+                ("algorithmic_bytes", C.c_longlong), ("auto_kernel", C.c_int), ("row_batch", C.c_int),
+                ("fused_batch", C.c_int), ("flat_batch", C.c_int), ("flat_chunks", C.c_int)]
 
 
 class Peers(C.Structure):  # include/spmv_b200.h spmv_b200_peers_t
@@ -123,6 +125,11 @@ SIGNATURES = {
     "spmv_b200_csr_interior_rows": (_I, [_V, _LL, _LL, c_int_p, c_int_p, _V]),
     "spmv_b200_csr_spmv_fused": (_I, [_V, _V, _V, _V, _V, C.POINTER(Peers), _V]),
     "spmv_b200_csr_spmv_fused_mail": (_I, [_V, _V, _V, _V, C.POINTER(Peers), C.POINTER(Mail), _V]),
+    "spmv_b200_csr_flat_partials_count": (_I, [_V]),
+    "spmv_b200_csr_spmv_fused_flat": (_I, [_V, _V, _V, _V, _V, C.POINTER(Peers), _V]),
+    "spmv_b200_mail_exchange": (_I, [_V, _I, C.POINTER(Mail), _V, _V]),
+    "spmv_b200_hll_flat_partials_count": (_I, [_V]),
+    "spmv_b200_hll_spmv_fused_flat": (_I, [_V, _V, _V, _V, _V, C.POINTER(Peers), _V]),
     "spmv_b200_csr_spmv_fused_async": (_I, [_V, _V, _V, _V, C.POINTER(Peers), C.POINTER(Async), _V]),
     "spmv_b200_vec_sum": (_I, [_V, _I, _V, _V]),
     "spmv_b200_ipc_alloc": (_I, [_LL, C.POINTER(_V), C.c_char * 64]),

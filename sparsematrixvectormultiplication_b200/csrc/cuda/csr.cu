@@ -274,17 +274,27 @@ csr_row_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, cons
 // in a fixed order; with a mailbox the launch first waits for the peers' previous launch and its last CTA publishes
 // |w|^2 (common.cuh).  A fixed grid walks the rows in 256-row chunks (grid-stride), so the number of partials -- and the
 // order of the sum of squares -- does not depend on the matrix size.
-template <int BATCH>
+//
+// FLAT (round 2, the two-launch form of the iterated product: spmv_b200_csr_spmv_fused_flat + spmv_b200_mail_exchange):
+// CTA b owns the flat_chunks consecutive chunks [b C, b C + C) and never waits for anything -- the exchange lives in a
+// one-CTA kernel of its own -- so the grid is as large as the matrix, the block scheduler balances the SMs, and the
+// per-row loop is unrolled as the compiler unrolls it in the plain row kernel.  Measured on lap3d 512^3, loop only
+// (profiles/r02h_diag_unroll.log): plain row kernel 2.07 ms, grid-stride 2.49, FLAT C=2 2.18.
+template <int BATCH, bool FLAT>
 __global__ void __launch_bounds__(256, 8)
 csr_row_fused_kernel(int M, const int *__restrict__ row_ptr, const int *__restrict__ col_idx, const double *__restrict__ values,
-                     const double *__restrict__ x, double *__restrict__ y, const __grid_constant__ Epilogue ep) {
+                     const double *__restrict__ x, double *__restrict__ y, const __grid_constant__ Epilogue ep, int flat_chunks) {
     __shared__ double warp_sq[8];
     __shared__ double mail_total;
     bool scaled;
     const double inv_norm = fused_inv_norm(ep, scaled, &mail_total);
     double sq = 0.0;
     const int chunks = (M + 255) >> 8;
-    for (int q = blockIdx.x; q < chunks; q += gridDim.x) {
+    const int q_begin = FLAT ? (int)blockIdx.x * flat_chunks : (int)blockIdx.x;
+    const int q_end = FLAT ? min(chunks, q_begin + flat_chunks) : chunks;
+    const int q_step = FLAT ? 1 : (int)gridDim.x;
+    constexpr int kUnroll = FLAT ? 4 : 1;
+    for (int q = q_begin; q < q_end; q += q_step) {
         // boundary chunks first (ChunkOrder); peer stores: a CTA-uniform test on the chunk (uniform datapath), the per-row
         // range test only inside -- done per row for every row it cost 30 us per peer per 56 M rows
         const long long chunk_lo = (long long)ordered_chunk(ep.order, q) * 256;
@@ -293,6 +303,10 @@ csr_row_fused_kernel(int M, const int *__restrict__ row_ptr, const int *__restri
         if (row >= M) continue;
         const int lo = __ldg(row_ptr + row), hi = __ldg(row_ptr + row + 1);
         double acc = 0.0;
+        // the plain row kernel gets this loop unrolled by the compiler (the loads of several batches in flight at once);
+        // inside the chunk walk that does not happen by itself.  Asked for in the FLAT form only: with the grid-stride
+        // walk it made batch 2 slower (2.49 -> 3.49 ms: the L1 footprint of the row streams is at the edge already)
+#pragma unroll kUnroll
         for (int k = lo; k < hi; k += BATCH) {
             int c[BATCH];
             double v[BATCH], xv[BATCH];
@@ -645,6 +659,54 @@ __global__ void interior_rows_kernel(int M, int mid, const int *__restrict__ row
     else atomicMin(out + 1, (int)r);
 }
 
+// The exchange of the two-launch iterated product (spmv_b200_mail_exchange): ONE CTA.  (1) the partials of the flat
+// product kernel, added in a fixed order (thread t adds elements t, t + 1024, ...; fixed tree); (2) {sum, tag k+1} into
+// slot [k&1][rank] of every rank's mailbox -- the product kernel has completed (stream order), a system-scope fence and
+// a release store order its peer stores before the tag; (3) wait for the tags of all ranks in the own mailbox, add
+// their sums in rank order, leave |w_k|^2 in *sumsq_out for the next product launch.
+__global__ void __launch_bounds__(1024)
+mail_exchange_kernel(const double *__restrict__ partials, int count, const __grid_constant__ spmv_b200_mail_t mail,
+                     double *__restrict__ sumsq_out) {
+    __shared__ double part[1024];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < count; i += 1024) s += __ldcg(partials + i);
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int half = 512; half > 0; half >>= 1) {
+        if ((int)threadIdx.x < half) part[threadIdx.x] += part[threadIdx.x + half];
+        __syncthreads();
+    }
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    const double mine = part[0];
+    if (mail.world == 1) {  // nobody to talk to
+        if (lane == 0) *sumsq_out = mine;
+        return;
+    }
+    __threadfence_system();
+    if (lane < mail.world) {
+        unsigned long long *slot = mail.box[lane] + 2 * ((int)(mail.iteration & 1) * mail.world + mail.rank);
+        st_relaxed_sys(slot, (unsigned long long)__double_as_longlong(mine));
+        st_release_sys(slot + 1, mail.iteration + 1);
+    }
+    double got = 0.0;
+    if (lane < mail.world) {
+        const unsigned long long *slot = mail.box[mail.rank] + 2 * ((int)(mail.iteration & 1) * mail.world + lane);
+        const long long t0 = clock64();
+        while (ld_acquire_sys(slot + 1) != mail.iteration + 1) {
+            if (clock64() - t0 > kMailSpinCycles) {
+                *mail.status = 1;
+                break;
+            }
+            __nanosleep(40);
+        }
+        got = __longlong_as_double((long long)ld_acquire_sys(slot));
+    }
+    double total = 0.0;
+    for (int r = 0; r < mail.world; ++r) total += __shfl_sync(0xffffffffu, got, r);
+    if (lane == 0) *sumsq_out = total;
+}
+
 __global__ void to_f32_kernel(const double *__restrict__ in, float *__restrict__ out, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (float)in[i];  // round to nearest even
@@ -728,6 +790,13 @@ template <typename V>
 static int launch_rows(int row_begin, int row_end, const int *row_ptr, const int *col_idx, const V *values,
                        const V *x, V *y, int batch, int accumulate, cudaStream_t stream);
 static int safe_vector_nnz(const spmv_b200_csr *A);
+struct FlatChoice {
+    int batch, chunks;
+};
+static const FlatChoice kFlatCandidates[] = {{2, 1}, {2, 2}, {2, 4}, {4, 2}, {4, 4}, {5, 2}, {5, 4}, {3, 2}};
+static int flat_grid(long long M, int chunks_per_cta);
+static int launch_fused_flat(const spmv_b200_csr *A, const double *x, double *y, const Epilogue &ep, cudaStream_t stream,
+                             int batch, int chunks_per_cta);
 static int launch_fused(const spmv_b200_csr *A, const double *x, double *y, const Epilogue &ep, cudaStream_t stream, int batch);
 static int fused_row_grid(const spmv_b200_csr *A);
 
@@ -850,6 +919,21 @@ static int build_plan(spmv_b200_csr *A, cudaStream_t stream) {
             }
             cudaGetLastError();
             cudaFree(partials);
+            // the FLAT form (two-launch iterated product): batch x chunks per CTA
+            double *flat_partials = nullptr;
+            if (cudaMalloc(&flat_partials, (size_t)flat_grid(M, 1) * sizeof(double)) == cudaSuccess) {
+                Epilogue fe;
+                fe.partials = flat_partials;
+                const int n = (int)(sizeof kFlatCandidates / sizeof kFlatCandidates[0]);
+                const int best = tune_candidates(M, A->N, n, 1, stream, [&](int i, double *x, double *y) {
+                    fe.partials_total = flat_grid(M, kFlatCandidates[i].chunks);
+                    return launch_fused_flat(A, x, y, fe, stream, kFlatCandidates[i].batch, kFlatCandidates[i].chunks);
+                });
+                A->flat_batch = kFlatCandidates[best].batch;
+                A->flat_chunks = kFlatCandidates[best].chunks;
+            }
+            cudaGetLastError();
+            cudaFree(flat_partials);
         }
     }
     return SPMV_B200_OK;
@@ -1122,14 +1206,38 @@ static int launch_fused(const spmv_b200_csr *A, const double *x, double *y, cons
     if (batch < 0) batch = env_int("SPMV_B200_FUSED_BATCH", A->fused_batch);
     if (batch == 0) return stream_launch_csr(A, x, y, 0, &ep, stream);
     const int g = fused_row_grid(A);
-#define FROW_CASE(B) case B: csr_row_fused_kernel<B><<<g, 256, 0, stream>>>(A->M, A->row_ptr, A->col_idx, A->values, x, y, ep); break;
+#define FROW_CASE(B) case B: csr_row_fused_kernel<B, false><<<g, 256, 0, stream>>>(A->M, A->row_ptr, A->col_idx, A->values, x, y, ep, 0); break;
     switch (batch) {
         FROW_CASE(2) FROW_CASE(3) FROW_CASE(5) FROW_CASE(6) FROW_CASE(7)
-        default: csr_row_fused_kernel<4><<<g, 256, 0, stream>>>(A->M, A->row_ptr, A->col_idx, A->values, x, y, ep); break;
+        default: csr_row_fused_kernel<4, false><<<g, 256, 0, stream>>>(A->M, A->row_ptr, A->col_idx, A->values, x, y, ep, 0); break;
     }
 #undef FROW_CASE
     SPMV_TRY_CUDA(cudaGetLastError());
     return SPMV_B200_OK;
+}
+
+// ---- the FLAT form: C consecutive chunks per CTA, grid = ceil(chunks / C); batch and C are timed at plan time ----
+static int flat_grid(long long M, int chunks_per_cta) {
+    const long long chunks = (M + 255) / 256;
+    return (int)std::max<long long>(1, (chunks + chunks_per_cta - 1) / chunks_per_cta);
+}
+
+static int launch_fused_flat(const spmv_b200_csr *A, const double *x, double *y, const Epilogue &ep, cudaStream_t stream,
+                             int batch, int chunks_per_cta) {
+    const int g = flat_grid(A->M, chunks_per_cta);
+#define FLAT_CASE(B) case B: csr_row_fused_kernel<B, true><<<g, 256, 0, stream>>>(A->M, A->row_ptr, A->col_idx, A->values, x, y, ep, chunks_per_cta); break;
+    switch (batch) {
+        FLAT_CASE(2) FLAT_CASE(3) FLAT_CASE(5)
+        default: csr_row_fused_kernel<4, true><<<g, 256, 0, stream>>>(A->M, A->row_ptr, A->col_idx, A->values, x, y, ep, chunks_per_cta); break;
+    }
+#undef FLAT_CASE
+    SPMV_TRY_CUDA(cudaGetLastError());
+    return SPMV_B200_OK;
+}
+
+static void flat_choice(const spmv_b200_csr *A, int &batch, int &chunks) {
+    batch = env_int("SPMV_B200_FLAT_BATCH", A->flat_batch);
+    chunks = std::max(1, env_int("SPMV_B200_FLAT_CHUNKS", A->flat_chunks));
 }
 
 int boundary_first_order(const spmv_b200_peers_t &peers, int M, ChunkOrder &order) {
@@ -1322,6 +1430,8 @@ int spmv_b200_csr_info(const spmv_b200_csr *A, spmv_b200_csr_info_t *info) {
     }
     info->row_batch = A->row_batch;
     info->fused_batch = A->fused_batch;
+    info->flat_batch = A->flat_batch;
+    info->flat_chunks = A->flat_chunks;
     return SPMV_B200_OK;
 }
 
@@ -1371,6 +1481,31 @@ int spmv_b200_csr_spmv_fused(const spmv_b200_csr *A, const double *d_x, double *
     if (A->M == 0) return SPMV_B200_OK;
     if (peers && env_int("SPMV_B200_FUSED_BOUNDARY_FIRST", 0)) SPMV_TRY(boundary_first_order(ep.peers, A->M, ep.order));
     return launch_fused(A, d_x, d_y, ep, as_stream(stream), -1);
+}
+
+int spmv_b200_csr_flat_partials_count(const spmv_b200_csr *A) {
+    if (!A) return 0;
+    int batch, chunks;
+    flat_choice(A, batch, chunks);
+    return flat_grid(A->M, chunks);
+}
+
+int spmv_b200_csr_spmv_fused_flat(const spmv_b200_csr *A, const double *d_x, double *d_y, const double *d_prev_sumsq,
+                                  double *d_partials, const spmv_b200_peers_t *peers, void *stream) {
+    if (!A || !d_y || (A->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_flat: NULL argument");
+    if (A->max_row > kRowKernelMaxLen)
+        return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_flat: rows of up to %d nonzeros only (longest row: %d)", kRowKernelMaxLen, A->max_row);
+    if (peers && (peers->count < 0 || peers->count > SPMV_B200_MAX_PEERS))
+        return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_flat: bad peer count %d", peers->count);
+    if (A->M == 0) return SPMV_B200_OK;
+    int batch, chunks;
+    flat_choice(A, batch, chunks);
+    Epilogue ep;
+    ep.prev_sumsq = d_prev_sumsq;
+    ep.partials = d_partials;
+    ep.partials_total = flat_grid(A->M, chunks);
+    if (peers) ep.peers = *peers;
+    return launch_fused_flat(A, d_x, d_y, ep, as_stream(stream), batch, chunks);
 }
 
 int spmv_b200_csr_spmv_fused_mail(const spmv_b200_csr *A, const double *d_x, double *d_y, double *d_partials,
@@ -1476,6 +1611,17 @@ int spmv_b200_csr_interior_rows(const spmv_b200_csr *A, long long col_lo, long l
     SPMV_TRY_CUDA(e);
     *row_lo = out[0];
     *row_hi = std::max(out[0], out[1]);
+    return SPMV_B200_OK;
+}
+
+int spmv_b200_mail_exchange(const double *d_partials, int count, const spmv_b200_mail_t *mail, double *d_sumsq_out, void *stream) {
+    if (!d_partials || count < 1 || !mail || !d_sumsq_out) return fail(SPMV_B200_ERR_INVALID, "mail_exchange: bad arguments");
+    if (mail->world < 1 || mail->world > SPMV_B200_MAX_RANKS || mail->rank < 0 || mail->rank >= mail->world || !mail->status)
+        return fail(SPMV_B200_ERR_INVALID, "mail_exchange: bad mailbox description (world %d, rank %d)", mail->world, mail->rank);
+    for (int r = 0; r < mail->world; ++r)
+        if (!mail->box[r]) return fail(SPMV_B200_ERR_INVALID, "mail_exchange: mailbox of rank %d is NULL", r);
+    mail_exchange_kernel<<<1, 1024, 0, as_stream(stream)>>>(d_partials, count, *mail, d_sumsq_out);
+    SPMV_TRY_CUDA(cudaGetLastError());
     return SPMV_B200_OK;
 }
 

@@ -147,6 +147,38 @@ struct HllTile {      // tiles[t] = first hack of tile t and its first slot; til
     long long slot;
 };
 
+
+// Times launch(i) for candidates i = 0 .. n-1 on scratch vectors and returns the fastest index (plan time, large matrices)
+template <class Launch>
+int tune_candidates(long long M, long long N, int n, int fallback, cudaStream_t stream, Launch launch) {
+    double *x = nullptr, *y = nullptr;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int best = fallback;
+    if (cudaMalloc(&x, (size_t)(N > 0 ? N : 1) * sizeof(double)) == cudaSuccess &&
+        cudaMalloc(&y, (size_t)(M > 0 ? M : 1) * sizeof(double)) == cudaSuccess &&
+        cudaMemsetAsync(x, 0, (size_t)(N > 0 ? N : 1) * sizeof(double), stream) == cudaSuccess &&
+        cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) {
+        float best_ms = -1.0f;
+        for (int i = 0; i < n; ++i) {
+            bool ok = launch(i, x, y) == SPMV_B200_OK;  // warm-up
+            ok = ok && cudaEventRecord(a, stream) == cudaSuccess;
+            for (int rep = 0; rep < 5 && ok; ++rep) ok = launch(i, x, y) == SPMV_B200_OK;
+            ok = ok && cudaEventRecord(b, stream) == cudaSuccess && cudaEventSynchronize(b) == cudaSuccess;
+            float ms = 0.0f;
+            if (!ok || cudaEventElapsedTime(&ms, a, b) != cudaSuccess) break;
+            if (best_ms < 0.0f || ms < best_ms) {
+                best_ms = ms;
+                best = i;
+            }
+        }
+    }
+    cudaGetLastError();
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+    cudaFree(x);
+    cudaFree(y);
+    return best;
+}
 }  // namespace spmv
 
 struct spmv_b200_csr {
@@ -174,6 +206,7 @@ struct spmv_b200_csr {
     int row_batch32 = 4; // the same for fp32 storage (tuned by spmv_b200_csr_enable_f32)
     bool short_rows_stream = false;  // plan-time timing found the stream kernel faster than every row-kernel batch
     int fused_batch = 0;             // fused iterated product: 0 = fused stream kernel, else batch of the fused row kernel
+    int flat_batch = 4, flat_chunks = 2;  // the FLAT fused row kernel (two-launch iterated product), timed at plan time
     // stream kernel launch shape
     int stages = spmv::kDefaultStages;
     int consumers = 12;
@@ -203,6 +236,7 @@ struct spmv_b200_hll {
     int row_batch = 4;   // hll_row_kernel batch (tuned at plan time on large matrices)
     int row_batch32 = 4; // the same for fp32 storage (tuned by spmv_b200_hll_enable_f32)
     int fused_batch = 0; // hll_row_fused_kernel batch (tuned at plan time; 0 = row_batch)
+    int flat_batch = 4, flat_chunks = 2;  // the FLAT form of hll_row_fused_kernel (two-launch iterated product)
     bool narrow_stream = false;  // plan-time timing found the stream kernel faster than every row-kernel batch
     double *stage_x = nullptr;
     double *stage_y = nullptr;

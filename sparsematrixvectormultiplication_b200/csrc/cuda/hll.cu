@@ -126,11 +126,12 @@ hll_row_kernel(int hack_begin, int hack_end, const long long *__restrict__ hack_
 // per-CTA partials: |w|^2, lambda and x are bitwise equal to the CSR iteration on rows without padding effects (a
 // padding slot adds v*x = +0.0, which leaves every finite sum unchanged).  Reference: spmv_hll (src/hll_matrix.c:376-408)
 // computes the per-block-range product; the scale / norm / exchange tail has no reference counterpart (BASELINE config 5).
-template <int BATCH>
+// FLAT: CTA b owns flat_chunks consecutive chunks and never waits (the two-launch form, see csr_row_fused_kernel).
+template <int BATCH, bool FLAT>
 __global__ void __launch_bounds__(256, 8)
 hll_row_fused_kernel(int num_hacks, const long long *__restrict__ hack_off, const int *__restrict__ JA,
                      const double *__restrict__ AS, const double *__restrict__ x, double *__restrict__ y, int M,
-                     const __grid_constant__ Epilogue ep) {
+                     const __grid_constant__ Epilogue ep, int flat_chunks) {
     __shared__ double warp_sq[8];
     __shared__ double mail_total;
     bool scaled;
@@ -138,7 +139,11 @@ hll_row_fused_kernel(int num_hacks, const long long *__restrict__ hack_off, cons
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double sq = 0.0;
     const int chunks = (M + 255) >> 8;
-    for (int q = blockIdx.x; q < chunks; q += gridDim.x) {  // boundary chunks first, exactly as csr_row_fused_kernel walks them
+    const int q_begin = FLAT ? (int)blockIdx.x * flat_chunks : (int)blockIdx.x;
+    const int q_end = FLAT ? min(chunks, q_begin + flat_chunks) : chunks;
+    const int q_step = FLAT ? 1 : (int)gridDim.x;
+    constexpr int kUnroll = FLAT ? 4 : 1;
+    for (int q = q_begin; q < q_end; q += q_step) {  // the walk of csr_row_fused_kernel, chunk for chunk
         const long long chunk_lo = (long long)ordered_chunk(ep.order, q) * 256;
         const bool boundary = ep.order.boundary_chunks > 0 ? q < ep.order.boundary_chunks : fused_chunk_is_boundary(ep, chunk_lo);
         const int hack = (int)(chunk_lo >> 5) + warp;
@@ -147,6 +152,7 @@ hll_row_fused_kernel(int num_hacks, const long long *__restrict__ hack_off, cons
         const int width = (int)((__ldg(hack_off + hack + 1) - off) >> 5);
         const long long base = off + lane;
         double acc = 0.0;
+#pragma unroll kUnroll
         for (int j = 0; j < width; j += BATCH) {
             int c[BATCH];
             double v[BATCH], xv[BATCH];
@@ -260,14 +266,43 @@ static int hll_launch_fused(const spmv_b200_hll *H, const double *d_x, double *d
                             int batch = -1) {
     if (batch < 0) batch = env_int("SPMV_B200_HLL_FUSED_BATCH", H->fused_batch > 0 ? H->fused_batch : H->row_batch);
     const int g = hll_fused_grid(H);
-#define HFUSED_CASE(B) case B: hll_row_fused_kernel<B><<<g, 256, 0, stream>>>(H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep); break;
+#define HFUSED_CASE(B) case B: hll_row_fused_kernel<B, false><<<g, 256, 0, stream>>>(H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep, 0); break;
     switch (batch) {
         HFUSED_CASE(2) HFUSED_CASE(3) HFUSED_CASE(5) HFUSED_CASE(6) HFUSED_CASE(7)
-        default: hll_row_fused_kernel<4><<<g, 256, 0, stream>>>(H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep); break;
+        default: hll_row_fused_kernel<4, false><<<g, 256, 0, stream>>>(H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep, 0); break;
     }
 #undef HFUSED_CASE
     SPMV_TRY_CUDA(cudaGetLastError());
     return SPMV_B200_OK;
+}
+
+// the FLAT form: C consecutive chunks per CTA, grid = ceil(chunks / C)
+static int hll_flat_grid(long long M, int chunks_per_cta) {
+    const long long chunks = (M + 255) / 256;
+    return (int)std::max<long long>(1, (chunks + chunks_per_cta - 1) / chunks_per_cta);
+}
+
+static int hll_launch_fused_flat(const spmv_b200_hll *H, const double *d_x, double *d_y, const Epilogue &ep, cudaStream_t stream,
+                                 int batch, int chunks_per_cta) {
+    const int g = hll_flat_grid(H->M, chunks_per_cta);
+#define HFLAT_CASE(B) case B: hll_row_fused_kernel<B, true><<<g, 256, 0, stream>>>(H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep, chunks_per_cta); break;
+    switch (batch) {
+        HFLAT_CASE(2) HFLAT_CASE(3) HFLAT_CASE(5) HFLAT_CASE(7)
+        default: hll_row_fused_kernel<4, true><<<g, 256, 0, stream>>>(H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep, chunks_per_cta); break;
+    }
+#undef HFLAT_CASE
+    SPMV_TRY_CUDA(cudaGetLastError());
+    return SPMV_B200_OK;
+}
+
+struct HllFlatChoice {
+    int batch, chunks;
+};
+static const HllFlatChoice kHllFlatCandidates[] = {{4, 1}, {4, 2}, {4, 4}, {3, 2}, {5, 2}, {7, 1}, {7, 2}, {2, 2}};
+
+static void hll_flat_choice(const spmv_b200_hll *H, int &batch, int &chunks) {
+    batch = env_int("SPMV_B200_HLL_FLAT_BATCH", H->flat_batch);
+    chunks = std::max(1, env_int("SPMV_B200_HLL_FLAT_CHUNKS", H->flat_chunks));
 }
 
 static int hll_launch_rows(const spmv_b200_hll *H, int hack_begin, int hack_end, const double *d_x, double *d_y,
@@ -335,6 +370,20 @@ static void hll_pick_row_batch(spmv_b200_hll *H, cudaStream_t stream) {
             H->fused_batch = tune_batch(H->M, H->N, H->row_batch, stream, [&](int batch, double *x, double *y) {
                 return hll_launch_fused(H, x, y, ep, stream, batch);
             });
+        }
+        cudaGetLastError();
+        cudaFree(partials);
+        partials = nullptr;
+        if (cudaMalloc(&partials, (size_t)hll_flat_grid(H->M, 1) * sizeof(double)) == cudaSuccess) {  // the FLAT form
+            Epilogue fe;
+            fe.partials = partials;
+            const int n = (int)(sizeof kHllFlatCandidates / sizeof kHllFlatCandidates[0]);
+            const int pick = tune_candidates(H->M, H->N, n, 1, stream, [&](int i, double *x, double *y) {
+                fe.partials_total = hll_flat_grid(H->M, kHllFlatCandidates[i].chunks);
+                return hll_launch_fused_flat(H, x, y, fe, stream, kHllFlatCandidates[i].batch, kHllFlatCandidates[i].chunks);
+            });
+            H->flat_batch = kHllFlatCandidates[pick].batch;
+            H->flat_chunks = kHllFlatCandidates[pick].chunks;
         }
         cudaGetLastError();
         cudaFree(partials);
@@ -495,6 +544,9 @@ int spmv_b200_hll_info(const spmv_b200_hll *H, spmv_b200_hll_info_t *info) {
     info->algorithmic_bytes = H->slots * 12 + 8LL * ((long long)H->num_hacks + 1) + 8LL * H->M + 8LL * H->N;
     info->auto_kernel = (int)hll_resolve(H);
     info->row_batch = H->row_batch;
+    info->fused_batch = H->fused_batch;
+    info->flat_batch = H->flat_batch;
+    info->flat_chunks = H->flat_chunks;
     return SPMV_B200_OK;
 }
 
@@ -608,6 +660,29 @@ int spmv_b200_hll_spmv_fused(const spmv_b200_hll *H, const double *d_x, double *
     if (peers) ep.peers = *peers;
     if (peers && env_int("SPMV_B200_FUSED_BOUNDARY_FIRST", 0)) SPMV_TRY(boundary_first_order(ep.peers, H->M, ep.order));
     return hll_launch_fused(H, d_x, d_y, ep, as_stream(stream));
+}
+
+int spmv_b200_hll_flat_partials_count(const spmv_b200_hll *H) {
+    if (!H) return 0;
+    int batch, chunks;
+    hll_flat_choice(H, batch, chunks);
+    return hll_flat_grid(H->M, chunks);
+}
+
+int spmv_b200_hll_spmv_fused_flat(const spmv_b200_hll *H, const double *d_x, double *d_y, const double *d_prev_sumsq,
+                                  double *d_partials, const spmv_b200_peers_t *peers, void *stream) {
+    if (!H || !d_y || (H->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_fused_flat: NULL argument");
+    if (peers && (peers->count < 0 || peers->count > SPMV_B200_MAX_PEERS))
+        return fail(SPMV_B200_ERR_INVALID, "hll_spmv_fused_flat: bad peer count %d", peers->count);
+    if (H->M == 0) return SPMV_B200_OK;
+    int batch, chunks;
+    hll_flat_choice(H, batch, chunks);
+    Epilogue ep;
+    ep.prev_sumsq = d_prev_sumsq;
+    ep.partials = d_partials;
+    ep.partials_total = hll_flat_grid(H->M, chunks);
+    if (peers) ep.peers = *peers;
+    return hll_launch_fused_flat(H, d_x, d_y, ep, as_stream(stream), batch, chunks);
 }
 
 int spmv_b200_hll_spmv_fused_mail(const spmv_b200_hll *H, const double *d_x, double *d_y, double *d_partials,

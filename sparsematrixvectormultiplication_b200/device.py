@@ -158,6 +158,17 @@ class DeviceCSR:
                                                  raw(partials) if partials is not None else None,
                                                  C.byref(peers) if peers is not None else None, _stream(stream)))
 
+    def flat_partials_count(self) -> int:
+        return N.lib().spmv_b200_csr_flat_partials_count(self._h)
+
+    def spmv_fused_flat(self, x_ptr, y_ptr, prev_sumsq=None, partials=None, peers=None, stream=None):
+        """The FLAT fused product of the two-launch iterated product (spmv_b200_csr_spmv_fused_flat)."""
+        def raw(v):
+            return C.c_void_p(v) if isinstance(v, int) else _ptr(v)
+        N.check(N.lib().spmv_b200_csr_spmv_fused_flat(self._h, raw(x_ptr), raw(y_ptr), raw(prev_sumsq) if prev_sumsq is not None else None,
+                                                      raw(partials) if partials is not None else None,
+                                                      C.byref(peers) if peers is not None else None, _stream(stream)))
+
     def spmv_fused_mail(self, x_ptr, y_ptr, partials, mail, peers=None, stream=None):
         """The fused launch with the |w|^2 exchange through peer mailboxes (spmv_b200_csr_spmv_fused_mail)."""
         def raw(v):
@@ -330,6 +341,16 @@ class DeviceHLL:
                                                       C.byref(peers) if peers is not None else None, C.byref(mail),
                                                       _stream(stream)))
 
+    def flat_partials_count(self) -> int:
+        return N.lib().spmv_b200_hll_flat_partials_count(self._h)
+
+    def spmv_fused_flat(self, x_ptr, y_ptr, prev_sumsq=None, partials=None, peers=None, stream=None):
+        def raw(v):
+            return C.c_void_p(v) if isinstance(v, int) else _ptr(v)
+        N.check(N.lib().spmv_b200_hll_spmv_fused_flat(self._h, raw(x_ptr), raw(y_ptr), raw(prev_sumsq) if prev_sumsq is not None else None,
+                                                      raw(partials) if partials is not None else None,
+                                                      C.byref(peers) if peers is not None else None, _stream(stream)))
+
     def spmv_hacks(self, hack_begin, hack_end, x, y, stream=None):
         N.check(N.lib().spmv_b200_hll_spmv_hacks(self._h, int(hack_begin), int(hack_end), _ptr(x), _ptr(y), _stream(stream)))
         return y
@@ -419,6 +440,12 @@ class PeerBuffer:
         if self.ptr:
             N.lib().spmv_b200_ipc_free(self.ptr)
             self.ptr = C.c_void_p()
+
+
+def mail_exchange(partials, count, mail, sumsq_out, stream=None):
+    """One CTA: fixed-order sum of the flat product's partials, publish into every rank's mailbox, wait for all ranks,
+    leave |w|^2 in sumsq_out (spmv_b200_mail_exchange)."""
+    N.check(N.lib().spmv_b200_mail_exchange(_ptr(partials), int(count), C.byref(mail), _ptr(sumsq_out), _stream(stream)))
 
 
 def vec_scale_by_inv_norm(dst, src, sumsq, n=None, stream=None):

@@ -198,8 +198,12 @@ class FusedPowerIteration(PowerIteration):
     collective library call in the loop (include/spmv_b200.h: spmv_b200_csr_spmv_fused_mail)."""
 
     def __init__(self, kind, p0, p1=0, p2=0, seed=0x5EED, group=None, parts=None, single=False, peer_stores=True,
-                 mailbox=False, fmt="csr", hack_aligned=None):
-        """fmt="hll": the same iteration on the column-major HLL image (hll_row_fused_kernel); the row ranges are then cut
+                 mailbox=False, fmt="csr", hack_aligned=None, split=False):
+        """split=True (implies mailbox): TWO launches per iteration -- the FLAT fused product, which never waits (grid as
+        large as the matrix, the block scheduler balances the SMs), and a one-CTA exchange kernel that adds the partials,
+        publishes |w|^2 + tag into every rank's mailbox and waits for all ranks (spmv_b200_*_spmv_fused_flat +
+        spmv_b200_mail_exchange).  Same mailboxes, same numerics as mailbox=True.
+        fmt="hll": the same iteration on the column-major HLL image (hll_row_fused_kernel); the row ranges are then cut
         on 32-row hack boundaries as the reference cuts HLL work.  hack_aligned=True with fmt="csr" gives the CSR iteration
         on exactly that partition (its results are bitwise those of the HLL iteration)."""
         if hack_aligned is None:
@@ -223,7 +227,8 @@ class FusedPowerIteration(PowerIteration):
             self.A = self.H           # same fused entry points (DeviceHLL.spmv_fused / spmv_fused_mail / partials_count)
         elif fmt != "csr":
             raise ValueError(f"unknown format {fmt!r}")
-        self.mailbox = bool(mailbox)
+        self.split = bool(split)
+        self.mailbox = bool(mailbox) or self.split
         self.peer_stores = (bool(peer_stores) or self.mailbox) and self.world > 1
         cu = self.x.device
         del self.x, self.y
@@ -247,7 +252,8 @@ class FusedPowerIteration(PowerIteration):
             self.buf = None
             self.xs = [torch.empty(self.N, dtype=torch.float64, device=cu) for _ in range(2)]
             self.peers = [None, None]
-        self.partials = torch.zeros(self.A.partials_count(), dtype=torch.float64, device=cu)
+        self.partials = torch.zeros(self.A.flat_partials_count() if self.split else self.A.partials_count(),
+                                    dtype=torch.float64, device=cu)
         self.sumsq = [torch.zeros(1, dtype=torch.float64, device=cu) for _ in range(2)]
         self.k = 0
         self.box = None
@@ -268,7 +274,7 @@ class FusedPowerIteration(PowerIteration):
             else:
                 self.mail.box[0] = self.box.ptr.value
         self.reset(1.0)
-        self.launches_per_step = 1 if self.mailbox else 2
+        self.launches_per_step = 2 if (self.split or not self.mailbox) else 1
         if self.world > 1:
             dist.barrier(group=self.group)
 
@@ -289,6 +295,14 @@ class FusedPowerIteration(PowerIteration):
     def step(self):
         cur, nxt = self.k & 1, (self.k & 1) ^ 1
         x, y = self.xs[cur], self.xs[nxt]
+        if self.split:
+            self.A.spmv_fused_flat(x.data_ptr(), y.data_ptr() + 8 * self.row_begin,
+                                   prev_sumsq=self.sumsq[0] if self.k > 0 else None, partials=self.partials,
+                                   peers=self.peers[nxt])
+            self.mail.iteration = self.k
+            self.dev.mail_exchange(self.partials, self.partials.numel(), self.mail, self.sumsq[0])
+            self.k += 1
+            return
         if self.mailbox:
             self.mail.iteration = self.k
             self.A.spmv_fused_mail(x.data_ptr(), y.data_ptr() + 8 * self.row_begin, self.partials, self.mail,
@@ -323,12 +337,19 @@ class FusedPowerIteration(PowerIteration):
         return total
 
     def eigenvalue_estimate(self) -> float:
+        if self.split:
+            torch.cuda.synchronize()
+            if int(self.sync[1].item()) != 0:
+                raise RuntimeError("a mailbox wait timed out: a peer rank did not finish its launch")
+            return float(self.sumsq[0].item()) ** 0.5
         if self.mailbox:
             return self._mail_total() ** 0.5
         return float(self.sumsq[self.k & 1].item()) ** 0.5
 
     def normalized_x(self) -> torch.Tensor:
         """v_k = w_k / |w_k| (valid on the owned rows and on the referenced halo)."""
+        if self.split:
+            return self.xs[self.k & 1] / (self.eigenvalue_estimate())
         if self.mailbox:
             return self.xs[self.k & 1] / (self._mail_total() ** 0.5)
         return self.xs[self.k & 1] / self.sumsq[self.k & 1].sqrt()

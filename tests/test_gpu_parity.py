@@ -602,6 +602,37 @@ def test_hll_fused_power_iteration_is_bitwise_the_csr_iteration(dev, port, mailb
     assert abs(float(pc.sum()) - float((y1 * y1).sum())) <= 1e-12 * float((y1 * y1).sum())
 
 
+@pytest.mark.parametrize("fmt", ["csr", "hll"])
+def test_two_launch_iterated_product_matches_the_oracle(dev, port, fmt):
+    """The two-launch form (FLAT fused product + one-CTA exchange kernel) against the oracle's power iteration and against
+    the one-launch mailbox form: x bitwise (same rows, same order), lambda within 1e-12 (the partials are grouped per CTA,
+    and the CTAs differ)."""
+    import torch
+    from sparsematrixvectormultiplication_b200 import synth
+    from sparsematrixvectormultiplication_b200.distributed import FusedPowerIteration
+    n, iters = 15, 25
+    rp, ci, va = synth.lap3d_csr(n)
+    x_ref, _, lam_ref = port.power_iteration(rp, ci, va, np.ones(n ** 3), iters)
+    S = FusedPowerIteration(synth.SYNTH_LAP3D, n, fmt=fmt, split=True)
+    F = FusedPowerIteration(synth.SYNTH_LAP3D, n, fmt=fmt, mailbox=True)
+    lam = []
+    for _ in range(iters):
+        S.step()
+        F.step()
+        lam.append(S.eigenvalue_estimate())
+    assert np.max(np.abs(np.array(lam) - lam_ref) / lam_ref) <= TOL
+    assert abs(S.eigenvalue_estimate() - F.eigenvalue_estimate()) <= TOL * lam_ref[-1]
+    vs = S.normalized_x().cpu().numpy()
+    assert np.max(np.abs(vs - x_ref)) <= TOL * np.max(np.abs(x_ref))
+    assert np.max(np.abs(vs - F.normalized_x().cpu().numpy())) <= TOL * np.max(np.abs(x_ref))
+    S.reset(1.0)                                          # and again after a reset
+    for _ in range(3):
+        S.step()
+    assert abs(S.eigenvalue_estimate() - lam_ref[2]) <= TOL * lam_ref[2]
+    info = S.A.info()
+    assert info.flat_chunks >= 1 and info.flat_batch >= 2
+
+
 def test_padded_allgather_layout_remap_and_interior_rows(dev, checker):
     """The one-collective allgather refresh keeps x in a padded rank-major layout and rewrites the column indices once
     (spmv_b200_csr_remap_columns); the product on the remapped matrix with the padded x gives the bits of the original

@@ -107,6 +107,28 @@ if "fusedgrid" in what:
         torch.cuda.empty_cache()
     os.environ.pop("SPMV_B200_FUSED_CTAS_PER_SM")
 
+if "flat" in what:
+    section("lap3d: fused row kernel, loop only: grid-stride vs C consecutive chunks per CTA")
+    for n in (512, 256):
+        A = device.DeviceCSR.synth(synth.SYNTH_LAP3D, n)
+        i = A.info()
+        x = torch.ones(i.N, dtype=torch.float64, device="cuda")
+        y = torch.empty(i.M, dtype=torch.float64, device="cuda")
+        for batch in (2, 5):
+            os.environ["SPMV_B200_ROW_BATCH"] = str(batch)
+            os.environ["SPMV_B200_FUSED_BATCH"] = str(batch)
+            A.replan()
+            line = f"n {n} batch {batch}: plain {timeit(lambda: A.spmv(x, y, algo=device.ALGO_ROW))*1e3:.1f} us | fused loop only:"
+            for flat in (0, 1, 2, 4, 8, 16, 64):
+                os.environ["SPMV_B200_FUSED_FLAT"] = str(flat)
+                line += f" C={flat or 'grid-stride'} {timeit(lambda: A.spmv_fused(x, y))*1e3:.1f}"
+            print(line, flush=True)
+        for k in ("SPMV_B200_ROW_BATCH", "SPMV_B200_FUSED_BATCH", "SPMV_B200_FUSED_FLAT"):
+            os.environ.pop(k, None)
+        A.close()
+        del x, y
+        torch.cuda.empty_cache()
+
 if "rmat" in what:
     section("R-MAT 24/16: binned kernel launch shapes")
     rp, ci, va = synth.rmat_csr_device(24, 16)
