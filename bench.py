@@ -665,15 +665,21 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler, head):
     # config 5 on ONE GPU: T1 of the multi-GPU scaling series
     try:
         from sparsematrixvectormultiplication_b200.distributed import FusedPowerIteration, PowerIteration
-        F = FusedPowerIteration(synth.SYNTH_LAP3D, 512, mailbox=True)
-        ms, per = time_device(F.step, steps, warm, sampler)
-        out["lap3d_512_power_1gpu"] = {"gflops": 2.0 * F.nnz_global / (ms * 1e-3) / 1e9, "ms_per_iteration": ms,
-                                       "nnz": F.nnz_global, "launches_per_step": F.launches_per_step,
-                                       "kernel": "fused: product + lazy normalisation + |w|^2 (mailbox) in one launch"}
-        F.close()
-        log(f"[bench] lap3d_512_power_1gpu (fused): {out['lap3d_512_power_1gpu']['gflops']:.1f} GFLOP/s ({ms:.3f} ms/iteration)")
-        del F
-        torch.cuda.empty_cache()
+        for key, kwargs, what in (
+                ("lap3d_512_power_1gpu", {"split": True}, "two launches: FLAT fused product (lazy normalisation, |w|^2 partials) + one-CTA exchange kernel"),
+                ("lap3d_512_power_1gpu_one_launch", {"mailbox": True}, "one launch: grid-stride fused product + lazy normalisation + |w|^2 (mailbox)"),
+                ("lap3d_512_power_1gpu_hll", {"split": True, "fmt": "hll"}, "HLL image, two launches"),
+                ("lap3d_512_power_1gpu_hll_one_launch", {"mailbox": True, "fmt": "hll"}, "HLL image, one launch")):
+            F = FusedPowerIteration(synth.SYNTH_LAP3D, 512, **kwargs)
+            ms, per = time_device(F.step, steps, warm, sampler)
+            fi = F.A.info()
+            out[key] = {"gflops": 2.0 * F.nnz_global / (ms * 1e-3) / 1e9, "ms_per_iteration": ms, "nnz": F.nnz_global,
+                        "launches_per_step": F.launches_per_step, "kernel": what,
+                        "plan": {"fused_batch": fi.fused_batch, "flat_batch": fi.flat_batch, "flat_chunks": fi.flat_chunks}}
+            F.close()
+            log(f"[bench] {key}: {out[key]['gflops']:.1f} GFLOP/s ({ms:.3f} ms/iteration)")
+            del F
+            torch.cuda.empty_cache()
         P = PowerIteration(synth.SYNTH_LAP3D, 512)
         ms, per = time_device(P.step, steps, warm, sampler)
         out["lap3d_512_power_1gpu_unfused"] = {"gflops": 2.0 * P.nnz_global / (ms * 1e-3) / 1e9, "ms_per_iteration": ms,
@@ -690,6 +696,7 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler, head):
     return out
 
 
+HEAD_MODE = "fused_split"   # the headline exchange of the N > 1 line (fastest measured: profiles/r02*_bench_n*.json)
 PARITY_ITERS = 12
 PARITY_TOL = 1e-12   # tools/dist_check.py: x and lambda of every exchange mode vs the single-GPU iteration
 
@@ -720,7 +727,7 @@ def bench_multi_gpu(args):
     lam_ref = torch.zeros(1, dtype=torch.float64, device=cu)
     if rank == 0 and not (args.no_t1 and args.no_parity):
         try:
-            F1 = FusedPowerIteration(synth.SYNTH_LAP3D, n, single=True, mailbox=True)
+            F1 = FusedPowerIteration(synth.SYNTH_LAP3D, n, single=True, split=True)   # the headline's kernels, whole matrix
             if not args.no_parity:
                 for _ in range(PARITY_ITERS):
                     F1.step()
@@ -767,7 +774,7 @@ def bench_multi_gpu(args):
     modes = ("fused_mailbox", "fused_split", "fused_split_hll", "fused_mailbox_hll", "fused_mailbox_csr_hack_aligned", "fused_async", "fused_peer_stores",
              "fused_nccl_halo", "halo", "allgather", "allgather_broadcasts")
     if args.modes:
-        modes = tuple(m for m in modes if m in args.modes.split(",") or m == "fused_mailbox")
+        modes = tuple(m for m in modes if m in args.modes.split(",") or m == HEAD_MODE)
     parity = {}
     for mode in modes:
         if mode == "fused_async":
@@ -801,7 +808,7 @@ def bench_multi_gpu(args):
                 log(f"[bench] {world} GPUs {mode}: parity after {PARITY_ITERS} iterations: x {parity[mode]['x_err']:.2e}, "
                     f"lambda {parity[mode]['lambda_err']:.2e} -> {'ok' if parity[mode]['ok'] else 'FAIL'}")
         P.reset(1.0)
-        head = mode == "fused_mailbox"
+        head = mode == HEAD_MODE
         steps = args.steps if head else max(3, min(args.steps, 20))
         ms, per = time_device(P.step, steps, args.warmup, sampler if head else None, world)
         lam = P.eigenvalue_estimate()
@@ -828,13 +835,14 @@ def bench_multi_gpu(args):
             log(f"[bench] {world} GPUs {mode}: {results[mode]['gflops']:.1f} GFLOP/s, {ms:.3f} ms/iteration, lambda={lam:.12g}")
         if head:  # kernel-only product time on this rank (roofline of the dominant kernel)
             xs, row_begin = P.xs, P.row_begin
-            kms, kper = time_device(lambda: P.A.spmv_fused(xs[0].data_ptr(), xs[1].data_ptr() + 8 * row_begin, partials=P.partials),
+            product = P.A.spmv_fused_flat if getattr(P, "split", False) else P.A.spmv_fused
+            kms, kper = time_device(lambda: product(xs[0].data_ptr(), xs[1].data_ptr() + 8 * row_begin, partials=P.partials),
                                     max(5, min(args.steps, 50)), 3, None, world)
             results["product_only_ms"] = kms
             results["fused_batch"] = int(os.environ.get("SPMV_B200_FUSED_BATCH", "0")) or None
             if getattr(P, "peers", None) and P.peers[1] is not None:   # the same launch with the NVLink peer stores of the boundary rows
-                pms, _ = time_device(lambda: P.A.spmv_fused(xs[0].data_ptr(), xs[1].data_ptr() + 8 * row_begin, partials=P.partials,
-                                                            peers=P.peers[1]), max(5, min(args.steps, 50)), 3, None, world)
+                pms, _ = time_device(lambda: product(xs[0].data_ptr(), xs[1].data_ptr() + 8 * row_begin, partials=P.partials,
+                                                     peers=P.peers[1]), max(5, min(args.steps, 50)), 3, None, world)
                 results["product_with_peer_stores_ms"] = pms
                 if rank == 0:
                     log(f"[bench] {world} GPUs local fused product alone {kms:.3f} ms, with peer stores {pms:.3f} ms")
@@ -897,17 +905,18 @@ def bench_multi_gpu(args):
         sampler.stop()
     parity_ok = all(v["ok"] for v in parity.values()) if parity else None
     if rank == 0:
-        h = results["fused_mailbox"]
+        h = results[HEAD_MODE]
         gbs = h["bytes_local"] / (results["product_only_ms"] * 1e-3) / 1e9
-        traffic, traffic_src = ncu_traffic(f"lap3d_{n}_power_rank_of_{world}", "csr_row_fused_kernel")
+        traffic, traffic_src = ncu_traffic(f"lap3d_{n}_power_rank_of_{world}", "csr_row_fused_kernel")  # same rows, same bytes as the FLAT form
         eff = (t1["ms_per_step"] / (world * h["ms_per_step"])) if t1 else None
         line = {"metric": "spmv_gflops", "value": h["gflops"], "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": h["ms_per_step"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world, n),
                 "implementation": {
+                    "mode": HEAD_MODE,
                     "partition": "contiguous rows balanced by nnz (reference greedy rule)",
-                    "exchange": "boundary rows AND |w|^2 stored into the peers' buffers / mailboxes over NVLink peer memory by the product kernel; no collective call in the loop",
-                    "step": "one power iteration = ONE launch: wait for the peers' tags, w=(A w_prev)/|w_prev|, |w|^2 partials, peer stores of boundary rows, last CTA publishes |w|^2 + tag"},
+                    "exchange": "boundary rows stored into the peers' buffers over NVLink peer memory by the product kernel, |w|^2 through peer mailboxes; no collective call in the loop",
+                    "step": "one power iteration = TWO launches: (1) FLAT fused product, grid as large as the matrix, never waits: w=(A w_prev)/|w_prev|, per-CTA |w|^2 partials, peer stores of boundary rows; (2) one-CTA exchange kernel: fixed-order sum of the partials, publish |w|^2 + tag into every rank's mailbox, wait for all ranks' tags (their boundary rows have landed), leave 1/|w| for the next launch"},
                 # T1 / (N * T_N) with T1 = the SAME workload and kernel on one GPU, measured in this run (the driver's own
                 # curve divides by the N=1 line of `bench.py --gpus 1`, which is another workload: lap2d single product)
                 "efficiency_same_workload": eff,

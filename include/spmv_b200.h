@@ -187,18 +187,19 @@ int spmv_b200_csr_spmv_fused_mail(const spmv_b200_csr *A, const double *d_x, dou
 
 /* The iterated product as TWO launches per iteration (round 2) -- the fastest form measured:
  *   spmv_b200_csr_spmv_fused_flat   the fused product on a grid as large as the matrix (C consecutive 256-row chunks per
- *       CTA, batch and C timed at plan time): y = (A x) / sqrt(*d_prev_sumsq) (NULL: no scaling), boundary rows mirrored
+ *       CTA, batch and C timed at plan time): y = (A x) * (*d_inv_norm) (NULL: no scaling), boundary rows mirrored
  *       into `peers`, one partial sum of y^2 per CTA in d_partials (spmv_b200_csr_flat_partials_count doubles).  It
  *       never waits for anything, so the block scheduler balances the SMs as it does for the plain product.  Rows of
  *       up to 12 nonzeros only (one thread per row, the reference's summation order).
  *   spmv_b200_mail_exchange         one CTA: adds the partials in a fixed order, publishes {sum, tag k+1} into slot
  *       [k&1][rank] of every rank's mailbox (mail->iteration = k; same mailbox layout and tag numbering as
  *       spmv_b200_csr_spmv_fused_mail), waits for the tags of all ranks in its own mailbox -- which also proves their
- *       boundary rows have landed -- and leaves |w_k|^2 (ranks added in rank order) in *d_sumsq_out for the next
- *       product launch.  mail->counter is not used.  Launches of one rank must be stream ordered.
+ *       boundary rows have landed -- and leaves {|w_k|^2, 1/|w_k|} (ranks added in rank order) in d_sumsq_out[0..1]; the
+ *       next product launch takes d_inv_norm = d_sumsq_out + 1 (the square root and the division are paid once, not once
+ *       per thread).  mail->counter is not used.  Launches of one rank must be stream ordered.
  * The HLL twins: spmv_b200_hll_spmv_fused_flat / spmv_b200_hll_flat_partials_count. */
 int spmv_b200_csr_flat_partials_count(const spmv_b200_csr *A);
-int spmv_b200_csr_spmv_fused_flat(const spmv_b200_csr *A, const double *d_x, double *d_y, const double *d_prev_sumsq,
+int spmv_b200_csr_spmv_fused_flat(const spmv_b200_csr *A, const double *d_x, double *d_y, const double *d_inv_norm,
                                   double *d_partials, const spmv_b200_peers_t *peers, void *stream);
 int spmv_b200_mail_exchange(const double *d_partials, int count, const spmv_b200_mail_t *mail, double *d_sumsq_out, void *stream);
 
@@ -292,7 +293,7 @@ int spmv_b200_hll_spmv_fused_mail(const spmv_b200_hll *H, const double *d_x, dou
                                   const spmv_b200_peers_t *peers, const spmv_b200_mail_t *mail, void *stream);
 /* the two-launch form (see spmv_b200_csr_spmv_fused_flat; the exchange kernel spmv_b200_mail_exchange is shared) */
 int spmv_b200_hll_flat_partials_count(const spmv_b200_hll *H);
-int spmv_b200_hll_spmv_fused_flat(const spmv_b200_hll *H, const double *d_x, double *d_y, const double *d_prev_sumsq,
+int spmv_b200_hll_spmv_fused_flat(const spmv_b200_hll *H, const double *d_x, double *d_y, const double *d_inv_norm,
                                   double *d_partials, const spmv_b200_peers_t *peers, void *stream);
 void spmv_b200_hll_free(spmv_b200_hll *H);
 

@@ -269,32 +269,68 @@ csr_row_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, cons
     y[row] = (V)acc;
 }
 
+// csr_row_kernel with the tail of the two-launch iterated product (spmv_b200_csr_spmv_fused_flat): one thread per row,
+// one CTA per 256 rows, NO chunk walk and no waiting -- the body of the plain kernel, then: multiply by 1/|w_prev| (read
+// from memory, computed once by the exchange kernel), store, mirror boundary rows into the peers, one partial sum of
+// squares per CTA.  (Round 2: the same epilogue on a chunk walk, grid-stride or C chunks per CTA, stayed 5-25 % behind the
+// plain kernel whatever the batch -- profiles/r02k_diag_flatpick.log; this form is the plain kernel plus ~15 instructions.)
+template <int BATCH>
+__global__ void __launch_bounds__(256, 8)
+csr_row_flat_kernel(int M, const int *__restrict__ row_ptr, const int *__restrict__ col_idx, const double *__restrict__ values,
+                    const double *__restrict__ x, double *__restrict__ y, const __grid_constant__ Epilogue ep) {
+    __shared__ double warp_sq[8];
+    const long long row = (long long)blockIdx.x * 256 + threadIdx.x;
+    const bool live = row < M;
+    double acc = 0.0;
+    if (live) {
+        const int lo = __ldg(row_ptr + row), hi = __ldg(row_ptr + row + 1);
+        for (int k = lo; k < hi; k += BATCH) {
+            int c[BATCH];
+            double v[BATCH], xv[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) c[u] = k + u < hi ? __ldg(col_idx + k + u) : -1;
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) v[u] = k + u < hi ? __ldg(values + k + u) : 0.0;
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u)
+                if (c[u] >= 0) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+        }
+        if (ep.inv_norm != nullptr) acc *= __ldg(ep.inv_norm);
+        y[row] = acc;
+        if (fused_chunk_is_boundary(ep, (long long)blockIdx.x * 256)) fused_peer_store(ep, row, acc);
+    }
+    if (ep.partials == nullptr) return;
+    double sq = acc * acc;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    if ((threadIdx.x & 31) == 0) warp_sq[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double total = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) total += warp_sq[w];
+        ep.partials[blockIdx.x] = total;
+    }
+}
+
 // The thread-per-row kernel with the fused tail of the iterated product (Epilogue, handles.cuh): every row is divided by
 // |w_prev|, squared into a per-thread sum, stored, and mirrored into the peers that reference it; per-CTA partial sums
 // in a fixed order; with a mailbox the launch first waits for the peers' previous launch and its last CTA publishes
 // |w|^2 (common.cuh).  A fixed grid walks the rows in 256-row chunks (grid-stride), so the number of partials -- and the
 // order of the sum of squares -- does not depend on the matrix size.
-//
-// FLAT (round 2, the two-launch form of the iterated product: spmv_b200_csr_spmv_fused_flat + spmv_b200_mail_exchange):
-// CTA b owns the flat_chunks consecutive chunks [b C, b C + C) and never waits for anything -- the exchange lives in a
-// one-CTA kernel of its own -- so the grid is as large as the matrix, the block scheduler balances the SMs, and the
-// per-row loop is unrolled as the compiler unrolls it in the plain row kernel.  Measured on lap3d 512^3, loop only
-// (profiles/r02h_diag_unroll.log): plain row kernel 2.07 ms, grid-stride 2.49, FLAT C=2 2.18.
-template <int BATCH, bool FLAT>
+template <int BATCH>
 __global__ void __launch_bounds__(256, 8)
 csr_row_fused_kernel(int M, const int *__restrict__ row_ptr, const int *__restrict__ col_idx, const double *__restrict__ values,
-                     const double *__restrict__ x, double *__restrict__ y, const __grid_constant__ Epilogue ep, int flat_chunks) {
+                     const double *__restrict__ x, double *__restrict__ y, const __grid_constant__ Epilogue ep) {
     __shared__ double warp_sq[8];
     __shared__ double mail_total;
     bool scaled;
     const double inv_norm = fused_inv_norm(ep, scaled, &mail_total);
     double sq = 0.0;
     const int chunks = (M + 255) >> 8;
-    const int q_begin = FLAT ? (int)blockIdx.x * flat_chunks : (int)blockIdx.x;
-    const int q_end = FLAT ? min(chunks, q_begin + flat_chunks) : chunks;
-    const int q_step = FLAT ? 1 : (int)gridDim.x;
-    constexpr int kUnroll = FLAT ? 4 : 1;
-    for (int q = q_begin; q < q_end; q += q_step) {
+    for (int q = blockIdx.x; q < chunks; q += gridDim.x) {
         // boundary chunks first (ChunkOrder); peer stores: a CTA-uniform test on the chunk (uniform datapath), the per-row
         // range test only inside -- done per row for every row it cost 30 us per peer per 56 M rows
         const long long chunk_lo = (long long)ordered_chunk(ep.order, q) * 256;
@@ -303,10 +339,6 @@ csr_row_fused_kernel(int M, const int *__restrict__ row_ptr, const int *__restri
         if (row >= M) continue;
         const int lo = __ldg(row_ptr + row), hi = __ldg(row_ptr + row + 1);
         double acc = 0.0;
-        // the plain row kernel gets this loop unrolled by the compiler (the loads of several batches in flight at once);
-        // inside the chunk walk that does not happen by itself.  Asked for in the FLAT form only: with the grid-stride
-        // walk it made batch 2 slower (2.49 -> 3.49 ms: the L1 footprint of the row streams is at the edge already)
-#pragma unroll kUnroll
         for (int k = lo; k < hi; k += BATCH) {
             int c[BATCH];
             double v[BATCH], xv[BATCH];
@@ -663,7 +695,7 @@ __global__ void interior_rows_kernel(int M, int mid, const int *__restrict__ row
 // product kernel, added in a fixed order (thread t adds elements t, t + 1024, ...; fixed tree); (2) {sum, tag k+1} into
 // slot [k&1][rank] of every rank's mailbox -- the product kernel has completed (stream order), a system-scope fence and
 // a release store order its peer stores before the tag; (3) wait for the tags of all ranks in the own mailbox, add
-// their sums in rank order, leave |w_k|^2 in *sumsq_out for the next product launch.
+// their sums in rank order, leave {|w_k|^2, 1/|w_k|} in sumsq_out[0..1] for the next product launch.
 __global__ void __launch_bounds__(1024)
 mail_exchange_kernel(const double *__restrict__ partials, int count, const __grid_constant__ spmv_b200_mail_t mail,
                      double *__restrict__ sumsq_out) {
@@ -680,7 +712,10 @@ mail_exchange_kernel(const double *__restrict__ partials, int count, const __gri
     const int lane = threadIdx.x;
     const double mine = part[0];
     if (mail.world == 1) {  // nobody to talk to
-        if (lane == 0) *sumsq_out = mine;
+        if (lane == 0) {
+            sumsq_out[0] = mine;
+            sumsq_out[1] = 1.0 / sqrt(mine);
+        }
         return;
     }
     __threadfence_system();
@@ -704,7 +739,10 @@ mail_exchange_kernel(const double *__restrict__ partials, int count, const __gri
     }
     double total = 0.0;
     for (int r = 0; r < mail.world; ++r) total += __shfl_sync(0xffffffffu, got, r);
-    if (lane == 0) *sumsq_out = total;
+    if (lane == 0) {
+        sumsq_out[0] = total;
+        sumsq_out[1] = 1.0 / sqrt(total);  // the next product launch multiplies by this: no square root or division per thread
+    }
 }
 
 __global__ void to_f32_kernel(const double *__restrict__ in, float *__restrict__ out, long long n) {
@@ -793,7 +831,7 @@ static int safe_vector_nnz(const spmv_b200_csr *A);
 struct FlatChoice {
     int batch, chunks;
 };
-static const FlatChoice kFlatCandidates[] = {{2, 1}, {2, 2}, {2, 4}, {4, 2}, {4, 4}, {5, 2}, {5, 4}, {3, 2}};
+static const FlatChoice kFlatCandidates[] = {{2, 1}, {3, 1}, {4, 1}, {5, 1}, {6, 1}, {7, 1}};
 static int flat_grid(long long M, int chunks_per_cta);
 static int launch_fused_flat(const spmv_b200_csr *A, const double *x, double *y, const Epilogue &ep, cudaStream_t stream,
                              int batch, int chunks_per_cta);
@@ -924,6 +962,7 @@ static int build_plan(spmv_b200_csr *A, cudaStream_t stream) {
             if (cudaMalloc(&flat_partials, (size_t)flat_grid(M, 1) * sizeof(double)) == cudaSuccess) {
                 Epilogue fe;
                 fe.partials = flat_partials;
+                fe.inv_norm = flat_partials;  // any finite double will do for the timing
                 const int n = (int)(sizeof kFlatCandidates / sizeof kFlatCandidates[0]);
                 const int best = tune_candidates(M, A->N, n, 1, stream, [&](int i, double *x, double *y) {
                     fe.partials_total = flat_grid(M, kFlatCandidates[i].chunks);
@@ -1206,29 +1245,29 @@ static int launch_fused(const spmv_b200_csr *A, const double *x, double *y, cons
     if (batch < 0) batch = env_int("SPMV_B200_FUSED_BATCH", A->fused_batch);
     if (batch == 0) return stream_launch_csr(A, x, y, 0, &ep, stream);
     const int g = fused_row_grid(A);
-#define FROW_CASE(B) case B: csr_row_fused_kernel<B, false><<<g, 256, 0, stream>>>(A->M, A->row_ptr, A->col_idx, A->values, x, y, ep, 0); break;
+#define FROW_CASE(B) case B: csr_row_fused_kernel<B><<<g, 256, 0, stream>>>(A->M, A->row_ptr, A->col_idx, A->values, x, y, ep); break;
     switch (batch) {
         FROW_CASE(2) FROW_CASE(3) FROW_CASE(5) FROW_CASE(6) FROW_CASE(7)
-        default: csr_row_fused_kernel<4, false><<<g, 256, 0, stream>>>(A->M, A->row_ptr, A->col_idx, A->values, x, y, ep, 0); break;
+        default: csr_row_fused_kernel<4><<<g, 256, 0, stream>>>(A->M, A->row_ptr, A->col_idx, A->values, x, y, ep); break;
     }
 #undef FROW_CASE
     SPMV_TRY_CUDA(cudaGetLastError());
     return SPMV_B200_OK;
 }
 
-// ---- the FLAT form: C consecutive chunks per CTA, grid = ceil(chunks / C); batch and C are timed at plan time ----
+// ---- the FLAT form (two-launch iterated product): one CTA per 256 rows; the batch is timed at plan time ----
 static int flat_grid(long long M, int chunks_per_cta) {
-    const long long chunks = (M + 255) / 256;
-    return (int)std::max<long long>(1, (chunks + chunks_per_cta - 1) / chunks_per_cta);
+    (void)chunks_per_cta;
+    return (int)std::max<long long>(1, (M + 255) / 256);
 }
 
 static int launch_fused_flat(const spmv_b200_csr *A, const double *x, double *y, const Epilogue &ep, cudaStream_t stream,
                              int batch, int chunks_per_cta) {
     const int g = flat_grid(A->M, chunks_per_cta);
-#define FLAT_CASE(B) case B: csr_row_fused_kernel<B, true><<<g, 256, 0, stream>>>(A->M, A->row_ptr, A->col_idx, A->values, x, y, ep, chunks_per_cta); break;
+#define FLAT_CASE(B) case B: csr_row_flat_kernel<B><<<g, 256, 0, stream>>>(A->M, A->row_ptr, A->col_idx, A->values, x, y, ep); break;
     switch (batch) {
-        FLAT_CASE(2) FLAT_CASE(3) FLAT_CASE(5)
-        default: csr_row_fused_kernel<4, true><<<g, 256, 0, stream>>>(A->M, A->row_ptr, A->col_idx, A->values, x, y, ep, chunks_per_cta); break;
+        FLAT_CASE(2) FLAT_CASE(3) FLAT_CASE(5) FLAT_CASE(6) FLAT_CASE(7)
+        default: csr_row_flat_kernel<4><<<g, 256, 0, stream>>>(A->M, A->row_ptr, A->col_idx, A->values, x, y, ep); break;
     }
 #undef FLAT_CASE
     SPMV_TRY_CUDA(cudaGetLastError());
@@ -1490,7 +1529,7 @@ int spmv_b200_csr_flat_partials_count(const spmv_b200_csr *A) {
     return flat_grid(A->M, chunks);
 }
 
-int spmv_b200_csr_spmv_fused_flat(const spmv_b200_csr *A, const double *d_x, double *d_y, const double *d_prev_sumsq,
+int spmv_b200_csr_spmv_fused_flat(const spmv_b200_csr *A, const double *d_x, double *d_y, const double *d_inv_norm,
                                   double *d_partials, const spmv_b200_peers_t *peers, void *stream) {
     if (!A || !d_y || (A->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "csr_spmv_fused_flat: NULL argument");
     if (A->max_row > kRowKernelMaxLen)
@@ -1501,7 +1540,7 @@ int spmv_b200_csr_spmv_fused_flat(const spmv_b200_csr *A, const double *d_x, dou
     int batch, chunks;
     flat_choice(A, batch, chunks);
     Epilogue ep;
-    ep.prev_sumsq = d_prev_sumsq;
+    ep.inv_norm = d_inv_norm;
     ep.partials = d_partials;
     ep.partials_total = flat_grid(A->M, chunks);
     if (peers) ep.peers = *peers;

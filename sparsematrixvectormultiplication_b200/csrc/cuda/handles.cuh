@@ -43,6 +43,8 @@ __device__ __forceinline__ int ordered_chunk(const ChunkOrder &o, int q) {  // q
 
 struct Epilogue {                 // optional fused tail of the CSR stream / row kernels and the HLL row kernel
     const double *prev_sumsq = nullptr;  // divide every row by sqrt(*prev_sumsq)
+    const double *inv_norm = nullptr;    // FLAT form: multiply every row by *inv_norm (1/|w_prev|, computed ONCE by the exchange
+                                         // kernel: a square root and a division per thread cost a flat CTA a quarter of its time)
     double *partials = nullptr;   // partials[blockIdx.x] = sum of the squares of the rows this CTA produced
     int partials_total = 0;       // size of the caller's buffer (spmv_b200_csr_partials_count): CTA 0 zeroes the entries
                                   // [gridDim.x, partials_total) so that a caller may always sum the whole buffer
@@ -68,6 +70,11 @@ __device__ __forceinline__ double fused_inv_norm(const Epilogue &ep, bool &scale
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     scaled = false;
     double prev_norm = 1.0;
+    if (ep.inv_norm != nullptr) {
+        scaled = true;
+        zero_partials_tail(ep);
+        return __ldg(ep.inv_norm);
+    }
     if (ep.mail.world > 0) {
         if (ep.mail.iteration > 0) {
             if (warp == 0) {

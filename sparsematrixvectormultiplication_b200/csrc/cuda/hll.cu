@@ -120,18 +120,70 @@ hll_row_kernel(int hack_begin, int hack_end, const long long *__restrict__ hack_
     if (row < M) y[row] = (V)acc;
 }
 
+// hll_row_kernel with the tail of the two-launch iterated product (spmv_b200_hll_spmv_fused_flat): one warp per hack, one
+// CTA per 8 hacks = 256 rows, no chunk walk and no waiting -- the body of the plain kernel, then scale by 1/|w_prev| (read
+// from memory), store, mirror boundary rows, one partial sum of squares per CTA (see csr_row_flat_kernel).  Thread t of
+// CTA b owns row 256 b + t as in the CSR kernel: same partials, bitwise the CSR iteration on the same partition.
+template <int BATCH>
+__global__ void __launch_bounds__(256, 8)
+hll_row_flat_kernel(int num_hacks, const long long *__restrict__ hack_off, const int *__restrict__ JA,
+                    const double *__restrict__ AS, const double *__restrict__ x, double *__restrict__ y, int M,
+                    const __grid_constant__ Epilogue ep) {
+    __shared__ double warp_sq[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int hack = blockIdx.x * 8 + warp;
+    const long long row = (long long)blockIdx.x * 256 + threadIdx.x;
+    double acc = 0.0;
+    if (hack < num_hacks) {  // warp-uniform
+        const long long off = __ldg(hack_off + hack);
+        const int width = (int)((__ldg(hack_off + hack + 1) - off) >> 5);
+        const long long base = off + lane;
+        for (int j = 0; j < width; j += BATCH) {
+            int c[BATCH];
+            double v[BATCH], xv[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) c[u] = j + u < width ? ldg_stream_s32(JA + base + (long long)(j + u) * kHack) : -1;
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) v[u] = j + u < width ? ldg_stream_f64(AS + base + (long long)(j + u) * kHack) : 0.0;
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u)
+                if (c[u] >= 0) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+        }
+        if (row < M) {
+            if (ep.inv_norm != nullptr) acc *= __ldg(ep.inv_norm);
+            y[row] = acc;
+            if (fused_chunk_is_boundary(ep, (long long)blockIdx.x * 256)) fused_peer_store(ep, row, acc);
+        } else {
+            acc = 0.0;  // padding rows of the last hack
+        }
+    }
+    if (ep.partials == nullptr) return;
+    double sq = acc * acc;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    if (lane == 0) warp_sq[warp] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double total = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) total += warp_sq[w];
+        ep.partials[blockIdx.x] = total;
+    }
+}
+
 // The lane-per-row kernel with the fused tail of the iterated product (Epilogue, handles.cuh): the HLL twin of
 // csr_row_fused_kernel.  A fixed grid walks the hacks in chunks of 8 (= 256 rows, one warp per hack, thread t of the CTA
 // owns row chunk*256 + t exactly as in the CSR kernel), so for the same row partition both formats produce the same
 // per-CTA partials: |w|^2, lambda and x are bitwise equal to the CSR iteration on rows without padding effects (a
 // padding slot adds v*x = +0.0, which leaves every finite sum unchanged).  Reference: spmv_hll (src/hll_matrix.c:376-408)
 // computes the per-block-range product; the scale / norm / exchange tail has no reference counterpart (BASELINE config 5).
-// FLAT: CTA b owns flat_chunks consecutive chunks and never waits (the two-launch form, see csr_row_fused_kernel).
-template <int BATCH, bool FLAT>
+template <int BATCH>
 __global__ void __launch_bounds__(256, 8)
 hll_row_fused_kernel(int num_hacks, const long long *__restrict__ hack_off, const int *__restrict__ JA,
                      const double *__restrict__ AS, const double *__restrict__ x, double *__restrict__ y, int M,
-                     const __grid_constant__ Epilogue ep, int flat_chunks) {
+                     const __grid_constant__ Epilogue ep) {
     __shared__ double warp_sq[8];
     __shared__ double mail_total;
     bool scaled;
@@ -139,11 +191,7 @@ hll_row_fused_kernel(int num_hacks, const long long *__restrict__ hack_off, cons
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double sq = 0.0;
     const int chunks = (M + 255) >> 8;
-    const int q_begin = FLAT ? (int)blockIdx.x * flat_chunks : (int)blockIdx.x;
-    const int q_end = FLAT ? min(chunks, q_begin + flat_chunks) : chunks;
-    const int q_step = FLAT ? 1 : (int)gridDim.x;
-    constexpr int kUnroll = FLAT ? 4 : 1;
-    for (int q = q_begin; q < q_end; q += q_step) {  // the walk of csr_row_fused_kernel, chunk for chunk
+    for (int q = blockIdx.x; q < chunks; q += gridDim.x) {  // the walk of csr_row_fused_kernel, chunk for chunk
         const long long chunk_lo = (long long)ordered_chunk(ep.order, q) * 256;
         const bool boundary = ep.order.boundary_chunks > 0 ? q < ep.order.boundary_chunks : fused_chunk_is_boundary(ep, chunk_lo);
         const int hack = (int)(chunk_lo >> 5) + warp;
@@ -152,7 +200,6 @@ hll_row_fused_kernel(int num_hacks, const long long *__restrict__ hack_off, cons
         const int width = (int)((__ldg(hack_off + hack + 1) - off) >> 5);
         const long long base = off + lane;
         double acc = 0.0;
-#pragma unroll kUnroll
         for (int j = 0; j < width; j += BATCH) {
             int c[BATCH];
             double v[BATCH], xv[BATCH];
@@ -266,29 +313,29 @@ static int hll_launch_fused(const spmv_b200_hll *H, const double *d_x, double *d
                             int batch = -1) {
     if (batch < 0) batch = env_int("SPMV_B200_HLL_FUSED_BATCH", H->fused_batch > 0 ? H->fused_batch : H->row_batch);
     const int g = hll_fused_grid(H);
-#define HFUSED_CASE(B) case B: hll_row_fused_kernel<B, false><<<g, 256, 0, stream>>>(H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep, 0); break;
+#define HFUSED_CASE(B) case B: hll_row_fused_kernel<B><<<g, 256, 0, stream>>>(H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep); break;
     switch (batch) {
         HFUSED_CASE(2) HFUSED_CASE(3) HFUSED_CASE(5) HFUSED_CASE(6) HFUSED_CASE(7)
-        default: hll_row_fused_kernel<4, false><<<g, 256, 0, stream>>>(H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep, 0); break;
+        default: hll_row_fused_kernel<4><<<g, 256, 0, stream>>>(H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep); break;
     }
 #undef HFUSED_CASE
     SPMV_TRY_CUDA(cudaGetLastError());
     return SPMV_B200_OK;
 }
 
-// the FLAT form: C consecutive chunks per CTA, grid = ceil(chunks / C)
+// the FLAT form (two-launch iterated product): one CTA per 8 hacks; the batch is timed at plan time
 static int hll_flat_grid(long long M, int chunks_per_cta) {
-    const long long chunks = (M + 255) / 256;
-    return (int)std::max<long long>(1, (chunks + chunks_per_cta - 1) / chunks_per_cta);
+    (void)chunks_per_cta;
+    return (int)std::max<long long>(1, (M + 255) / 256);
 }
 
 static int hll_launch_fused_flat(const spmv_b200_hll *H, const double *d_x, double *d_y, const Epilogue &ep, cudaStream_t stream,
                                  int batch, int chunks_per_cta) {
     const int g = hll_flat_grid(H->M, chunks_per_cta);
-#define HFLAT_CASE(B) case B: hll_row_fused_kernel<B, true><<<g, 256, 0, stream>>>(H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep, chunks_per_cta); break;
+#define HFLAT_CASE(B) case B: hll_row_flat_kernel<B><<<g, 256, 0, stream>>>(H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep); break;
     switch (batch) {
-        HFLAT_CASE(2) HFLAT_CASE(3) HFLAT_CASE(5) HFLAT_CASE(7)
-        default: hll_row_fused_kernel<4, true><<<g, 256, 0, stream>>>(H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep, chunks_per_cta); break;
+        HFLAT_CASE(2) HFLAT_CASE(3) HFLAT_CASE(5) HFLAT_CASE(6) HFLAT_CASE(7)
+        default: hll_row_flat_kernel<4><<<g, 256, 0, stream>>>(H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep); break;
     }
 #undef HFLAT_CASE
     SPMV_TRY_CUDA(cudaGetLastError());
@@ -298,7 +345,7 @@ static int hll_launch_fused_flat(const spmv_b200_hll *H, const double *d_x, doub
 struct HllFlatChoice {
     int batch, chunks;
 };
-static const HllFlatChoice kHllFlatCandidates[] = {{4, 1}, {4, 2}, {4, 4}, {3, 2}, {5, 2}, {7, 1}, {7, 2}, {2, 2}};
+static const HllFlatChoice kHllFlatCandidates[] = {{2, 1}, {3, 1}, {4, 1}, {5, 1}, {6, 1}, {7, 1}};
 
 static void hll_flat_choice(const spmv_b200_hll *H, int &batch, int &chunks) {
     batch = env_int("SPMV_B200_HLL_FLAT_BATCH", H->flat_batch);
@@ -377,6 +424,7 @@ static void hll_pick_row_batch(spmv_b200_hll *H, cudaStream_t stream) {
         if (cudaMalloc(&partials, (size_t)hll_flat_grid(H->M, 1) * sizeof(double)) == cudaSuccess) {  // the FLAT form
             Epilogue fe;
             fe.partials = partials;
+            fe.inv_norm = partials;  // any finite double will do for the timing
             const int n = (int)(sizeof kHllFlatCandidates / sizeof kHllFlatCandidates[0]);
             const int pick = tune_candidates(H->M, H->N, n, 1, stream, [&](int i, double *x, double *y) {
                 fe.partials_total = hll_flat_grid(H->M, kHllFlatCandidates[i].chunks);
@@ -669,7 +717,7 @@ int spmv_b200_hll_flat_partials_count(const spmv_b200_hll *H) {
     return hll_flat_grid(H->M, chunks);
 }
 
-int spmv_b200_hll_spmv_fused_flat(const spmv_b200_hll *H, const double *d_x, double *d_y, const double *d_prev_sumsq,
+int spmv_b200_hll_spmv_fused_flat(const spmv_b200_hll *H, const double *d_x, double *d_y, const double *d_inv_norm,
                                   double *d_partials, const spmv_b200_peers_t *peers, void *stream) {
     if (!H || !d_y || (H->N > 0 && !d_x)) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_fused_flat: NULL argument");
     if (peers && (peers->count < 0 || peers->count > SPMV_B200_MAX_PEERS))
@@ -678,7 +726,7 @@ int spmv_b200_hll_spmv_fused_flat(const spmv_b200_hll *H, const double *d_x, dou
     int batch, chunks;
     hll_flat_choice(H, batch, chunks);
     Epilogue ep;
-    ep.prev_sumsq = d_prev_sumsq;
+    ep.inv_norm = d_inv_norm;
     ep.partials = d_partials;
     ep.partials_total = hll_flat_grid(H->M, chunks);
     if (peers) ep.peers = *peers;

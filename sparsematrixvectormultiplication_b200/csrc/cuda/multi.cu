@@ -13,10 +13,11 @@
 // ALLGATHER), and the fused mailbox kernels (exchange mode MAILBOX) address the very same slots through peer pointers.
 //
 // Exchange modes of spmv_b200_multi_iterate:
-//   MAILBOX    one launch per GPU per iteration (csr_row_fused_kernel / fused stream kernel / hll_row_fused_kernel):
-//              product, lazy normalisation, |w|^2 partials, boundary rows stored straight into the neighbours' replicas,
-//              |w|^2 and an iteration tag published into every GPU's mailbox; no collective call.  Needs peer access
-//              and a matrix without rows above the long-row threshold.
+//   MAILBOX    product, lazy normalisation, |w|^2 partials, boundary rows stored straight into the neighbours' replicas,
+//              |w|^2 and an iteration tag published into every GPU's mailbox; no collective call.  Rows of up to 12
+//              nonzeros: two launches per GPU per iteration (flat product that never waits + one-CTA exchange kernel,
+//              the fastest form measured); longer rows: one launch (fused stream kernel).  Needs peer access and a
+//              matrix without rows above the long-row threshold.
 //   ALLGATHER  product (any kernel the plan picks, so skewed matrices work), |y|^2, a 1-double ncclAllReduce, scale of the
 //              own slice, one in-place ncclAllGather of x.  NCCL is loaded with dlopen at first use (libnccl.so.2); the
 //              library has no link-time dependency on it.
@@ -99,6 +100,9 @@ struct Part {
     spmv_b200_csr *A = nullptr;
     spmv_b200_hll *H = nullptr;
     bool fusable = true;
+    bool flat = false;                  // rows of up to 12 nonzeros: the two-launch form (flat product + exchange kernel)
+    double *scale = nullptr;            // {|w|^2, 1/|w|} written by the exchange kernel
+    int flat_partials = 0;
     double *x[2] = {nullptr, nullptr};  // padded replicas, double buffered
     double *y = nullptr;                // owned rows (ALLGATHER mode and the plain product)
     double *partials = nullptr, *ws = nullptr, *ss = nullptr;
@@ -124,6 +128,7 @@ struct spmv_b200_multi {
     int cur = 0;               // which replica holds the current iterate
     int mode = -1;             // exchange mode of the iterations since the last reset
     bool nccl_ready = false;
+    bool flat = false;         // every part has short rows: MAILBOX runs as two launches per iteration (fastest measured)
     double last_sumsq = 0.0;
 };
 
@@ -196,6 +201,7 @@ static int multi_finish(spmv_b200_multi *ctx) {
     const int n = ctx->n;
     long long rows_max = 0;
     for (const Part &p : ctx->parts) rows_max = std::max<long long>(rows_max, p.rows());
+
     ctx->stride = (rows_max + 31) / 32 * 32;
     if ((long long)n * ctx->stride > 0x7fffffffLL) return fail(SPMV_B200_ERR_INVALID, "multi: padded x exceeds int32 indexing");
     long long starts[SPMV_B200_MAX_RANKS + 1];
@@ -208,6 +214,7 @@ static int multi_finish(spmv_b200_multi *ctx) {
         SPMV_TRY(spmv_b200_csr_info(p.A, &info));
         p.nnz = info.nnz;
         p.fusable = info.num_long_rows == 0;
+        p.flat = info.max_row_nnz <= 12;
         int mm[2] = {0x7fffffff, -1}, *d_mm = nullptr;
         if (info.nnz > 0) {
             const int *cols = nullptr;
@@ -230,9 +237,11 @@ static int multi_finish(spmv_b200_multi *ctx) {
         const size_t xbytes = (size_t)std::max<long long>(n > 1 ? n * ctx->stride : ctx->N, 1) * sizeof(double);
         for (int b = 0; b < 2; ++b) SPMV_TRY_CUDA(cudaMalloc(&p.x[b], xbytes));
         SPMV_TRY_CUDA(cudaMalloc(&p.y, (size_t)std::max(p.rows(), 1) * sizeof(double)));
-        const int pc = std::max(p.A ? spmv_b200_csr_partials_count(p.A) : spmv_b200_hll_partials_count(p.H), 1);
+        p.flat_partials = p.flat ? (p.A ? spmv_b200_csr_flat_partials_count(p.A) : spmv_b200_hll_flat_partials_count(p.H)) : 0;
+        const int pc = std::max(std::max(p.A ? spmv_b200_csr_partials_count(p.A) : spmv_b200_hll_partials_count(p.H), p.flat_partials), 1);
         SPMV_TRY_CUDA(cudaMalloc(&p.partials, (size_t)pc * sizeof(double)));
         SPMV_TRY_CUDA(cudaMemset(p.partials, 0, (size_t)pc * sizeof(double)));
+        SPMV_TRY_CUDA(cudaMalloc(&p.scale, 2 * sizeof(double)));
         SPMV_TRY_CUDA(cudaMalloc(&p.ws, (size_t)spmv_b200_vec_ws_doubles() * sizeof(double)));
         SPMV_TRY_CUDA(cudaMalloc(&p.ss, sizeof(double)));
         SPMV_TRY_CUDA(cudaMalloc(&p.box, SPMV_B200_MAILBOX_BYTES));
@@ -241,6 +250,8 @@ static int multi_finish(spmv_b200_multi *ctx) {
         SPMV_TRY_CUDA(cudaEventCreate(&p.t0));
         SPMV_TRY_CUDA(cudaEventCreate(&p.t1));
     }
+    ctx->flat = true;
+    for (const Part &p : ctx->parts) ctx->flat = ctx->flat && p.flat;
     // who needs which of my rows (ExchangePlan of distributed.py): part j references columns [need_lo, need_hi)
     for (int i = 0; i < n; ++i) {
         Part &me = ctx->parts[i];
@@ -476,8 +487,16 @@ int spmv_b200_multi_iterate(spmv_b200_multi *ctx, int iters, int exchange, doubl
                 mail.counter = p.counter;
                 mail.status = reinterpret_cast<int *>(p.counter + 1);
                 double *y = own_slot(ctx, p, nxt, i);
-                if (p.A) SPMV_TRY(spmv_b200_csr_spmv_fused_mail(p.A, p.x[cur], y, p.partials, &p.peers[nxt], &mail, p.stream));
-                else SPMV_TRY(spmv_b200_hll_spmv_fused_mail(p.H, p.x[cur], y, p.partials, &p.peers[nxt], &mail, p.stream));
+                if (ctx->flat) {  // two launches: flat product (never waits) + one-CTA exchange kernel
+                    const double *inv = ctx->k > 0 ? p.scale + 1 : nullptr;
+                    if (p.A) SPMV_TRY(spmv_b200_csr_spmv_fused_flat(p.A, p.x[cur], y, inv, p.partials, &p.peers[nxt], p.stream));
+                    else SPMV_TRY(spmv_b200_hll_spmv_fused_flat(p.H, p.x[cur], y, inv, p.partials, &p.peers[nxt], p.stream));
+                    SPMV_TRY(spmv_b200_mail_exchange(p.partials, p.flat_partials, &mail, p.scale, p.stream));
+                } else if (p.A) {
+                    SPMV_TRY(spmv_b200_csr_spmv_fused_mail(p.A, p.x[cur], y, p.partials, &p.peers[nxt], &mail, p.stream));
+                } else {
+                    SPMV_TRY(spmv_b200_hll_spmv_fused_mail(p.H, p.x[cur], y, p.partials, &p.peers[nxt], &mail, p.stream));
+                }
             }
             ctx->cur = nxt;
         } else {
@@ -609,6 +628,7 @@ void spmv_b200_multi_free(spmv_b200_multi *ctx) {
         for (int b = 0; b < 2; ++b) cudaFree(p.x[b]);
         cudaFree(p.y);
         cudaFree(p.partials);
+        cudaFree(p.scale);
         cudaFree(p.ws);
         cudaFree(p.ss);
         cudaFree(p.box);

@@ -161,11 +161,11 @@ class DeviceCSR:
     def flat_partials_count(self) -> int:
         return N.lib().spmv_b200_csr_flat_partials_count(self._h)
 
-    def spmv_fused_flat(self, x_ptr, y_ptr, prev_sumsq=None, partials=None, peers=None, stream=None):
-        """The FLAT fused product of the two-launch iterated product (spmv_b200_csr_spmv_fused_flat)."""
+    def spmv_fused_flat(self, x_ptr, y_ptr, inv_norm=None, partials=None, peers=None, stream=None):
+        """The FLAT fused product of the two-launch iterated product (spmv_b200_csr_spmv_fused_flat): y = (A x) * (*inv_norm)."""
         def raw(v):
             return C.c_void_p(v) if isinstance(v, int) else _ptr(v)
-        N.check(N.lib().spmv_b200_csr_spmv_fused_flat(self._h, raw(x_ptr), raw(y_ptr), raw(prev_sumsq) if prev_sumsq is not None else None,
+        N.check(N.lib().spmv_b200_csr_spmv_fused_flat(self._h, raw(x_ptr), raw(y_ptr), raw(inv_norm) if inv_norm is not None else None,
                                                       raw(partials) if partials is not None else None,
                                                       C.byref(peers) if peers is not None else None, _stream(stream)))
 
@@ -344,10 +344,10 @@ class DeviceHLL:
     def flat_partials_count(self) -> int:
         return N.lib().spmv_b200_hll_flat_partials_count(self._h)
 
-    def spmv_fused_flat(self, x_ptr, y_ptr, prev_sumsq=None, partials=None, peers=None, stream=None):
+    def spmv_fused_flat(self, x_ptr, y_ptr, inv_norm=None, partials=None, peers=None, stream=None):
         def raw(v):
             return C.c_void_p(v) if isinstance(v, int) else _ptr(v)
-        N.check(N.lib().spmv_b200_hll_spmv_fused_flat(self._h, raw(x_ptr), raw(y_ptr), raw(prev_sumsq) if prev_sumsq is not None else None,
+        N.check(N.lib().spmv_b200_hll_spmv_fused_flat(self._h, raw(x_ptr), raw(y_ptr), raw(inv_norm) if inv_norm is not None else None,
                                                       raw(partials) if partials is not None else None,
                                                       C.byref(peers) if peers is not None else None, _stream(stream)))
 

@@ -255,6 +255,7 @@ class FusedPowerIteration(PowerIteration):
         self.partials = torch.zeros(self.A.flat_partials_count() if self.split else self.A.partials_count(),
                                     dtype=torch.float64, device=cu)
         self.sumsq = [torch.zeros(1, dtype=torch.float64, device=cu) for _ in range(2)]
+        self.scale = torch.ones(2, dtype=torch.float64, device=cu)   # split form: {|w|^2, 1/|w|} written by the exchange kernel
         self.k = 0
         self.box = None
         if self.mailbox:
@@ -297,10 +298,10 @@ class FusedPowerIteration(PowerIteration):
         x, y = self.xs[cur], self.xs[nxt]
         if self.split:
             self.A.spmv_fused_flat(x.data_ptr(), y.data_ptr() + 8 * self.row_begin,
-                                   prev_sumsq=self.sumsq[0] if self.k > 0 else None, partials=self.partials,
+                                   inv_norm=self.scale.data_ptr() + 8 if self.k > 0 else None, partials=self.partials,
                                    peers=self.peers[nxt])
             self.mail.iteration = self.k
-            self.dev.mail_exchange(self.partials, self.partials.numel(), self.mail, self.sumsq[0])
+            self.dev.mail_exchange(self.partials, self.partials.numel(), self.mail, self.scale)
             self.k += 1
             return
         if self.mailbox:
@@ -341,7 +342,7 @@ class FusedPowerIteration(PowerIteration):
             torch.cuda.synchronize()
             if int(self.sync[1].item()) != 0:
                 raise RuntimeError("a mailbox wait timed out: a peer rank did not finish its launch")
-            return float(self.sumsq[0].item()) ** 0.5
+            return float(self.scale[0].item()) ** 0.5
         if self.mailbox:
             return self._mail_total() ** 0.5
         return float(self.sumsq[self.k & 1].item()) ** 0.5

@@ -129,6 +129,36 @@ if "flat" in what:
         del x, y
         torch.cuda.empty_cache()
 
+if "flatpick" in what:
+    section("FLAT fused kernels: plan-time choice and every candidate, lap3d 512^3 and the 8-GPU rank size (512^3 / 8 rows)")
+    for n, rows in ((512, None), (512, 512 ** 3 // 8)):
+        A = device.DeviceCSR.synth(synth.SYNTH_LAP3D, n, row_begin=0, row_end=rows)
+        i = A.info()
+        H = A.to_hll()
+        hi = H.info()
+        print(f"rows {i.M}: CSR plan fused_batch {i.fused_batch} flat ({i.flat_batch}, {i.flat_chunks}); HLL plan row_batch {hi.row_batch} fused_batch {hi.fused_batch} flat ({hi.flat_batch}, {hi.flat_chunks})")
+        x = torch.ones(i.N, dtype=torch.float64, device="cuda")
+        y = torch.empty(i.M, dtype=torch.float64, device="cuda")
+        ss = torch.ones(1, dtype=torch.float64, device="cuda")
+        part = torch.zeros((i.M + 255) // 256, dtype=torch.float64, device="cuda")
+        print(f"  plain: CSR {timeit(lambda: A.spmv(x, y))*1e3:.1f} us, HLL {timeit(lambda: H.spmv(x, y))*1e3:.1f} us; "
+              f"grid-stride fused: CSR {timeit(lambda: A.spmv_fused(x, y, prev_sumsq=ss, partials=part))*1e3:.1f} us, HLL {timeit(lambda: H.spmv_fused(x, y, prev_sumsq=ss, partials=part))*1e3:.1f} us")
+        for batch in (2, 3, 4, 5, 6, 7):
+            line = f"  batch {batch}:"
+            for chunks in (1,):
+                os.environ["SPMV_B200_FLAT_BATCH"], os.environ["SPMV_B200_FLAT_CHUNKS"] = str(batch), str(chunks)
+                os.environ["SPMV_B200_HLL_FLAT_BATCH"], os.environ["SPMV_B200_HLL_FLAT_CHUNKS"] = str(batch), str(chunks)
+                a = timeit(lambda: A.spmv_fused_flat(x, y, inv_norm=ss, partials=part))
+                b = timeit(lambda: H.spmv_fused_flat(x, y, inv_norm=ss, partials=part))
+                line += f"  C={chunks}: CSR {a*1e3:.1f} HLL {b*1e3:.1f}"
+            print(line, flush=True)
+        for k in ("SPMV_B200_FLAT_BATCH", "SPMV_B200_FLAT_CHUNKS", "SPMV_B200_HLL_FLAT_BATCH", "SPMV_B200_HLL_FLAT_CHUNKS"):
+            os.environ.pop(k, None)
+        H.close()
+        A.close()
+        del x, y
+        torch.cuda.empty_cache()
+
 if "rmat" in what:
     section("R-MAT 24/16: binned kernel launch shapes")
     rp, ci, va = synth.rmat_csr_device(24, 16)
