@@ -543,7 +543,17 @@ int spmv_b200_multi_iterate(spmv_b200_multi *ctx, int iters, int exchange, doubl
     if (ms_per_iteration) *ms_per_iteration = (double)worst / iters;
     // |w_k|^2
     double total = 0.0;
-    if (exchange == SPMV_B200_EXCHANGE_MAILBOX) {
+    if (exchange == SPMV_B200_EXCHANGE_MAILBOX && ctx->flat) {  // the exchange kernel left {|w|^2, 1/|w|} on every GPU
+        for (Part &p : ctx->parts) {
+            unsigned int sync[2];
+            SPMV_TRY(multi_set(p));
+            SPMV_TRY_CUDA(cudaMemcpy(sync, p.counter, sizeof sync, cudaMemcpyDeviceToHost));
+            if (sync[1] != 0) return fail(SPMV_B200_ERR_CUDA, "multi_iterate: a mailbox wait on GPU %d timed out (a peer did not finish its launch)", p.dev);
+        }
+        Part &p0 = ctx->parts[0];
+        SPMV_TRY(multi_set(p0));
+        SPMV_TRY_CUDA(cudaMemcpy(&total, p0.scale, sizeof total, cudaMemcpyDeviceToHost));
+    } else if (exchange == SPMV_B200_EXCHANGE_MAILBOX) {
         Part &p0 = ctx->parts[0];
         SPMV_TRY(multi_set(p0));
         unsigned long long host_box[SPMV_B200_MAILBOX_BYTES / 8];
