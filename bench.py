@@ -839,7 +839,9 @@ def bench_multi_gpu(args):
             kms, kper = time_device(lambda: product(xs[0].data_ptr(), xs[1].data_ptr() + 8 * row_begin, partials=P.partials),
                                     max(5, min(args.steps, 50)), 3, None, world)
             results["product_only_ms"] = kms
-            results["fused_batch"] = int(os.environ.get("SPMV_B200_FUSED_BATCH", "0")) or None
+            pi = P.A.info()
+            results["product_kernel"] = (f"csr_row_flat_kernel<{pi.flat_batch}>" if getattr(P, "split", False)
+                                         else ("csr_stream_kernel (fused)" if pi.fused_batch == 0 else f"csr_row_fused_kernel<{pi.fused_batch}>"))
             if getattr(P, "peers", None) and P.peers[1] is not None:   # the same launch with the NVLink peer stores of the boundary rows
                 pms, _ = time_device(lambda: product(xs[0].data_ptr(), xs[1].data_ptr() + 8 * row_begin, partials=P.partials,
                                                      peers=P.peers[1]), max(5, min(args.steps, 50)), 3, None, world)
@@ -907,7 +909,7 @@ def bench_multi_gpu(args):
     if rank == 0:
         h = results[HEAD_MODE]
         gbs = h["bytes_local"] / (results["product_only_ms"] * 1e-3) / 1e9
-        traffic, traffic_src = ncu_traffic(f"lap3d_{n}_power_rank_of_{world}", "csr_row_fused_kernel")  # same rows, same bytes as the FLAT form
+        traffic, traffic_src = ncu_traffic(f"lap3d_{n}_power_rank_of_{world}", results.get("product_kernel", ""))
         eff = (t1["ms_per_step"] / (world * h["ms_per_step"])) if t1 else None
         line = {"metric": "spmv_gflops", "value": h["gflops"], "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": h["ms_per_step"], "higher_is_better": True, "scaling": "strong",
@@ -924,7 +926,7 @@ def bench_multi_gpu(args):
                            "reference": "single-GPU fused iteration on rank 0 (whole matrix), x on every rank's owned + referenced rows (max abs error / max |x|) and lambda (relative), max over ranks",
                            "modes": parity},
                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                             "traffic": traffic, "traffic_source": traffic_src,
+                             "traffic": traffic, "traffic_source": traffic_src, "kernel": results.get("product_kernel"),
                              "peak_source": peak_src, "note": "rank 0's local CSR product alone (max over ranks); algorithmic bytes of its row slice = 12 nnz_local + 4 (rows+1) + 8 rows + 8 x (referenced columns of x)",
                              "algorithmic_bytes_per_launch": int(h["bytes_local"])},
                 "cpu_baseline": None,
