@@ -158,25 +158,37 @@ struct HllTile {      // tiles[t] = first hack of tile t and its first slot; til
 // Times launch(i) for candidates i = 0 .. n-1 on scratch vectors and returns the fastest index (plan time, large matrices)
 template <class Launch>
 int tune_candidates(long long M, long long N, int n, int fallback, cudaStream_t stream, Launch launch) {
+    // ROUNDS passes over all candidates, REPS launches each, the MINIMUM per candidate decides: a transient slowdown of the
+    // GPU (power capping under sustained load shifts timings by 10 % for seconds) then cannot favour whichever candidate
+    // happened to run in a quiet moment -- round 2 saw a one-pass tuner pick a 25 % slower kernel at the end of bench.py.
+    constexpr int ROUNDS = 3, REPS = 3;
     double *x = nullptr, *y = nullptr;
     cudaEvent_t a = nullptr, b = nullptr;
     int best = fallback;
-    if (cudaMalloc(&x, (size_t)(N > 0 ? N : 1) * sizeof(double)) == cudaSuccess &&
+    if (n > 0 && cudaMalloc(&x, (size_t)(N > 0 ? N : 1) * sizeof(double)) == cudaSuccess &&
         cudaMalloc(&y, (size_t)(M > 0 ? M : 1) * sizeof(double)) == cudaSuccess &&
         cudaMemsetAsync(x, 0, (size_t)(N > 0 ? N : 1) * sizeof(double), stream) == cudaSuccess &&
         cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) {
-        float best_ms = -1.0f;
-        for (int i = 0; i < n; ++i) {
-            bool ok = launch(i, x, y) == SPMV_B200_OK;  // warm-up
-            ok = ok && cudaEventRecord(a, stream) == cudaSuccess;
-            for (int rep = 0; rep < 5 && ok; ++rep) ok = launch(i, x, y) == SPMV_B200_OK;
-            ok = ok && cudaEventRecord(b, stream) == cudaSuccess && cudaEventSynchronize(b) == cudaSuccess;
-            float ms = 0.0f;
-            if (!ok || cudaEventElapsedTime(&ms, a, b) != cudaSuccess) break;
-            if (best_ms < 0.0f || ms < best_ms) {
-                best_ms = ms;
-                best = i;
+        std::vector<float> fastest((size_t)n, -1.0f);
+        bool ok = true;
+        for (int round = 0; round < ROUNDS && ok; ++round) {
+            for (int i = 0; i < n && ok; ++i) {
+                if (round == 0) ok = launch(i, x, y) == SPMV_B200_OK;  // warm-up
+                ok = ok && cudaEventRecord(a, stream) == cudaSuccess;
+                for (int rep = 0; rep < REPS && ok; ++rep) ok = launch(i, x, y) == SPMV_B200_OK;
+                ok = ok && cudaEventRecord(b, stream) == cudaSuccess && cudaEventSynchronize(b) == cudaSuccess;
+                float ms = 0.0f;
+                ok = ok && cudaEventElapsedTime(&ms, a, b) == cudaSuccess;
+                if (ok && (fastest[i] < 0.0f || ms < fastest[i])) fastest[i] = ms;
             }
+        }
+        if (ok) {
+            float best_ms = -1.0f;
+            for (int i = 0; i < n; ++i)
+                if (fastest[i] >= 0.0f && (best_ms < 0.0f || fastest[i] < best_ms)) {
+                    best_ms = fastest[i];
+                    best = i;
+                }
         }
     }
     cudaGetLastError();
@@ -302,33 +314,13 @@ inline cudaError_t launch_x(void (*kernel)(Params...), unsigned int grid, unsign
 // matrices).  Candidates 2..7 are batches of the row kernels; 0 (first = 0 only, 1 is skipped) stands for the stream kernel.
 template <class Launch>
 int tune_batch(long long M, long long N, int fallback, cudaStream_t stream, Launch launch, int first = 2) {
-    double *x = nullptr, *y = nullptr;
-    cudaEvent_t a = nullptr, b = nullptr;
-    int best = fallback;
-    if (cudaMalloc(&x, (size_t)(N > 0 ? N : 1) * sizeof(double)) == cudaSuccess &&
-        cudaMalloc(&y, (size_t)(M > 0 ? M : 1) * sizeof(double)) == cudaSuccess &&
-        cudaMemsetAsync(x, 0, (size_t)(N > 0 ? N : 1) * sizeof(double), stream) == cudaSuccess &&
-        cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) {
-        float best_ms = -1.0f;
-        for (int batch = first; batch <= 7; ++batch) {
-            if (batch == 1) continue;
-            bool ok = launch(batch, x, y) == SPMV_B200_OK;  // warm-up
-            ok = ok && cudaEventRecord(a, stream) == cudaSuccess;
-            for (int rep = 0; rep < 5 && ok; ++rep) ok = launch(batch, x, y) == SPMV_B200_OK;
-            ok = ok && cudaEventRecord(b, stream) == cudaSuccess && cudaEventSynchronize(b) == cudaSuccess;
-            float ms = 0.0f;
-            if (!ok || cudaEventElapsedTime(&ms, a, b) != cudaSuccess) break;
-            if (best_ms < 0.0f || ms < best_ms) {
-                best_ms = ms;
-                best = batch;
-            }
-        }
-    }
-    cudaGetLastError();  // a failed scratch allocation is not an error of the plan: the fallback batch stands
-    if (a) cudaEventDestroy(a);
-    if (b) cudaEventDestroy(b);
-    cudaFree(x);
-    cudaFree(y);
-    return best;
+    int ids[8], n = 0;
+    for (int batch = first; batch <= 7; ++batch)
+        if (batch != 1) ids[n++] = batch;
+    int fallback_index = 0;
+    for (int i = 0; i < n; ++i)
+        if (ids[i] == fallback) fallback_index = i;
+    const int pick = tune_candidates(M, N, n, fallback_index, stream, [&](int i, double *x, double *y) { return launch(ids[i], x, y); });
+    return ids[pick] == fallback || pick != fallback_index ? ids[pick] : fallback;
 }
 }  // namespace spmv
