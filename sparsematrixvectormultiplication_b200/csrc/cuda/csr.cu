@@ -692,7 +692,7 @@ __global__ void interior_rows_kernel(int M, int mid, const int *__restrict__ row
 }
 
 // The exchange of the two-launch iterated product (spmv_b200_mail_exchange): ONE CTA.  (1) the partials of the flat
-// product kernel, added in a fixed order (thread t adds elements t, t + 1024, ...; fixed tree); (2) {sum, tag k+1} into
+// product kernel, added in a fixed order (thread t adds its contiguous block left to right; fixed tree); (2) {sum, tag k+1} into
 // slot [k&1][rank] of every rank's mailbox -- the product kernel has completed (stream order), a system-scope fence and
 // a release store order its peer stores before the tag; (3) wait for the tags of all ranks in the own mailbox, add
 // their sums in rank order, leave {|w_k|^2, 1/|w_k|} in sumsq_out[0..1] for the next product launch.
@@ -700,8 +700,34 @@ __global__ void __launch_bounds__(1024)
 mail_exchange_kernel(const double *__restrict__ partials, int count, const __grid_constant__ spmv_b200_mail_t mail,
                      double *__restrict__ sumsq_out) {
     __shared__ double part[1024];
+    // thread t adds ITS contiguous block of ceil(count / 1024) partials (rounded up to a multiple of 4) left to right; the
+    // loads of a block are independent 256-bit loads, all in flight at once (one by one the 64 L2 round trips of a
+    // 65 536-CTA launch cost 10 us, profiles/r02n_ncu_full_summary.md)
+    const int per = (((count + 1023) >> 10) + 3) & ~3;
+    const int lo = (int)threadIdx.x * per, hi = min(count, lo + per);
     double s = 0.0;
-    for (int i = threadIdx.x; i < count; i += 1024) s += __ldcg(partials + i);
+    if ((reinterpret_cast<uintptr_t>(partials) & 31) == 0) {
+        constexpr int kGroup = 8;  // 8 x 4 doubles per round
+        for (int base = lo; base < hi; base += 4 * kGroup) {
+            double v[kGroup][4];
+#pragma unroll
+            for (int g = 0; g < kGroup; ++g) {
+                const int at = base + 4 * g;
+                if (at + 4 <= hi) {
+                    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[g][0]), "=d"(v[g][1]), "=d"(v[g][2]), "=d"(v[g][3]) : "l"(partials + at));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[g][e] = at + e < hi ? __ldcg(partials + at + e) : 0.0;
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < kGroup; ++g)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) s += v[g][e];
+        }
+    } else {
+        for (int i = lo; i < hi; ++i) s += __ldcg(partials + i);
+    }
     part[threadIdx.x] = s;
     __syncthreads();
     for (int half = 512; half > 0; half >>= 1) {
