@@ -706,7 +706,8 @@ def bench_multi_gpu(args):
     import torch.distributed as dist
     from sparsematrixvectormultiplication_b200 import device, synth
     from sparsematrixvectormultiplication_b200.distributed import (AllgatherPowerIteration, AsyncPowerIteration,
-                                                                   FusedPowerIteration, PowerIteration)
+                                                                   FusedPowerIteration, PeerAllgatherPowerIteration,
+                                                                   PowerIteration)
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -772,7 +773,7 @@ def bench_multi_gpu(args):
         return {"x_err": x_err, "lambda_err": lam_err, "lambda": lam, "ok": ok}
 
     modes = ("fused_mailbox", "fused_split", "fused_split_hll", "fused_mailbox_hll", "fused_mailbox_csr_hack_aligned", "fused_async", "fused_peer_stores",
-             "fused_nccl_halo", "halo", "allgather", "allgather_broadcasts")
+             "fused_nccl_halo", "halo", "allgather_peer", "allgather_peer_copy_engine", "allgather", "allgather_broadcasts")
     if args.modes:
         modes = tuple(m for m in modes if m in args.modes.split(",") or m == HEAD_MODE)
     parity = {}
@@ -798,6 +799,10 @@ def bench_multi_gpu(args):
             P = FusedPowerIteration(synth.SYNTH_LAP3D, n, peer_stores=False)
         elif mode == "allgather":
             P = AllgatherPowerIteration(synth.SYNTH_LAP3D, n)
+        elif mode == "allgather_peer":
+            P = PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n, push_ctas=int(os.environ.get("SPMV_B200_PUSH_CTAS", "0")))
+        elif mode == "allgather_peer_copy_engine":
+            P = PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n, copy_engine=True)
         elif mode == "allgather_broadcasts":
             P = PowerIteration(synth.SYNTH_LAP3D, n, exchange="allgather")
         else:
@@ -812,7 +817,7 @@ def bench_multi_gpu(args):
         steps = args.steps if head else max(3, min(args.steps, 20))
         ms, per = time_device(P.step, steps, args.warmup, sampler if head else None, world)
         lam = P.eigenvalue_estimate()
-        if mode == "allgather":
+        if hasattr(P, "recv_bytes"):
             recv = P.recv_bytes // 8
         else:
             recv = P.plan.allgather_doubles_received() if mode.startswith("allgather") else P.plan.halo_doubles_received()
@@ -822,6 +827,22 @@ def bench_multi_gpu(args):
                          "bytes_local": P.algorithmic_bytes_local}
         if mode.startswith("allgather"):   # the whole-vector refresh is NVLink bound: say how fast the links ran
             results[mode]["nvlink_ingress_gbs_if_all_of_the_step"] = 8 * recv / (ms * 1e-3) / 1e9
+        if mode.startswith("allgather_peer"):
+            results[mode]["collective"] = (
+                "no library call: every rank stores its slice into all replicas over NVLink peer memory ("
+                + ("one cudaMemcpyAsync per peer, copy engines" if P.copy_engine else "spmv_b200_vec_push: one kernel, 256-bit loads, 128-bit peer stores")
+                + f"), then tags through peer mailboxes; interior rows [{P.interior[0]},{P.interior[1]}) of {P.rows} multiplied while it is in flight")
+            try:   # the push + tags alone, same buffers
+                def push_only():
+                    P.ev_own.record(torch.cuda.current_stream())
+                    P._push(0)
+                    torch.cuda.current_stream().wait_event(P.ev_landed)
+                    P.k += 1
+                ams, _ = time_device(push_only, 10, 3, None, world)
+                results[mode]["allgather_alone_ms"] = ams
+                results[mode]["allgather_alone_ingress_gbs"] = 8 * recv / (ams * 1e-3) / 1e9
+            except Exception as e:  # pragma: no cover
+                results[mode]["allgather_alone_error"] = repr(e)
         if mode == "allgather":
             results[mode]["collective"] = ("ONE in-place ncclAllGather (dist.all_gather_into_tensor) over a padded rank-major x, "
                                            f"stride {P.stride} doubles; interior rows [{P.interior[0]},{P.interior[1]}) of {P.rows} multiplied while it is in flight")

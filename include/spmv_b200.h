@@ -338,6 +338,13 @@ int spmv_b200_vec_sum(const double *d_in, int n, double *d_out, void *stream);
 int spmv_b200_vec_scale_by_inv_norm(double *d_dst, const double *d_src, long long n,
                                     const double *d_sumsq, void *stream);
 
+/* d_peer_dst[p][i] = d_src[i] for p < npeers, i < n: a slice of x pushed into the replicas of the other ranks with NVLink
+ * peer stores (the all-gather of the "allgather_peer" exchange written against peer memory; `ctas` = grid size, 0 = one
+ * CTA per SM).  256-bit loads / 128-bit peer stores when the source and every target share their offset within 32
+ * bytes (the same row range of equally aligned replicas), scalar otherwise.  d_peer_dst is a HOST array of device
+ * pointers.  No ordering is implied towards the peers: follow it with spmv_b200_mail_exchange (tag after fence). */
+int spmv_b200_vec_push(const double *d_src, long long n, int npeers, double *const *d_peer_dst, int ctas, void *stream);
+
 /* ---- peer memory for the fused exchange: device buffers that other ranks (processes) on the same NVLink
  * domain can map.  handle is an opaque 64-byte token (cudaIpcMemHandle_t) to ship to the peers. ---- */
 int spmv_b200_ipc_alloc(long long bytes, void **d_ptr, unsigned char handle[64]);

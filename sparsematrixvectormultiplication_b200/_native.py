@@ -171,6 +171,7 @@ SIGNATURES = {
     "spmv_b200_vec_ws_doubles": (_I, []),
     "spmv_b200_vec_sumsq": (_I, [_V, _LL, _V, _V, _V]),
     "spmv_b200_vec_scale_by_inv_norm": (_I, [_V, _V, _LL, _V, _V]),
+    "spmv_b200_vec_push": (_I, [_V, _LL, _I, C.POINTER(_V), _I, _V]),
     "spmv_b200_multi_init_synth": (_I, [_I, _I, _I, _LL, _LL, _I, _ULL, C.POINTER(_V)]),
     "spmv_b200_multi_init_csr": (_I, [_I, _I, _I, _I, _LL, _V, _V, _V, C.POINTER(_V)]),
     "spmv_b200_multi_info": (_I, [_V, C.POINTER(MultiInfo)]),

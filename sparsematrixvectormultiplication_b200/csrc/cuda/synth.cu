@@ -346,6 +346,72 @@ int spmv_b200_ipc_free(void *d_ptr) {
     return SPMV_B200_OK;
 }
 
+// dst_p[i] = src[i] for every peer p: the all-gather of a slice written against peer memory (NVLink stores).  A
+// persistent grid of one CTA per SM is all the links need; 256-bit loads, 128-bit peer stores.  The source and every
+// target sit at the SAME offset of equally aligned buffers (a row range of the replicas of x), so one scalar head of
+// up to three elements brings all of them onto a 32-byte boundary; targets aligned differently take the scalar path.
+struct PushTargets {
+    int count;
+    int vector_ok;
+    double *dst[SPMV_B200_MAX_PEERS];
+};
+
+__global__ void __launch_bounds__(512)
+vec_push_kernel(const double *__restrict__ src, long long n, const __grid_constant__ PushTargets t) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    if (!t.vector_ok) {
+        for (long long i = tid; i < n; i += stride) {
+            const double v = __ldg(src + i);
+            for (int p = 0; p < t.count; ++p) t.dst[p][i] = v;
+        }
+        return;
+    }
+    const long long head = min(n, (long long)(((32 - (reinterpret_cast<uintptr_t>(src) & 31)) & 31) >> 3));
+    const long long quads = (n - head) >> 2;
+    for (long long q = tid; q < quads; q += stride) {
+        const long long at = head + 4 * q;
+        double v[4];
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(src + at));
+        for (int p = 0; p < t.count; ++p) {
+            double2 *d = reinterpret_cast<double2 *>(t.dst[p] + at);
+            d[0] = make_double2(v[0], v[1]);
+            d[1] = make_double2(v[2], v[3]);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 8) {  // up to three elements at either end
+        const long long tail = head + 4 * quads;
+        const long long i = threadIdx.x < 4 ? threadIdx.x : tail + (threadIdx.x - 4);
+        const bool mine = threadIdx.x < 4 ? i < head : i < n;
+        if (mine) {
+            const double v = src[i];
+            for (int p = 0; p < t.count; ++p) t.dst[p][i] = v;
+        }
+    }
+}
+
+int spmv_b200_vec_push(const double *d_src, long long n, int npeers, double *const *d_peer_dst, int ctas, void *stream) {
+    if (n < 0 || npeers < 0 || npeers > SPMV_B200_MAX_PEERS || (npeers > 0 && !d_peer_dst) || (n > 0 && !d_src))
+        return fail(SPMV_B200_ERR_INVALID, "vec_push: bad arguments");
+    if (n == 0 || npeers == 0) return SPMV_B200_OK;
+    if (reinterpret_cast<uintptr_t>(d_src) & 7) return fail(SPMV_B200_ERR_INVALID, "vec_push: the source must be 8-byte aligned");
+    PushTargets t;
+    t.count = npeers;
+    t.vector_ok = 1;
+    for (int p = 0; p < npeers; ++p) {
+        if (!d_peer_dst[p] || (reinterpret_cast<uintptr_t>(d_peer_dst[p]) & 7))
+            return fail(SPMV_B200_ERR_INVALID, "vec_push: peer %d: NULL or not 8-byte aligned", p);
+        if ((reinterpret_cast<uintptr_t>(d_peer_dst[p]) & 31) != (reinterpret_cast<uintptr_t>(d_src) & 31)) t.vector_ok = 0;
+        t.dst[p] = d_peer_dst[p];
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = ctas > 0 ? ctas : sms;
+    vec_push_kernel<<<grid, 512, 0, as_stream(stream)>>>(d_src, n, t);
+    SPMV_TRY_CUDA(cudaGetLastError());
+    return SPMV_B200_OK;
+}
+
 int spmv_b200_vec_scale_by_inv_norm(double *d_dst, const double *d_src, long long n, const double *d_sumsq,
                                     void *stream) {
     if (n < 0 || (n > 0 && (!d_dst || !d_src)) || !d_sumsq)

@@ -442,6 +442,12 @@ class PeerBuffer:
             self.ptr = C.c_void_p()
 
 
+def vec_push(src, n, peer_ptrs, ctas=0, stream=None):
+    """peer_ptrs[p][i] = src[i]: a slice pushed into the other ranks' replicas with NVLink peer stores (spmv_b200_vec_push)."""
+    arr = (C.c_void_p * max(len(peer_ptrs), 1))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+    N.check(N.lib().spmv_b200_vec_push(_ptr(src), int(n), len(peer_ptrs), arr, int(ctas), _stream(stream)))
+
+
 def mail_exchange(partials, count, mail, sumsq_out, stream=None):
     """One CTA: fixed-order sum of the flat product's partials, publish into every rank's mailbox, wait for all ranks,
     leave |w|^2 in sumsq_out (spmv_b200_mail_exchange)."""

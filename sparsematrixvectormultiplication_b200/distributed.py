@@ -563,3 +563,169 @@ class AllgatherPowerIteration(PowerIteration):
         if self.world > 1:
             dist.all_gather_into_tensor(self.xg, self.own, group=self.group)
         return unpad(self.xg, self.parts, self.stride)
+
+
+class PeerAllgatherPowerIteration(PowerIteration):
+    """The whole-vector refresh of BASELINE config 5 written against peer memory instead of calling NCCL ("allgather_peer").
+
+    Every rank keeps two full replicas of x in peer-mappable buffers (x_k, x_{k+1}; original index space, no padding --
+    peer stores do not need equal slices).  The all-gather is ONE kernel per rank (spmv_b200_vec_push): 256-bit loads of
+    the own slice, 128-bit NVLink stores into the same rows of every other rank's replica, followed by the one-CTA
+    mailbox kernel (spmv_b200_mail_exchange on a mailbox of its own) whose tags prove that every rank's slice has landed
+    here.  It runs on a high-priority stream WHILE the interior rows -- a matrix handle of their own, columns inside the
+    rank's slice -- are multiplied; the boundary rows (two more handles) follow once the replica is complete.  Lazy
+    normalisation as in FusedPowerIteration(split=True): the product kernels are the FLAT fused ones (w = (A w_prev) /
+    |w_prev|, written straight into the own slice of the next replica, one |w|^2 partial per CTA), a second mailbox
+    exchange adds the partials of all ranks in rank order and leaves 1/|w| for the next launches.
+
+        step k:   [push stream]    own slice of x_k -> all replicas ; tags            (started at the end of step k-1)
+                  [compute stream] interior rows | wait for the tags | boundary rows | |w|^2 exchange -> start push k+1
+
+    No collective library call in the loop; 5 + 2 launches per iteration."""
+
+    def __init__(self, kind, p0, p1=0, p2=0, seed=0x5EED, group=None, parts=None, push_ctas=0, copy_engine=False):
+        super().__init__(kind, p0, p1, p2, seed=seed, exchange="allgather", group=group, parts=parts)
+        from . import _native as N
+        d = self.dev
+        cu = self.x.device
+        if self.A.info().num_long_rows:
+            raise ValueError("PeerAllgatherPowerIteration needs a matrix without long rows")
+        lo, hi = self.A.interior_rows(self.row_begin, self.row_end) if self.world > 1 else (0, self.rows)
+        self.interior = (lo, hi)
+        self.A.close()
+        self.A = None
+        del self.x, self.y
+        rb = self.row_begin
+        # (local first row, handle) of the interior block and the two boundary blocks; empty blocks are skipped
+        self.blocks = []
+        for b_lo, b_hi in ((lo, hi), (0, lo), (hi, self.rows)):
+            if b_hi > b_lo:
+                self.blocks.append((b_lo, d.DeviceCSR.synth(kind, p0, p1, p2, seed=seed, row_begin=rb + b_lo, row_end=rb + b_hi)))
+        self.has_interior = hi > lo
+        counts = [A.flat_partials_count() for _, A in self.blocks]
+        self.partials = torch.zeros(max(sum(counts), 1), dtype=torch.float64, device=cu)
+        self.partial_views, at = [], 0
+        for c in counts:
+            self.partial_views.append(self.partials[at: at + c])
+            at += c
+        self.n_partials = max(at, 1)
+        self.scale = torch.ones(2, dtype=torch.float64, device=cu)      # {|w|^2, 1/|w|} written by the norm exchange
+        self.one = torch.ones(4, dtype=torch.float64, device=cu)        # the push barrier's dummy partial
+        self.junk = torch.zeros(4, dtype=torch.float64, device=cu)
+        nbytes = 8 * self.N
+        self.buf = [d.PeerBuffer(nbytes), d.PeerBuffer(nbytes)]
+        self.xs = [b.as_tensor() for b in self.buf]
+        self.boxes = [d.PeerBuffer(N.MAILBOX_BYTES), d.PeerBuffer(N.MAILBOX_BYTES)]   # [0] |w|^2, [1] "my slice has landed"
+        self.box_t = [b.as_tensor("<i8", 8) for b in self.boxes]
+        self.sync = torch.zeros(4, dtype=torch.int32, device=cu)
+        self.mails = []
+        for i in range(2):
+            m = N.Mail()
+            m.world, m.rank = self.world, self.rank
+            m.counter = self.sync.data_ptr() + 8 * i
+            m.status = self.sync.data_ptr() + 8 * i + 4
+            self.mails.append(m)
+        self.push_targets = [[], []]          # per replica: the other ranks' slot for MY rows, nearest successor first
+        self.push_views = [[], []]
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, ([b.handle_bytes() for b in self.buf], [b.handle_bytes() for b in self.boxes]),
+                                   group=self.group)
+            for i in range(2):
+                for r in range(self.world):
+                    self.mails[i].box[r] = self.boxes[i].ptr.value if r == self.rank else self.boxes[i].open_peer(handles[r][1][i])
+            for parity in (0, 1):
+                for step in range(1, self.world):
+                    peer = (self.rank + step) % self.world
+                    base = self.buf[parity].open_peer(handles[peer][0][parity])
+                    self.push_targets[parity].append(base + 8 * rb)
+                    self.push_views[parity].append(torch.as_tensor(_CudaView(base + 8 * rb, max(self.rows, 1), "<f8"), device=cu))
+        else:
+            for i in range(2):
+                self.mails[i].box[0] = self.boxes[i].ptr.value
+        self.push_ctas = int(push_ctas)
+        self.copy_engine = bool(copy_engine)
+        self.push_stream = torch.cuda.Stream(device=cu, priority=-1)
+        self.ev_own = torch.cuda.Event()
+        self.ev_landed = torch.cuda.Event()
+        self.recv_bytes = 8 * (self.N - self.rows)
+        self.launches_per_step = len(self.blocks) + 1 + (2 if self.world > 1 else 0)
+        self.k = 0
+        self.reset(1.0)
+
+    def reset(self, value=1.0):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)   # nobody may still be pushing rows or tags of the previous run
+        for t in self.xs:
+            self.dev.vec_fill(t, value)      # every replica starts complete: step 0 waits for nothing
+        for t in self.box_t:
+            t.zero_()
+        self.sync.zero_()
+        self.k = 0
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def _push(self, nxt):
+        """Own slice of xs[nxt] -> every other replica, then the tags (push stream; the caller recorded ev_own)."""
+        ps = self.push_stream
+        ps.wait_event(self.ev_own)
+        own = self.xs[nxt][self.row_begin: self.row_end]
+        if self.copy_engine:     # comparison point: one cudaMemcpyAsync per peer (copy engines instead of SMs)
+            with torch.cuda.stream(ps):
+                for v in self.push_views[nxt]:
+                    v[: self.rows].copy_(own, non_blocking=True)
+        else:
+            self.dev.vec_push(own, self.rows, self.push_targets[nxt], ctas=self.push_ctas, stream=ps)
+        self.mails[1].iteration = self.k
+        self.dev.mail_exchange(self.one, 1, self.mails[1], self.junk, stream=ps)
+        self.ev_landed.record(ps)
+
+    def step(self):
+        cur, nxt = self.k & 1, (self.k & 1) ^ 1
+        x, y = self.xs[cur], self.xs[nxt]
+        cs = torch.cuda.current_stream()
+        inv = self.scale.data_ptr() + 8 if self.k > 0 else None
+        waited = self.k == 0 or self.world == 1
+        for i, (first, A) in enumerate(self.blocks):
+            if not waited and (i > 0 or not self.has_interior):
+                cs.wait_event(self.ev_landed)      # boundary rows read the other ranks' slices
+                waited = True
+            A.spmv_fused_flat(x.data_ptr(), y.data_ptr() + 8 * (self.row_begin + first), inv_norm=inv, partials=self.partial_views[i])
+        if not waited:
+            cs.wait_event(self.ev_landed)          # keeps the replicas two-deep even if no row needs the other slices
+        self.mails[0].iteration = self.k
+        self.dev.mail_exchange(self.partials, self.n_partials, self.mails[0], self.scale)
+        if self.world > 1:
+            self.ev_own.record(cs)
+            self._push(nxt)
+        self.k += 1
+
+    def _settle(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        if int(self.sync[1].item()) != 0 or int(self.sync[3].item()) != 0:
+            raise RuntimeError("a mailbox wait timed out: a peer rank did not finish its launch")
+
+    def eigenvalue_estimate(self) -> float:
+        self._settle()
+        return float(self.scale[0].item()) ** 0.5
+
+    def normalized_x(self) -> torch.Tensor:
+        """v_k = w_k / |w_k| on the WHOLE replica (the last step's push has landed: _settle synchronises all ranks)."""
+        lam = self.eigenvalue_estimate()
+        return self.xs[self.k & 1] / lam
+
+    def close(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        self.xs, self.box_t, self.push_views = [], [], [[], []]
+        for _, A in self.blocks:
+            A.close()
+        self.blocks = []
+        for b in self.buf + self.boxes:
+            b.close()
+        self.buf, self.boxes = [], []

@@ -14,7 +14,8 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 from sparsematrixvectormultiplication_b200 import synth  # noqa: E402
-from sparsematrixvectormultiplication_b200.distributed import AsyncPowerIteration, FusedPowerIteration, PowerIteration  # noqa: E402
+from sparsematrixvectormultiplication_b200.distributed import (AllgatherPowerIteration, AsyncPowerIteration, FusedPowerIteration,  # noqa: E402
+                                                               PeerAllgatherPowerIteration, PowerIteration)
 
 
 def main():
@@ -65,6 +66,45 @@ def main():
         print(f"rank {rank}/{world} fused peer_stores={peer_stores} mailbox={mailbox}: x err {err:.2e}, lambda err {lam_err:.2e} -> {'ok' if good else 'FAIL'}", flush=True)
         ok = ok and good
         F.close()
+    # round 2: the two-launch form (CSR and HLL), the one-collective NCCL all-gather and the all-gather written against
+    # peer memory (kernel push and copy-engine push); whole replica compared for the all-gather modes
+    makers = (("split", lambda: FusedPowerIteration(synth.SYNTH_LAP3D, n, split=True), False),
+              ("split hll", lambda: FusedPowerIteration(synth.SYNTH_LAP3D, n, split=True, fmt="hll"), False),
+              ("allgather (one ncclAllGather)", lambda: AllgatherPowerIteration(synth.SYNTH_LAP3D, n), True),
+              ("allgather_peer", lambda: PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n), True),
+              ("allgather_peer copy engine", lambda: PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n, copy_engine=True), True))
+    for name, make, whole in makers:
+        F = make()
+        lam = []
+        for _ in range(iters):
+            F.step()
+            lam.append(F.eigenvalue_estimate())
+        v = F.normalized_x()
+        lo = 0 if whole else min([F.row_begin] + [a for _, a, _ in F.plan.recvs])
+        hi = F.N if whole else max([F.row_end] + [b for _, _, b in F.plan.recvs])
+        err = float((v[lo:hi] - ref.x[lo:hi]).abs().max() / ref.x.abs().max())
+        lam_err = max(abs(a - b) / b for a, b in zip(lam, lam_ref))
+        good = err <= 1e-12 and lam_err <= 1e-12
+        print(f"rank {rank}/{world} {name}: rows [{F.row_begin},{F.row_end}), x err {err:.2e} on [{lo},{hi}), lambda err {lam_err:.2e} -> {'ok' if good else 'FAIL'}", flush=True)
+        ok = ok and good
+        if hasattr(F, "close"):
+            F.close()
+    # the peer all-gather free-running on a small matrix (short launches, no host synchronisation): a slice or a sum read
+    # before it landed, or a replica overwritten while a slow rank still reads it, would throw lambda off
+    small = 24
+    S = PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, small)
+    R = PowerIteration(synth.SYNTH_LAP3D, small, single=True)
+    for _ in range(600):
+        S.step()
+    for _ in range(600):
+        R.step()
+    good = abs(S.eigenvalue_estimate() - R.eigenvalue_estimate()) / R.eigenvalue_estimate() <= 1e-12
+    xerr = float((S.normalized_x() - R.x).abs().max() / R.x.abs().max())
+    good = good and xerr <= 1e-11
+    print(f"rank {rank}/{world} allgather_peer stress {small}^3 x 600 iterations: lambda {S.eigenvalue_estimate():.15g} vs {R.eigenvalue_estimate():.15g}, x err {xerr:.2e} -> {'ok' if good else 'FAIL'}", flush=True)
+    ok = ok and good
+    S.close()
+    del R
     # asynchronous form: boundary rows first, halo tags, scale factor lagging one launch; twice (reset in between)
     G = AsyncPowerIteration(synth.SYNTH_LAP3D, n)
     for attempt in range(2):
