@@ -773,7 +773,7 @@ def bench_multi_gpu(args):
         return {"x_err": x_err, "lambda_err": lam_err, "lambda": lam, "ok": ok}
 
     modes = ("fused_mailbox", "fused_split", "fused_split_hll", "fused_mailbox_hll", "fused_mailbox_csr_hack_aligned", "fused_async", "fused_peer_stores",
-             "fused_nccl_halo", "halo", "allgather_peer", "allgather_peer_copy_engine", "allgather", "allgather_broadcasts")
+             "fused_nccl_halo", "halo", "allgather_peer", "allgather_peer_kernel", "allgather", "allgather_broadcasts")
     if args.modes:
         modes = tuple(m for m in modes if m in args.modes.split(",") or m == HEAD_MODE)
     parity = {}
@@ -800,9 +800,9 @@ def bench_multi_gpu(args):
         elif mode == "allgather":
             P = AllgatherPowerIteration(synth.SYNTH_LAP3D, n)
         elif mode == "allgather_peer":
-            P = PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n, push_ctas=int(os.environ.get("SPMV_B200_PUSH_CTAS", "0")))
-        elif mode == "allgather_peer_copy_engine":
-            P = PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n, copy_engine=True)
+            P = PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n, copy_streams=int(os.environ.get("SPMV_B200_PUSH_STREAMS", "1")))
+        elif mode == "allgather_peer_kernel":
+            P = PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n, copy_engine=False, push_ctas=int(os.environ.get("SPMV_B200_PUSH_CTAS", "0")))
         elif mode == "allgather_broadcasts":
             P = PowerIteration(synth.SYNTH_LAP3D, n, exchange="allgather")
         else:
@@ -830,7 +830,7 @@ def bench_multi_gpu(args):
         if mode.startswith("allgather_peer"):
             results[mode]["collective"] = (
                 "no library call: every rank stores its slice into all replicas over NVLink peer memory ("
-                + ("one cudaMemcpyAsync per peer, copy engines" if P.copy_engine else "spmv_b200_vec_push: one kernel, 256-bit loads, 128-bit peer stores")
+                + (f"one cudaMemcpyAsync per peer on {len(P.copy_streams)} stream(s), copy engines" if P.copy_engine else "spmv_b200_vec_push: one kernel, 256-bit loads, 128-bit peer stores")
                 + f"), then tags through peer mailboxes; interior rows [{P.interior[0]},{P.interior[1]}) of {P.rows} multiplied while it is in flight")
             try:   # the push + tags alone, same buffers
                 def push_only():

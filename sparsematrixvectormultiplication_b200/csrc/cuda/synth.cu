@@ -368,14 +368,26 @@ vec_push_kernel(const double *__restrict__ src, long long n, const __grid_consta
     }
     const long long head = min(n, (long long)(((32 - (reinterpret_cast<uintptr_t>(src) & 31)) & 31) >> 3));
     const long long quads = (n - head) >> 2;
-    for (long long q = tid; q < quads; q += stride) {
-        const long long at = head + 4 * q;
-        double v[4];
-        asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(src + at));
+    constexpr int kUnroll = 4;  // 4 x 32 bytes loaded before the first store: 128 bytes per thread in flight towards HBM
+    for (long long q0 = tid; q0 < quads; q0 += kUnroll * stride) {
+        double v[kUnroll][4];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long q = q0 + u * stride;
+            if (q < quads)
+                asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                             : "=d"(v[u][0]), "=d"(v[u][1]), "=d"(v[u][2]), "=d"(v[u][3]) : "l"(src + head + 4 * q));
+        }
         for (int p = 0; p < t.count; ++p) {
-            double2 *d = reinterpret_cast<double2 *>(t.dst[p] + at);
-            d[0] = make_double2(v[0], v[1]);
-            d[1] = make_double2(v[2], v[3]);
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const long long q = q0 + u * stride;
+                if (q < quads) {
+                    double2 *d = reinterpret_cast<double2 *>(t.dst[p] + head + 4 * q);
+                    d[0] = make_double2(v[u][0], v[u][1]);
+                    d[1] = make_double2(v[u][2], v[u][3]);
+                }
+            }
         }
     }
     if (blockIdx.x == 0 && threadIdx.x < 8) {  // up to three elements at either end

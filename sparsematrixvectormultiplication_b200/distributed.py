@@ -583,7 +583,10 @@ class PeerAllgatherPowerIteration(PowerIteration):
 
     No collective library call in the loop; 5 + 2 launches per iteration."""
 
-    def __init__(self, kind, p0, p1=0, p2=0, seed=0x5EED, group=None, parts=None, push_ctas=0, copy_engine=False):
+    def __init__(self, kind, p0, p1=0, p2=0, seed=0x5EED, group=None, parts=None, push_ctas=0, copy_engine=True, copy_streams=1):
+        """copy_engine=True (default, the faster one measured): the slice travels as one cudaMemcpyAsync per peer -- the
+        DMA engines drive NVLink and every SM stays with the product; copy_streams > 1 spreads the peers over that many
+        streams.  copy_engine=False: spmv_b200_vec_push, the same transfer as ONE kernel of peer stores."""
         super().__init__(kind, p0, p1, p2, seed=seed, exchange="allgather", group=group, parts=parts)
         from . import _native as N
         d = self.dev
@@ -646,6 +649,9 @@ class PeerAllgatherPowerIteration(PowerIteration):
         self.push_ctas = int(push_ctas)
         self.copy_engine = bool(copy_engine)
         self.push_stream = torch.cuda.Stream(device=cu, priority=-1)
+        self.copy_streams = [self.push_stream] + [torch.cuda.Stream(device=cu, priority=-1)
+                                                  for _ in range(max(1, min(int(copy_streams), self.world - 1)) - 1)]
+        self.copy_events = [torch.cuda.Event() for _ in self.copy_streams]
         self.ev_own = torch.cuda.Event()
         self.ev_landed = torch.cuda.Event()
         self.recv_bytes = 8 * (self.N - self.rows)
@@ -672,10 +678,15 @@ class PeerAllgatherPowerIteration(PowerIteration):
         ps = self.push_stream
         ps.wait_event(self.ev_own)
         own = self.xs[nxt][self.row_begin: self.row_end]
-        if self.copy_engine:     # comparison point: one cudaMemcpyAsync per peer (copy engines instead of SMs)
-            with torch.cuda.stream(ps):
-                for v in self.push_views[nxt]:
+        if self.copy_engine:     # one cudaMemcpyAsync per peer, nearest successor first (every rank targets another one)
+            for st in self.copy_streams[1:]:
+                st.wait_event(self.ev_own)
+            for j, v in enumerate(self.push_views[nxt]):
+                with torch.cuda.stream(self.copy_streams[j % len(self.copy_streams)]):
                     v[: self.rows].copy_(own, non_blocking=True)
+            for st, ev in zip(self.copy_streams[1:], self.copy_events[1:]):
+                ev.record(st)
+                ps.wait_event(ev)
         else:
             self.dev.vec_push(own, self.rows, self.push_targets[nxt], ctas=self.push_ctas, stream=ps)
         self.mails[1].iteration = self.k

@@ -71,8 +71,9 @@ def main():
     makers = (("split", lambda: FusedPowerIteration(synth.SYNTH_LAP3D, n, split=True), False),
               ("split hll", lambda: FusedPowerIteration(synth.SYNTH_LAP3D, n, split=True, fmt="hll"), False),
               ("allgather (one ncclAllGather)", lambda: AllgatherPowerIteration(synth.SYNTH_LAP3D, n), True),
-              ("allgather_peer", lambda: PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n), True),
-              ("allgather_peer copy engine", lambda: PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n, copy_engine=True), True))
+              ("allgather_peer (copy engines)", lambda: PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n), True),
+              ("allgather_peer (copy engines, 3 streams)", lambda: PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n, copy_streams=3), True),
+              ("allgather_peer (push kernel)", lambda: PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n, copy_engine=False), True))
     for name, make, whole in makers:
         F = make()
         lam = []
@@ -92,18 +93,20 @@ def main():
     # the peer all-gather free-running on a small matrix (short launches, no host synchronisation): a slice or a sum read
     # before it landed, or a replica overwritten while a slow rank still reads it, would throw lambda off
     small = 24
-    S = PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, small)
     R = PowerIteration(synth.SYNTH_LAP3D, small, single=True)
     for _ in range(600):
-        S.step()
-    for _ in range(600):
         R.step()
-    good = abs(S.eigenvalue_estimate() - R.eigenvalue_estimate()) / R.eigenvalue_estimate() <= 1e-12
-    xerr = float((S.normalized_x() - R.x).abs().max() / R.x.abs().max())
-    good = good and xerr <= 1e-11
-    print(f"rank {rank}/{world} allgather_peer stress {small}^3 x 600 iterations: lambda {S.eigenvalue_estimate():.15g} vs {R.eigenvalue_estimate():.15g}, x err {xerr:.2e} -> {'ok' if good else 'FAIL'}", flush=True)
-    ok = ok and good
-    S.close()
+    for engine in (True, False):
+        S = PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, small, copy_engine=engine)
+        for _ in range(600):
+            S.step()
+        good = abs(S.eigenvalue_estimate() - R.eigenvalue_estimate()) / R.eigenvalue_estimate() <= 1e-12
+        xerr = float((S.normalized_x() - R.x).abs().max() / R.x.abs().max())
+        good = good and xerr <= 1e-11
+        print(f"rank {rank}/{world} allgather_peer ({'copy engines' if engine else 'push kernel'}) stress {small}^3 x 600 iterations: lambda {S.eigenvalue_estimate():.15g} "
+              f"vs {R.eigenvalue_estimate():.15g}, x err {xerr:.2e} -> {'ok' if good else 'FAIL'}", flush=True)
+        ok = ok and good
+        S.close()
     del R
     # asynchronous form: boundary rows first, halo tags, scale factor lagging one launch; twice (reset in between)
     G = AsyncPowerIteration(synth.SYNTH_LAP3D, n)
