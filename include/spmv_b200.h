@@ -364,6 +364,10 @@ int spmv_b200_ipc_free(void *d_ptr);
  *                                   peer stores and mailboxes (spmv_b200_csr_spmv_fused_mail / _hll_), no collective
  *     SPMV_B200_EXCHANGE_ALLGATHER  product, |y|^2, 1-double ncclAllReduce, scale, ONE in-place ncclAllGather of x
  *                                   (NCCL resolved with dlopen at first use; works for skewed matrices too)
+ *     SPMV_B200_EXCHANGE_ALLGATHER_PEER  the same iteration without NCCL: |y|^2 through the peer mailboxes
+ *                                   (spmv_b200_mail_exchange), then every GPU copies its slice into the replicas of all
+ *                                   the others over NVLink (one cudaMemcpyPeerAsync per peer: the copy engines drive
+ *                                   the links, 750 GB/s per direction measured against NCCL's 500-600); any matrix
  *   ms = device time per iteration, cudaEvents on every GPU's stream, maximum over the GPUs.  lambda = |A v_{k-1}| of
  *   the last iteration.  The iterate continues across calls; spmv_b200_multi_reset starts again from x0 (NULL: ones)
  *   and is required before switching the exchange mode. ---- */
@@ -371,6 +375,7 @@ int spmv_b200_ipc_free(void *d_ptr);
 #define SPMV_B200_FORMAT_HLL 1
 #define SPMV_B200_EXCHANGE_MAILBOX 0
 #define SPMV_B200_EXCHANGE_ALLGATHER 1
+#define SPMV_B200_EXCHANGE_ALLGATHER_PEER 2
 typedef struct spmv_b200_multi spmv_b200_multi;
 typedef struct {
     int ngpus, format;

@@ -37,6 +37,7 @@ constexpr long long kAutotuneMinNnz = 1 << 22;  // plan-time timing of the row-k
 constexpr int kRowBatch = 4;                // the same with ONE lane per row (bin 0 of the binned kernel)
 constexpr int kVec4Default = 1;              // vector / binned kernels: aligned groups of four nonzeros per lane (SPMV_B200_VEC4)
 constexpr int kFusedCtasPerSm = 8;          // grid of the fused row kernels per SM (SPMV_B200_FUSED_CTAS_PER_SM)
+constexpr int kMatrixPersistDefault = 0;    // head of row_ptr / JA held in the persisting carve-out across products (SPMV_B200_MATRIX_PERSIST)
 constexpr int kL2PersistDefault = 0;        // persisting-L2 window on x for the gather-bound kernels (SPMV_B200_L2_PERSIST)
 
 __device__ __forceinline__ void ldg_stream_f64x4(const float *p, double (&v)[4]) {  // fp32 storage: one 128-bit load
@@ -1028,10 +1029,11 @@ static int launch_rows(int row_begin, int row_end, const int *row_ptr, const int
     const long long rows = (long long)row_end - row_begin;
     if (rows <= 0) return SPMV_B200_OK;
     const unsigned int g = blocks_for(rows, 256);
-#define ROW_CASE(B) case B: csr_row_kernel<B, V><<<g, 256, 0, stream>>>(row_begin, row_end, row_ptr, col_idx, values, x, y, accumulate); break;
+    const XPolicy keep = matrix_policy(row_ptr + row_begin, (size_t)(rows + 1) * sizeof(int));
+#define ROW_CASE(B) case B: SPMV_TRY_CUDA(launch_x(csr_row_kernel<B, V>, g, 256, 0, stream, keep, row_begin, row_end, row_ptr, col_idx, values, x, y, accumulate)); break;
     switch (batch) {
         ROW_CASE(1) ROW_CASE(2) ROW_CASE(3) ROW_CASE(5) ROW_CASE(6) ROW_CASE(7) ROW_CASE(8)
-        default: csr_row_kernel<4, V><<<g, 256, 0, stream>>>(row_begin, row_end, row_ptr, col_idx, values, x, y, accumulate); break;
+        default: SPMV_TRY_CUDA(launch_x(csr_row_kernel<4, V>, g, 256, 0, stream, keep, row_begin, row_end, row_ptr, col_idx, values, x, y, accumulate)); break;
     }
 #undef ROW_CASE
     SPMV_TRY_CUDA(cudaGetLastError());
@@ -1290,10 +1292,11 @@ static int flat_grid(long long M, int chunks_per_cta) {
 static int launch_fused_flat(const spmv_b200_csr *A, const double *x, double *y, const Epilogue &ep, cudaStream_t stream,
                              int batch, int chunks_per_cta) {
     const int g = flat_grid(A->M, chunks_per_cta);
-#define FLAT_CASE(B) case B: csr_row_flat_kernel<B><<<g, 256, 0, stream>>>(A->M, A->row_ptr, A->col_idx, A->values, x, y, ep); break;
+    const XPolicy keep = matrix_policy(A->row_ptr, (size_t)(A->M + 1) * sizeof(int));
+#define FLAT_CASE(B) case B: SPMV_TRY_CUDA(launch_x(csr_row_flat_kernel<B>, g, 256, 0, stream, keep, A->M, A->row_ptr, A->col_idx, A->values, x, y, ep)); break;
     switch (batch) {
         FLAT_CASE(2) FLAT_CASE(3) FLAT_CASE(5) FLAT_CASE(6) FLAT_CASE(7)
-        default: csr_row_flat_kernel<4><<<g, 256, 0, stream>>>(A->M, A->row_ptr, A->col_idx, A->values, x, y, ep); break;
+        default: SPMV_TRY_CUDA(launch_x(csr_row_flat_kernel<4>, g, 256, 0, stream, keep, A->M, A->row_ptr, A->col_idx, A->values, x, y, ep)); break;
     }
 #undef FLAT_CASE
     SPMV_TRY_CUDA(cudaGetLastError());
@@ -1327,14 +1330,12 @@ int boundary_first_order(const spmv_b200_peers_t &peers, int M, ChunkOrder &orde
     return SPMV_B200_OK;
 }
 
-// Per-launch access-policy window over x (handles.cuh).  The device-wide persisting carve-out is raised once per device.
-XPolicy x_policy(const void *x, size_t bytes) {
-    XPolicy p;
-    if (!x || bytes == 0 || env_int("SPMV_B200_L2_PERSIST", kL2PersistDefault) == 0) return p;
+// Per-launch access-policy windows (handles.cuh).  The device-wide persisting carve-out is raised once per device.
+static bool persisting_limits(size_t &carve_out, size_t &max_window_out) {
     static int ready[64];
     static size_t carve[64], max_window[64];
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return p;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
     if (!ready[dev]) {
         int max_persist = 0, max_win = 0;
         cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
@@ -1350,9 +1351,18 @@ XPolicy x_policy(const void *x, size_t bytes) {
         ready[dev] = 1;
         cudaGetLastError();
     }
-    if (carve[dev] == 0 || max_window[dev] == 0) return p;
-    const size_t window = std::min(bytes, max_window[dev]);
-    float ratio = window <= carve[dev] ? 1.0f : (float)((double)carve[dev] / (double)window);
+    carve_out = carve[dev];
+    max_window_out = max_window[dev];
+    return carve[dev] > 0 && max_window[dev] > 0;
+}
+
+XPolicy x_policy(const void *x, size_t bytes) {
+    XPolicy p;
+    if (!x || bytes == 0 || env_int("SPMV_B200_L2_PERSIST", kL2PersistDefault) == 0) return p;
+    size_t carve = 0, max_window = 0;
+    if (!persisting_limits(carve, max_window)) return p;
+    const size_t window = std::min(bytes, max_window);
+    float ratio = window <= carve ? 1.0f : (float)((double)carve / (double)window);
     const int pct = env_int("SPMV_B200_L2_HIT_PCT", 0);
     if (pct > 0 && pct <= 100) ratio = std::min(ratio, pct / 100.0f);
     cudaAccessPolicyWindow w = {};
@@ -1361,6 +1371,29 @@ XPolicy x_policy(const void *x, size_t bytes) {
     w.hitRatio = ratio;
     w.hitProp = cudaAccessPropertyPersisting;
     w.missProp = env_int("SPMV_B200_L2_MISS_NORMAL", 0) ? cudaAccessPropertyNormal : cudaAccessPropertyStreaming;
+    p.attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    p.attr[0].val.accessPolicyWindow = w;
+    p.count = 1;
+    return p;
+}
+
+// The head of a matrix array (row_ptr of the thread-per-row CSR kernels; JA of the HLL row kernels) kept in the persisting
+// carve-out ACROSS products: an iterated product re-reads the whole matrix every launch, and whatever part of it the L2
+// holds on to is DRAM traffic saved on every launch after the first (64 MiB of 1.34 GB on lap2d 4096^2).  The window is
+// clamped to the carve-out (hitRatio 1: no thrashing among the persisting lines); everything outside it is untouched.
+XPolicy matrix_policy(const void *head, size_t bytes) {
+    XPolicy p;
+    if (!head || bytes == 0 || env_int("SPMV_B200_MATRIX_PERSIST", kMatrixPersistDefault) == 0) return p;
+    size_t carve = 0, max_window = 0;
+    if (!persisting_limits(carve, max_window)) return p;
+    const int pct = env_int("SPMV_B200_MATRIX_PERSIST_PCT", 100);
+    const size_t budget = (size_t)((double)carve * std::min(std::max(pct, 1), 100) / 100.0);
+    cudaAccessPolicyWindow w = {};
+    w.base_ptr = const_cast<void *>(head);
+    w.num_bytes = std::min(std::min(bytes, max_window), budget);
+    w.hitRatio = 1.0f;
+    w.hitProp = cudaAccessPropertyPersisting;
+    w.missProp = cudaAccessPropertyNormal;
     p.attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
     p.attr[0].val.accessPolicyWindow = w;
     p.count = 1;

@@ -297,6 +297,7 @@ struct XPolicy {
     unsigned int count = 0;
 };
 XPolicy x_policy(const void *x, size_t bytes);
+XPolicy matrix_policy(const void *head, size_t bytes);  // head of a matrix array held in L2 across products (csr.cu)
 
 template <typename... Params, typename... Args>
 inline cudaError_t launch_x(void (*kernel)(Params...), unsigned int grid, unsigned int block, size_t smem,

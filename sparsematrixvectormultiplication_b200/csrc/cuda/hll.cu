@@ -291,10 +291,11 @@ static int hll_launch_rows_t(const spmv_b200_hll *H, const V *AS, int hack_begin
     if (hack_end <= hack_begin) return SPMV_B200_OK;
     if (batch < 0) batch = sizeof(V) == 4 ? H->row_batch32 : H->row_batch;
     const unsigned int g = blocks_for(hack_end - hack_begin, 8);
-#define HROW_CASE(B) case B: hll_row_kernel<B, V><<<g, 256, 0, stream>>>(hack_begin, hack_end, H->hack_off, H->JA, AS, d_x, d_y, H->M); break;
+    const XPolicy keep = matrix_policy(H->JA, (size_t)H->slots * sizeof(int));   // head of JA held in L2 across products
+#define HROW_CASE(B) case B: SPMV_TRY_CUDA(launch_x(hll_row_kernel<B, V>, g, 256, 0, stream, keep, hack_begin, hack_end, H->hack_off, H->JA, AS, d_x, d_y, H->M)); break;
     switch (batch) {
         HROW_CASE(1) HROW_CASE(2) HROW_CASE(3) HROW_CASE(5) HROW_CASE(6) HROW_CASE(7) HROW_CASE(8)
-        default: hll_row_kernel<4, V><<<g, 256, 0, stream>>>(hack_begin, hack_end, H->hack_off, H->JA, AS, d_x, d_y, H->M); break;
+        default: SPMV_TRY_CUDA(launch_x(hll_row_kernel<4, V>, g, 256, 0, stream, keep, hack_begin, hack_end, H->hack_off, H->JA, AS, d_x, d_y, H->M)); break;
     }
 #undef HROW_CASE
     SPMV_TRY_CUDA(cudaGetLastError());
@@ -332,10 +333,11 @@ static int hll_flat_grid(long long M, int chunks_per_cta) {
 static int hll_launch_fused_flat(const spmv_b200_hll *H, const double *d_x, double *d_y, const Epilogue &ep, cudaStream_t stream,
                                  int batch, int chunks_per_cta) {
     const int g = hll_flat_grid(H->M, chunks_per_cta);
-#define HFLAT_CASE(B) case B: hll_row_flat_kernel<B><<<g, 256, 0, stream>>>(H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep); break;
+    const XPolicy keep = matrix_policy(H->JA, (size_t)H->slots * sizeof(int));
+#define HFLAT_CASE(B) case B: SPMV_TRY_CUDA(launch_x(hll_row_flat_kernel<B>, g, 256, 0, stream, keep, H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep)); break;
     switch (batch) {
         HFLAT_CASE(2) HFLAT_CASE(3) HFLAT_CASE(5) HFLAT_CASE(6) HFLAT_CASE(7)
-        default: hll_row_flat_kernel<4><<<g, 256, 0, stream>>>(H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep); break;
+        default: SPMV_TRY_CUDA(launch_x(hll_row_flat_kernel<4>, g, 256, 0, stream, keep, H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep)); break;
     }
 #undef HFLAT_CASE
     SPMV_TRY_CUDA(cudaGetLastError());

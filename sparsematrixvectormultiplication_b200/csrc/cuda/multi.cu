@@ -111,6 +111,7 @@ struct Part {
     spmv_b200_peers_t peers[2];
     cudaStream_t stream = nullptr;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    cudaEvent_t pushed = nullptr;       // ALLGATHER_PEER: my slice has been copied into every other replica
     ncclComm_t comm = nullptr;
     long long halo = 0;                 // doubles received from neighbours per iteration (MAILBOX mode)
     int rows() const { return (int)(row_end - row_begin); }
@@ -249,6 +250,7 @@ static int multi_finish(spmv_b200_multi *ctx) {
         SPMV_TRY_CUDA(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
         SPMV_TRY_CUDA(cudaEventCreate(&p.t0));
         SPMV_TRY_CUDA(cudaEventCreate(&p.t1));
+        SPMV_TRY_CUDA(cudaEventCreateWithFlags(&p.pushed, cudaEventDisableTiming));
     }
     ctx->flat = true;
     for (const Part &p : ctx->parts) ctx->flat = ctx->flat && p.flat;
@@ -454,7 +456,7 @@ int spmv_b200_multi_reset(spmv_b200_multi *ctx, const double *x0) {
 
 int spmv_b200_multi_iterate(spmv_b200_multi *ctx, int iters, int exchange, double *lambda, double *ms_per_iteration) {
     if (!ctx || iters < 1) return fail(SPMV_B200_ERR_INVALID, "multi_iterate: bad arguments");
-    if (exchange != SPMV_B200_EXCHANGE_MAILBOX && exchange != SPMV_B200_EXCHANGE_ALLGATHER)
+    if (exchange != SPMV_B200_EXCHANGE_MAILBOX && exchange != SPMV_B200_EXCHANGE_ALLGATHER && exchange != SPMV_B200_EXCHANGE_ALLGATHER_PEER)
         return fail(SPMV_B200_ERR_INVALID, "multi_iterate: unknown exchange mode %d", exchange);
     if (ctx->mode >= 0 && ctx->mode != exchange)
         return fail(SPMV_B200_ERR_INVALID, "multi_iterate: the exchange mode changed; call spmv_b200_multi_reset first (MAILBOX keeps "
@@ -464,7 +466,7 @@ int spmv_b200_multi_iterate(spmv_b200_multi *ctx, int iters, int exchange, doubl
     if (exchange == SPMV_B200_EXCHANGE_MAILBOX) {
         for (const Part &p : ctx->parts)
             if (!p.fusable) return fail(SPMV_B200_ERR_INVALID, "multi_iterate: rows above the long-row threshold on GPU %d; use SPMV_B200_EXCHANGE_ALLGATHER", p.dev);
-    } else if (n > 1) {
+    } else if (n > 1 && exchange == SPMV_B200_EXCHANGE_ALLGATHER) {
         SPMV_TRY(multi_nccl(ctx, &api));
     }
     ctx->mode = exchange;
@@ -499,6 +501,40 @@ int spmv_b200_multi_iterate(spmv_b200_multi *ctx, int iters, int exchange, doubl
                 }
             }
             ctx->cur = nxt;
+        } else if (exchange == SPMV_B200_EXCHANGE_ALLGATHER_PEER) {
+            // No library call: |y|^2 through the mailboxes (the exchange kernel also proves that EVERY GPU has finished
+            // reading x for this iteration, so the replicas may be overwritten), then one DMA copy of the own slice per
+            // peer, nearest successor first -- at any moment every GPU is the target of one other GPU.
+            for (int i = 0; i < n; ++i) {
+                Part &p = ctx->parts[i];
+                SPMV_TRY(multi_set(p));
+                if (p.A) SPMV_TRY(spmv_b200_csr_spmv(p.A, p.x[0], p.y, 0, SPMV_B200_ALGO_AUTO, p.stream));
+                else SPMV_TRY(spmv_b200_hll_spmv(p.H, p.x[0], p.y, p.stream));
+                SPMV_TRY(spmv_b200_vec_sumsq(p.y, p.rows(), p.ws, p.ss, p.stream));
+                spmv_b200_mail_t mail;
+                std::memset(&mail, 0, sizeof mail);
+                mail.world = n;
+                mail.rank = i;
+                mail.iteration = ctx->k;
+                for (int r = 0; r < n; ++r) mail.box[r] = ctx->parts[r].box;
+                mail.counter = p.counter;
+                mail.status = reinterpret_cast<int *>(p.counter + 1);
+                SPMV_TRY(spmv_b200_mail_exchange(p.ss, 1, &mail, p.scale, p.stream));  // scale[0] = |y|^2 over all GPUs, rank order
+                SPMV_TRY(spmv_b200_vec_scale_by_inv_norm(own_slot(ctx, p, 0, i), p.y, p.rows(), p.scale, p.stream));
+                for (int step = 1; step < n; ++step) {
+                    const int j = (i + step) % n;
+                    const Part &q = ctx->parts[j];
+                    SPMV_TRY_CUDA(cudaMemcpyPeerAsync(q.x[0] + (long long)i * ctx->stride, q.dev, own_slot(ctx, p, 0, i), p.dev,
+                                                      (size_t)p.rows() * sizeof(double), p.stream));
+                }
+                if (n > 1) SPMV_TRY_CUDA(cudaEventRecord(p.pushed, p.stream));
+            }
+            for (int j = 0; n > 1 && j < n; ++j) {  // the next product on GPU j starts when every slice has landed there
+                Part &q = ctx->parts[j];
+                SPMV_TRY(multi_set(q));
+                for (int i = 0; i < n; ++i)
+                    if (i != j) SPMV_TRY_CUDA(cudaStreamWaitEvent(q.stream, ctx->parts[i].pushed, 0));
+            }
         } else {
             for (int i = 0; i < n; ++i) {  // y = A x ; |y|^2
                 Part &p = ctx->parts[i];
@@ -543,7 +579,7 @@ int spmv_b200_multi_iterate(spmv_b200_multi *ctx, int iters, int exchange, doubl
     if (ms_per_iteration) *ms_per_iteration = (double)worst / iters;
     // |w_k|^2
     double total = 0.0;
-    if (exchange == SPMV_B200_EXCHANGE_MAILBOX && ctx->flat) {  // the exchange kernel left {|w|^2, 1/|w|} on every GPU
+    if ((exchange == SPMV_B200_EXCHANGE_MAILBOX && ctx->flat) || exchange == SPMV_B200_EXCHANGE_ALLGATHER_PEER) {  // the exchange kernel left {|w|^2, 1/|w|} on every GPU
         for (Part &p : ctx->parts) {
             unsigned int sync[2];
             SPMV_TRY(multi_set(p));
@@ -645,6 +681,7 @@ void spmv_b200_multi_free(spmv_b200_multi *ctx) {
         cudaFree(p.counter);
         if (p.t0) cudaEventDestroy(p.t0);
         if (p.t1) cudaEventDestroy(p.t1);
+        if (p.pushed) cudaEventDestroy(p.pushed);
         if (p.stream) cudaStreamDestroy(p.stream);
     }
     cudaGetLastError();

@@ -80,8 +80,8 @@ int main(int argc, char **argv) {
 
     const int formats[2] = {SPMV_B200_FORMAT_CSR, SPMV_B200_FORMAT_HLL};
     const char *fname[2] = {"csr", "hll"};
-    const int modes[2] = {SPMV_B200_EXCHANGE_MAILBOX, SPMV_B200_EXCHANGE_ALLGATHER};
-    const char *mname[2] = {"mailbox", "allgather"};
+    const int modes[3] = {SPMV_B200_EXCHANGE_MAILBOX, SPMV_B200_EXCHANGE_ALLGATHER, SPMV_B200_EXCHANGE_ALLGATHER_PEER};
+    const char *mname[3] = {"mailbox", "allgather", "allgather_peer"};
     for (int f = 0; f < 2; ++f) {
         spmv_b200_multi *ctx = NULL;
         CALL(spmv_b200_multi_init_synth(ngpus, formats[f], SPMV_B200_SYNTH_LAP3D, n, 0, 0, 0x5EED, &ctx));
@@ -93,7 +93,7 @@ int main(int argc, char **argv) {
             REQUIRE(info.row_begin[g] == info.row_end[g - 1], "partition has a gap at GPU %d", g);
             if (formats[f] == SPMV_B200_FORMAT_HLL) REQUIRE(info.row_begin[g] % 32 == 0, "HLL cut %lld is not on a hack boundary", info.row_begin[g]);
         }
-        for (int m = 0; m < 2; ++m) {
+        for (int m = 0; m < 3; ++m) {
             char label[64];
             double lam = 0.0;
             snprintf(label, sizeof label, "%s/%s", fname[f], mname[m]);

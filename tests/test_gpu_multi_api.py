@@ -1,6 +1,6 @@
 """The single-process multi-GPU C entry points (spmv_b200_multi_*) on GENERAL matrices handed over as host CSR arrays
 (the reference's CSRMatrix fields), bound with ctypes: the row-partitioned product against the serial oracle, and the power
-iteration in both exchange modes against the oracle's power iteration, for
+iteration in all three exchange modes (MAILBOX, NCCL ALLGATHER, ALLGATHER_PEER) against the oracle's power iteration, for
   * short rows (<= 12 nonzeros: the two-launch flat form),
   * medium rows (<= 40: one fused launch of the stream kernel),
   * a matrix with a 3000-nonzero row (MAILBOX is refused with a clear error, ALLGATHER works),
@@ -15,7 +15,7 @@ from sparsematrixvectormultiplication_b200 import _native as N
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
 CSR, HLL = 0, 1
-MAILBOX, ALLGATHER = 0, 1
+MAILBOX, ALLGATHER, ALLGATHER_PEER = 0, 1, 2
 
 
 def random_square(rng, M, max_len, long_row=0):
@@ -91,7 +91,7 @@ def test_multi_entry_points_on_general_matrices(checker, port, fmt, shape):
             assert sum(info.nnz_part[g] for g in range(info.ngpus)) == rp[-1]
             y = A.spmv(x)
             assert np.all(np.abs(y - y_ref) <= TOL * y_ref), (shape, fmt, ngpus)     # all terms positive
-            for mode in (MAILBOX, ALLGATHER):
+            for mode in (MAILBOX, ALLGATHER, ALLGATHER_PEER):
                 A.reset()
                 rc, lam = A.iterate(iters, mode)
                 if shape == "long" and mode == MAILBOX:
