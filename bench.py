@@ -830,7 +830,7 @@ def bench_multi_gpu(args):
         if mode.startswith("allgather_peer"):
             results[mode]["collective"] = (
                 "no library call: every rank stores its slice into all replicas over NVLink peer memory ("
-                + (f"one cudaMemcpyAsync per peer on {len(P.copy_streams)} stream(s), copy engines" if P.copy_engine else "spmv_b200_vec_push: one kernel, 256-bit loads, 128-bit peer stores")
+                + (f"one cudaMemcpyAsync per peer on {len(P.copy_streams)} stream(s), copy engines" if P.copy_engine else "spmv_b200_vec_push: one kernel, 256-bit loads and peer stores")
                 + f"), then tags through peer mailboxes; interior rows [{P.interior[0]},{P.interior[1]}) of {P.rows} multiplied while it is in flight")
             try:   # the push + tags alone, same buffers
                 def push_only():

@@ -347,7 +347,7 @@ int spmv_b200_ipc_free(void *d_ptr) {
 }
 
 // dst_p[i] = src[i] for every peer p: the all-gather of a slice written against peer memory (NVLink stores).  A
-// persistent grid of one CTA per SM is all the links need; 256-bit loads, 128-bit peer stores.  The source and every
+// persistent grid of one CTA per SM is all the links need; 256-bit loads, 256-bit peer stores.  The source and every
 // target sit at the SAME offset of equally aligned buffers (a row range of the replicas of x), so one scalar head of
 // up to three elements brings all of them onto a 32-byte boundary; targets aligned differently take the scalar path.
 struct PushTargets {
@@ -356,6 +356,7 @@ struct PushTargets {
     double *dst[SPMV_B200_MAX_PEERS];
 };
 
+template <int UNROLL>
 __global__ void __launch_bounds__(512)
 vec_push_kernel(const double *__restrict__ src, long long n, const __grid_constant__ PushTargets t) {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
@@ -368,11 +369,12 @@ vec_push_kernel(const double *__restrict__ src, long long n, const __grid_consta
     }
     const long long head = min(n, (long long)(((32 - (reinterpret_cast<uintptr_t>(src) & 31)) & 31) >> 3));
     const long long quads = (n - head) >> 2;
-    constexpr int kUnroll = 4;  // 4 x 32 bytes loaded before the first store: 128 bytes per thread in flight towards HBM
-    for (long long q0 = tid; q0 < quads; q0 += kUnroll * stride) {
-        double v[kUnroll][4];
+    // a lane moves whole 32-byte sectors (LDG.256 / STG.256): a warp instruction covers 1 KB of contiguous peer memory,
+    // never half a sector (two 128-bit stores per lane wrote every sector of the peer twice: 290-420 GB/s on 2 GPUs)
+    for (long long q0 = tid; q0 < quads; q0 += UNROLL * stride) {
+        double v[UNROLL][4];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
+        for (int u = 0; u < UNROLL; ++u) {
             const long long q = q0 + u * stride;
             if (q < quads)
                 asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
@@ -380,13 +382,11 @@ vec_push_kernel(const double *__restrict__ src, long long n, const __grid_consta
         }
         for (int p = 0; p < t.count; ++p) {
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
+            for (int u = 0; u < UNROLL; ++u) {
                 const long long q = q0 + u * stride;
-                if (q < quads) {
-                    double2 *d = reinterpret_cast<double2 *>(t.dst[p] + head + 4 * q);
-                    d[0] = make_double2(v[u][0], v[u][1]);
-                    d[1] = make_double2(v[u][2], v[u][3]);
-                }
+                if (q < quads)
+                    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(t.dst[p] + head + 4 * q), "d"(v[u][0]), "d"(v[u][1]),
+                                 "d"(v[u][2]), "d"(v[u][3]) : "memory");
             }
         }
     }
@@ -419,7 +419,11 @@ int spmv_b200_vec_push(const double *d_src, long long n, int npeers, double *con
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = ctas > 0 ? ctas : sms;
-    vec_push_kernel<<<grid, 512, 0, as_stream(stream)>>>(d_src, n, t);
+    switch (env_int("SPMV_B200_PUSH_UNROLL", 2)) {
+        case 1: vec_push_kernel<1><<<grid, 512, 0, as_stream(stream)>>>(d_src, n, t); break;
+        case 4: vec_push_kernel<4><<<grid, 512, 0, as_stream(stream)>>>(d_src, n, t); break;
+        default: vec_push_kernel<2><<<grid, 512, 0, as_stream(stream)>>>(d_src, n, t); break;
+    }
     SPMV_TRY_CUDA(cudaGetLastError());
     return SPMV_B200_OK;
 }

@@ -569,8 +569,9 @@ class PeerAllgatherPowerIteration(PowerIteration):
     """The whole-vector refresh of BASELINE config 5 written against peer memory instead of calling NCCL ("allgather_peer").
 
     Every rank keeps two full replicas of x in peer-mappable buffers (x_k, x_{k+1}; original index space, no padding --
-    peer stores do not need equal slices).  The all-gather is ONE kernel per rank (spmv_b200_vec_push): 256-bit loads of
-    the own slice, 128-bit NVLink stores into the same rows of every other rank's replica, followed by the one-CTA
+    peer stores do not need equal slices).  The all-gather is the own slice written into the same rows of every other
+    rank's replica -- one DMA copy per peer (copy engines; the default), or ONE kernel per rank (spmv_b200_vec_push:
+    256-bit loads, 256-bit NVLink stores) -- followed by the one-CTA
     mailbox kernel (spmv_b200_mail_exchange on a mailbox of its own) whose tags prove that every rank's slice has landed
     here.  It runs on a high-priority stream WHILE the interior rows -- a matrix handle of their own, columns inside the
     rank's slice -- are multiplied; the boundary rows (two more handles) follow once the replica is complete.  Lazy

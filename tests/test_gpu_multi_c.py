@@ -30,6 +30,6 @@ def test_c_entry_points_match_the_oracle(port):
     counts = sorted({1, min(2, torch.cuda.device_count()), min(4, torch.cuda.device_count()), torch.cuda.device_count()})
     for ngpus in counts:
         lams = _run(ngpus, n)
-        assert len(lams) == 6            # 1-GPU reference, csr/hll x mailbox/allgather, host CSR
+        assert len(lams) == 8            # 1-GPU reference, csr/hll x mailbox/allgather/allgather_peer, host CSR
         for lam in lams:
             assert abs(lam - lam_ref[-1]) <= 1e-12 * lam_ref[-1], (ngpus, lam, lam_ref[-1])
