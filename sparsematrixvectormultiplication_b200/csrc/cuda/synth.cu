@@ -9,6 +9,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "handles.cuh"
 
 // csr.cu
 extern "C" int spmv_b200_csr_adopt_device_(int M, int N, long long nnz, int *d_row_ptr, int *d_col_idx,
@@ -175,6 +176,83 @@ __global__ void scale_by_inv_norm_kernel(double *__restrict__ dst, const double 
     const double norm = sqrt(*sumsq);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[i] / norm;
+}
+
+// dst_p[i] = src[i] for every peer p: the all-gather of a slice written against peer memory (NVLink stores).  A
+// persistent grid of one CTA per SM is all the links need; 256-bit loads, 256-bit peer stores.  The source and every
+// target sit at the SAME offset of equally aligned buffers (a row range of the replicas of x), so one scalar head of
+// up to three elements brings all of them onto a 32-byte boundary; targets aligned differently take the scalar path.
+struct PushTargets {
+    int count;
+    int vector_ok;
+    double *dst[SPMV_B200_MAX_PEERS];
+};
+
+template <int UNROLL, int WIDTH>
+__global__ void __launch_bounds__(512)
+vec_push_kernel(const double *__restrict__ src, long long n, const __grid_constant__ PushTargets t) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    if (!t.vector_ok) {
+        for (long long i = tid; i < n; i += stride) {
+            const double v = __ldg(src + i);
+            for (int p = 0; p < t.count; ++p) t.dst[p][i] = v;
+        }
+        return;
+    }
+    const long long head = min(n, (long long)(((32 - (reinterpret_cast<uintptr_t>(src) & 31)) & 31) >> 3));
+    const long long quads = (n - head) >> 2;
+    if constexpr (WIDTH == 32) {
+        // a lane moves whole 32-byte sectors (LDG.256 / STG.256): a warp instruction covers 1 KB of contiguous peer memory
+        for (long long q0 = tid; q0 < quads; q0 += UNROLL * stride) {
+            double v[UNROLL][4];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const long long q = q0 + u * stride;
+                if (q < quads)
+                    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                                 : "=d"(v[u][0]), "=d"(v[u][1]), "=d"(v[u][2]), "=d"(v[u][3]) : "l"(src + head + 4 * q));
+            }
+            for (int p = 0; p < t.count; ++p) {
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const long long q = q0 + u * stride;
+                    if (q < quads)
+                        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(t.dst[p] + head + 4 * q), "d"(v[u][0]), "d"(v[u][1]),
+                                     "d"(v[u][2]), "d"(v[u][3]) : "memory");
+                }
+            }
+        }
+    } else {
+        // a lane moves 16 bytes, a warp instruction 512 contiguous bytes (the classic coalesced pattern)
+        const long long pairs = quads * 2;
+        const double2 *s2 = reinterpret_cast<const double2 *>(src + head);
+        for (long long i0 = tid; i0 < pairs; i0 += UNROLL * stride) {
+            double2 v[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const long long i = i0 + u * stride;
+                if (i < pairs)
+                    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v[u].x), "=d"(v[u].y) : "l"(s2 + i));
+            }
+            for (int p = 0; p < t.count; ++p) {
+                double2 *d2 = reinterpret_cast<double2 *>(t.dst[p] + head);
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const long long i = i0 + u * stride;
+                    if (i < pairs) d2[i] = v[u];
+                }
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 8) {  // up to three elements at either end
+        const long long tail = head + 4 * quads;
+        const long long i = threadIdx.x < 4 ? threadIdx.x : tail + (threadIdx.x - 4);
+        const bool mine = threadIdx.x < 4 ? i < head : i < n;
+        if (mine) {
+            const double v = src[i];
+            for (int p = 0; p < t.count; ++p) t.dst[p][i] = v;
+        }
+    }
 }
 
 }  // namespace spmv
@@ -346,61 +424,6 @@ int spmv_b200_ipc_free(void *d_ptr) {
     return SPMV_B200_OK;
 }
 
-// dst_p[i] = src[i] for every peer p: the all-gather of a slice written against peer memory (NVLink stores).  A
-// persistent grid of one CTA per SM is all the links need; 256-bit loads, 256-bit peer stores.  The source and every
-// target sit at the SAME offset of equally aligned buffers (a row range of the replicas of x), so one scalar head of
-// up to three elements brings all of them onto a 32-byte boundary; targets aligned differently take the scalar path.
-struct PushTargets {
-    int count;
-    int vector_ok;
-    double *dst[SPMV_B200_MAX_PEERS];
-};
-
-template <int UNROLL>
-__global__ void __launch_bounds__(512)
-vec_push_kernel(const double *__restrict__ src, long long n, const __grid_constant__ PushTargets t) {
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
-    if (!t.vector_ok) {
-        for (long long i = tid; i < n; i += stride) {
-            const double v = __ldg(src + i);
-            for (int p = 0; p < t.count; ++p) t.dst[p][i] = v;
-        }
-        return;
-    }
-    const long long head = min(n, (long long)(((32 - (reinterpret_cast<uintptr_t>(src) & 31)) & 31) >> 3));
-    const long long quads = (n - head) >> 2;
-    // a lane moves whole 32-byte sectors (LDG.256 / STG.256): a warp instruction covers 1 KB of contiguous peer memory,
-    // never half a sector (two 128-bit stores per lane wrote every sector of the peer twice: 290-420 GB/s on 2 GPUs)
-    for (long long q0 = tid; q0 < quads; q0 += UNROLL * stride) {
-        double v[UNROLL][4];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const long long q = q0 + u * stride;
-            if (q < quads)
-                asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
-                             : "=d"(v[u][0]), "=d"(v[u][1]), "=d"(v[u][2]), "=d"(v[u][3]) : "l"(src + head + 4 * q));
-        }
-        for (int p = 0; p < t.count; ++p) {
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const long long q = q0 + u * stride;
-                if (q < quads)
-                    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(t.dst[p] + head + 4 * q), "d"(v[u][0]), "d"(v[u][1]),
-                                 "d"(v[u][2]), "d"(v[u][3]) : "memory");
-            }
-        }
-    }
-    if (blockIdx.x == 0 && threadIdx.x < 8) {  // up to three elements at either end
-        const long long tail = head + 4 * quads;
-        const long long i = threadIdx.x < 4 ? threadIdx.x : tail + (threadIdx.x - 4);
-        const bool mine = threadIdx.x < 4 ? i < head : i < n;
-        if (mine) {
-            const double v = src[i];
-            for (int p = 0; p < t.count; ++p) t.dst[p][i] = v;
-        }
-    }
-}
-
 int spmv_b200_vec_push(const double *d_src, long long n, int npeers, double *const *d_peer_dst, int ctas, void *stream) {
     if (n < 0 || npeers < 0 || npeers > SPMV_B200_MAX_PEERS || (npeers > 0 && !d_peer_dst) || (n > 0 && !d_src))
         return fail(SPMV_B200_ERR_INVALID, "vec_push: bad arguments");
@@ -419,11 +442,14 @@ int spmv_b200_vec_push(const double *d_src, long long n, int npeers, double *con
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = ctas > 0 ? ctas : sms;
-    switch (env_int("SPMV_B200_PUSH_UNROLL", 2)) {
-        case 1: vec_push_kernel<1><<<grid, 512, 0, as_stream(stream)>>>(d_src, n, t); break;
-        case 4: vec_push_kernel<4><<<grid, 512, 0, as_stream(stream)>>>(d_src, n, t); break;
-        default: vec_push_kernel<2><<<grid, 512, 0, as_stream(stream)>>>(d_src, n, t); break;
+    const int unroll = env_int("SPMV_B200_PUSH_UNROLL", 2), width = env_int("SPMV_B200_PUSH_WIDTH", 16);
+#define PUSH_CASE(U, W) vec_push_kernel<U, W><<<grid, 512, 0, as_stream(stream)>>>(d_src, n, t)
+    if (width == 32) {
+        if (unroll == 1) PUSH_CASE(1, 32); else if (unroll == 4) PUSH_CASE(4, 32); else PUSH_CASE(2, 32);
+    } else {
+        if (unroll == 1) PUSH_CASE(1, 16); else if (unroll == 4) PUSH_CASE(4, 16); else PUSH_CASE(2, 16);
     }
+#undef PUSH_CASE
     SPMV_TRY_CUDA(cudaGetLastError());
     return SPMV_B200_OK;
 }

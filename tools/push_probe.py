@@ -57,10 +57,12 @@ def main():
         for v in views:
             v.copy_(src, non_blocking=True)
     report("cudaMemcpyAsync per peer, one stream", timed(copies))
-    for unroll in (1, 2, 4):
-        os.environ["SPMV_B200_PUSH_UNROLL"] = str(unroll)
-        for ctas in (148, 296, 592, 1184):
-            report(f"vec_push unroll {unroll} ctas {ctas}", timed(lambda: device.vec_push(src, n, targets, ctas=ctas)))
+    for width in (16, 32):
+        os.environ["SPMV_B200_PUSH_WIDTH"] = str(width)
+        for unroll in (1, 2, 4):
+            os.environ["SPMV_B200_PUSH_UNROLL"] = str(unroll)
+            for ctas in (148, 592):
+                report(f"vec_push {width}-byte lanes, unroll {unroll}, ctas {ctas}", timed(lambda: device.vec_push(src, n, targets, ctas=ctas)))
     # what landed
     dist.barrier()
     torch.cuda.synchronize()
