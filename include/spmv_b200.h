@@ -339,8 +339,8 @@ int spmv_b200_vec_scale_by_inv_norm(double *d_dst, const double *d_src, long lon
                                     const double *d_sumsq, void *stream);
 
 /* d_peer_dst[p][i] = d_src[i] for p < npeers, i < n: a slice of x pushed into the replicas of the other ranks with NVLink
- * peer stores (the all-gather of the "allgather_peer" exchange written against peer memory; `ctas` = grid size, 0 = one
- * CTA per SM).  256-bit loads / 256-bit peer stores when the source and every target share their offset within 32
+ * peer stores (the all-gather of the "allgather_peer" exchange written against peer memory; `ctas` = grid size, 0 = two
+ * CTAs per SM).  256-bit loads / 256-bit peer stores when the source and every target share their offset within 32
  * bytes (the same row range of equally aligned replicas), scalar otherwise.  d_peer_dst is a HOST array of device
  * pointers.  No ordering is implied towards the peers: follow it with spmv_b200_mail_exchange (tag after fence). */
 int spmv_b200_vec_push(const double *d_src, long long n, int npeers, double *const *d_peer_dst, int ctas, void *stream);

@@ -441,8 +441,8 @@ int spmv_b200_vec_push(const double *d_src, long long n, int npeers, double *con
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = ctas > 0 ? ctas : sms;
-    const int unroll = env_int("SPMV_B200_PUSH_UNROLL", 2), width = env_int("SPMV_B200_PUSH_WIDTH", 16);
+    const int grid = ctas > 0 ? ctas : 2 * sms;
+    const int unroll = env_int("SPMV_B200_PUSH_UNROLL", 2), width = env_int("SPMV_B200_PUSH_WIDTH", 32);
 #define PUSH_CASE(U, W) vec_push_kernel<U, W><<<grid, 512, 0, as_stream(stream)>>>(d_src, n, t)
     if (width == 32) {
         if (unroll == 1) PUSH_CASE(1, 32); else if (unroll == 4) PUSH_CASE(4, 32); else PUSH_CASE(2, 32);
