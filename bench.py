@@ -773,7 +773,7 @@ def bench_multi_gpu(args):
         return {"x_err": x_err, "lambda_err": lam_err, "lambda": lam, "ok": ok}
 
     modes = ("fused_mailbox", "fused_split", "fused_split_hll", "fused_mailbox_hll", "fused_mailbox_csr_hack_aligned", "fused_async", "fused_peer_stores",
-             "fused_nccl_halo", "halo", "allgather_peer", "allgather_peer_kernel", "allgather", "allgather_broadcasts")
+             "fused_nccl_halo", "halo", "allgather_peer", "allgather_peer_2streams", "allgather_peer_hybrid", "allgather_peer_kernel", "allgather", "allgather_broadcasts")
     if args.modes:
         modes = tuple(m for m in modes if m in args.modes.split(",") or m == HEAD_MODE)
     parity = {}
@@ -801,6 +801,11 @@ def bench_multi_gpu(args):
             P = AllgatherPowerIteration(synth.SYNTH_LAP3D, n)
         elif mode == "allgather_peer":
             P = PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n, copy_streams=int(os.environ.get("SPMV_B200_PUSH_STREAMS", "1")))
+        elif mode == "allgather_peer_2streams":
+            P = PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n, copy_streams=int(os.environ.get("SPMV_B200_PUSH_STREAMS2", "2")))
+        elif mode == "allgather_peer_hybrid":     # copy engines + push kernel at the same time
+            P = PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n, kernel_peers=int(os.environ.get("SPMV_B200_PUSH_KERNEL_PEERS", str(max(1, (world - 1) // 3)))),
+                                            push_ctas=int(os.environ.get("SPMV_B200_PUSH_CTAS", "0")))
         elif mode == "allgather_peer_kernel":
             P = PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n, copy_engine=False, push_ctas=int(os.environ.get("SPMV_B200_PUSH_CTAS", "0")))
         elif mode == "allgather_broadcasts":
@@ -830,7 +835,7 @@ def bench_multi_gpu(args):
         if mode.startswith("allgather_peer"):
             results[mode]["collective"] = (
                 "no library call: every rank stores its slice into all replicas over NVLink peer memory ("
-                + (f"one cudaMemcpyAsync per peer on {len(P.copy_streams)} stream(s), copy engines" if P.copy_engine else "spmv_b200_vec_push: one kernel, 256-bit loads and peer stores")
+                + (f"one cudaMemcpyAsync per peer on {len(P.copy_streams)} stream(s), copy engines" + (f"; the last {P.kernel_peers} peer(s) of the rotation by spmv_b200_vec_push at the same time" if P.kernel_peers else "") if P.copy_engine else "spmv_b200_vec_push: one kernel, 256-bit loads and peer stores")
                 + f"), then tags through peer mailboxes; interior rows [{P.interior[0]},{P.interior[1]}) of {P.rows} multiplied while it is in flight")
             try:   # the push + tags alone, same buffers
                 def push_only():

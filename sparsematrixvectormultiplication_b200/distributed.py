@@ -584,10 +584,13 @@ class PeerAllgatherPowerIteration(PowerIteration):
 
     No collective library call in the loop; 5 + 2 launches per iteration."""
 
-    def __init__(self, kind, p0, p1=0, p2=0, seed=0x5EED, group=None, parts=None, push_ctas=0, copy_engine=True, copy_streams=1):
+    def __init__(self, kind, p0, p1=0, p2=0, seed=0x5EED, group=None, parts=None, push_ctas=0, copy_engine=True, copy_streams=1,
+                 kernel_peers=0):
         """copy_engine=True (default, the faster one measured): the slice travels as one cudaMemcpyAsync per peer -- the
         DMA engines drive NVLink and every SM stays with the product; copy_streams > 1 spreads the peers over that many
-        streams.  copy_engine=False: spmv_b200_vec_push, the same transfer as ONE kernel of peer stores."""
+        streams.  copy_engine=False: spmv_b200_vec_push, the same transfer as ONE kernel of peer stores.
+        kernel_peers=k with copy_engine=True: the LAST k peers of the rotation are served by the push kernel on a stream
+        of its own while the copy engines serve the others (both drive the links at the same time)."""
         super().__init__(kind, p0, p1, p2, seed=seed, exchange="allgather", group=group, parts=parts)
         from . import _native as N
         d = self.dev
@@ -649,6 +652,9 @@ class PeerAllgatherPowerIteration(PowerIteration):
                 self.mails[i].box[0] = self.boxes[i].ptr.value
         self.push_ctas = int(push_ctas)
         self.copy_engine = bool(copy_engine)
+        self.kernel_peers = max(0, min(int(kernel_peers), self.world - 1)) if self.copy_engine else 0
+        self.kernel_stream = torch.cuda.Stream(device=cu, priority=-1)
+        self.kernel_event = torch.cuda.Event()
         self.push_stream = torch.cuda.Stream(device=cu, priority=-1)
         self.copy_streams = [self.push_stream] + [torch.cuda.Stream(device=cu, priority=-1)
                                                   for _ in range(max(1, min(int(copy_streams), self.world - 1)) - 1)]
@@ -682,12 +688,19 @@ class PeerAllgatherPowerIteration(PowerIteration):
         if self.copy_engine:     # one cudaMemcpyAsync per peer, nearest successor first (every rank targets another one)
             for st in self.copy_streams[1:]:
                 st.wait_event(self.ev_own)
-            for j, v in enumerate(self.push_views[nxt]):
+            by_copy = len(self.push_views[nxt]) - self.kernel_peers
+            if self.kernel_peers:
+                self.kernel_stream.wait_event(self.ev_own)
+                self.dev.vec_push(own, self.rows, self.push_targets[nxt][by_copy:], ctas=self.push_ctas, stream=self.kernel_stream)
+                self.kernel_event.record(self.kernel_stream)
+            for j, v in enumerate(self.push_views[nxt][:by_copy]):
                 with torch.cuda.stream(self.copy_streams[j % len(self.copy_streams)]):
                     v[: self.rows].copy_(own, non_blocking=True)
             for st, ev in zip(self.copy_streams[1:], self.copy_events[1:]):
                 ev.record(st)
                 ps.wait_event(ev)
+            if self.kernel_peers:
+                ps.wait_event(self.kernel_event)
         else:
             self.dev.vec_push(own, self.rows, self.push_targets[nxt], ctas=self.push_ctas, stream=ps)
         self.mails[1].iteration = self.k

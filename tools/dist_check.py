@@ -73,6 +73,7 @@ def main():
               ("allgather (one ncclAllGather)", lambda: AllgatherPowerIteration(synth.SYNTH_LAP3D, n), True),
               ("allgather_peer (copy engines)", lambda: PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n), True),
               ("allgather_peer (copy engines, 3 streams)", lambda: PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n, copy_streams=3), True),
+              ("allgather_peer (copy engines + push kernel for the last peer)", lambda: PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n, kernel_peers=1), True),
               ("allgather_peer (push kernel)", lambda: PeerAllgatherPowerIteration(synth.SYNTH_LAP3D, n, copy_engine=False), True))
     for name, make, whole in makers:
         F = make()
