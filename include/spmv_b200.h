@@ -196,12 +196,15 @@ int spmv_b200_csr_spmv_fused_mail(const spmv_b200_csr *A, const double *d_x, dou
  *       spmv_b200_csr_spmv_fused_mail), waits for the tags of all ranks in its own mailbox -- which also proves their
  *       boundary rows have landed -- and leaves {|w_k|^2, 1/|w_k|} (ranks added in rank order) in d_sumsq_out[0..1]; the
  *       next product launch takes d_inv_norm = d_sumsq_out + 1 (the square root and the division are paid once, not once
- *       per thread).  mail->counter is not used.  Launches of one rank must be stream ordered.
+ *       per thread).  Above 8192 partials the sum is spread over up to 64 CTAs (the last one to finish carries on with
+ *       the exchange): d_partials is then CONSUMED (a few entries are overwritten with chunk sums) and mail->counter must
+ *       point to one zeroed unsigned int (self-resetting); with mail->counter == NULL one CTA does all of it.  Launches of
+ *       one rank must be stream ordered.
  * The HLL twins: spmv_b200_hll_spmv_fused_flat / spmv_b200_hll_flat_partials_count. */
 int spmv_b200_csr_flat_partials_count(const spmv_b200_csr *A);
 int spmv_b200_csr_spmv_fused_flat(const spmv_b200_csr *A, const double *d_x, double *d_y, const double *d_inv_norm,
                                   double *d_partials, const spmv_b200_peers_t *peers, void *stream);
-int spmv_b200_mail_exchange(const double *d_partials, int count, const spmv_b200_mail_t *mail, double *d_sumsq_out, void *stream);
+int spmv_b200_mail_exchange(double *d_partials, int count, const spmv_b200_mail_t *mail, double *d_sumsq_out, void *stream);
 
 /* The asynchronous form of the fused iterated product: no rank ever waits for the CURRENT launch of another rank.
  *   - x lives in a ring of THREE buffers (launch k reads ring[k%3], writes ring[(k+1)%3], own rows locally and the

@@ -692,20 +692,24 @@ __global__ void interior_rows_kernel(int M, int mid, const int *__restrict__ row
     else atomicMin(out + 1, (int)r);
 }
 
-// The exchange of the two-launch iterated product (spmv_b200_mail_exchange): ONE CTA.  (1) the partials of the flat
-// product kernel, added in a fixed order (thread t adds its contiguous block left to right; fixed tree); (2) {sum, tag k+1} into
-// slot [k&1][rank] of every rank's mailbox -- the product kernel has completed (stream order), a system-scope fence and
-// a release store order its peer stores before the tag; (3) wait for the tags of all ranks in the own mailbox, add
-// their sums in rank order, leave {|w_k|^2, 1/|w_k|} in sumsq_out[0..1] for the next product launch.
+// The exchange of the two-launch iterated product (spmv_b200_mail_exchange).  (1) the partials of the flat product kernel,
+// added in a fixed order: CTA g adds chunk g (thread t its contiguous block left to right, then a fixed tree); with more
+// than one CTA the chunk sum replaces the chunk's first element and the LAST CTA to arrive (ticket in mail.counter, one
+// device-scope fence per CTA -- at most 64 of them) adds the chunk sums in chunk order and carries on alone: one SM read
+// 8 KB of partials per microsecond, which put 8 / 17 / 30 us on the critical path of every iteration at 8 / 4 / 2 GPUs;
+// (2) {sum, tag k+1} into slot [k&1][rank] of every rank's mailbox -- the product kernel has completed (stream order), a
+// system-scope fence and a release store order its peer stores before the tag; (3) wait for the tags of all ranks in the own
+// mailbox, add their sums in rank order, leave {|w_k|^2, 1/|w_k|} in sumsq_out[0..1] for the next product launch.
 __global__ void __launch_bounds__(1024)
-mail_exchange_kernel(const double *__restrict__ partials, int count, const __grid_constant__ spmv_b200_mail_t mail,
+mail_exchange_kernel(double *__restrict__ partials, int count, int chunk, const __grid_constant__ spmv_b200_mail_t mail,
                      double *__restrict__ sumsq_out) {
     __shared__ double part[1024];
-    // thread t adds ITS contiguous block of ceil(count / 1024) partials (rounded up to a multiple of 4) left to right; the
-    // loads of a block are independent 256-bit loads, all in flight at once (one by one the 64 L2 round trips of a
-    // 65 536-CTA launch cost 10 us, profiles/r02n_ncu_full_summary.md)
-    const int per = (((count + 1023) >> 10) + 3) & ~3;
-    const int lo = (int)threadIdx.x * per, hi = min(count, lo + per);
+    __shared__ int is_last;
+    const int c_lo = (int)blockIdx.x * chunk, c_hi = min(count, c_lo + chunk);
+    // thread t adds ITS contiguous block of the chunk (a multiple of 4 elements) left to right; the loads of a block are
+    // independent 256-bit loads, all in flight at once
+    const int per = ((((c_hi - c_lo) + 1023) >> 10) + 3) & ~3;
+    const int lo = c_lo + (int)threadIdx.x * per, hi = min(c_hi, lo + per);
     double s = 0.0;
     if ((reinterpret_cast<uintptr_t>(partials) & 31) == 0) {
         constexpr int kGroup = 8;  // 8 x 4 doubles per round
@@ -735,9 +739,27 @@ mail_exchange_kernel(const double *__restrict__ partials, int count, const __gri
         if ((int)threadIdx.x < half) part[threadIdx.x] += part[threadIdx.x + half];
         __syncthreads();
     }
-    if (threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
-    const double mine = part[0];
+    double mine = part[0];
+    if (gridDim.x > 1) {
+        if (threadIdx.x == 0) {
+            partials[c_lo] = mine;  // only this CTA read the chunk
+            __threadfence();
+            is_last = atomicAdd(mail.counter, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (!is_last || threadIdx.x >= 32) return;
+        __threadfence();
+        const int chunks = (int)gridDim.x;  // <= 64
+        const double a = lane < chunks ? __ldcg(partials + (long long)lane * chunk) : 0.0;
+        const double b = lane + 32 < chunks ? __ldcg(partials + (long long)(lane + 32) * chunk) : 0.0;
+        mine = 0.0;
+        for (int g = 0; g < min(chunks, 32); ++g) mine += __shfl_sync(0xffffffffu, a, g);
+        for (int g = 32; g < chunks; ++g) mine += __shfl_sync(0xffffffffu, b, g - 32);
+        if (lane == 0) *mail.counter = 0;  // every CTA has drawn its ticket: ready for the next launch
+    } else if (threadIdx.x >= 32) {
+        return;
+    }
     if (mail.world == 1) {  // nobody to talk to
         if (lane == 0) {
             sumsq_out[0] = mine;
@@ -1712,13 +1734,18 @@ int spmv_b200_csr_interior_rows(const spmv_b200_csr *A, long long col_lo, long l
     return SPMV_B200_OK;
 }
 
-int spmv_b200_mail_exchange(const double *d_partials, int count, const spmv_b200_mail_t *mail, double *d_sumsq_out, void *stream) {
+int spmv_b200_mail_exchange(double *d_partials, int count, const spmv_b200_mail_t *mail, double *d_sumsq_out, void *stream) {
     if (!d_partials || count < 1 || !mail || !d_sumsq_out) return fail(SPMV_B200_ERR_INVALID, "mail_exchange: bad arguments");
     if (mail->world < 1 || mail->world > SPMV_B200_MAX_RANKS || mail->rank < 0 || mail->rank >= mail->world || !mail->status)
         return fail(SPMV_B200_ERR_INVALID, "mail_exchange: bad mailbox description (world %d, rank %d)", mail->world, mail->rank);
     for (int r = 0; r < mail->world; ++r)
         if (!mail->box[r]) return fail(SPMV_B200_ERR_INVALID, "mail_exchange: mailbox of rank %d is NULL", r);
-    mail_exchange_kernel<<<1, 1024, 0, as_stream(stream)>>>(d_partials, count, *mail, d_sumsq_out);
+    // one CTA up to 8192 partials; beyond that up to 64 CTAs of at least 4096 (the last one to finish does the exchange)
+    int ctas = (count <= 8192 || !mail->counter) ? 1 : std::min(64, (count + 4095) / 4096);
+    ctas = std::max(1, std::min(ctas, env_int("SPMV_B200_EXCHANGE_CTAS", ctas)));
+    const int chunk = (((count + ctas - 1) / ctas) + 3) & ~3;
+    ctas = (count + chunk - 1) / chunk;
+    mail_exchange_kernel<<<ctas, 1024, 0, as_stream(stream)>>>(d_partials, count, chunk, *mail, d_sumsq_out);
     SPMV_TRY_CUDA(cudaGetLastError());
     return SPMV_B200_OK;
 }
