@@ -138,13 +138,6 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
-// start while its predecessor in the stream still runs; griddepcontrol.wait blocks until the predecessor has COMPLETED
-// and its writes are visible, griddepcontrol.launch_dependents lets the successor start early.  Both are no-ops in a
-// launch without the attribute.
-__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
 constexpr long long kMailSpinCycles = 4000000000LL;  // ~2 s at 1.9 GHz: a peer that has not answered by then is gone
 
 // Launch k > 0, one whole warp: wait until every rank's slot of parity (k-1)&1 in MY mailbox carries tag k (launch k-1

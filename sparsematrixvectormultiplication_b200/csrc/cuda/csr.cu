@@ -280,8 +280,6 @@ __global__ void __launch_bounds__(256, 8)
 csr_row_flat_kernel(int M, const int *__restrict__ row_ptr, const int *__restrict__ col_idx, const double *__restrict__ values,
                     const double *__restrict__ x, double *__restrict__ y, const __grid_constant__ Epilogue ep) {
     __shared__ double warp_sq[8];
-    if (ep.pdl) grid_dep_launch();  // the exchange kernel behind this launch may take its SM slot now (it waits for us)
-    bool waited = ep.pdl == 0;      // with PDL: the exchange kernel of the previous iteration may still be running
     const long long row = (long long)blockIdx.x * 256 + threadIdx.x;
     const bool live = row < M;
     double acc = 0.0;
@@ -294,19 +292,12 @@ csr_row_flat_kernel(int M, const int *__restrict__ row_ptr, const int *__restric
             for (int u = 0; u < BATCH; ++u) c[u] = k + u < hi ? __ldg(col_idx + k + u) : -1;
 #pragma unroll
             for (int u = 0; u < BATCH; ++u) v[u] = k + u < hi ? __ldg(values + k + u) : 0.0;
-            if (!waited) {  // the matrix never changes: its loads are in flight while we wait for x, 1/|w| and the halo
-                grid_dep_wait();
-                waited = true;
-            }
 #pragma unroll
             for (int u = 0; u < BATCH; ++u) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
 #pragma unroll
             for (int u = 0; u < BATCH; ++u)
                 if (c[u] >= 0) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
         }
-    }
-    if (!waited) grid_dep_wait();  // empty rows and the threads past the last row: y, the partials and the peers come next
-    if (live) {
         if (ep.inv_norm != nullptr) acc *= __ldg(ep.inv_norm);
         y[row] = acc;
         if (fused_chunk_is_boundary(ep, (long long)blockIdx.x * 256)) fused_peer_store(ep, row, acc);
@@ -711,13 +702,9 @@ __global__ void interior_rows_kernel(int M, int mid, const int *__restrict__ row
 // mailbox, add their sums in rank order, leave {|w_k|^2, 1/|w_k|} in sumsq_out[0..1] for the next product launch.
 __global__ void __launch_bounds__(1024)
 mail_exchange_kernel(double *__restrict__ partials, int count, int chunk, const __grid_constant__ spmv_b200_mail_t mail,
-                     double *__restrict__ sumsq_out, int pdl) {
+                     double *__restrict__ sumsq_out) {
     __shared__ double part[1024];
     __shared__ int is_last;
-    if (pdl) {  // launched while the product still runs: let the NEXT product start its matrix loads, then wait for ours
-        grid_dep_launch();
-        grid_dep_wait();
-    }
     const int c_lo = (int)blockIdx.x * chunk, c_hi = min(count, c_lo + chunk);
     // thread t adds ITS contiguous block of the chunk (a multiple of 4 elements) left to right; the loads of a block are
     // independent 256-bit loads, all in flight at once
@@ -1327,7 +1314,7 @@ static int flat_grid(long long M, int chunks_per_cta) {
 static int launch_fused_flat(const spmv_b200_csr *A, const double *x, double *y, const Epilogue &ep, cudaStream_t stream,
                              int batch, int chunks_per_cta) {
     const int g = flat_grid(A->M, chunks_per_cta);
-    const XPolicy keep = with_pdl(matrix_policy(A->row_ptr, (size_t)(A->M + 1) * sizeof(int)), ep.pdl != 0);
+    const XPolicy keep = matrix_policy(A->row_ptr, (size_t)(A->M + 1) * sizeof(int));
 #define FLAT_CASE(B) case B: SPMV_TRY_CUDA(launch_x(csr_row_flat_kernel<B>, g, 256, 0, stream, keep, A->M, A->row_ptr, A->col_idx, A->values, x, y, ep)); break;
     switch (batch) {
         FLAT_CASE(2) FLAT_CASE(3) FLAT_CASE(5) FLAT_CASE(6) FLAT_CASE(7)
@@ -1638,7 +1625,6 @@ int spmv_b200_csr_spmv_fused_flat(const spmv_b200_csr *A, const double *d_x, dou
     ep.partials = d_partials;
     ep.partials_total = flat_grid(A->M, chunks);
     if (peers) ep.peers = *peers;
-    ep.pdl = env_int("SPMV_B200_PDL", kPdlDefault);
     return launch_fused_flat(A, d_x, d_y, ep, as_stream(stream), batch, chunks);
 }
 
@@ -1759,9 +1745,7 @@ int spmv_b200_mail_exchange(double *d_partials, int count, const spmv_b200_mail_
     ctas = std::max(1, std::min(ctas, env_int("SPMV_B200_EXCHANGE_CTAS", ctas)));
     const int chunk = (((count + ctas - 1) / ctas) + 3) & ~3;
     ctas = (count + chunk - 1) / chunk;
-    const int pdl = env_int("SPMV_B200_PDL", kPdlDefault);
-    SPMV_TRY_CUDA(launch_x(mail_exchange_kernel, (unsigned int)ctas, 1024, 0, as_stream(stream), with_pdl(XPolicy(), pdl != 0), d_partials,
-                           count, chunk, *mail, d_sumsq_out, pdl));
+    mail_exchange_kernel<<<ctas, 1024, 0, as_stream(stream)>>>(d_partials, count, chunk, *mail, d_sumsq_out);
     SPMV_TRY_CUDA(cudaGetLastError());
     return SPMV_B200_OK;
 }

@@ -51,8 +51,6 @@ struct Epilogue {                 // optional fused tail of the CSR stream / row
     spmv_b200_peers_t peers = {}; // rows mirrored into peer memory
     spmv_b200_mail_t mail = {};   // world > 0: |w|^2 travels through peer mailboxes instead of prev_sumsq (spmv_b200.h)
     ChunkOrder order;             // row kernels only: boundary chunks first (filled by boundary_first_order)
-    int pdl = 0;                  // FLAT form: launched with programmatic stream serialization -- the matrix stream of a row is
-                                  // requested BEFORE griddepcontrol.wait, x / 1/|w| / the partials are touched after it
 };
 
 // the union of the peers' row ranges in 256-row chunks, ascending and disjoint (host side)
@@ -294,19 +292,10 @@ int fused_ctas_per_sm();  // csr.cu: CTAs per SM in the grid of the fused row ke
 // "persisting", the rest of the window "streaming"; the device's persisting carve-out (cudaLimitPersistingL2CacheSize)
 // is raised once per device to its maximum.  hitRatio = 1 when x fits the carve-out, else carve-out / bytes, so the
 // persisting lines never thrash among themselves.  SPMV_B200_L2_PERSIST=0 switches it off (plain launches).
-constexpr int kPdlDefault = 0;  // programmatic dependent launch of the two-launch iterated product (SPMV_B200_PDL)
 struct XPolicy {
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[1];
     unsigned int count = 0;
 };
-inline XPolicy with_pdl(XPolicy p, bool on) {  // + programmatic stream serialization (see grid_dep_wait, common.cuh)
-    if (on) {
-        p.attr[p.count].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        p.attr[p.count].val.programmaticStreamSerializationAllowed = 1;
-        ++p.count;
-    }
-    return p;
-}
 XPolicy x_policy(const void *x, size_t bytes);
 XPolicy matrix_policy(const void *head, size_t bytes);  // head of a matrix array held in L2 across products (csr.cu)
 

@@ -130,8 +130,6 @@ hll_row_flat_kernel(int num_hacks, const long long *__restrict__ hack_off, const
                     const double *__restrict__ AS, const double *__restrict__ x, double *__restrict__ y, int M,
                     const __grid_constant__ Epilogue ep) {
     __shared__ double warp_sq[8];
-    if (ep.pdl) grid_dep_launch();  // see csr_row_flat_kernel: the matrix stream is requested before the wait
-    bool waited = ep.pdl == 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int hack = blockIdx.x * 8 + warp;
     const long long row = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -147,19 +145,12 @@ hll_row_flat_kernel(int num_hacks, const long long *__restrict__ hack_off, const
             for (int u = 0; u < BATCH; ++u) c[u] = j + u < width ? ldg_stream_s32(JA + base + (long long)(j + u) * kHack) : -1;
 #pragma unroll
             for (int u = 0; u < BATCH; ++u) v[u] = j + u < width ? ldg_stream_f64(AS + base + (long long)(j + u) * kHack) : 0.0;
-            if (!waited) {
-                grid_dep_wait();
-                waited = true;
-            }
 #pragma unroll
             for (int u = 0; u < BATCH; ++u) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
 #pragma unroll
             for (int u = 0; u < BATCH; ++u)
                 if (c[u] >= 0) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
         }
-    }
-    if (!waited) grid_dep_wait();
-    if (hack < num_hacks) {
         if (row < M) {
             if (ep.inv_norm != nullptr) acc *= __ldg(ep.inv_norm);
             y[row] = acc;
@@ -342,7 +333,7 @@ static int hll_flat_grid(long long M, int chunks_per_cta) {
 static int hll_launch_fused_flat(const spmv_b200_hll *H, const double *d_x, double *d_y, const Epilogue &ep, cudaStream_t stream,
                                  int batch, int chunks_per_cta) {
     const int g = hll_flat_grid(H->M, chunks_per_cta);
-    const XPolicy keep = with_pdl(matrix_policy(H->JA, (size_t)H->slots * sizeof(int)), ep.pdl != 0);
+    const XPolicy keep = matrix_policy(H->JA, (size_t)H->slots * sizeof(int));
 #define HFLAT_CASE(B) case B: SPMV_TRY_CUDA(launch_x(hll_row_flat_kernel<B>, g, 256, 0, stream, keep, H->num_hacks, H->hack_off, H->JA, H->AS, d_x, d_y, H->M, ep)); break;
     switch (batch) {
         HFLAT_CASE(2) HFLAT_CASE(3) HFLAT_CASE(5) HFLAT_CASE(6) HFLAT_CASE(7)
@@ -741,7 +732,6 @@ int spmv_b200_hll_spmv_fused_flat(const spmv_b200_hll *H, const double *d_x, dou
     ep.partials = d_partials;
     ep.partials_total = hll_flat_grid(H->M, chunks);
     if (peers) ep.peers = *peers;
-    ep.pdl = env_int("SPMV_B200_PDL", kPdlDefault);
     return hll_launch_fused_flat(H, d_x, d_y, ep, as_stream(stream), batch, chunks);
 }
 
