@@ -89,6 +89,10 @@ typedef struct {
 
 /* ---- library / device ---------------------------------------------------------------- */
 const char *spmv_b200_last_error(void);
+/* forget the calling thread's message: the void drop-in products (csr_matrix_vector_mult, spmv_hll, ...) report a
+ * failure by filling y with NaN and leaving a message here, so a caller that wants to tell "failed" from "x held a
+ * NaN" clears the message first and looks at it afterwards */
+void spmv_b200_clear_error(void);
 int spmv_b200_version(void);
 int spmv_b200_device_count(int *count);
 /* name[len], sm count, L2 bytes, total global memory of the current device */

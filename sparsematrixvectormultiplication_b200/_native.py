@@ -106,6 +106,7 @@ _D = C.c_double
 SIGNATURES = {
     # ---- spmv_b200.h ----
     "spmv_b200_last_error": (C.c_char_p, []),
+    "spmv_b200_clear_error": (None, []),
     "spmv_b200_version": (_I, []),
     "spmv_b200_device_count": (_I, [c_int_p]),
     "spmv_b200_device_info": (_I, [C.c_char_p, _I, c_int_p, c_ll_p, c_ll_p]),
@@ -271,6 +272,10 @@ def lib() -> C.CDLL:
             fn.argtypes = argtypes
         _lib = handle
     return _lib
+
+
+def clear_error() -> None:
+    lib().spmv_b200_clear_error()
 
 
 def last_error() -> str:

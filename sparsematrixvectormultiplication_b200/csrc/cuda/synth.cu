@@ -262,6 +262,7 @@ using namespace spmv;
 extern "C" {
 
 const char *spmv_b200_last_error(void) { return g_error; }
+void spmv_b200_clear_error(void) { g_error[0] = '\0'; }
 
 int spmv_b200_version(void) { return 100; }
 

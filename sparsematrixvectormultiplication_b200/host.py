@@ -211,6 +211,7 @@ def csr_matrix_vector_mult(num_row, row_ptr, col_idx, values, x, y):
     """y += A x, in place on the float64 array ``y`` (reference src/csr_matrix.c:130-139)."""
     row_ptr, col_idx, values, x = _i32(row_ptr), _i32(col_idx), _f64(values), _f64(x)
     assert y.dtype == np.float64 and y.flags.c_contiguous
+    N.clear_error()      # a stale message of an earlier call must not turn a NaN in x into a failure
     N.lib().csr_matrix_vector_mult(int(num_row), _ip(row_ptr), _ip(col_idx), _dp(values), _dp(x), _dp(y))
     if num_row and _poisoned(y[:num_row]) and N.last_error():
         raise N.SpmvError(-2, N.last_error())
@@ -221,6 +222,7 @@ def _csr_ranged(fn, row_ptr, col_idx, values, x, y, starts, ends):
     row_ptr, col_idx, values, x = _i32(row_ptr), _i32(col_idx), _f64(values), _f64(x)
     starts, ends = _i32(starts), _i32(ends)
     assert y.dtype == np.float64 and y.flags.c_contiguous
+    N.clear_error()
     fn(_ip(row_ptr), _ip(col_idx), _dp(values), _dp(x), _dp(y), len(starts), _ip(starts), _ip(ends))
     if len(starts) and _poisoned(y) and N.last_error():
         raise N.SpmvError(-2, N.last_error())
@@ -241,6 +243,7 @@ def spmv_hll_serial(hll: HLLMatrix, x, y):
     """y[32 b + i] = (A x) for every block (reference src/hll_matrix.c:286-308)."""
     x = _f64(x)
     assert y.dtype == np.float64 and y.flags.c_contiguous
+    N.clear_error()
     N.lib().spmv_hll_serial(hll.c.num_blocks, hll.c.blocks, _dp(x), _dp(y))
     if _poisoned(y) and N.last_error():
         raise N.SpmvError(-2, N.last_error())
@@ -250,6 +253,7 @@ def spmv_hll_serial(hll: HLLMatrix, x, y):
 def _hll_ranged(fn, hll, x, y, starts, ends):
     x, starts, ends = _f64(x), _i32(starts), _i32(ends)
     assert y.dtype == np.float64 and y.flags.c_contiguous
+    N.clear_error()
     fn(hll.c.blocks, _dp(x), _dp(y), len(starts), _ip(starts), _ip(ends))
     if len(starts) and _poisoned(y) and N.last_error():
         raise N.SpmvError(-2, N.last_error())
