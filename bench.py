@@ -416,14 +416,17 @@ def bench_single_gpu(args):
     for _ in range(2):
         A.spmv_host_ptr(xh.data_ptr(), yh.data_ptr())
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    e2e_each = []
+    for _ in range(e2e_steps):          # every call is synchronous: per-call times for the spread, the mean for the value
+        t_call = time.perf_counter()
         A.spmv_host_ptr(xh.data_ptr(), yh.data_ptr())
+        e2e_each.append(time.perf_counter() - t_call)
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     sampler.window(t0, time.perf_counter())
     torch.cuda.synchronize()
     assert torch.equal(yh.cuda(), y), "end-to-end result differs from the resident product"
     e2e = {"value": 2.0 * nnz / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * info.N, "d2h_bytes_per_step": 8 * M,
-           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "ms_min": min(e2e_each) * 1e3, "ms_median": statistics.median(e2e_each) * 1e3,
            "api": "spmv_b200_csr_spmv_host (one synchronous C-ABI call: pinned host x -> device, product, device -> pinned host y; upload, product and download pipelined over row windows on three streams)"}
     log(f"[bench] e2e: {e2e['value']:.1f} GFLOP/s ({e2e_s*1e3:.2f} ms/step)")
 
