@@ -10,9 +10,14 @@ N = 1  workload "lap2d_4096_csr" (BASELINE.json configs[1]): fp64 CSR product of
        (HLL of the same matrix, uniform 8M x 8M x 32 CSR/HLL, R-MAT, the 512^3 power iteration on one
        GPU) are measured too and reported under "others" -- they are not the headline.
 N > 1  workload "lap3d_512_power" (configs[4]): power iteration on the 512^3 7-point Laplacian,
-       rows partitioned by nnz over the N ranks, x refreshed every iteration ("halo" = only the
-       referenced column range, "allgather" = the whole vector; both reported).  A step is one
-       iteration (product + norm + scale + exchange); value = 2 * nnz_global / t, strong scaling.
+       rows partitioned by nnz over the N ranks, x refreshed every iteration.  Headline = "fused_split": boundary
+       rows stored into the neighbours over NVLink by the product kernel, |w|^2 through peer mailboxes, two
+       launches per iteration, no collective call.  Every other exchange is timed beside it under
+       "exchange_modes" (halo-only and whole-vector refreshes: "allgather" = one ncclAllGather, "allgather_peer"
+       = the same data movement written against peer memory; HLL twins; the one-launch forms) and every one of
+       them is parity-checked against the single-GPU iteration inside the run ("parity").  A step is one
+       iteration (product + norm + scale + exchange); value = 2 * nnz_global / t, strong scaling; "e2e" = the
+       same loop with lambda read back on the host after every iteration.
 
 --impl reference times the reference's own CPU implementation (oracle/_ref, built from the unmodified
 reference sources; the oracle port if that .so is absent) on the host cores, same workload and metric.
@@ -777,8 +782,11 @@ def bench_multi_gpu(args):
 
     modes = ("fused_mailbox", "fused_split", "fused_split_hll", "fused_mailbox_hll", "fused_mailbox_csr_hack_aligned", "fused_async", "fused_peer_stores",
              "fused_nccl_halo", "halo", "allgather_peer", "allgather_peer_2streams", "allgather_peer_hybrid", "allgather_peer_kernel", "allgather", "allgather_broadcasts")
+    extra_only = ("allgather_peer_2streams", "allgather_peer_hybrid")   # measured variants that lost: on request only
     if args.modes:
         modes = tuple(m for m in modes if m in args.modes.split(",") or m == HEAD_MODE)
+    else:
+        modes = tuple(m for m in modes if m not in extra_only)
     parity = {}
     for mode in modes:
         if mode == "fused_async":
