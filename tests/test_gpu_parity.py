@@ -787,7 +787,9 @@ def test_main_style_driver_writes_the_csv(dev, tmp_path):
     assert exe.exists(), "build() makes the driver next to the library"
     out_csv = tmp_path / "result_b200.csv"
     files = [str(GOLDEN / "mtx" / f"{n}.mtx") for n in ("general_matrix", "rand_symmetric_64x64", "rand_longrow_65x3000")]
-    run = subprocess.run([str(exe), "--csv", str(out_csv), "--iters", "7", "--warmup", "2", "--lap2d", "300", *files],
+    import torch
+    gpus = min(2, torch.cuda.device_count())
+    run = subprocess.run([str(exe), "--csv", str(out_csv), "--iters", "7", "--warmup", "2", "--gpus", str(gpus), "--lap2d", "300", *files],
                          capture_output=True, text=True)
     assert run.returncode == 0, run.stdout[-3000:] + run.stderr[-3000:]
     rows = list(csv.DictReader(open(out_csv)))
@@ -798,7 +800,17 @@ def test_main_style_driver_writes_the_csv(dev, tmp_path):
         for k in ("csr_auto", "csr_row", "csr_stream", "csr_vector", "csr_binned", "hll_auto", "hll_rows", "hll_stream", "hll_slice"):
             assert float(r[f"time_{k}"]) > 0 and float(r[f"flops_{k}"]) > 0
             assert float(r[f"relative_error_{k}"]) <= 1e-12 and float(r[f"absolute_error_{k}"]) <= 1e-9
-        assert float(r["time_e2e_csr_host"]) > 0 and r["ngpus"] == "1" and r["check_baseline"] == "gpu_serial_order_kernel"
+        assert float(r["time_e2e_csr_host"]) > 0 and r["check_baseline"] == "gpu_serial_order_kernel"
+    # --gpus N: the square matrices from files also went through spmv_b200_multi_* (product + 23 power iterations)
+    sym = rows[1]
+    assert 1 <= int(sym["ngpus"]) <= gpus and float(sym["time_multi_iteration"]) > 0 and float(sym["relative_error_multi_product"]) <= 1e-12
+    from oracle import oracle as O
+    port = O.Restated()
+    rp, ci, va = port.coo_to_csr(port.read_matrix_market(GOLDEN / "mtx" / "rand_symmetric_64x64.mtx"))
+    _, _, lam_ref = port.power_iteration(rp, ci, va, np.ones(64), 23)
+    assert abs(float(sym["lambda_multi"]) - lam_ref[-1]) <= 1e-11 * abs(lam_ref[-1])
+    assert rows[2]["ngpus"] == "1" and float(rows[2]["time_multi_iteration"]) == 0.0      # 65 x 3000: not square, skipped
+    assert float(rows[3]["time_multi_iteration"]) == 0.0                                   # generated on the device: no host arrays
 
 
 def test_short_rows_are_summed_in_serial_order_on_every_path(dev, checker):

@@ -12,8 +12,12 @@
  * time_* (mean seconds), flops_* (2 nz / t), gbs_* (algorithmic bytes / t), roofline_* (fraction of --peak-gbs)
  * and relative_/absolute_error_*; then the host-buffer (end-to-end) times.
  *
- * Usage: spmv_driver [--csv out.csv] [--iters 95] [--warmup 5] [--peak-gbs 8000] [--lap2d n] matrix.mtx ...
+ * Usage: spmv_driver [--csv out.csv] [--iters 95] [--warmup 5] [--peak-gbs 8000] [--gpus N] [--lap2d n] matrix.mtx ...
  *        --lap2d n  adds the 2-D 5-point Laplacian on an n x n grid, generated on the device (no file).
+ *        --gpus N   (N >= 1; square matrices from files) additionally runs the row-partitioned product and 20 power
+ *                   iterations on N GPUs through spmv_b200_multi_* (fused MAILBOX exchange when every row is short enough,
+ *                   else ALLGATHER_PEER): columns ngpus, time_multi_iteration, flops_multi_iteration, lambda_multi,
+ *                   relative_error_multi_product.  Without it those columns read 1, 0, 0, 0, 0.
  * Exit status: 0 ok, 1 usage / file error, 2 a result differs from the serial-order product, 3 no CUDA device.
  */
 #include <omp.h>
@@ -44,7 +48,13 @@ typedef struct {
     const char *csv;
     int iters, warmup;
     double peak_gbs;
+    int gpus;
 } Options;
+
+typedef struct {
+    int ngpus;              /* GPUs the partitioner actually used */
+    double time, flops, lambda, rel_err;
+} MultiRow;
 
 static int die_cuda(const char *what) {
     fprintf(stderr, "spmv_driver: %s: %s\n", what, spmv_b200_last_error());
@@ -52,7 +62,7 @@ static int die_cuda(const char *what) {
 }
 
 static void write_csv(const Options *opt, const char *matrix, int M, int N, long long nz, const KernelRow *k,
-                      double e2e_csr, double e2e_hll) {
+                      double e2e_csr, double e2e_hll, const MultiRow *multi) {
     FILE *fp = fopen(opt->csv, "a+");
     if (!fp) {
         printf("Errore nell'apertura del file %s\n", opt->csv);
@@ -66,7 +76,8 @@ static void write_csv(const Options *opt, const char *matrix, int M, int N, long
         for (int i = 0; i < K_COUNT; ++i) fprintf(fp, ",gbs_%s", kNames[i]);
         for (int i = 0; i < K_COUNT; ++i) fprintf(fp, ",roofline_%s", kNames[i]);
         for (int i = 0; i < K_COUNT; ++i) fprintf(fp, ",relative_error_%s,absolute_error_%s", kNames[i], kNames[i]);
-        fprintf(fp, ",time_e2e_csr_host,time_e2e_hll_host,peak_gbs,ngpus,check_baseline\n");
+        fprintf(fp, ",time_e2e_csr_host,time_e2e_hll_host,peak_gbs,ngpus,check_baseline");
+        fprintf(fp, ",time_multi_iteration,flops_multi_iteration,lambda_multi,relative_error_multi_product\n");
     }
     fprintf(fp, "%s,%d,%d,%lld", matrix, M, N, nz);
     for (int i = 0; i < K_COUNT; ++i) fprintf(fp, ",%.15f", k[i].time);
@@ -76,12 +87,14 @@ static void write_csv(const Options *opt, const char *matrix, int M, int N, long
     for (int i = 0; i < K_COUNT; ++i) fprintf(fp, ",%.15f,%.15f", k[i].err.mean_rel_err, k[i].err.mean_abs_err);
     /* the error columns compare with this library's one-thread-per-row kernel in the reference's summation order (bit-identical
      * to csr_matrix_vector_mult, tests/test_gpu_parity.py) -- NOT with a CPU product: the library has no CPU path */
-    fprintf(fp, ",%.15f,%.15f,%.1f,1,gpu_serial_order_kernel\n", e2e_csr, e2e_hll, opt->peak_gbs);
+    fprintf(fp, ",%.15f,%.15f,%.1f,%d,gpu_serial_order_kernel", e2e_csr, e2e_hll, opt->peak_gbs, multi ? multi->ngpus : 1);
+    fprintf(fp, ",%.15f,%.15f,%.15g,%.15g\n", multi ? multi->time : 0.0, multi ? multi->flops : 0.0, multi ? multi->lambda : 0.0,
+            multi ? multi->rel_err : 0.0);
     fclose(fp);
 }
 
 /* everything after the matrix is resident: timing, checks, report */
-static int run_resident(const Options *opt, const char *name, spmv_b200_csr *A, spmv_b200_hll *H) {
+static int run_resident(const Options *opt, const char *name, spmv_b200_csr *A, spmv_b200_hll *H, const CSRMatrix *host) {
     spmv_b200_csr_info_t ci;
     spmv_b200_hll_info_t hi;
     if (spmv_b200_csr_info(A, &ci) || spmv_b200_hll_info(H, &hi)) return die_cuda("info");
@@ -155,7 +168,42 @@ static int run_resident(const Options *opt, const char *name, spmv_b200_csr *A, 
         printf("%-11s mean %.6f s (host x -> device, product, device -> host y)  diffs %d\n", f ? "hll_host" : "csr_host", e2e[f],
                d.significant_diffs);
     }
-    if (opt->csv) write_csv(opt, name, M, N, ci.nnz, k, e2e[0], e2e[1]);
+    /* N GPUs of this box through the single-process entry points (spmv_b200_multi_*): the row-partitioned product against
+     * the same serial-order baseline, then the power method (y = A x; lambda = |y|; x = y / lambda) */
+    MultiRow multi = {1, 0.0, 0.0, 0.0, 0.0};
+    int have_multi = 0;
+    if (opt->gpus >= 1 && host && M == N && M > 0) {
+        spmv_b200_multi *ctx = NULL;
+        spmv_b200_multi_info_t mi;
+        rc = spmv_b200_multi_init_csr(opt->gpus, SPMV_B200_FORMAT_CSR, host->M, host->N, host->nz, host->row_ptr, host->col_idx,
+                                      host->values, &ctx);
+        if (!rc) rc = spmv_b200_multi_info(ctx, &mi);
+        if (!rc) rc = spmv_b200_multi_spmv(ctx, x, y);
+        if (!rc) {
+            DiffMetrics d = computeDifferenceMetrics(y_ref, y, M, 1e-5, 1e-4, false);
+            if (d.significant_diffs) bad = 1;
+            multi.rel_err = d.mean_rel_err;
+            multi.ngpus = mi.ngpus;
+            const int mode = mi.fused_ok ? SPMV_B200_EXCHANGE_MAILBOX : SPMV_B200_EXCHANGE_ALLGATHER_PEER;
+            double ms = 0.0;
+            rc = spmv_b200_multi_reset(ctx, NULL);
+            if (!rc) rc = spmv_b200_multi_iterate(ctx, 3, mode, NULL, NULL); /* warm-up */
+            if (!rc) rc = spmv_b200_multi_iterate(ctx, 20, mode, &multi.lambda, &ms);
+            multi.time = ms * 1e-3;
+            multi.flops = calculate_flops((int)ci.nnz, multi.time);
+            have_multi = !rc;
+            if (!rc)
+                printf("%d GPU(s)    product rel.err %.3g diffs %d; power iteration (%s) %.6f s / iteration, lambda %.12g  ", mi.ngpus,
+                       d.mean_rel_err, d.significant_diffs, mi.fused_ok ? "fused mailbox exchange" : "peer all-gather", multi.time, multi.lambda);
+            if (!rc) print_flops(multi.flops);
+        }
+        spmv_b200_multi_free(ctx);
+        if (rc) {
+            free(x), free(y_ref), free(y);
+            return die_cuda("multi-GPU run");
+        }
+    }
+    if (opt->csv) write_csv(opt, name, M, N, ci.nnz, k, e2e[0], e2e[1], have_multi ? &multi : NULL);
     free(x), free(y_ref), free(y);
     return bad ? 2 : 0;
 }
@@ -180,7 +228,7 @@ static int run_file(const Options *opt, const char *path) {
         status = die_cuda("upload");
         goto out;
     }
-    status = run_resident(opt, base, A, H);
+    status = run_resident(opt, base, A, H, &csr);
 out:
     spmv_b200_hll_free(H);
     spmv_b200_csr_free(A);
@@ -200,14 +248,14 @@ static int run_lap2d(const Options *opt, int n) {
         spmv_b200_hll_from_csr(A, NULL, &H))
         status = die_cuda("synthetic matrix");
     else
-        status = run_resident(opt, name, A, H);
+        status = run_resident(opt, name, A, H, NULL);
     spmv_b200_hll_free(H);
     spmv_b200_csr_free(A);
     return status;
 }
 
 int main(int argc, char **argv) {
-    Options opt = {NULL, DEFAULT_ITERS, ITERATION_SKIP, 8000.0};
+    Options opt = {NULL, DEFAULT_ITERS, ITERATION_SKIP, 8000.0, 0};
     int lap2d[8], nlap = 0, status = 0, ran = 0;
     initialize_metrics();
     for (int i = 1; i < argc; ++i) {
@@ -215,9 +263,10 @@ int main(int argc, char **argv) {
         else if (!strcmp(argv[i], "--iters") && i + 1 < argc) opt.iters = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--warmup") && i + 1 < argc) opt.warmup = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--peak-gbs") && i + 1 < argc) opt.peak_gbs = atof(argv[++i]);
+        else if (!strcmp(argv[i], "--gpus") && i + 1 < argc) opt.gpus = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--lap2d") && i + 1 < argc && nlap < 8) lap2d[nlap++] = atoi(argv[++i]);
         else if (argv[i][0] == '-') {
-            fprintf(stderr, "usage: %s [--csv out.csv] [--iters 95] [--warmup 5] [--peak-gbs 8000] [--lap2d n] matrix.mtx ...\n", argv[0]);
+            fprintf(stderr, "usage: %s [--csv out.csv] [--iters 95] [--warmup 5] [--peak-gbs 8000] [--gpus N] [--lap2d n] matrix.mtx ...\n", argv[0]);
             return 1;
         }
     }
@@ -233,7 +282,7 @@ int main(int argc, char **argv) {
     }
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "--csv") || !strcmp(argv[i], "--iters") || !strcmp(argv[i], "--warmup") ||
-            !strcmp(argv[i], "--peak-gbs") || !strcmp(argv[i], "--lap2d")) {
+            !strcmp(argv[i], "--peak-gbs") || !strcmp(argv[i], "--lap2d") || !strcmp(argv[i], "--gpus")) {
             ++i;
             continue;
         }
