@@ -526,14 +526,31 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler, head):
         x32, y32 = x2d.to(torch.float32), torch.empty(y2d.numel(), dtype=torch.float32, device="cuda")
         ia = A2d.info()
         run("lap2d_4096_csr_f32", lambda: A2d.spmv_f32(x32, y32), ia.nnz, A2d.algorithmic_bytes_f32(),
-            {"dtype": "f32 storage (values, x, y), f64 arithmetic", "bytes_formula": "8 nnz + 4 (M+1) + 4 M + 4 N"})
+            {"dtype": "f32 storage (values, x, y), f64 arithmetic", "bytes_formula": "8 nnz + 4 (M+1) + 4 M + 4 N",
+             "kernel": A2d.row_form_f32()})
         A2d.spmv(x2d, y2d)
         out["lap2d_4096_csr_f32"]["max_rel_diff_vs_f64"] = float(((y32.double() - y2d).abs() / (8.0 * 1.75)).max().item())
+        y32_multi = y32.clone()
         H32 = A2d.to_hll().enable_f32()
         run("lap2d_4096_hll_f32", lambda: H32.spmv_f32(x32, y32), ia.nnz, H32.algorithmic_bytes_f32(),
-            {"dtype": "f32 storage (values, x, y), f64 arithmetic"})
+            {"dtype": "f32 storage (values, x, y), f64 arithmetic", "kernel": H32.row_form_f32()})
+        # the same with the plan-time choice restricted to the one-row-per-thread forms (the round-1 / 2d kernels): what
+        # the multi-row forms buy, on the same box in the same run; results must be bitwise equal
+        os.environ["SPMV_B200_ROW_MULTI_TUNE"] = "0"
+        try:
+            A1 = device.DeviceCSR.synth(synth.SYNTH_LAP2D, 4096).enable_f32()
+            run("lap2d_4096_csr_f32_one_row_forms", lambda: A1.spmv_f32(x32, y32), ia.nnz, A1.algorithmic_bytes_f32(),
+                {"kernel": A1.row_form_f32()})
+            out["lap2d_4096_csr_f32"]["bitwise_equal_to_one_row_form"] = bool(torch.equal(y32, y32_multi))
+            H1 = A1.to_hll().enable_f32()
+            run("lap2d_4096_hll_f32_one_row_forms", lambda: H1.spmv_f32(x32, y32), ia.nnz, H1.algorithmic_bytes_f32(),
+                {"kernel": H1.row_form_f32()})
+            H1.close()
+            A1.close()
+        finally:
+            del os.environ["SPMV_B200_ROW_MULTI_TUNE"]
         H32.close()
-        del x32, y32
+        del x32, y32, y32_multi
     except Exception as e:  # pragma: no cover
         out["lap2d_4096_csr_f32"] = {"error": repr(e)}
         log(f"[bench] fp32 leg failed: {e!r}")

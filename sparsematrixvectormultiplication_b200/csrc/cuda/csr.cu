@@ -270,6 +270,80 @@ csr_row_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, cons
     y[row] = (V)acc;
 }
 
+// csr_row_kernel with ROWS rows per thread (round 2e; fp32 storage).  The thread-per-row kernel is LATENCY bound once
+// the rows get lighter: a row is three dependent round trips (row_ptr -> columns / values -> x) and an SM cannot hold
+// more than 2048 threads, so with fp32 values (52 instead of 80 bytes per 5-point row) 2048 rows in flight no longer
+// cover the HBM latency (ncu: nothing saturated, DRAM at 68 %).  Here a thread owns rows t, t + 256, ... of its CTA's
+// 256*ROWS rows (a warp still reads 32 consecutive rows per instruction) and CTAS CTAs share an SM (register budget
+// 65536 / (256 CTAS)): the trips of ROWS rows overlap inside one thread, 256*CTAS*ROWS rows in flight per SM.
+// Second difference: slots past the end of a row gather x[0] (always a valid address here: the loop only runs when the
+// matrix has a nonzero) instead of being predicated on the LOADED column -- every predicate is then index arithmetic,
+// and ptxas issues all loads of a step before the first multiply (cuobjdump: 34 / 34 loads ahead of the first DMUL for
+// <5, 2, float, 5>; the one-row kernels issue 9-12 of 17 and stall on the first gather before requesting the rest).
+// Every row is still summed by one lane in index order, mul and add rounded separately, padding slots skipped: the
+// same bits as csr_row_kernel.  Which (ROWS, BATCH, CTAS) runs is timed at plan time (kRowmVariants).
+template <int BATCH, int ROWS, int CTAS, typename V>
+__global__ void __launch_bounds__(256, CTAS)
+csr_rowm_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                const V *__restrict__ values, const V *__restrict__ x, V *__restrict__ y, int accumulate) {
+    const long long first = row_begin + (long long)blockIdx.x * (256 * ROWS) + threadIdx.x;
+    int lo[ROWS], hi[ROWS];
+    double acc[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const long long row = first + (long long)r * 256;
+        const bool live = row < row_end;
+        lo[r] = live ? __ldg(row_ptr + row) : 0;
+        hi[r] = live ? __ldg(row_ptr + row + 1) : 0;
+    }
+    int longest = 0;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const long long row = first + (long long)r * 256;
+        acc[r] = accumulate && row < row_end ? (double)y[row] : 0.0;
+        longest = max(longest, hi[r] - lo[r]);
+    }
+    for (int s = 0; s < longest; s += BATCH) {
+        int c[ROWS][BATCH];
+        V v[ROWS][BATCH], xv[ROWS][BATCH];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) c[r][u] = lo[r] + s + u < hi[r] ? __ldg(col_idx + lo[r] + s + u) : 0;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) v[r][u] = lo[r] + s + u < hi[r] ? __ldg(values + lo[r] + s + u) : (V)0;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) xv[r][u] = __ldg(x + c[r][u]);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u)
+                if (lo[r] + s + u < hi[r]) acc[r] = __dadd_rn(acc[r], __dmul_rn((double)v[r][u], (double)xv[r][u]));
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const long long row = first + (long long)r * 256;
+        if (row < row_end) y[row] = (V)acc[r];
+    }
+}
+
+// (ROWS, BATCH, CTAS per SM) forms of csr_rowm_kernel offered to the plan-time tuner; chosen from the ptxas / SASS
+// survey of tools/rowm_survey.py: no or negligible spills, all loads of a step ahead of the first multiply.
+struct RowmVariant {
+    int rows, batch, ctas;
+};
+#define SPMV_ROWM_VARIANTS(X) \
+    X(2, 3, 5) X(2, 3, 6) X(2, 4, 5) X(2, 5, 5) X(2, 5, 4) X(2, 6, 4) X(2, 7, 4) \
+    X(3, 3, 5) X(3, 3, 4) X(3, 4, 4) X(3, 5, 4) X(3, 5, 3) X(4, 3, 4) X(4, 4, 4)
+#define ROWM_ENTRY(R, B, C) {R, B, C},
+static const RowmVariant kRowmVariants[] = {SPMV_ROWM_VARIANTS(ROWM_ENTRY)};
+#undef ROWM_ENTRY
+constexpr int kNumRowmVariants = (int)(sizeof kRowmVariants / sizeof kRowmVariants[0]);
+
 // csr_row_kernel with the tail of the two-launch iterated product (spmv_b200_csr_spmv_fused_flat): one thread per row,
 // one CTA per 256 rows, NO chunk walk and no waiting -- the body of the plain kernel, then: multiply by 1/|w_prev| (read
 // from memory, computed once by the exchange kernel), store, mirror boundary rows into the peers, one partial sum of
@@ -1050,8 +1124,25 @@ static int launch_rows(int row_begin, int row_end, const int *row_ptr, const int
                        const V *x, V *y, int batch, int accumulate, cudaStream_t stream) {
     const long long rows = (long long)row_end - row_begin;
     if (rows <= 0) return SPMV_B200_OK;
-    const unsigned int g = blocks_for(rows, 256);
     const XPolicy keep = matrix_policy(row_ptr + row_begin, (size_t)(rows + 1) * sizeof(int));
+    // batch >= 16: csr_rowm_kernel, form kRowmVariants[batch - 16].  SPMV_B200_ROW_MULTI=k (k >= 1) sends EVERY row-kernel
+    // launch through form k - 1 (parity runs: tests/test_gpu_parity.py walks all forms, fp64 bit for bit)
+    const int forced_multi = env_int("SPMV_B200_ROW_MULTI", 0);
+    const int variant = forced_multi >= 1 ? std::min(forced_multi, kNumRowmVariants) - 1 : batch - 16;
+    if (variant >= 0) {
+        if (variant >= kNumRowmVariants) return fail(SPMV_B200_ERR_INVALID, "row kernel: unknown multi-row form %d", variant);
+        const unsigned int gm = blocks_for(rows, 256 * kRowmVariants[variant].rows);
+        int at = 0;
+#define ROWM_CASE(R, B, C)                                                                                                    \
+    if (at++ == variant)                                                                                                      \
+        SPMV_TRY_CUDA(launch_x(csr_rowm_kernel<B, R, C, V>, gm, 256, 0, stream, keep, row_begin, row_end, row_ptr, col_idx, values, x, \
+                               y, accumulate));
+        SPMV_ROWM_VARIANTS(ROWM_CASE)
+#undef ROWM_CASE
+        SPMV_TRY_CUDA(cudaGetLastError());
+        return SPMV_B200_OK;
+    }
+    const unsigned int g = blocks_for(rows, 256);
 #define ROW_CASE(B) case B: SPMV_TRY_CUDA(launch_x(csr_row_kernel<B, V>, g, 256, 0, stream, keep, row_begin, row_end, row_ptr, col_idx, values, x, y, accumulate)); break;
     switch (batch) {
         ROW_CASE(1) ROW_CASE(2) ROW_CASE(3) ROW_CASE(5) ROW_CASE(6) ROW_CASE(7) ROW_CASE(8)
@@ -1782,10 +1873,20 @@ int spmv_b200_csr_enable_f32(spmv_b200_csr *A, void *stream) {
     A->row_batch32 = A->row_batch;
     if (A->max_row <= kRowKernelMaxLen && A->nnz >= kAutotuneMinNnz && env_int("SPMV_B200_AUTOTUNE", 1) &&
         env_int("SPMV_B200_ROW_BATCH", 0) == 0) {  // the best batch differs with the element size: time it again
-        A->row_batch32 = tune_batch(A->M, A->N, A->row_batch, as_stream(stream), [&](int batch, double *x, double *y) {
+        // candidates: one row per thread with batch 2..7, and the multi-row forms (csr_rowm_kernel, ids >= 16); all give
+        // the same bits.  SPMV_B200_ROW_MULTI_TUNE=0 keeps the one-row forms only.
+        int ids[8 + kNumRowmVariants], n = 0, fallback = 0;
+        for (int batch = 2; batch <= 7; ++batch) {
+            if (batch == A->row_batch) fallback = n;
+            ids[n++] = batch;
+        }
+        if (env_int("SPMV_B200_ROW_MULTI_TUNE", 1))
+            for (int v = 0; v < kNumRowmVariants; ++v) ids[n++] = 16 + v;
+        const int pick = tune_candidates(A->M, A->N, n, fallback, as_stream(stream), [&](int i, double *x, double *y) {
             return launch_rows<float>(0, A->M, A->row_ptr, A->col_idx, A->values32, reinterpret_cast<const float *>(x),
-                                      reinterpret_cast<float *>(y), batch, 0, as_stream(stream));
+                                      reinterpret_cast<float *>(y), ids[i], 0, as_stream(stream));
         });
+        A->row_batch32 = ids[pick];
     }
     return SPMV_B200_OK;
 }
@@ -1811,6 +1912,29 @@ int spmv_b200_csr_spmv_f32(const spmv_b200_csr *A, const float *d_x, float *d_y,
         return launch_vector<float>(0, A->M, A->row_ptr, A->col_idx, A->values32, d_x, d_y, pick_vector_width(A->nnz, A->M), accumulate, s,
                                     (size_t)A->N * sizeof(float), safe_vector_nnz(A));
     return launch_binned<float>(A, A->values32, d_x, d_y, accumulate, s);
+}
+
+int spmv_b200_csr_row_form_f32(const spmv_b200_csr *A) { return A && A->values32 ? A->row_batch32 : 0; }
+
+int spmv_b200_row_forms(int format) {
+    if (format == SPMV_B200_FORMAT_CSR) return kNumRowmVariants;
+    if (format == SPMV_B200_FORMAT_HLL) return hll_row_forms();
+    return 0;
+}
+
+int spmv_b200_row_form_describe(int format, int index, int *rows_per_thread, int *batch, int *ctas_per_sm) {
+    int rows = 0, b = 0, ctas = 0;
+    if (format == SPMV_B200_FORMAT_CSR && index >= 0 && index < kNumRowmVariants) {
+        rows = kRowmVariants[index].rows;
+        b = kRowmVariants[index].batch;
+        ctas = kRowmVariants[index].ctas;
+    } else if (format != SPMV_B200_FORMAT_HLL || hll_row_form(index, &rows, &b, &ctas) != 0) {
+        return fail(SPMV_B200_ERR_INVALID, "row_form_describe: no form %d of format %d", index, format);
+    }
+    if (rows_per_thread) *rows_per_thread = rows;
+    if (batch) *batch = b;
+    if (ctas_per_sm) *ctas_per_sm = ctas;
+    return SPMV_B200_OK;
 }
 
 int spmv_b200_csr_spmv_host_f32(spmv_b200_csr *A, const float *x, float *y) {

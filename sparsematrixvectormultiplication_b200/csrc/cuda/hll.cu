@@ -120,6 +120,84 @@ hll_row_kernel(int hack_begin, int hack_end, const long long *__restrict__ hack_
     if (row < M) y[row] = (V)acc;
 }
 
+// hll_row_kernel with HACKS consecutive hacks per warp (round 2e; fp32 storage): the lane-per-row kernel is latency bound
+// once the rows get lighter (hack_off -> JA / AS -> x are dependent round trips and an SM holds at most 2048 lanes; ncu on
+// the fp32 image: DRAM 58 %, nothing saturated).  CTAS CTAs per SM (register budget 65536 / (256 CTAS)), every lane owns
+// row `lane` of HACKS hacks and keeps their trips in flight together; slots past the width of a hack gather x[0] instead
+// of being predicated on the loaded column, so that every predicate is index arithmetic and ptxas issues all loads of a
+// step ahead of the first multiply (see csr_rowm_kernel).  Order of the sums unchanged, skipped slots skipped: the same
+// bits as hll_row_kernel.  Which (HACKS, BATCH, CTAS) runs is timed at plan time (kHllRowmVariants).
+template <int BATCH, int HACKS, int CTAS, typename V>
+__global__ void __launch_bounds__(256, CTAS)
+hll_rowm_kernel(int hack_begin, int hack_end, const long long *__restrict__ hack_off, const int *__restrict__ JA,
+                const V *__restrict__ AS, const V *__restrict__ x, V *__restrict__ y, int M) {
+    const int first = hack_begin + (blockIdx.x * 8 + (threadIdx.x >> 5)) * HACKS;
+    if (first >= hack_end) return;  // warp-uniform
+    const int lane = threadIdx.x & 31;
+    long long off[HACKS + 1];
+#pragma unroll
+    for (int h = 0; h <= HACKS; ++h) off[h] = __ldg(hack_off + min(first + h, hack_end));
+    int width[HACKS], widest = 0;
+    double acc[HACKS];
+#pragma unroll
+    for (int h = 0; h < HACKS; ++h) {
+        width[h] = first + h < hack_end ? (int)((off[h + 1] - off[h]) >> 5) : 0;
+        widest = max(widest, width[h]);
+        acc[h] = 0.0;
+    }
+    for (int j = 0; j < widest; j += BATCH) {
+        int c[HACKS][BATCH];
+        double v[HACKS][BATCH], xv[HACKS][BATCH];
+#pragma unroll
+        for (int h = 0; h < HACKS; ++h)
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u)
+                c[h][u] = j + u < width[h] ? ldg_stream_s32(JA + off[h] + lane + (long long)(j + u) * kHack) : 0;
+#pragma unroll
+        for (int h = 0; h < HACKS; ++h)
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u)
+                v[h][u] = j + u < width[h] ? ldg_stream_f64(AS + off[h] + lane + (long long)(j + u) * kHack) : 0.0;
+#pragma unroll
+        for (int h = 0; h < HACKS; ++h)
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) xv[h][u] = ldg_x(x, c[h][u]);
+#pragma unroll
+        for (int h = 0; h < HACKS; ++h)
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u)
+                if (j + u < width[h]) acc[h] = __dadd_rn(acc[h], __dmul_rn(v[h][u], xv[h][u]));
+    }
+#pragma unroll
+    for (int h = 0; h < HACKS; ++h) {
+        const long long row = (long long)(first + h) * kHack + lane;
+        if (first + h < hack_end && row < M) y[row] = (V)acc[h];
+    }
+}
+
+// (HACKS, BATCH, CTAS per SM) forms of hll_rowm_kernel offered to the plan-time tuner (tools/rowm_survey.py: no or
+// negligible spills, all loads of a step ahead of the first multiply); HACKS = 1 is the plain shape with the
+// index-only predicates.
+struct HllRowmVariant {
+    int hacks, batch, ctas;
+};
+#define SPMV_HLL_ROWM_VARIANTS(X) \
+    X(1, 4, 8) X(1, 5, 8) X(2, 3, 6) X(2, 3, 5) X(2, 4, 5) X(2, 4, 4) X(2, 5, 4) X(2, 7, 3) \
+    X(3, 3, 4) X(3, 4, 3) X(3, 5, 3) X(4, 3, 3)
+#define HROWM_ENTRY(H, B, C) {H, B, C},
+static const HllRowmVariant kHllRowmVariants[] = {SPMV_HLL_ROWM_VARIANTS(HROWM_ENTRY)};
+#undef HROWM_ENTRY
+constexpr int kNumHllRowmVariants = (int)(sizeof kHllRowmVariants / sizeof kHllRowmVariants[0]);
+
+int hll_row_forms() { return kNumHllRowmVariants; }
+int hll_row_form(int index, int *hacks, int *batch, int *ctas) {
+    if (index < 0 || index >= kNumHllRowmVariants) return -1;
+    *hacks = kHllRowmVariants[index].hacks;
+    *batch = kHllRowmVariants[index].batch;
+    *ctas = kHllRowmVariants[index].ctas;
+    return 0;
+}
+
 // hll_row_kernel with the tail of the two-launch iterated product (spmv_b200_hll_spmv_fused_flat): one warp per hack, one
 // CTA per 8 hacks = 256 rows, no chunk walk and no waiting -- the body of the plain kernel, then scale by 1/|w_prev| (read
 // from memory), store, mirror boundary rows, one partial sum of squares per CTA (see csr_row_flat_kernel).  Thread t of
@@ -290,8 +368,25 @@ static int hll_launch_rows_t(const spmv_b200_hll *H, const V *AS, int hack_begin
                              cudaStream_t stream, int batch = -1) {
     if (hack_end <= hack_begin) return SPMV_B200_OK;
     if (batch < 0) batch = sizeof(V) == 4 ? H->row_batch32 : H->row_batch;
-    const unsigned int g = blocks_for(hack_end - hack_begin, 8);
     const XPolicy keep = matrix_policy(H->JA, (size_t)H->slots * sizeof(int));   // head of JA held in L2 across products
+    // batch >= 16: hll_rowm_kernel, form kHllRowmVariants[batch - 16].  SPMV_B200_ROW_MULTI=k (k >= 1) sends EVERY
+    // row-kernel launch through form k - 1 (parity runs: tests/test_gpu_parity.py walks all forms, fp64 bit for bit)
+    const int forced_multi = env_int("SPMV_B200_ROW_MULTI", 0);
+    const int variant = forced_multi >= 1 ? std::min(forced_multi, kNumHllRowmVariants) - 1 : batch - 16;
+    if (variant >= 0) {
+        if (variant >= kNumHllRowmVariants) return fail(SPMV_B200_ERR_INVALID, "hll row kernel: unknown multi-hack form %d", variant);
+        const unsigned int gm = blocks_for(hack_end - hack_begin, 8 * kHllRowmVariants[variant].hacks);
+        int at = 0;
+#define HROWM_CASE(R, B, C)                                                                                                  \
+    if (at++ == variant)                                                                                                     \
+        SPMV_TRY_CUDA(launch_x(hll_rowm_kernel<B, R, C, V>, gm, 256, 0, stream, keep, hack_begin, hack_end, H->hack_off, H->JA, AS, \
+                               d_x, d_y, H->M));
+        SPMV_HLL_ROWM_VARIANTS(HROWM_CASE)
+#undef HROWM_CASE
+        SPMV_TRY_CUDA(cudaGetLastError());
+        return SPMV_B200_OK;
+    }
+    const unsigned int g = blocks_for(hack_end - hack_begin, 8);
 #define HROW_CASE(B) case B: SPMV_TRY_CUDA(launch_x(hll_row_kernel<B, V>, g, 256, 0, stream, keep, hack_begin, hack_end, H->hack_off, H->JA, AS, d_x, d_y, H->M)); break;
     switch (batch) {
         HROW_CASE(1) HROW_CASE(2) HROW_CASE(3) HROW_CASE(5) HROW_CASE(6) HROW_CASE(7) HROW_CASE(8)
@@ -782,10 +877,20 @@ int spmv_b200_hll_enable_f32(spmv_b200_hll *H, void *stream) {
     H->row_batch32 = H->row_batch;
     if (H->max_width <= kRowKernelMaxLen && H->slots >= (1 << 22) && env_int("SPMV_B200_AUTOTUNE", 1) &&
         env_int("SPMV_B200_HLL_ROW_BATCH", 0) == 0) {
-        H->row_batch32 = tune_batch(H->M, H->N, H->row_batch, as_stream(stream), [&](int batch, double *x, double *y) {
+        // candidates: one hack per warp with batch 2..7, and the forms of hll_rowm_kernel (ids >= 16); all give the same
+        // bits.  SPMV_B200_ROW_MULTI_TUNE=0 keeps the one-hack forms only.
+        int ids[8 + kNumHllRowmVariants], n = 0, fallback = 0;
+        for (int batch = 2; batch <= 7; ++batch) {
+            if (batch == H->row_batch) fallback = n;
+            ids[n++] = batch;
+        }
+        if (env_int("SPMV_B200_ROW_MULTI_TUNE", 1))
+            for (int v = 0; v < kNumHllRowmVariants; ++v) ids[n++] = 16 + v;
+        const int pick = tune_candidates(H->M, H->N, n, fallback, as_stream(stream), [&](int i, double *x, double *y) {
             return hll_launch_rows_t<float>(H, H->AS32, 0, H->num_hacks, reinterpret_cast<const float *>(x),
-                                            reinterpret_cast<float *>(y), as_stream(stream), batch);
+                                            reinterpret_cast<float *>(y), as_stream(stream), ids[i]);
         });
+        H->row_batch32 = ids[pick];
     }
     return SPMV_B200_OK;
 }
@@ -800,6 +905,8 @@ int spmv_b200_hll_spmv_f32(const spmv_b200_hll *H, const float *d_x, float *d_y,
                            H->M));
     return SPMV_B200_OK;
 }
+
+int spmv_b200_hll_row_form_f32(const spmv_b200_hll *H) { return H && H->AS32 ? H->row_batch32 : 0; }
 
 int spmv_b200_hll_spmv_host_f32(spmv_b200_hll *H, const float *x, float *y) {
     if (!H || (H->M > 0 && !y) || (H->N > 0 && H->slots > 0 && !x)) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_host_f32: NULL argument");

@@ -40,6 +40,28 @@ def _check_vec(t, n, what):
         raise ValueError(f"{what} must be a contiguous float64 CUDA tensor with at least {n} elements")
 
 
+FORMAT_CSR, FORMAT_HLL = 0, 1
+
+
+def row_forms(fmt: int):
+    """The multi-row forms of the row kernels, [(rows per thread | hacks per warp, batch, CTAs per SM), ...]: form k is
+    what SPMV_B200_ROW_MULTI=k+1 forces and what id 16+k of spmv_b200_{csr,hll}_row_form_f32 names."""
+    out = []
+    for k in range(N.lib().spmv_b200_row_forms(fmt)):
+        r, b, c = C.c_int(), C.c_int(), C.c_int()
+        N.check(N.lib().spmv_b200_row_form_describe(fmt, k, C.byref(r), C.byref(b), C.byref(c)))
+        out.append((r.value, b.value, c.value))
+    return out
+
+
+def row_form_name(fmt: int, form: int) -> str:
+    base = "csr_row" if fmt == FORMAT_CSR else "hll_row"
+    if form >= 16:
+        r, b, c = row_forms(fmt)[form - 16]
+        return f"{base}m_kernel<{b},{r},{c},float>"
+    return f"{base}_kernel<{form},float>" if form > 0 else "none"
+
+
 def device_count() -> int:
     n = C.c_int()
     N.lib().spmv_b200_device_count(C.byref(n))
@@ -221,6 +243,10 @@ class DeviceCSR:
         N.check(N.lib().spmv_b200_csr_enable_f32(self._h, _stream(stream)))
         return self
 
+    def row_form_f32(self) -> str:
+        """Name of the row kernel enable_f32 timed fastest for this matrix (spmv_b200_csr_row_form_f32)."""
+        return row_form_name(FORMAT_CSR, N.lib().spmv_b200_csr_row_form_f32(self._h))
+
     def spmv_f32(self, x, y, accumulate=False, algo=ALGO_AUTO, stream=None):
         """y = A x on float32 CUDA tensors (float values, x, y; products and sums in double)."""
         N.check(N.lib().spmv_b200_csr_spmv_f32(self._h, _ptr(x), _ptr(y), int(bool(accumulate)), algo, _stream(stream)))
@@ -306,6 +332,9 @@ class DeviceHLL:
     def enable_f32(self, stream=None):
         N.check(N.lib().spmv_b200_hll_enable_f32(self._h, _stream(stream)))
         return self
+
+    def row_form_f32(self) -> str:
+        return row_form_name(FORMAT_HLL, N.lib().spmv_b200_hll_row_form_f32(self._h))
 
     def spmv_f32(self, x, y, stream=None):
         N.check(N.lib().spmv_b200_hll_spmv_f32(self._h, _ptr(x), _ptr(y), _stream(stream)))

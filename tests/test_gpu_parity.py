@@ -992,6 +992,78 @@ def test_fp32_path_within_1e_5(dev, checker, kind):
         B.spmv_f32(x32, yacc)                            # enable_f32 not called
 
 
+def test_multi_row_forms_give_the_bits_of_the_one_row_kernels(dev, checker, monkeypatch):
+    """Every (rows per thread | hacks per warp, batch, CTAs per SM) form of csr_rowm_kernel / hll_rowm_kernel, forced
+    through SPMV_B200_ROW_MULTI (read at every launch): fp64 results bit for bit the reference's serial loop
+    (src/csr_matrix.c:134-138) on ragged rows -- empty, 1..12 and a few longer ones, a row count that is no multiple of
+    256 * rows, the whole matrix, row windows and accumulate -- and fp32 results bit for bit those of the one-row fp32
+    kernel; HLL forms against the lane-per-row kernel (itself pinned to spmv_hll_serial by the tests above)."""
+    import torch
+    rng = np.random.default_rng(77)
+    cases = []
+    M, N = 9001, 7000
+    lengths = rng.choice([0, 1, 3, 5, 6, 7, 12, 13, 40], size=M, p=[.08, .1, .2, .25, .1, .1, .1, .05, .02])
+    lengths[-3:] = [12, 0, 7]
+    cases.append((M, N, lengths))
+    cases.append((1, 5, np.array([3])))
+    cases.append((300, 300, np.zeros(300, np.int64)))            # no nonzero at all: x is never read
+    cases.append((777, 64, rng.integers(4, 8, 777)))             # stencil-like: every form in its intended regime
+    csr_forms, hll_forms = dev.row_forms(dev.FORMAT_CSR), dev.row_forms(dev.FORMAT_HLL)
+    assert len(csr_forms) >= 8 and len(hll_forms) >= 8
+    for M, N, lengths in cases:
+        rp = np.zeros(M + 1, np.int32)
+        np.cumsum(lengths, out=rp[1:])
+        ci = (np.concatenate([np.sort(rng.choice(N, n, replace=False)) for n in lengths]).astype(np.int32)
+              if rp[-1] else np.zeros(0, np.int32))
+        va = rng.standard_normal(rp[-1])
+        x = rng.standard_normal(N)
+        y_ref = checker.spmv_csr_serial(rp, ci, va, x)
+        acc0 = rng.standard_normal(M)
+        A = dev.DeviceCSR.upload(M, N, rp, ci, va).enable_f32()
+        H = A.to_hll().enable_f32()
+        xd = torch.from_numpy(x).cuda()
+        x32 = xd.float()
+        monkeypatch.delenv("SPMV_B200_ROW_MULTI", raising=False)
+
+        def products():
+            out = {}
+            y = torch.full((M,), float("nan"), dtype=torch.float64, device="cuda")
+            A.spmv(xd, y, algo=dev.ALGO_ROW)
+            out["csr"] = y.cpu().numpy()
+            y = torch.from_numpy(acc0.copy()).cuda()
+            A.spmv(xd, y, accumulate=True, algo=dev.ALGO_ROW)
+            out["csr accumulate"] = y.cpu().numpy()
+            y = torch.full((M,), float("nan"), dtype=torch.float64, device="cuda")
+            lo, hi = M // 3, max(M // 3, M - 5)
+            A.spmv_rows(lo, hi, xd, y)
+            out["csr rows window"] = y.cpu().numpy()[lo:hi]
+            y32 = torch.full((M,), float("nan"), dtype=torch.float32, device="cuda")
+            A.spmv_f32(x32, y32, algo=dev.ALGO_ROW)
+            out["csr f32"] = y32.cpu().numpy()
+            y = torch.full((M,), float("nan"), dtype=torch.float64, device="cuda")
+            H.spmv(xd, y, slice_kernel="rows")
+            out["hll"] = y.cpu().numpy()
+            if H.info().max_maxnz <= 12:
+                y32 = torch.full((M,), float("nan"), dtype=torch.float32, device="cuda")
+                H.spmv_f32(x32, y32)
+                out["hll f32"] = y32.cpu().numpy()
+            return out
+
+        plain = products()
+        assert np.array_equal(bits(plain["csr"]), bits(y_ref))
+        for k in range(max(len(csr_forms), len(hll_forms))):
+            monkeypatch.setenv("SPMV_B200_ROW_MULTI", str(k + 1))   # beyond a format's last form: its last form again
+            forced = products()
+            for name, y in forced.items():
+                same = (np.array_equal(y.view(np.uint32), plain[name].view(np.uint32)) if y.dtype == np.float32
+                        else np.array_equal(bits(y), bits(plain[name])))
+                assert same, f"form {k} ({csr_forms[min(k, len(csr_forms) - 1)]} / {hll_forms[min(k, len(hll_forms) - 1)]}), {name}, M={M}"
+            assert np.array_equal(bits(forced["csr"]), bits(y_ref))
+        monkeypatch.delenv("SPMV_B200_ROW_MULTI", raising=False)
+        H.close()
+        A.close()
+
+
 def test_resident_cache_of_the_drop_in_api(dev, checker):
     """The reference's stateless product signatures upload the matrix on every call; with the opt-in cache
     (spmv_b200_resident_cache) the second call on the same arrays reuses the device copy.  Same results, the
