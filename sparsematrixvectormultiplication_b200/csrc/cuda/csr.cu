@@ -270,18 +270,21 @@ csr_row_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, cons
     y[row] = (V)acc;
 }
 
-// csr_row_kernel with ROWS rows per thread (round 2e; fp32 storage).  The thread-per-row kernel is LATENCY bound once
-// the rows get lighter: a row is three dependent round trips (row_ptr -> columns / values -> x) and an SM cannot hold
-// more than 2048 threads, so with fp32 values (52 instead of 80 bytes per 5-point row) 2048 rows in flight no longer
-// cover the HBM latency (ncu: nothing saturated, DRAM at 68 %).  Here a thread owns rows t, t + 256, ... of its CTA's
-// 256*ROWS rows (a warp still reads 32 consecutive rows per instruction) and CTAS CTAs share an SM (register budget
-// 65536 / (256 CTAS)): the trips of ROWS rows overlap inside one thread, 256*CTAS*ROWS rows in flight per SM.
-// Second difference: slots past the end of a row gather x[0] (always a valid address here: the loop only runs when the
-// matrix has a nonzero) instead of being predicated on the LOADED column -- every predicate is then index arithmetic,
-// and ptxas issues all loads of a step before the first multiply (cuobjdump: 34 / 34 loads ahead of the first DMUL for
-// <5, 2, float, 5>; the one-row kernels issue 9-12 of 17 and stall on the first gather before requesting the rest).
-// Every row is still summed by one lane in index order, mul and add rounded separately, padding slots skipped: the
-// same bits as csr_row_kernel.  Which (ROWS, BATCH, CTAS) runs is timed at plan time (kRowmVariants).
+// csr_row_kernel in a second form (round 2e; candidates of the fp32 path): ROWS rows per thread, CTAS CTAs per SM, and --
+// the part that pays -- predicates that are INDEX ARITHMETIC only.  csr_row_kernel marks a slot past the end of its row
+// with column -1 and predicates the gather and the add on the LOADED column; ptxas then issues 9-12 of a step's 17 loads,
+// stalls on the first gather, and only then requests the rest (cuobjdump, tools/rowm_survey.py).  Here such a slot
+// gathers x[0] (always a valid address: the loop only runs when the matrix has a nonzero) and is skipped by `k < hi`, so
+// ptxas may issue every load of a step ahead of the first multiply.  Measured on lap2d 4096^2 with fp32 storage
+// (profiles/r02e_rowm_probe_second_pass.log): <5 loads, 1 row, 8 CTAs> 152.3 us against 155.0 us for the best
+// csr_row_kernel batch; its HLL twin 145.8 against 166.5 us.  It is a scheduling lottery, not a law: on lap3d 256^3 the
+// old form wins (183 against 197 us), and with fp64 storage it wins everywhere -- hence candidates timed at plan time.
+// ROWS > 1 (a thread owns rows t, t + 256, ... of its CTA's 256*ROWS rows; register budget 65536 / (256 CTAS)) was the
+// hypothesis this kernel was written for -- "the fp32 kernels are latency bound, so put more rows in flight per SM than
+// the 2048 threads an SM can hold" -- and the measurement REFUTED it: every multi-row form is 4-40 % slower than the
+// one-row forms, fp32 and fp64, CSR and HLL (profiles/r02e_rowm_probe_first_pass.log).  Three such forms stay in the
+// table so that the record can be re-measured.  Every row is summed by one lane in index order, mul and add rounded
+// separately, skipped slots skipped: the same bits as csr_row_kernel (tests/test_gpu_parity.py walks all forms).
 template <int BATCH, int ROWS, int CTAS, typename V>
 __global__ void __launch_bounds__(256, CTAS)
 csr_rowm_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
@@ -331,14 +334,13 @@ csr_rowm_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, con
     }
 }
 
-// (ROWS, BATCH, CTAS per SM) forms of csr_rowm_kernel offered to the plan-time tuner; chosen from the ptxas / SASS
-// survey of tools/rowm_survey.py: no or negligible spills, all loads of a step ahead of the first multiply.
+// (ROWS, BATCH, CTAS per SM) forms of csr_rowm_kernel offered to the plan-time tuner of the fp32 path (tools/rowm_survey.py
+// prints registers, spills and the load schedule of each; tools/rowm_probe.py times them).
 struct RowmVariant {
     int rows, batch, ctas;
 };
 #define SPMV_ROWM_VARIANTS(X) \
-    X(2, 3, 5) X(2, 3, 6) X(2, 4, 5) X(2, 5, 5) X(2, 5, 4) X(2, 6, 4) X(2, 7, 4) \
-    X(3, 3, 5) X(3, 3, 4) X(3, 4, 4) X(3, 5, 4) X(3, 5, 3) X(4, 3, 4) X(4, 4, 4)
+    X(1, 4, 8) X(1, 5, 8) X(1, 6, 8) X(1, 7, 8) X(1, 5, 6) X(2, 3, 5) X(2, 4, 5) X(3, 3, 5)
 #define ROWM_ENTRY(R, B, C) {R, B, C},
 static const RowmVariant kRowmVariants[] = {SPMV_ROWM_VARIANTS(ROWM_ENTRY)};
 #undef ROWM_ENTRY

@@ -120,13 +120,14 @@ hll_row_kernel(int hack_begin, int hack_end, const long long *__restrict__ hack_
     if (row < M) y[row] = (V)acc;
 }
 
-// hll_row_kernel with HACKS consecutive hacks per warp (round 2e; fp32 storage): the lane-per-row kernel is latency bound
-// once the rows get lighter (hack_off -> JA / AS -> x are dependent round trips and an SM holds at most 2048 lanes; ncu on
-// the fp32 image: DRAM 58 %, nothing saturated).  CTAS CTAs per SM (register budget 65536 / (256 CTAS)), every lane owns
-// row `lane` of HACKS hacks and keeps their trips in flight together; slots past the width of a hack gather x[0] instead
-// of being predicated on the loaded column, so that every predicate is index arithmetic and ptxas issues all loads of a
-// step ahead of the first multiply (see csr_rowm_kernel).  Order of the sums unchanged, skipped slots skipped: the same
-// bits as hll_row_kernel.  Which (HACKS, BATCH, CTAS) runs is timed at plan time (kHllRowmVariants).
+// hll_row_kernel in a second form (round 2e; candidates of the fp32 path; see csr_rowm_kernel in csr.cu): slots past the
+// width of a hack gather x[0] and are skipped by `j < width` instead of being predicated on the LOADED column, so every
+// predicate is index arithmetic and ptxas issues all loads of a step ahead of the first multiply (17 of 17 for <5, 1, 8,
+// float> against 9 of 17).  lap2d 4096^2, fp32 storage: 145.8 us against 166.5 us for the best hll_row_kernel batch
+// (profiles/r02e_rowm_probe_second_pass.log); not so on lap3d 256^3 or with fp64 storage, hence plan-time candidates.
+// HACKS > 1 (every lane owns row `lane` of HACKS consecutive hacks, CTAS CTAs per SM) tested the idea that more rows in
+// flight per SM would cover the latency of the lighter fp32 rows: refuted, 10-100 % slower; kept for the record.
+// Order of the sums unchanged, padding slots (x 0.0) included: the same bits as hll_row_kernel.
 template <int BATCH, int HACKS, int CTAS, typename V>
 __global__ void __launch_bounds__(256, CTAS)
 hll_rowm_kernel(int hack_begin, int hack_end, const long long *__restrict__ hack_off, const int *__restrict__ JA,
@@ -175,15 +176,12 @@ hll_rowm_kernel(int hack_begin, int hack_end, const long long *__restrict__ hack
     }
 }
 
-// (HACKS, BATCH, CTAS per SM) forms of hll_rowm_kernel offered to the plan-time tuner (tools/rowm_survey.py: no or
-// negligible spills, all loads of a step ahead of the first multiply); HACKS = 1 is the plain shape with the
-// index-only predicates.
+// (HACKS, BATCH, CTAS per SM) forms of hll_rowm_kernel offered to the plan-time tuner of the fp32 path
 struct HllRowmVariant {
     int hacks, batch, ctas;
 };
 #define SPMV_HLL_ROWM_VARIANTS(X) \
-    X(1, 4, 8) X(1, 5, 8) X(2, 3, 6) X(2, 3, 5) X(2, 4, 5) X(2, 4, 4) X(2, 5, 4) X(2, 7, 3) \
-    X(3, 3, 4) X(3, 4, 3) X(3, 5, 3) X(4, 3, 3)
+    X(1, 4, 8) X(1, 5, 8) X(1, 6, 8) X(1, 7, 8) X(1, 7, 6) X(2, 3, 5) X(2, 5, 4) X(3, 3, 4)
 #define HROWM_ENTRY(H, B, C) {H, B, C},
 static const HllRowmVariant kHllRowmVariants[] = {SPMV_HLL_ROWM_VARIANTS(HROWM_ENTRY)};
 #undef HROWM_ENTRY
