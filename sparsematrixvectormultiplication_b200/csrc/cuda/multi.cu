@@ -221,11 +221,14 @@ static int multi_finish(spmv_b200_multi *ctx) {
             const int *cols = nullptr;
             SPMV_TRY(spmv_b200_csr_device_arrays(p.A, nullptr, &cols, nullptr));
             SPMV_TRY_CUDA(cudaMalloc(&d_mm, sizeof mm));
-            SPMV_TRY_CUDA(cudaMemcpy(d_mm, mm, sizeof mm, cudaMemcpyHostToDevice));
-            col_minmax_kernel<<<1024, 256>>>(info.nnz, cols, d_mm);
-            SPMV_TRY_CUDA(cudaGetLastError());
-            SPMV_TRY_CUDA(cudaMemcpy(mm, d_mm, sizeof mm, cudaMemcpyDeviceToHost));
-            cudaFree(d_mm);
+            cudaError_t e = cudaMemcpy(d_mm, mm, sizeof mm, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) {
+                col_minmax_kernel<<<1024, 256>>>(info.nnz, cols, d_mm);
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaMemcpy(mm, d_mm, sizeof mm, cudaMemcpyDeviceToHost);
+            cudaFree(d_mm);  // on every path: an error below returns from this function
+            SPMV_TRY_CUDA(e);
         }
         p.need_lo = mm[1] >= 0 ? mm[0] : p.row_begin;
         p.need_hi = mm[1] >= 0 ? mm[1] + 1 : p.row_begin;

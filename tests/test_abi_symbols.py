@@ -61,3 +61,23 @@ def test_no_cpu_fallback_without_a_gpu():
     with pytest.raises(N.SpmvError):
         host.csr_matrix_vector_mult(2, rp, ci, va, np.ones(2), y)
     assert np.isnan(y).all()  # poisoned, never silently computed on the CPU
+
+
+def test_row_kernel_forms_are_described_without_a_gpu():
+    """spmv_b200_row_forms / _describe (the forms of csr_rowm_kernel / hll_rowm_kernel the fp32 tuner times): pure table
+    look-ups, usable on a CPU box; an index outside the table is an error, not a crash."""
+    from sparsematrixvectormultiplication_b200 import device
+    for fmt in (device.FORMAT_CSR, device.FORMAT_HLL):
+        forms = device.row_forms(fmt)
+        assert len(forms) >= 4 and len(set(forms)) == len(forms)
+        for rows, batch, ctas in forms:
+            assert 1 <= rows <= 4 and 3 <= batch <= 7 and 3 <= ctas <= 8
+        assert any(rows == 1 for rows, _, _ in forms) and any(rows > 1 for rows, _, _ in forms)
+        r = ctypes.c_int()
+        assert N.lib().spmv_b200_row_form_describe(fmt, len(forms), ctypes.byref(r), None, None) != 0
+        assert N.lib().spmv_b200_row_form_describe(fmt, -1, None, None, None) != 0
+        assert N.lib().spmv_b200_row_form_describe(fmt, 0, None, None, None) == 0   # NULL outputs are allowed
+    assert N.lib().spmv_b200_row_forms(7) == 0
+    assert device.row_form_name(device.FORMAT_CSR, 5) == "csr_row_kernel<5,float>"
+    assert device.row_form_name(device.FORMAT_HLL, 16).startswith("hll_rowm_kernel<")
+    assert N.lib().spmv_b200_csr_row_form_f32(None) == 0 and N.lib().spmv_b200_hll_row_form_f32(None) == 0
