@@ -288,8 +288,13 @@ csr_row_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, cons
 template <int BATCH, int ROWS, int CTAS, typename V>
 __global__ void __launch_bounds__(256, CTAS)
 csr_rowm_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
-                const V *__restrict__ values, const V *__restrict__ x, V *__restrict__ y, int accumulate) {
+                const V *__restrict__ values, const V *__restrict__ x, V *__restrict__ y, int accumulate, int ahead) {
     const long long first = row_begin + (long long)blockIdx.x * (256 * ROWS) + threadIdx.x;
+    // SPMV_B200_ROW_PREFETCH (experiment, off): one lane per warp asks L2 for the row_ptr line of the warp `ahead` rows
+    // further on, so that the first of that warp's three round trips ends in L2 instead of DRAM.  Unlike the round-2d
+    // prefetch (row_ptr AND the column / value lines, which needs the far row_ptr first) this costs no dependent load.
+    if (ahead > 0 && (threadIdx.x & 31) == 0 && first + ahead < row_end)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(row_ptr + first + ahead));
     int lo[ROWS], hi[ROWS];
     double acc[ROWS];
 #pragma unroll
@@ -1134,11 +1139,12 @@ static int launch_rows(int row_begin, int row_end, const int *row_ptr, const int
     if (variant >= 0) {
         if (variant >= kNumRowmVariants) return fail(SPMV_B200_ERR_INVALID, "row kernel: unknown multi-row form %d", variant);
         const unsigned int gm = blocks_for(rows, 256 * kRowmVariants[variant].rows);
+        const int ahead = env_int("SPMV_B200_ROW_PREFETCH", 0) * 256 * kRowmVariants[variant].rows;  // CTAs ahead -> rows
         int at = 0;
 #define ROWM_CASE(R, B, C)                                                                                                    \
     if (at++ == variant)                                                                                                      \
         SPMV_TRY_CUDA(launch_x(csr_rowm_kernel<B, R, C, V>, gm, 256, 0, stream, keep, row_begin, row_end, row_ptr, col_idx, values, x, \
-                               y, accumulate));
+                               y, accumulate, ahead));
         SPMV_ROWM_VARIANTS(ROWM_CASE)
 #undef ROWM_CASE
         SPMV_TRY_CUDA(cudaGetLastError());

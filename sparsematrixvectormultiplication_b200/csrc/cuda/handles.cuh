@@ -236,8 +236,22 @@ struct spmv_b200_csr {
     spmv::HostPipe *pipe = nullptr;
 };
 
+namespace spmv {
+// Runs of hacks of equal width (regular ELLPACK regions): hacks [begin[s], begin[s+1]) have `width[s]` columns and hack h
+// of the run starts at slot base[s] + (h - begin[s]) * 32 * width[s] -- the offset by arithmetic, without the hack_off
+// load (hll_rowu_kernel).  count = 0: the image has more than kMaxHllSegments runs, the kernel is not offered.
+constexpr int kMaxHllSegments = 8;
+struct HllSegments {
+    int count = 0;
+    int begin[kMaxHllSegments + 1] = {};
+    int width[kMaxHllSegments] = {};
+    long long base[kMaxHllSegments] = {};
+};
+}  // namespace spmv
+
 struct spmv_b200_hll {
     int M = 0, N = 0, num_hacks = 0, max_width = 0;
+    spmv::HllSegments segments;     // from host_off at plan time (hll_pick_row_batch)
     long long slots = 0, ref_slots = 0;
     long long *hack_off = nullptr;  // device [num_hacks+1]
     int *JA = nullptr;              // device [slots]

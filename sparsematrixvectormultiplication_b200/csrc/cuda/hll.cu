@@ -131,8 +131,11 @@ hll_row_kernel(int hack_begin, int hack_end, const long long *__restrict__ hack_
 template <int BATCH, int HACKS, int CTAS, typename V>
 __global__ void __launch_bounds__(256, CTAS)
 hll_rowm_kernel(int hack_begin, int hack_end, const long long *__restrict__ hack_off, const int *__restrict__ JA,
-                const V *__restrict__ AS, const V *__restrict__ x, V *__restrict__ y, int M) {
+                const V *__restrict__ AS, const V *__restrict__ x, V *__restrict__ y, int M, int ahead) {
     const int first = hack_begin + (blockIdx.x * 8 + (threadIdx.x >> 5)) * HACKS;
+    // SPMV_B200_ROW_PREFETCH (experiment, off): one thread per CTA asks L2 for the hack_off line of the CTA `ahead` hacks on
+    if (ahead > 0 && threadIdx.x == 0 && first + ahead < hack_end)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(hack_off + first + ahead));
     if (first >= hack_end) return;  // warp-uniform
     const int lane = threadIdx.x & 31;
     long long off[HACKS + 1];
@@ -174,6 +177,46 @@ hll_rowm_kernel(int hack_begin, int hack_end, const long long *__restrict__ hack
         const long long row = (long long)(first + h) * kHack + lane;
         if (first + h < hack_end && row < M) y[row] = (V)acc[h];
     }
+}
+
+// The lane-per-row kernel WITHOUT the hack_off round trip (round 2e; fp32 path and regular images only): when the image
+// consists of at most kMaxHllSegments runs of hacks of equal width -- a 2-D stencil: one run per grid-row class, three
+// on lap2d -- a warp finds its run with a handful of compares on kernel parameters and computes its first slot, so the
+// row's dependent chain is two memory round trips (JA / AS -> x) instead of three.  Same loop, same order, same bits as
+// hll_rowm_kernel<BATCH, 1, 8>.  Form ids 64 + BATCH of the fp32 tuner.
+template <int BATCH, typename V>
+__global__ void __launch_bounds__(256, 8)
+hll_rowu_kernel(int hack_begin, int hack_end, const __grid_constant__ HllSegments seg, const int *__restrict__ JA,
+                const V *__restrict__ AS, const V *__restrict__ x, V *__restrict__ y, int M) {
+    const int hack = hack_begin + blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (hack >= hack_end) return;  // warp-uniform
+    const int lane = threadIdx.x & 31;
+    int first = seg.begin[0], width = seg.width[0];
+    long long base = seg.base[0];
+#pragma unroll
+    for (int s = 1; s < kMaxHllSegments; ++s)
+        if (s < seg.count && hack >= seg.begin[s]) {
+            first = seg.begin[s];
+            width = seg.width[s];
+            base = seg.base[s];
+        }
+    const long long off = base + (long long)(hack - first) * kHack * width + lane;
+    double acc = 0.0;
+    for (int j = 0; j < width; j += BATCH) {
+        int c[BATCH];
+        double v[BATCH], xv[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) c[u] = j + u < width ? ldg_stream_s32(JA + off + (long long)(j + u) * kHack) : 0;
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) v[u] = j + u < width ? ldg_stream_f64(AS + off + (long long)(j + u) * kHack) : 0.0;
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) xv[u] = ldg_x(x, c[u]);
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u)
+            if (j + u < width) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+    }
+    const long long row = (long long)hack * kHack + lane;
+    if (row < M) y[row] = (V)acc;
 }
 
 // (HACKS, BATCH, CTAS per SM) forms of hll_rowm_kernel offered to the plan-time tuner of the fp32 path
@@ -366,19 +409,40 @@ static int hll_launch_rows_t(const spmv_b200_hll *H, const V *AS, int hack_begin
                              cudaStream_t stream, int batch = -1) {
     if (hack_end <= hack_begin) return SPMV_B200_OK;
     if (batch < 0) batch = sizeof(V) == 4 ? H->row_batch32 : H->row_batch;
-    const XPolicy keep = matrix_policy(H->JA, (size_t)H->slots * sizeof(int));   // head of JA held in L2 across products
+    // head of JA held in L2 across products (SPMV_B200_MATRIX_PERSIST, off); with SPMV_B200_HACKOFF_PERSIST the window is
+    // the offset array instead (4 MB on lap2d 4096^2): the first of a row's round trips then ends in L2
+    const XPolicy keep = env_int("SPMV_B200_HACKOFF_PERSIST", 0)
+                             ? matrix_policy(H->hack_off, ((size_t)H->num_hacks + 1) * sizeof(long long))
+                             : matrix_policy(H->JA, (size_t)H->slots * sizeof(int));
     // batch >= 16: hll_rowm_kernel, form kHllRowmVariants[batch - 16].  SPMV_B200_ROW_MULTI=k (k >= 1) sends EVERY
     // row-kernel launch through form k - 1 (parity runs: tests/test_gpu_parity.py walks all forms, fp64 bit for bit)
     const int forced_multi = env_int("SPMV_B200_ROW_MULTI", 0);
+    // ids 64 + B: hll_rowu_kernel<B> (offsets by arithmetic; regular images only).  SPMV_B200_HLL_UNIFORM=B forces it
+    // on every row launch of an image that qualifies (parity runs).
+    const int forced_uniform = env_int("SPMV_B200_HLL_UNIFORM", 0);
+    const int uniform = batch >= 64 ? batch - 64 : (forced_uniform >= 3 && forced_uniform <= 7 && H->segments.count > 0 ? forced_uniform : 0);
+    if (uniform > 0) {
+        if (H->segments.count <= 0) return fail(SPMV_B200_ERR_INVALID, "hll row kernel: the image is not regular enough for the offset-free form");
+        const unsigned int gu = blocks_for(hack_end - hack_begin, 8);
+#define HROWU_CASE(B) case B: SPMV_TRY_CUDA(launch_x(hll_rowu_kernel<B, V>, gu, 256, 0, stream, keep, hack_begin, hack_end, H->segments, H->JA, AS, d_x, d_y, H->M)); break;
+        switch (uniform) {
+            HROWU_CASE(3) HROWU_CASE(4) HROWU_CASE(6) HROWU_CASE(7)
+            default: SPMV_TRY_CUDA(launch_x(hll_rowu_kernel<5, V>, gu, 256, 0, stream, keep, hack_begin, hack_end, H->segments, H->JA, AS, d_x, d_y, H->M)); break;
+        }
+#undef HROWU_CASE
+        SPMV_TRY_CUDA(cudaGetLastError());
+        return SPMV_B200_OK;
+    }
     const int variant = forced_multi >= 1 ? std::min(forced_multi, kNumHllRowmVariants) - 1 : batch - 16;
     if (variant >= 0) {
         if (variant >= kNumHllRowmVariants) return fail(SPMV_B200_ERR_INVALID, "hll row kernel: unknown multi-hack form %d", variant);
         const unsigned int gm = blocks_for(hack_end - hack_begin, 8 * kHllRowmVariants[variant].hacks);
+        const int ahead = env_int("SPMV_B200_ROW_PREFETCH", 0) * 8 * kHllRowmVariants[variant].hacks;  // CTAs ahead -> hacks
         int at = 0;
 #define HROWM_CASE(R, B, C)                                                                                                  \
     if (at++ == variant)                                                                                                     \
         SPMV_TRY_CUDA(launch_x(hll_rowm_kernel<B, R, C, V>, gm, 256, 0, stream, keep, hack_begin, hack_end, H->hack_off, H->JA, AS, \
-                               d_x, d_y, H->M));
+                               d_x, d_y, H->M, ahead));
         SPMV_HLL_ROWM_VARIANTS(HROWM_CASE)
 #undef HROWM_CASE
         SPMV_TRY_CUDA(cudaGetLastError());
@@ -484,7 +548,30 @@ int hll_launch_window(const spmv_b200_hll *H, HllPath path, int unit_begin, int 
 }
 
 // batch of the lane-per-row kernel: the hack width when it is uniform and small; timed at plan time on large images
+// runs of hacks of equal width, from the host copy of the offsets (HllSegments, handles.cuh)
+static void hll_find_segments(spmv_b200_hll *H) {
+    HllSegments seg;
+    const std::vector<long long> &off = H->host_off;
+    bool regular = (int)off.size() == H->num_hacks + 1 && H->num_hacks > 0;
+    for (int h = 0; regular && h < H->num_hacks; ++h) {
+        const int w = (int)((off[h + 1] - off[h]) / kHack);
+        if (seg.count > 0 && seg.width[seg.count - 1] == w) continue;
+        if (seg.count == kMaxHllSegments) {
+            regular = false;
+            break;
+        }
+        seg.begin[seg.count] = h;
+        seg.width[seg.count] = w;
+        seg.base[seg.count] = off[h];
+        ++seg.count;
+    }
+    if (!regular) seg = HllSegments();
+    else seg.begin[seg.count] = H->num_hacks;
+    H->segments = seg;
+}
+
 static void hll_pick_row_batch(spmv_b200_hll *H, cudaStream_t stream) {
+    hll_find_segments(H);
     const int forced = env_int("SPMV_B200_HLL_ROW_BATCH", 0);
     H->narrow_stream = false;
     const long long mean = H->num_hacks > 0 ? (H->slots / 32 + H->num_hacks - 1) / H->num_hacks : 4;
@@ -877,13 +964,16 @@ int spmv_b200_hll_enable_f32(spmv_b200_hll *H, void *stream) {
         env_int("SPMV_B200_HLL_ROW_BATCH", 0) == 0) {
         // candidates: one hack per warp with batch 2..7, and the forms of hll_rowm_kernel (ids >= 16); all give the same
         // bits.  SPMV_B200_ROW_MULTI_TUNE=0 keeps the one-hack forms only.
-        int ids[8 + kNumHllRowmVariants], n = 0, fallback = 0;
+        int ids[12 + kNumHllRowmVariants], n = 0, fallback = 0;
         for (int batch = 2; batch <= 7; ++batch) {
             if (batch == H->row_batch) fallback = n;
             ids[n++] = batch;
         }
-        if (env_int("SPMV_B200_ROW_MULTI_TUNE", 1))
+        if (env_int("SPMV_B200_ROW_MULTI_TUNE", 1)) {
             for (int v = 0; v < kNumHllRowmVariants; ++v) ids[n++] = 16 + v;
+            if (H->segments.count > 0)  // regular image: the forms without the hack_off round trip
+                for (int batch = 4; batch <= 7; ++batch) ids[n++] = 64 + batch;
+        }
         const int pick = tune_candidates(H->M, H->N, n, fallback, as_stream(stream), [&](int i, double *x, double *y) {
             return hll_launch_rows_t<float>(H, H->AS32, 0, H->num_hacks, reinterpret_cast<const float *>(x),
                                             reinterpret_cast<float *>(y), as_stream(stream), ids[i]);

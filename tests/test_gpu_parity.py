@@ -1008,14 +1008,22 @@ def test_multi_row_forms_give_the_bits_of_the_one_row_kernels(dev, checker, monk
     cases.append((1, 5, np.array([3])))
     cases.append((300, 300, np.zeros(300, np.int64)))            # no nonzero at all: x is never read
     cases.append((777, 64, rng.integers(4, 8, 777)))             # stencil-like: every form in its intended regime
+    cases.append("lap2d")                                        # regular image (three runs of equal-width hacks): hll_rowu_kernel
     csr_forms, hll_forms = dev.row_forms(dev.FORMAT_CSR), dev.row_forms(dev.FORMAT_HLL)
     assert len(csr_forms) >= 8 and len(hll_forms) >= 8
-    for M, N, lengths in cases:
-        rp = np.zeros(M + 1, np.int32)
-        np.cumsum(lengths, out=rp[1:])
-        ci = (np.concatenate([np.sort(rng.choice(N, n, replace=False)) for n in lengths]).astype(np.int32)
-              if rp[-1] else np.zeros(0, np.int32))
-        va = rng.standard_normal(rp[-1])
+    for case in cases:
+        if case == "lap2d":
+            from sparsematrixvectormultiplication_b200 import synth
+            rp, ci, va = synth.lap2d_csr(70)
+            M = N = 4900
+            va = va * rng.uniform(0.5, 1.5, va.size)
+        else:
+            M, N, lengths = case
+            rp = np.zeros(M + 1, np.int32)
+            np.cumsum(lengths, out=rp[1:])
+            ci = (np.concatenate([np.sort(rng.choice(N, n, replace=False)) for n in lengths]).astype(np.int32)
+                  if rp[-1] else np.zeros(0, np.int32))
+            va = rng.standard_normal(rp[-1])
         x = rng.standard_normal(N)
         y_ref = checker.spmv_csr_serial(rp, ci, va, x)
         acc0 = rng.standard_normal(M)
@@ -1051,15 +1059,21 @@ def test_multi_row_forms_give_the_bits_of_the_one_row_kernels(dev, checker, monk
 
         plain = products()
         assert np.array_equal(bits(plain["csr"]), bits(y_ref))
-        for k in range(max(len(csr_forms), len(hll_forms))):
-            monkeypatch.setenv("SPMV_B200_ROW_MULTI", str(k + 1))   # beyond a format's last form: its last form again
+        # beyond a format's last form SPMV_B200_ROW_MULTI means its last form again; SPMV_B200_HLL_UNIFORM=B: the HLL row
+        # launches of a regular image go through hll_rowu_kernel<B> (offsets by arithmetic), other images are unaffected
+        settings = [{"SPMV_B200_ROW_MULTI": str(k + 1)} for k in range(max(len(csr_forms), len(hll_forms)))]
+        settings += [{"SPMV_B200_HLL_UNIFORM": str(b)} for b in (3, 4, 5, 6, 7)]
+        for setting in settings:
+            for key, value in setting.items():
+                monkeypatch.setenv(key, value)
             forced = products()
             for name, y in forced.items():
                 same = (np.array_equal(y.view(np.uint32), plain[name].view(np.uint32)) if y.dtype == np.float32
                         else np.array_equal(bits(y), bits(plain[name])))
-                assert same, f"form {k} ({csr_forms[min(k, len(csr_forms) - 1)]} / {hll_forms[min(k, len(hll_forms) - 1)]}), {name}, M={M}"
+                assert same, f"{setting}, {name}, M={M}"
             assert np.array_equal(bits(forced["csr"]), bits(y_ref))
-        monkeypatch.delenv("SPMV_B200_ROW_MULTI", raising=False)
+            for key in setting:
+                monkeypatch.delenv(key, raising=False)
         H.close()
         A.close()
 

@@ -35,7 +35,7 @@ def main():
     rows = []
     for body in re.split(r"Function : ", sass)[1:]:
         name = body.split()[0]
-        m = re.search(r"(csr|hll)_row(m?)_kernelILi(\d)E(?:Li(\d)ELi(\d)E)?([fd])E", name)
+        m = re.search(r"(csr|hll)_row(m|u?)_kernelILi(\d)E(?:Li(\d)ELi(\d)E)?([fd])E", name)
         if not m:
             continue
         fmt, multi, batch, rows_per, ctas, v = m.groups()
@@ -48,7 +48,7 @@ def main():
         total = ops.count("LDG")
         rec = info.get(name, {})
         rows.append((fmt, v, int(rows_per or 1), int(batch), int(ctas or 8), rec.get("regs"), rec.get("spill"), ahead, total,
-                     "rowm" if multi else "row"))
+                     "row" + multi))
     print("format storage rows batch ctas/SM regs spill_bytes loads_ahead_of_first_DMUL/loads rows_in_flight/SM kernel")
     for r in sorted(rows):
         fmt, v, rp, b, c, regs, spill, ahead, total, kind = r
