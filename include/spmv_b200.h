@@ -317,7 +317,8 @@ int spmv_b200_hll_spmv_host_f32(spmv_b200_hll *H, const float *x, float *y);
 /* Which form of the row kernel enable_f32 timed fastest for this matrix: 1..8 = csr_row_kernel / hll_row_kernel with that
  * many loads in flight per row; >= 16 = form (id - 16) of csr_rowm_kernel / hll_rowm_kernel (index-only predicates, so
  * that every load of a step is issued ahead of the first multiply; rows per thread, loads in flight per row and CTAs
- * per SM from spmv_b200_row_form_describe); 0 before enable_f32.  The environment variable SPMV_B200_ROW_MULTI=k
+ * per SM from spmv_b200_row_form_describe); HLL only, 64 + b = hll_rowu_kernel with b loads in flight (regular images:
+ * hack offsets by arithmetic, no offset load); 0 before enable_f32.  The environment variable SPMV_B200_ROW_MULTI=k
  * (k >= 1) sends every row-kernel launch, fp64 included, through form k - 1: all forms give the same bits, which is
  * what the parity tests use it for. */
 int spmv_b200_csr_row_form_f32(const spmv_b200_csr *A);

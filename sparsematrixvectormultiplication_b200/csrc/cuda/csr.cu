@@ -285,16 +285,15 @@ csr_row_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, cons
 // one-row forms, fp32 and fp64, CSR and HLL (profiles/r02e_rowm_probe_first_pass.log).  Three such forms stay in the
 // table so that the record can be re-measured.  Every row is summed by one lane in index order, mul and add rounded
 // separately, skipped slots skipped: the same bits as csr_row_kernel (tests/test_gpu_parity.py walks all forms).
+// Also tried on this kernel and removed (profiles/r02e_rowm_probe_third_pass.log): one lane per warp prefetching into L2
+// the row_ptr line of the warp N CTAs further on, so that the first of that warp's three round trips ends in L2 -- CSR
+// fp32 lap2d 152 us at N = 148, 162-166 us from N = 592 up, against 152-156 without; and the extra parameter alone moved
+// ptxas from 15 to 12 of 18 loads ahead of the first multiply.
 template <int BATCH, int ROWS, int CTAS, typename V>
 __global__ void __launch_bounds__(256, CTAS)
 csr_rowm_kernel(int row_begin, int row_end, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
-                const V *__restrict__ values, const V *__restrict__ x, V *__restrict__ y, int accumulate, int ahead) {
+                const V *__restrict__ values, const V *__restrict__ x, V *__restrict__ y, int accumulate) {
     const long long first = row_begin + (long long)blockIdx.x * (256 * ROWS) + threadIdx.x;
-    // SPMV_B200_ROW_PREFETCH (experiment, off): one lane per warp asks L2 for the row_ptr line of the warp `ahead` rows
-    // further on, so that the first of that warp's three round trips ends in L2 instead of DRAM.  Unlike the round-2d
-    // prefetch (row_ptr AND the column / value lines, which needs the far row_ptr first) this costs no dependent load.
-    if (ahead > 0 && (threadIdx.x & 31) == 0 && first + ahead < row_end)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(row_ptr + first + ahead));
     int lo[ROWS], hi[ROWS];
     double acc[ROWS];
 #pragma unroll
@@ -1139,12 +1138,11 @@ static int launch_rows(int row_begin, int row_end, const int *row_ptr, const int
     if (variant >= 0) {
         if (variant >= kNumRowmVariants) return fail(SPMV_B200_ERR_INVALID, "row kernel: unknown multi-row form %d", variant);
         const unsigned int gm = blocks_for(rows, 256 * kRowmVariants[variant].rows);
-        const int ahead = env_int("SPMV_B200_ROW_PREFETCH", 0) * 256 * kRowmVariants[variant].rows;  // CTAs ahead -> rows
         int at = 0;
 #define ROWM_CASE(R, B, C)                                                                                                    \
     if (at++ == variant)                                                                                                      \
         SPMV_TRY_CUDA(launch_x(csr_rowm_kernel<B, R, C, V>, gm, 256, 0, stream, keep, row_begin, row_end, row_ptr, col_idx, values, x, \
-                               y, accumulate, ahead));
+                               y, accumulate));
         SPMV_ROWM_VARIANTS(ROWM_CASE)
 #undef ROWM_CASE
         SPMV_TRY_CUDA(cudaGetLastError());

@@ -131,11 +131,8 @@ hll_row_kernel(int hack_begin, int hack_end, const long long *__restrict__ hack_
 template <int BATCH, int HACKS, int CTAS, typename V>
 __global__ void __launch_bounds__(256, CTAS)
 hll_rowm_kernel(int hack_begin, int hack_end, const long long *__restrict__ hack_off, const int *__restrict__ JA,
-                const V *__restrict__ AS, const V *__restrict__ x, V *__restrict__ y, int M, int ahead) {
+                const V *__restrict__ AS, const V *__restrict__ x, V *__restrict__ y, int M) {
     const int first = hack_begin + (blockIdx.x * 8 + (threadIdx.x >> 5)) * HACKS;
-    // SPMV_B200_ROW_PREFETCH (experiment, off): one thread per CTA asks L2 for the hack_off line of the CTA `ahead` hacks on
-    if (ahead > 0 && threadIdx.x == 0 && first + ahead < hack_end)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(hack_off + first + ahead));
     if (first >= hack_end) return;  // warp-uniform
     const int lane = threadIdx.x & 31;
     long long off[HACKS + 1];
@@ -183,7 +180,12 @@ hll_rowm_kernel(int hack_begin, int hack_end, const long long *__restrict__ hack
 // consists of at most kMaxHllSegments runs of hacks of equal width -- a 2-D stencil: one run per grid-row class, three
 // on lap2d -- a warp finds its run with a handful of compares on kernel parameters and computes its first slot, so the
 // row's dependent chain is two memory round trips (JA / AS -> x) instead of three.  Same loop, same order, same bits as
-// hll_rowm_kernel<BATCH, 1, 8>.  Form ids 64 + BATCH of the fp32 tuner.
+// hll_rowm_kernel<BATCH, 1, 8>.  Form ids 64 + BATCH of the fp32 tuner.  Measured (lap2d 4096^2, fp32 storage,
+// profiles/r02e_rowm_probe_third_pass.log): 139.9 us against 146.0 us for hll_rowm_kernel<5, 1, 8> and 166.4 us for
+// hll_row_kernel<5> -- the first round trip is worth 4 %, not the third of the time a pure latency model gives it.  Two
+// other ways to shorten that trip on images that are NOT regular, tried and removed: the hack_off line of the CTA N CTAs
+// further on prefetched into L2 by one thread per CTA (141-142 us at every N from 148 to 9472: the same 3 %), and the
+// offset array held in the persisting L2 carve-out (194.6 us: the carve-out costs the gathers more than the trip saves).
 template <int BATCH, typename V>
 __global__ void __launch_bounds__(256, 8)
 hll_rowu_kernel(int hack_begin, int hack_end, const __grid_constant__ HllSegments seg, const int *__restrict__ JA,
@@ -409,11 +411,7 @@ static int hll_launch_rows_t(const spmv_b200_hll *H, const V *AS, int hack_begin
                              cudaStream_t stream, int batch = -1) {
     if (hack_end <= hack_begin) return SPMV_B200_OK;
     if (batch < 0) batch = sizeof(V) == 4 ? H->row_batch32 : H->row_batch;
-    // head of JA held in L2 across products (SPMV_B200_MATRIX_PERSIST, off); with SPMV_B200_HACKOFF_PERSIST the window is
-    // the offset array instead (4 MB on lap2d 4096^2): the first of a row's round trips then ends in L2
-    const XPolicy keep = env_int("SPMV_B200_HACKOFF_PERSIST", 0)
-                             ? matrix_policy(H->hack_off, ((size_t)H->num_hacks + 1) * sizeof(long long))
-                             : matrix_policy(H->JA, (size_t)H->slots * sizeof(int));
+    const XPolicy keep = matrix_policy(H->JA, (size_t)H->slots * sizeof(int));   // head of JA held in L2 across products
     // batch >= 16: hll_rowm_kernel, form kHllRowmVariants[batch - 16].  SPMV_B200_ROW_MULTI=k (k >= 1) sends EVERY
     // row-kernel launch through form k - 1 (parity runs: tests/test_gpu_parity.py walks all forms, fp64 bit for bit)
     const int forced_multi = env_int("SPMV_B200_ROW_MULTI", 0);
@@ -437,12 +435,11 @@ static int hll_launch_rows_t(const spmv_b200_hll *H, const V *AS, int hack_begin
     if (variant >= 0) {
         if (variant >= kNumHllRowmVariants) return fail(SPMV_B200_ERR_INVALID, "hll row kernel: unknown multi-hack form %d", variant);
         const unsigned int gm = blocks_for(hack_end - hack_begin, 8 * kHllRowmVariants[variant].hacks);
-        const int ahead = env_int("SPMV_B200_ROW_PREFETCH", 0) * 8 * kHllRowmVariants[variant].hacks;  // CTAs ahead -> hacks
         int at = 0;
 #define HROWM_CASE(R, B, C)                                                                                                  \
     if (at++ == variant)                                                                                                     \
         SPMV_TRY_CUDA(launch_x(hll_rowm_kernel<B, R, C, V>, gm, 256, 0, stream, keep, hack_begin, hack_end, H->hack_off, H->JA, AS, \
-                               d_x, d_y, H->M, ahead));
+                               d_x, d_y, H->M));
         SPMV_HLL_ROWM_VARIANTS(HROWM_CASE)
 #undef HROWM_CASE
         SPMV_TRY_CUDA(cudaGetLastError());

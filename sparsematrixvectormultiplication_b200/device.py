@@ -56,6 +56,8 @@ def row_forms(fmt: int):
 
 def row_form_name(fmt: int, form: int) -> str:
     base = "csr_row" if fmt == FORMAT_CSR else "hll_row"
+    if form >= 64:  # HLL only: offsets by arithmetic on a regular image
+        return f"hll_rowu_kernel<{form - 64},float>"
     if form >= 16:
         r, b, c = row_forms(fmt)[form - 16]
         return f"{base}m_kernel<{b},{r},{c},float>"

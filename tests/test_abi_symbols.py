@@ -80,4 +80,5 @@ def test_row_kernel_forms_are_described_without_a_gpu():
     assert N.lib().spmv_b200_row_forms(7) == 0
     assert device.row_form_name(device.FORMAT_CSR, 5) == "csr_row_kernel<5,float>"
     assert device.row_form_name(device.FORMAT_HLL, 16).startswith("hll_rowm_kernel<")
+    assert device.row_form_name(device.FORMAT_HLL, 64 + 5) == "hll_rowu_kernel<5,float>"
     assert N.lib().spmv_b200_csr_row_form_f32(None) == 0 and N.lib().spmv_b200_hll_row_form_f32(None) == 0

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
-"""Second probe of the fp32 row path on lap2d 4096^2 (and lap3d 256^3): what removing or shortening the FIRST of a row's
-three dependent round trips buys.  (a) hll_rowu_kernel: hack offsets by arithmetic (regular images), (b) the offset /
-row_ptr line of a later CTA prefetched into L2 (SPMV_B200_ROW_PREFETCH = CTAs ahead), (c) the offset array held in the
-persisting L2 carve-out.  Everything is an environment variable read at launch time, so one process sweeps all of it.
+"""Second probe of the fp32 row path on lap2d 4096^2 (and lap3d 256^3): what removing the FIRST of a row's three dependent
+round trips buys -- hll_rowu_kernel, hack offsets by arithmetic on regular images (SPMV_B200_HLL_UNIFORM = batch, read at
+launch time) -- next to the index-only forms and the plain kernels.  The run kept as
+profiles/r02e_rowm_probe_third_pass.log also swept two switches that were removed afterwards because they lost: a
+prefetch of the row_ptr / hack_off line of a later CTA into L2, and the offset array in the persisting L2 carve-out.
 """
 import os
 import sys
@@ -16,7 +17,7 @@ from tune import timeit  # noqa: E402
 
 torch.cuda.set_device(0)
 os.environ["SPMV_B200_AUTOTUNE"] = "0"
-KEYS = ("SPMV_B200_ROW_MULTI", "SPMV_B200_HLL_UNIFORM", "SPMV_B200_ROW_PREFETCH", "SPMV_B200_MATRIX_PERSIST", "SPMV_B200_HACKOFF_PERSIST")
+KEYS = ("SPMV_B200_ROW_MULTI", "SPMV_B200_HLL_UNIFORM")
 
 
 def best(fn):
@@ -56,28 +57,9 @@ for name, kind, p in (("lap2d_4096", synth.SYNTH_LAP2D, 4096), ("lap3d_256", syn
     for b in (4, 5, 6, 7):
         setting(HLL_UNIFORM=b)
         print(f"{name} hll_rowu batch {b}: hll f32 {best(hll32)*1e3:6.1f} us {H.algorithmic_bytes_f32()/best(hll32)/1e6:5.0f} GB/s | hll f64 {best(hll64)*1e3:6.1f} us", flush=True)
-    for ahead in (148, 592, 1184, 2368, 4736, 9472):
-        setting(ROW_MULTI=pick["hll"][b0], ROW_PREFETCH=ahead)
-        t_h = best(hll32)
-        setting(ROW_MULTI=pick["csr"][b0], ROW_PREFETCH=ahead)
-        t_c = best(csr32)
-        print(f"{name} prefetch {ahead} CTAs ahead (index-only form batch {b0}): csr f32 {t_c*1e3:6.1f} us | hll f32 {t_h*1e3:6.1f} us", flush=True)
     setting()
     H.close()
     A.close()
     del x, y, x32, y32
     torch.cuda.empty_cache()
 
-# last, because raising the persisting carve-out is a per-device setting that stays for the rest of the process
-A = device.DeviceCSR.synth(synth.SYNTH_LAP2D, 4096).enable_f32()
-H = A.to_hll().enable_f32()
-i = A.info()
-x32 = torch.ones(i.N, dtype=torch.float32, device="cuda")
-y32 = torch.empty(i.M, dtype=torch.float32, device="cuda")
-form = 1 + device.row_forms(device.FORMAT_HLL).index((1, 5, 8))
-setting(ROW_MULTI=form)
-t0 = best(lambda: H.spmv_f32(x32, y32))
-setting(ROW_MULTI=form, MATRIX_PERSIST=1, HACKOFF_PERSIST=1)
-t1 = best(lambda: H.spmv_f32(x32, y32))
-print(f"lap2d_4096 hack_off in the persisting carve-out (index-only form batch 5): hll f32 {t1*1e3:6.1f} us against {t0*1e3:6.1f} us without", flush=True)
-setting()
