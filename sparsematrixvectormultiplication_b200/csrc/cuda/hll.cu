@@ -197,13 +197,28 @@ hll_rowu_kernel(int hack_begin, int hack_end, const __grid_constant__ HllSegment
     long long base = seg.base[0];
 #pragma unroll
     for (int s = 1; s < kMaxHllSegments; ++s)
-        if (s < seg.count && hack >= seg.begin[s]) {
+        if (hack >= seg.begin[s]) {  // unused entries hold INT_MAX (hll_find_segments)
             first = seg.begin[s];
             width = seg.width[s];
             base = seg.base[s];
         }
     const long long off = base + (long long)(hack - first) * kHack * width + lane;
     double acc = 0.0;
+    if (width == BATCH) {
+        // the run's width IS the batch (the form the tuner ends up with on a stencil): straight-line code, no predicates.
+        // ncu on the predicated loop alone (profiles/r02e_ncu_f32_summary.md): issue slots 70 % busy, SM throughput 84 %
+        // -- without the offset trip this kernel is close to instruction-issue bound, so instructions count.
+        int c[BATCH];
+        double v[BATCH], xv[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) c[u] = ldg_stream_s32(JA + off + (long long)u * kHack);
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) v[u] = ldg_stream_f64(AS + off + (long long)u * kHack);
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) xv[u] = ldg_x(x, c[u]);
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+    } else
     for (int j = 0; j < width; j += BATCH) {
         int c[BATCH];
         double v[BATCH], xv[BATCH];
@@ -563,7 +578,10 @@ static void hll_find_segments(spmv_b200_hll *H) {
         ++seg.count;
     }
     if (!regular) seg = HllSegments();
-    else seg.begin[seg.count] = H->num_hacks;
+    else {
+        seg.begin[seg.count] = H->num_hacks;
+        for (int s = seg.count + 1; s <= kMaxHllSegments; ++s) seg.begin[s] = 0x7fffffff;  // never reached: the kernel tests no count
+    }
     H->segments = seg;
 }
 

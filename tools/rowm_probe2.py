@@ -31,7 +31,8 @@ def setting(**kw):
         os.environ["SPMV_B200_" + k] = str(v)
 
 
-for name, kind, p in (("lap2d_4096", synth.SYNTH_LAP2D, 4096), ("lap3d_256", synth.SYNTH_LAP3D, 256)):
+SHAPES = (("lap2d_4096", synth.SYNTH_LAP2D, 4096), ("lap3d_256", synth.SYNTH_LAP3D, 256))
+for name, kind, p in [s for s in SHAPES if not sys.argv[1:] or s[0] in sys.argv[1:]]:
     A = device.DeviceCSR.synth(kind, p).enable_f32()
     H = A.to_hll().enable_f32()
     i = A.info()
