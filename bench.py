@@ -509,7 +509,8 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler, head):
         run(f"{name}_hll_stream_kernel", lambda: H.spmv(x, y, slice_kernel=False), ia.nnz, hi.algorithmic_bytes)
         run(f"{name}_hll_slice_kernel", lambda: H.spmv(x, y, slice_kernel=True), ia.nnz, hi.algorithmic_bytes)
         if hi.max_maxnz <= 64:
-            run(f"{name}_hll_row_kernel", lambda: H.spmv(x, y, slice_kernel="rows"), ia.nnz, hi.algorithmic_bytes, {"row_batch": hi.row_batch})
+            run(f"{name}_hll_row_kernel", lambda: H.spmv(x, y, slice_kernel="rows"), ia.nnz, hi.algorithmic_bytes,
+                {"row_batch": hi.row_batch, "kernel": H.row_form()})
         if f"{name}_hll" in out and "error" not in out[f"{name}_hll"]:
             out[f"{name}_hll"]["kernel"] = "automatic choice: " + device.HLL_KERNEL_NAMES[hi.auto_kernel]
         H.close()

@@ -323,6 +323,8 @@ int spmv_b200_hll_spmv_host_f32(spmv_b200_hll *H, const float *x, float *y);
  * what the parity tests use it for. */
 int spmv_b200_csr_row_form_f32(const spmv_b200_csr *A);
 int spmv_b200_hll_row_form_f32(const spmv_b200_hll *H);
+/* the same for the fp64 lane-per-row kernel of an HLL image: 1..8 = hll_row_kernel with that batch, 64 + b = hll_rowu_kernel */
+int spmv_b200_hll_row_form(const spmv_b200_hll *H);
 /* number of multi-row forms of a format (SPMV_B200_FORMAT_CSR / _HLL), and what form `index` is */
 int spmv_b200_row_forms(int format);
 int spmv_b200_row_form_describe(int format, int index, int *rows_per_thread, int *batch, int *ctas_per_sm);

@@ -157,6 +157,7 @@ SIGNATURES = {
     "spmv_b200_hll_spmv_host_f32": (_I, [_V, _V, _V]),
     "spmv_b200_csr_row_form_f32": (_I, [_V]),
     "spmv_b200_hll_row_form_f32": (_I, [_V]),
+    "spmv_b200_hll_row_form": (_I, [_V]),
     "spmv_b200_row_forms": (_I, [_I]),
     "spmv_b200_row_form_describe": (_I, [_I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "spmv_b200_resident_cache": (_I, [_I]),

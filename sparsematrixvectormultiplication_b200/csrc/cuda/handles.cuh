@@ -267,6 +267,7 @@ struct spmv_b200_hll {
     spmv::HllTile *tiles = nullptr;
     int stream_grid = 0;
     int row_batch = 4;   // hll_row_kernel batch (tuned at plan time on large matrices)
+    int row_form = 0;    // fp64 row path: 0 = hll_row_kernel<row_batch>; 64 + b = hll_rowu_kernel<b> (regular images, timed at plan time)
     int row_batch32 = 4; // the same for fp32 storage (tuned by spmv_b200_hll_enable_f32)
     int fused_batch = 0; // hll_row_fused_kernel batch (tuned at plan time; 0 = row_batch)
     int flat_batch = 4, flat_chunks = 2;  // the FLAT form of hll_row_fused_kernel (two-launch iterated product)

@@ -425,7 +425,7 @@ template <typename V>
 static int hll_launch_rows_t(const spmv_b200_hll *H, const V *AS, int hack_begin, int hack_end, const V *d_x, V *d_y,
                              cudaStream_t stream, int batch = -1) {
     if (hack_end <= hack_begin) return SPMV_B200_OK;
-    if (batch < 0) batch = sizeof(V) == 4 ? H->row_batch32 : H->row_batch;
+    if (batch < 0) batch = sizeof(V) == 4 ? H->row_batch32 : (H->row_form > 0 ? H->row_form : H->row_batch);
     const XPolicy keep = matrix_policy(H->JA, (size_t)H->slots * sizeof(int));   // head of JA held in L2 across products
     // batch >= 16: hll_rowm_kernel, form kHllRowmVariants[batch - 16].  SPMV_B200_ROW_MULTI=k (k >= 1) sends EVERY
     // row-kernel launch through form k - 1 (parity runs: tests/test_gpu_parity.py walks all forms, fp64 bit for bit)
@@ -589,6 +589,7 @@ static void hll_pick_row_batch(spmv_b200_hll *H, cudaStream_t stream) {
     hll_find_segments(H);
     const int forced = env_int("SPMV_B200_HLL_ROW_BATCH", 0);
     H->narrow_stream = false;
+    H->row_form = 0;
     const long long mean = H->num_hacks > 0 ? (H->slots / 32 + H->num_hacks - 1) / H->num_hacks : 4;
     H->row_batch = (int)std::max<long long>(2, std::min<long long>(7, mean));
     if (forced >= 1 && forced <= 8) {
@@ -604,6 +605,20 @@ static void hll_pick_row_batch(spmv_b200_hll *H, cudaStream_t stream) {
         }, 0);
         if (best == 0) H->narrow_stream = true;
         else H->row_batch = best;
+        // regular images: hll_rowu_kernel (no hack_off round trip; ids 64 + batch) against the winner so far -- same bits.
+        // lap2d 4096^2, fp64: 182.1 us against 201.3 us (profiles/r02e_rowm_probe_fourth_pass.log)
+        if (H->segments.count > 0 && env_int("SPMV_B200_HLL_UNIFORM_TUNE", 1)) {
+            const int ids[5] = {-1, 64 + 4, 64 + 5, 64 + 6, 64 + 7};  // -1: the winner so far
+            const int pick = tune_candidates(H->M, H->N, 5, 0, stream, [&](int i, double *x, double *y) {
+                if (ids[i] < 0)
+                    return H->narrow_stream ? stream_launch_hll(H, x, y, stream) : hll_launch_rows(H, 0, H->num_hacks, x, y, stream);
+                return hll_launch_rows_t<double>(H, H->AS, 0, H->num_hacks, x, y, stream, ids[i]);
+            });
+            if (pick > 0) {
+                H->row_form = ids[pick];
+                H->narrow_stream = false;
+            }
+        }
         // the fused iterated product (scale + |w|^2 partials in the tail) has its own best batch
         double *partials = nullptr;
         const int count = hll_fused_grid(H);
@@ -1010,6 +1025,7 @@ int spmv_b200_hll_spmv_f32(const spmv_b200_hll *H, const float *d_x, float *d_y,
 }
 
 int spmv_b200_hll_row_form_f32(const spmv_b200_hll *H) { return H && H->AS32 ? H->row_batch32 : 0; }
+int spmv_b200_hll_row_form(const spmv_b200_hll *H) { return !H ? 0 : (H->row_form > 0 ? H->row_form : H->row_batch); }
 
 int spmv_b200_hll_spmv_host_f32(spmv_b200_hll *H, const float *x, float *y) {
     if (!H || (H->M > 0 && !y) || (H->N > 0 && H->slots > 0 && !x)) return fail(SPMV_B200_ERR_INVALID, "hll_spmv_host_f32: NULL argument");

@@ -54,14 +54,14 @@ def row_forms(fmt: int):
     return out
 
 
-def row_form_name(fmt: int, form: int) -> str:
+def row_form_name(fmt: int, form: int, storage: str = "float") -> str:
     base = "csr_row" if fmt == FORMAT_CSR else "hll_row"
     if form >= 64:  # HLL only: offsets by arithmetic on a regular image
-        return f"hll_rowu_kernel<{form - 64},float>"
+        return f"hll_rowu_kernel<{form - 64},{storage}>"
     if form >= 16:
         r, b, c = row_forms(fmt)[form - 16]
-        return f"{base}m_kernel<{b},{r},{c},float>"
-    return f"{base}_kernel<{form},float>" if form > 0 else "none"
+        return f"{base}m_kernel<{b},{r},{c},{storage}>"
+    return f"{base}_kernel<{form},{storage}>" if form > 0 else "none"
 
 
 def device_count() -> int:
@@ -337,6 +337,10 @@ class DeviceHLL:
 
     def row_form_f32(self) -> str:
         return row_form_name(FORMAT_HLL, N.lib().spmv_b200_hll_row_form_f32(self._h))
+
+    def row_form(self) -> str:
+        """Name of the fp64 lane-per-row kernel the plan-time timing chose (spmv_b200_hll_row_form)."""
+        return row_form_name(FORMAT_HLL, N.lib().spmv_b200_hll_row_form(self._h), "double")
 
     def spmv_f32(self, x, y, stream=None):
         N.check(N.lib().spmv_b200_hll_spmv_f32(self._h, _ptr(x), _ptr(y), _stream(stream)))
