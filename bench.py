@@ -513,6 +513,8 @@ def measure_others(args, A2d, x2d, y2d, peak, sampler, head):
                 {"row_batch": hi.row_batch, "kernel": H.row_form()})
         if f"{name}_hll" in out and "error" not in out[f"{name}_hll"]:
             out[f"{name}_hll"]["kernel"] = "automatic choice: " + device.HLL_KERNEL_NAMES[hi.auto_kernel]
+            if hi.auto_kernel == 2:  # the lane-per-row path: which of its kernels the plan-time timing chose
+                out[f"{name}_hll"]["kernel_symbol"] = H.row_form()
         H.close()
 
     try:
